@@ -1,0 +1,204 @@
+/*
+ * moog_b200_program.h -- binary layout of a compiled MOOG task ("program") and
+ * of the per-env state record the kernels operate on.
+ *
+ * A *program* is what the host-side config compiler produces from the dict a
+ * MOOG config's get_config(level) returns (reference:
+ * moog/environment.py:28-35 -- state_initializer, physics, task, action_space,
+ * observers, game_rules).  It is a flat, position-independent blob:
+ *
+ *     int32   hdr[MOOG_HDR_WORDS]
+ *     moog_op ops[hdr[MOOG_H_N_OPS]]
+ *     int32   ipool[hdr[MOOG_H_N_IPOOL]]      (padded to a multiple of 2)
+ *     moog_ex expr[hdr[MOOG_H_N_EXPR]]
+ *
+ * Sections of `ops` (forces, correctives, rules, tasks, actions, conditions)
+ * are addressed by (start, count) pairs in the header.  Layer lists live in
+ * `ipool`; small per-sprite predicates / assignments (the lambdas MOOG configs
+ * pass as filters, conditions and modifiers) are postfix programs in `expr`.
+ *
+ * State of env n (all arrays owned by the caller; N envs, S sprite slots,
+ * L layers; slots of layer l are [layer_off[l], layer_off[l+1]) and the live
+ * sprites of a layer are its first cnt[n][l] slots, in MOOG list order, which
+ * is also z-order -- reference moog/environment.py:20-25):
+ *
+ *     double  dyn [N][MOOG_DYN_FIELDS ][S]   x y vx vy angle angle_vel
+ *     double  stat[N][MOOG_STAT_FIELDS][S]   mass scale aspect ix iy max_radius c0 c1 c2 opacity
+ *     int32   meta[N][MOOG_META_FIELDS][S]   shape_id flags n_vertices
+ *     double  vtx [N][VT][2]                 cached WORLD vertices; slot s owns
+ *                                            vertices [voff[s], voff[s]+nv)
+ *     int32   cnt [N][MOOG_MAX_LAYERS]
+ *     int32   envi[N][MOOG_ENVI_WORDS]       step_count reset_next err episodes rng...
+ *     double  envf[N][hdr[MOOG_H_N_ENVF]]    action-space memory, task countdowns
+ *
+ * `vtx` mirrors the reference's Sprite._path cache (moog/sprite.py:411-424):
+ * the reference never recomputes world vertices from (position, angle, scale)
+ * during an episode, it translates / rotates the cached path incrementally
+ * (sprite.py:531-540, 616-633).  The roundings of that cache decide exact
+ * ties -- two identical circles colliding head-on pick the contact side by the
+ * last bit -- so the cache is state, not a derived quantity.
+ *
+ * The per-env record is contiguous and field-major so that a warp that owns
+ * one env reads it with unit-stride, fully coalesced loads (lane == slot).
+ */
+#ifndef MOOG_B200_PROGRAM_H_
+#define MOOG_B200_PROGRAM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOOG_MAGIC 0x474F4F4D /* "MOOG" little endian */
+#define MOOG_VERSION 1
+
+#define MOOG_MAX_LAYERS 16
+#define MOOG_MAX_VERTS 32   /* per sprite; 'circle' is a 30-gon (moog/shapes.py:17) */
+#define MOOG_MAX_SLOTS 256
+
+#define MOOG_DYN_FIELDS 6
+enum { MOOG_D_X = 0, MOOG_D_Y, MOOG_D_VX, MOOG_D_VY, MOOG_D_ANG, MOOG_D_ANGVEL };
+
+#define MOOG_STAT_FIELDS 10
+enum {
+  MOOG_S_MASS = 0, MOOG_S_SCALE, MOOG_S_ASPECT, MOOG_S_IX, MOOG_S_IY,
+  MOOG_S_MAXR, MOOG_S_C0, MOOG_S_C1, MOOG_S_C2, MOOG_S_OPACITY
+};
+
+#define MOOG_META_FIELDS 3
+enum { MOOG_M_SHAPE = 0, MOOG_M_FLAGS, MOOG_M_NV };
+#define MOOG_SF_CIRCLE 1 /* shape name == 'circle' (moog/sprite.py:500-502) */
+/* NumPy dtype of the reference's per-sprite fields: a sampled
+ * velocity is a float32 ndarray, a sampled angle_vel a float32 0-d array, and
+ * the angle turns float32 with it.  kind: 0 python float, 1 float32, 2 float64. */
+#define MOOG_SF_VEL32 2
+#define MOOG_SF_ANGVEL_SHIFT 2 /* 2 bits */
+#define MOOG_SF_ANG_SHIFT 4    /* 2 bits */
+
+#define MOOG_ENVI_WORDS 8
+enum {
+  MOOG_EI_STEP_COUNT = 0, MOOG_EI_RESET_NEXT, MOOG_EI_ERR, MOOG_EI_EPISODES,
+  MOOG_EI_RNG0, MOOG_EI_RNG1, MOOG_EI_LAST_RESET, MOOG_EI_SPARE
+};
+
+/* error bits (data-dependent reference exceptions, raised lazily by the host) */
+#define MOOG_ERR_NORMAL_NOT_UNIT 1u  /* collisions.py:323-326 ValueError        */
+#define MOOG_ERR_DISJOINT_LOOP   2u  /* collisions.py:740 loop would not end     */
+#define MOOG_ERR_TETHER_ZIP      4u  /* tether_physics.py:192-196 ValueError     */
+#define MOOG_ERR_LAYER_OVERFLOW  8u  /* layer capacity exceeded                  */
+
+/* header words */
+#define MOOG_HDR_WORDS 64
+enum {
+  MOOG_H_MAGIC = 0, MOOG_H_VERSION, MOOG_H_BYTES, MOOG_H_N_LAYERS, MOOG_H_N_SLOTS,
+  MOOG_H_K, MOOG_H_N_OPS, MOOG_H_N_IPOOL, MOOG_H_N_EXPR, MOOG_H_N_ENVF,
+  MOOG_H_FORCES, MOOG_H_N_FORCES, MOOG_H_CORR, MOOG_H_N_CORR,
+  MOOG_H_RULES, MOOG_H_N_RULES, MOOG_H_TASKS, MOOG_H_N_TASKS,
+  MOOG_H_ACTIONS, MOOG_H_N_ACTIONS, MOOG_H_ACTION_DIM, MOOG_H_NOISE_DIM,
+  MOOG_H_R_HEIGHT, MOOG_H_R_WIDTH, MOOG_H_R_AA, MOOG_H_R_BG, /* bg = r | g<<8 | b<<16 */
+  MOOG_H_R_COLORMAP, MOOG_H_R_MODIFIER, MOOG_H_R_MOD_LAYER, MOOG_H_R_ENABLED,
+  MOOG_H_RULE_NOISE_DIM, /* uniforms per env per step consumed by sample_one rules */
+  MOOG_H_VOFF,           /* index in ipool of voff[S+1]: first cached vertex of each slot */
+  MOOG_H_LAYER_OFF = 32, /* MOOG_MAX_LAYERS+1 words */
+  MOOG_H_N_VTX = 49      /* VT: cached vertices per env */
+};
+
+enum { MOOG_CMAP_NONE = 0, MOOG_CMAP_HSV = 1 };
+enum { MOOG_PMOD_NONE = 0, MOOG_PMOD_FIRST_PERSON = 1, MOOG_PMOD_TORUS = 2 };
+
+typedef struct {
+  int32_t kind;
+  int32_t flags;
+  int32_t i[6];
+  double p[6];
+} moog_op; /* 80 bytes */
+
+/* op kinds ---------------------------------------------------------------- */
+enum {
+  /* forces: i[0]=layer a, i[1]=layer b (-1 if unary) */
+  MOOG_F_DRAG = 1,          /* p0 coeff            friction.py:54-56          */
+  MOOG_F_KINETIC_FRICTION,  /* p0 coeff            friction.py:25-33          */
+  MOOG_F_DOWN_GRAVITY,      /* p0 g                gravity.py:21-23           */
+  MOOG_F_GRAVITY,           /* p0 g, SYMMETRIC     gravity.py:44-60           */
+  MOOG_F_RANDOM,            /* p0 max magnitude; i[2] noise column  random_force.py:22-26 */
+  MOOG_F_DIST_LINEAR,       /* p0 intercept p1 slope p2 horizon  distance_fn_force.py:48-74 */
+  MOOG_F_DIST_SPRING,       /* p0 k p1 equilibrium distance_fn_force.py:77-89 */
+  MOOG_F_COLLISION,         /* p0 elasticity; i[2] max_recursion  collisions.py:494-584 */
+
+  /* corrective physics: i[0]=ipool start of layer list, i[1]=count */
+  MOOG_C_TETHER = 32,       /* p0,p1 anchor        tether_physics.py:126-140  */
+  MOOG_C_TETHER_ZIPPED,     /*                     tether_physics.py:186-201  */
+  MOOG_C_CONSTANT_SPEED,    /* p0 speed            constant_speed.py:34-46    */
+
+  /* rules */
+  MOOG_R_VANISH_ON_CONTACT = 64, /* i0 vanishing layer, i1 contacting layer  vanish.py:66-86 */
+  MOOG_R_VANISH_BY_FILTER,       /* i0 layer, i2 filter expr (-1: all)       vanish.py:42-63 */
+  MOOG_R_MODIFY_ON_CONTACT,      /* i0,i1 list0; i2,i3 list1; i4 -> ipool[4]: mod0 filt0 mod1 filt1  contact_rules.py:54-120 */
+  MOOG_R_MODIFY_SPRITES,         /* i0,i1 list; i2 modifier, i3 filter; SAMPLE_ONE; i4 noise column  modify_sprites.py:35-52 */
+  MOOG_R_COND_BEGIN,             /* i0 condition op index, i1 number of following rule ops guarded   conditional.py:55-58 */
+
+  /* tasks: i[5] = envf slot of the countdown */
+  MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps  contact_reward.py:70-102 */
+  MOOG_T_RESET,               /* i0 condition op index; p0 steps_after p1 reward   reset.py:48-61  */
+  MOOG_T_STAY_ALIVE,          /* p0 period p1 value                          stay_alive.py:22-32   */
+  MOOG_T_TIMEOUT,             /* p0 timeout_steps                            composite_task.py:35  */
+
+  /* action spaces: i0,i1 layer list; i2 offset in action vector; i5 envf slot */
+  MOOG_A_JOYSTICK = 128,   /* p0 scaling p1 momentum      joystick.py:45-65    */
+  MOOG_A_GRID,             /* p0 scaling p1 momentum      grid.py:52-70        */
+  MOOG_A_SET_POSITION,     /* p0 inertia                  set_position.py:34-47 */
+
+  /* state conditions (value = double; used by MOOG_T_RESET / MOOG_R_COND_BEGIN) */
+  MOOG_SC_ALL = 160,       /* i0,i1 layer list; i2 sprite expr: all(expr(s))   */
+  MOOG_SC_ANY,             /* any(expr(s))                                     */
+  MOOG_SC_COUNT,           /* sum(bool(expr(s)))                               */
+  MOOG_SC_CONTACT_COUNT,   /* i0 layer0 i1 layer1: len(get_contact_indices)    contact_rules.py:38-51 */
+  MOOG_SC_CONTACT_ANY_COUNT, /* i0,i1 list of sprites' layers; i2,i3 other list; i4 filter expr:
+                                count of list-0 sprites passing the filter that overlap any list-1 sprite */
+  MOOG_SC_CONST            /* p0                                                */
+};
+
+/* op flags */
+#define MOOG_FL_SYMMETRIC        1
+#define MOOG_FL_UPDATE_ANGLE_VEL 2
+#define MOOG_FL_APPLY_DISTANT    4
+#define MOOG_FL_APPLY_NEARBY     8
+#define MOOG_FL_HAS_ANCHOR       16
+#define MOOG_FL_CONSTRAINED_LR   32
+#define MOOG_FL_CONTROL_VELOCITY 64
+#define MOOG_FL_SAMPLE_ONE       128
+
+/* expression VM ------------------------------------------------------------ */
+typedef struct {
+  int32_t op;
+  int32_t arg;
+  double c;
+} moog_ex; /* 16 bytes */
+
+enum {
+  MOOG_X_END = 0,
+  MOOG_X_CONST,      /* push c                                              */
+  MOOG_X_ATTR0,      /* push attribute `arg` of sprite 0 (see MOOG_AT_*)     */
+  MOOG_X_ATTR1,      /* push attribute `arg` of sprite 1                     */
+  MOOG_X_LT, MOOG_X_LE, MOOG_X_GT, MOOG_X_GE, MOOG_X_EQ, MOOG_X_NE,
+  MOOG_X_AND, MOOG_X_OR, MOOG_X_NOT,
+  MOOG_X_ADD, MOOG_X_SUB, MOOG_X_MUL, MOOG_X_DIV, MOOG_X_NEG, MOOG_X_ABS,
+  MOOG_X_MOD,        /* python float modulo                                  */
+  MOOG_X_STORE       /* pop -> attribute `arg` of sprite 0 (modifier programs) */
+};
+
+/* attribute ids for the expression VM (Sprite.FACTOR_NAMES, sprite.py:237-253) */
+enum {
+  MOOG_AT_X = 0, MOOG_AT_Y, MOOG_AT_X_VEL, MOOG_AT_Y_VEL, MOOG_AT_ANGLE,
+  MOOG_AT_ANGLE_VEL, MOOG_AT_MASS, MOOG_AT_SCALE, MOOG_AT_ASPECT_RATIO,
+  MOOG_AT_C0, MOOG_AT_C1, MOOG_AT_C2, MOOG_AT_OPACITY
+};
+
+/* step_type values written by the kernels (dm_env.StepType) */
+enum { MOOG_STEP_FIRST = 0, MOOG_STEP_MID = 1, MOOG_STEP_LAST = 2 };
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOOG_B200_PROGRAM_H_ */

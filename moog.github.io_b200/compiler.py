@@ -1,0 +1,732 @@
+"""Config compiler: MOOG component objects -> device program + state records.
+
+Input is the dict a MOOG config's `get_config(level)` returns (reference:
+moog/environment.py:28-35).  The component objects are read by duck typing on
+class name and the reference's private attribute names (`Physics._forces`,
+`Collision._elasticity`, `ContactReward._layers_0`, ...), so the same compiler
+accepts this repo's `moog` spec classes (production) and the reference's own
+instances (parity runs on the very same config object).
+
+Output:
+  * `Program` -- the binary blob described in include/moog_b200_program.h plus
+    host-side metadata (layer names, capacities, action / noise layout);
+  * `pack_states` -- list of `OrderedDict[str, list[Sprite]]` -> the SoA numpy
+    arrays of the per-env state record.
+
+Nothing here touches the GPU or the oracle.
+"""
+
+import collections
+import itertools
+import struct
+
+import numpy as np
+
+from . import lambdas
+
+# ---- constants mirrored from include/moog_b200_program.h -------------------
+MAGIC = 0x474F4F4D
+VERSION = 1
+MAX_LAYERS = 16
+MAX_VERTS = 32
+MAX_SLOTS = 256
+DYN_FIELDS = 6
+STAT_FIELDS = 10
+META_FIELDS = 3
+ENVI_WORDS = 8
+HDR_WORDS = 64
+SF_CIRCLE = 1
+SF_VEL32 = 2
+SF_ANGVEL_SHIFT = 2
+SF_ANG_SHIFT = 4
+
+(H_MAGIC, H_VERSION, H_BYTES, H_N_LAYERS, H_N_SLOTS, H_K, H_N_OPS, H_N_IPOOL,
+ H_N_EXPR, H_N_ENVF, H_FORCES, H_N_FORCES, H_CORR, H_N_CORR, H_RULES,
+ H_N_RULES, H_TASKS, H_N_TASKS, H_ACTIONS, H_N_ACTIONS, H_ACTION_DIM,
+ H_NOISE_DIM, H_R_HEIGHT, H_R_WIDTH, H_R_AA, H_R_BG, H_R_COLORMAP,
+ H_R_MODIFIER, H_R_MOD_LAYER, H_R_ENABLED) = range(30)
+H_RULE_NOISE_DIM = 30
+H_VOFF = 31
+H_LAYER_OFF = 32
+H_N_VTX = 49
+
+F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
+    F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION = range(1, 9)
+C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED = 32, 33, 34
+R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
+    R_MODIFY_SPRITES, R_COND_BEGIN = 64, 65, 66, 67, 68
+T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
+A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
+SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST = \
+    160, 161, 162, 163, 164, 165
+
+FL_SYMMETRIC = 1
+FL_UPDATE_ANGLE_VEL = 2
+FL_APPLY_DISTANT = 4
+FL_APPLY_NEARBY = 8
+FL_HAS_ANCHOR = 16
+FL_CONSTRAINED_LR = 32
+FL_CONTROL_VELOCITY = 64
+FL_SAMPLE_ONE = 128
+
+CMAP_NONE, CMAP_HSV = 0, 1
+PMOD_NONE, PMOD_FIRST_PERSON, PMOD_TORUS = 0, 1, 2
+
+OP_DTYPE = np.dtype([('kind', '<i4'), ('flags', '<i4'), ('i', '<i4', (6,)),
+                     ('p', '<f8', (6,))])
+EX_DTYPE = np.dtype([('op', '<i4'), ('arg', '<i4'), ('c', '<f8')])
+assert OP_DTYPE.itemsize == 80 and EX_DTYPE.itemsize == 16
+
+
+class CompileError(ValueError):
+    """The config uses something the accelerated path cannot express."""
+
+
+def _kind(obj):
+    return type(obj).__name__
+
+
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+class Program(object):
+    """Compiled task: `blob` (bytes) + the metadata the host needs."""
+
+    def __init__(self):
+        self.layer_names = []
+        self.layer_cap = []
+        self.layer_off = [0]
+        self.ops = []            # list of dict(kind, flags, i, p)
+        self.ipool = []
+        self.expr = []           # list of (op, arg, c)
+        self.sections = {}
+        self.n_envf = 0
+        self.action_dim = 0
+        self.action_layout = []  # (key or None, kind, offset, width)
+        self.noise_dim = 0
+        self.rule_noise_dim = 0
+        self.K = 1
+        self.layer_vcap = []     # cached-vertex capacity per sprite, per layer
+        self.voff = [0]          # first cached vertex of each slot
+        self.render = None       # dict or None
+        self.blob = b''
+
+    # -- helpers used while building --
+    def layer_index(self, name):
+        try:
+            return self.layer_names.index(name)
+        except ValueError:
+            raise CompileError(
+                'layer {!r} is not in the environment state (layers: {})'
+                .format(name, self.layer_names))
+
+    def add_list(self, names):
+        start = len(self.ipool)
+        self.ipool.extend(self.layer_index(n) for n in names)
+        return start, len(names)
+
+    def add_ints(self, ints):
+        start = len(self.ipool)
+        self.ipool.extend(int(v) for v in ints)
+        return start
+
+    def add_expr(self, code):
+        """code: list of (op, arg, c) WITHOUT the terminator; returns start."""
+        if code is None:
+            return -1
+        start = len(self.expr)
+        self.expr.extend(code)
+        self.expr.append((lambdas.X_END, 0, 0.0))
+        return start
+
+    def alloc_envf(self, n):
+        start = self.n_envf
+        self.n_envf += n
+        return start
+
+    def emit(self, kind, flags=0, i=(), p=()):
+        i = list(i) + [0] * (6 - len(i))
+        p = list(p) + [0.0] * (6 - len(p))
+        self.ops.append(dict(kind=kind, flags=flags, i=i, p=p))
+        return len(self.ops) - 1
+
+    @property
+    def n_slots(self):
+        return self.layer_off[-1]
+
+    @property
+    def n_layers(self):
+        return len(self.layer_names)
+
+    @property
+    def n_vtx(self):
+        return self.voff[-1]
+
+    def finalize(self):
+        hdr = np.zeros(HDR_WORDS, dtype='<i4')
+        hdr[H_VOFF] = self.add_ints(self.voff)
+        hdr[H_N_VTX] = self.voff[-1]
+        ops = np.zeros(len(self.ops), dtype=OP_DTYPE)
+        for k, o in enumerate(self.ops):
+            ops[k]['kind'] = o['kind']
+            ops[k]['flags'] = o['flags']
+            ops[k]['i'] = o['i']
+            ops[k]['p'] = o['p']
+        ipool = list(self.ipool)
+        if len(ipool) % 2:
+            ipool.append(0)
+        ipool = np.array(ipool, dtype='<i4')
+        expr = np.zeros(len(self.expr), dtype=EX_DTYPE)
+        for k, (op, arg, c) in enumerate(self.expr):
+            expr[k] = (op, arg, c)
+        hdr[H_MAGIC] = MAGIC
+        hdr[H_VERSION] = VERSION
+        hdr[H_N_LAYERS] = self.n_layers
+        hdr[H_N_SLOTS] = self.n_slots
+        hdr[H_K] = self.K
+        hdr[H_N_OPS] = len(ops)
+        hdr[H_N_IPOOL] = len(self.ipool)
+        hdr[H_N_EXPR] = len(expr)
+        hdr[H_N_ENVF] = max(self.n_envf, 1)
+        for name, (hs, hn) in (('forces', (H_FORCES, H_N_FORCES)),
+                               ('corr', (H_CORR, H_N_CORR)),
+                               ('rules', (H_RULES, H_N_RULES)),
+                               ('tasks', (H_TASKS, H_N_TASKS)),
+                               ('actions', (H_ACTIONS, H_N_ACTIONS))):
+            start, count = self.sections.get(name, (0, 0))
+            hdr[hs] = start
+            hdr[hn] = count
+        hdr[H_ACTION_DIM] = max(self.action_dim, 1)
+        hdr[H_NOISE_DIM] = self.noise_dim
+        hdr[H_RULE_NOISE_DIM] = self.rule_noise_dim
+        if self.render is not None:
+            r = self.render
+            hdr[H_R_ENABLED] = 1
+            hdr[H_R_HEIGHT] = r['height']
+            hdr[H_R_WIDTH] = r['width']
+            hdr[H_R_AA] = r['aa']
+            bg = r['bg']
+            hdr[H_R_BG] = int(bg[0]) | (int(bg[1]) << 8) | (int(bg[2]) << 16)
+            hdr[H_R_COLORMAP] = r['colormap']
+            hdr[H_R_MODIFIER] = r['modifier']
+            hdr[H_R_MOD_LAYER] = r['modifier_layer']
+        hdr[H_LAYER_OFF:H_LAYER_OFF + len(self.layer_off)] = self.layer_off
+        blob = hdr.tobytes() + ops.tobytes() + ipool.tobytes() + expr.tobytes()
+        hdr[H_BYTES] = len(blob)
+        self.blob = hdr.tobytes() + blob[HDR_WORDS * 4:]
+        self.header = hdr
+        return self
+
+
+# ---------------------------------------------------------------------------
+# physics
+# ---------------------------------------------------------------------------
+
+def _force_fn_params(fn):
+    """Parameters of a DistanceForce force_fn: this repo's callable objects,
+    or the reference's closures (distance_fn_force.py:48-89)."""
+    kind = getattr(fn, 'kind', None)
+    if kind == 'linear':
+        return 'linear', (fn.zero_intercept, fn.slope, fn.event_horizon,
+                          fn.apply_distant_force, fn.apply_nearby_force)
+    if kind == 'spring':
+        return 'spring', (fn.spring_constant, fn.equilibrium)
+    cells = lambdas.closure_vars(fn)
+    if {'zero_intercept', 'slope', 'event_horizon'} <= set(cells):
+        return 'linear', (cells['zero_intercept'], cells['slope'],
+                          cells['event_horizon'],
+                          cells['apply_distant_force'],
+                          cells['apply_nearby_force'])
+    if {'spring_constant', 'equilibrium'} <= set(cells):
+        return 'spring', (cells['spring_constant'], cells['equilibrium'])
+    raise CompileError(
+        'DistanceForce force_fn {!r} is not linear_force_fn / spring_force_fn; '
+        'arbitrary Python force functions cannot run on the device'.format(fn))
+
+
+def _emit_force(prog, force, layers):
+    k = _kind(force)
+    la = prog.layer_index(layers[0])
+    lb = prog.layer_index(layers[1]) if len(layers) > 1 else -1
+    arity = {'Drag': 1, 'KineticFriction': 1, 'DownGravity': 1,
+             'RandomForce': 1, 'Gravity': 2, 'DistanceForce': 2,
+             'Collision': 2}.get(k)
+    if arity is None:
+        raise CompileError('unsupported force {}'.format(k))
+    if arity != len(layers):
+        raise CompileError('{} takes {} layer argument(s), got {}'.format(
+            k, arity, len(layers)))
+    if k == 'Drag':
+        prog.emit(F_DRAG, 0, (la, -1), (force._coeff_friction,))
+    elif k == 'KineticFriction':
+        prog.emit(F_KINETIC_FRICTION, 0, (la, -1), (force._coeff_friction,))
+    elif k == 'DownGravity':
+        prog.emit(F_DOWN_GRAVITY, 0, (la, -1), (force._g,))
+    elif k == 'RandomForce':
+        col = prog.noise_dim
+        prog.noise_dim += 2 * prog.layer_cap[la]
+        prog.emit(F_RANDOM, 0, (la, -1, col), (force._max_force_magnitude,))
+    elif k == 'Gravity':
+        prog.emit(F_GRAVITY, FL_SYMMETRIC if force._symmetric else 0,
+                  (la, lb), (force._g,))
+    elif k == 'DistanceForce':
+        fl = FL_SYMMETRIC if force._symmetric else 0
+        kind, params = _force_fn_params(force._force_fn)
+        if kind == 'linear':
+            zi, slope, horizon, far, near = params
+            fl |= (FL_APPLY_DISTANT if far else 0) | (
+                FL_APPLY_NEARBY if near else 0)
+            prog.emit(F_DIST_LINEAR, fl, (la, lb), (zi, slope, horizon))
+        else:
+            prog.emit(F_DIST_SPRING, fl, (la, lb), params)
+    elif k == 'Collision':
+        fl = (FL_SYMMETRIC if force._symmetric else 0) | (
+            FL_UPDATE_ANGLE_VEL if force._update_angle_vel else 0)
+        prog.emit(F_COLLISION, fl, (la, lb, int(force._max_recursion_depth)),
+                  (force._elasticity,))
+
+
+def _compile_physics(prog, physics):
+    k = _kind(physics)
+    if k != 'Physics':
+        raise CompileError(
+            'physics must be a Physics instance, got {}'.format(k))
+    prog.K = int(physics._updates_per_env_step)
+    start = len(prog.ops)
+    for entry in physics._forces:
+        force, args = entry[0], entry[1:]
+        # physics.py:92-108: product over the layer-name lists, in order.
+        for combo in itertools.product(*[_as_list(a) for a in args]):
+            _emit_force(prog, force, combo)
+    prog.sections['forces'] = (start, len(prog.ops) - start)
+
+    start = len(prog.ops)
+    for cp in physics._corrective_physics:
+        ck = _kind(cp)
+        if ck in ('Tether', 'TetherZippedLayers'):
+            ls, ln = prog.add_list(cp._layer_names)
+            fl = FL_UPDATE_ANGLE_VEL if cp._update_angle_vel else 0
+            ax = ay = 0.0
+            if cp._anchor is not None:
+                fl |= FL_HAS_ANCHOR
+                ax, ay = float(cp._anchor[0]), float(cp._anchor[1])
+            prog.emit(C_TETHER if ck == 'Tether' else C_TETHER_ZIPPED, fl,
+                      (ls, ln), (ax, ay))
+        elif ck == 'ConstantSpeed':
+            ls, ln = prog.add_list(cp._layer_names)
+            prog.emit(C_CONSTANT_SPEED, 0, (ls, ln), (cp._speed,))
+        else:
+            raise CompileError(
+                'corrective physics {} is not on the accelerated path'
+                .format(ck))
+    prog.sections['corr'] = (start, len(prog.ops) - start)
+
+
+# ---------------------------------------------------------------------------
+# tasks
+# ---------------------------------------------------------------------------
+
+def _emit_condition(prog, cond):
+    """State condition -> index of a MOOG_SC_* op (appended out of section)."""
+    spec = lambdas.compile_state_condition(cond, prog)
+    return spec
+
+
+def _compile_task(prog, task, out):
+    k = _kind(task)
+    if k == 'CompositeTask':
+        timeout = task._timeout_steps
+        if np.isfinite(timeout):
+            out.append(dict(kind=T_TIMEOUT, p=(float(timeout),)))
+        for sub in task._tasks:
+            _compile_task(prog, sub, out)
+    elif k == 'StayAlive':
+        out.append(dict(kind=T_STAY_ALIVE,
+                        p=(float(task._reward_period),
+                           float(task._reward_value))))
+    elif k == 'ContactReward':
+        reward = lambdas.constant_reward(task._reward_fn)
+        cond = lambdas.compile_pair_condition(task._condition)
+        l0s, l0n = prog.add_list(_as_list(task._layers_0))
+        l1s, l1n = prog.add_list(_as_list(task._layers_1))
+        out.append(dict(
+            kind=T_CONTACT_REWARD,
+            i=(l0s, l0n, l1s, l1n, prog.add_expr(cond), prog.alloc_envf(1)),
+            p=(float(reward), float(task._reset_steps_after_contact))))
+    elif k == 'Reset':
+        reward = lambdas.constant_state_reward(task._reward_fn)
+        out.append(dict(
+            kind=T_RESET, cond=task._condition,
+            i=[0, 0, 0, 0, 0, prog.alloc_envf(1)],
+            p=(float(task._steps_after_condition), float(reward))))
+    else:
+        raise CompileError('unsupported task {}'.format(k))
+
+
+def _compile_tasks(prog, task):
+    specs = []
+    _compile_task(prog, task, specs)
+    # Conditions are emitted first (outside any section) so that the task ops
+    # themselves stay contiguous.
+    for s in specs:
+        if 'cond' in s:
+            s['i'][0] = _emit_condition(prog, s.pop('cond'))
+    start = len(prog.ops)
+    for s in specs:
+        prog.emit(s['kind'], 0, s.get('i', ()), s.get('p', ()))
+    prog.sections['tasks'] = (start, len(prog.ops) - start)
+
+
+# ---------------------------------------------------------------------------
+# action spaces
+# ---------------------------------------------------------------------------
+
+def _compile_action(prog, space, key, out):
+    k = _kind(space)
+    if k == 'Composite':
+        for sub_key, sub in space.action_spaces.items():
+            _compile_action(prog, sub, sub_key, out)
+        return
+    ls, ln = prog.add_list(_as_list(space._action_layers))
+    off = prog.action_dim
+    if k == 'Joystick':
+        fl = (FL_CONSTRAINED_LR if space._constrained_lr else 0) | (
+            FL_CONTROL_VELOCITY if space._control_velocity else 0)
+        out.append(dict(kind=A_JOYSTICK, flags=fl,
+                        i=(ls, ln, off, 0, 0, prog.alloc_envf(2)),
+                        p=(float(space._scaling_factor),
+                           float(space._momentum))))
+        width = 2
+    elif k == 'Grid':
+        fl = FL_CONTROL_VELOCITY if space._control_velocity else 0
+        out.append(dict(kind=A_GRID, flags=fl,
+                        i=(ls, ln, off, 0, 0, prog.alloc_envf(2)),
+                        p=(float(space._scaling_factor),
+                           float(space._momentum))))
+        width = 1
+    elif k == 'SetPosition':
+        out.append(dict(kind=A_SET_POSITION, flags=0, i=(ls, ln, off),
+                        p=(float(space._inertia),)))
+        width = 2
+    else:
+        raise CompileError('unsupported action space {}'.format(k))
+    prog.action_layout.append((key, k, off, width))
+    prog.action_dim += width
+
+
+def _compile_actions(prog, action_space):
+    specs = []
+    _compile_action(prog, action_space, None, specs)
+    start = len(prog.ops)
+    for s in specs:
+        prog.emit(s['kind'], s['flags'], s['i'], s['p'])
+    prog.sections['actions'] = (start, len(prog.ops) - start)
+
+
+# ---------------------------------------------------------------------------
+# rules
+# ---------------------------------------------------------------------------
+
+def _rule_specs(prog, rule, out):
+    k = _kind(rule)
+    if k == 'VanishOnContact':
+        gci = rule._get_contact_indices
+        l0, l1 = lambdas.contact_layers(gci)
+        out.append(dict(kind=R_VANISH_ON_CONTACT,
+                        i=(prog.layer_index(l0), prog.layer_index(l1))))
+    elif k == 'VanishByFilter':
+        code = lambdas.compile_sprite_predicate(rule._filter_fn)
+        out.append(dict(kind=R_VANISH_BY_FILTER,
+                        i=(prog.layer_index(rule._layer), 0,
+                           prog.add_expr(code))))
+    elif k == 'ModifyOnContact':
+        l0s, l0n = prog.add_list(_as_list(rule._layers_0))
+        l1s, l1n = prog.add_list(_as_list(rule._layers_1))
+        quad = []
+        for mod, filt in ((rule._modifier_0, rule._filter_0),
+                          (rule._modifier_1, rule._filter_1)):
+            quad.append(prog.add_expr(lambdas.compile_modifier(mod))
+                        if mod is not None else -1)
+            quad.append(prog.add_expr(lambdas.compile_sprite_predicate(filt)))
+        out.append(dict(kind=R_MODIFY_ON_CONTACT,
+                        i=(l0s, l0n, l1s, l1n, prog.add_ints(quad))))
+    elif k == 'ModifySprites':
+        ls, ln = prog.add_list(_as_list(rule._layers))
+        mod = prog.add_expr(lambdas.compile_modifier(rule._modifier))
+        filt = (prog.add_expr(lambdas.compile_sprite_predicate(rule._filter_fn))
+                if rule._filter_fn else -1)
+        col = 0
+        if rule._sample_one:
+            col = prog.rule_noise_dim
+            prog.rule_noise_dim += 1
+        out.append(dict(kind=R_MODIFY_SPRITES,
+                        flags=FL_SAMPLE_ONE if rule._sample_one else 0,
+                        i=(ls, ln, mod, filt, col)))
+    elif k == 'ConditionalRule':
+        sub = []
+        for r in rule._rules:
+            _rule_specs(prog, r, sub)
+        out.append(dict(kind=R_COND_BEGIN, cond=rule._condition,
+                        i=[0, len(sub)]))
+        out.extend(sub)
+    else:
+        raise CompileError(
+            'game rule {} is not on the accelerated path'.format(k))
+
+
+def _compile_rules(prog, rules):
+    specs = []
+    for r in (rules or ()):
+        _rule_specs(prog, r, specs)
+    for s in specs:
+        if 'cond' in s:
+            s['i'][0] = _emit_condition(prog, s.pop('cond'))
+    start = len(prog.ops)
+    for s in specs:
+        prog.emit(s['kind'], s.get('flags', 0), s.get('i', ()), s.get('p', ()))
+    prog.sections['rules'] = (start, len(prog.ops) - start)
+
+
+# ---------------------------------------------------------------------------
+# observers
+# ---------------------------------------------------------------------------
+
+def _compile_render(prog, observers):
+    renderer = None
+    for obs in (observers or {}).values():
+        if _kind(obs) == 'PILRenderer':
+            if renderer is not None:
+                raise CompileError('only one PILRenderer observer is supported')
+            renderer = obs
+        elif _kind(obs) == 'RawState':
+            continue
+        elif callable(obs) and _kind(obs) == 'function':
+            continue  # e.g. runtime_benchmark's `lambda _: None`
+        else:
+            raise CompileError('unsupported observer {}'.format(_kind(obs)))
+    if renderer is None:
+        prog.render = None
+        return
+    size = tuple(renderer._image_size)
+    if len(size) != 2:
+        raise CompileError('image_size must be (height, width)')
+    bg = getattr(renderer, '_bg_color', None)
+    if bg is None:
+        bg = renderer._canvas_bg.getpixel((0, 0))
+    fn = renderer.color_to_rgb
+    if fn is None:
+        cmap = CMAP_NONE
+    elif getattr(fn, '__name__', '') == 'hsv_to_rgb':
+        cmap = CMAP_HSV
+    else:
+        probe = (3, 5, 7)
+        try:
+            same = tuple(fn(probe)) == probe
+        except Exception:  # pylint: disable=broad-except
+            same = False
+        if not same:
+            raise CompileError(
+                'color_to_rgb must be None or "hsv_to_rgb" on the device path')
+        cmap = CMAP_NONE
+    pm = renderer._polygon_modifier
+    pk = _kind(pm)
+    modifier, mod_layer = PMOD_NONE, 0
+    if pk == 'FirstPersonAgent':
+        modifier, mod_layer = PMOD_FIRST_PERSON, prog.layer_index(
+            pm._agent_layer)
+    elif pk == 'TorusGeometry':
+        modifier = PMOD_TORUS
+    elif pk != 'DoNothing':
+        raise CompileError('unsupported polygon modifier {}'.format(pk))
+    # pil_renderer.py:46,65-66: canvas = (aa*size[0], aa*size[1]) is handed to
+    # PIL as (width, height) while the array that comes back is [height, width].
+    prog.render = dict(height=int(size[1]), width=int(size[0]),
+                       aa=int(renderer._anti_aliasing), bg=tuple(bg)[:3],
+                       colormap=cmap, modifier=modifier,
+                       modifier_layer=mod_layer)
+
+
+# ---------------------------------------------------------------------------
+# entry points
+# ---------------------------------------------------------------------------
+
+def compile_config(config, sample_states, layer_capacity=None):
+    """Compile a MOOG config dict.
+
+    Args:
+        config: dict with the reference's Environment kwargs
+            (environment.py:28-35).
+        sample_states: list of states (`OrderedDict[str, list[Sprite]]`) from
+            the config's state_initializer; fixes layer names / order and the
+            per-layer capacities (max count seen).
+        layer_capacity: optional {layer: capacity} overrides.
+    """
+    prog = Program()
+    first = sample_states[0]
+    prog.layer_names = list(first.keys())
+    if len(prog.layer_names) > MAX_LAYERS:
+        raise CompileError('at most {} layers'.format(MAX_LAYERS))
+    for st in sample_states:
+        if list(st.keys()) != prog.layer_names:
+            raise CompileError('state initializer changed its layer set')
+    caps = [max(len(st[name]) for st in sample_states)
+            for name in prog.layer_names]
+    for name, cap in (layer_capacity or {}).items():
+        caps[prog.layer_index(name)] = max(cap, caps[prog.layer_index(name)])
+    prog.layer_cap = caps
+    prog.layer_off = [0] + list(np.cumsum(caps))
+    if prog.n_slots > MAX_SLOTS:
+        raise CompileError('at most {} sprites per env'.format(MAX_SLOTS))
+    vcap = []
+    for name in prog.layer_names:
+        nvs = [len(sp.vertices) for st in sample_states for sp in st[name]]
+        vcap.append(max(nvs) if nvs else 0)
+    if max(vcap + [0]) > MAX_VERTS:
+        raise CompileError(
+            'a sprite outline has {} vertices; the device path supports at '
+            'most {}'.format(max(vcap), MAX_VERTS))
+    prog.layer_vcap = vcap
+    voff = [0]
+    for cap, vc in zip(caps, vcap):
+        for _ in range(cap):
+            voff.append(voff[-1] + vc)
+    prog.voff = voff
+
+    _compile_physics(prog, config['physics'])
+    _compile_tasks(prog, config['task'])
+    _compile_actions(prog, config['action_space'])
+    _compile_rules(prog, config.get('game_rules', ()))
+    _compile_render(prog, config.get('observers', {}))
+    return prog.finalize()
+
+
+def _scalar_kind(v):
+    """0 python number (weak), 1 float32, 2 float64 -- how NumPy will promote
+    the value in `angle + dt * angle_vel` (sprite.py:426-430)."""
+    dt = getattr(v, 'dtype', None)
+    if dt is None:
+        return 0
+    return 1 if dt == np.float32 else 2
+
+
+def _sprite_flags(sp):
+    flags = SF_CIRCLE if sp.shape == 'circle' else 0
+    if getattr(sp.velocity, 'dtype', None) == np.float32:
+        flags |= SF_VEL32
+    flags |= _scalar_kind(sp.angle_vel) << SF_ANGVEL_SHIFT
+    flags |= _scalar_kind(sp.angle) << SF_ANG_SHIFT
+    return flags
+
+
+class ShapeTable(object):
+    """Deduplicated table of COM-centred unit outlines."""
+
+    def __init__(self):
+        self._index = {}
+        self.verts = []
+        self.nv = []
+
+    def add(self, outline):
+        outline = np.ascontiguousarray(outline, dtype=np.float64)
+        key = outline.tobytes()
+        sid = self._index.get(key)
+        if sid is None:
+            n = len(outline)
+            if n > MAX_VERTS:
+                raise CompileError(
+                    'sprite outline has {} vertices; the device path supports '
+                    'at most {}'.format(n, MAX_VERTS))
+            if n < 3:
+                raise CompileError('sprite outline needs at least 3 vertices')
+            sid = len(self.nv)
+            padded = np.zeros((MAX_VERTS, 2))
+            padded[:n] = outline
+            self.verts.append(padded)
+            self.nv.append(n)
+            self._index[key] = sid
+        return sid
+
+    def arrays(self):
+        n = max(len(self.nv), 1)
+        verts = np.zeros((n, MAX_VERTS, 2))
+        nv = np.zeros(n, dtype=np.int32)
+        if self.nv:
+            verts[:len(self.nv)] = np.stack(self.verts)
+            nv[:len(self.nv)] = self.nv
+        return verts, nv
+
+
+def pack_states(prog, states, shape_table=None):
+    """States -> dict of numpy arrays laid out as the device state record.
+
+    Reads each sprite through the attributes shared by the reference's Sprite
+    (sprite.py:261-327) and this repo's: position, velocity, angle, angle_vel,
+    mass, scale, aspect_ratio, color, opacity, shape, max_radius and the
+    private `_shape_path.vertices` / `_x_y_rotational_inertia`.
+    """
+    table = ShapeTable() if shape_table is None else shape_table
+    n, S, L = len(states), prog.n_slots, prog.n_layers
+    dyn = np.zeros((n, DYN_FIELDS, S))
+    stat = np.zeros((n, STAT_FIELDS, S))
+    stat[:, 0, :] = 1.0  # mass of unused slots: harmless, never read
+    stat[:, 1, :] = 1.0
+    stat[:, 2, :] = 1.0
+    meta = np.zeros((n, META_FIELDS, S), dtype=np.int32)
+    vtx = np.zeros((n, max(prog.n_vtx, 1), 2))
+    cnt = np.zeros((n, MAX_LAYERS), dtype=np.int32)
+    for e, st in enumerate(states):
+        for l, name in enumerate(prog.layer_names):
+            sprites = st[name]
+            if len(sprites) > prog.layer_cap[l]:
+                raise CompileError(
+                    'layer {!r} holds {} sprites, capacity is {}'.format(
+                        name, len(sprites), prog.layer_cap[l]))
+            cnt[e, l] = len(sprites)
+            for k, sp in enumerate(sprites):
+                s = prog.layer_off[l] + k
+                pos, vel = sp.position, sp.velocity
+                dyn[e, :, s] = (pos[0], pos[1], vel[0], vel[1],
+                                float(sp.angle), float(sp.angle_vel))
+                ixy = sp._x_y_rotational_inertia  # pylint: disable=protected-access
+                col = sp.color
+                stat[e, :, s] = (float(sp.mass), float(sp.scale),
+                                 float(sp.aspect_ratio), ixy[0], ixy[1],
+                                 float(sp.max_radius), float(col[0]),
+                                 float(col[1]), float(col[2]),
+                                 float(sp.opacity))
+                base = sp._shape_path.vertices[:-1]  # pylint: disable=protected-access
+                meta[e, 0, s] = table.add(base)
+                meta[e, 1, s] = _sprite_flags(sp)
+                world = np.asarray(sp.vertices, dtype=np.float64)
+                if len(world) > prog.layer_vcap[l]:
+                    raise CompileError(
+                        'a sprite of layer {!r} has {} vertices, more than any '
+                        'sample state showed ({})'.format(
+                            name, len(world), prog.layer_vcap[l]))
+                meta[e, 2, s] = len(world)
+                vtx[e, prog.voff[s]:prog.voff[s] + len(world)] = world
+    envi = np.zeros((n, ENVI_WORDS), dtype=np.int32)
+    envf = np.zeros((n, max(prog.n_envf, 1)))
+    shape_verts, shape_nv = table.arrays()
+    return dict(dyn=dyn, stat=stat, meta=meta, vtx=vtx, cnt=cnt, envi=envi,
+                envf=envf, shape_verts=shape_verts, shape_nv=shape_nv,
+                shape_table=table)
+
+
+def unpack_state(prog, arrays, e):
+    """Inverse of pack_states for env `e`: {layer: [dict of factors]}."""
+    out = collections.OrderedDict()
+    for l, name in enumerate(prog.layer_names):
+        rows = []
+        for k in range(int(arrays['cnt'][e, l])):
+            s = prog.layer_off[l] + k
+            d = arrays['dyn'][e, :, s]
+            t = arrays['stat'][e, :, s]
+            rows.append(dict(
+                x=d[0], y=d[1], x_vel=d[2], y_vel=d[3], angle=d[4],
+                angle_vel=d[5], mass=t[0], scale=t[1], aspect_ratio=t[2],
+                c0=t[6], c1=t[7], c2=t[8], opacity=t[9],
+                shape_id=int(arrays['meta'][e, 0, s])))
+        out[name] = rows
+    return out

@@ -1,0 +1,388 @@
+"""Lowering of the small Python callables MOOG configs pass around.
+
+MOOG configs hand plain Python functions to rules and tasks: sprite filters
+(`lambda s: s.c2 > 0.6`, cleanup.py:196), sprite modifiers (`def _spoil_fruit
+(sprite): sprite.c2 = _BAD_VALUE`, cleanup.py:174-175), pair conditions
+(`lambda s_0, s_1: s_1.c2 > T`, cleanup.py:143) and state conditions
+(`lambda state: all([s.y < 0. for s in state['prey']])`, pong.py:87).  A
+device kernel cannot call them, so they are lowered once, at compile time:
+
+  * sprite-level callables are *traced* with symbolic sprites whose attribute
+    reads / writes build an expression tree, emitted as a postfix program for
+    the device expression VM (MOOG_X_* in include/moog_b200_program.h);
+  * state-level conditions are recognised from their source (all / any / len /
+    sum over one layer, combined with not / and / or / comparisons) and become
+    MOOG_SC_* ops; contact counters built with `get_contact_counter` are read
+    from their closure.
+
+Anything that cannot be lowered raises `LoweringError` at construction time --
+there is no per-step Python fallback.
+"""
+
+import ast
+import inspect
+import textwrap
+
+(X_END, X_CONST, X_ATTR0, X_ATTR1, X_LT, X_LE, X_GT, X_GE, X_EQ, X_NE, X_AND,
+ X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE) = \
+    range(21)
+
+ATTRS = ('x', 'y', 'x_vel', 'y_vel', 'angle', 'angle_vel', 'mass', 'scale',
+         'aspect_ratio', 'c0', 'c1', 'c2', 'opacity')
+_WRITABLE = ('x_vel', 'y_vel', 'angle_vel', 'mass', 'c0', 'c1', 'c2',
+             'opacity')
+
+
+class LoweringError(ValueError):
+    pass
+
+
+# ---------------------------------------------------------------------------
+# symbolic expressions
+# ---------------------------------------------------------------------------
+
+class Sym(object):
+    """Node of a traced expression; `code` is its postfix program."""
+
+    __slots__ = ('code',)
+    __hash__ = None
+
+    def __init__(self, code):
+        self.code = code
+
+    @staticmethod
+    def lift(v):
+        if isinstance(v, Sym):
+            return v
+        if isinstance(v, (bool, int, float)) or hasattr(v, '__float__'):
+            return Sym([(X_CONST, 0, float(v))])
+        raise LoweringError(
+            'cannot use a value of type {} in a device expression'.format(
+                type(v).__name__))
+
+    def _bin(self, other, op, swap=False):
+        a, b = Sym.lift(self), Sym.lift(other)
+        if swap:
+            a, b = b, a
+        return Sym(a.code + b.code + [(op, 0, 0.0)])
+
+    def __lt__(self, o): return self._bin(o, X_LT)
+    def __le__(self, o): return self._bin(o, X_LE)
+    def __gt__(self, o): return self._bin(o, X_GT)
+    def __ge__(self, o): return self._bin(o, X_GE)
+    def __eq__(self, o): return self._bin(o, X_EQ)
+    def __ne__(self, o): return self._bin(o, X_NE)
+    def __add__(self, o): return self._bin(o, X_ADD)
+    def __radd__(self, o): return self._bin(o, X_ADD, True)
+    def __sub__(self, o): return self._bin(o, X_SUB)
+    def __rsub__(self, o): return self._bin(o, X_SUB, True)
+    def __mul__(self, o): return self._bin(o, X_MUL)
+    def __rmul__(self, o): return self._bin(o, X_MUL, True)
+    def __truediv__(self, o): return self._bin(o, X_DIV)
+    def __rtruediv__(self, o): return self._bin(o, X_DIV, True)
+    def __mod__(self, o): return self._bin(o, X_MOD)
+    def __rmod__(self, o): return self._bin(o, X_MOD, True)
+    def __and__(self, o): return self._bin(o, X_AND)
+    def __rand__(self, o): return self._bin(o, X_AND, True)
+    def __or__(self, o): return self._bin(o, X_OR)
+    def __ror__(self, o): return self._bin(o, X_OR, True)
+    def __neg__(self): return Sym(self.code + [(X_NEG, 0, 0.0)])
+    def __abs__(self): return Sym(self.code + [(X_ABS, 0, 0.0)])
+    def __invert__(self): return Sym(self.code + [(X_NOT, 0, 0.0)])
+
+    def __bool__(self):
+        raise LoweringError(
+            'the callable branches on a per-sprite value (if / and / or / not '
+            'on a sprite attribute); write the test as a single comparison or '
+            'combine comparisons with & and |')
+
+
+class SymSprite(object):
+    """Stand-in for a Sprite while tracing: reads give Sym nodes, writes are
+    recorded as stores."""
+
+    def __init__(self, which, stores=None):
+        object.__setattr__(self, '_which', which)
+        object.__setattr__(self, '_stores', stores)
+
+    def __getattr__(self, name):
+        if name in ATTRS:
+            op = X_ATTR0 if self._which == 0 else X_ATTR1
+            return Sym([(op, ATTRS.index(name), 0.0)])
+        if name == 'position':
+            return (self.x, self.y)
+        if name == 'velocity':
+            return (self.x_vel, self.y_vel)
+        raise LoweringError(
+            'sprite attribute {!r} is not available on the device'.format(name))
+
+    def __setattr__(self, name, value):
+        if self._stores is None:
+            raise LoweringError('this callable may not modify sprites')
+        if name == 'velocity':
+            self._stores.append(('x_vel', Sym.lift(value[0])))
+            self._stores.append(('y_vel', Sym.lift(value[1])))
+            return
+        if name not in _WRITABLE:
+            raise LoweringError(
+                'assigning sprite.{} is not supported on the device path '
+                '(writable: {})'.format(name, ', '.join(_WRITABLE)))
+        self._stores.append((name, Sym.lift(value)))
+
+
+def _n_params(fn):
+    return len(inspect.signature(fn).parameters)
+
+
+def closure_vars(fn):
+    """{free variable name: value} of a Python function (empty if none)."""
+    code = getattr(fn, '__code__', None)
+    cells = getattr(fn, '__closure__', None)
+    if code is None or not cells:
+        return {}
+    out = {}
+    for name, cell in zip(code.co_freevars, cells):
+        try:
+            out[name] = cell.cell_contents
+        except ValueError:
+            pass
+    return out
+
+
+def _unwrap(fn, name):
+    """Peel the reference's signature-adapting lambdas, e.g.
+    `lambda s_a, s_t, meta_state: condition(s_a, s_t)` (contact_reward.py:60)."""
+    seen = 0
+    while callable(fn) and seen < 4:
+        cv = closure_vars(fn)
+        if set(cv) == {name} and getattr(fn, '__name__', '') == '<lambda>':
+            fn = cv[name]
+            seen += 1
+        else:
+            break
+    return fn
+
+
+def _code_of(value):
+    return Sym.lift(value).code
+
+
+# ---------------------------------------------------------------------------
+# sprite-level callables
+# ---------------------------------------------------------------------------
+
+def compile_sprite_predicate(fn):
+    """`fn(sprite) -> bool`  ->  postfix code, or None for "always true"."""
+    if fn is None:
+        return None
+    out = fn(SymSprite(0))
+    if out is True:
+        return None
+    return _code_of(out)
+
+
+def compile_pair_condition(fn):
+    """`fn(s0, s1[, meta_state]) -> bool` -> postfix code / None."""
+    fn = _unwrap(fn, 'condition')
+    if fn is None:
+        return None
+    n = _n_params(fn)
+    args = (SymSprite(0), SymSprite(1)) + ((None,) if n >= 3 else ())
+    out = fn(*args)
+    if out is True:
+        return None
+    return _code_of(out)
+
+
+def compile_modifier(fn):
+    """`fn(sprite)` mutating the sprite -> postfix code of its stores."""
+    stores = []
+    fn(SymSprite(0, stores))
+    code = []
+    for name, value in stores:
+        code += value.code + [(X_STORE, ATTRS.index(name), 0.0)]
+    # Leave a value on the stack so the VM has a defined result.
+    return code + [(X_CONST, 0, 1.0)]
+
+
+def constant_reward(reward_fn):
+    """ContactReward reward_fn -> float (contact_reward.py:48-51)."""
+    if not callable(reward_fn):
+        return float(reward_fn)
+    cv = closure_vars(reward_fn)
+    if set(cv) == {'reward_fn'} and not callable(cv['reward_fn']):
+        return float(cv['reward_fn'])
+    try:
+        out = reward_fn(SymSprite(0), SymSprite(1))
+        return float(out)
+    except (LoweringError, TypeError):
+        raise LoweringError(
+            'ContactReward reward_fn must be a constant on the device path')
+
+
+def constant_state_reward(reward_fn):
+    """Reset reward_fn -> float (reset.py:41-43 defaults to `lambda _: 0.`)."""
+    if reward_fn is None:
+        return 0.0
+    try:
+        return float(reward_fn(None))
+    except Exception:  # pylint: disable=broad-except
+        raise LoweringError(
+            'Reset reward_fn must not depend on the state on the device path')
+
+
+# ---------------------------------------------------------------------------
+# state-level conditions
+# ---------------------------------------------------------------------------
+
+def contact_layers(fn):
+    """(layer_0, layer_1) of a get_contact_indices / get_contact_counter."""
+    if hasattr(fn, 'layer_0') and hasattr(fn, 'layer_1'):
+        return fn.layer_0, fn.layer_1
+    cv = closure_vars(fn)
+    if {'layer_0', 'layer_1'} <= set(cv):
+        return cv['layer_0'], cv['layer_1']
+    if '_get_contact_indices' in cv:
+        return contact_layers(cv['_get_contact_indices'])
+    return None
+
+
+def _lambda_ast(fn):
+    """Parse the source of `fn` and return its Lambda / FunctionDef node."""
+    try:
+        src = textwrap.dedent(inspect.getsource(fn))
+    except (OSError, TypeError):
+        raise LoweringError('no source available for {!r}'.format(fn))
+    if fn.__name__ != '<lambda>':
+        tree = ast.parse(src)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.FunctionDef) and node.name == fn.__name__:
+                return node
+        raise LoweringError('cannot find def {} in its source'.format(
+            fn.__name__))
+    # A lambda's "source" is the physical line(s) it sits on: cut at each
+    # 'lambda' keyword and shrink from the right until it parses.
+    argnames = list(inspect.signature(fn).parameters)
+    pos = -1
+    while True:
+        pos = src.find('lambda', pos + 1)
+        if pos < 0:
+            break
+        for end in range(len(src), pos + 6, -1):
+            try:
+                node = ast.parse(src[pos:end].strip(), mode='eval').body
+            except SyntaxError:
+                continue
+            if isinstance(node, ast.Lambda) and [
+                    a.arg for a in node.args.args] == argnames:
+                return node
+    raise LoweringError('cannot isolate the lambda in: {}'.format(src.strip()))
+
+
+class _StateLowering(object):
+    def __init__(self, fn, prog, node):
+        self.fn = fn
+        self.prog = prog
+        self.ns = dict(getattr(fn, '__globals__', {}))
+        self.ns.update(closure_vars(fn))
+        args = [a.arg for a in node.args.args]
+        self.state_name = args[0]
+
+    def fail(self, node):
+        raise LoweringError(
+            'state condition is not in the supported form (all / any / sum / '
+            'len over one layer, combined with not / and / or / comparisons): '
+            + ast.unparse(node))
+
+    def _layer_of(self, node):
+        """state['name'] -> 'name'."""
+        if (isinstance(node, ast.Subscript) and isinstance(node.value, ast.Name)
+                and node.value.id == self.state_name):
+            key = node.slice
+            try:
+                return eval(compile(ast.Expression(key), '<cond>', 'eval'),  # pylint: disable=eval-used
+                            self.ns)
+            except Exception:  # pylint: disable=broad-except
+                self.fail(node)
+        self.fail(node)
+
+    def _comprehension(self, node):
+        """[elt for s in state['L'] (if cond)] -> (layer, Sym)."""
+        if not isinstance(node, (ast.ListComp, ast.GeneratorExp)):
+            self.fail(node)
+        if len(node.generators) != 1:
+            self.fail(node)
+        gen = node.generators[0]
+        if not isinstance(gen.target, ast.Name):
+            self.fail(node)
+        layer = self._layer_of(gen.iter)
+        var = gen.target.id
+
+        def _trace(expr_node):
+            fn_node = ast.Expression(ast.Lambda(
+                args=ast.arguments(posonlyargs=[], args=[ast.arg(arg=var)],
+                                   kwonlyargs=[], kw_defaults=[], defaults=[]),
+                body=expr_node))
+            ast.fix_missing_locations(fn_node)
+            f = eval(compile(fn_node, '<cond>', 'eval'), self.ns)  # pylint: disable=eval-used
+            return Sym.lift(f(SymSprite(0)))
+
+        elt = _trace(node.elt)
+        for cond in gen.ifs:
+            elt = elt & _trace(cond)
+        return layer, elt
+
+    def lower(self, node):
+        """-> op index producing the value of `node` as a double."""
+        prog = self.prog
+        # the C enum values are duplicated here to avoid a circular import
+        SC_ALL, SC_ANY, SC_COUNT, SC_CONST = 160, 161, 162, 165
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name):
+            name = node.func.id
+            if name in ('all', 'any', 'sum') and len(node.args) == 1:
+                layer, elt = self._comprehension(node.args[0])
+                ls, ln = prog.add_list([layer])
+                kind = {'all': SC_ALL, 'any': SC_ANY, 'sum': SC_COUNT}[name]
+                return ('op', prog.emit(kind, 0, (ls, ln, prog.add_expr(elt.code))))
+            if name == 'len' and len(node.args) == 1:
+                layer = self._layer_of(node.args[0])
+                ls, ln = prog.add_list([layer])
+                return ('op', prog.emit(SC_COUNT, 0, (ls, ln, -1)))
+        if isinstance(node, ast.Constant) and isinstance(
+                node.value, (bool, int, float)):
+            return ('const', float(node.value))
+        self.fail(node)
+
+
+def compile_state_condition(cond, prog):
+    """State condition -> index of the op that evaluates it.
+
+    Supported: contact counters (`get_contact_counter(l0, l1)`); and Python
+    callables of the form `all(...)`, `any(...)`, `sum(...)`, `len(state[L])`
+    over one layer with a per-sprite expression.
+    """
+    from . import compiler as C  # late import: compiler imports this module
+    cond = _unwrap(cond, 'condition')
+    layers = contact_layers(cond) if callable(cond) else None
+    if layers is not None:
+        return prog.emit(C.SC_CONTACT_COUNT, 0,
+                         (prog.layer_index(layers[0]),
+                          prog.layer_index(layers[1])))
+    declared = getattr(cond, 'moog_b200_condition', None)
+    if declared is not None:
+        return declared(prog)
+    node = _lambda_ast(cond)
+    body = node.body
+    if isinstance(body, list):  # def: single `return <expr>`
+        stmts = [s for s in body if not (
+            isinstance(s, ast.Expr) and isinstance(s.value, ast.Constant))]
+        if len(stmts) != 1 or not isinstance(stmts[0], ast.Return):
+            raise LoweringError(
+                'state condition {} must be a single return expression'.format(
+                    cond.__name__))
+        body = stmts[0].value
+    low = _StateLowering(cond, prog, node)
+    kind, value = low.lower(body)
+    if kind == 'const':
+        return prog.emit(C.SC_CONST, 0, (), (value,))
+    return value

@@ -1,0 +1,126 @@
+"""Game-rule specs (reference: moog/game_rules/).
+
+On the hot path (lowered to device ops by moog_b200.compiler):
+`VanishOnContact`, `VanishByFilter`, `ModifyOnContact`, `ModifySprites`,
+`ConditionalRule`, plus the `get_contact_indices` / `get_contact_counter`
+condition builders.  The psychophysics trial-structure rules of the reference
+(Phase*, TimedRule, Fixation, Portal, CreateSprites, ...) are outside the
+accelerated path; constructing one raises so that a config never silently
+loses a rule.
+"""
+
+import abc
+
+
+def _as_tuple(x):
+    return tuple(x) if isinstance(x, (list, tuple)) else (x,)
+
+
+class AbstractRule(abc.ABC):
+    def reset(self, state, meta_state):
+        pass
+
+    def step(self, state, meta_state):
+        raise RuntimeError(
+            'game rules are applied on the device by BatchedEnvironment')
+
+
+class ContactCondition(object):
+    """Declarative state -> int condition: number of contacting index pairs
+    between two layers (contact_rules.py:15-51)."""
+
+    def __init__(self, layer_0, layer_1, as_indices=False):
+        self.layer_0 = layer_0
+        self.layer_1 = layer_1
+        self.as_indices = as_indices
+
+    def __call__(self, state):
+        raise RuntimeError('contact conditions are evaluated on the device')
+
+
+def get_contact_indices(layer_0, layer_1):
+    return ContactCondition(layer_0, layer_1, as_indices=True)
+
+
+def get_contact_counter(layer_0, layer_1):
+    return ContactCondition(layer_0, layer_1)
+
+
+class ModifyOnContact(AbstractRule):
+    """contact_rules.py:54-96."""
+
+    def __init__(self, layers_0, layers_1, modifier_0=None, modifier_1=None,
+                 filter_0=None, filter_1=None):
+        self._layers_0 = _as_tuple(layers_0)
+        self._layers_1 = _as_tuple(layers_1)
+        self._modifier_0 = modifier_0
+        self._modifier_1 = modifier_1
+        self._filter_0 = filter_0
+        self._filter_1 = filter_1
+
+
+class Vanish(AbstractRule):
+    def __init__(self, layer):
+        self._layer = layer
+
+
+class VanishByFilter(Vanish):
+    """vanish.py:42-63."""
+
+    def __init__(self, layer, filter_fn=None):
+        super().__init__(layer)
+        self._filter_fn = filter_fn
+
+
+class VanishOnContact(Vanish):
+    """vanish.py:66-86."""
+
+    def __init__(self, vanishing_layer, contacting_layer):
+        super().__init__(vanishing_layer)
+        self._contacting_layer = contacting_layer
+        self._get_contact_indices = get_contact_indices(
+            vanishing_layer, contacting_layer)
+
+
+class ModifySprites(AbstractRule):
+    """modify_sprites.py:17-33."""
+
+    def __init__(self, layers, modifier, sample_one=False, filter_fn=None):
+        self._layers = [layers] if isinstance(layers, str) else layers
+        self._modifier = modifier
+        self._sample_one = sample_one
+        self._filter_fn = filter_fn
+
+
+class ConditionalRule(AbstractRule):
+    """conditional.py:30-53."""
+
+    def __init__(self, condition, rules):
+        self._condition = condition
+        self._rules = list(rules) if isinstance(rules, (list, tuple)) else [
+            rules]
+
+
+def _out_of_scope(name, where):
+    def _ctor(*args, **kwargs):
+        raise NotImplementedError(
+            'game_rules.{} ({}) is outside the accelerated Environment.step '
+            'path of this build (see DESIGN.md, "out of scope").'.format(
+                name, where))
+    _ctor.__name__ = name
+    return _ctor
+
+
+ChangeLayer = _out_of_scope('ChangeLayer', 'change_layer.py')
+CreateSprites = _out_of_scope('CreateSprites', 'create_sprites.py')
+Fixation = _out_of_scope('Fixation', 'fixation.py')
+ModifyMetaState = _out_of_scope('ModifyMetaState', 'modify_meta_state.py')
+UpdateMetaStateValue = _out_of_scope(
+    'UpdateMetaStateValue', 'modify_meta_state.py')
+Portal = _out_of_scope('Portal', 'portal.py')
+KeepNearCenter = _out_of_scope('KeepNearCenter', 're_center.py')
+Phase = _out_of_scope('Phase', 'task_phases.py')
+PhaseSequence = _out_of_scope('PhaseSequence', 'task_phases.py')
+DelayedRule = _out_of_scope('DelayedRule', 'timing.py')
+TemporaryRule = _out_of_scope('TemporaryRule', 'timing.py')
+TimedRule = _out_of_scope('TimedRule', 'timing.py')

@@ -1,0 +1,68 @@
+"""Sprite generators: callables producing lists of host Sprites by sampling
+a factor distribution, with optional rejection against overlap.
+
+Reference: moog/state_initialization/sprite_generators.py:26-190.
+"""
+
+import numpy as np
+
+from moog import sprite as sprite_lib
+
+
+def generate_sprites(factor_dist, num_sprites=1, max_recursion_depth=int(1e4),
+                     fail_gracefully=False):
+    """Returns `_generate(disjoint=False, without_overlapping=[])`."""
+
+    def _touches_any(s, others):
+        # Every pair is evaluated (no short-circuit), like the reference.
+        return any([s.overlaps_sprite(o) for o in others]) if others else False
+
+    def _generate(disjoint=False, without_overlapping=[]):
+        count = num_sprites() if callable(num_sprites) else num_sprites
+        avoid = list(without_overlapping)
+        out = []
+        for _ in range(count):
+            candidate = sprite_lib.Sprite(**factor_dist.sample())
+            rejected = 0
+            while _touches_any(candidate, avoid):
+                if rejected > max_recursion_depth:
+                    if fail_gracefully:
+                        return out
+                    raise RecursionError(
+                        'max_recursion_depth exceeded trying to initialize '
+                        'a non-overlapping sprite.')
+                rejected += 1
+                candidate = sprite_lib.Sprite(**factor_dist.sample())
+            out.append(candidate)
+            if disjoint:
+                avoid = avoid + [candidate]
+        return out
+
+    return _generate
+
+
+def chain_generators(*sprite_generators):
+    """Concatenates the outputs of several generators."""
+    def _generate(*args, **kwargs):
+        out = []
+        for g in sprite_generators:
+            out.extend(g(*args, **kwargs))
+        return out
+    return _generate
+
+
+def sample_generator(sprite_generators, p=None):
+    """Calls one generator picked at random."""
+    def _generate(*args, **kwargs):
+        return np.random.choice(sprite_generators, p=p)(*args, **kwargs)
+    return _generate
+
+
+def shuffle(sprite_generator):
+    """Randomly permutes a generator's output (z-order randomisation)."""
+    def _generate(*args, **kwargs):
+        sprites = sprite_generator(*args, **kwargs)
+        order = np.arange(len(sprites))
+        np.random.shuffle(order)
+        return [sprites[i] for i in order]
+    return _generate
