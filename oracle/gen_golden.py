@@ -1,0 +1,185 @@
+"""Generate golden vectors by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY; runs in the build container only (needs
+/root/reference, imported through oracle/shims).  Usage:
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+For each scene the reference `Environment` (moog/environment.py) is reset and
+stepped with seeded random actions.  Recorded per scene:
+
+    blob                 program compiled from the reference's own config objects
+    init_*               state record packed from state_initializer()'s output
+                         (before the reference steps its rules at reset)
+    reset_*              state record after Environment.reset()
+    actions[T, A]        action fed at step t
+    noise[T, K, ND]      unit uniforms behind RandomForce's draws at step t
+    dyn/stat/meta/vtx/cnt[T, ...]  state record after step t
+    reward[T], last[T]   TimeStep.reward / TimeStep.last()
+    n_calls[T], n_true[T], true_hash[T]
+                         Sprite.overlaps_sprite calls of step t: count, number
+                         that returned True, order-sensitive hash of the True
+                         (slot_a, slot_b) events
+    frames[F, H, W, 3]   PILRenderer output at steps frame_steps[F]
+"""
+
+import importlib
+import os
+import sys
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:] = [p for p in sys.path if os.path.abspath(p or '.') != os.path.join(_ROOT, 'oracle')]
+sys.path.insert(0, _ROOT)
+
+from oracle import refenv  # noqa: E402
+
+refenv.activate()
+
+import moog_b200  # noqa: E402,F401  (adds the configs package path)
+from moog_b200 import compiler  # noqa: E402
+from moog import environment  # noqa: E402
+
+MASK64 = (1 << 64) - 1
+
+
+def true_event_hash(h, a, b):
+    """Same mixing as oracle/moog_oracle.c `overlaps` (True events only)."""
+    x = ((a * 1315423911) & 0xFFFFFFFF) ^ ((b * 2654435761) & 0xFFFFFFFF) ^ 1
+    return ((h ^ x) * 1099511628211) & MASK64
+
+
+SCENES = {
+    # name: (module, level, seed, T, frame_every)
+    'pong': ('moog_demos.example_configs.pong', None, 0, 60, 6),
+    'falling_balls': ('moog_demos.example_configs.falling_balls', None, 1, 40, 8),
+    'falling_balls20': ('moog_b200.configs.falling_balls20', None, 2, 45, 9),
+    'colliding_predators': ('moog_demos.example_configs.colliding_predators', None, 3, 50, 10),
+    'predators_arena': ('moog_demos.example_configs.predators_arena', 3, 4, 40, 10),
+    'synthetic32': ('moog_b200.configs.synthetic32', None, 5, 30, 10),
+}
+
+
+def _slot_map(prog, state):
+    m = {}
+    for l, name in enumerate(prog.layer_names):
+        for k, sp in enumerate(state[name]):
+            m[id(sp)] = int(prog.layer_off[l]) + k
+    return m
+
+
+def _flat_action(prog, action):
+    out = np.zeros(max(prog.action_dim, 1))
+    for key, kind, off, width in prog.action_layout:
+        a = action if key is None else action[key]
+        out[off:off + width] = np.asarray(a, dtype=np.float64).reshape(-1)[:width]
+    return out
+
+
+def generate(name, out_dir):
+    module, level, seed, T, frame_every = SCENES[name]
+    np.random.seed(seed)
+    mod = importlib.import_module(module)
+    config = mod.get_config(level)
+    env = environment.Environment(**config)
+
+    # capture the state initializer's output before the reference steps rules
+    init_state = env.state_initializer()
+    samples = [init_state]
+    prog = compiler.compile_config(config, samples)
+    init = compiler.pack_states(prog, [init_state])
+    env.state_initializer = lambda: init_state
+    ts = env.reset()
+    table = init['shape_table']
+    after_reset = compiler.pack_states(prog, [env.state], table)
+    renderer = config.get('observers', {}).get('image')
+
+    # uniforms behind RandomForce (random_force.py:22-26)
+    draws = []
+    orig_uniform = np.random.uniform
+
+    def _uniform(low=0.0, high=1.0, size=None):
+        if size is not None:
+            return orig_uniform(low, high, size)
+        u = np.random.random_sample()
+        draws.append(u)
+        return low + (high - low) * u
+
+    rec = {k: [] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt', 'reward', 'last',
+                           'actions', 'noise', 'n_calls', 'n_true', 'true_hash')}
+    frames, frame_steps = [], []
+    if renderer is not None:
+        frames.append(np.asarray(ts.observation['image']))
+        frame_steps.append(-1)
+    K, nd = prog.K, prog.noise_dim
+    for t in range(T):
+        action = env.action_space.random_action()
+        flat = _flat_action(prog, action)
+        slots = _slot_map(prog, env.state)
+        del draws[:]
+        np.random.uniform = _uniform
+        try:
+            with refenv.OverlapLog() as log:
+                ts = env.step(action)
+        finally:
+            np.random.uniform = orig_uniform
+        h, n_true = 0, 0
+        for a, b, r in log.calls:
+            if r:
+                n_true += 1
+                h = true_event_hash(h, slots[id(a)], slots[id(b)])
+        noise = np.zeros((K, max(nd, 1)))
+        if nd:
+            # draws arrive substep by substep, in force order, 2 per sprite
+            per = len(draws) // K
+            assert per * K == len(draws) and per <= nd, (per, nd, len(draws))
+            noise[:, :per] = np.array(draws).reshape(K, per)
+        st = compiler.pack_states(prog, [env.state], table)
+        for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt'):
+            rec[k].append(st[k][0])
+        rec['reward'].append(0.0 if ts.reward is None else float(ts.reward))
+        rec['last'].append(bool(ts.last()))
+        rec['actions'].append(flat)
+        rec['noise'].append(noise)
+        rec['n_calls'].append(len(log.calls))
+        rec['n_true'].append(n_true)
+        rec['true_hash'].append(np.uint64(h))
+        if renderer is not None and (t % frame_every == 0 or ts.last()):
+            frames.append(np.asarray(ts.observation['image']))
+            frame_steps.append(t)
+        if ts.last():
+            break
+
+    shape_verts, shape_nv = table.arrays()
+    out = dict(
+        blob=np.frombuffer(prog.blob, dtype=np.uint8),
+        layer_names=np.array(prog.layer_names),
+        shape_verts=shape_verts, shape_nv=shape_nv,
+        frames=np.array(frames, dtype=np.uint8).reshape(
+            (len(frames),) + ((renderer._image_size[1], renderer._image_size[0], 3)  # pylint: disable=protected-access
+                              if renderer is not None else (0, 0, 3))),
+        frame_steps=np.array(frame_steps, dtype=np.int32),
+    )
+    for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt', 'envi', 'envf'):
+        out['init_' + k] = init[k][0]
+        out['reset_' + k] = after_reset[k][0]
+    for k, v in rec.items():
+        out[k] = np.array(v)
+    path = os.path.join(out_dir, name + '.npz')
+    np.savez_compressed(path, **out)
+    print('{:22s} T={:3d} slots={:3d} vtx={:4d} true/step={:.1f} -> {} ({} KB)'.format(
+        name, len(rec['reward']), prog.n_slots, prog.n_vtx,
+        float(np.mean(rec['n_true'])), path, os.path.getsize(path) // 1024))
+
+
+def main():
+    out_dir = os.path.join(_ROOT, 'tests', 'golden')
+    os.makedirs(out_dir, exist_ok=True)
+    names = sys.argv[1:] or list(SCENES)
+    for n in names:
+        generate(n, out_dir)
+
+
+if __name__ == '__main__':
+    main()

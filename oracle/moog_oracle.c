@@ -142,7 +142,7 @@ typedef struct {
   int substep;
   /* instrumentation for parity tests */
   int64_t n_overlap_calls, n_overlap_true, n_collisions;
-  uint64_t overlap_hash; /* order-sensitive hash of (a, b, result) of every overlaps() call */
+  uint64_t overlap_hash; /* order-sensitive hash of the (a, b) of every overlaps() call that returned True */
 } env_t;
 
 #define DYN(e, f, s) ((e)->dyn[(f) * (e)->S + (s)])
@@ -323,8 +323,9 @@ static int overlaps(env_t *e, int a, int b) {
     g_log[g_log_len + 2] = (uint8_t)r;
   }
   g_log_len += 3;
-  e->overlap_hash = (e->overlap_hash ^ (uint64_t)((a * 1315423911u) ^ (b * 2654435761u) ^ (unsigned)r)) *
-                    1099511628211ull;
+  if (r) /* order-sensitive hash of the True events only (cheap enough to keep on the device) */
+    e->overlap_hash = (e->overlap_hash ^ (uint64_t)((a * 1315423911u) ^ (b * 2654435761u) ^ 1u)) *
+                      1099511628211ull;
   return r;
 }
 

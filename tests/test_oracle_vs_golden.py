@@ -1,0 +1,54 @@
+"""Pins the CPU oracle (oracle/moog_oracle.c, pil_oracle.c) against golden
+vectors recorded from the UNMODIFIED reference (oracle/gen_golden.py).
+
+Runs on CPU.  The oracle follows the golden trajectory step by step from the
+recorded initial state, fed with the recorded actions (and the unit uniforms
+behind RandomForce); after every step the full state record -- positions,
+velocities, angles, the cached world vertices, sprite counts -- the reward,
+the termination flag and the overlap-call statistics must match.
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from tests import util
+
+
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_oracle_follows_reference_trajectory(scene):
+    g = util.load_golden(scene)
+    prog = g['program']
+    orc = Oracle(prog, util.state_at(g, None, prefix='init'))
+    orc.post_reset()
+    for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta'):
+        assert np.array_equal(getattr(orc, k)[0], g['reset_' + k]), 'reset ' + k
+    T = len(g['reward'])
+    worst = 0.0
+    for t in range(T):
+        noise = g['noise'][t][None] if prog.noise_dim else None
+        reward, step_type = orc.step(g['actions'][t][None], noise=noise)
+        assert np.array_equal(orc.cnt[0], g['cnt'][t]), (scene, t)
+        live = util.live_mask(prog, g['cnt'][t])
+        for k in ('dyn', 'stat'):
+            worst = max(worst, util.rel_err(getattr(orc, k)[0][:, live], g[k][t][:, live]))
+        worst = max(worst, util.rel_err(orc.vtx[0], g['vtx'][t]))
+        assert reward[0] == g['reward'][t], (scene, t)
+        assert bool(step_type[0] == 2) == bool(g['last'][t]), (scene, t)
+        n_calls, n_true, _, h = orc.counters[0]
+        assert n_calls == g['n_calls'][t], (scene, t, 'overlap call count')
+        assert n_true == g['n_true'][t], (scene, t, 'overlap true count')
+        assert np.uint64(h) == g['true_hash'][t], (scene, t, 'overlap pair set')
+        assert worst == 0.0, (scene, t, worst)   # the oracle is bit-exact vs the reference
+
+
+@pytest.mark.parametrize('scene', [s for s in util.SCENES])
+def test_oracle_render_matches_reference_frames(scene):
+    g = util.load_golden(scene)
+    prog = g['program']
+    if prog.render is None or len(g['frames']) == 0:
+        pytest.skip('scene has no renderer')
+    for f, t in zip(g['frames'], g['frame_steps']):
+        orc = Oracle(prog, util.state_at(g, int(t)))
+        out = orc.render()[0]
+        assert out.shape == f.shape
+        assert np.array_equal(out, f), (scene, int(t), int((out != f).sum()))

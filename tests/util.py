@@ -1,0 +1,94 @@
+"""Shared helpers of the test-suite: golden fixtures and comparison rules."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+SCENES = ['pong', 'falling_balls', 'falling_balls20', 'colliding_predators',
+          'predators_arena', 'synthetic32']
+# scenes whose step() uses no sin/cos of a non-zero angle: every operation on
+# the path is IEEE-exact (+ - * / sqrt fma), so the CUDA path must be bit-exact
+EXACT_SCENES = ['pong', 'falling_balls', 'falling_balls20']
+
+STATE_KEYS = ('dyn', 'stat', 'meta', 'vtx', 'cnt', 'envi', 'envf')
+
+# north_star: single-step positions / velocities / angles within 1e-5 relative.
+RTOL = 1e-5
+ATOL_FLOOR = 1e-9   # absolute floor for components that are exactly 0 in the reference
+
+
+class ProgramStub(object):
+    """Just enough of moog_b200.compiler.Program, rebuilt from a stored blob."""
+
+    def __init__(self, blob, layer_names=None):
+        from moog_b200 import compiler as C
+        self.blob = bytes(bytearray(blob))
+        hdr = np.frombuffer(self.blob[:C.HDR_WORDS * 4], dtype='<i4')
+        self.header = hdr
+        self.n_layers = int(hdr[C.H_N_LAYERS])
+        self.n_slots = int(hdr[C.H_N_SLOTS])
+        self.K = int(hdr[C.H_K])
+        self.n_envf = int(hdr[C.H_N_ENVF])
+        self.action_dim = int(hdr[C.H_ACTION_DIM])
+        self.noise_dim = int(hdr[C.H_NOISE_DIM])
+        self.rule_noise_dim = int(hdr[C.H_RULE_NOISE_DIM])
+        self.n_vtx = int(hdr[C.H_N_VTX])
+        self.layer_off = [int(v) for v in hdr[C.H_LAYER_OFF:C.H_LAYER_OFF + self.n_layers + 1]]
+        self.layer_cap = [b - a for a, b in zip(self.layer_off[:-1], self.layer_off[1:])]
+        self.layer_names = [str(n) for n in layer_names] if layer_names is not None else [
+            'layer%d' % i for i in range(self.n_layers)]
+        self.render = None
+        if hdr[C.H_R_ENABLED]:
+            self.render = dict(height=int(hdr[C.H_R_HEIGHT]), width=int(hdr[C.H_R_WIDTH]),
+                               aa=int(hdr[C.H_R_AA]))
+
+    def layer_index(self, name):
+        return self.layer_names.index(name)
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    g['program'] = ProgramStub(g['blob'], g['layer_names'])
+    return g
+
+
+def state_at(g, t, prefix=None):
+    """State record (batch of 1) after step t of the golden trajectory
+    (t = -1: after reset).  envi / envf are not recorded per step."""
+    if prefix is not None:
+        return {k: g[prefix + '_' + k][None].copy() for k in STATE_KEYS}
+    if t < 0:
+        return {k: g['reset_' + k][None].copy() for k in STATE_KEYS}
+    out = {k: g[k][t][None].copy() for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')}
+    out['envi'] = g['reset_envi'][None].copy()
+    out['envf'] = g['reset_envf'][None].copy()
+    return out
+
+
+def tile_state(st, n):
+    return {k: np.repeat(v, n, axis=0) for k, v in st.items()}
+
+
+def live_mask(prog, cnt):
+    """[S] bool: slots that hold a live sprite."""
+    m = np.zeros(prog.n_slots, dtype=bool)
+    for l in range(prog.n_layers):
+        m[prog.layer_off[l]:prog.layer_off[l] + int(cnt[l])] = True
+    return m
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, floor-scaled) as one number (0 when bit-equal)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    d = np.abs(a - b)
+    scale = np.maximum(np.abs(b), ATOL_FLOOR / RTOL)
+    with np.errstate(invalid='ignore'):
+        e = d / scale
+    e = np.where(np.isnan(a) & np.isnan(b), 0.0, e)
+    e = np.where((a == b), 0.0, e)
+    return float(np.nanmax(e)) if not np.all(np.isnan(e)) else float('inf')
