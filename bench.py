@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- batched env-steps/s including the 64x64 RGB render (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--scene falling_balls20|synthetic32] [--envs E]
+
+A "step" is one Environment.step of every env of the batch (physics K substeps
++ rules + task) followed by the PILRenderer frame of every env.  N=1 workload:
+BASELINE.json configs[1], `falling_balls20` with 4096 envs per GPU (weak
+scaling: every rank owns its own 4096 envs; no data-path collective, one NCCL
+all_reduce of the 4 episode statistics at the end of the timed region).
+
+Prints ONE JSON line (see the contract in the task statement).  `--impl
+reference` times the CPU oracle port of the same path on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'batched env-steps/sec incl. 64x64 RGB render'
+UNIT = 'env-steps/s'
+
+# algorithmic bytes per env-step
+#   B = S*(32 R + 32 W dynamic + 32 R static) + 8 (action) + 12 (reward, step_type, discount) + H*W*3
+ALGO_BYTES = {
+    'falling_balls20': dict(state=24 * 96 + 20, frame=64 * 64 * 3),
+    'synthetic32': dict(state=32 * 96 + 20, frame=64 * 64 * 3),
+}
+
+
+def _scene_config(scene):
+    import moog_b200  # noqa: F401  (puts the MOOG-compatible `moog` package on sys.path)
+    import importlib
+    mod = importlib.import_module('moog_b200.configs.' + scene)
+    return mod.get_config()
+
+
+def _host_states(config, n, seed):
+    np.random.seed(seed)
+    return [config['state_initializer']() for _ in range(n)]
+
+
+def _json_default(o):
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    raise TypeError(type(o).__name__)
+
+
+def _peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured'
+    except Exception:  # pylint: disable=broad-except
+        return 6650.0, 'fallback'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # pylint: disable=broad-except
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # pylint: disable=broad-except
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(np.max(mx)) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------
+
+def cpu_oracle_throughput(scene, envs_per_thread, steps, threads, seed=1234):
+    """env-steps/s (incl. render) of oracle/ on `threads` host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle, lib as orc_lib
+    orc_lib()
+    config = _scene_config(scene)
+    states = _host_states(config, max(8, min(64, envs_per_thread)), seed)
+    prog = compiler.compile_config(config, states)
+    base = compiler.pack_states(prog, states)
+    oracles = []
+    for t in range(threads):
+        idx = np.arange(envs_per_thread) % len(states)
+        arr = {k: np.ascontiguousarray(base[k][idx]) for k in ('dyn', 'stat', 'meta', 'cnt', 'envi', 'envf', 'vtx')}
+        o = Oracle(prog, arr)
+        o.post_reset()
+        oracles.append(o)
+    ad = max(prog.action_dim, 1)
+    actions = np.zeros((envs_per_thread, ad))
+    render = prog.render is not None
+
+    def work(o):
+        for _ in range(steps):
+            o.step(actions)
+            if render:
+                o.render()
+        return True
+
+    for o in oracles:   # warm-up: one step each
+        o.step(actions)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, oracles))
+    dt = time.perf_counter() - t0
+    total = threads * envs_per_thread * steps
+    return total / dt, dt, total
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_thread = 16
+    # ~0.4 s of CPU work per thread per step of the sample
+    vals = []
+    for _ in range(args.warmup):
+        cpu_oracle_throughput(args.scene, per_thread, 1, cores)
+    t0 = time.perf_counter()
+    total_steps = 0
+    for _ in range(args.steps):
+        v, dt, n = cpu_oracle_throughput(args.scene, per_thread, 2, cores)
+        vals.append(v)
+        total_steps += n
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = '{} threads x {} envs x 2 env-steps per timed step of {} (oracle/moog_oracle.c + pil_oracle.c)'.format(
+        cores, per_thread, args.scene)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * wall / max(args.steps, 1), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.scene, 'envs_per_gpu': args.envs, 'image': '64x64x3',
+                   'note': 'CPU oracle port of Environment.step + PILRenderer on all host threads'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from moog_b200 import capi
+    from moog_b200.batched_env import BatchedEnvironment
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    config = _scene_config(args.scene)
+    E = args.envs
+    seed = 1234 + 1000 * rank
+    states = _host_states(config, args.pool, seed)
+    env = BatchedEnvironment(**config, num_envs=E, device=dev, seed=seed, initial_states=states)
+    eng = env.engine
+    prog = env.program
+    ad = env.action_dim
+    H, W = prog.render['height'], prog.render['width']
+
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    host_actions = torch.randint(0, 5, (E, ad), generator=g).to(torch.float64).pin_memory()
+    dev_actions = host_actions.to(dev)
+    host_frames = torch.empty((E, H, W, 3), dtype=torch.uint8).pin_memory()
+    host_reward = torch.empty(E, dtype=torch.float32).pin_memory()
+    host_step_type = torch.empty(E, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    env.reset()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident arm ------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.env_step(dev_actions)
+        eng.render()
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = capi.launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 255)          # evict L2 between timed iterations (untimed)
+        ev[k][0].record()
+        eng.env_step(dev_actions)
+        ev[k][1].record()
+        eng.render()
+        ev[k][2].record()
+    stats = env.episode_stats(reduce=True)   # the only collective: 4 doubles
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_step_k = [ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]
+    ms_rend_k = [ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]
+    ms_total = float(np.sum(ms_step_k) + np.sum(ms_rend_k))
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    value = world * E * args.steps / (ms_total_max * 1e-3)
+
+    # ---- end-to-end arm: host actions in, host TimeStep (frames included) out --
+    for _ in range(2):
+        ts = env.step(host_actions)
+    torch.cuda.synchronize()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        ts = env.step(host_actions)                       # H2D of the actions inside
+        host_frames.copy_(ts.observation['image'], non_blocking=True)
+        host_reward.copy_(ts.reward, non_blocking=True)
+        host_step_type.copy_(ts.step_type, non_blocking=True)
+        torch.cuda.current_stream().synchronize()         # the caller owns the TimeStep now
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * args.steps / (float(te.item()) * 1e-3)
+    h2d = host_actions.numel() * host_actions.element_size()
+    d2h = host_frames.numel() + host_reward.numel() * 4 + host_step_type.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = _peaks()
+    ab = ALGO_BYTES.get(args.scene, dict(state=prog.n_slots * 96 + 20, frame=H * W * 3))
+    step_ms = float(np.mean(ms_step_k))
+    rend_ms = float(np.mean(ms_rend_k))
+    step_gbs = E * ab['state'] / (step_ms * 1e-3) / 1e9
+    rend_gbs = E * (ab['frame'] + prog.n_slots * 32) / (rend_ms * 1e-3) / 1e9
+    record_bytes = eng.state.nbytes() // E
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_total_max / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.scene, 'envs_per_gpu': E, 'sprites': prog.n_slots,
+                   'substeps': prog.K, 'image': '{}x{}x3'.format(H, W), 'parallelism': 'env-sharded x{}'.format(world),
+                   'l2': 'flushed between timed iterations (256 MiB fill, untimed)',
+                   'state_record_bytes': int(record_bytes)},
+        'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
+                     'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_env_step': ab['state'], 'kernel_ms': step_ms,
+                     'render_kernel': {'kernel': 'moog_render_kernel', 'achieved': rend_gbs, 'frac': rend_gbs / peak,
+                                       'algorithmic_bytes_per_env_step': ab['frame'] + prog.n_slots * 32,
+                                       'kernel_ms': rend_ms},
+                     'share_of_step': {'moog_step_kernel': step_ms / (step_ms + rend_ms),
+                                       'moog_render_kernel': rend_ms / (step_ms + rend_ms)}},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'episode_stats': [float(x) for x in stats.tolist()],
+        'wall_s_timed_region': t_wall,
+    }
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, dt, n = cpu_oracle_throughput(args.scene, 16, 4, cores)
+        line['cpu_baseline'] = {
+            'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '{} env-steps of {} (16 envs x 4 steps per thread, {} threads, {:.1f} s)'.format(
+                n, args.scene, cores, dt)}
+    print(json.dumps(line, default=_json_default))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scene', default='falling_balls20')
+    ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
+    ap.add_argument('--pool', type=int, default=128, help='host-generated initial states')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

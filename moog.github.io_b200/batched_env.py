@@ -1,0 +1,326 @@
+"""BatchedEnvironment: N independent MOOG environments stepped on one B200.
+
+Mirrors `moog.environment.Environment` (reference moog/environment.py:28-131):
+same constructor arguments -- so `BatchedEnvironment(**get_config(level),
+num_envs=N)` works on an unchanged MOOG config -- and the same `reset()` /
+`step(action)` / `observation()` protocol, with every TimeStep field batched:
+
+    step_type   int32  [N]   0 FIRST, 1 MID, 2 LAST        (dm_env.StepType)
+    reward      float32[N]   NaN on FIRST steps            (dm_env: None)
+    discount    float32[N]   1 mid, 0 last, NaN first
+    observation {'image': uint8 [N, H, W, 3]}              (PILRenderer)
+
+An env whose previous step returned LAST is reset by the next `step()` call and
+ignores that call's action (environment.py:100-101).  Initial states come from
+a pool produced by the config's own `state_initializer` on the host and kept
+on the device; which pool entry a resetting env receives is drawn on the device.
+
+PyTorch is used for device memory and streams only.  All arithmetic happens in
+libmoog_b200.so (include/moog_b200.h); there is no fallback path.
+"""
+import collections
+import ctypes
+
+import numpy as np
+import torch
+
+from . import capi
+from . import compiler
+
+TimeStep = collections.namedtuple(
+    'TimeStep', ['step_type', 'reward', 'discount', 'observation'])
+
+STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
+
+_ERR_TEXT = {
+    1: 'ValueError: collision normal is not a unit vector (collisions.py:323-326)',
+    2: 'RuntimeError: _position_correction would not terminate (collisions.py:740)',
+    4: 'ValueError: TetherZippedLayers layers differ in length (tether_physics.py:192-196)',
+    8: 'RuntimeError: layer capacity exceeded',
+}
+
+_STATE_DTYPES = dict(dyn=torch.float64, stat=torch.float64, meta=torch.int32,
+                     cnt=torch.int32, envi=torch.int32, envf=torch.float64,
+                     vtx=torch.float64)
+
+
+class DeviceState(object):
+    """The SoA state record of n envs as torch tensors on one device."""
+
+    KEYS = ('dyn', 'stat', 'meta', 'cnt', 'envi', 'envf', 'vtx')
+
+    def __init__(self, program, n, device):
+        S, VT = program.n_slots, max(program.n_vtx, 1)
+        self.n = n
+        self.device = torch.device(device)
+        z = lambda shape, k: torch.zeros(shape, dtype=_STATE_DTYPES[k], device=self.device)
+        self.dyn = z((n, compiler.DYN_FIELDS, S), 'dyn')
+        self.stat = z((n, compiler.STAT_FIELDS, S), 'stat')
+        self.meta = z((n, compiler.META_FIELDS, S), 'meta')
+        self.cnt = z((n, compiler.MAX_LAYERS), 'cnt')
+        self.envi = z((n, compiler.ENVI_WORDS), 'envi')
+        self.envf = z((n, max(program.n_envf, 1)), 'envf')
+        self.vtx = z((n, VT, 2), 'vtx')
+
+    def upload(self, arrays, rows=None):
+        """arrays: dict from compiler.pack_states (numpy); rows: env indices."""
+        for k in self.KEYS:
+            src = torch.from_numpy(np.ascontiguousarray(arrays[k])).to(
+                self.device, dtype=_STATE_DTYPES[k])
+            dst = getattr(self, k)
+            if rows is None:
+                if src.shape != dst.shape:
+                    raise ValueError('{}: shape {} != {}'.format(k, tuple(src.shape), tuple(dst.shape)))
+                dst.copy_(src)
+            else:
+                dst[rows] = src
+
+    def download(self):
+        return {k: getattr(self, k).cpu().numpy() for k in self.KEYS}
+
+    def clone(self):
+        out = object.__new__(DeviceState)
+        out.n, out.device = self.n, self.device
+        for k in self.KEYS:
+            setattr(out, k, getattr(self, k).clone())
+        return out
+
+    def copy_from(self, other):
+        for k in self.KEYS:
+            getattr(self, k).copy_(getattr(other, k))
+
+    def struct(self):
+        return capi.MoogState(*[getattr(self, k).data_ptr() for k in self.KEYS])
+
+    def nbytes(self):
+        return sum(getattr(self, k).numel() * getattr(self, k).element_size() for k in self.KEYS)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Engine(object):
+    """Program + state + the raw C-ABI calls (used by BatchedEnvironment and
+    directly by the parity tests / bench)."""
+
+    def __init__(self, program, num_envs, device='cuda', seed=0):
+        if not torch.cuda.is_available():
+            raise capi.MoogError('moog_b200 needs a CUDA device; there is no CPU path')
+        self.program = program
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise capi.MoogError('device must be a CUDA device')
+        self.n = int(num_envs)
+        self.seed = int(seed)
+        with torch.cuda.device(self.device):
+            self.dev_program = capi.DeviceProgram(program.blob)
+        self.state = DeviceState(program, self.n, self.device)
+        self.pool = None
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.reward = torch.zeros(self.n, **f32)
+        self.discount = torch.zeros(self.n, **f32)
+        self.step_type = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        self.counters = torch.zeros((self.n, 4), dtype=torch.int64, device=self.device)
+        self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.frames = None
+        if program.render is not None:
+            r = program.render
+            self.frames = torch.zeros((self.n, r['height'], r['width'], 3),
+                                      dtype=torch.uint8, device=self.device)
+        self._calls = 0
+
+    # -- helpers -----------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_pool(self, arrays):
+        n = arrays['dyn'].shape[0]
+        self.pool = DeviceState(self.program, n, self.device)
+        self.pool.upload(arrays)
+
+    def _as_f64(self, x, width):
+        if x is None:
+            return None
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x))
+        x = x.to(self.device, dtype=torch.float64, non_blocking=True).reshape(self.n, -1)
+        if x.shape[1] != width:
+            raise ValueError('expected [{}, {}], got {}'.format(self.n, width, tuple(x.shape)))
+        return x.contiguous()
+
+    # -- C-ABI calls ---------------------------------------------------------
+    def post_reset(self, rule_noise=None):
+        rn = self._as_f64(rule_noise, self.program.rule_noise_dim) if rule_noise is not None else None
+        st = self.state.struct()
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib().moog_env_post_reset(
+                self.dev_program.handle, ctypes.byref(st), self.n, _ptr(rn), self._stream()))
+
+    def env_step(self, actions=None, noise=None, rule_noise=None, auto_reset=True,
+                 reset_index=None, want_counters=False):
+        p = self.program
+        act = self._as_f64(actions, max(p.action_dim, 1)) if actions is not None else None
+        nz = self._as_f64(noise, p.K * p.noise_dim) if (noise is not None and p.noise_dim) else None
+        rn = self._as_f64(rule_noise, p.rule_noise_dim) if (
+            rule_noise is not None and p.rule_noise_dim) else None
+        ri = None
+        if reset_index is not None:
+            ri = torch.as_tensor(reset_index).to(self.device, dtype=torch.int32).contiguous()
+        io = capi.MoogStepIO()
+        io.actions, io.noise, io.rule_noise = _ptr(act), _ptr(nz), _ptr(rn)
+        pool_struct = None
+        if auto_reset and self.pool is not None:
+            pool_struct = self.pool.struct()
+            io.pool = ctypes.pointer(pool_struct)
+            io.pool_size = self.pool.n
+        io.reset_index = _ptr(ri)
+        io.seed = (self.seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
+        io.reward, io.step_type, io.discount = _ptr(self.reward), _ptr(self.step_type), _ptr(self.discount)
+        io.counters = _ptr(self.counters) if want_counters else None
+        io.stats = _ptr(self.stats)
+        st = self.state.struct()
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib().moog_env_step(
+                self.dev_program.handle, ctypes.byref(st), self.n, ctypes.byref(io), self._stream()))
+        self._calls += 1
+
+    def physics_step(self, noise=None, want_counters=True):
+        p = self.program
+        nz = self._as_f64(noise, p.K * p.noise_dim) if (noise is not None and p.noise_dim) else None
+        st = self.state.struct()
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib().moog_physics_step(
+                self.dev_program.handle, ctypes.byref(st), self.n, _ptr(nz),
+                _ptr(self.counters) if want_counters else None, self._stream()))
+
+    def overlap_pairs(self, layer_a, layer_b):
+        p = self.program
+        la, lb = p.layer_index(layer_a), p.layer_index(layer_b)
+        out = torch.zeros((self.n, p.layer_cap[la], p.layer_cap[lb]), dtype=torch.uint8, device=self.device)
+        st = self.state.struct()
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib().moog_overlap_pairs(
+                self.dev_program.handle, ctypes.byref(st), self.n, la, lb, _ptr(out), self._stream()))
+        return out
+
+    def render(self, out=None):
+        if self.frames is None:
+            raise capi.MoogError('the program has no PILRenderer observer')
+        out = self.frames if out is None else out
+        st = self.state.struct()
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib().moog_render(
+                self.dev_program.handle, ctypes.byref(st), self.n, _ptr(out), self._stream()))
+        return out
+
+
+class BatchedEnvironment(object):
+    """See module docstring.  Reference: moog/environment.py:28-131."""
+
+    def __init__(self, state_initializer, physics, task, action_space, observers,
+                 game_rules=(), meta_state_initializer=None, *, num_envs,
+                 device='cuda', pool_size=None, seed=0, layer_capacity=None,
+                 initial_states=None):
+        if meta_state_initializer is not None and meta_state_initializer() is not None:
+            raise compiler.CompileError(
+                'meta_state is an arbitrary Python object in MOOG; the device '
+                'path supports configs whose meta_state is None')
+        self.state_initializer = state_initializer
+        self.num_envs = int(num_envs)
+        config = dict(state_initializer=state_initializer, physics=physics, task=task,
+                      action_space=action_space, observers=observers, game_rules=game_rules)
+        if initial_states is None:
+            pool_size = int(pool_size or min(self.num_envs, 256))
+            initial_states = [state_initializer() for _ in range(pool_size)]
+        self.program = compiler.compile_config(config, initial_states, layer_capacity)
+        self._pool_arrays = compiler.pack_states(self.program, initial_states)
+        self.engine = Engine(self.program, self.num_envs, device, seed)
+        self.engine.set_pool(self._pool_arrays)
+        self.action_space = action_space
+        self.observers = observers
+        self._image_key = None
+        for k, obs in (observers or {}).items():
+            if type(obs).__name__ == 'PILRenderer':
+                self._image_key = k
+        self._rng = np.random.RandomState(seed)
+        self._started = False
+
+    # -- dm_env-like protocol -------------------------------------------------
+    def reset(self):
+        """environment.py:82-96 for every env."""
+        e = self.engine
+        idx = torch.from_numpy(self._rng.randint(0, e.pool.n, size=self.num_envs)).to(e.device)
+        for k in DeviceState.KEYS:
+            if k == 'envi':
+                e.state.envi.zero_()
+            else:
+                getattr(e.state, k).copy_(getattr(e.pool, k).index_select(0, idx))
+        e.post_reset()
+        e.step_type.fill_(STEP_FIRST)
+        e.reward.fill_(float('nan'))
+        e.discount.fill_(float('nan'))
+        self._started = True
+        return self._timestep()
+
+    def step(self, action=None):
+        """environment.py:98-126 for every env; `action` is [N, action_dim]
+        (Joystick: 2 floats, Grid: 1 index; Composite: dict of those or the
+        concatenation in the order of `program.action_layout`)."""
+        if not self._started:
+            return self.reset()
+        self.engine.env_step(self._flatten_action(action))
+        return self._timestep()
+
+    def observation(self):
+        obs = {}
+        if self._image_key is not None:
+            obs[self._image_key] = self.engine.render()
+        return obs
+
+    def _timestep(self):
+        e = self.engine
+        return TimeStep(e.step_type, e.reward, e.discount, self.observation())
+
+    def _flatten_action(self, action):
+        if action is None:
+            return None
+        if isinstance(action, dict):
+            cols = []
+            for key, _, _, width in self.program.action_layout:
+                a = action[key]
+                a = a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a))
+                cols.append(a.to(self.engine.device, dtype=torch.float64).reshape(self.num_envs, width))
+            return torch.cat(cols, dim=1)
+        return action
+
+    # -- extras -----------------------------------------------------------------
+    def raise_errors(self):
+        """Raises the data-dependent exceptions the reference would have raised."""
+        err = self.engine.state.envi[:, 2]  # MOOG_EI_ERR
+        bad = torch.nonzero(err).flatten()
+        if bad.numel():
+            i = int(bad[0])
+            code = int(err[i])
+            text = '; '.join(t for b, t in _ERR_TEXT.items() if code & b)
+            raise ValueError('env {}: {}'.format(i, text))
+
+    def state_dict(self):
+        """Snapshot (cf. SimulationEnvironment, env_wrappers/simulation.py:55-83)."""
+        return {k: getattr(self.engine.state, k).clone() for k in DeviceState.KEYS}
+
+    def load_state_dict(self, sd):
+        for k in DeviceState.KEYS:
+            getattr(self.engine.state, k).copy_(sd[k])
+
+    def episode_stats(self, reduce=True):
+        """[sum reward, sum finished-episode length, finished episodes, env-steps];
+        summed over ranks with one NCCL all_reduce when torch.distributed is up."""
+        s = self.engine.stats.clone()
+        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(s)
+        return s
+
+    @property
+    def action_dim(self):
+        return max(self.program.action_dim, 1)

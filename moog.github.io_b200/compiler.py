@@ -574,8 +574,8 @@ def compile_config(config, sample_states, layer_capacity=None):
             for name in prog.layer_names]
     for name, cap in (layer_capacity or {}).items():
         caps[prog.layer_index(name)] = max(cap, caps[prog.layer_index(name)])
-    prog.layer_cap = caps
-    prog.layer_off = [0] + list(np.cumsum(caps))
+    prog.layer_cap = [int(c) for c in caps]
+    prog.layer_off = [0] + [int(v) for v in np.cumsum(caps)]
     if prog.n_slots > MAX_SLOTS:
         raise CompileError('at most {} sprites per env'.format(MAX_SLOTS))
     vcap = []

@@ -1,0 +1,149 @@
+// moog_capi.cu -- the extern "C" boundary declared in include/moog_b200.h.
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "moog_common.cuh"
+
+struct moog_program {
+  void *dev_blob;
+  size_t nbytes;
+  int32_t hdr[MOOG_HDR_WORDS];
+};
+
+namespace {
+std::atomic<int64_t> g_launches{0};
+thread_local std::string g_cuda_error;
+
+int cuda_fail(cudaError_t err) {
+  g_cuda_error = cudaGetErrorString(err);
+  return MOOG_E_CUDA;
+}
+
+bool valid_state(const moog_state *st) {
+  return st && st->dyn && st->stat && st->meta && st->cnt && st->envi && st->envf && st->vtx;
+}
+}  // namespace
+
+extern "C" {
+
+int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
+  if (!blob || !out || nbytes < sizeof(int32_t) * MOOG_HDR_WORDS) return MOOG_E_INVAL;
+  const int32_t *hdr = (const int32_t *)blob;
+  if ((uint32_t)hdr[MOOG_H_MAGIC] != MOOG_MAGIC || hdr[MOOG_H_VERSION] != MOOG_VERSION) return MOOG_E_INVAL;
+  if ((size_t)hdr[MOOG_H_BYTES] != nbytes) return MOOG_E_INVAL;
+  if (hdr[MOOG_H_N_SLOTS] < 0 || hdr[MOOG_H_N_SLOTS] > MOOG_MAX_SLOTS || hdr[MOOG_H_N_LAYERS] > MOOG_MAX_LAYERS ||
+      hdr[MOOG_H_K] < 1)
+    return MOOG_E_INVAL;
+  size_t need = sizeof(int32_t) * MOOG_HDR_WORDS + sizeof(moog_op) * (size_t)hdr[MOOG_H_N_OPS] +
+                sizeof(int32_t) * (size_t)((hdr[MOOG_H_N_IPOOL] + 1) & ~1) + sizeof(moog_ex) * (size_t)hdr[MOOG_H_N_EXPR];
+  if (need != nbytes) return MOOG_E_INVAL;
+  if (moog::env_smem_bytes(hdr) > 220 * 1024) return MOOG_E_TOO_BIG;
+  moog_program *p = (moog_program *)calloc(1, sizeof(moog_program));
+  if (!p) return MOOG_E_INVAL;
+  memcpy(p->hdr, hdr, sizeof(p->hdr));
+  p->nbytes = nbytes;
+  cudaError_t err = cudaMalloc(&p->dev_blob, nbytes);
+  if (err == cudaSuccess) err = cudaMemcpy(p->dev_blob, blob, nbytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    if (p->dev_blob) cudaFree(p->dev_blob);
+    free(p);
+    return cuda_fail(err);
+  }
+  *out = p;
+  return 0;
+}
+
+void moog_program_destroy(moog_program *p) {
+  if (!p) return;
+  if (p->dev_blob) cudaFree(p->dev_blob);
+  free(p);
+}
+
+int moog_program_env_smem_bytes(const moog_program *p) { return p ? moog::env_smem_bytes(p->hdr) : MOOG_E_INVAL; }
+
+static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode, const moog_step_io *io,
+                    int layer_a, int layer_b, uint8_t *overlap_out, void *stream) {
+  if (!p || !valid_state(st) || n_envs < 0) return MOOG_E_INVAL;
+  moog::StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = p->dev_blob;
+  a.st = *st;
+  a.n_envs = n_envs;
+  a.mode = mode;
+  if (io) a.io = *io;
+  if (a.io.pool) {
+    if (!valid_state(a.io.pool) || a.io.pool_size <= 0) return MOOG_E_INVAL;
+    a.pool = *a.io.pool;
+  }
+  a.layer_a = layer_a;
+  a.layer_b = layer_b;
+  a.overlap_out = overlap_out;
+  int launches = 0;
+  cudaError_t err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches);
+  g_launches += launches;
+  return err == cudaSuccess ? 0 : cuda_fail(err);
+}
+
+int moog_env_step(moog_program *p, const moog_state *st, int n_envs, const moog_step_io *io, void *stream) {
+  return run_step(p, st, n_envs, moog::MODE_ENV_STEP, io, 0, 0, nullptr, stream);
+}
+
+int moog_env_post_reset(moog_program *p, const moog_state *st, int n_envs, const double *rule_noise,
+                        void *stream) {
+  moog_step_io io;
+  memset(&io, 0, sizeof(io));
+  io.rule_noise = rule_noise;
+  return run_step(p, st, n_envs, moog::MODE_POST_RESET, &io, 0, 0, nullptr, stream);
+}
+
+int moog_physics_step(moog_program *p, const moog_state *st, int n_envs, const double *noise, int64_t *counters,
+                      void *stream) {
+  moog_step_io io;
+  memset(&io, 0, sizeof(io));
+  io.noise = noise;
+  io.counters = counters;
+  return run_step(p, st, n_envs, moog::MODE_PHYSICS, &io, 0, 0, nullptr, stream);
+}
+
+int moog_overlap_pairs(moog_program *p, const moog_state *st, int n_envs, int layer_a, int layer_b, uint8_t *out,
+                       void *stream) {
+  if (!p || !out) return MOOG_E_INVAL;
+  int L = p->hdr[MOOG_H_N_LAYERS];
+  if (layer_a < 0 || layer_a >= L || layer_b < 0 || layer_b >= L) return MOOG_E_INVAL;
+  return run_step(p, st, n_envs, moog::MODE_OVERLAP, nullptr, layer_a, layer_b, out, stream);
+}
+
+int moog_render(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream) {
+  if (!p || !valid_state(st) || !frames || n_envs < 0) return MOOG_E_INVAL;
+  if (!p->hdr[MOOG_H_R_ENABLED]) return MOOG_E_INVAL;
+  if (p->hdr[MOOG_H_R_AA] != 1 || p->hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS) return MOOG_E_UNSUPPORTED;
+  moog::RenderArgs a;
+  a.blob = p->dev_blob;
+  a.st = *st;
+  a.n_envs = n_envs;
+  a.frames = frames;
+  int launches = 0;
+  cudaError_t err = moog::launch_render(a, p->hdr, (cudaStream_t)stream, &launches);
+  g_launches += launches;
+  return err == cudaSuccess ? 0 : cuda_fail(err);
+}
+
+const char *moog_strerror(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case MOOG_E_INVAL: return "invalid argument or malformed program blob";
+    case MOOG_E_CUDA: return "CUDA runtime error";
+    case MOOG_E_TOO_BIG: return "one env record does not fit in shared memory";
+    case MOOG_E_UNSUPPORTED: return "configuration not supported by the device path yet";
+  }
+  return "unknown error";
+}
+
+const char *moog_last_cuda_error(void) { return g_cuda_error.c_str(); }
+
+int64_t moog_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

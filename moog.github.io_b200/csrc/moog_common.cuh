@@ -1,0 +1,56 @@
+// moog_common.cuh -- shared declarations of the libmoog_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/moog_b200.h"
+
+namespace moog {
+
+// Parsed view of a program blob (pointers may be host or device).
+struct ProgramView {
+  const int32_t *hdr;
+  const moog_op *ops;
+  const int32_t *ipool;
+  const moog_ex *expr;
+  const int32_t *voff;
+};
+
+__host__ __device__ inline ProgramView view_of(const void *blob) {
+  ProgramView v;
+  v.hdr = (const int32_t *)blob;
+  v.ops = (const moog_op *)(v.hdr + MOOG_HDR_WORDS);
+  v.ipool = (const int32_t *)(v.ops + v.hdr[MOOG_H_N_OPS]);
+  int npool = (v.hdr[MOOG_H_N_IPOOL] + 1) & ~1;
+  v.expr = (const moog_ex *)(v.ipool + npool);
+  v.voff = v.ipool + v.hdr[MOOG_H_VOFF];
+  return v;
+}
+
+enum StepMode { MODE_ENV_STEP = 0, MODE_PHYSICS = 1, MODE_POST_RESET = 2, MODE_OVERLAP = 3 };
+
+struct StepArgs {
+  const void *blob;  // device copy of the program
+  moog_state st;
+  int n_envs;
+  int mode;
+  moog_step_io io;
+  moog_state pool;  // valid iff io.pool != nullptr
+  // MODE_OVERLAP
+  int layer_a, layer_b;
+  uint8_t *overlap_out;
+};
+
+struct RenderArgs {
+  const void *blob;
+  moog_state st;
+  int n_envs;
+  uint8_t *frames;
+};
+
+// host-side launchers (defined in the .cu files)
+int env_smem_bytes(const int32_t *hdr);
+cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
+cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
+
+}  // namespace moog

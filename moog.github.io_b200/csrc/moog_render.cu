@@ -1,0 +1,358 @@
+// moog_render.cu -- PILRenderer.__call__ for N envs (moog/observers/pil_renderer.py:88-120).
+//
+// The reference pastes a background, then for every layer and sprite (z-order,
+// back to front) calls Pillow's ImageDraw.polygon with an RGBA fill on an RGB
+// canvas, resizes (identity for anti_aliasing=1, which every shipped config
+// uses) and flips the rows.  Pillow's fill (src/libImaging/Draw.c,
+// polygon_generic + hline32rgba) is an integer-scanline algorithm: vertices are
+// truncated to int, every scanline collects the float32 x of the edges it
+// touches (non-fused (y-y0)*dx + x0), sorts them and blends the spans; rows never
+// interact.  So: one thread per scanline, one canvas per env in shared memory
+// (packed RGBX words, row stride W+1 -> conflict-free), sprites walked in
+// z-order by every row thread, and the finished canvas is written to HBM once,
+// flipped, as coalesced 16-byte stores.
+#include <math.h>
+
+#include "moog_common.cuh"
+
+namespace moog {
+
+#define MAXV MOOG_MAX_VERTS
+#define MAX_XX (2 * MAXV + 8)
+
+__device__ __forceinline__ unsigned div255(unsigned a) { return (((a + 128) >> 8) + (a + 128)) >> 8; }
+
+__device__ __forceinline__ unsigned blend_px(unsigned bg, unsigned ink) {
+  unsigned a = ink >> 24;
+  unsigned r = div255((bg & 255) * (255 - a) + (ink & 255) * a);
+  unsigned g = div255(((bg >> 8) & 255) * (255 - a) + ((ink >> 8) & 255) * a);
+  unsigned b = div255(((bg >> 16) & 255) * (255 - a) + ((ink >> 16) & 255) * a);
+  return r | (g << 8) | (b << 16);
+}
+
+// Draw.c hline32rgba for the row this thread owns (y is already known to be in range)
+__device__ __forceinline__ void hline(unsigned *row, int W, int x0, int x1, unsigned ink) {
+  if (x0 < 0) x0 = 0; else if (x0 >= W) return;
+  if (x1 < 0) return; else if (x1 >= W) x1 = W - 1;
+  for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], ink);
+}
+
+__device__ __forceinline__ int round_up_(float f) { return (int)(f >= 0.0f ? floorf(f + 0.5f) : -floorf(fabsf(f) + 0.5f)); }
+__device__ __forceinline__ int round_down_(float f) { return (int)(f >= 0.0f ? ceilf(f - 0.5f) : -ceilf(fabsf(f) - 0.5f)); }
+
+// Draw.c: (y - e->y0) * e->dx + e->x0, float32, no fused multiply-add
+__device__ __forceinline__ float edge_x(int x0, int y0, float dx, int y) {
+  return __fadd_rn(__fmul_rn((float)(y - y0), dx), (float)x0);
+}
+
+struct PEdge { int x0, y0, ymin, ymax; float dx; };
+
+__device__ __forceinline__ PEdge make_edge(int2 a, int2 b) {
+  PEdge e;
+  e.x0 = a.x; e.y0 = a.y;
+  e.ymin = min(a.y, b.y); e.ymax = max(a.y, b.y);
+  e.dx = (a.y == b.y) ? 0.0f : __fdiv_rn((float)(b.x - a.x), (float)(b.y - a.y));
+  return e;
+}
+
+// Draw.c draw_horizontal_lines for row y: walks the edge list ImagingDrawPolygon
+// would have built (consecutive collinear horizontal edges merged) in order.
+__device__ inline void draw_horizontal_lines(const int2 *xy, int count, bool closing, int y, int *x_pos,
+                                             unsigned *row, int W, bool row_visible, unsigned ink) {
+  bool pend = false;
+  int pmin = 0, pmax = 0;
+#define MOOG_FLUSH_PENDING()                                        \
+  if (pend) {                                                       \
+    pend = false;                                                   \
+    int xmin_ = pmin, xmax_ = pmax;                                 \
+    bool skip_ = (*x_pos != -1 && *x_pos < xmin_);                  \
+    if (!skip_ && *x_pos > xmin_) {                                 \
+      xmin_ = *x_pos;                                               \
+      if (xmax_ < xmin_) skip_ = true;                              \
+    }                                                               \
+    if (!skip_) {                                                   \
+      if (row_visible && xmin_ <= xmax_) hline(row, W, xmin_, xmax_, ink); \
+      *x_pos = xmax_ + 1;                                           \
+    }                                                               \
+  }
+  for (int i = 0; i < count - 1; ++i) {
+    int2 a = xy[i], b = xy[i + 1];
+    if (a.y == b.y && i != 0 && a.y == xy[i - 1].y) {
+      int xp = xy[i - 1].x;
+      if (b.x > a.x && a.x > xp) {
+        if (pend) pmax = b.x;
+        continue;
+      } else if (b.x < a.x && a.x < xp) {
+        if (pend) pmin = b.x;
+        continue;
+      }
+    }
+    MOOG_FLUSH_PENDING();
+    if (a.y == b.y && a.y == y) {
+      pend = true;
+      pmin = min(a.x, b.x);
+      pmax = max(a.x, b.x);
+    }
+  }
+  if (closing) {
+    MOOG_FLUSH_PENDING();
+    int2 a = xy[count - 1], b = xy[0];
+    if (a.y == b.y && a.y == y) {
+      pend = true;
+      pmin = min(a.x, b.x);
+      pmax = max(a.x, b.x);
+    }
+  }
+  MOOG_FLUSH_PENDING();
+#undef MOOG_FLUSH_PENDING
+}
+
+// Draw.c polygon_generic, the iteration of its scanline loop for row y.
+// ymax_c = min(polygon ymax, H) as in the reference; row == nullptr-safe via row_visible.
+__device__ inline void polygon_row(const int2 *xy, int count, int y, int ymax_c, bool has_horizontal,
+                                   unsigned *row, int W, bool row_visible, unsigned ink) {
+  float xx[MAX_XX];
+  int j = 0;
+  bool closing = (xy[count - 1].x != xy[0].x) || (xy[count - 1].y != xy[0].y);
+  int n_edges = count - 1 + (closing ? 1 : 0);
+  for (int i = 0; i < n_edges; ++i) {
+    int2 a = xy[i], b = xy[(i + 1 == count) ? 0 : i + 1];
+    if (a.y == b.y) continue;  // horizontal edges are deferred when blending
+    PEdge cur = make_edge(a, b);
+    if (y >= cur.ymin && y <= cur.ymax) {
+      xx[j++] = edge_x(cur.x0, cur.y0, cur.dx, y);
+      if (y == cur.ymax && y < ymax_c) {
+        xx[j] = xx[j - 1];
+        j++;
+      } else if ((y == cur.ymin || y == cur.ymax) && cur.dx != 0) {
+        for (int k = 0; k < i; ++k) {
+          int2 c = xy[k], d = xy[(k + 1 == count) ? 0 : k + 1];
+          if (c.y == d.y) continue;
+          PEdge oth = make_edge(c, d);
+          if ((y != oth.ymin && y != oth.ymax) || oth.dx == 0) continue;
+          if (roundf(xx[j - 1]) == roundf(edge_x(oth.x0, oth.y0, oth.dx, y))) {
+            int off = (y == ymax_c) ? -1 : 1;
+            if (y + off >= oth.ymin && y + off <= oth.ymax) {
+              float adj = edge_x(cur.x0, cur.y0, cur.dx, y + off);
+              float oadj = edge_x(oth.x0, oth.y0, oth.dx, y + off);
+              if (xx[j - 1] > adj + 1 && xx[j - 1] > oadj + 1)
+                xx[j - 1] = roundf(fmaxf(adj, oadj)) + 1;
+              else if (xx[j - 1] < adj - 1 && xx[j - 1] < oadj - 1)
+                xx[j - 1] = roundf(fminf(adj, oadj)) - 1;
+              break;
+            }
+          }
+        }
+      }
+    }
+  }
+  // qsort ascending
+  for (int a = 1; a < j; ++a) {
+    float v = xx[a];
+    int b = a;
+    while (b > 0 && xx[b - 1] > v) {
+      xx[b] = xx[b - 1];
+      --b;
+    }
+    xx[b] = v;
+  }
+  int x_pos = (j == 0) ? -1 : 0;
+  for (int i = 1; i < j; i += 2) {
+    int x_end = round_down_(xx[i]);
+    if (x_end < x_pos) continue;
+    if (has_horizontal) draw_horizontal_lines(xy, count, closing, y, &x_pos, row, W, row_visible, ink);
+    if (x_end < x_pos) continue;
+    int x_start = round_up_(xx[i - 1]);
+    if (x_pos > x_start) {
+      x_start = x_pos;
+      if (x_end < x_start) continue;
+    }
+    if (row_visible && x_start <= x_end) hline(row, W, x_start, x_end, ink);
+    x_pos = x_end + 1;
+  }
+  if (has_horizontal) draw_horizontal_lines(xy, count, closing, y, &x_pos, row, W, row_visible, ink);
+}
+
+// color_maps.py:21-23 (CPython colorsys.hsv_to_rgb, x255, astype(uint8))
+__device__ __forceinline__ unsigned to_u8(double v) { return (unsigned)(unsigned char)(long long)v; }
+
+__device__ inline unsigned color_to_ink(int cmap, double c0, double c1, double c2, double opacity) {
+  unsigned r8, g8, b8;
+  if (cmap != MOOG_CMAP_HSV) {
+    r8 = to_u8(c0); g8 = to_u8(c1); b8 = to_u8(c2);
+  } else {
+    double h = c0, s = c1, v = c2, r, g, b;
+    if (s == 0.0) {
+      r = g = b = v;
+    } else {
+      int i = (int)(h * 6.0);
+      double f = (h * 6.0) - i;
+      double p = v * (1.0 - s);
+      double q = v * (1.0 - s * f);
+      double t = v * (1.0 - s * (1.0 - f));
+      i = ((i % 6) + 6) % 6;
+      switch (i) {
+        case 0: r = v; g = t; b = p; break;
+        case 1: r = q; g = v; b = p; break;
+        case 2: r = p; g = v; b = t; break;
+        case 3: r = p; g = q; b = v; break;
+        case 4: r = t; g = p; b = v; break;
+        default: r = v; g = p; b = q; break;
+      }
+    }
+    r8 = to_u8(255 * r); g8 = to_u8(255 * g); b8 = to_u8(255 * b);
+  }
+  return r8 | (g8 << 8) | (b8 << 16) | (to_u8(opacity) << 24);
+}
+
+struct RenderLayout { int canvas, ivtx, ink, ymin, ymax, horiz, total; };
+
+__host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int VT) {
+  RenderLayout L;
+  int o = 0;
+  L.canvas = o; o += 4 * H * (W + 1);
+  o = (o + 7) & ~7;
+  L.ivtx = o;   o += 8 * VT;
+  L.ink = o;    o += 4 * S;
+  L.ymin = o;   o += 4 * S;
+  L.ymax = o;   o += 4 * S;
+  L.horiz = o;  o += 4 * S;
+  L.total = (o + 15) & ~15;
+  return L;
+}
+
+// blockDim.x = envs_per_block * T, T = threads of one env (>= H, multiple of 32)
+__global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ProgramView pv = view_of(a.blob);
+  const int32_t *hdr = pv.hdr;
+  const int S = hdr[MOOG_H_N_SLOTS], L = hdr[MOOG_H_N_LAYERS], VT = hdr[MOOG_H_N_VTX];
+  const int H = hdr[MOOG_H_R_HEIGHT], W = hdr[MOOG_H_R_WIDTH];
+  const unsigned bgc = (unsigned)hdr[MOOG_H_R_BG] & 0xffffffu;
+  const int cmap = hdr[MOOG_H_R_COLORMAP], pmod = hdr[MOOG_H_R_MODIFIER], pml = hdr[MOOG_H_R_MOD_LAYER];
+  const int g = threadIdx.x / T, t = threadIdx.x - g * T;
+  const int n = blockIdx.x * envs_per_block + g;
+  const bool live = n < a.n_envs;
+  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1);
+  unsigned char *base = smem_raw + (size_t)g * lay.total;
+  unsigned *canvas = (unsigned *)(base + lay.canvas);
+  int2 *ivtx = (int2 *)(base + lay.ivtx);
+  unsigned *ink = (unsigned *)(base + lay.ink);
+  int *symin = (int *)(base + lay.ymin), *symax = (int *)(base + lay.ymax), *shoriz = (int *)(base + lay.horiz);
+  const int stride = W + 1;
+
+  if (live) {
+    const double *dyn = a.st.dyn + (size_t)n * MOOG_DYN_FIELDS * S;
+    const double *stat = a.st.stat + (size_t)n * MOOG_STAT_FIELDS * S;
+    const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
+    const double2 *vtx = (const double2 *)(a.st.vtx + (size_t)n * 2 * VT);
+    for (int i = t; i < H * stride; i += T) canvas[i] = bgc;
+    double ox = 0, oy = 0;
+    if (pmod == MOOG_PMOD_FIRST_PERSON) {  // polygon_modifiers.py:54-63
+      int s = hdr[MOOG_H_LAYER_OFF + pml];
+      ox = 0.5 - dyn[MOOG_D_X * S + s];
+      oy = 0.5 - dyn[MOOG_D_Y * S + s];
+    }
+    // int-truncated canvas vertices (C cast toward zero), per-slot extents and ink
+    for (int v = t; v < VT; v += T) {
+      double2 p = vtx[v];
+      double x = p.x, y = p.y;
+      if (pmod != MOOG_PMOD_NONE) { x = x + ox; y = y + oy; }
+      ivtx[v] = make_int2((int)((double)W * x), (int)((double)H * y));
+    }
+    for (int s = t; s < S; s += T)
+      ink[s] = color_to_ink(cmap, stat[MOOG_S_C0 * S + s], stat[MOOG_S_C1 * S + s], stat[MOOG_S_C2 * S + s],
+                            stat[MOOG_S_OPACITY * S + s]);
+    (void)meta;
+  }
+  __syncthreads();
+  if (live) {
+    const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
+    for (int s = t; s < S; s += T) {
+      int nv = meta[MOOG_M_NV * S + s];
+      const int2 *xy = ivtx + pv.voff[s];
+      int lo = 0x7fffffff, hi = -0x7fffffff, hz = 0;
+      for (int i = 0; i < nv; ++i) {
+        lo = min(lo, xy[i].y);
+        hi = max(hi, xy[i].y);
+        if (xy[i].y == xy[(i + 1 == nv) ? 0 : i + 1].y) hz = 1;
+      }
+      symin[s] = lo; symax[s] = hi; shoriz[s] = hz;
+    }
+  }
+  __syncthreads();
+  if (live && t < H) {
+    const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
+    const int32_t *cnt = a.st.cnt + (size_t)n * MOOG_MAX_LAYERS;
+    const int y = t;
+    unsigned *row = canvas + y * stride;
+    for (int l = 0; l < L; ++l) {
+      int c = cnt[l];
+      for (int k = 0; k < c; ++k) {
+        int s = hdr[MOOG_H_LAYER_OFF + l] + k;
+        int nv = meta[MOOG_M_NV * S + s];
+        if (nv <= 0) continue;
+        // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H)
+        int ymin_c = max(symin[s], 0), ymax_c = min(symax[s], H);
+        if (y < ymin_c || y > ymax_c) continue;
+        polygon_row(ivtx + pv.voff[s], nv, y, ymax_c, shoriz[s] != 0, row, W, true, ink[s]);
+      }
+    }
+  }
+  __syncthreads();
+  if (live) {
+    // pil_renderer.py:118-120: np.flipud -> output row j is canvas row H-1-j
+    unsigned char *out = a.frames + (size_t)n * H * W * 3;
+    const int nbytes = H * W * 3;
+    if ((nbytes & 15) == 0) {
+      uint4 *out4 = (uint4 *)out;
+      for (int q = t; q < nbytes / 16; q += T) {
+        unsigned w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          unsigned word = 0;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            int b = q * 16 + u * 4 + bb;
+            int p = b / 3, ch = b - 3 * p;
+            int j = p / W, col = p - j * W;
+            unsigned px = canvas[(H - 1 - j) * stride + col];
+            word |= ((px >> (8 * ch)) & 255u) << (8 * bb);
+          }
+          w[u] = word;
+        }
+        out4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      for (int b = t; b < nbytes; b += T) {
+        int p = b / 3, ch = b - 3 * p;
+        int j = p / W, col = p - j * W;
+        out[b] = (unsigned char)((canvas[(H - 1 - j) * stride + col] >> (8 * ch)) & 255u);
+      }
+    }
+  }
+}
+
+cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
+  if (a.n_envs <= 0) return cudaSuccess;
+  int H = hdr[MOOG_H_R_HEIGHT], W = hdr[MOOG_H_R_WIDTH], S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
+  int T = (H + 31) & ~31;
+  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1);
+  int epb = 256 / T;
+  if (epb < 1) epb = 1;
+  while (epb > 1 && (size_t)lay.total * epb > 100 * 1024) --epb;
+  size_t smem = (size_t)lay.total * epb;
+  if (smem > 220 * 1024 || T > 1024) return cudaErrorInvalidConfiguration;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(moog_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  int blocks = (a.n_envs + epb - 1) / epb;
+  moog_render_kernel<<<blocks, epb * T, smem, stream>>>(a, T, epb);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace moog

@@ -1,0 +1,1845 @@
+// moog_step.cu -- one-warp-per-env kernel for MOOG's Environment.step.
+//
+// Reference path (moog/environment.py:98-126): game rules -> action space ->
+// Physics.step (K substeps: forces in itertools.product order, the rotational
+// Collision, corrective physics, Euler integration) -> task reward.
+//
+// Execution model.  One warp owns one env.  The env's whole state record
+// (positions, velocities, the cached world vertices, ...) is staged in shared
+// memory for the duration of the step and written back once, so HBM sees one
+// read and one write of the record per env-step.  Control flow is warp-uniform:
+// every decision is taken on values all 32 lanes agree on (shared-memory reads,
+// ballots, shuffled reductions).  Lanes are spent on the inner dimensions the
+// reference loops over serially inside numpy / matplotlib:
+//   * lane = second sprite of a layer pair      (broad phase, abstract_force loops)
+//   * lane = polygon edge / vertex              (Path.intersects_path, contains_points,
+//                                                segment_crossing_coefficients)
+//   * lane = cached vertex                      (position / angle setters)
+// The ORDER in which sprite pairs are visited is the reference's (physics.py:92-108):
+// a Collision mutates positions and velocities the next pair sees, so pairs are
+// never reordered -- the broad phase of the pairs (i, j0..j31) is evaluated in
+// one shot and re-evaluated after every resolved contact of sprite i.
+//
+// Arithmetic is float64 with the reference's operation order (compiled with
+// -fmad=false; fma() appears only where numpy's BLAS kernels fuse, see
+// oracle/moog_oracle.c), because contact decisions and argmin / argmax ties are
+// decided by the last bit.
+#include <math.h>
+
+#include "moog_common.cuh"
+
+namespace moog {
+
+#define FULL 0xffffffffu
+#define MAXV MOOG_MAX_VERTS
+#define EPS_INTERP 1e-8 /* moog/sprite.py:35 */
+#define EPS_COLL 1e-2   /* moog/physics/collisions.py:46 */
+
+// Padding of the bounding boxes used to skip work whose result is provably
+// "no intersection" ("exact culling").
+#define AABB_PAD 1e-7
+#define SHORT_EDGE2 1e-8
+
+#define SLF_SHORT_EDGE 1  // slot flag: some edge is shorter than 1e-4 -> serial matplotlib path
+
+enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
+
+struct SmemLayout {
+  int dyn, stat, aabb, tmp, vtx, envf, meta, sflag, voff, cnt, envi, vslot, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF) {
+  SmemLayout L;
+  int o = 0;
+  L.dyn = o;   o += 8 * MOOG_DYN_FIELDS * S;
+  L.stat = o;  o += 8 * MOOG_STAT_FIELDS * S;
+  L.aabb = o;  o += 8 * 4 * S;
+  L.tmp = o;   o += 8 * 8 * S;
+  L.vtx = o;   o += 16 * VT;
+  L.envf = o;  o += 8 * NF;
+  L.meta = o;  o += 4 * MOOG_META_FIELDS * S;
+  L.sflag = o; o += 4 * S;
+  L.voff = o;  o += 4 * (S + 1);
+  L.cnt = o;   o += 4 * MOOG_MAX_LAYERS;
+  L.envi = o;  o += 4 * MOOG_ENVI_WORDS;
+  L.vslot = o; o += VT;
+  L.total = (o + 15) & ~15;
+  return L;
+}
+
+int env_smem_bytes(const int32_t *hdr) {
+  return smem_layout(hdr[MOOG_H_N_SLOTS], hdr[MOOG_H_N_VTX] > 0 ? hdr[MOOG_H_N_VTX] : 1, hdr[MOOG_H_N_ENVF]).total;
+}
+
+struct Env {
+  // shared memory
+  double *dyn, *stat, *aabb, *tmp, *envf;
+  double2 *vtx;
+  int *meta, *sflag, *voff, *cnt, *envi;
+  unsigned char *vslot;
+  // program (global memory, read-only)
+  const int32_t *hdr;
+  const moog_op *ops;
+  const int32_t *ipool;
+  const moog_ex *expr;
+  int S, L, K, VT, lane;
+  const double *noise;       // [K][noise_dim] of this env or nullptr
+  const double *rule_noise;  // [rule_noise_dim] of this env or nullptr
+  uint64_t seed;
+  int env_id, substep;
+  long long n_calls, n_true, n_coll;
+  unsigned long long hash;
+};
+
+#define DYN(e, f, s) ((e).dyn[(f) * (e).S + (s)])
+#define STAT(e, f, s) ((e).stat[(f) * (e).S + (s)])
+#define META(e, f, s) ((e).meta[(f) * (e).S + (s)])
+#define BOX(e, f, s) ((e).aabb[(f) * (e).S + (s)])
+#define TMP(e, f, s) ((e).tmp[(f) * (e).S + (s)])
+#define LOFF(e, l) ((e).hdr[MOOG_H_LAYER_OFF + (l)])
+
+__device__ __forceinline__ void wsync() { __syncwarp(); }
+// scalar store by one lane; callers wsync() before anybody reads it back
+__device__ __forceinline__ void put(const Env &e, double *p, double v) {
+  if (e.lane == 0) *p = v;
+}
+__device__ __forceinline__ void puti(const Env &e, int *p, int v) {
+  if (e.lane == 0) *p = v;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shflx_d(double v, int m) { return __shfl_xor_sync(FULL, v, m); }
+
+// ---------------------------------------------------------------------------
+// counter-based RNG (Philox4x32-10) for RandomForce / sample_one when the
+// caller supplies no noise tensor
+// ---------------------------------------------------------------------------
+__device__ inline double philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  uint64_t bits = ((uint64_t)c0 << 21) ^ (uint64_t)(c1 >> 11);  // 53 bits
+  return (double)(bits & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------------------
+// numpy arithmetic conventions (see oracle/moog_oracle.c for the derivation)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double norm_ax(double x, double y) { return sqrt(x * x + y * y); }
+__device__ __forceinline__ double dot2(double ax, double ay, double bx, double by) { return fma(ay, by, ax * bx); }
+__device__ __forceinline__ double norm1(double x, double y) { return sqrt(dot2(x, y, x, y)); }
+__device__ __forceinline__ double f32r(double x) { return (double)(float)x; }
+__device__ __forceinline__ double f32mul(double a, double b) { return (double)__fmul_rn((float)a, (float)b); }
+__device__ __forceinline__ double f32add(double a, double b) { return (double)__fadd_rn((float)a, (float)b); }
+__device__ __forceinline__ double f32sub(double a, double b) { return (double)__fsub_rn((float)a, (float)b); }
+__device__ __forceinline__ double f32div(double a, double b) { return (double)__fdiv_rn((float)a, (float)b); }
+
+__device__ __forceinline__ bool vel32(const Env &e, int s) { return (META(e, MOOG_M_FLAGS, s) & MOOG_SF_VEL32) != 0; }
+__device__ __forceinline__ int angvel_kind(const Env &e, int s) { return (META(e, MOOG_M_FLAGS, s) >> MOOG_SF_ANGVEL_SHIFT) & 3; }
+__device__ __forceinline__ int ang_kind(const Env &e, int s) { return (META(e, MOOG_M_FLAGS, s) >> MOOG_SF_ANG_SHIFT) & 3; }
+__device__ __forceinline__ void set_angvel_kind(const Env &e, int s, int k) {
+  puti(e, &META(e, MOOG_M_FLAGS, s), (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANGVEL_SHIFT)) | (k << MOOG_SF_ANGVEL_SHIFT));
+  wsync();
+}
+
+// `sprite.velocity += dv` (float64 dv; a float32 velocity array keeps its dtype)
+__device__ inline void add_velocity(const Env &e, int s, double dvx, double dvy) {
+  double vx = DYN(e, MOOG_D_VX, s) + dvx, vy = DYN(e, MOOG_D_VY, s) + dvy;
+  if (vel32(e, s)) {
+    vx = f32r(vx);
+    vy = f32r(vy);
+  }
+  wsync();
+  put(e, &DYN(e, MOOG_D_VX, s), vx);
+  put(e, &DYN(e, MOOG_D_VY, s), vy);
+  wsync();
+}
+// `sprite.velocity = value` replaces the array by a float64 one
+__device__ inline void assign_velocity(const Env &e, int s, double vx, double vy) {
+  int fl = META(e, MOOG_M_FLAGS, s) & ~MOOG_SF_VEL32;
+  wsync();
+  put(e, &DYN(e, MOOG_D_VX, s), vx);
+  put(e, &DYN(e, MOOG_D_VY, s), vy);
+  puti(e, &META(e, MOOG_M_FLAGS, s), fl);
+  wsync();
+}
+// `sprite.angle_vel += dw` with an np.float64 dw
+__device__ inline void add_angvel(const Env &e, int s, double dw) {
+  double w = DYN(e, MOOG_D_ANGVEL, s) + dw;
+  int k = angvel_kind(e, s);
+  wsync();
+  if (k == KIND_F32)
+    w = f32r(w);
+  else
+    set_angvel_kind(e, s, KIND_F64);
+  put(e, &DYN(e, MOOG_D_ANGVEL, s), w);
+  wsync();
+}
+__device__ __forceinline__ double scaled_vel(const Env &e, int s, int field, double c, double dt) {
+  double v = DYN(e, field, s);
+  return vel32(e, s) ? f32mul(f32mul(c, v), dt) : c * v * dt;
+}
+__device__ __forceinline__ double scaled_angvel(const Env &e, int s, double c, double dt) {
+  double w = DYN(e, MOOG_D_ANGVEL, s);
+  return angvel_kind(e, s) == KIND_F32 ? f32mul(f32mul(c, w), dt) : c * w * dt;
+}
+__device__ __forceinline__ bool is_symmetric_circle(const Env &e, int s) {
+  return (META(e, MOOG_M_FLAGS, s) & MOOG_SF_CIRCLE) && STAT(e, MOOG_S_ASPECT, s) == 1.0;  // sprite.py:500-502
+}
+__device__ __forceinline__ double moment_of_inertia(const Env &e, int s) {
+  double m = STAT(e, MOOG_S_MASS, s);  // sprite.py:662-664
+  return 0.0 + m * STAT(e, MOOG_S_IX, s) + m * STAT(e, MOOG_S_IY, s);
+}
+
+// ---------------------------------------------------------------------------
+// bounding boxes of the cached outlines
+// ---------------------------------------------------------------------------
+
+// lane-parallel over the vertices of slot s: box + short-edge flag
+__device__ inline void refresh_box(const Env &e, int s) {
+  int n = META(e, MOOG_M_NV, s);
+  const double2 *v = e.vtx + e.voff[s];
+  int i = e.lane < n ? e.lane : 0;
+  double2 p = n > 0 ? v[i] : make_double2(0., 0.);
+  double2 q = n > 0 ? v[(i + 1 == n) ? 0 : i + 1] : p;
+  double len2 = (p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y);
+  bool shortedge = (e.lane < n) && !(len2 > SHORT_EDGE2);
+  double xmin = p.x, xmax = p.x, ymin = p.y, ymax = p.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fmin(xmin, shflx_d(xmin, o));
+    xmax = fmax(xmax, shflx_d(xmax, o));
+    ymin = fmin(ymin, shflx_d(ymin, o));
+    ymax = fmax(ymax, shflx_d(ymax, o));
+  }
+  unsigned sh = __ballot_sync(FULL, shortedge);
+  if (e.lane == 0) {
+    BOX(e, 0, s) = xmin;
+    BOX(e, 1, s) = ymin;
+    BOX(e, 2, s) = xmax;
+    BOX(e, 3, s) = ymax;
+    e.sflag[s] = (sh || n < 3) ? SLF_SHORT_EDGE : 0;
+  }
+  wsync();
+}
+
+// lane = slot: every lane scans its own outline (used at load time)
+__device__ inline void refresh_all_boxes(const Env &e) {
+  for (int s = e.lane; s < e.S; s += 32) {
+    int n = META(e, MOOG_M_NV, s);
+    const double2 *v = e.vtx + e.voff[s];
+    double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    bool sh = n < 3;
+    double2 prev = n > 0 ? v[n - 1] : make_double2(0., 0.);
+    for (int i = 0; i < n; ++i) {
+      double2 p = v[i];
+      xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
+      ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
+      double len2 = (p.x - prev.x) * (p.x - prev.x) + (p.y - prev.y) * (p.y - prev.y);
+      sh |= !(len2 > SHORT_EDGE2);
+      prev = p;
+    }
+    BOX(e, 0, s) = xmin; BOX(e, 1, s) = ymin; BOX(e, 2, s) = xmax; BOX(e, 3, s) = ymax;
+    e.sflag[s] = sh ? SLF_SHORT_EDGE : 0;
+  }
+  wsync();
+}
+
+__device__ __forceinline__ bool boxes_apart(const Env &e, int a, int b) {
+  return BOX(e, 2, a) + AABB_PAD < BOX(e, 0, b) || BOX(e, 2, b) + AABB_PAD < BOX(e, 0, a) ||
+         BOX(e, 3, a) + AABB_PAD < BOX(e, 1, b) || BOX(e, 3, b) + AABB_PAD < BOX(e, 1, a);
+}
+
+// ---------------------------------------------------------------------------
+// position / angle setters (sprite.py:531-540, 616-633): the cached outline is
+// transformed incrementally, exactly like the reference's Sprite._path
+// ---------------------------------------------------------------------------
+__device__ inline void set_position(const Env &e, int s, double nx, double ny) {
+  double tx = nx - DYN(e, MOOG_D_X, s), ty = ny - DYN(e, MOOG_D_Y, s);
+  int n = META(e, MOOG_M_NV, s);
+  double2 *v = e.vtx + e.voff[s];
+  double b0 = BOX(e, 0, s), b1 = BOX(e, 1, s), b2 = BOX(e, 2, s), b3 = BOX(e, 3, s);
+  wsync();
+  if (e.lane < n) {
+    double2 p = v[e.lane];
+    double x = 1.0 * p.x + 0.0 * p.y + tx;
+    double y = 0.0 * p.x + 1.0 * p.y + ty;
+    v[e.lane] = make_double2(x, y);
+  }
+  if (e.lane == 0) {
+    DYN(e, MOOG_D_X, s) = nx;
+    DYN(e, MOOG_D_Y, s) = ny;
+    // x -> fl(x + tx) is monotone, so the translated box is exactly the box of the
+    // translated vertices
+    BOX(e, 0, s) = b0 + tx; BOX(e, 1, s) = b1 + ty; BOX(e, 2, s) = b2 + tx; BOX(e, 3, s) = b3 + ty;
+  }
+  wsync();
+}
+
+struct Aff { double m0, m1, m2, m3, m4, m5; };  // rows 0,1 of the 3x3 (row 2 = 0 0 1)
+
+__device__ __forceinline__ Aff aff_identity() { Aff a = {1., 0., 0., 0., 1., 0.}; return a; }
+__device__ __forceinline__ void aff_translate(Aff &m, double tx, double ty) { m.m2 += tx; m.m5 += ty; }
+__device__ inline void aff_rotate(Aff &m, double theta) {
+  double a = cos(theta), b = sin(theta);
+  double xx = m.m0, xy = m.m1, x0 = m.m2, yx = m.m3, yy = m.m4, y0 = m.m5;
+  m.m0 = a * xx - b * yx; m.m1 = a * xy - b * yy; m.m2 = a * x0 - b * y0;
+  m.m3 = b * xx + a * yx; m.m4 = b * xy + a * yy; m.m5 = b * x0 + a * y0;
+}
+__device__ inline void aff_rotate_around(Aff &m, double x, double y, double theta) {
+  aff_translate(m, -x, -y);
+  aff_rotate(m, theta);
+  aff_translate(m, x, y);
+}
+// out = b . a ("a, then b"); numpy 3x3 matmul fuses: fma(b2,a2, fma(b1,a1, b0*a0)).
+// Row 2 of both is (0,0,1) exactly, so the third term of columns 0,1 is fma(b2, 0, .) = exact.
+__device__ inline Aff aff_then(const Aff &a, const Aff &b) {
+  Aff o;
+  o.m0 = fma(b.m2, 0.0, fma(b.m1, a.m3, b.m0 * a.m0));
+  o.m1 = fma(b.m2, 0.0, fma(b.m1, a.m4, b.m0 * a.m1));
+  o.m2 = fma(b.m2, 1.0, fma(b.m1, a.m5, b.m0 * a.m2));
+  o.m3 = fma(b.m5, 0.0, fma(b.m4, a.m3, b.m3 * a.m0));
+  o.m4 = fma(b.m5, 0.0, fma(b.m4, a.m4, b.m3 * a.m1));
+  o.m5 = fma(b.m5, 1.0, fma(b.m4, a.m5, b.m3 * a.m2));
+  return o;
+}
+
+// ---------------------------------------------------------------------------
+// matplotlib src/_path.h restatement (lane-parallel)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool isclose_(double a, double b) {
+  return fabs(a - b) <= fmax(1e-10 * fmax(fabs(a), fabs(b)), 1e-13);
+}
+
+__device__ inline bool segments_intersect(double x1, double y1, double x2, double y2, double x3, double y3,
+                                          double x4, double y4) {
+  double den = ((y4 - y3) * (x2 - x1)) - ((x4 - x3) * (y2 - y1));
+  if (isclose_(den, 0.0)) {
+    double t_area = (x2 * y3 - x3 * y2) - x1 * (y3 - y2) + y1 * (x3 - x2);
+    if (isclose_(t_area, 0.0)) {
+      if (x1 == x2 && x2 == x3) {
+        return (fmin(y1, y2) <= fmin(y3, y4) && fmin(y3, y4) <= fmax(y1, y2)) ||
+               (fmin(y3, y4) <= fmin(y1, y2) && fmin(y1, y2) <= fmax(y3, y4));
+      }
+      return (fmin(x1, x2) <= fmin(x3, x4) && fmin(x3, x4) <= fmax(x1, x2)) ||
+             (fmin(x3, x4) <= fmin(x1, x2) && fmin(x1, x2) <= fmax(x3, x4));
+    }
+    return false;
+  }
+  double n1 = ((x4 - x3) * (y1 - y3)) - ((y4 - y3) * (x1 - x3));
+  double n2 = ((x2 - x1) * (y1 - y3)) - ((y2 - y1) * (x1 - x3));
+  double u1 = n1 / den;
+  double u2 = n2 / den;
+  return ((u1 > 0.0 || isclose_(u1, 0.0)) && (u1 < 1.0 || isclose_(u1, 1.0)) &&
+          (u2 > 0.0 || isclose_(u2, 0.0)) && (u2 < 1.0 || isclose_(u2, 1.0)));
+}
+
+// point_in_path_impl for one point against the closed outline Q[0..n-1]
+// (the reference passes the V+1 closed path; its extra closing edge has zero
+// length and never toggles).  All lanes walk the edges together.
+__device__ inline bool point_in_poly(double tx, double ty, const double2 *Q, int n) {
+  if (n < 2) return false;  // nv = n + 1 < 3
+  bool finite = isfinite(tx) && isfinite(ty);
+  int inside = 0;
+  double2 p0 = Q[0];
+  for (int k = 0; k < n; ++k) {
+    double2 p1 = Q[(k + 1 == n) ? 0 : k + 1];
+    bool f0 = p0.y >= ty, f1 = p1.y >= ty;
+    if (f0 != f1) {
+      if ((((p1.y - ty) * (p0.x - p1.x)) >= ((p1.x - tx) * (p0.y - p1.y))) == f1) inside ^= 1;
+    }
+    p0 = p1;
+  }
+  return finite && inside;
+}
+
+// serial restatement of path_intersects_path for outlines with degenerate
+// (nearly zero-length) edges, where matplotlib merges consecutive points.
+// All lanes run it redundantly; it is never on the hot path.
+__device__ __noinline__ bool path_intersects_path_serial(const double2 *A, int nA, const double2 *B, int nB) {
+  int na = nA + 1, nb = nB + 1;
+  if (na < 2 || nb < 2) return false;
+  double x11 = A[0].x, y11 = A[0].y;
+  for (int i = 1; i < na; ++i) {
+    double2 pa = A[i == nA ? 0 : i];
+    double x12 = pa.x, y12 = pa.y;
+    if (isclose_((x11 - x12) * (x11 - x12) + (y11 - y12) * (y11 - y12), 0.0)) continue;
+    double x21 = B[0].x, y21 = B[0].y;
+    for (int j = 1; j < nb; ++j) {
+      double2 pb = B[j == nB ? 0 : j];
+      double x22 = pb.x, y22 = pb.y;
+      if (isclose_((x21 - x22) * (x21 - x22) + (y21 - y22) * (y21 - y22), 0.0)) continue;
+      if (segments_intersect(x11, y11, x12, y12, x21, y21, x22, y22)) return true;
+      x21 = x22;
+      y21 = y22;
+    }
+    x11 = x12;
+    y11 = y12;
+  }
+  return false;
+}
+
+// all vertices of P (np of them, + the duplicated closing one) inside Q?
+__device__ inline bool all_points_in_poly(const Env &e, const double2 *P, int np_, const double2 *Q, int nq) {
+  if (nq + 1 < 3) return false;
+  bool act = e.lane < np_;
+  double2 p = P[act ? e.lane : 0];
+  bool in = point_in_poly(p.x, p.y, Q, nq);
+  return __all_sync(FULL, in || !act);
+}
+
+// Path.intersects_path(a, b, filled=True) as MOOG calls it (sprite.py:482-483)
+__device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
+  const double2 *A = e.vtx + e.voff[a];
+  const double2 *B = e.vtx + e.voff[b];
+  int nA = META(e, MOOG_M_NV, a), nB = META(e, MOOG_M_NV, b);
+  bool serial = (e.sflag[a] | e.sflag[b]) & SLF_SHORT_EDGE;
+  if (serial) {
+    if (path_intersects_path_serial(A, nA, B, nB)) return true;
+  } else {
+    // lanes own the edges of the outline with more edges; the other outline's
+    // edges are walked together.  Argument order of segments_intersect is kept.
+    bool lanesA = nA >= nB;
+    const double2 *P = lanesA ? A : B;
+    const double2 *Q = lanesA ? B : A;
+    int nP = lanesA ? nA : nB, nQ = lanesA ? nB : nA;
+    int pslot = lanesA ? a : b, qslot = lanesA ? b : a;
+    bool act = e.lane < nP;
+    double2 p1 = P[act ? e.lane : 0];
+    double2 p2 = P[act ? ((e.lane + 1 == nP) ? 0 : e.lane + 1) : 0];
+    double pxmin = fmin(p1.x, p2.x) - AABB_PAD, pxmax = fmax(p1.x, p2.x) + AABB_PAD;
+    double pymin = fmin(p1.y, p2.y) - AABB_PAD, pymax = fmax(p1.y, p2.y) + AABB_PAD;
+    // my edge against the other outline's box
+    act = act && !(pxmax < BOX(e, 0, qslot) || pxmin > BOX(e, 2, qslot) || pymax < BOX(e, 1, qslot) ||
+                   pymin > BOX(e, 3, qslot));
+    if (__any_sync(FULL, act)) {
+      double Pxmin = BOX(e, 0, pslot) - AABB_PAD, Pymin = BOX(e, 1, pslot) - AABB_PAD;
+      double Pxmax = BOX(e, 2, pslot) + AABB_PAD, Pymax = BOX(e, 3, pslot) + AABB_PAD;
+      double2 q1 = Q[0];
+      for (int j = 0; j < nQ; ++j) {
+        double2 q2 = Q[(j + 1 == nQ) ? 0 : j + 1];
+        double qxmin = fmin(q1.x, q2.x), qxmax = fmax(q1.x, q2.x);
+        double qymin = fmin(q1.y, q2.y), qymax = fmax(q1.y, q2.y);
+        if (!(qxmax < Pxmin || qxmin > Pxmax || qymax < Pymin || qymin > Pymax)) {
+          bool h = false;
+          if (act && !(qxmax < pxmin || qxmin > pxmax || qymax < pymin || qymin > pymax)) {
+            h = lanesA ? segments_intersect(p1.x, p1.y, p2.x, p2.y, q1.x, q1.y, q2.x, q2.y)
+                       : segments_intersect(q1.x, q1.y, q2.x, q2.y, p1.x, p1.y, p2.x, p2.y);
+          }
+          if (__any_sync(FULL, h)) return true;
+        }
+        q1 = q2;
+      }
+    }
+  }
+  // containment fall-backs: a point outside the (padded) box of an outline is
+  // outside the outline, so "all inside" needs box containment first
+  bool b_in_a_box = BOX(e, 0, b) >= BOX(e, 0, a) - AABB_PAD && BOX(e, 2, b) <= BOX(e, 2, a) + AABB_PAD &&
+                    BOX(e, 1, b) >= BOX(e, 1, a) - AABB_PAD && BOX(e, 3, b) <= BOX(e, 3, a) + AABB_PAD;
+  if (b_in_a_box && all_points_in_poly(e, B, nB, A, nA)) return true;  // b inside a
+  bool a_in_b_box = BOX(e, 0, a) >= BOX(e, 0, b) - AABB_PAD && BOX(e, 2, a) <= BOX(e, 2, b) + AABB_PAD &&
+                    BOX(e, 1, a) >= BOX(e, 1, b) - AABB_PAD && BOX(e, 3, a) <= BOX(e, 3, b) + AABB_PAD;
+  if (a_in_b_box && all_points_in_poly(e, A, nA, B, nB)) return true;  // a inside b
+  return false;
+}
+
+__device__ __forceinline__ void count_overlap(Env &e, int a, int b, bool r) {
+  e.n_calls++;
+  if (r) {
+    e.n_true++;
+    e.hash = (e.hash ^ (uint64_t)(((uint32_t)a * 1315423911u) ^ ((uint32_t)b * 2654435761u) ^ 1u)) * 1099511628211ull;
+  }
+}
+
+// sprite.py:462-484 Sprite.overlaps_sprite
+__device__ inline bool overlaps(Env &e, int a, int b) {
+  bool r = false;
+  double dx = DYN(e, MOOG_D_X, a) - DYN(e, MOOG_D_X, b);
+  double dy = DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, b);
+  double center_dist = norm1(dx, dy);
+  if (!(center_dist > STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b))) {
+    if (!boxes_apart(e, a, b)) r = path_intersects_filled(e, a, b);
+  }
+  count_overlap(e, a, b, r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// collisions.py
+// ---------------------------------------------------------------------------
+struct CVec {
+  int has_point, future, has_since;
+  double px, py, nx, ny, sx, sy, qx, qy;  // point, normal, since, perp
+};
+
+// collisions.py:62-98 _relative_motion_trajectory (matrix only)
+__device__ inline Aff rel_motion_matrix(const Env &e, int ps, int as, double dt) {
+  Aff m1 = aff_identity(), m2 = aff_identity(), m3 = aff_identity(), m4 = aff_identity();
+  aff_rotate_around(m1, DYN(e, MOOG_D_X, ps), DYN(e, MOOG_D_Y, ps), scaled_angvel(e, ps, -1.0, dt));
+  aff_translate(m2, scaled_vel(e, ps, MOOG_D_VX, -1.0, dt), scaled_vel(e, ps, MOOG_D_VY, -1.0, dt));
+  aff_rotate_around(m3, DYN(e, MOOG_D_X, as), DYN(e, MOOG_D_Y, as),
+                    angvel_kind(e, as) == KIND_F32 ? f32mul(DYN(e, MOOG_D_ANGVEL, as), dt)
+                                                   : DYN(e, MOOG_D_ANGVEL, as) * dt);
+  aff_translate(m4, vel32(e, as) ? f32mul(DYN(e, MOOG_D_VX, as), dt) : DYN(e, MOOG_D_VX, as) * dt,
+                vel32(e, as) ? f32mul(DYN(e, MOOG_D_VY, as), dt) : DYN(e, MOOG_D_VY, as) * dt);
+  Aff t12 = aff_then(m1, m2);
+  Aff t123 = aff_then(t12, m3);
+  return aff_then(t123, m4);
+}
+
+// np.argmin order: a NaN beats everything, then the smaller value, then the smaller index
+__device__ __forceinline__ bool argmin_better(double v2, int i2, double v1, int i1) {
+  bool n1 = isnan(v1), n2 = isnan(v2);
+  if (n1 || n2) return (n1 && n2) ? (i2 < i1) : n2;
+  if (v2 < v1) return true;
+  if (v2 > v1) return false;
+  return i2 < i1;
+}
+
+// collisions.py:101-232 _directed_collision_vectors(sprite_0=s0, sprite_1=s1):
+// vertices of s0 that lie inside s1, traced back along the relative motion.
+__device__ inline void directed_collision_vectors(const Env &e, int s0, int s1, double dt, CVec &o) {
+  o.has_point = o.future = o.has_since = 0;
+  o.px = o.py = o.nx = o.ny = o.sx = o.sy = o.qx = o.qy = 0.0;
+  const double2 *P0 = e.vtx + e.voff[s0];
+  const double2 *P1 = e.vtx + e.voff[s1];
+  int n0 = META(e, MOOG_M_NV, s0), n1 = META(e, MOOG_M_NV, s1);
+  // sprite.py:442-460 contains_points: lane = vertex of s0
+  bool act = e.lane < n0;
+  double2 myv = P0[act ? e.lane : 0];
+  bool inside;
+  if (is_symmetric_circle(e, s1)) {
+    inside = norm_ax(myv.x - DYN(e, MOOG_D_X, s1), myv.y - DYN(e, MOOG_D_Y, s1)) <= STAT(e, MOOG_S_MAXR, s1);
+  } else {
+    inside = point_in_poly(myv.x, myv.y, P1, n1);
+  }
+  unsigned mask = __ballot_sync(FULL, inside && act);
+  if (mask == 0) return;  // (None, None, None, None)
+
+  Aff M = rel_motion_matrix(e, s0, s1, dt);
+
+  // lane = edge j of s1
+  bool eact = e.lane < n1;
+  double2 q1 = P1[eact ? e.lane : 0];
+  double2 q2 = P1[eact ? ((e.lane + 1 == n1) ? 0 : e.lane + 1) : 0];
+  double d1x = q2.x - q1.x, d1y = q2.y - q1.y;
+
+  bool any_cross = false;
+  bool have = false;
+  double b_dist = 0, b_cpx = 0, b_cpy = 0, b_dfx = 0, b_dfy = 0, b_a = 0;
+  int b_edge = 0;
+  while (mask) {
+    int c = __ffs(mask) - 1;
+    mask &= mask - 1;
+    double2 ev = P0[c];  // traj[:,1]
+    double ex = ev.x, ey = ev.y;
+    double sx = M.m0 * ex + M.m1 * ey + M.m2;  // traj[:,0]
+    double sy = M.m3 * ex + M.m4 * ey + M.m5;
+    double d0x = ex - sx, d0y = ey - sy;
+    // sprite.py:145-161 segment_crossing_coefficients against edge `lane`
+    double den = (d0x * d1y - d0y * d1x) + EPS_INTERP;
+    double qx = q1.x - sx, qy = q1.y - sy;
+    double A = (qx * d1y - qy * d1x) / den;
+    double Bc = (qx * d0y - qy * d0x) / den;
+    bool crossing = eact && (Bc >= 0) && (Bc <= 1);
+    any_cross |= (__any_sync(FULL, crossing) != 0);
+    if (!crossing) A = -INFINITY;
+    double ab = fabs(1.0 - A);
+    int idx = eact ? e.lane : 0x7fffffff;
+    if (!eact) { ab = INFINITY; A = -INFINITY; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double ov = shflx_d(ab, off), oa = shflx_d(A, off);
+      int oi = __shfl_xor_sync(FULL, idx, off);
+      if (argmin_better(ov, oi, ab, idx)) { ab = ov; A = oa; idx = oi; }
+    }
+    double cpx = sx + A * (ex - sx), cpy = sy + A * (ey - sy);
+    double dfx = ex - cpx, dfy = ey - cpy;
+    double dist = norm_ax(dfx, dfy);
+    if (dist == INFINITY) dist = 0.0;
+    // np.argmax over the contained vertices: first NaN wins, else first maximum
+    bool take = !have || (!isnan(b_dist) && (isnan(dist) || dist > b_dist));
+    if (take) {
+      have = true;
+      b_dist = dist; b_cpx = cpx; b_cpy = cpy; b_dfx = dfx; b_dfy = dfy; b_a = A; b_edge = idx;
+    }
+  }
+  if (!any_cross) return;  // collisions.py:177-179
+  o.has_point = 1;
+  o.has_since = 1;
+  o.px = b_cpx; o.py = b_cpy;
+  o.sx = b_dfx; o.sy = b_dfy;
+  if (b_a > 1) {  // collisions.py:214-217
+    o.future = 1;
+    return;
+  }
+  double2 e0 = P1[b_edge], e1 = P1[(b_edge + 1 == n1) ? 0 : b_edge + 1];
+  double dvx = e1.x - e0.x, dvy = e1.y - e0.y;
+  double nx = dvy, ny = -1.0 * dvx;
+  double nn = norm1(nx, ny);
+  o.nx = nx / nn;
+  o.ny = ny / nn;
+  double f = dot2(o.sx, o.sy, dvx, dvy) / dot2(dvx, dvy, dvx, dvy);
+  o.qx = o.sx - dvx * f;
+  o.qy = o.sy - dvy * f;
+}
+
+// collisions.py:235-289 _get_collision_vectors
+__device__ inline void get_collision_vectors(const Env &e, int s0, int s1, double dt, CVec &o) {
+  CVec c0, c1;
+  directed_collision_vectors(e, s1, s0, dt, c0);
+  directed_collision_vectors(e, s0, s1, dt, c1);
+  double s0x = 0, s0y = 0, s1x = 0, s1y = 0;
+  if (c0.has_point) {
+    if (!c0.future) {
+      c0.nx = -1.0 * c0.nx;
+      c0.ny = -1.0 * c0.ny;
+    }
+    c0.sx = -1.0 * c0.sx;
+    c0.sy = -1.0 * c0.sy;
+    s0x = c0.sx;
+    s0y = c0.sy;
+  }
+  if (c1.has_since) {
+    s1x = c1.sx;
+    s1y = c1.sy;
+  }
+  if (norm1(s0x, s0y) > norm1(s1x, s1y))
+    o = c0;
+  else
+    o = c1;
+}
+
+// collisions.py:292-350
+__device__ inline void collide_without_update_angle_vel(const Env &e, int s0, int s1, const CVec &cv,
+                                                        double elasticity, bool symmetric) {
+  double nx = cv.nx, ny = cv.ny;
+  double nn = norm1(nx, ny);
+  if (!(fabs(nn - 1.0) <= 1e-4 + 1e-5 * 1.0)) {
+    int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_NORMAL_NOT_UNIT;
+    wsync();
+    puti(e, &e.envi[MOOG_EI_ERR], err);
+    wsync();
+    return;
+  }
+  double v0x = DYN(e, MOOG_D_VX, s0), v0y = DYN(e, MOOG_D_VY, s0);
+  double v1x = DYN(e, MOOG_D_VX, s1), v1y = DYN(e, MOOG_D_VY, s1);
+  double m0 = STAT(e, MOOG_S_MASS, s0), m1 = STAT(e, MOOG_S_MASS, s1);
+  double d0 = dot2(v0x, v0y, nx, ny), d1 = dot2(v1x, v1y, nx, ny);
+  double v0nx = d0 * nx, v0ny = d0 * ny, v1nx = d1 * nx, v1ny = d1 * ny;
+  double cmx, cmy;
+  if (symmetric) {
+    cmx = (v0nx * m0 + v1nx * m1) / (m0 + m1);
+    cmy = (v0ny * m0 + v1ny * m1) / (m0 + m1);
+  } else {
+    cmx = v1nx;
+    cmy = v1ny;
+  }
+  double k = 1 + elasticity;
+  add_velocity(e, s0, k * (cmx - v0nx), k * (cmy - v0ny));
+  add_velocity(e, s1, k * (cmx - v1nx), k * (cmy - v1ny));
+}
+
+// collisions.py:353-454
+__device__ inline void collide_with_update_angle_vel(const Env &e, int s0, int s1, const CVec &cv,
+                                                     double elasticity, bool symmetric) {
+  double nx = cv.nx, ny = cv.ny;
+  double m0 = STAT(e, MOOG_S_MASS, s0), m1 = STAT(e, MOOG_S_MASS, s1);
+  double w0 = DYN(e, MOOG_D_ANGVEL, s0), w1 = DYN(e, MOOG_D_ANGVEL, s1);
+  double i0 = moment_of_inertia(e, s0), i1 = moment_of_inertia(e, s1);
+  double v0 = dot2(DYN(e, MOOG_D_VX, s0), DYN(e, MOOG_D_VY, s0), nx, ny);
+  double v1 = dot2(DYN(e, MOOG_D_VX, s1), DYN(e, MOOG_D_VY, s1), nx, ny);
+  double c0x = cv.px - DYN(e, MOOG_D_X, s0), c0y = cv.py - DYN(e, MOOG_D_Y, s0);
+  double c1x = cv.px - DYN(e, MOOG_D_X, s1), c1y = cv.py - DYN(e, MOOG_D_Y, s1);
+  double r0 = norm1(c0x, c0y), r1 = norm1(c1x, c1y);
+  double sin0 = (c0x * ny - c0y * nx) / r0;
+  double sin1 = (c1x * ny - c1y * nx) / r1;
+  double sa = r0 * sin0, sb = r1 * sin1;
+  double a = m0 + m1 + m0 * m1 * ((sa * sa / i0) + (sb * sb / i1));
+  double b = (1 + elasticity) * (v0 - v1 + w0 * sa - w1 * sb);
+  double dv0, dv1;
+  if (symmetric) {
+    dv0 = -1 * m1 * b / a;
+    dv1 = m0 * b / a;
+  } else {
+    dv0 = -1 * m1 * b / (a - m0);
+    dv1 = 0.0;
+  }
+  double dw0 = m0 * dv0 * sa / i0;
+  double dw1 = m1 * dv1 * sb / i1;
+  add_velocity(e, s0, dv0 * nx, dv0 * ny);
+  add_velocity(e, s1, dv1 * nx, dv1 * ny);
+  add_angvel(e, s0, dw0);
+  add_angvel(e, s1, dw1);
+}
+
+__device__ __forceinline__ double sign_(double x) { return isnan(x) ? x : (double)((x > 0) - (x < 0)); }
+
+// sprite.py:166-226 sprite_edge_crossings, reduced to what _position_correction
+// consumes: the number of strict crossings and the crossing closest to (px, py)
+// (first in row-major (i, j) order on ties -- argsort()[0] of collisions.py:688).
+struct Closest { int count; double ptx, pty; int i0, i1; };
+
+__device__ inline Closest closest_crossing(const Env &e, const double2 *P0, int n0, const double2 *P1, int n1,
+                                           double px, double py) {
+  bool act = e.lane < n0;
+  double2 a1 = P0[act ? e.lane : 0];
+  double2 a2 = P0[act ? ((e.lane + 1 == n0) ? 0 : e.lane + 1) : 0];
+  double d0x = a2.x - a1.x, d0y = a2.y - a1.y;
+  int cnt = 0, bj = 0x7fffffff;
+  double bd = INFINITY, bx = 0, by = 0;
+  bool bhave = false;
+  for (int j = 0; j < n1; ++j) {
+    double2 b1 = P1[j], b2 = P1[(j + 1 == n1) ? 0 : j + 1];
+    double d1x = b2.x - b1.x, d1y = b2.y - b1.y;
+    double den = (d0x * d1y - d0y * d1x) + EPS_INTERP;
+    double qx = b1.x - a1.x, qy = b1.y - a1.y;
+    double A = (qx * d1y - qy * d1x) / den;
+    double B = (qx * d0y - qy * d0x) / den;
+    if (act && (A > 0) && (A < 1) && (B > 0) && (B < 1)) {
+      ++cnt;
+      double cx = a1.x + A * d0x, cy = a1.y + A * d0y;
+      double d = norm_ax(cx - px, cy - py);
+      if (!bhave || d < bd) { bhave = true; bd = d; bx = cx; by = cy; bj = j; }
+    }
+  }
+  int bi = bhave ? e.lane : 0x7fffffff;
+  if (!bhave) bd = INFINITY;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    cnt += __shfl_xor_sync(FULL, cnt, off);
+    double od = shflx_d(bd, off), ox = shflx_d(bx, off), oy = shflx_d(by, off);
+    int oi = __shfl_xor_sync(FULL, bi, off), oj = __shfl_xor_sync(FULL, bj, off);
+    bool take = (oi != 0x7fffffff) && (bi == 0x7fffffff || od < bd || (od == bd && oi < bi));
+    if (take) { bd = od; bx = ox; by = oy; bi = oi; bj = oj; }
+  }
+  Closest c;
+  c.count = cnt; c.ptx = bx; c.pty = by; c.i0 = bi; c.i1 = bj;
+  return c;
+}
+
+// collisions.py:658-748 _position_correction.  `me` / `other` are the function's
+// sprite_0 / sprite_1; ind_me / ind_other the edge indices of the closest crossing.
+__device__ __noinline__ void position_correction(const Env &e, double pt0x, double pt0y, int ind_me, int ind_other,
+                                                 int me, int other, double out[2]) {
+  const double2 *Pme = e.vtx + e.voff[me];
+  const double2 *Pother = e.vtx + e.voff[other];
+  int n = META(e, MOOG_M_NV, me), no = META(e, MOOG_M_NV, other);
+  int pt0_ind = ind_other;  // collisions.py:706 compares a value with itself -> always the edge branch
+  int pt1_ind = (pt0_ind - 1 + no) % no;
+  double q0x = Pother[pt1_ind].x, q0y = Pother[pt1_ind].y;
+  double bx = Pother[pt0_ind].x - q0x, by = Pother[pt0_ind].y - q0y;
+  double bn = norm1(bx, by);
+  bx /= bn;
+  by /= bn;
+  double sg = sign_(dot2(DYN(e, MOOG_D_X, other) - q0x, DYN(e, MOOG_D_Y, other) - q0y, bx, by));
+  double nvx = bx * -1 * sg, nvy = by * -1 * sg;
+  int ind_forward = ind_me;
+  int ind_backward = (ind_forward - 1 + n) % n;
+  int parity, cur;
+  if (dot2(Pme[ind_forward].x - pt0x, Pme[ind_forward].y - pt0y, nvx, nvy) > 0) {
+    parity = 1;
+    cur = ind_forward;
+  } else if (dot2(Pme[ind_backward].x - pt0x, Pme[ind_backward].y - pt0y, nvx, nvy) > 0) {
+    parity = -1;
+    cur = ind_backward;
+  } else {
+    out[0] = out[1] = INFINITY;
+    return;
+  }
+  double worst = 0;
+  int guard = 0;
+  for (;;) {
+    double pen = dot2(Pme[cur].x - pt0x, Pme[cur].y - pt0y, nvx, nvy);
+    if (!(pen > 0)) break;
+    if (pen > worst) worst = pen;
+    cur = (cur + parity + n) % n;
+    if (++guard > n) {  // the reference would spin forever here
+      int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_DISJOINT_LOOP;
+      wsync();
+      puti(e, &e.envi[MOOG_EI_ERR], err);
+      wsync();
+      break;
+    }
+  }
+  out[0] = worst * nvx;
+  out[1] = worst * nvy;
+}
+
+// collisions.py:586-655 Collision._make_disjoint
+__device__ __noinline__ void make_disjoint(const Env &e, int s0, int s1, bool symmetric) {
+  const double2 *P0 = e.vtx + e.voff[s0];
+  const double2 *P1 = e.vtx + e.voff[s1];
+  int n0 = META(e, MOOG_M_NV, s0), n1 = META(e, MOOG_M_NV, s1);
+  Closest k0 = closest_crossing(e, P0, n0, P1, n1, DYN(e, MOOG_D_X, s0), DYN(e, MOOG_D_Y, s0));
+  if (k0.count <= 1) return;
+  Closest k1 = closest_crossing(e, P0, n0, P1, n1, DYN(e, MOOG_D_X, s1), DYN(e, MOOG_D_Y, s1));
+  double c0[2], c1[2];
+  position_correction(e, k0.ptx, k0.pty, k0.i0, k0.i1, s0, s1, c0);
+  position_correction(e, k1.ptx, k1.pty, k1.i1, k1.i0, s1, s0, c1);
+  double cx, cy;
+  if (norm1(c0[0], c0[1]) > norm1(c1[0], c1[1])) {
+    cx = -1 * (1 + EPS_COLL) * c0[0];
+    cy = -1 * (1 + EPS_COLL) * c0[1];
+  } else {
+    cx = (1 + EPS_COLL) * c0[0];
+    cy = (1 + EPS_COLL) * c0[1];
+  }
+  if (!(isfinite(cx) && isfinite(cy))) cx = cy = 0.0;
+  if (symmetric) {
+    set_position(e, s0, DYN(e, MOOG_D_X, s0) + 0.5 * cx, DYN(e, MOOG_D_Y, s0) + 0.5 * cy);
+    set_position(e, s1, DYN(e, MOOG_D_X, s1) - 0.5 * cx, DYN(e, MOOG_D_Y, s1) - 0.5 * cy);
+  } else {
+    set_position(e, s0, DYN(e, MOOG_D_X, s0) + cx, DYN(e, MOOG_D_Y, s0) + cy);
+  }
+}
+
+// collisions.py:494-584 Collision.step; returns true when any state changed
+__device__ inline bool collision_step(Env &e, const moog_op *op, int s0, int s1, bool first_overlap_known) {
+  bool symmetric = (op->flags & MOOG_FL_SYMMETRIC) != 0;
+  bool changed = false;
+  int depth = 0;
+  for (;;) {  // tail recursion of collisions.py:583-584
+    if (depth > op->i[2]) return changed;
+    if (s0 == s1) return changed;
+    bool ov;
+    if (first_overlap_known && depth == 0) {
+      // the caller's broad phase already established that the circles and the
+      // boxes meet: go straight to the outline test
+      ov = path_intersects_filled(e, s0, s1);
+      count_overlap(e, s0, s1, ov);
+    } else {
+      ov = overlaps(e, s0, s1);
+    }
+    if (!ov) return changed;
+    double dt = 1.0 / e.K;
+    CVec cv;
+    get_collision_vectors(e, s0, s1, dt, cv);
+    if (!cv.has_point) {
+      make_disjoint(e, s0, s1, symmetric);
+      changed = true;
+    } else {
+      if (cv.future) return changed;
+      e.n_coll++;
+      changed = true;
+      if (symmetric) {
+        set_position(e, s0, DYN(e, MOOG_D_X, s0) - (0.5 + EPS_COLL) * cv.qx,
+                     DYN(e, MOOG_D_Y, s0) - (0.5 + EPS_COLL) * cv.qy);
+        set_position(e, s1, DYN(e, MOOG_D_X, s1) + (0.5 + EPS_COLL) * cv.qx,
+                     DYN(e, MOOG_D_Y, s1) + (0.5 + EPS_COLL) * cv.qy);
+      } else {
+        set_position(e, s0, DYN(e, MOOG_D_X, s0) - (1. + EPS_COLL) * cv.qx,
+                     DYN(e, MOOG_D_Y, s0) - (1. + EPS_COLL) * cv.qy);
+      }
+      if (op->flags & MOOG_FL_UPDATE_ANGLE_VEL)
+        collide_with_update_angle_vel(e, s0, s1, cv, op->p[0], symmetric);
+      else
+        collide_without_update_angle_vel(e, s0, s1, cv, op->p[0], symmetric);
+    }
+    depth += 1;
+  }
+}
+
+// All (s0, j) pairs of one Collision entry for a fixed s0, j over layer lb in
+// order.  The broad phase (circle test of sprite.py:464-466 plus the exact box
+// cull) is evaluated for 32 second sprites at once; candidates are then resolved
+// one by one in index order, and the broad phase of the remaining ones is
+// re-evaluated whenever a contact moved something.
+__device__ inline void collision_row(Env &e, const moog_op *op, int s0, int lb) {
+  int nb = e.cnt[lb], base_slot = LOFF(e, lb);
+  for (int base = 0; base < nb; base += 32) {
+    int j = base + e.lane;
+    int s1 = base_slot + j;
+    bool valid = j < nb && s1 != s0;
+    unsigned vmask = __ballot_sync(FULL, valid);
+    e.n_calls += __popc(vmask);  // every valid pair costs the reference one overlaps_sprite call
+    int jstart = 0;
+    bool recompute = true;
+    unsigned cand = 0;
+    for (;;) {
+      if (recompute) {
+        bool c = false;
+        if (valid && e.lane >= jstart) {
+          double dx = DYN(e, MOOG_D_X, s0) - DYN(e, MOOG_D_X, s1);
+          double dy = DYN(e, MOOG_D_Y, s0) - DYN(e, MOOG_D_Y, s1);
+          double cd = norm1(dx, dy);
+          c = !(cd > STAT(e, MOOG_S_MAXR, s0) + STAT(e, MOOG_S_MAXR, s1)) && !boxes_apart(e, s0, s1);
+        }
+        cand = __ballot_sync(FULL, c);
+        recompute = false;
+      }
+      if (!cand) break;
+      int l = __ffs(cand) - 1;
+      cand &= cand - 1;
+      e.n_calls--;  // collision_step counts this pair's first call itself
+      bool changed = collision_step(e, op, s0, base_slot + base + l, true);
+      jstart = l + 1;
+      if (changed) recompute = true;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// forces (abstract_force.py:64-74 + the individual _compute_forces)
+// ---------------------------------------------------------------------------
+__device__ inline double noise_at(const Env &e, int col) {
+  if (e.noise) return e.noise[(size_t)e.substep * e.hdr[MOOG_H_NOISE_DIM] + col];
+  return philox_uniform(e.seed, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_STEP_COUNT],
+                        (uint32_t)e.substep | ((uint32_t)e.envi[MOOG_EI_EPISODES] << 8), (uint32_t)col);
+}
+
+// lane = sprite of the layer; a unary force only touches its own sprite's velocity
+__device__ inline void force_unary_layer(const Env &e, const moog_op *op) {
+  int la = op->i[0], n = e.cnt[la];
+  for (int base = 0; base < n; base += 32) {
+    int idx = base + e.lane;
+    if (idx < n) {
+      int s = LOFF(e, la) + idx;
+      double m = STAT(e, MOOG_S_MASS, s);
+      double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
+      bool v32 = vel32(e, s);
+      double fx = 0, fy = 0;
+      bool done = false;
+      switch (op->kind) {
+        case MOOG_F_DRAG:  // friction.py:54-56
+          if (v32) {
+            // python-float scalars are weak: the whole chain runs in float32
+            if (isfinite(m)) {
+              double c = -1 * op->p[0], den = m * (double)e.K;
+              DYN(e, MOOG_D_VX, s) = f32add(vx, f32div(f32mul(f32mul(c, vx), m), den));
+              DYN(e, MOOG_D_VY, s) = f32add(vy, f32div(f32mul(f32mul(c, vy), m), den));
+            }
+            done = true;
+          } else {
+            fx = -1 * op->p[0] * vx * m;
+            fy = -1 * op->p[0] * vy * m;
+          }
+          break;
+        case MOOG_F_KINETIC_FRICTION: {  // friction.py:25-33
+          double nrm = norm1(vx, vy);
+          double ux = 0, uy = 0;
+          if (nrm != 0) {
+            ux = vx / nrm;
+            uy = vy / nrm;
+          }
+          fx = -1 * op->p[0] * ux * m;
+          fy = -1 * op->p[0] * uy * m;
+          break;
+        }
+        case MOOG_F_DOWN_GRAVITY:  // gravity.py:21-23
+          fx = op->p[0] * m * 0;
+          fy = op->p[0] * m * 1;
+          break;
+        case MOOG_F_RANDOM: {  // random_force.py:22-26
+          double u0 = noise_at(e, op->i[2] + 2 * idx), u1 = noise_at(e, op->i[2] + 2 * idx + 1);
+          double r = 0.0 + (op->p[0] - 0.0) * u0;
+          double th = 0.0 + (2 * M_PI - 0.0) * u1;
+          fx = r * cos(th);
+          fy = r * sin(th);
+          break;
+        }
+      }
+      if (!done && isfinite(m)) {  // abstract_force.py:64-74
+        double den = m * (double)e.K;
+        double nvx = vx + fx / den, nvy = vy + fy / den;
+        if (v32) {
+          nvx = f32r(nvx);
+          nvy = f32r(nvy);
+        }
+        DYN(e, MOOG_D_VX, s) = nvx;
+        DYN(e, MOOG_D_VY, s) = nvy;
+      }
+    }
+  }
+  wsync();
+}
+
+__device__ inline void newton(const Env &e, int s, double fx, double fy) {
+  double m = STAT(e, MOOG_S_MASS, s);
+  if (!isfinite(m)) return;
+  double den = m * (double)e.K;
+  add_velocity(e, s, fx / den, fy / den);
+}
+
+__device__ inline void force_binary(const Env &e, const moog_op *op, int s0, int s1) {
+  // gravity.py:44-60, distance_fn_force.py:30-45
+  double dx = DYN(e, MOOG_D_X, s1) - DYN(e, MOOG_D_X, s0);
+  double dy = DYN(e, MOOG_D_Y, s1) - DYN(e, MOOG_D_Y, s0);
+  double dist = norm1(dx, dy);
+  double f0x = 0, f0y = 0, f1x = 0, f1y = 0;
+  if (dist != 0.) {
+    double ux = dx / dist, uy = dy / dist;
+    double mag = 0;
+    if (op->kind == MOOG_F_GRAVITY) {
+      mag = op->p[0] * STAT(e, MOOG_S_MASS, s0) * STAT(e, MOOG_S_MASS, s1) * dist;
+    } else if (op->kind == MOOG_F_DIST_LINEAR) {  // distance_fn_force.py:48-74
+      mag = op->p[0] + op->p[1] * dist;
+      if (!(op->flags & MOOG_FL_APPLY_DISTANT) && dist > op->p[2]) mag = 0;
+      if (!(op->flags & MOOG_FL_APPLY_NEARBY) && dist < op->p[2]) mag = 0;
+    } else if (op->kind == MOOG_F_DIST_SPRING) {  // distance_fn_force.py:77-89
+      mag = -1. * op->p[0] * (dist - op->p[1]);
+    }
+    f1x = mag * ux;
+    f1y = mag * uy;
+    if (op->flags & MOOG_FL_SYMMETRIC) {
+      f0x = -1 * f1x;
+      f0y = -1 * f1y;
+    }
+  }
+  newton(e, s0, f0x, f0y);
+  newton(e, s1, f1x, f1y);
+}
+
+// ---------------------------------------------------------------------------
+// corrective physics
+// ---------------------------------------------------------------------------
+
+// q-th live sprite of a layer list; -1 past the end
+__device__ inline int list_slot(const Env &e, int start, int n, int q) {
+  for (int k = 0; k < n; ++k) {
+    int l = e.ipool[start + k];
+    int c = e.cnt[l];
+    if (q < c) return LOFF(e, l) + q;
+    q -= c;
+  }
+  return -1;
+}
+__device__ inline int list_count(const Env &e, int start, int n) {
+  int t = 0;
+  for (int k = 0; k < n; ++k) t += e.cnt[e.ipool[start + k]];
+  return t;
+}
+
+// tether_physics.py:16-91.  The sprite set is given by `pick(i)`.
+template <class Pick>
+__device__ inline void tether_sprites(const Env &e, Pick pick, int n, bool update_angle_vel, bool has_anchor,
+                                      double ax, double ay) {
+  if (n == 0) return;
+  double total_mass = 0;
+  for (int i = 0; i < n; ++i) total_mass = total_mass + STAT(e, MOOG_S_MASS, pick(i));
+  if (isinf(total_mass)) return;
+  double cx = 0, cy = 0, mx = 0, my = 0;
+  for (int i = 0; i < n; ++i) {
+    int s = pick(i);
+    double m = STAT(e, MOOG_S_MASS, s);
+    cx = cx + m * DYN(e, MOOG_D_X, s);
+    cy = cy + m * DYN(e, MOOG_D_Y, s);
+    mx = mx + m * DYN(e, MOOG_D_VX, s);
+    my = my + m * DYN(e, MOOG_D_VY, s);
+  }
+  cx /= total_mass;
+  cy /= total_mass;
+  double tvx = mx / total_mass, tvy = my / total_mass;
+  if (has_anchor) {
+    cx = ax;
+    cy = ay;
+    tvx = tvy = 0;
+  }
+  if (update_angle_vel) {
+    double Ltot = 0, Itot = 0;
+    for (int i = 0; i < n; ++i) {
+      int s = pick(i);
+      double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
+      double dpx = vx / e.K, dpy = vy / e.K;
+      double px = (DYN(e, MOOG_D_X, s) + 0.5 * dpx) - cx;
+      double py = (DYN(e, MOOG_D_Y, s) + 0.5 * dpy) - cy;
+      double r = norm1(px, py);
+      px /= r;
+      py /= r;
+      double qx = 0 * px + -1 * py, qy = 1 * px + 0 * py;
+      double perp_vel = dot2(vx - tvx, vy - tvy, qx, qy);
+      double m = STAT(e, MOOG_S_MASS, s);
+      double I = moment_of_inertia(e, s);
+      double Lz = perp_vel * m * r;
+      Lz += DYN(e, MOOG_D_ANGVEL, s) * I;
+      Ltot = Ltot + Lz;
+      Itot = Itot + (I + m * r * r);
+      wsync();
+      put(e, &TMP(e, 0, s), r);
+      put(e, &TMP(e, 1, s), qx);
+      put(e, &TMP(e, 2, s), qy);
+      wsync();
+    }
+    double w = Ltot / Itot;
+    for (int i = 0; i < n; ++i) {
+      int s = pick(i);
+      double r = TMP(e, 0, s), qx = TMP(e, 1, s), qy = TMP(e, 2, s);
+      assign_velocity(e, s, tvx + r * qx * w, tvy + r * qy * w);
+      put(e, &DYN(e, MOOG_D_ANGVEL, s), w);
+      set_angvel_kind(e, s, KIND_F64);
+    }
+  } else {
+    for (int i = 0; i < n; ++i) {
+      int s = pick(i);
+      assign_velocity(e, s, tvx, tvy);
+      put(e, &DYN(e, MOOG_D_ANGVEL, s), 0.);
+      set_angvel_kind(e, s, KIND_WEAK);
+    }
+  }
+}
+
+__device__ __noinline__ void corrective(const Env &e, const moog_op *op) {
+  switch (op->kind) {
+    case MOOG_C_TETHER: {  // tether_physics.py:126-140
+      int st = op->i[0], nl = op->i[1];
+      int n = list_count(e, st, nl);
+      tether_sprites(e, [&](int i) { return list_slot(e, st, nl, i); }, n,
+                     (op->flags & MOOG_FL_UPDATE_ANGLE_VEL) != 0, (op->flags & MOOG_FL_HAS_ANCHOR) != 0, op->p[0],
+                     op->p[1]);
+      break;
+    }
+    case MOOG_C_TETHER_ZIPPED: {  // tether_physics.py:186-201
+      int nl = op->i[1];
+      int c0 = nl ? e.cnt[e.ipool[op->i[0]]] : 0;
+      for (int q = 1; q < nl; ++q)
+        if (e.cnt[e.ipool[op->i[0] + q]] != c0) {
+          int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_TETHER_ZIP;
+          wsync();
+          puti(e, &e.envi[MOOG_EI_ERR], err);
+          wsync();
+          return;
+        }
+      for (int i = 0; i < c0; ++i) {
+        int st = op->i[0];
+        tether_sprites(e, [&](int q) { return LOFF(e, e.ipool[st + q]) + i; }, nl,
+                       (op->flags & MOOG_FL_UPDATE_ANGLE_VEL) != 0, (op->flags & MOOG_FL_HAS_ANCHOR) != 0,
+                       op->p[0], op->p[1]);
+      }
+      break;
+    }
+    case MOOG_C_CONSTANT_SPEED: {  // constant_speed.py:34-46
+      int n = list_count(e, op->i[0], op->i[1]);
+      for (int i = 0; i < n; ++i) {
+        int s = list_slot(e, op->i[0], op->i[1], i);
+        double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
+        double nv = norm1(vx, vy);
+        if (nv != 0) assign_velocity(e, s, op->p[0] * vx / nv, op->p[0] * vy / nv);
+      }
+      break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Euler integration of every sprite (physics.py:113-117, sprite.py:426-430)
+// ---------------------------------------------------------------------------
+#define TF_MOVE 1
+#define TF_ROT 2
+
+__device__ inline void integrate_all(const Env &e) {
+  double dt = 1. / e.K;
+  // phase 1: lane = slot.  New position / angle and the affine update of the outline.
+  for (int s = e.lane; s < e.S; s += 32) {
+    int vs_layer_live = 0;
+    // live?  slots of layer l are [LOFF(l), LOFF(l) + cnt[l])
+    for (int l = 0; l < e.L; ++l)
+      if (s >= LOFF(e, l) && s < LOFF(e, l) + e.cnt[l]) vs_layer_live = 1;
+    int flag = 0;
+    if (vs_layer_live) {
+      bool v32 = vel32(e, s);
+      double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
+      double dx = v32 ? f32mul(dt, vx) : dt * vx;
+      double dy = v32 ? f32mul(dt, vy) : dt * vy;
+      double ox = DYN(e, MOOG_D_X, s), oy = DYN(e, MOOG_D_Y, s);
+      double nx = ox + dx, ny = oy + dy;
+      double tx = nx - ox, ty = ny - oy;
+      DYN(e, MOOG_D_X, s) = nx;
+      DYN(e, MOOG_D_Y, s) = ny;
+      TMP(e, 0, s) = tx;
+      TMP(e, 1, s) = ty;
+      if (!(tx == 0.0 && ty == 0.0)) {
+        flag |= TF_MOVE;
+        BOX(e, 0, s) = BOX(e, 0, s) + tx;
+        BOX(e, 1, s) = BOX(e, 1, s) + ty;
+        BOX(e, 2, s) = BOX(e, 2, s) + tx;
+        BOX(e, 3, s) = BOX(e, 3, s) + ty;
+      }
+      double w = DYN(e, MOOG_D_ANGVEL, s);
+      if (w != 0) {  // `if self._angle_vel:` (NaN is truthy)
+        int wk = angvel_kind(e, s), ak = ang_kind(e, s);
+        double t = (wk == KIND_F32) ? f32mul(dt, w) : dt * w;
+        double a = DYN(e, MOOG_D_ANG, s), na;
+        int nk;
+        if (ak == KIND_F64 || wk == KIND_F64) { na = a + t; nk = KIND_F64; }
+        else if (ak == KIND_WEAK && wk == KIND_WEAK) { na = a + t; nk = KIND_WEAK; }
+        else { na = f32add(a, t); nk = KIND_F32; }
+        // sprite.py:531-540: rotate_around(x, y, a_new - a_old) about the NEW position
+        double dth = (nk == KIND_F32 && ak != KIND_F64) ? f32sub(na, a) : na - a;
+        Aff m = aff_identity();
+        aff_rotate_around(m, nx, ny, dth);
+        TMP(e, 2, s) = m.m0; TMP(e, 3, s) = m.m1; TMP(e, 4, s) = m.m2;
+        TMP(e, 5, s) = m.m3; TMP(e, 6, s) = m.m4; TMP(e, 7, s) = m.m5;
+        DYN(e, MOOG_D_ANG, s) = na;
+        META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (nk << MOOG_SF_ANG_SHIFT);
+        flag |= TF_ROT;
+      }
+    }
+    e.sflag[s] = (e.sflag[s] & SLF_SHORT_EDGE) | (flag << 8);
+  }
+  wsync();
+  // phase 2: lane = cached vertex
+  for (int v = e.lane; v < e.VT; v += 32) {
+    int s = e.vslot[v];
+    int flag = e.sflag[s] >> 8;
+    if (flag && (v - e.voff[s]) < META(e, MOOG_M_NV, s)) {
+      double2 p = e.vtx[v];
+      double x = 1.0 * p.x + 0.0 * p.y + TMP(e, 0, s);
+      double y = 0.0 * p.x + 1.0 * p.y + TMP(e, 1, s);
+      if (flag & TF_ROT) {
+        double rx = TMP(e, 2, s) * x + TMP(e, 3, s) * y + TMP(e, 4, s);
+        double ry = TMP(e, 5, s) * x + TMP(e, 6, s) * y + TMP(e, 7, s);
+        x = rx;
+        y = ry;
+      }
+      e.vtx[v] = make_double2(x, y);
+    }
+  }
+  wsync();
+  // phase 3: boxes of rotated outlines (lane = slot)
+  for (int s = e.lane; s < e.S; s += 32) {
+    int flag = e.sflag[s] >> 8;
+    if (flag & TF_ROT) {
+      int n = META(e, MOOG_M_NV, s);
+      const double2 *v = e.vtx + e.voff[s];
+      double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+      for (int i = 0; i < n; ++i) {
+        double2 p = v[i];
+        xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
+        ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
+      }
+      BOX(e, 0, s) = xmin; BOX(e, 1, s) = ymin; BOX(e, 2, s) = xmax; BOX(e, 3, s) = ymax;
+    }
+    e.sflag[s] &= SLF_SHORT_EDGE;
+  }
+  wsync();
+}
+
+// physics.py:88-117 Physics.apply_physics (one substep)
+__device__ inline void apply_physics(Env &e) {
+  const int32_t *h = e.hdr;
+  for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
+    const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
+    int la = op->i[0], lb = op->i[1];
+    if (lb < 0) {
+      force_unary_layer(e, op);
+    } else if (op->kind == MOOG_F_COLLISION) {
+      for (int i = 0; i < e.cnt[la]; ++i) collision_row(e, op, LOFF(e, la) + i, lb);
+    } else {
+      for (int i = 0; i < e.cnt[la]; ++i)
+        for (int j = 0; j < e.cnt[lb]; ++j) force_binary(e, op, LOFF(e, la) + i, LOFF(e, lb) + j);
+    }
+  }
+  for (int c = 0; c < h[MOOG_H_N_CORR]; ++c) corrective(e, e.ops + h[MOOG_H_CORR] + c);
+  integrate_all(e);
+}
+
+// ---------------------------------------------------------------------------
+// expression VM (config lambdas compiled by the host)
+// ---------------------------------------------------------------------------
+__device__ inline double *attr_ptr(const Env &e, int s, int at) {
+  switch (at) {
+    case MOOG_AT_X: return &DYN(e, MOOG_D_X, s);
+    case MOOG_AT_Y: return &DYN(e, MOOG_D_Y, s);
+    case MOOG_AT_X_VEL: return &DYN(e, MOOG_D_VX, s);
+    case MOOG_AT_Y_VEL: return &DYN(e, MOOG_D_VY, s);
+    case MOOG_AT_ANGLE: return &DYN(e, MOOG_D_ANG, s);
+    case MOOG_AT_ANGLE_VEL: return &DYN(e, MOOG_D_ANGVEL, s);
+    case MOOG_AT_MASS: return &STAT(e, MOOG_S_MASS, s);
+    case MOOG_AT_SCALE: return &STAT(e, MOOG_S_SCALE, s);
+    case MOOG_AT_ASPECT_RATIO: return &STAT(e, MOOG_S_ASPECT, s);
+    case MOOG_AT_C0: return &STAT(e, MOOG_S_C0, s);
+    case MOOG_AT_C1: return &STAT(e, MOOG_S_C1, s);
+    case MOOG_AT_C2: return &STAT(e, MOOG_S_C2, s);
+    case MOOG_AT_OPACITY: return &STAT(e, MOOG_S_OPACITY, s);
+  }
+  return &DYN(e, MOOG_D_X, s);
+}
+
+__device__ inline double py_fmod(double a, double b) {
+  double r = fmod(a, b);
+  if (r != 0 && ((r < 0) != (b < 0))) r += b;
+  return r;
+}
+
+__device__ __noinline__ double eval_expr(const Env &e, int start, int s0, int s1) {
+  if (start < 0) return 1.0;
+  double st[16];
+  int sp = 0;
+  for (const moog_ex *x = e.expr + start; x->op != MOOG_X_END; ++x) {
+    double a, b;
+    switch (x->op) {
+      case MOOG_X_CONST: st[sp++] = x->c; break;
+      case MOOG_X_ATTR0: st[sp++] = *attr_ptr(e, s0, x->arg); break;
+      case MOOG_X_ATTR1: st[sp++] = *attr_ptr(e, s1, x->arg); break;
+      case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
+      case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      case MOOG_X_STORE: {
+        double v = st[--sp];
+        wsync();
+        put(e, attr_ptr(e, s0, x->arg), v);
+        wsync();
+        break;
+      }
+      default:
+        b = st[--sp];
+        a = st[--sp];
+        switch (x->op) {
+          case MOOG_X_LT: a = a < b; break;
+          case MOOG_X_LE: a = a <= b; break;
+          case MOOG_X_GT: a = a > b; break;
+          case MOOG_X_GE: a = a >= b; break;
+          case MOOG_X_EQ: a = a == b; break;
+          case MOOG_X_NE: a = a != b; break;
+          case MOOG_X_AND: a = (a != 0) && (b != 0); break;
+          case MOOG_X_OR: a = (a != 0) || (b != 0); break;
+          case MOOG_X_ADD: a = a + b; break;
+          case MOOG_X_SUB: a = a - b; break;
+          case MOOG_X_MUL: a = a * b; break;
+          case MOOG_X_DIV: a = a / b; break;
+          case MOOG_X_MOD: a = py_fmod(a, b); break;
+        }
+        st[sp++] = a;
+    }
+  }
+  return sp ? st[sp - 1] : 1.0;
+}
+
+__device__ __noinline__ double eval_condition(Env &e, int op_index) {
+  const moog_op *op = e.ops + op_index;
+  switch (op->kind) {
+    case MOOG_SC_CONST: return op->p[0];
+    case MOOG_SC_ALL:
+    case MOOG_SC_ANY:
+    case MOOG_SC_COUNT: {
+      int n = list_count(e, op->i[0], op->i[1]);
+      int cnt = 0;
+      for (int i = 0; i < n; ++i) {
+        int s = list_slot(e, op->i[0], op->i[1], i);
+        cnt += eval_expr(e, op->i[2], s, s) != 0;
+      }
+      if (op->kind == MOOG_SC_ALL) return cnt == n;
+      if (op->kind == MOOG_SC_ANY) return cnt > 0;
+      return cnt;
+    }
+    case MOOG_SC_CONTACT_COUNT: {  // contact_rules.py:15-51
+      int la = op->i[0], lb = op->i[1], cnt = 0;
+      for (int i = 0; i < e.cnt[la]; ++i)
+        for (int j = 0; j < e.cnt[lb]; ++j) cnt += overlaps(e, LOFF(e, la) + i, LOFF(e, lb) + j);
+      return cnt;
+    }
+    case MOOG_SC_CONTACT_ANY_COUNT: {
+      int n = list_count(e, op->i[0], op->i[1]);
+      int m = list_count(e, op->i[2], op->i[3]);
+      int cnt = 0;
+      for (int i = 0; i < n; ++i) {
+        int s = list_slot(e, op->i[0], op->i[1], i);
+        if (eval_expr(e, op->i[4], s, s) == 0) continue;
+        bool any = false;
+        for (int j = 0; j < m && !any; ++j) any = overlaps(e, s, list_slot(e, op->i[2], op->i[3], j));
+        cnt += any;
+      }
+      return cnt;
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// rules
+// ---------------------------------------------------------------------------
+__device__ inline void copy_slot(const Env &e, int dst, int src) {
+  wsync();
+  int nv = META(e, MOOG_M_NV, src);
+  if (e.lane < MOOG_DYN_FIELDS) DYN(e, e.lane, dst) = DYN(e, e.lane, src);
+  if (e.lane < MOOG_STAT_FIELDS) STAT(e, e.lane, dst) = STAT(e, e.lane, src);
+  if (e.lane < MOOG_META_FIELDS) META(e, e.lane, dst) = META(e, e.lane, src);
+  if (e.lane < 4) BOX(e, e.lane, dst) = BOX(e, e.lane, src);
+  if (e.lane == 0) e.sflag[dst] = e.sflag[src];
+  if (e.lane < nv) e.vtx[e.voff[dst] + e.lane] = e.vtx[e.voff[src] + e.lane];
+  wsync();
+}
+
+// vanish.py:31-39: pop the flagged sprites of layer l, preserving order.
+// `gone` is a per-lane bitmask chunk list: bit i of word w flags sprite 32*w+i.
+__device__ inline void vanish(const Env &e, int l, const unsigned *gone) {
+  int base = LOFF(e, l), n = e.cnt[l], w = 0;
+  for (int i = 0; i < n; ++i) {
+    if ((gone[i >> 5] >> (i & 31)) & 1u) continue;
+    if (w != i) copy_slot(e, base + w, base + i);
+    ++w;
+  }
+  wsync();
+  puti(e, &e.cnt[l], w);
+  wsync();
+}
+
+__device__ double rule_noise_at(const Env &e, int col) {
+  if (e.rule_noise) return e.rule_noise[col];
+  return philox_uniform(e.seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_STEP_COUNT],
+                        (uint32_t)e.envi[MOOG_EI_EPISODES], (uint32_t)col);
+}
+
+// one non-conditional rule
+__device__ __noinline__ void rule_leaf(Env &e, int r) {
+  const moog_op *op = e.ops + r;
+  unsigned flag[MOOG_MAX_SLOTS / 32];
+  switch (op->kind) {
+    case MOOG_R_VANISH_ON_CONTACT: {  // vanish.py:66-86, contact_rules.py:28-35
+      int la = op->i[0], lb = op->i[1];
+      for (int w = 0; w < MOOG_MAX_SLOTS / 32; ++w) flag[w] = 0;
+      for (int i = 0; i < e.cnt[la]; ++i)
+        for (int j = 0; j < e.cnt[lb]; ++j)  // every pair is evaluated (no short-circuit)
+          if (overlaps(e, LOFF(e, la) + i, LOFF(e, lb) + j)) flag[i >> 5] |= 1u << (i & 31);
+      vanish(e, la, flag);
+      return;
+    }
+    case MOOG_R_VANISH_BY_FILTER: {  // vanish.py:42-63
+      int la = op->i[0];
+      for (int w = 0; w < MOOG_MAX_SLOTS / 32; ++w) flag[w] = 0;
+      for (int i = 0; i < e.cnt[la]; ++i)
+        if (eval_expr(e, op->i[2], LOFF(e, la) + i, LOFF(e, la) + i) != 0) flag[i >> 5] |= 1u << (i & 31);
+      vanish(e, la, flag);
+      return;
+    }
+    case MOOG_R_MODIFY_ON_CONTACT: {  // contact_rules.py:86-120
+      const int32_t *q = e.ipool + op->i[4];  // mod0 filt0 mod1 filt1
+      for (int pass = 0; pass < 2; ++pass) {
+        int as = pass ? op->i[2] : op->i[0], an = pass ? op->i[3] : op->i[1];
+        int bs = pass ? op->i[0] : op->i[2], bn = pass ? op->i[1] : op->i[3];
+        int na = list_count(e, as, an), nb = list_count(e, bs, bn);
+        int mod = q[2 * pass], filt = q[2 * pass + 1];
+        if (mod < 0) continue;
+        for (int i = 0; i < na; ++i) {
+          int sa = list_slot(e, as, an, i);
+          if (eval_expr(e, filt, sa, sa) == 0) continue;
+          bool any = false;
+          for (int j = 0; j < nb; ++j) {
+            int sb = list_slot(e, bs, bn, j);
+            if (sb != sa && overlaps(e, sa, sb)) any = true;  // list comprehension: all evaluated
+          }
+          if (any) eval_expr(e, mod, sa, sa);
+        }
+      }
+      return;
+    }
+    case MOOG_R_MODIFY_SPRITES: {  // modify_sprites.py:35-52
+      int n = list_count(e, op->i[0], op->i[1]);
+      // the filter sees the pre-modification state of every sprite (the reference
+      // builds the filtered list first): flag, then modify
+      int m = 0;
+      for (int w = 0; w < MOOG_MAX_SLOTS / 32; ++w) flag[w] = 0;
+      for (int i = 0; i < n; ++i) {
+        int s = list_slot(e, op->i[0], op->i[1], i);
+        if (op->i[3] < 0 || eval_expr(e, op->i[3], s, s) != 0) {
+          flag[i >> 5] |= 1u << (i & 31);
+          ++m;
+        }
+      }
+      if (m == 0) return;
+      int pick = -1;
+      if (op->flags & MOOG_FL_SAMPLE_ONE) {
+        double u = rule_noise_at(e, op->i[4]);
+        pick = (int)(u * m);
+        if (pick >= m) pick = m - 1;
+      }
+      int k = 0;
+      for (int i = 0; i < n; ++i) {
+        if (!((flag[i >> 5] >> (i & 31)) & 1u)) continue;
+        int s = list_slot(e, op->i[0], op->i[1], i);
+        if (pick < 0 || k == pick) eval_expr(e, op->i[2], s, s);
+        ++k;
+      }
+      return;
+    }
+  }
+}
+
+// game_rules in order; ConditionalRule blocks (conditional.py:55-58) run their
+// sub-rules `int(condition(state))` times.  Iterative (explicit block stack) so
+// that the kernel's stack size is static.
+#define MOOG_MAX_COND_DEPTH 4
+__device__ inline void rules_step(Env &e) {
+  const int32_t *h = e.hdr;
+  int r = h[MOOG_H_RULES];
+  const int end = h[MOOG_H_RULES] + h[MOOG_H_N_RULES];
+  int blk_start[MOOG_MAX_COND_DEPTH], blk_end[MOOG_MAX_COND_DEPTH], blk_left[MOOG_MAX_COND_DEPTH];
+  int depth = 0;
+  for (;;) {
+    if (depth > 0 && r >= blk_end[depth - 1]) {
+      if (--blk_left[depth - 1] > 0) {
+        r = blk_start[depth - 1];
+      } else {
+        r = blk_end[depth - 1];
+        --depth;
+      }
+      continue;
+    }
+    if (depth == 0 && r >= end) break;
+    const moog_op *op = e.ops + r;
+    if (op->kind == MOOG_R_COND_BEGIN) {
+      int times = (int)eval_condition(e, op->i[0]);
+      int nsub = op->i[1];
+      if (times <= 0 || nsub <= 0 || depth == MOOG_MAX_COND_DEPTH) {
+        r += 1 + nsub;
+        continue;
+      }
+      blk_start[depth] = r + 1;
+      blk_end[depth] = r + 1 + nsub;
+      blk_left[depth] = times;
+      ++depth;
+      r += 1;
+      continue;
+    }
+    rule_leaf(e, r);
+    r += 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// action spaces
+// ---------------------------------------------------------------------------
+__device__ inline void actions_step(const Env &e, const double *action) {
+  const int32_t *h = e.hdr;
+  for (int a = 0; a < h[MOOG_H_N_ACTIONS]; ++a) {
+    const moog_op *op = e.ops + h[MOOG_H_ACTIONS] + a;
+    double a0 = action ? action[op->i[2]] : 0.0;
+    double a1 = (action && op->kind != MOOG_A_GRID) ? action[op->i[2] + 1] : 0.0;
+    int n = list_count(e, op->i[0], op->i[1]);
+    if (op->kind == MOOG_A_SET_POSITION) {  // set_position.py:34-47
+      for (int i = 0; i < n; ++i) {
+        int s = list_slot(e, op->i[0], op->i[1], i);
+        set_position(e, s, op->p[0] * DYN(e, MOOG_D_X, s) + (1 - op->p[0]) * a0,
+                     op->p[0] * DYN(e, MOOG_D_Y, s) + (1 - op->p[0]) * a1);
+      }
+      continue;
+    }
+    double *mem = e.envf + op->i[5];
+    double m0 = mem[0], m1 = mem[1];
+    if (op->kind == MOOG_A_JOYSTICK) {  // joystick.py:45-65
+      double ax = a0;
+      double ay = (op->flags & MOOG_FL_CONSTRAINED_LR) ? 0. : a1;
+      m0 = m0 * op->p[1] + op->p[0] * ax;
+      m1 = m1 * op->p[1] + op->p[0] * ay;
+    } else {  // grid.py:52-70: the UNIT action is added, then clipped
+      int k = action ? (int)a0 : 4;
+      if (k < 0 || k > 4) k = 4;
+      double gx = (k == 0) ? -1. : (k == 1) ? 1. : 0.;
+      double gy = (k == 2) ? -1. : (k == 3) ? 1. : 0.;
+      m0 = m0 * op->p[1] + gx;
+      m1 = m1 * op->p[1] + gy;
+    }
+    m0 = fmin(fmax(m0, -op->p[0]), op->p[0]);
+    m1 = fmin(fmax(m1, -op->p[0]), op->p[0]);
+    wsync();
+    put(e, &mem[0], m0);
+    put(e, &mem[1], m1);
+    wsync();
+    for (int i = 0; i < n; ++i) {
+      int s = list_slot(e, op->i[0], op->i[1], i);
+      double m = STAT(e, MOOG_S_MASS, s);
+      if (op->flags & MOOG_FL_CONTROL_VELOCITY)
+        assign_velocity(e, s, m0 / m, m1 / m);
+      else
+        add_velocity(e, s, m0 / m, m1 / m);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tasks
+// ---------------------------------------------------------------------------
+__device__ inline void tasks_reset(const Env &e) {
+  const int32_t *h = e.hdr;
+  wsync();
+  for (int t = 0; t < h[MOOG_H_N_TASKS]; ++t) {
+    const moog_op *op = e.ops + h[MOOG_H_TASKS] + t;
+    if (op->kind == MOOG_T_CONTACT_REWARD || op->kind == MOOG_T_RESET)
+      put(e, &e.envf[op->i[5]], INFINITY);  // contact_reward.py:67-68, reset.py:45-46
+  }
+  wsync();
+}
+
+__device__ inline void actions_reset(const Env &e) {
+  const int32_t *h = e.hdr;
+  wsync();
+  for (int a = 0; a < h[MOOG_H_N_ACTIONS]; ++a) {
+    const moog_op *op = e.ops + h[MOOG_H_ACTIONS] + a;
+    if (op->kind == MOOG_A_JOYSTICK || op->kind == MOOG_A_GRID) {
+      put(e, &e.envf[op->i[5]], 0.);  // joystick.py:67-70, grid.py:72-75
+      put(e, &e.envf[op->i[5] + 1], 0.);
+    }
+  }
+  wsync();
+}
+
+// composite_task.py:32-42 flattened over the task tree
+__device__ inline void tasks_reward(Env &e, int step_count, double *reward, int *should_reset) {
+  const int32_t *h = e.hdr;
+  double total = 0;
+  int reset = 0;
+  for (int t = 0; t < h[MOOG_H_N_TASKS]; ++t) {
+    const moog_op *op = e.ops + h[MOOG_H_TASKS] + t;
+    switch (op->kind) {
+      case MOOG_T_TIMEOUT:
+        if (step_count >= op->p[0]) reset = 1;
+        break;
+      case MOOG_T_STAY_ALIVE:  // stay_alive.py:22-32
+        if (((step_count + 1) % (int)op->p[0]) == 0) total += op->p[1];
+        break;
+      case MOOG_T_CONTACT_REWARD: {  // contact_reward.py:70-102
+        double r = 0;
+        double cd = e.envf[op->i[5]];
+        int n = list_count(e, op->i[0], op->i[1]);
+        int m = list_count(e, op->i[2], op->i[3]);
+        for (int i = 0; i < n; ++i) {
+          int sa = list_slot(e, op->i[0], op->i[1], i);
+          for (int j = 0; j < m; ++j) {
+            int sb = list_slot(e, op->i[2], op->i[3], j);
+            if (eval_expr(e, op->i[4], sa, sb) == 0) continue;
+            if (overlaps(e, sa, sb)) {
+              r = op->p[0];
+              if (cd == INFINITY) cd = op->p[1];
+            }
+          }
+        }
+        cd -= 1;
+        if (cd < 0) reset = 1;
+        wsync();
+        put(e, &e.envf[op->i[5]], cd);
+        wsync();
+        total += r;
+        break;
+      }
+      case MOOG_T_RESET: {  // reset.py:48-61
+        double r = 0.;
+        double cd = e.envf[op->i[5]];
+        if (cd == INFINITY && eval_condition(e, op->i[0]) != 0) {
+          r = op->p[1];
+          cd = op->p[0];
+        }
+        cd -= 1;
+        if (cd < 0) reset = 1;
+        wsync();
+        put(e, &e.envf[op->i[5]], cd);
+        wsync();
+        total += r;
+        break;
+      }
+    }
+  }
+  *reward = total;
+  *should_reset = reset;
+}
+
+// ---------------------------------------------------------------------------
+// staging: global <-> shared
+// ---------------------------------------------------------------------------
+__device__ inline void copy_d(double *dst, const double *src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__device__ inline void copy_i(int *dst, const int *src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__device__ inline void load_env(Env &e, const moog_state &st, size_t n, bool with_envi) {
+  int S = e.S, NF = e.hdr[MOOG_H_N_ENVF];
+  copy_d(e.dyn, st.dyn + n * MOOG_DYN_FIELDS * S, MOOG_DYN_FIELDS * S, e.lane);
+  copy_d(e.stat, st.stat + n * MOOG_STAT_FIELDS * S, MOOG_STAT_FIELDS * S, e.lane);
+  copy_i(e.meta, st.meta + n * MOOG_META_FIELDS * S, MOOG_META_FIELDS * S, e.lane);
+  copy_i(e.cnt, st.cnt + n * MOOG_MAX_LAYERS, MOOG_MAX_LAYERS, e.lane);
+  copy_d(e.envf, st.envf + n * NF, NF, e.lane);
+  copy_d((double *)e.vtx, st.vtx + n * 2 * (size_t)e.hdr[MOOG_H_N_VTX], 2 * e.hdr[MOOG_H_N_VTX], e.lane);
+  if (with_envi) copy_i(e.envi, st.envi + n * MOOG_ENVI_WORDS, MOOG_ENVI_WORDS, e.lane);
+}
+
+__device__ inline void store_env(const Env &e, const moog_state &st, size_t n) {
+  int S = e.S, NF = e.hdr[MOOG_H_N_ENVF];
+  copy_d(st.dyn + n * MOOG_DYN_FIELDS * S, e.dyn, MOOG_DYN_FIELDS * S, e.lane);
+  copy_d(st.stat + n * MOOG_STAT_FIELDS * S, e.stat, MOOG_STAT_FIELDS * S, e.lane);
+  copy_i(st.meta + n * MOOG_META_FIELDS * S, e.meta, MOOG_META_FIELDS * S, e.lane);
+  copy_i(st.cnt + n * MOOG_MAX_LAYERS, e.cnt, MOOG_MAX_LAYERS, e.lane);
+  copy_d(st.envf + n * NF, e.envf, NF, e.lane);
+  copy_d(st.vtx + n * 2 * (size_t)e.hdr[MOOG_H_N_VTX], (const double *)e.vtx, 2 * e.hdr[MOOG_H_N_VTX], e.lane);
+  copy_i(st.envi + n * MOOG_ENVI_WORDS, e.envi, MOOG_ENVI_WORDS, e.lane);
+}
+
+// environment.py:88-96: task / action reset, every rule reset and stepped once
+__device__ inline void post_reset(Env &e) {
+  wsync();
+  puti(e, &e.envi[MOOG_EI_STEP_COUNT], 0);
+  puti(e, &e.envi[MOOG_EI_RESET_NEXT], 0);
+  wsync();
+  tasks_reset(e);
+  actions_reset(e);
+  rules_step(e);
+}
+
+__global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= a.n_envs) return;
+
+  Env e;
+  ProgramView pv = view_of(a.blob);
+  e.hdr = pv.hdr; e.ops = pv.ops; e.ipool = pv.ipool; e.expr = pv.expr;
+  e.S = pv.hdr[MOOG_H_N_SLOTS];
+  e.L = pv.hdr[MOOG_H_N_LAYERS];
+  e.K = pv.hdr[MOOG_H_K];
+  e.VT = pv.hdr[MOOG_H_N_VTX];
+  e.lane = lane;
+  const int NF = pv.hdr[MOOG_H_N_ENVF];
+  SmemLayout lay = smem_layout(e.S, e.VT > 0 ? e.VT : 1, NF);
+  unsigned char *base = smem_raw + (size_t)warp * lay.total;
+  e.dyn = (double *)(base + lay.dyn);
+  e.stat = (double *)(base + lay.stat);
+  e.aabb = (double *)(base + lay.aabb);
+  e.tmp = (double *)(base + lay.tmp);
+  e.vtx = (double2 *)(base + lay.vtx);
+  e.envf = (double *)(base + lay.envf);
+  e.meta = (int *)(base + lay.meta);
+  e.sflag = (int *)(base + lay.sflag);
+  e.voff = (int *)(base + lay.voff);
+  e.cnt = (int *)(base + lay.cnt);
+  e.envi = (int *)(base + lay.envi);
+  e.vslot = base + lay.vslot;
+  e.env_id = n;
+  e.seed = a.io.seed;
+  e.substep = 0;
+  e.n_calls = e.n_true = e.n_coll = 0;
+  e.hash = 0;
+  const int ND = pv.hdr[MOOG_H_NOISE_DIM], RND = pv.hdr[MOOG_H_RULE_NOISE_DIM];
+  e.noise = a.io.noise ? a.io.noise + (size_t)n * e.K * ND : nullptr;
+  e.rule_noise = a.io.rule_noise ? a.io.rule_noise + (size_t)n * RND : nullptr;
+
+  // slot -> first cached vertex, vertex -> slot
+  for (int s = lane; s <= e.S; s += 32) e.voff[s] = pv.voff[s];
+  wsync();
+  for (int s = lane; s < e.S; s += 32)
+    for (int v = e.voff[s]; v < e.voff[s + 1]; ++v) e.vslot[v] = (unsigned char)s;
+
+  copy_i(e.envi, a.st.envi + (size_t)n * MOOG_ENVI_WORDS, MOOG_ENVI_WORDS, lane);
+  wsync();
+  const bool do_reset = a.mode == MODE_ENV_STEP && a.io.pool != nullptr && e.envi[MOOG_EI_RESET_NEXT] != 0;
+  if (do_reset) {
+    int idx;
+    if (a.io.reset_index) {
+      idx = a.io.reset_index[n];
+    } else {
+      double u = philox_uniform(a.io.seed ^ 0xD1B54A32D192ED03ull, (uint32_t)n, (uint32_t)e.envi[MOOG_EI_EPISODES], 0u, 0u);
+      idx = (int)(u * a.io.pool_size);
+    }
+    idx = idx < 0 ? 0 : (idx >= a.io.pool_size ? a.io.pool_size - 1 : idx);
+    load_env(e, a.pool, (size_t)idx, false);
+  } else {
+    load_env(e, a.st, (size_t)n, false);
+  }
+  wsync();
+  refresh_all_boxes(e);
+
+  double reward = 0.0;
+  int step_type = MOOG_STEP_MID;
+  double ep_len_done = 0.0, ep_done = 0.0;
+
+  if (a.mode == MODE_POST_RESET) {
+    post_reset(e);
+    reward = NAN;
+    step_type = MOOG_STEP_FIRST;
+  } else if (a.mode == MODE_PHYSICS) {
+    for (int k = 0; k < e.K; ++k) {
+      e.substep = k;
+      apply_physics(e);
+    }
+  } else if (a.mode == MODE_OVERLAP) {
+    int la = a.layer_a, lb = a.layer_b;
+    int ca = LOFF(e, la + 1) - LOFF(e, la), cb = LOFF(e, lb + 1) - LOFF(e, lb);
+    uint8_t *o = a.overlap_out + (size_t)n * ca * cb;
+    for (int i = lane; i < ca * cb; i += 32) o[i] = 0;
+    wsync();
+    for (int i = 0; i < e.cnt[la]; ++i)
+      for (int j = 0; j < e.cnt[lb]; ++j) {
+        bool r = overlaps(e, LOFF(e, la) + i, LOFF(e, lb) + j);
+        if (lane == 0) o[i * cb + j] = (uint8_t)r;
+      }
+  } else if (do_reset) {
+    int ep = e.envi[MOOG_EI_EPISODES] + 1;
+    wsync();
+    puti(e, &e.envi[MOOG_EI_EPISODES], ep);
+    post_reset(e);
+    reward = NAN;
+    step_type = MOOG_STEP_FIRST;
+  } else {
+    // environment.py:98-126
+    rules_step(e);
+    actions_step(e, a.io.actions ? a.io.actions + (size_t)n * pv.hdr[MOOG_H_ACTION_DIM] : nullptr);
+    for (int k = 0; k < e.K; ++k) {
+      e.substep = k;
+      apply_physics(e);
+    }
+    int sc = e.envi[MOOG_EI_STEP_COUNT] + 1;
+    wsync();
+    puti(e, &e.envi[MOOG_EI_STEP_COUNT], sc);
+    wsync();
+    int reset;
+    tasks_reward(e, sc, &reward, &reset);
+    step_type = reset ? MOOG_STEP_LAST : MOOG_STEP_MID;
+    wsync();
+    puti(e, &e.envi[MOOG_EI_RESET_NEXT], reset);
+    wsync();
+    if (reset) {
+      ep_len_done = (double)sc;
+      ep_done = 1.0;
+    }
+  }
+  wsync();
+  if (a.mode != MODE_OVERLAP) store_env(e, a.st, (size_t)n);
+  if (lane == 0) {
+    if (a.io.reward) a.io.reward[n] = (float)reward;
+    if (a.io.step_type) a.io.step_type[n] = step_type;
+    if (a.io.discount)
+      a.io.discount[n] = step_type == MOOG_STEP_FIRST ? NAN : (step_type == MOOG_STEP_LAST ? 0.0f : 1.0f);
+    if (a.io.counters) {
+      a.io.counters[4 * (size_t)n + 0] = e.n_calls;
+      a.io.counters[4 * (size_t)n + 1] = e.n_true;
+      a.io.counters[4 * (size_t)n + 2] = e.n_coll;
+      a.io.counters[4 * (size_t)n + 3] = (long long)e.hash;
+    }
+    if (a.io.stats && a.mode == MODE_ENV_STEP) {
+      if (step_type != MOOG_STEP_FIRST) {
+        if (reward != 0.0) atomicAdd(&a.io.stats[0], reward);
+        atomicAdd(&a.io.stats[3], 1.0);
+      }
+      if (ep_done != 0.0) {
+        atomicAdd(&a.io.stats[1], ep_len_done);
+        atomicAdd(&a.io.stats[2], ep_done);
+      }
+    }
+  }
+}
+
+cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
+  if (a.n_envs <= 0) return cudaSuccess;
+  int per_env = env_smem_bytes(hdr);
+  int warps = 2;
+  if (per_env * warps > 200 * 1024) warps = 1;
+  size_t smem = (size_t)per_env * warps;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(moog_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  int blocks = (a.n_envs + warps - 1) / warps;
+  moog_step_kernel<<<blocks, warps * 32, smem, stream>>>(a);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace moog

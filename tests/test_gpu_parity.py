@@ -1,0 +1,162 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors recorded from the unmodified reference.  Needs a B200.
+
+Bars (north_star): overlap / contact pair sets identical (call count, True
+count and the order-sensitive hash of the True (slot_a, slot_b) events), state
+within 1e-5 relative after a step -- and bit-exact on the scenes whose step
+involves only IEEE-exact operations (no sin / cos of a non-zero angle) --
+rewards and termination flags identical, frames identical to PILRenderer's.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+
+def _engine(prog, arrays, n=None):
+    from moog_b200.batched_env import Engine
+    n = arrays['dyn'].shape[0] if n is None else n
+    eng = Engine(prog, n, 'cuda:0')
+    eng.state.upload(arrays)
+    return eng
+
+
+def _compare_state(scene, t, prog, dev, ref_arrays, cnt, exact):
+    worst = 0.0
+    for e in range(cnt.shape[0]):
+        live = util.live_mask(prog, cnt[e])
+        for k in ('dyn', 'stat'):
+            worst = max(worst, util.rel_err(dev[k][e][:, live], ref_arrays[k][e][:, live]))
+        vlive = np.zeros(prog.n_vtx, dtype=bool)
+        voff = prog_voff(prog)
+        for s in np.nonzero(live)[0]:
+            vlive[voff[s]:voff[s] + int(ref_arrays['meta'][e][2, s])] = True
+        worst = max(worst, util.rel_err(dev['vtx'][e][vlive], ref_arrays['vtx'][e][vlive]))
+        assert np.array_equal(dev['meta'][e][:, live], ref_arrays['meta'][e][:, live]), (scene, t, 'meta')
+    if exact:
+        assert worst == 0.0, (scene, t, worst)
+    else:
+        assert worst <= util.RTOL, (scene, t, worst)
+    return worst
+
+
+def prog_voff(prog):
+    from moog_b200 import compiler as C
+    blob = np.frombuffer(prog.blob, dtype=np.uint8)
+    hdr = np.frombuffer(prog.blob[:C.HDR_WORDS * 4], dtype='<i4')
+    n_ops = int(hdr[C.H_N_OPS])
+    start = C.HDR_WORDS * 4 + 80 * n_ops
+    ipool = np.frombuffer(blob[start:start + 4 * int(hdr[C.H_N_IPOOL])].tobytes(), dtype='<i4')
+    return ipool[int(hdr[C.H_VOFF]):int(hdr[C.H_VOFF]) + prog.n_slots + 1]
+
+
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_cuda_follows_reference_trajectory(scene):
+    """Step by step along the golden trajectory: CUDA vs golden (reference)."""
+    g = util.load_golden(scene)
+    prog = g['program']
+    eng = _engine(prog, util.state_at(g, None, prefix='init'))
+    eng.post_reset()
+    dev = eng.state.download()
+    for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta'):
+        assert np.array_equal(dev[k][0], g['reset_' + k]), 'reset ' + k
+    exact = scene in util.EXACT_SCENES
+    T = len(g['reward'])
+    for t in range(T):
+        noise = g['noise'][t][None] if prog.noise_dim else None
+        eng.env_step(g['actions'][t][None], noise=noise, auto_reset=False, want_counters=True)
+        dev = eng.state.download()
+        assert np.array_equal(dev['cnt'][0], g['cnt'][t]), (scene, t)
+        ref = {k: g[k][t][None] for k in ('dyn', 'stat', 'vtx', 'meta')}
+        _compare_state(scene, t, prog, dev, ref, g['cnt'][t][None], exact)
+        assert float(eng.reward[0]) == np.float32(g['reward'][t]), (scene, t)
+        assert bool(int(eng.step_type[0]) == 2) == bool(g['last'][t]), (scene, t)
+        n_calls, n_true, _, h = eng.counters[0].tolist()
+        assert n_calls == g['n_calls'][t], (scene, t, 'overlap call count')
+        assert n_true == g['n_true'][t], (scene, t, 'overlap true count')
+        assert np.uint64(h & 0xFFFFFFFFFFFFFFFF) == g['true_hash'][t], (scene, t, 'overlap pair set')
+        # re-synchronise on the reference state so that one step is compared at a time
+        if not exact:
+            st = util.state_at(g, t)
+            st['envi'] = dev['envi']
+            st['envf'] = dev['envf']
+            eng.state.upload(st)
+
+
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_cuda_matches_oracle_batched(scene):
+    """Every state of the golden trajectory becomes one env of a batch; CUDA and
+    the oracle advance the batch 3 steps with the same seeded actions / noise."""
+    from oracle.oracle import Oracle
+    g = util.load_golden(scene)
+    prog = g['program']
+    T = len(g['reward'])
+    parts = [util.state_at(g, t) for t in range(-1, T - 1)]
+    arrays = {k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}
+    n = arrays['dyn'].shape[0]
+    rng = np.random.RandomState(7)
+    orc = Oracle(prog, arrays)
+    eng = _engine(prog, arrays)
+    exact = scene in util.EXACT_SCENES
+    for step in range(3):
+        ad = max(prog.action_dim, 1)
+        if any(kind == 'Grid' for _, kind, _, _ in getattr(prog, 'action_layout', [])) or ad == 1:
+            actions = rng.randint(0, 5, size=(n, ad)).astype(np.float64)
+        else:
+            actions = rng.uniform(-1, 1, size=(n, ad))
+        noise = rng.uniform(size=(n, prog.K, prog.noise_dim)) if prog.noise_dim else None
+        if not exact:
+            st = orc.arrays()
+            st = {k: v.copy() for k, v in st.items()}
+            eng.state.upload(st)
+        r_ref, st_ref = orc.step(actions, noise=noise)
+        eng.env_step(actions, noise=noise, auto_reset=False, want_counters=True)
+        dev = eng.state.download()
+        assert np.array_equal(dev['cnt'], orc.cnt), (scene, step)
+        _compare_state(scene, step, prog, dev, orc.arrays(), orc.cnt, exact)
+        assert np.array_equal(eng.reward.cpu().numpy(), r_ref.astype(np.float32)), (scene, step)
+        assert np.array_equal(eng.step_type.cpu().numpy(), st_ref), (scene, step)
+        c = eng.counters.cpu().numpy()
+        assert np.array_equal(c[:, 0], orc.counters[:, 0]), (scene, step, 'overlap call counts')
+        assert np.array_equal(c[:, 1], orc.counters[:, 1]), (scene, step, 'overlap true counts')
+        assert np.array_equal(c[:, 2], orc.counters[:, 2]), (scene, step, 'resolved collisions')
+        assert np.array_equal(c[:, 3], orc.counters[:, 3]), (scene, step, 'overlap pair sets')
+
+
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_cuda_render_matches_reference_frames(scene):
+    g = util.load_golden(scene)
+    prog = g['program']
+    if prog.render is None or len(g['frames']) == 0:
+        pytest.skip('scene has no renderer')
+    parts = [util.state_at(g, int(t)) for t in g['frame_steps']]
+    arrays = {k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}
+    eng = _engine(prog, arrays)
+    out = eng.render().cpu().numpy()
+    assert out.shape == g['frames'].shape
+    bad = int((out != g['frames']).sum())
+    assert bad == 0, (scene, bad)
+
+
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_cuda_overlap_pairs_match_oracle(scene):
+    from oracle.oracle import Oracle
+    g = util.load_golden(scene)
+    prog = g['program']
+    T = len(g['reward'])
+    parts = [util.state_at(g, t) for t in range(-1, T)]
+    arrays = {k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}
+    orc = Oracle(prog, arrays)
+    eng = _engine(prog, arrays)
+    names = prog.layer_names
+    for a in names:
+        for b in names:
+            ref = orc.overlap_pairs(a, b)
+            if ref.size == 0:
+                continue
+            out = eng.overlap_pairs(a, b).cpu().numpy()
+            assert np.array_equal(out, ref), (scene, a, b)
