@@ -250,7 +250,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not args.no_clocks:
+        sampler.start()
     launches0 = capi.launch_count()
     barrier()
     torch.cuda.synchronize()
@@ -271,6 +272,8 @@ def run_ours(args):
     ms_step_k = [ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]
     ms_rend_k = [ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]
     ms_total = float(np.sum(ms_step_k) + np.sum(ms_rend_k))
+    if args.verbose:
+        sys.stderr.write('step ms %s\nrender ms %s\n' % (ms_step_k, ms_rend_k))
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,6 +358,8 @@ def main():
     ap.add_argument('--scene', default='falling_balls20')
     ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
     ap.add_argument('--pool', type=int, default=128, help='host-generated initial states')
+    ap.add_argument('--no-clocks', action='store_true')
+    ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

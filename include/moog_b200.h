@@ -36,6 +36,8 @@ extern "C" {
 #define MOOG_E_TOO_BIG (-3)  /* one env record does not fit in shared memory   */
 #define MOOG_E_UNSUPPORTED (-4)
 
+#define MOOG_N_COUNTERS 8
+
 typedef struct moog_program moog_program;
 
 /* Device pointers to the SoA state record of N envs (layout: moog_b200_program.h). */
@@ -65,8 +67,9 @@ typedef struct {
   float *reward;       /* [N]  TimeStep.reward   (NaN on a FIRST step: dm_env's None)           */
   int32_t *step_type;  /* [N]  MOOG_STEP_FIRST / MID / LAST                                     */
   float *discount;     /* [N]  1 mid, 0 last, NaN first                                         */
-  int64_t *counters;   /* [N][4] overlaps_sprite calls, calls that returned True, resolved
-                          collisions, order-sensitive hash of the True (slot_a, slot_b) events   */
+  int64_t *counters;   /* [N][MOOG_N_COUNTERS]: overlaps_sprite calls, calls that returned True,
+                          resolved collisions, order-sensitive hash of the True (slot_a, slot_b)
+                          events, SM cycles the env's warp spent in the kernel, 3 spare          */
   double *stats;       /* [4]  += sum reward, sum finished-episode length, finished episodes,
                           env-steps; the only quantity ever reduced across GPUs                 */
 } moog_step_io;

@@ -121,7 +121,7 @@ class Engine(object):
         self.reward = torch.zeros(self.n, **f32)
         self.discount = torch.zeros(self.n, **f32)
         self.step_type = torch.zeros(self.n, dtype=torch.int32, device=self.device)
-        self.counters = torch.zeros((self.n, 4), dtype=torch.int64, device=self.device)
+        self.counters = torch.zeros((self.n, 8), dtype=torch.int64, device=self.device)
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.frames = None
         if program.render is not None:

@@ -20,6 +20,12 @@ namespace moog {
 #define MAXV MOOG_MAX_VERTS
 #define MAX_XX (2 * MAXV + 8)
 
+// C `(int)double` as the reference's host executes it (x86-64 cvttsd2si): NaN and
+// out-of-range values give INT_MIN (CUDA's conversion would saturate / give 0)
+__device__ __forceinline__ int c_int_cast(double v) {
+  return (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
+}
+
 __device__ __forceinline__ unsigned div255(unsigned a) { return (((a + 128) >> 8) + (a + 128)) >> 8; }
 
 __device__ __forceinline__ unsigned blend_px(unsigned bg, unsigned ink) {
@@ -258,7 +264,7 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
       double2 p = vtx[v];
       double x = p.x, y = p.y;
       if (pmod != MOOG_PMOD_NONE) { x = x + ox; y = y + oy; }
-      ivtx[v] = make_int2((int)((double)W * x), (int)((double)H * y));
+      ivtx[v] = make_int2(c_int_cast((double)W * x), c_int_cast((double)H * y));
     }
     for (int s = t; s < S; s += T)
       ink[s] = color_to_ink(cmap, stat[MOOG_S_C0 * S + s], stat[MOOG_S_C1 * S + s], stat[MOOG_S_C2 * S + s],

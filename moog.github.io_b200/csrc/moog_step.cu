@@ -41,6 +41,9 @@ namespace moog {
 #define SHORT_EDGE2 1e-8
 
 #define SLF_SHORT_EDGE 1  // slot flag: some edge is shorter than 1e-4 -> serial matplotlib path
+#define SLF_NONFINITE 2   // some cached vertex coordinate is NaN / inf -> no culling at all
+#define SLF_ALLNAN 4      // every cached vertex coordinate is NaN -> overlaps nothing
+#define SLF_MASK 7
 
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
@@ -201,31 +204,20 @@ __device__ __forceinline__ double moment_of_inertia(const Env &e, int s) {
 // bounding boxes of the cached outlines
 // ---------------------------------------------------------------------------
 
-// lane-parallel over the vertices of slot s: box + short-edge flag
-__device__ inline void refresh_box(const Env &e, int s) {
+// lane-parallel over the vertices of slot s: NaN / inf classification (called
+// when a setter moved the outline by a non-finite amount)
+__device__ inline void classify_slot(const Env &e, int s) {
   int n = META(e, MOOG_M_NV, s);
   const double2 *v = e.vtx + e.voff[s];
-  int i = e.lane < n ? e.lane : 0;
-  double2 p = n > 0 ? v[i] : make_double2(0., 0.);
-  double2 q = n > 0 ? v[(i + 1 == n) ? 0 : i + 1] : p;
-  double len2 = (p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y);
-  bool shortedge = (e.lane < n) && !(len2 > SHORT_EDGE2);
-  double xmin = p.x, xmax = p.x, ymin = p.y, ymax = p.y;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    xmin = fmin(xmin, shflx_d(xmin, o));
-    xmax = fmax(xmax, shflx_d(xmax, o));
-    ymin = fmin(ymin, shflx_d(ymin, o));
-    ymax = fmax(ymax, shflx_d(ymax, o));
-  }
-  unsigned sh = __ballot_sync(FULL, shortedge);
-  if (e.lane == 0) {
-    BOX(e, 0, s) = xmin;
-    BOX(e, 1, s) = ymin;
-    BOX(e, 2, s) = xmax;
-    BOX(e, 3, s) = ymax;
-    e.sflag[s] = (sh || n < 3) ? SLF_SHORT_EDGE : 0;
-  }
+  bool act = e.lane < n;
+  double2 p = act ? v[e.lane] : make_double2(0., 0.);
+  bool nonfinite = act && !(isfinite(p.x) && isfinite(p.y));
+  bool nan2 = !act || (isnan(p.x) && isnan(p.y));
+  unsigned nf = __ballot_sync(FULL, nonfinite);
+  bool allnan = __all_sync(FULL, nan2) && n > 0;
+  int fl = (e.sflag[s] & ~(SLF_NONFINITE | SLF_ALLNAN)) | (nf ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+  wsync();
+  puti(e, &e.sflag[s], fl);
   wsync();
 }
 
@@ -235,7 +227,7 @@ __device__ inline void refresh_all_boxes(const Env &e) {
     int n = META(e, MOOG_M_NV, s);
     const double2 *v = e.vtx + e.voff[s];
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-    bool sh = n < 3;
+    bool sh = n < 3, nonfinite = false, allnan = n > 0;
     double2 prev = n > 0 ? v[n - 1] : make_double2(0., 0.);
     for (int i = 0; i < n; ++i) {
       double2 p = v[i];
@@ -243,10 +235,12 @@ __device__ inline void refresh_all_boxes(const Env &e) {
       ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
       double len2 = (p.x - prev.x) * (p.x - prev.x) + (p.y - prev.y) * (p.y - prev.y);
       sh |= !(len2 > SHORT_EDGE2);
+      nonfinite |= !(isfinite(p.x) && isfinite(p.y));
+      allnan &= isnan(p.x) && isnan(p.y);
       prev = p;
     }
     BOX(e, 0, s) = xmin; BOX(e, 1, s) = ymin; BOX(e, 2, s) = xmax; BOX(e, 3, s) = ymax;
-    e.sflag[s] = sh ? SLF_SHORT_EDGE : 0;
+    e.sflag[s] = (sh ? SLF_SHORT_EDGE : 0) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
   }
   wsync();
 }
@@ -280,6 +274,7 @@ __device__ inline void set_position(const Env &e, int s, double nx, double ny) {
     BOX(e, 0, s) = b0 + tx; BOX(e, 1, s) = b1 + ty; BOX(e, 2, s) = b2 + tx; BOX(e, 3, s) = b3 + ty;
   }
   wsync();
+  if (!(isfinite(tx) && isfinite(ty))) classify_slot(e, s);
 }
 
 struct Aff { double m0, m1, m2, m3, m4, m5; };  // rows 0,1 of the 3x3 (row 2 = 0 0 1)
@@ -399,7 +394,13 @@ __device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
   const double2 *A = e.vtx + e.voff[a];
   const double2 *B = e.vtx + e.voff[b];
   int nA = META(e, MOOG_M_NV, a), nB = META(e, MOOG_M_NV, b);
-  bool serial = (e.sflag[a] | e.sflag[b]) & SLF_SHORT_EDGE;
+  const int fl = e.sflag[a] | e.sflag[b];
+  // an outline whose every coordinate is NaN intersects nothing and contains /
+  // is contained in nothing: every segment test has a NaN denominator, every
+  // crossing-number comparison is false
+  if (fl & SLF_ALLNAN) return false;
+  const bool nocull = (fl & SLF_NONFINITE) != 0;  // boxes are meaningless with NaN / inf around
+  bool serial = (fl & (SLF_SHORT_EDGE | SLF_NONFINITE)) != 0;
   if (serial) {
     if (path_intersects_path_serial(A, nA, B, nB)) return true;
   } else {
@@ -442,10 +443,10 @@ __device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
   // outside the outline, so "all inside" needs box containment first
   bool b_in_a_box = BOX(e, 0, b) >= BOX(e, 0, a) - AABB_PAD && BOX(e, 2, b) <= BOX(e, 2, a) + AABB_PAD &&
                     BOX(e, 1, b) >= BOX(e, 1, a) - AABB_PAD && BOX(e, 3, b) <= BOX(e, 3, a) + AABB_PAD;
-  if (b_in_a_box && all_points_in_poly(e, B, nB, A, nA)) return true;  // b inside a
+  if ((b_in_a_box || nocull) && all_points_in_poly(e, B, nB, A, nA)) return true;  // b inside a
   bool a_in_b_box = BOX(e, 0, a) >= BOX(e, 0, b) - AABB_PAD && BOX(e, 2, a) <= BOX(e, 2, b) + AABB_PAD &&
                     BOX(e, 1, a) >= BOX(e, 1, b) - AABB_PAD && BOX(e, 3, a) <= BOX(e, 3, b) + AABB_PAD;
-  if (a_in_b_box && all_points_in_poly(e, A, nA, B, nB)) return true;  // a inside b
+  if ((a_in_b_box || nocull) && all_points_in_poly(e, A, nA, B, nB)) return true;  // a inside b
   return false;
 }
 
@@ -464,7 +465,7 @@ __device__ inline bool overlaps(Env &e, int a, int b) {
   double dy = DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, b);
   double center_dist = norm1(dx, dy);
   if (!(center_dist > STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b))) {
-    if (!boxes_apart(e, a, b)) r = path_intersects_filled(e, a, b);
+    if (((e.sflag[a] | e.sflag[b]) & SLF_NONFINITE) || !boxes_apart(e, a, b)) r = path_intersects_filled(e, a, b);
   }
   count_overlap(e, a, b, r);
   return r;
@@ -869,7 +870,9 @@ __device__ inline void collision_row(Env &e, const moog_op *op, int s0, int lb) 
           double dx = DYN(e, MOOG_D_X, s0) - DYN(e, MOOG_D_X, s1);
           double dy = DYN(e, MOOG_D_Y, s0) - DYN(e, MOOG_D_Y, s1);
           double cd = norm1(dx, dy);
-          c = !(cd > STAT(e, MOOG_S_MAXR, s0) + STAT(e, MOOG_S_MAXR, s1)) && !boxes_apart(e, s0, s1);
+          int fl = e.sflag[s0] | e.sflag[s1];
+          c = !(cd > STAT(e, MOOG_S_MAXR, s0) + STAT(e, MOOG_S_MAXR, s1)) && !(fl & SLF_ALLNAN) &&
+              ((fl & SLF_NONFINITE) || !boxes_apart(e, s0, s1));
         }
         cand = __ballot_sync(FULL, c);
         recompute = false;
@@ -1131,6 +1134,7 @@ __device__ __noinline__ void corrective(const Env &e, const moog_op *op) {
 // ---------------------------------------------------------------------------
 #define TF_MOVE 1
 #define TF_ROT 2
+#define TF_CLASSIFY 4
 
 __device__ inline void integrate_all(const Env &e) {
   double dt = 1. / e.K;
@@ -1180,7 +1184,9 @@ __device__ inline void integrate_all(const Env &e) {
         flag |= TF_ROT;
       }
     }
-    e.sflag[s] = (e.sflag[s] & SLF_SHORT_EDGE) | (flag << 8);
+    if (vs_layer_live && !(isfinite(TMP(e, 0, s)) && isfinite(TMP(e, 1, s)))) flag |= TF_CLASSIFY;
+    if ((flag & TF_ROT) && (e.sflag[s] & SLF_NONFINITE)) flag |= TF_CLASSIFY;
+    e.sflag[s] = (e.sflag[s] & SLF_MASK) | (flag << 8);
   }
   wsync();
   // phase 2: lane = cached vertex
@@ -1215,7 +1221,19 @@ __device__ inline void integrate_all(const Env &e) {
       }
       BOX(e, 0, s) = xmin; BOX(e, 1, s) = ymin; BOX(e, 2, s) = xmax; BOX(e, 3, s) = ymax;
     }
-    e.sflag[s] &= SLF_SHORT_EDGE;
+    int low = e.sflag[s] & SLF_MASK;
+    if (flag & TF_CLASSIFY) {
+      int n = META(e, MOOG_M_NV, s);
+      const double2 *v = e.vtx + e.voff[s];
+      bool nonfinite = false, allnan = n > 0;
+      for (int i = 0; i < n; ++i) {
+        double2 p = v[i];
+        nonfinite |= !(isfinite(p.x) && isfinite(p.y));
+        allnan &= isnan(p.x) && isnan(p.y);
+      }
+      low = (low & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+    }
+    e.sflag[s] = low;
   }
   wsync();
 }
@@ -1686,6 +1704,7 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + warp;
   if (n >= a.n_envs) return;
+  const long long t_begin = clock64();
 
   Env e;
   ProgramView pv = view_of(a.blob);
@@ -1806,10 +1825,14 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
     if (a.io.discount)
       a.io.discount[n] = step_type == MOOG_STEP_FIRST ? NAN : (step_type == MOOG_STEP_LAST ? 0.0f : 1.0f);
     if (a.io.counters) {
-      a.io.counters[4 * (size_t)n + 0] = e.n_calls;
-      a.io.counters[4 * (size_t)n + 1] = e.n_true;
-      a.io.counters[4 * (size_t)n + 2] = e.n_coll;
-      a.io.counters[4 * (size_t)n + 3] = (long long)e.hash;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 0] = e.n_calls;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 1] = e.n_true;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 2] = e.n_coll;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 3] = (long long)e.hash;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 4] = clock64() - t_begin;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 5] = 0;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 6] = 0;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 7] = 0;
     }
     if (a.io.stats && a.mode == MODE_ENV_STEP) {
       if (step_type != MOOG_STEP_FIRST) {

@@ -58,6 +58,10 @@ SCENES = {
     'colliding_predators': ('moog_demos.example_configs.colliding_predators', None, 3, 50, 10),
     'predators_arena': ('moog_demos.example_configs.predators_arena', 3, 4, 40, 10),
     'synthetic32': ('moog_b200.configs.synthetic32', None, 5, 30, 10),
+    # a ball-ball contact whose back-projected vertex has no valid crossing: the
+    # reference's argmax picks the NaN entry (collisions.py:207-209) and the sprite's
+    # position becomes NaN for the rest of the episode
+    'falling_balls20_nan': ('moog_b200.configs.falling_balls20', None, 297, 8, 2),
 }
 
 
