@@ -126,64 +126,92 @@ class ClockSampler(object):
 # CPU arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------
 
-def cpu_oracle_throughput(scene, envs_per_thread, steps, threads, seed=1234):
-    """env-steps/s (incl. render) of oracle/ on `threads` host threads."""
-    from concurrent.futures import ThreadPoolExecutor
-    from moog_b200 import compiler
-    from oracle.oracle import Oracle, lib as orc_lib
-    orc_lib()
-    config = _scene_config(scene)
-    states = _host_states(config, max(8, min(64, envs_per_thread)), seed)
-    prog = compiler.compile_config(config, states)
-    base = compiler.pack_states(prog, states)
-    oracles = []
-    for t in range(threads):
-        idx = np.arange(envs_per_thread) % len(states)
-        arr = {k: np.ascontiguousarray(base[k][idx]) for k in ('dyn', 'stat', 'meta', 'cnt', 'envi', 'envf', 'vtx')}
-        o = Oracle(prog, arr)
-        o.post_reset()
-        oracles.append(o)
-    ad = max(prog.action_dim, 1)
-    actions = np.zeros((envs_per_thread, ad))
-    render = prog.render is not None
+class CpuArm(object):
+    """The oracle port (oracle/moog_oracle.c + pil_oracle.c) on the host cores.
 
-    def work(o):
+    One Oracle of `envs_per_thread` envs per thread (ctypes releases the GIL).
+    Thread t is pre-advanced by t/threads of an episode (untimed), and envs are
+    re-initialised when their episode ends, so any timed window sees the same
+    uniform mix of episode phases as the GPU arm.
+    """
+
+    def __init__(self, scene, envs_per_thread=8, threads=None, episode=100, seed=1234):
+        from moog_b200 import compiler
+        from oracle.oracle import Oracle, lib as orc_lib
+        orc_lib()
+        self.threads = threads or (os.cpu_count() or 1)
+        self.n = envs_per_thread
+        self.episode = episode
+        config = _scene_config(scene)
+        states = _host_states(config, max(16, envs_per_thread), seed)
+        self.prog = compiler.compile_config(config, states)
+        base = compiler.pack_states(self.prog, states)
+        self.keys = ('dyn', 'stat', 'meta', 'cnt', 'envi', 'envf', 'vtx')
+        self.init = []
+        self.oracles = []
+        for t in range(self.threads):
+            idx = (np.arange(self.n) + t * self.n) % len(states)
+            arr = {k: np.ascontiguousarray(base[k][idx]) for k in self.keys}
+            self.init.append(arr)
+            o = Oracle(self.prog, arr)
+            o.post_reset()
+            self.oracles.append(o)
+        self.actions = np.zeros((self.n, max(self.prog.action_dim, 1)))
+        self.render = self.prog.render is not None
+        self._pool = None
+
+    def _advance(self, t, steps, render=True):
+        o = self.oracles[t]
         for _ in range(steps):
-            o.step(actions)
-            if render:
+            _, st = o.step(self.actions)
+            if render and self.render:
                 o.render()
+            if (st == 2).all():      # environment.py:100-101: next step() is reset()
+                for k in self.keys:
+                    getattr(o, k)[...] = self.init[t][k]
+                o.post_reset()
+                if render and self.render:
+                    o.render()
         return True
 
-    for o in oracles:   # warm-up: one step each
-        o.step(actions)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(work, oracles))
-    dt = time.perf_counter() - t0
-    total = threads * envs_per_thread * steps
-    return total / dt, dt, total
+    def _map(self, fn):
+        from concurrent.futures import ThreadPoolExecutor
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=self.threads)
+        return list(self._pool.map(fn, range(self.threads)))
+
+    def stagger(self):
+        self._map(lambda t: self._advance(t, (t * self.episode) // self.threads, render=False))
+
+    def run(self, steps):
+        """Advances every env by `steps` env-steps; returns (env-steps/s, seconds, env-steps)."""
+        t0 = time.perf_counter()
+        self._map(lambda t: self._advance(t, steps))
+        dt = time.perf_counter() - t0
+        total = self.threads * self.n * steps
+        return total / dt, dt, total
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_thread = 16
-    # ~0.4 s of CPU work per thread per step of the sample
-    vals = []
+    arm = CpuArm(args.scene, envs_per_thread=8, episode=args.episode)
+    arm.stagger()
+    per_step = 5   # env-steps per env per timed step: 20 steps cover a whole episode
     for _ in range(args.warmup):
-        cpu_oracle_throughput(args.scene, per_thread, 1, cores)
+        arm.run(1)
+    vals = []
     t0 = time.perf_counter()
-    total_steps = 0
+    total = 0
     for _ in range(args.steps):
-        v, dt, n = cpu_oracle_throughput(args.scene, per_thread, 2, cores)
+        v, dt, n = arm.run(per_step)
         vals.append(v)
-        total_steps += n
+        total += n
     wall = time.perf_counter() - t0
-    value = float(np.mean(vals))
-    sample = '{} threads x {} envs x 2 env-steps per timed step of {} (oracle/moog_oracle.c + pil_oracle.c)'.format(
-        cores, per_thread, args.scene)
+    value = total / wall
+    sample = ('{} threads x {} envs x {} env-steps per timed step of {} (oracle/moog_oracle.c + pil_oracle.c, '
+              'uniform episode-phase mix)').format(arm.threads, arm.n, per_step, args.scene)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -191,11 +219,11 @@ def run_reference(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': args.scene, 'envs_per_gpu': args.envs, 'image': '64x64x3',
                    'note': 'CPU oracle port of Environment.step + PILRenderer on all host threads'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line, default=_json_default))
 
 
 # ---------------------------------------------------------------------------
@@ -206,6 +234,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from moog_b200 import capi
+    from moog_b200 import dist as mdist
     from moog_b200.batched_env import BatchedEnvironment
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -220,7 +249,7 @@ def run_ours(args):
 
     config = _scene_config(args.scene)
     E = args.envs
-    seed = 1234 + 1000 * rank
+    seed = mdist.rank_seed(1234, rank)
     states = _host_states(config, args.pool, seed)
     env = BatchedEnvironment(**config, num_envs=E, device=dev, seed=seed, initial_states=states)
     eng = env.engine
@@ -237,6 +266,19 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     env.reset()
+    # Burn-in: every env is force-reset once at a random time of the first
+    # `episode` steps (host sets its reset_next word), so that by the timed region
+    # the batch holds a uniform mix of episode phases -- free fall, first contacts,
+    # settled piles, and ~1/episode of the envs resetting per step -- instead of
+    # N copies of step 0.
+    episode = args.episode
+    phase = torch.randint(0, episode, (E,), generator=g).to(dev)
+    for t in range(args.burn_in):
+        if t < episode:
+            eng.state.envi[:, 1] = torch.where(phase == t, torch.ones_like(phase, dtype=torch.int32),
+                                               eng.state.envi[:, 1])
+        eng.env_step(dev_actions)
+    eng.stats.zero_()
     torch.cuda.synchronize()
 
     def barrier():
@@ -274,10 +316,7 @@ def run_ours(args):
     ms_total = float(np.sum(ms_step_k) + np.sum(ms_rend_k))
     if args.verbose:
         sys.stderr.write('step ms %s\nrender ms %s\n' % (ms_step_k, ms_rend_k))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
+    ms_total_max = mdist.max_over_ranks(ms_total, dev)
     value = world * E * args.steps / (ms_total_max * 1e-3)
 
     # ---- end-to-end arm: host actions in, host TimeStep (frames included) out --
@@ -296,10 +335,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()         # the caller owns the TimeStep now
     e1.record()
     torch.cuda.synchronize()
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * args.steps / (float(te.item()) * 1e-3)
+    e2e_value = world * E * args.steps / (mdist.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3)
     h2d = host_actions.numel() * host_actions.element_size()
     d2h = host_frames.numel() + host_reward.numel() * 4 + host_step_type.numel() * 4
 
@@ -322,6 +358,7 @@ def run_ours(args):
         'config': {'workload': args.scene, 'envs_per_gpu': E, 'sprites': prog.n_slots,
                    'substeps': prog.K, 'image': '{}x{}x3'.format(H, W), 'parallelism': 'env-sharded x{}'.format(world),
                    'l2': 'flushed between timed iterations (256 MiB fill, untimed)',
+                   'phases': 'uniform mix of episode phases after {} burn-in steps with staggered resets'.format(args.burn_in),
                    'state_record_bytes': int(record_bytes)},
         'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
@@ -338,12 +375,13 @@ def run_ours(args):
         'wall_s_timed_region': t_wall,
     }
     if not args.no_cpu:
-        cores = os.cpu_count() or 1
-        v, dt, n = cpu_oracle_throughput(args.scene, 16, 4, cores)
+        arm = CpuArm(args.scene, envs_per_thread=8, episode=args.episode)
+        arm.stagger()
+        v, dt, n = arm.run(args.episode)     # every env walks one whole episode
         line['cpu_baseline'] = {
-            'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '{} env-steps of {} (16 envs x 4 steps per thread, {} threads, {:.1f} s)'.format(
-                n, args.scene, cores, dt)}
+            'value': v, 'unit': UNIT, 'cores': arm.threads, 'kind': 'port',
+            'sample': '{} env-steps of {} incl. render: {} threads x 8 envs x one whole {}-step episode each '
+                      '(uniform phase mix), {:.1f} s'.format(n, args.scene, arm.threads, args.episode, dt)}
     print(json.dumps(line, default=_json_default))
     if world > 1:
         dist.destroy_process_group()
@@ -357,7 +395,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scene', default='falling_balls20')
     ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
-    ap.add_argument('--pool', type=int, default=128, help='host-generated initial states')
+    ap.add_argument('--pool', type=int, default=512, help='host-generated initial states')
+    ap.add_argument('--episode', type=int, default=100, help='episode length used to stagger phases')
+    ap.add_argument('--burn-in', type=int, default=130, help='untimed steps before the timed region')
     ap.add_argument('--no-clocks', action='store_true')
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')

@@ -316,10 +316,9 @@ class BatchedEnvironment(object):
     def episode_stats(self, reduce=True):
         """[sum reward, sum finished-episode length, finished episodes, env-steps];
         summed over ranks with one NCCL all_reduce when torch.distributed is up."""
+        from . import dist as mdist
         s = self.engine.stats.clone()
-        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(s)
-        return s
+        return mdist.reduce_stats(s) if reduce else s
 
     @property
     def action_dim(self):

@@ -1,0 +1,186 @@
+"""CPU-side tests: the C-ABI library loads and exports what include/moog_b200.h
+declares, the host geometry agrees with the oracle, the product path refuses to
+run without a GPU, the env-sharding logic works over 2 gloo ranks."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import util
+
+ROOT = util.ROOT
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, 'include', 'moog_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(moog_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import moog_b200  # noqa: F401
+    from moog_b200 import build, capi
+    lib = build.build()
+    L = ctypes.CDLL(lib)
+    declared = _header_functions()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(capi.SYMBOLS) == declared
+
+
+def test_program_blob_is_validated_without_a_gpu():
+    """moog_program_create rejects malformed blobs before touching CUDA."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import capi
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    junk = ctypes.create_string_buffer(b'\0' * 512, 512)
+    assert L.moog_program_create(junk, 512, ctypes.byref(h)) == -1
+    assert L.moog_strerror(-1).decode().startswith('invalid')
+
+
+def test_host_geometry_matches_oracle():
+    """moog_host_paths_overlap (host Sprite.overlaps_sprite) vs the oracle's
+    restatement of Path.intersects_path on random near-touching polygons."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import capi
+    from oracle.oracle import lib as orc_lib
+    L, O = capi.lib(), orc_lib()
+    O.orc_path_intersects_filled.restype = ctypes.c_int
+    rng = np.random.RandomState(0)
+    n_true = 0
+    for trial in range(4000):
+        polys = []
+        for _ in range(2):
+            n = rng.randint(3, 12)
+            ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+            r = rng.uniform(0.05, 0.2)
+            c = rng.uniform(0.3, 0.7, 2)
+            p = c + r * np.stack([np.cos(ang), np.sin(ang)], 1)
+            polys.append(np.ascontiguousarray(np.vstack([p, p[:1]])))
+        a, b = polys
+        ra = L.moog_host_paths_overlap(a.ctypes.data_as(ctypes.c_void_p), len(a),
+                                       b.ctypes.data_as(ctypes.c_void_p), len(b))
+        rb = O.orc_path_intersects_filled(a.ctypes.data_as(ctypes.c_void_p), len(a),
+                                          b.ctypes.data_as(ctypes.c_void_p), len(b))
+        assert bool(ra) == bool(rb), trial
+        n_true += bool(ra)
+    assert 200 < n_true < 3800
+
+
+def test_device_path_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    import moog_b200  # noqa: F401
+    from moog_b200 import capi
+    from moog_b200.batched_env import Engine
+    g = util.load_golden('pong')
+    with pytest.raises(capi.MoogError):
+        Engine(g['program'], 4, 'cuda:0')
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, 'moog.github.io_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                assert 'libmoog_oracle' not in text, f
+
+
+def test_compile_shipped_style_config_and_pack_states():
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from moog_b200.configs import falling_balls20
+    np.random.seed(3)
+    cfg = falling_balls20.get_config()
+    states = [cfg['state_initializer']() for _ in range(3)]
+    prog = compiler.compile_config(cfg, states)
+    assert prog.layer_names == ['walls', 'balls', 'agent']
+    assert prog.n_slots == 24 and prog.K == 20 and prog.n_vtx == 4 * 4 + 20 * 30
+    arr = compiler.pack_states(prog, states)
+    assert arr['dyn'].shape == (3, 6, 24) and arr['vtx'].shape == (3, 616, 2)
+    assert (arr['cnt'][:, :3] == [4, 20, 0]).all()
+    hdr = np.frombuffer(prog.blob[:256], dtype='<i4')
+    assert hdr[compiler.H_MAGIC] == compiler.MAGIC and hdr[compiler.H_BYTES] == len(prog.blob)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import moog_b200
+from moog_b200 import dist as mdist
+from oracle.oracle import Oracle
+from tests import util
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+g = util.load_golden('falling_balls20')
+prog = g['program']
+T = 10
+parts = [util.state_at(g, t) for t in range(T)]
+arrays = {{k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}}
+lo, hi = mdist.shard_range(T, rank, world)
+mine = {{k: v[lo:hi] for k, v in arrays.items()}}
+orc = Oracle(prog, mine)
+stats = torch.zeros(4, dtype=torch.float64)
+for step in range(3):
+    r, st = orc.step(np.zeros((hi - lo, 1)))
+    stats[0] += float(r.sum()); stats[3] += hi - lo
+    stats[2] += float((st == 2).sum())
+mdist.reduce_stats(stats)
+slowest = mdist.max_over_ranks(1.0 + rank)
+chk = torch.tensor([float(orc.dyn.sum())], dtype=torch.float64)
+dist.all_reduce(chk)
+if rank == 0:
+    full = Oracle(prog, arrays)
+    for step in range(3):
+        full.step(np.zeros((T, 1)))
+    assert stats[3] == 3 * T, stats
+    assert slowest == float(world), slowest
+    assert abs(chk.item() - full.dyn.sum()) < 1e-9, (chk.item(), full.dyn.sum())
+    print('OK')
+dist.destroy_process_group()
+'''
+
+
+def test_env_sharding_over_two_gloo_ranks(tmp_path):
+    """world_size-2 run of the N>1 host logic on CPU: contiguous env shards, the
+    stats all_reduce, max-over-ranks timing; sharded result == unsharded."""
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=240) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert 'OK' in outs[0][0]
+
+
+def test_shard_range_partitions():
+    import moog_b200  # noqa: F401
+    from moog_b200 import dist as mdist
+    for n in (0, 1, 7, 4096, 1 << 20):
+        for w in (1, 2, 3, 8):
+            spans = [mdist.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans[:-1], spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
