@@ -101,7 +101,11 @@ enum {
   MOOG_H_RULE_NOISE_DIM, /* uniforms per env per step consumed by sample_one rules */
   MOOG_H_VOFF,           /* index in ipool of voff[S+1]: first cached vertex of each slot */
   MOOG_H_LAYER_OFF = 32, /* MOOG_MAX_LAYERS+1 words */
-  MOOG_H_N_VTX = 49      /* VT: cached vertices per env */
+  MOOG_H_N_VTX = 49,     /* VT: cached vertices per env */
+  MOOG_H_CMASK_WORDS = 50 /* 32-bit words of the per-env broad-phase candidate matrices of all
+                             MOOG_F_COLLISION ops (rows = capacity of layer a, ceil(capacity of
+                             layer b / 32) words per row).  Derived: moog_program_create fills
+                             it in, whatever the blob says. */
 };
 
 enum { MOOG_CMAP_NONE = 0, MOOG_CMAP_HSV = 1 };

@@ -40,13 +40,21 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
   size_t need = sizeof(int32_t) * MOOG_HDR_WORDS + sizeof(moog_op) * (size_t)hdr[MOOG_H_N_OPS] +
                 sizeof(int32_t) * (size_t)((hdr[MOOG_H_N_IPOOL] + 1) & ~1) + sizeof(moog_ex) * (size_t)hdr[MOOG_H_N_EXPR];
   if (need != nbytes) return MOOG_E_INVAL;
-  if (moog::env_smem_bytes(hdr) > 220 * 1024) return MOOG_E_TOO_BIG;
+  if (hdr[MOOG_H_N_FORCES] > moog::kMaxForceOps) return MOOG_E_TOO_BIG;
   moog_program *p = (moog_program *)calloc(1, sizeof(moog_program));
   if (!p) return MOOG_E_INVAL;
   memcpy(p->hdr, hdr, sizeof(p->hdr));
+  p->hdr[MOOG_H_CMASK_WORDS] = moog::candidate_matrix_words(blob);
+  if (moog::env_smem_bytes(p->hdr) > 220 * 1024) {
+    free(p);
+    return MOOG_E_TOO_BIG;
+  }
   p->nbytes = nbytes;
   cudaError_t err = cudaMalloc(&p->dev_blob, nbytes);
   if (err == cudaSuccess) err = cudaMemcpy(p->dev_blob, blob, nbytes, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess)  // the derived header word, in the device copy too
+    err = cudaMemcpy((int32_t *)p->dev_blob + MOOG_H_CMASK_WORDS, &p->hdr[MOOG_H_CMASK_WORDS], sizeof(int32_t),
+                     cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     if (p->dev_blob) cudaFree(p->dev_blob);
     free(p);

@@ -49,7 +49,9 @@ struct RenderArgs {
 };
 
 // host-side launchers (defined in the .cu files)
+constexpr int kMaxForceOps = 32;
 int env_smem_bytes(const int32_t *hdr);
+int candidate_matrix_words(const void *host_blob);
 cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
 cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
 

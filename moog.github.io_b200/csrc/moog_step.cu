@@ -48,10 +48,12 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int dyn, stat, aabb, tmp, vtx, envf, meta, sflag, voff, cnt, envi, vslot, total;
+  int dyn, stat, aabb, tmp, vtx, envf, meta, sflag, voff, cnt, envi, cmoff, cmask, scratch, vslot, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF) {
+#define MOOG_MAX_FORCE_OPS 32
+
+__host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW) {
   SmemLayout L;
   int o = 0;
   L.dyn = o;   o += 8 * MOOG_DYN_FIELDS * S;
@@ -65,21 +67,40 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF) {
   L.voff = o;  o += 4 * (S + 1);
   L.cnt = o;   o += 4 * MOOG_MAX_LAYERS;
   L.envi = o;  o += 4 * MOOG_ENVI_WORDS;
+  L.cmoff = o; o += 4 * MOOG_MAX_FORCE_OPS;
+  L.cmask = o; o += 4 * (CMW > 0 ? CMW : 1);
+  L.scratch = o; o += 64;
   L.vslot = o; o += VT;
   L.total = (o + 15) & ~15;
   return L;
 }
 
 int env_smem_bytes(const int32_t *hdr) {
-  return smem_layout(hdr[MOOG_H_N_SLOTS], hdr[MOOG_H_N_VTX] > 0 ? hdr[MOOG_H_N_VTX] : 1, hdr[MOOG_H_N_ENVF]).total;
+  return smem_layout(hdr[MOOG_H_N_SLOTS], hdr[MOOG_H_N_VTX] > 0 ? hdr[MOOG_H_N_VTX] : 1, hdr[MOOG_H_N_ENVF],
+                     hdr[MOOG_H_CMASK_WORDS]).total;
+}
+
+// words of the candidate matrices of all collision ops (see MOOG_H_CMASK_WORDS)
+int candidate_matrix_words(const void *host_blob) {
+  ProgramView pv = view_of(host_blob);
+  int words = 0;
+  for (int f = 0; f < pv.hdr[MOOG_H_N_FORCES]; ++f) {
+    const moog_op *op = pv.ops + pv.hdr[MOOG_H_FORCES] + f;
+    if (op->kind != MOOG_F_COLLISION) continue;
+    int ca = pv.hdr[MOOG_H_LAYER_OFF + op->i[0] + 1] - pv.hdr[MOOG_H_LAYER_OFF + op->i[0]];
+    int cb = pv.hdr[MOOG_H_LAYER_OFF + op->i[1] + 1] - pv.hdr[MOOG_H_LAYER_OFF + op->i[1]];
+    words += ca * ((cb + 31) / 32);
+  }
+  return words;
 }
 
 struct Env {
   // shared memory
   double *dyn, *stat, *aabb, *tmp, *envf;
   double2 *vtx;
-  int *meta, *sflag, *voff, *cnt, *envi;
-  unsigned char *vslot;
+  int *meta, *sflag, *voff, *cnt, *envi, *cmoff;
+  unsigned *cmask;
+  unsigned char *scratch, *vslot;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -282,7 +303,12 @@ struct Aff { double m0, m1, m2, m3, m4, m5; };  // rows 0,1 of the 3x3 (row 2 = 
 __device__ __forceinline__ Aff aff_identity() { Aff a = {1., 0., 0., 0., 1., 0.}; return a; }
 __device__ __forceinline__ void aff_translate(Aff &m, double tx, double ty) { m.m2 += tx; m.m5 += ty; }
 __device__ inline void aff_rotate(Aff &m, double theta) {
-  double a = cos(theta), b = sin(theta);
+  // cos(+-0) == 1 and sin(+-0) == +-0 exactly: skip the libm call for sprites that do not rotate
+  double a = 1.0, b = theta;
+  if (theta != 0.0) {
+    a = cos(theta);
+    b = sin(theta);
+  }
   double xx = m.m0, xy = m.m1, x0 = m.m2, yx = m.m3, yy = m.m4, y0 = m.m5;
   m.m0 = a * xx - b * yx; m.m1 = a * xy - b * yy; m.m2 = a * x0 - b * y0;
   m.m3 = b * xx + a * yx; m.m4 = b * xy + a * yy; m.m5 = b * x0 + a * y0;
@@ -404,8 +430,11 @@ __device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
   if (serial) {
     if (path_intersects_path_serial(A, nA, B, nB)) return true;
   } else {
-    // lanes own the edges of the outline with more edges; the other outline's
-    // edges are walked together.  Argument order of segments_intersect is kept.
+    // Lanes first own the edges of each outline to find the few that can matter:
+    // edges of P whose (padded) box meets Q's box and edges of Q whose box meets
+    // P's padded box.  The surviving (P edge, Q edge) pairs -- a handful for two
+    // touching outlines -- are then tested all at once, one pair per lane.
+    // Argument order of segments_intersect is kept.
     bool lanesA = nA >= nB;
     const double2 *P = lanesA ? A : B;
     const double2 *Q = lanesA ? B : A;
@@ -416,26 +445,43 @@ __device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
     double2 p2 = P[act ? ((e.lane + 1 == nP) ? 0 : e.lane + 1) : 0];
     double pxmin = fmin(p1.x, p2.x) - AABB_PAD, pxmax = fmax(p1.x, p2.x) + AABB_PAD;
     double pymin = fmin(p1.y, p2.y) - AABB_PAD, pymax = fmax(p1.y, p2.y) + AABB_PAD;
-    // my edge against the other outline's box
     act = act && !(pxmax < BOX(e, 0, qslot) || pxmin > BOX(e, 2, qslot) || pymax < BOX(e, 1, qslot) ||
                    pymin > BOX(e, 3, qslot));
-    if (__any_sync(FULL, act)) {
+    bool qact = e.lane < nQ;
+    {
+      double2 q1 = Q[qact ? e.lane : 0];
+      double2 q2 = Q[qact ? ((e.lane + 1 == nQ) ? 0 : e.lane + 1) : 0];
       double Pxmin = BOX(e, 0, pslot) - AABB_PAD, Pymin = BOX(e, 1, pslot) - AABB_PAD;
       double Pxmax = BOX(e, 2, pslot) + AABB_PAD, Pymax = BOX(e, 3, pslot) + AABB_PAD;
-      double2 q1 = Q[0];
-      for (int j = 0; j < nQ; ++j) {
-        double2 q2 = Q[(j + 1 == nQ) ? 0 : j + 1];
-        double qxmin = fmin(q1.x, q2.x), qxmax = fmax(q1.x, q2.x);
-        double qymin = fmin(q1.y, q2.y), qymax = fmax(q1.y, q2.y);
-        if (!(qxmax < Pxmin || qxmin > Pxmax || qymax < Pymin || qymin > Pymax)) {
-          bool h = false;
-          if (act && !(qxmax < pxmin || qxmin > pxmax || qymax < pymin || qymin > pymax)) {
-            h = lanesA ? segments_intersect(p1.x, p1.y, p2.x, p2.y, q1.x, q1.y, q2.x, q2.y)
-                       : segments_intersect(q1.x, q1.y, q2.x, q2.y, p1.x, p1.y, p2.x, p2.y);
-          }
-          if (__any_sync(FULL, h)) return true;
+      qact = qact && !(fmax(q1.x, q2.x) < Pxmin || fmin(q1.x, q2.x) > Pxmax || fmax(q1.y, q2.y) < Pymin ||
+                       fmin(q1.y, q2.y) > Pymax);
+    }
+    const unsigned pm = __ballot_sync(FULL, act), qm = __ballot_sync(FULL, qact);
+    if (pm && qm) {
+      const unsigned lt = (1u << e.lane) - 1u;
+      const int np_ = __popc(pm), nq_ = __popc(qm);
+      wsync();
+      if (act) e.scratch[__popc(pm & lt)] = (unsigned char)e.lane;
+      if (qact) e.scratch[32 + __popc(qm & lt)] = (unsigned char)e.lane;
+      wsync();
+      const int total = np_ * nq_;
+      for (int base = 0; base < total; base += 32) {
+        int t = base + e.lane;
+        bool v = t < total;
+        int pi = v ? t / nq_ : 0;
+        int qi = v ? t - pi * nq_ : 0;
+        int pl = e.scratch[pi], ql = e.scratch[32 + qi];
+        double2 a1 = P[pl], a2 = P[(pl + 1 == nP) ? 0 : pl + 1];
+        double2 b1 = Q[ql], b2 = Q[(ql + 1 == nQ) ? 0 : ql + 1];
+        double axmin = fmin(a1.x, a2.x) - AABB_PAD, axmax = fmax(a1.x, a2.x) + AABB_PAD;
+        double aymin = fmin(a1.y, a2.y) - AABB_PAD, aymax = fmax(a1.y, a2.y) + AABB_PAD;
+        bool h = false;
+        if (v && !(fmax(b1.x, b2.x) < axmin || fmin(b1.x, b2.x) > axmax || fmax(b1.y, b2.y) < aymin ||
+                   fmin(b1.y, b2.y) > aymax)) {
+          h = lanesA ? segments_intersect(a1.x, a1.y, a2.x, a2.y, b1.x, b1.y, b2.x, b2.y)
+                     : segments_intersect(b1.x, b1.y, b2.x, b2.y, a1.x, a1.y, a2.x, a2.y);
         }
-        q1 = q2;
+        if (__any_sync(FULL, h)) return true;
       }
     }
   }
@@ -552,14 +598,17 @@ __device__ inline void directed_collision_vectors(const Env &e, int s0, int s1, 
     any_cross |= (__any_sync(FULL, crossing) != 0);
     if (!crossing) A = -INFINITY;
     double ab = fabs(1.0 - A);
-    int idx = eact ? e.lane : 0x7fffffff;
-    if (!eact) { ab = INFINITY; A = -INFINITY; }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      double ov = shflx_d(ab, off), oa = shflx_d(A, off);
-      int oi = __shfl_xor_sync(FULL, idx, off);
-      if (argmin_better(ov, oi, ab, idx)) { ab = ov; A = oa; idx = oi; }
-    }
+    // np.argmin over the edges: a NaN beats everything, then the smaller value,
+    // then the smaller index.  ab >= 0 or NaN, so its bit pattern orders like the
+    // value: two 32-bit warp minima + a ballot replace a 5-round shuffle tournament.
+    unsigned long long key = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
+    if (!eact) key = ~0ull;
+    const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(FULL, khi);
+    const bool c1 = khi == mhi;
+    const unsigned mlo = __reduce_min_sync(FULL, c1 ? klo : 0xffffffffu);
+    const int idx = __ffs(__ballot_sync(FULL, c1 && klo == mlo)) - 1;
+    A = shfl_d(A, idx);
     double cpx = sx + A * (ex - sx), cpy = sy + A * (ey - sy);
     double dfx = ex - cpx, dfy = ey - cpy;
     double dist = norm_ax(dfx, dfy);
@@ -801,10 +850,11 @@ __device__ __noinline__ void make_disjoint(const Env &e, int s0, int s1, bool sy
   }
 }
 
-// collisions.py:494-584 Collision.step; returns true when any state changed
-__device__ inline bool collision_step(Env &e, const moog_op *op, int s0, int s1, bool first_overlap_known) {
+// collisions.py:494-584 Collision.step; returns which sprites were moved
+// (bit 0: s0, bit 1: s1)
+__device__ inline int collision_step(Env &e, const moog_op *op, int s0, int s1, bool first_overlap_known) {
   bool symmetric = (op->flags & MOOG_FL_SYMMETRIC) != 0;
-  bool changed = false;
+  int changed = 0;
   int depth = 0;
   for (;;) {  // tail recursion of collisions.py:583-584
     if (depth > op->i[2]) return changed;
@@ -824,11 +874,11 @@ __device__ inline bool collision_step(Env &e, const moog_op *op, int s0, int s1,
     get_collision_vectors(e, s0, s1, dt, cv);
     if (!cv.has_point) {
       make_disjoint(e, s0, s1, symmetric);
-      changed = true;
+      changed |= symmetric ? 3 : 1;
     } else {
       if (cv.future) return changed;
       e.n_coll++;
-      changed = true;
+      changed |= symmetric ? 3 : 1;
       if (symmetric) {
         set_position(e, s0, DYN(e, MOOG_D_X, s0) - (0.5 + EPS_COLL) * cv.qx,
                      DYN(e, MOOG_D_Y, s0) - (0.5 + EPS_COLL) * cv.qy);
@@ -847,43 +897,150 @@ __device__ inline bool collision_step(Env &e, const moog_op *op, int s0, int s1,
   }
 }
 
-// All (s0, j) pairs of one Collision entry for a fixed s0, j over layer lb in
-// order.  The broad phase (circle test of sprite.py:464-466 plus the exact box
-// cull) is evaluated for 32 second sprites at once; candidates are then resolved
-// one by one in index order, and the broad phase of the remaining ones is
-// re-evaluated whenever a contact moved something.
-__device__ inline void collision_row(Env &e, const moog_op *op, int s0, int lb) {
-  int nb = e.cnt[lb], base_slot = LOFF(e, lb);
-  for (int base = 0; base < nb; base += 32) {
-    int j = base + e.lane;
-    int s1 = base_slot + j;
-    bool valid = j < nb && s1 != s0;
-    unsigned vmask = __ballot_sync(FULL, valid);
-    e.n_calls += __popc(vmask);  // every valid pair costs the reference one overlaps_sprite call
-    int jstart = 0;
-    bool recompute = true;
-    unsigned cand = 0;
-    for (;;) {
-      if (recompute) {
-        bool c = false;
-        if (valid && e.lane >= jstart) {
-          double dx = DYN(e, MOOG_D_X, s0) - DYN(e, MOOG_D_X, s1);
-          double dy = DYN(e, MOOG_D_Y, s0) - DYN(e, MOOG_D_Y, s1);
-          double cd = norm1(dx, dy);
-          int fl = e.sflag[s0] | e.sflag[s1];
-          c = !(cd > STAT(e, MOOG_S_MAXR, s0) + STAT(e, MOOG_S_MAXR, s1)) && !(fl & SLF_ALLNAN) &&
-              ((fl & SLF_NONFINITE) || !boxes_apart(e, s0, s1));
+// ---------------------------------------------------------------------------
+// Broad phase of the Collision entries.
+//
+// The reference visits every (sprite_0, sprite_1) pair of every Collision entry
+// in itertools.product order and starts each visit with overlaps_sprite
+// (collisions.py:516).  A visit whose overlap test is False changes nothing, and
+// positions only change when a contact is resolved, so the outcome of "could
+// this pair overlap at all" -- the circle test of sprite.py:464-466 AND the
+// exact padded-box cull -- is evaluated for ALL pairs of ALL entries once per
+// substep into bit matrices (row = sprite_0, bit = sprite_1), the set bits are
+// visited in the reference's order, and after a resolved contact only the row
+// and column of the sprites that moved are re-evaluated.
+// ---------------------------------------------------------------------------
+
+// per-lane: can (a, b) overlap?  (false is exact: the reference would return False)
+__device__ __forceinline__ bool pair_candidate(const Env &e, int a, int b, bool valid) {
+  bool c = false;
+  if (valid) {
+    int fl = e.sflag[a] | e.sflag[b];
+    c = !(fl & SLF_ALLNAN) && ((fl & SLF_NONFINITE) || !boxes_apart(e, a, b));
+  }
+  if (__any_sync(FULL, c)) {
+    if (c) {
+      double dx = DYN(e, MOOG_D_X, a) - DYN(e, MOOG_D_X, b);
+      double dy = DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, b);
+      c = !(norm1(dx, dy) > STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b));
+    }
+  }
+  return c;
+}
+
+// row `i` of the matrix of force op `f`: lane = sprite_1
+__device__ inline void candidate_row(const Env &e, const moog_op *op, int f, int i) {
+  const int la = op->i[0], lb = op->i[1];
+  const int nb = e.cnt[lb], sb = LOFF(e, lb), s0 = LOFF(e, la) + i;
+  const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
+  for (int w = 0; w * 32 < nb; ++w) {
+    int j = w * 32 + e.lane;
+    unsigned m = __ballot_sync(FULL, pair_candidate(e, s0, sb + j, j < nb && sb + j != s0));
+    if (e.lane == 0) e.cmask[e.cmoff[f] + i * wpr + w] = m;
+  }
+}
+
+// column `j` of the matrix of force op `f`: lane = sprite_0, every lane patches its own row word
+__device__ inline void candidate_col(const Env &e, const moog_op *op, int f, int j) {
+  const int la = op->i[0], lb = op->i[1];
+  const int na = e.cnt[la], sa = LOFF(e, la), s1 = LOFF(e, lb) + j;
+  const int wpr = (LOFF(e, lb + 1) - LOFF(e, lb) + 31) >> 5;
+  for (int base = 0; base < na; base += 32) {
+    int i = base + e.lane;
+    bool c = pair_candidate(e, sa + i, s1, i < na && sa + i != s1);
+    if (i < na) {
+      unsigned *w = &e.cmask[e.cmoff[f] + i * wpr + (j >> 5)];
+      *w = (*w & ~(1u << (j & 31))) | ((unsigned)c << (j & 31));
+    }
+  }
+}
+
+// all matrices, from scratch (start of a substep)
+__device__ inline void build_candidates(const Env &e) {
+  const int32_t *h = e.hdr;
+  wsync();
+  for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
+    const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
+    if (op->kind != MOOG_F_COLLISION) continue;
+    const int la = op->i[0], lb = op->i[1];
+    const int na = e.cnt[la], nb = e.cnt[lb];
+    if (nb >= na) {
+      for (int i = 0; i < na; ++i) candidate_row(e, op, f, i);
+    } else {
+      // fewer second sprites than first ones: lane = sprite_0, loop over sprite_1
+      const int sa = LOFF(e, la), sb = LOFF(e, lb);
+      const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
+      for (int base = 0; base < na; base += 32) {
+        int i = base + e.lane;
+        for (int w = 0; w * 32 < nb; ++w) {
+          unsigned m = 0;
+          int jend = min(nb - w * 32, 32);
+          for (int jj = 0; jj < jend; ++jj) {
+            int s1 = sb + w * 32 + jj;
+            m |= (unsigned)pair_candidate(e, sa + i, s1, i < na && sa + i != s1) << jj;
+          }
+          if (i < na) e.cmask[e.cmoff[f] + i * wpr + w] = m;
         }
-        cand = __ballot_sync(FULL, c);
-        recompute = false;
       }
-      if (!cand) break;
-      int l = __ffs(cand) - 1;
-      cand &= cand - 1;
-      e.n_calls--;  // collision_step counts this pair's first call itself
-      bool changed = collision_step(e, op, s0, base_slot + base + l, true);
-      jstart = l + 1;
-      if (changed) recompute = true;
+    }
+  }
+  wsync();
+}
+
+// sprite `s` moved: refresh its row / column in every matrix
+__device__ inline void update_candidates(const Env &e, int s) {
+  const int32_t *h = e.hdr;
+  wsync();
+  for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
+    const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
+    if (op->kind != MOOG_F_COLLISION) continue;
+    const int la = op->i[0], lb = op->i[1];
+    int i = s - LOFF(e, la), j = s - LOFF(e, lb);
+    if (i >= 0 && i < e.cnt[la]) candidate_row(e, op, f, i);
+    wsync();
+    if (j >= 0 && j < e.cnt[lb]) candidate_col(e, op, f, j);
+    wsync();
+  }
+}
+
+// One Collision entry (physics.py:92-108 for a Collision force): the candidate
+// pairs of its matrix in row-major order = itertools.product order.
+__device__ inline void collision_op(Env &e, const moog_op *op, int f) {
+  const int la = op->i[0], lb = op->i[1];
+  const int na = e.cnt[la], nb = e.cnt[lb];
+  const int sa = LOFF(e, la), sb = LOFF(e, lb);
+  const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
+  // every pair costs the reference one overlaps_sprite call (identical objects
+  // return before it, collisions.py:513)
+  {
+    int lo = max(sa, sb), hi = min(sa + na, sb + nb);
+    e.n_calls += (long long)na * nb - (hi > lo ? hi - lo : 0);
+  }
+  const unsigned *M = e.cmask + e.cmoff[f];
+  const int nwords = na * wpr;
+  for (int base = 0; base < nwords; base += 32) {
+    int widx = base + e.lane;
+    unsigned nz = __ballot_sync(FULL, widx < nwords && M[widx] != 0u);
+    while (nz) {
+      const int t = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const int wi = base + t;
+      const int i = wi / wpr, w = wi - i * wpr;
+      unsigned m = M[wi];
+      while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const int s0 = sa + i, s1 = sb + w * 32 + l;
+        e.n_calls--;  // collision_step counts this pair's first call itself
+        int moved = collision_step(e, op, s0, s1, true);
+        if (moved) {
+          if (moved & 1) update_candidates(e, s0);
+          if (moved & 2) update_candidates(e, s1);
+          // continue after (i, w, l) with the refreshed matrix
+          m = M[wi] & ~((2u << l) - 1u);
+          nz = __ballot_sync(FULL, widx < nwords && M[widx] != 0u) & ~((2u << t) - 1u);
+        }
+      }
     }
   }
 }
@@ -1241,13 +1398,14 @@ __device__ inline void integrate_all(const Env &e) {
 // physics.py:88-117 Physics.apply_physics (one substep)
 __device__ inline void apply_physics(Env &e) {
   const int32_t *h = e.hdr;
+  build_candidates(e);
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
     const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
     int la = op->i[0], lb = op->i[1];
     if (lb < 0) {
       force_unary_layer(e, op);
     } else if (op->kind == MOOG_F_COLLISION) {
-      for (int i = 0; i < e.cnt[la]; ++i) collision_row(e, op, LOFF(e, la) + i, lb);
+      collision_op(e, op, f);
     } else {
       for (int i = 0; i < e.cnt[la]; ++i)
         for (int j = 0; j < e.cnt[lb]; ++j) force_binary(e, op, LOFF(e, la) + i, LOFF(e, lb) + j);
@@ -1715,7 +1873,7 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
   e.VT = pv.hdr[MOOG_H_N_VTX];
   e.lane = lane;
   const int NF = pv.hdr[MOOG_H_N_ENVF];
-  SmemLayout lay = smem_layout(e.S, e.VT > 0 ? e.VT : 1, NF);
+  SmemLayout lay = smem_layout(e.S, e.VT > 0 ? e.VT : 1, NF, pv.hdr[MOOG_H_CMASK_WORDS]);
   unsigned char *base = smem_raw + (size_t)warp * lay.total;
   e.dyn = (double *)(base + lay.dyn);
   e.stat = (double *)(base + lay.stat);
@@ -1728,6 +1886,9 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
   e.voff = (int *)(base + lay.voff);
   e.cnt = (int *)(base + lay.cnt);
   e.envi = (int *)(base + lay.envi);
+  e.cmoff = (int *)(base + lay.cmoff);
+  e.cmask = (unsigned *)(base + lay.cmask);
+  e.scratch = base + lay.scratch;
   e.vslot = base + lay.vslot;
   e.env_id = n;
   e.seed = a.io.seed;
@@ -1744,6 +1905,18 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
   for (int s = lane; s < e.S; s += 32)
     for (int v = e.voff[s]; v < e.voff[s + 1]; ++v) e.vslot[v] = (unsigned char)s;
 
+  if (lane == 0) {  // offsets of the candidate matrices of the Collision entries
+    int off = 0;
+    for (int f = 0; f < pv.hdr[MOOG_H_N_FORCES] && f < MOOG_MAX_FORCE_OPS; ++f) {
+      const moog_op *op = pv.ops + pv.hdr[MOOG_H_FORCES] + f;
+      e.cmoff[f] = off;
+      if (op->kind == MOOG_F_COLLISION) {
+        int ca = pv.hdr[MOOG_H_LAYER_OFF + op->i[0] + 1] - pv.hdr[MOOG_H_LAYER_OFF + op->i[0]];
+        int cb = pv.hdr[MOOG_H_LAYER_OFF + op->i[1] + 1] - pv.hdr[MOOG_H_LAYER_OFF + op->i[1]];
+        off += ca * ((cb + 31) >> 5);
+      }
+    }
+  }
   copy_i(e.envi, a.st.envi + (size_t)n * MOOG_ENVI_WORDS, MOOG_ENVI_WORDS, lane);
   wsync();
   const bool do_reset = a.mode == MODE_ENV_STEP && a.io.pool != nullptr && e.envi[MOOG_EI_RESET_NEXT] != 0;
