@@ -34,6 +34,7 @@ struct StepArgs {
   moog_state st;
   int n_envs;
   int mode;
+  int S, L, K, VT, NF, CMW;  // program dimensions (filled in by launch_step from the header)
   moog_step_io io;
   moog_state pool;  // valid iff io.pool != nullptr
   // MODE_OVERLAP

@@ -48,7 +48,7 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int dyn, stat, aabb, tmp, vtx, envf, meta, sflag, voff, cnt, envi, cmoff, cmask, scratch, vslot, total;
+  int rec, dyn, stat, aabb, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, hdr, scratch, vslot, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
@@ -56,12 +56,14 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW) {
   SmemLayout L;
   int o = 0;
+  L.rec = o;   o += 192;  // EnvRec (static_assert below)
   L.dyn = o;   o += 8 * MOOG_DYN_FIELDS * S;
   L.stat = o;  o += 8 * MOOG_STAT_FIELDS * S;
   L.aabb = o;  o += 8 * 4 * S;
   L.tmp = o;   o += 8 * 8 * S;
   L.vtx = o;   o += 16 * VT;
   L.envf = o;  o += 8 * NF;
+  L.ctr = o;   o += 8 * 10;
   L.meta = o;  o += 4 * MOOG_META_FIELDS * S;
   L.sflag = o; o += 4 * S;
   L.voff = o;  o += 4 * (S + 1);
@@ -69,6 +71,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.envi = o;  o += 4 * MOOG_ENVI_WORDS;
   L.cmoff = o; o += 4 * MOOG_MAX_FORCE_OPS;
   L.cmask = o; o += 4 * (CMW > 0 ? CMW : 1);
+  L.hdr = o;   o += 4 * MOOG_HDR_WORDS;
   L.scratch = o; o += 64;
   L.vslot = o; o += VT;
   L.total = (o + 15) & ~15;
@@ -110,10 +113,64 @@ struct Env {
   const double *noise;       // [K][noise_dim] of this env or nullptr
   const double *rule_noise;  // [rule_noise_dim] of this env or nullptr
   uint64_t seed;
-  int env_id, substep;
-  long long n_calls, n_true, n_coll;
-  unsigned long long hash;
+  int env_id;
+  // Mutable per-env bookkeeping lives in shared memory (lane 0 updates it), so
+  // that this struct is immutable after set-up and stays in registers: passed
+  // by const reference through the inlined hot path and BY VALUE to the rare
+  // out-of-line paths, its address never escapes.
+  //   ctr[0..7] = counters (moog_step_io::counters), ctr[8] = current substep
+  long long *ctr;
 };
+
+// The env's view record at the start of the CTA's shared memory: out-of-line
+// device functions rebuild their `Env` from it (a few broadcast LDS) instead
+// of receiving ~50 registers through the stack.
+struct EnvRec {
+  SmemLayout lay;
+  int S, L, K, VT, env_id, pad;
+  const moog_op *ops;
+  const int32_t *ipool;
+  const moog_ex *expr;
+  const double *noise, *rule_noise;
+  uint64_t seed;
+};
+static_assert(sizeof(EnvRec) <= 192, "EnvRec must fit its shared-memory slot");
+
+__device__ __forceinline__ Env env_view() {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char *base = smem_raw;
+  const EnvRec *r = (const EnvRec *)base;
+  Env e;
+  e.dyn = (double *)(base + r->lay.dyn);
+  e.stat = (double *)(base + r->lay.stat);
+  e.aabb = (double *)(base + r->lay.aabb);
+  e.tmp = (double *)(base + r->lay.tmp);
+  e.vtx = (double2 *)(base + r->lay.vtx);
+  e.envf = (double *)(base + r->lay.envf);
+  e.ctr = (long long *)(base + r->lay.ctr);
+  e.meta = (int *)(base + r->lay.meta);
+  e.sflag = (int *)(base + r->lay.sflag);
+  e.voff = (int *)(base + r->lay.voff);
+  e.cnt = (int *)(base + r->lay.cnt);
+  e.envi = (int *)(base + r->lay.envi);
+  e.cmoff = (int *)(base + r->lay.cmoff);
+  e.cmask = (unsigned *)(base + r->lay.cmask);
+  e.hdr = (const int32_t *)(base + r->lay.hdr);
+  e.scratch = base + r->lay.scratch;
+  e.vslot = base + r->lay.vslot;
+  e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
+  e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
+  e.lane = threadIdx.x;
+  e.noise = r->noise; e.rule_noise = r->rule_noise;
+  e.seed = r->seed;
+  e.env_id = r->env_id;
+  return e;
+}
+
+enum { CT_CALLS = 0, CT_TRUE, CT_COLL, CT_HASH, CT_CYCLES, CT_NARROW, CT_CYC_NARROW, CT_CYC_RESOLVE, CT_SUBSTEP };
+__device__ __forceinline__ void ctr_add(const Env &e, int k, long long v) {
+  if (e.lane == 0) e.ctr[k] += v;
+}
 
 #define DYN(e, f, s) ((e).dyn[(f) * (e).S + (s)])
 #define STAT(e, f, s) ((e).stat[(f) * (e).S + (s)])
@@ -275,7 +332,7 @@ __device__ __forceinline__ bool boxes_apart(const Env &e, int a, int b) {
 // position / angle setters (sprite.py:531-540, 616-633): the cached outline is
 // transformed incrementally, exactly like the reference's Sprite._path
 // ---------------------------------------------------------------------------
-__device__ inline void set_position(const Env &e, int s, double nx, double ny) {
+__device__ __forceinline__ void set_position_impl(const Env &e, int s, double nx, double ny) {
   double tx = nx - DYN(e, MOOG_D_X, s), ty = ny - DYN(e, MOOG_D_Y, s);
   int n = META(e, MOOG_M_NV, s);
   double2 *v = e.vtx + e.voff[s];
@@ -298,16 +355,25 @@ __device__ inline void set_position(const Env &e, int s, double nx, double ny) {
   if (!(isfinite(tx) && isfinite(ty))) classify_slot(e, s);
 }
 
+__device__ __noinline__ void set_position_ol(int s, double nx, double ny) {
+  const Env e = env_view();
+  set_position_impl(e, s, nx, ny);
+}
+__device__ __forceinline__ void set_position(const Env &, int s, double nx, double ny) { set_position_ol(s, nx, ny); }
+
 struct Aff { double m0, m1, m2, m3, m4, m5; };  // rows 0,1 of the 3x3 (row 2 = 0 0 1)
 
 __device__ __forceinline__ Aff aff_identity() { Aff a = {1., 0., 0., 0., 1., 0.}; return a; }
 __device__ __forceinline__ void aff_translate(Aff &m, double tx, double ty) { m.m2 += tx; m.m5 += ty; }
+__device__ __noinline__ double2 cos_sin_ol(double theta) { return make_double2(cos(theta), sin(theta)); }
+
 __device__ inline void aff_rotate(Aff &m, double theta) {
   // cos(+-0) == 1 and sin(+-0) == +-0 exactly: skip the libm call for sprites that do not rotate
   double a = 1.0, b = theta;
   if (theta != 0.0) {
-    a = cos(theta);
-    b = sin(theta);
+    double2 cs = cos_sin_ol(theta);
+    a = cs.x;
+    b = cs.y;
   }
   double xx = m.m0, xy = m.m1, x0 = m.m2, yx = m.m3, yy = m.m4, y0 = m.m5;
   m.m0 = a * xx - b * yx; m.m1 = a * xy - b * yy; m.m2 = a * x0 - b * y0;
@@ -416,7 +482,7 @@ __device__ inline bool all_points_in_poly(const Env &e, const double2 *P, int np
 }
 
 // Path.intersects_path(a, b, filled=True) as MOOG calls it (sprite.py:482-483)
-__device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
+__device__ __forceinline__ bool path_intersects_filled_impl(const Env &e, int a, int b) {
   const double2 *A = e.vtx + e.voff[a];
   const double2 *B = e.vtx + e.voff[b];
   int nA = META(e, MOOG_M_NV, a), nB = META(e, MOOG_M_NV, b);
@@ -496,16 +562,26 @@ __device__ inline bool path_intersects_filled(const Env &e, int a, int b) {
   return false;
 }
 
-__device__ __forceinline__ void count_overlap(Env &e, int a, int b, bool r) {
-  e.n_calls++;
-  if (r) {
-    e.n_true++;
-    e.hash = (e.hash ^ (uint64_t)(((uint32_t)a * 1315423911u) ^ ((uint32_t)b * 2654435761u) ^ 1u)) * 1099511628211ull;
+__device__ __noinline__ bool path_intersects_filled_ol(int a, int b) {
+  const Env e = env_view();
+  return path_intersects_filled_impl(e, a, b);
+}
+__device__ __forceinline__ bool path_intersects_filled(const Env &, int a, int b) { return path_intersects_filled_ol(a, b); }
+
+__device__ __forceinline__ void count_overlap(const Env &e, int a, int b, bool r) {
+  if (e.lane == 0) {
+    e.ctr[CT_CALLS]++;
+    if (r) {
+      e.ctr[CT_TRUE]++;
+      unsigned long long h = (unsigned long long)e.ctr[CT_HASH];
+      h = (h ^ (uint64_t)(((uint32_t)a * 1315423911u) ^ ((uint32_t)b * 2654435761u) ^ 1u)) * 1099511628211ull;
+      e.ctr[CT_HASH] = (long long)h;
+    }
   }
 }
 
 // sprite.py:462-484 Sprite.overlaps_sprite
-__device__ inline bool overlaps(Env &e, int a, int b) {
+__device__ inline bool overlaps(const Env &e, int a, int b) {
   bool r = false;
   double dx = DYN(e, MOOG_D_X, a) - DYN(e, MOOG_D_X, b);
   double dy = DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, b);
@@ -551,7 +627,7 @@ __device__ __forceinline__ bool argmin_better(double v2, int i2, double v1, int 
 
 // collisions.py:101-232 _directed_collision_vectors(sprite_0=s0, sprite_1=s1):
 // vertices of s0 that lie inside s1, traced back along the relative motion.
-__device__ inline void directed_collision_vectors(const Env &e, int s0, int s1, double dt, CVec &o) {
+__device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, int s0, int s1, double dt, CVec &o) {
   o.has_point = o.future = o.has_since = 0;
   o.px = o.py = o.nx = o.ny = o.sx = o.sy = o.qx = o.qy = 0.0;
   const double2 *P0 = e.vtx + e.voff[s0];
@@ -640,6 +716,11 @@ __device__ inline void directed_collision_vectors(const Env &e, int s0, int s1, 
   o.qy = o.sy - dvy * f;
 }
 
+__device__ __noinline__ void directed_collision_vectors(const Env &, int s0, int s1, double dt, CVec &o) {
+  const Env e = env_view();
+  directed_collision_vectors_impl(e, s0, s1, dt, o);
+}
+
 // collisions.py:235-289 _get_collision_vectors
 __device__ inline void get_collision_vectors(const Env &e, int s0, int s1, double dt, CVec &o) {
   CVec c0, c1;
@@ -667,8 +748,9 @@ __device__ inline void get_collision_vectors(const Env &e, int s0, int s1, doubl
 }
 
 // collisions.py:292-350
-__device__ inline void collide_without_update_angle_vel(const Env &e, int s0, int s1, const CVec &cv,
-                                                        double elasticity, bool symmetric) {
+__device__ __noinline__ void collide_without_update_angle_vel(const Env &, int s0, int s1, const CVec &cv,
+                                                            double elasticity, bool symmetric) {
+  const Env e = env_view();
   double nx = cv.nx, ny = cv.ny;
   double nn = norm1(nx, ny);
   if (!(fabs(nn - 1.0) <= 1e-4 + 1e-5 * 1.0)) {
@@ -697,8 +779,9 @@ __device__ inline void collide_without_update_angle_vel(const Env &e, int s0, in
 }
 
 // collisions.py:353-454
-__device__ inline void collide_with_update_angle_vel(const Env &e, int s0, int s1, const CVec &cv,
-                                                     double elasticity, bool symmetric) {
+__device__ __noinline__ void collide_with_update_angle_vel(const Env &, int s0, int s1, const CVec &cv,
+                                                         double elasticity, bool symmetric) {
+  const Env e = env_view();
   double nx = cv.nx, ny = cv.ny;
   double m0 = STAT(e, MOOG_S_MASS, s0), m1 = STAT(e, MOOG_S_MASS, s1);
   double w0 = DYN(e, MOOG_D_ANGVEL, s0), w1 = DYN(e, MOOG_D_ANGVEL, s1);
@@ -776,8 +859,9 @@ __device__ inline Closest closest_crossing(const Env &e, const double2 *P0, int 
 
 // collisions.py:658-748 _position_correction.  `me` / `other` are the function's
 // sprite_0 / sprite_1; ind_me / ind_other the edge indices of the closest crossing.
-__device__ __noinline__ void position_correction(const Env &e, double pt0x, double pt0y, int ind_me, int ind_other,
+__device__ __noinline__ void position_correction(const Env &, double pt0x, double pt0y, int ind_me, int ind_other,
                                                  int me, int other, double out[2]) {
+  const Env e = env_view();
   const double2 *Pme = e.vtx + e.voff[me];
   const double2 *Pother = e.vtx + e.voff[other];
   int n = META(e, MOOG_M_NV, me), no = META(e, MOOG_M_NV, other);
@@ -823,7 +907,8 @@ __device__ __noinline__ void position_correction(const Env &e, double pt0x, doub
 }
 
 // collisions.py:586-655 Collision._make_disjoint
-__device__ __noinline__ void make_disjoint(const Env &e, int s0, int s1, bool symmetric) {
+__device__ __noinline__ void make_disjoint(const Env &, int s0, int s1, bool symmetric) {
+  const Env e = env_view();
   const double2 *P0 = e.vtx + e.voff[s0];
   const double2 *P1 = e.vtx + e.voff[s1];
   int n0 = META(e, MOOG_M_NV, s0), n1 = META(e, MOOG_M_NV, s1);
@@ -852,7 +937,7 @@ __device__ __noinline__ void make_disjoint(const Env &e, int s0, int s1, bool sy
 
 // collisions.py:494-584 Collision.step; returns which sprites were moved
 // (bit 0: s0, bit 1: s1)
-__device__ inline int collision_step(Env &e, const moog_op *op, int s0, int s1, bool first_overlap_known) {
+__device__ inline int collision_step(const Env &e, const moog_op *op, int s0, int s1, bool first_overlap_known) {
   bool symmetric = (op->flags & MOOG_FL_SYMMETRIC) != 0;
   int changed = 0;
   int depth = 0;
@@ -860,6 +945,7 @@ __device__ inline int collision_step(Env &e, const moog_op *op, int s0, int s1, 
     if (depth > op->i[2]) return changed;
     if (s0 == s1) return changed;
     bool ov;
+    long long t0 = clock64();
     if (first_overlap_known && depth == 0) {
       // the caller's broad phase already established that the circles and the
       // boxes meet: go straight to the outline test
@@ -868,7 +954,10 @@ __device__ inline int collision_step(Env &e, const moog_op *op, int s0, int s1, 
     } else {
       ov = overlaps(e, s0, s1);
     }
+    ctr_add(e, CT_NARROW, 1);
+    ctr_add(e, CT_CYC_NARROW, clock64() - t0);
     if (!ov) return changed;
+    long long t1 = clock64();
     double dt = 1.0 / e.K;
     CVec cv;
     get_collision_vectors(e, s0, s1, dt, cv);
@@ -876,8 +965,11 @@ __device__ inline int collision_step(Env &e, const moog_op *op, int s0, int s1, 
       make_disjoint(e, s0, s1, symmetric);
       changed |= symmetric ? 3 : 1;
     } else {
-      if (cv.future) return changed;
-      e.n_coll++;
+      if (cv.future) {
+        ctr_add(e, CT_CYC_RESOLVE, clock64() - t1);
+        return changed;
+      }
+      ctr_add(e, CT_COLL, 1);
       changed |= symmetric ? 3 : 1;
       if (symmetric) {
         set_position(e, s0, DYN(e, MOOG_D_X, s0) - (0.5 + EPS_COLL) * cv.qx,
@@ -893,6 +985,7 @@ __device__ inline int collision_step(Env &e, const moog_op *op, int s0, int s1, 
       else
         collide_without_update_angle_vel(e, s0, s1, cv, op->p[0], symmetric);
     }
+    ctr_add(e, CT_CYC_RESOLVE, clock64() - t1);
     depth += 1;
   }
 }
@@ -1005,7 +1098,7 @@ __device__ inline void update_candidates(const Env &e, int s) {
 
 // One Collision entry (physics.py:92-108 for a Collision force): the candidate
 // pairs of its matrix in row-major order = itertools.product order.
-__device__ inline void collision_op(Env &e, const moog_op *op, int f) {
+__device__ inline void collision_op(const Env &e, const moog_op *op, int f) {
   const int la = op->i[0], lb = op->i[1];
   const int na = e.cnt[la], nb = e.cnt[lb];
   const int sa = LOFF(e, la), sb = LOFF(e, lb);
@@ -1014,7 +1107,7 @@ __device__ inline void collision_op(Env &e, const moog_op *op, int f) {
   // return before it, collisions.py:513)
   {
     int lo = max(sa, sb), hi = min(sa + na, sb + nb);
-    e.n_calls += (long long)na * nb - (hi > lo ? hi - lo : 0);
+    ctr_add(e, CT_CALLS, (long long)na * nb - (hi > lo ? hi - lo : 0));
   }
   const unsigned *M = e.cmask + e.cmoff[f];
   const int nwords = na * wpr;
@@ -1031,7 +1124,7 @@ __device__ inline void collision_op(Env &e, const moog_op *op, int f) {
         const int l = __ffs(m) - 1;
         m &= m - 1;
         const int s0 = sa + i, s1 = sb + w * 32 + l;
-        e.n_calls--;  // collision_step counts this pair's first call itself
+        ctr_add(e, CT_CALLS, -1);  // collision_step counts this pair's first call itself
         int moved = collision_step(e, op, s0, s1, true);
         if (moved) {
           if (moved & 1) update_candidates(e, s0);
@@ -1049,9 +1142,9 @@ __device__ inline void collision_op(Env &e, const moog_op *op, int f) {
 // forces (abstract_force.py:64-74 + the individual _compute_forces)
 // ---------------------------------------------------------------------------
 __device__ inline double noise_at(const Env &e, int col) {
-  if (e.noise) return e.noise[(size_t)e.substep * e.hdr[MOOG_H_NOISE_DIM] + col];
+  if (e.noise) return e.noise[(size_t)e.ctr[CT_SUBSTEP] * e.hdr[MOOG_H_NOISE_DIM] + col];
   return philox_uniform(e.seed, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_STEP_COUNT],
-                        (uint32_t)e.substep | ((uint32_t)e.envi[MOOG_EI_EPISODES] << 8), (uint32_t)col);
+                        (uint32_t)e.ctr[CT_SUBSTEP] | ((uint32_t)e.envi[MOOG_EI_EPISODES] << 8), (uint32_t)col);
 }
 
 // lane = sprite of the layer; a unary force only touches its own sprite's velocity
@@ -1244,7 +1337,8 @@ __device__ inline void tether_sprites(const Env &e, Pick pick, int n, bool updat
   }
 }
 
-__device__ __noinline__ void corrective(const Env &e, const moog_op *op) {
+__device__ __noinline__ void corrective(const Env &, const moog_op *op) {
+  const Env e = env_view();
   switch (op->kind) {
     case MOOG_C_TETHER: {  // tether_physics.py:126-140
       int st = op->i[0], nl = op->i[1];
@@ -1396,7 +1490,7 @@ __device__ inline void integrate_all(const Env &e) {
 }
 
 // physics.py:88-117 Physics.apply_physics (one substep)
-__device__ inline void apply_physics(Env &e) {
+__device__ inline void apply_physics(const Env &e) {
   const int32_t *h = e.hdr;
   build_candidates(e);
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
@@ -1443,7 +1537,8 @@ __device__ inline double py_fmod(double a, double b) {
   return r;
 }
 
-__device__ __noinline__ double eval_expr(const Env &e, int start, int s0, int s1) {
+__device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1) {
+  const Env e = env_view();
   if (start < 0) return 1.0;
   double st[16];
   int sp = 0;
@@ -1487,7 +1582,8 @@ __device__ __noinline__ double eval_expr(const Env &e, int start, int s0, int s1
   return sp ? st[sp - 1] : 1.0;
 }
 
-__device__ __noinline__ double eval_condition(Env &e, int op_index) {
+__device__ __noinline__ double eval_condition(const Env &, int op_index) {
+  const Env e = env_view();
   const moog_op *op = e.ops + op_index;
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
@@ -1563,7 +1659,8 @@ __device__ double rule_noise_at(const Env &e, int col) {
 }
 
 // one non-conditional rule
-__device__ __noinline__ void rule_leaf(Env &e, int r) {
+__device__ __noinline__ void rule_leaf(const Env &, int r) {
+  const Env e = env_view();
   const moog_op *op = e.ops + r;
   unsigned flag[MOOG_MAX_SLOTS / 32];
   switch (op->kind) {
@@ -1641,7 +1738,8 @@ __device__ __noinline__ void rule_leaf(Env &e, int r) {
 // sub-rules `int(condition(state))` times.  Iterative (explicit block stack) so
 // that the kernel's stack size is static.
 #define MOOG_MAX_COND_DEPTH 4
-__device__ inline void rules_step(Env &e) {
+__device__ __noinline__ void rules_step(const Env &) {
+  const Env e = env_view();
   const int32_t *h = e.hdr;
   int r = h[MOOG_H_RULES];
   const int end = h[MOOG_H_RULES] + h[MOOG_H_N_RULES];
@@ -1681,7 +1779,8 @@ __device__ inline void rules_step(Env &e) {
 // ---------------------------------------------------------------------------
 // action spaces
 // ---------------------------------------------------------------------------
-__device__ inline void actions_step(const Env &e, const double *action) {
+__device__ __noinline__ void actions_step(const Env &, const double *action) {
+  const Env e = env_view();
   const int32_t *h = e.hdr;
   for (int a = 0; a < h[MOOG_H_N_ACTIONS]; ++a) {
     const moog_op *op = e.ops + h[MOOG_H_ACTIONS] + a;
@@ -1756,7 +1855,8 @@ __device__ inline void actions_reset(const Env &e) {
 }
 
 // composite_task.py:32-42 flattened over the task tree
-__device__ inline void tasks_reward(Env &e, int step_count, double *reward, int *should_reset) {
+__device__ __noinline__ void tasks_reward(const Env &, int step_count, double *reward, int *should_reset) {
+  const Env e = env_view();
   const int32_t *h = e.hdr;
   double total = 0;
   int reset = 0;
@@ -1824,7 +1924,7 @@ __device__ inline void copy_i(int *dst, const int *src, int n, int lane) {
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
-__device__ inline void load_env(Env &e, const moog_state &st, size_t n, bool with_envi) {
+__device__ inline void load_env(const Env &e, const moog_state &st, size_t n, bool with_envi) {
   int S = e.S, NF = e.hdr[MOOG_H_N_ENVF];
   copy_d(e.dyn, st.dyn + n * MOOG_DYN_FIELDS * S, MOOG_DYN_FIELDS * S, e.lane);
   copy_d(e.stat, st.stat + n * MOOG_STAT_FIELDS * S, MOOG_STAT_FIELDS * S, e.lane);
@@ -1847,7 +1947,7 @@ __device__ inline void store_env(const Env &e, const moog_state &st, size_t n) {
 }
 
 // environment.py:88-96: task / action reset, every rule reset and stepped once
-__device__ inline void post_reset(Env &e) {
+__device__ inline void post_reset(const Env &e) {
   wsync();
   puti(e, &e.envi[MOOG_EI_STEP_COUNT], 0);
   puti(e, &e.envi[MOOG_EI_RESET_NEXT], 0);
@@ -1857,47 +1957,39 @@ __device__ inline void post_reset(Env &e) {
   rules_step(e);
 }
 
-__global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
+// One warp = one CTA = one env: every shared-memory address below is a
+// CTA-uniform offset from the dynamic shared-memory base, and the program's
+// dimensions arrive in the parameter bank, so address arithmetic stays on the
+// uniform datapath instead of occupying vector registers.
+__global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int lane = threadIdx.x;
+  const int n = blockIdx.x;
   if (n >= a.n_envs) return;
   const long long t_begin = clock64();
 
-  Env e;
   ProgramView pv = view_of(a.blob);
-  e.hdr = pv.hdr; e.ops = pv.ops; e.ipool = pv.ipool; e.expr = pv.expr;
-  e.S = pv.hdr[MOOG_H_N_SLOTS];
-  e.L = pv.hdr[MOOG_H_N_LAYERS];
-  e.K = pv.hdr[MOOG_H_K];
-  e.VT = pv.hdr[MOOG_H_N_VTX];
-  e.lane = lane;
-  const int NF = pv.hdr[MOOG_H_N_ENVF];
-  SmemLayout lay = smem_layout(e.S, e.VT > 0 ? e.VT : 1, NF, pv.hdr[MOOG_H_CMASK_WORDS]);
-  unsigned char *base = smem_raw + (size_t)warp * lay.total;
-  e.dyn = (double *)(base + lay.dyn);
-  e.stat = (double *)(base + lay.stat);
-  e.aabb = (double *)(base + lay.aabb);
-  e.tmp = (double *)(base + lay.tmp);
-  e.vtx = (double2 *)(base + lay.vtx);
-  e.envf = (double *)(base + lay.envf);
-  e.meta = (int *)(base + lay.meta);
-  e.sflag = (int *)(base + lay.sflag);
-  e.voff = (int *)(base + lay.voff);
-  e.cnt = (int *)(base + lay.cnt);
-  e.envi = (int *)(base + lay.envi);
-  e.cmoff = (int *)(base + lay.cmoff);
-  e.cmask = (unsigned *)(base + lay.cmask);
-  e.scratch = base + lay.scratch;
-  e.vslot = base + lay.vslot;
-  e.env_id = n;
-  e.seed = a.io.seed;
-  e.substep = 0;
-  e.n_calls = e.n_true = e.n_coll = 0;
-  e.hash = 0;
-  const int ND = pv.hdr[MOOG_H_NOISE_DIM], RND = pv.hdr[MOOG_H_RULE_NOISE_DIM];
-  e.noise = a.io.noise ? a.io.noise + (size_t)n * e.K * ND : nullptr;
-  e.rule_noise = a.io.rule_noise ? a.io.rule_noise + (size_t)n * RND : nullptr;
+  const int NF = a.NF;
+  const SmemLayout lay = smem_layout(a.S, a.VT > 0 ? a.VT : 1, NF, a.CMW);
+  unsigned char *base = smem_raw;
+  {
+    int *h = (int *)(base + lay.hdr);
+    for (int i = lane; i < MOOG_HDR_WORDS; i += 32) h[i] = pv.hdr[i];
+    if (lane < 10) ((long long *)(base + lay.ctr))[lane] = 0;
+    if (lane == 0) {
+      EnvRec *r = (EnvRec *)(base + lay.rec);
+      r->lay = lay;
+      r->S = a.S; r->L = a.L; r->K = a.K; r->VT = a.VT;
+      r->env_id = n;
+      r->ops = pv.ops; r->ipool = pv.ipool; r->expr = pv.expr;
+      const int ND = pv.hdr[MOOG_H_NOISE_DIM], RND = pv.hdr[MOOG_H_RULE_NOISE_DIM];
+      r->noise = a.io.noise ? a.io.noise + (size_t)n * a.K * ND : nullptr;
+      r->rule_noise = a.io.rule_noise ? a.io.rule_noise + (size_t)n * RND : nullptr;
+      r->seed = a.io.seed;
+    }
+    wsync();
+  }
+  const Env e = env_view();
 
   // slot -> first cached vertex, vertex -> slot
   for (int s = lane; s <= e.S; s += 32) e.voff[s] = pv.voff[s];
@@ -1920,18 +2012,22 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
   copy_i(e.envi, a.st.envi + (size_t)n * MOOG_ENVI_WORDS, MOOG_ENVI_WORDS, lane);
   wsync();
   const bool do_reset = a.mode == MODE_ENV_STEP && a.io.pool != nullptr && e.envi[MOOG_EI_RESET_NEXT] != 0;
-  if (do_reset) {
-    int idx;
-    if (a.io.reset_index) {
-      idx = a.io.reset_index[n];
-    } else {
-      double u = philox_uniform(a.io.seed ^ 0xD1B54A32D192ED03ull, (uint32_t)n, (uint32_t)e.envi[MOOG_EI_EPISODES], 0u, 0u);
-      idx = (int)(u * a.io.pool_size);
+  {
+    const moog_state *src = &a.st;
+    size_t row = (size_t)n;
+    if (do_reset) {
+      int idx;
+      if (a.io.reset_index) {
+        idx = a.io.reset_index[n];
+      } else {
+        double u = philox_uniform(a.io.seed ^ 0xD1B54A32D192ED03ull, (uint32_t)n, (uint32_t)e.envi[MOOG_EI_EPISODES], 0u, 0u);
+        idx = (int)(u * a.io.pool_size);
+      }
+      idx = idx < 0 ? 0 : (idx >= a.io.pool_size ? a.io.pool_size - 1 : idx);
+      src = &a.pool;
+      row = (size_t)idx;
     }
-    idx = idx < 0 ? 0 : (idx >= a.io.pool_size ? a.io.pool_size - 1 : idx);
-    load_env(e, a.pool, (size_t)idx, false);
-  } else {
-    load_env(e, a.st, (size_t)n, false);
+    load_env(e, *src, row, false);
   }
   wsync();
   refresh_all_boxes(e);
@@ -1940,15 +2036,16 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
   int step_type = MOOG_STEP_MID;
   double ep_len_done = 0.0, ep_done = 0.0;
 
-  if (a.mode == MODE_POST_RESET) {
+  const bool full_step = a.mode == MODE_ENV_STEP && !do_reset;
+  if (a.mode == MODE_POST_RESET || do_reset) {
+    if (do_reset) {
+      int ep = e.envi[MOOG_EI_EPISODES] + 1;
+      wsync();
+      puti(e, &e.envi[MOOG_EI_EPISODES], ep);
+    }
     post_reset(e);
     reward = NAN;
     step_type = MOOG_STEP_FIRST;
-  } else if (a.mode == MODE_PHYSICS) {
-    for (int k = 0; k < e.K; ++k) {
-      e.substep = k;
-      apply_physics(e);
-    }
   } else if (a.mode == MODE_OVERLAP) {
     int la = a.layer_a, lb = a.layer_b;
     int ca = LOFF(e, la + 1) - LOFF(e, la), cb = LOFF(e, lb + 1) - LOFF(e, lb);
@@ -1960,34 +2057,33 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
         bool r = overlaps(e, LOFF(e, la) + i, LOFF(e, lb) + j);
         if (lane == 0) o[i * cb + j] = (uint8_t)r;
       }
-  } else if (do_reset) {
-    int ep = e.envi[MOOG_EI_EPISODES] + 1;
-    wsync();
-    puti(e, &e.envi[MOOG_EI_EPISODES], ep);
-    post_reset(e);
-    reward = NAN;
-    step_type = MOOG_STEP_FIRST;
   } else {
-    // environment.py:98-126
-    rules_step(e);
-    actions_step(e, a.io.actions ? a.io.actions + (size_t)n * pv.hdr[MOOG_H_ACTION_DIM] : nullptr);
+    // environment.py:98-126 (MODE_PHYSICS: abstract_physics.py:39-42 alone)
+    if (full_step) {
+      rules_step(e);
+      actions_step(e, a.io.actions ? a.io.actions + (size_t)n * e.hdr[MOOG_H_ACTION_DIM] : nullptr);
+    }
     for (int k = 0; k < e.K; ++k) {
-      e.substep = k;
+      wsync();
+      if (lane == 0) e.ctr[CT_SUBSTEP] = k;
+      wsync();
       apply_physics(e);
     }
-    int sc = e.envi[MOOG_EI_STEP_COUNT] + 1;
-    wsync();
-    puti(e, &e.envi[MOOG_EI_STEP_COUNT], sc);
-    wsync();
-    int reset;
-    tasks_reward(e, sc, &reward, &reset);
-    step_type = reset ? MOOG_STEP_LAST : MOOG_STEP_MID;
-    wsync();
-    puti(e, &e.envi[MOOG_EI_RESET_NEXT], reset);
-    wsync();
-    if (reset) {
-      ep_len_done = (double)sc;
-      ep_done = 1.0;
+    if (full_step) {
+      int sc = e.envi[MOOG_EI_STEP_COUNT] + 1;
+      wsync();
+      puti(e, &e.envi[MOOG_EI_STEP_COUNT], sc);
+      wsync();
+      int reset;
+      tasks_reward(e, sc, &reward, &reset);
+      step_type = reset ? MOOG_STEP_LAST : MOOG_STEP_MID;
+      wsync();
+      puti(e, &e.envi[MOOG_EI_RESET_NEXT], reset);
+      wsync();
+      if (reset) {
+        ep_len_done = (double)sc;
+        ep_done = 1.0;
+      }
     }
   }
   wsync();
@@ -1998,14 +2094,14 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
     if (a.io.discount)
       a.io.discount[n] = step_type == MOOG_STEP_FIRST ? NAN : (step_type == MOOG_STEP_LAST ? 0.0f : 1.0f);
     if (a.io.counters) {
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 0] = e.n_calls;
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 1] = e.n_true;
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 2] = e.n_coll;
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 3] = (long long)e.hash;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 0] = e.ctr[CT_CALLS];
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 1] = e.ctr[CT_TRUE];
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 2] = e.ctr[CT_COLL];
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 3] = e.ctr[CT_HASH];
       a.io.counters[MOOG_N_COUNTERS * (size_t)n + 4] = clock64() - t_begin;
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 5] = 0;
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 6] = 0;
-      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 7] = 0;
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 5] = e.ctr[CT_NARROW];
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 6] = e.ctr[CT_CYC_NARROW];
+      a.io.counters[MOOG_N_COUNTERS * (size_t)n + 7] = e.ctr[CT_CYC_RESOLVE];
     }
     if (a.io.stats && a.mode == MODE_ENV_STEP) {
       if (step_type != MOOG_STEP_FIRST) {
@@ -2023,8 +2119,7 @@ __global__ void __launch_bounds__(64) moog_step_kernel(StepArgs a) {
 cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
   if (a.n_envs <= 0) return cudaSuccess;
   int per_env = env_smem_bytes(hdr);
-  int warps = 2;
-  if (per_env * warps > 200 * 1024) warps = 1;
+  const int warps = 1;
   size_t smem = (size_t)per_env * warps;
   static size_t configured = 0;
   if (smem > configured) {
@@ -2033,7 +2128,14 @@ cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stre
     configured = smem;
   }
   int blocks = (a.n_envs + warps - 1) / warps;
-  moog_step_kernel<<<blocks, warps * 32, smem, stream>>>(a);
+  StepArgs b = a;
+  b.S = hdr[MOOG_H_N_SLOTS];
+  b.L = hdr[MOOG_H_N_LAYERS];
+  b.K = hdr[MOOG_H_K];
+  b.VT = hdr[MOOG_H_N_VTX];
+  b.NF = hdr[MOOG_H_N_ENVF];
+  b.CMW = hdr[MOOG_H_CMASK_WORDS];
+  moog_step_kernel<<<blocks, warps * 32, smem, stream>>>(b);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

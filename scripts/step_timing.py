@@ -20,4 +20,8 @@ for t in range(T):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); eng.env_step(act, want_counters=True); e1.record(); torch.cuda.synchronize()
     c = eng.counters.double().mean(0).tolist()
-    print('step %3d  %8.3f ms  calls %.0f true %.1f coll %.1f  last %d' % (t, e0.elapsed_time(e1), c[0], c[1], c[2], int((eng.step_type == 2).sum())), flush=True)
+    cm = eng.counters.double().max(0).values.tolist()
+    top = int(eng.counters[:, 4].argmax())
+    tc = eng.counters[top].tolist()
+    print('step %3d  %8.3f ms  calls %.0f true %.1f coll %.1f  last %d | cycles mean %.3g max %.3g | narrow n %.1f cyc %.3g | resolve cyc %.3g' % (
+        t, e0.elapsed_time(e1), c[0], c[1], c[2], int((eng.step_type == 2).sum()), c[4], cm[4], c[5], c[6], c[7]), 'top env', top, tc, flush=True)
