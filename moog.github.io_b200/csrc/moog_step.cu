@@ -48,7 +48,7 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, hdr, scratch, vslot, total;
+  int rec, dyn, stat, aabb, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, hdr, scratch, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
@@ -73,7 +73,6 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.cmask = o; o += 4 * (CMW > 0 ? CMW : 1);
   L.hdr = o;   o += 4 * MOOG_HDR_WORDS;
   L.scratch = o; o += 64;
-  L.vslot = o; o += VT;
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -103,7 +102,7 @@ struct Env {
   double2 *vtx;
   int *meta, *sflag, *voff, *cnt, *envi, *cmoff;
   unsigned *cmask;
-  unsigned char *scratch, *vslot;
+  unsigned char *scratch;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -157,7 +156,6 @@ __device__ __forceinline__ Env env_view() {
   e.cmask = (unsigned *)(base + r->lay.cmask);
   e.hdr = (const int32_t *)(base + r->lay.hdr);
   e.scratch = base + r->lay.scratch;
-  e.vslot = base + r->lay.vslot;
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x;
@@ -175,7 +173,10 @@ __device__ __forceinline__ void ctr_add(const Env &e, int k, long long v) {
 #define DYN(e, f, s) ((e).dyn[(f) * (e).S + (s)])
 #define STAT(e, f, s) ((e).stat[(f) * (e).S + (s)])
 #define META(e, f, s) ((e).meta[(f) * (e).S + (s)])
-#define BOX(e, f, s) ((e).aabb[(f) * (e).S + (s)])
+// bounding box of slot s: [xmin, ymin, xmax + AABB_PAD, ymax + AABB_PAD], interleaved per slot.
+// The maxima are stored padded so that the broad phase is four compares; the
+// pad only has to be conservative (>> accumulated rounding), never exact.
+#define BOX(e, f, s) ((e).aabb[4 * (s) + (f)])
 #define TMP(e, f, s) ((e).tmp[(f) * (e).S + (s)])
 #define LOFF(e, l) ((e).hdr[MOOG_H_LAYER_OFF + (l)])
 
@@ -282,6 +283,15 @@ __device__ __forceinline__ double moment_of_inertia(const Env &e, int s) {
 // bounding boxes of the cached outlines
 // ---------------------------------------------------------------------------
 
+// A slot with a NaN / inf coordinate gets an all-covering box: it is never culled.
+__device__ __forceinline__ void store_box(const Env &e, int s, double xmin, double ymin, double xmax, double ymax,
+                                          bool nonfinite) {
+  BOX(e, 0, s) = nonfinite ? -INFINITY : xmin;
+  BOX(e, 1, s) = nonfinite ? -INFINITY : ymin;
+  BOX(e, 2, s) = nonfinite ? INFINITY : xmax + AABB_PAD;
+  BOX(e, 3, s) = nonfinite ? INFINITY : ymax + AABB_PAD;
+}
+
 // lane-parallel over the vertices of slot s: NaN / inf classification (called
 // when a setter moved the outline by a non-finite amount)
 __device__ inline void classify_slot(const Env &e, int s) {
@@ -296,6 +306,7 @@ __device__ inline void classify_slot(const Env &e, int s) {
   int fl = (e.sflag[s] & ~(SLF_NONFINITE | SLF_ALLNAN)) | (nf ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
   wsync();
   puti(e, &e.sflag[s], fl);
+  if (nf && e.lane == 0) store_box(e, s, 0., 0., 0., 0., true);
   wsync();
 }
 
@@ -317,15 +328,15 @@ __device__ inline void refresh_all_boxes(const Env &e) {
       allnan &= isnan(p.x) && isnan(p.y);
       prev = p;
     }
-    BOX(e, 0, s) = xmin; BOX(e, 1, s) = ymin; BOX(e, 2, s) = xmax; BOX(e, 3, s) = ymax;
+    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite);
     e.sflag[s] = (sh ? SLF_SHORT_EDGE : 0) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
   }
   wsync();
 }
 
 __device__ __forceinline__ bool boxes_apart(const Env &e, int a, int b) {
-  return BOX(e, 2, a) + AABB_PAD < BOX(e, 0, b) || BOX(e, 2, b) + AABB_PAD < BOX(e, 0, a) ||
-         BOX(e, 3, a) + AABB_PAD < BOX(e, 1, b) || BOX(e, 3, b) + AABB_PAD < BOX(e, 1, a);
+  return BOX(e, 2, a) < BOX(e, 0, b) || BOX(e, 2, b) < BOX(e, 0, a) ||
+         BOX(e, 3, a) < BOX(e, 1, b) || BOX(e, 3, b) < BOX(e, 1, a);
 }
 
 // ---------------------------------------------------------------------------
@@ -347,8 +358,8 @@ __device__ __forceinline__ void set_position_impl(const Env &e, int s, double nx
   if (e.lane == 0) {
     DYN(e, MOOG_D_X, s) = nx;
     DYN(e, MOOG_D_Y, s) = ny;
-    // x -> fl(x + tx) is monotone, so the translated box is exactly the box of the
-    // translated vertices
+    // x -> fl(x + tx) is monotone, so the translated minima are exactly the minima of the
+    // translated vertices; the padded maxima stay conservative
     BOX(e, 0, s) = b0 + tx; BOX(e, 1, s) = b1 + ty; BOX(e, 2, s) = b2 + tx; BOX(e, 3, s) = b3 + ty;
   }
   wsync();
@@ -518,7 +529,7 @@ __device__ __forceinline__ bool path_intersects_filled_impl(const Env &e, int a,
       double2 q1 = Q[qact ? e.lane : 0];
       double2 q2 = Q[qact ? ((e.lane + 1 == nQ) ? 0 : e.lane + 1) : 0];
       double Pxmin = BOX(e, 0, pslot) - AABB_PAD, Pymin = BOX(e, 1, pslot) - AABB_PAD;
-      double Pxmax = BOX(e, 2, pslot) + AABB_PAD, Pymax = BOX(e, 3, pslot) + AABB_PAD;
+      double Pxmax = BOX(e, 2, pslot), Pymax = BOX(e, 3, pslot);
       qact = qact && !(fmax(q1.x, q2.x) < Pxmin || fmin(q1.x, q2.x) > Pxmax || fmax(q1.y, q2.y) < Pymin ||
                        fmin(q1.y, q2.y) > Pymax);
     }
@@ -544,8 +555,9 @@ __device__ __forceinline__ bool path_intersects_filled_impl(const Env &e, int a,
         bool h = false;
         if (v && !(fmax(b1.x, b2.x) < axmin || fmin(b1.x, b2.x) > axmax || fmax(b1.y, b2.y) < aymin ||
                    fmin(b1.y, b2.y) > aymax)) {
-          h = lanesA ? segments_intersect(a1.x, a1.y, a2.x, a2.y, b1.x, b1.y, b2.x, b2.y)
-                     : segments_intersect(b1.x, b1.y, b2.x, b2.y, a1.x, a1.y, a2.x, a2.y);
+          const double2 f1 = lanesA ? a1 : b1, f2 = lanesA ? a2 : b2;
+          const double2 g1 = lanesA ? b1 : a1, g2 = lanesA ? b2 : a2;
+          h = segments_intersect(f1.x, f1.y, f2.x, f2.y, g1.x, g1.y, g2.x, g2.y);
         }
         if (__any_sync(FULL, h)) return true;
       }
@@ -1006,16 +1018,14 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
 
 // per-lane: can (a, b) overlap?  (false is exact: the reference would return False)
 __device__ __forceinline__ bool pair_candidate(const Env &e, int a, int b, bool valid) {
-  bool c = false;
-  if (valid) {
-    int fl = e.sflag[a] | e.sflag[b];
-    c = !(fl & SLF_ALLNAN) && ((fl & SLF_NONFINITE) || !boxes_apart(e, a, b));
-  }
+  if (!valid) b = a;
+  bool c = valid && !boxes_apart(e, a, b);
   if (__any_sync(FULL, c)) {
     if (c) {
+      const int fl = e.sflag[a] | e.sflag[b];
       double dx = DYN(e, MOOG_D_X, a) - DYN(e, MOOG_D_X, b);
       double dy = DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, b);
-      c = !(norm1(dx, dy) > STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b));
+      c = !(fl & SLF_ALLNAN) && !(norm1(dx, dy) > STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b));
     }
   }
   return c;
@@ -1440,49 +1450,54 @@ __device__ inline void integrate_all(const Env &e) {
     e.sflag[s] = (e.sflag[s] & SLF_MASK) | (flag << 8);
   }
   wsync();
-  // phase 2: lane = cached vertex
-  for (int v = e.lane; v < e.VT; v += 32) {
-    int s = e.vslot[v];
-    int flag = e.sflag[s] >> 8;
-    if (flag && (v - e.voff[s]) < META(e, MOOG_M_NV, s)) {
-      double2 p = e.vtx[v];
-      double x = 1.0 * p.x + 0.0 * p.y + TMP(e, 0, s);
-      double y = 0.0 * p.x + 1.0 * p.y + TMP(e, 1, s);
-      if (flag & TF_ROT) {
-        double rx = TMP(e, 2, s) * x + TMP(e, 3, s) * y + TMP(e, 4, s);
-        double ry = TMP(e, 5, s) * x + TMP(e, 6, s) * y + TMP(e, 7, s);
-        x = rx;
-        y = ry;
+  // phase 2: one moved slot at a time, lane = vertex of its outline
+  for (int base = 0; base < e.S; base += 32) {
+    const int sl = base + e.lane;
+    unsigned mv = __ballot_sync(FULL, sl < e.S && (e.sflag[sl] >> 8) != 0);
+    while (mv) {
+      const int s = base + __ffs(mv) - 1;
+      mv &= mv - 1;
+      const int flag = e.sflag[s] >> 8;
+      const int n = META(e, MOOG_M_NV, s);
+      double2 *v = e.vtx + e.voff[s];
+      const double tx = TMP(e, 0, s), ty = TMP(e, 1, s);
+      if (e.lane < n) {
+        double2 p = v[e.lane];
+        // Affine2D().translate(tx, ty): 1.0 * x is exact, the 0.0 * y term keeps the
+        // reference's NaN / signed-zero behaviour
+        double x = (p.x + 0.0 * p.y) + tx;
+        double y = (0.0 * p.x + p.y) + ty;
+        if (flag & TF_ROT) {
+          double rx = TMP(e, 2, s) * x + TMP(e, 3, s) * y + TMP(e, 4, s);
+          double ry = TMP(e, 5, s) * x + TMP(e, 6, s) * y + TMP(e, 7, s);
+          x = rx;
+          y = ry;
+        }
+        v[e.lane] = make_double2(x, y);
       }
-      e.vtx[v] = make_double2(x, y);
     }
   }
   wsync();
-  // phase 3: boxes of rotated outlines (lane = slot)
+  // phase 3: boxes of rotated outlines, NaN / inf classification (lane = slot)
   for (int s = e.lane; s < e.S; s += 32) {
-    int flag = e.sflag[s] >> 8;
-    if (flag & TF_ROT) {
+    const int flag = e.sflag[s] >> 8;
+    int low = e.sflag[s] & SLF_MASK;
+    if (flag & (TF_ROT | TF_CLASSIFY)) {
       int n = META(e, MOOG_M_NV, s);
       const double2 *v = e.vtx + e.voff[s];
       double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+      bool nonfinite = false, allnan = n > 0;
+#pragma unroll 1
       for (int i = 0; i < n; ++i) {
         double2 p = v[i];
         xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
         ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
-      }
-      BOX(e, 0, s) = xmin; BOX(e, 1, s) = ymin; BOX(e, 2, s) = xmax; BOX(e, 3, s) = ymax;
-    }
-    int low = e.sflag[s] & SLF_MASK;
-    if (flag & TF_CLASSIFY) {
-      int n = META(e, MOOG_M_NV, s);
-      const double2 *v = e.vtx + e.voff[s];
-      bool nonfinite = false, allnan = n > 0;
-      for (int i = 0; i < n; ++i) {
-        double2 p = v[i];
         nonfinite |= !(isfinite(p.x) && isfinite(p.y));
         allnan &= isnan(p.x) && isnan(p.y);
       }
-      low = (low & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+      if (flag & TF_CLASSIFY)
+        low = (low & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+      store_box(e, s, xmin, ymin, xmax, ymax, (low & SLF_NONFINITE) != 0);
     }
     e.sflag[s] = low;
   }
@@ -1917,10 +1932,12 @@ __device__ __noinline__ void tasks_reward(const Env &, int step_count, double *r
 // ---------------------------------------------------------------------------
 // staging: global <-> shared
 // ---------------------------------------------------------------------------
-__device__ inline void copy_d(double *dst, const double *src, int n, int lane) {
+__device__ __noinline__ void copy_d(double *dst, const double *src, int n, int lane) {
+#pragma unroll 4
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
-__device__ inline void copy_i(int *dst, const int *src, int n, int lane) {
+__device__ __noinline__ void copy_i(int *dst, const int *src, int n, int lane) {
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
@@ -1991,11 +2008,9 @@ __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
   }
   const Env e = env_view();
 
-  // slot -> first cached vertex, vertex -> slot
+  // slot -> first cached vertex
   for (int s = lane; s <= e.S; s += 32) e.voff[s] = pv.voff[s];
   wsync();
-  for (int s = lane; s < e.S; s += 32)
-    for (int v = e.voff[s]; v < e.voff[s + 1]; ++v) e.vslot[v] = (unsigned char)s;
 
   if (lane == 0) {  // offsets of the candidate matrices of the Collision entries
     int off = 0;
