@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     '-std=c++17', '-fmad=false', '-prec-div=true', '-prec-sqrt=true',
     '--expt-extended-lambda', '-Xcompiler', '-fPIC,-ffp-contract=off',
     '-Wno-deprecated-gpu-targets',
-]
+] + (['-DMOOG_PROFILE_PHASES'] if os.environ.get('MOOG_PROFILE_PHASES') else [])
 
 
 def _nvcc():

@@ -45,7 +45,7 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
   if (!p) return MOOG_E_INVAL;
   memcpy(p->hdr, hdr, sizeof(p->hdr));
   p->hdr[MOOG_H_CMASK_WORDS] = moog::candidate_matrix_words(blob);
-  if (moog::env_smem_bytes(p->hdr) > 220 * 1024) {
+  if (moog::env_smem_bytes(p->hdr) > 220 * 1024 || p->hdr[MOOG_H_CMASK_WORDS] > 2048) {
     free(p);
     return MOOG_E_TOO_BIG;
   }

@@ -48,22 +48,26 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, hdr, scratch, total;
+  int rec, dyn, stat, aabb, aabb0, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, kscr, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
+#define DCV_TILE 8     /* contained vertices per pass of _directed_collision_vectors */
+#define NEAR_SKIN 0.02
+#define NEAR_CAP 384  /* near-list entries; more near pairs than this -> every pair is tested */
 
 __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW) {
   SmemLayout L;
   int o = 0;
-  L.rec = o;   o += 192;  // EnvRec (static_assert below)
+  L.rec = o;   o += 224;  // EnvRec (static_assert below)
   L.dyn = o;   o += 8 * MOOG_DYN_FIELDS * S;
   L.stat = o;  o += 8 * MOOG_STAT_FIELDS * S;
   L.aabb = o;  o += 8 * 4 * S;
+  L.aabb0 = o; o += 8 * 4 * S;
   L.tmp = o;   o += 8 * 8 * S;
   L.vtx = o;   o += 16 * VT;
   L.envf = o;  o += 8 * NF;
-  L.ctr = o;   o += 8 * 10;
+  L.ctr = o;   o += 8 * 12;
   L.meta = o;  o += 4 * MOOG_META_FIELDS * S;
   L.sflag = o; o += 4 * S;
   L.voff = o;  o += 4 * (S + 1);
@@ -71,8 +75,11 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.envi = o;  o += 4 * MOOG_ENVI_WORDS;
   L.cmoff = o; o += 4 * MOOG_MAX_FORCE_OPS;
   L.cmask = o; o += 4 * (CMW > 0 ? CMW : 1);
+  L.nearp = o; o += CMW > 0 ? 4 * NEAR_CAP : 4;
   L.hdr = o;   o += 4 * MOOG_HDR_WORDS;
   L.scratch = o; o += 64;
+  o = (o + 7) & ~7;
+  L.kscr = o;  o += CMW > 0 ? 8 * 32 * DCV_TILE : 8;
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -98,11 +105,12 @@ int candidate_matrix_words(const void *host_blob) {
 
 struct Env {
   // shared memory
-  double *dyn, *stat, *aabb, *tmp, *envf;
+  double *dyn, *stat, *aabb, *aabb0, *tmp, *envf;
   double2 *vtx;
   int *meta, *sflag, *voff, *cnt, *envi, *cmoff;
-  unsigned *cmask;
+  unsigned *cmask, *nearp;
   unsigned char *scratch;
+  unsigned long long *kscr;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -133,7 +141,7 @@ struct EnvRec {
   const double *noise, *rule_noise;
   uint64_t seed;
 };
-static_assert(sizeof(EnvRec) <= 192, "EnvRec must fit its shared-memory slot");
+static_assert(sizeof(EnvRec) <= 224, "EnvRec must fit its shared-memory slot");
 
 __device__ __forceinline__ Env env_view() {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -143,6 +151,7 @@ __device__ __forceinline__ Env env_view() {
   e.dyn = (double *)(base + r->lay.dyn);
   e.stat = (double *)(base + r->lay.stat);
   e.aabb = (double *)(base + r->lay.aabb);
+  e.aabb0 = (double *)(base + r->lay.aabb0);
   e.tmp = (double *)(base + r->lay.tmp);
   e.vtx = (double2 *)(base + r->lay.vtx);
   e.envf = (double *)(base + r->lay.envf);
@@ -154,8 +163,10 @@ __device__ __forceinline__ Env env_view() {
   e.envi = (int *)(base + r->lay.envi);
   e.cmoff = (int *)(base + r->lay.cmoff);
   e.cmask = (unsigned *)(base + r->lay.cmask);
+  e.nearp = (unsigned *)(base + r->lay.nearp);
   e.hdr = (const int32_t *)(base + r->lay.hdr);
   e.scratch = base + r->lay.scratch;
+  e.kscr = (unsigned long long *)(base + r->lay.kscr);
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x;
@@ -165,7 +176,14 @@ __device__ __forceinline__ Env env_view() {
   return e;
 }
 
-enum { CT_CALLS = 0, CT_TRUE, CT_COLL, CT_HASH, CT_CYCLES, CT_NARROW, CT_CYC_NARROW, CT_CYC_RESOLVE, CT_SUBSTEP };
+#ifdef MOOG_PROFILE_PHASES
+#define PROF_RESOLVE(e, t1)
+#else
+#define PROF_RESOLVE(e, t1) ctr_add(e, CT_CYC_RESOLVE, clock64() - (t1))
+#endif
+
+enum { CT_CALLS = 0, CT_TRUE, CT_COLL, CT_HASH, CT_CYCLES, CT_NARROW, CT_CYC_NARROW, CT_CYC_RESOLVE, CT_SUBSTEP,
+       CT_NEAR /* near-list length; -1 overflowed, -2 not built yet */ };
 __device__ __forceinline__ void ctr_add(const Env &e, int k, long long v) {
   if (e.lane == 0) e.ctr[k] += v;
 }
@@ -216,6 +234,12 @@ __device__ inline double philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1,
 __device__ __forceinline__ double norm_ax(double x, double y) { return sqrt(x * x + y * y); }
 __device__ __forceinline__ double dot2(double ax, double ay, double bx, double by) { return fma(ay, by, ax * bx); }
 __device__ __forceinline__ double norm1(double x, double y) { return sqrt(dot2(x, y, x, y)); }
+// a / b where a is often exactly zero (DownGravity's x component): a zero numerator
+// takes the fp64 division's slow path, so produce its signed-zero result directly
+__device__ __forceinline__ double div_z(double a, double b) {
+  if (a == 0.0 && b != 0.0 && isfinite(b)) return (signbit(a) != signbit(b)) ? -0.0 : 0.0;
+  return a / b;
+}
 __device__ __forceinline__ double f32r(double x) { return (double)(float)x; }
 __device__ __forceinline__ double f32mul(double a, double b) { return (double)__fmul_rn((float)a, (float)b); }
 __device__ __forceinline__ double f32add(double a, double b) { return (double)__fadd_rn((float)a, (float)b); }
@@ -665,49 +689,104 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
   double2 q2 = P1[eact ? ((e.lane + 1 == n1) ? 0 : e.lane + 1) : 0];
   double d1x = q2.x - q1.x, d1y = q2.y - q1.y;
 
-  bool any_cross = false;
+  // Stage A (lane = edge of s1, one contained vertex after the other, no
+  // cross-lane traffic so consecutive vertices overlap in the pipeline): the
+  // argmin key of every (vertex, edge) goes to a shared-memory tile.
+  // Stage B (lane = vertex): each lane scans its row of the tile for np.argmin
+  // (first index on ties), recomputes the winning edge's coefficient -- the same
+  // IEEE operations, hence the same bits -- and the penetration length.
+  // Stage C: np.argmax over the vertices by two warp maxima.
+  bool my_cross = false;
   bool have = false;
   double b_dist = 0, b_cpx = 0, b_cpy = 0, b_dfx = 0, b_dfy = 0, b_a = 0;
   int b_edge = 0;
+  unsigned long long *keys = e.kscr;
   while (mask) {
-    int c = __ffs(mask) - 1;
-    mask &= mask - 1;
-    double2 ev = P0[c];  // traj[:,1]
-    double ex = ev.x, ey = ev.y;
-    double sx = M.m0 * ex + M.m1 * ey + M.m2;  // traj[:,0]
-    double sy = M.m3 * ex + M.m4 * ey + M.m5;
-    double d0x = ex - sx, d0y = ey - sy;
-    // sprite.py:145-161 segment_crossing_coefficients against edge `lane`
-    double den = (d0x * d1y - d0y * d1x) + EPS_INTERP;
-    double qx = q1.x - sx, qy = q1.y - sy;
-    double A = (qx * d1y - qy * d1x) / den;
-    double Bc = (qx * d0y - qy * d0x) / den;
-    bool crossing = eact && (Bc >= 0) && (Bc <= 1);
-    any_cross |= (__any_sync(FULL, crossing) != 0);
-    if (!crossing) A = -INFINITY;
-    double ab = fabs(1.0 - A);
-    // np.argmin over the edges: a NaN beats everything, then the smaller value,
-    // then the smaller index.  ab >= 0 or NaN, so its bit pattern orders like the
-    // value: two 32-bit warp minima + a ballot replace a 5-round shuffle tournament.
-    unsigned long long key = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
-    if (!eact) key = ~0ull;
-    const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
-    const unsigned mhi = __reduce_min_sync(FULL, khi);
-    const bool c1 = khi == mhi;
-    const unsigned mlo = __reduce_min_sync(FULL, c1 ? klo : 0xffffffffu);
-    const int idx = __ffs(__ballot_sync(FULL, c1 && klo == mlo)) - 1;
-    A = shfl_d(A, idx);
-    double cpx = sx + A * (ex - sx), cpy = sy + A * (ey - sy);
-    double dfx = ex - cpx, dfy = ey - cpy;
-    double dist = norm_ax(dfx, dfy);
-    if (dist == INFINITY) dist = 0.0;
-    // np.argmax over the contained vertices: first NaN wins, else first maximum
-    bool take = !have || (!isnan(b_dist) && (isnan(dist) || dist > b_dist));
+    int cnt = 0;
+#pragma unroll 2
+    for (; cnt < DCV_TILE && mask; ++cnt) {
+      const int c = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double2 ev = P0[c];  // traj[:,1]
+      const double ex = ev.x, ey = ev.y;
+      const double sx = M.m0 * ex + M.m1 * ey + M.m2;  // traj[:,0]
+      const double sy = M.m3 * ex + M.m4 * ey + M.m5;
+      const double d0x = ex - sx, d0y = ey - sy;
+      // sprite.py:145-161 segment_crossing_coefficients against edge `lane`
+      const double den = (d0x * d1y - d0y * d1x) + EPS_INTERP;
+      const double qx = q1.x - sx, qy = q1.y - sy;
+      // (lanes past the last edge skip the divisions: their zero numerators would
+      // send the whole warp through the fp64 division slow path)
+      double A = -INFINITY;
+      if (eact) {
+        const double Bc = (qx * d0y - qy * d0x) / den;
+        if ((Bc >= 0) && (Bc <= 1)) {
+          my_cross = true;
+          A = (qx * d1y - qy * d1x) / den;
+        }
+      }
+      const double ab = fabs(1.0 - A);
+      // np.argmin order: a NaN beats everything, then the smaller value (ab >= 0, so
+      // its bit pattern orders like the value), then the smaller index
+      unsigned long long key = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
+      if (!eact) key = ~0ull;
+      keys[cnt * 32 + e.lane] = key;
+      if (e.lane == 0) e.scratch[cnt] = (unsigned char)c;
+    }
+    wsync();
+    // stage B
+    const bool vact = e.lane < cnt;
+    int idx = 0;
+    double A = 0, cpx = 0, cpy = 0, dfx = 0, dfy = 0, dist = 0;
+    if (vact) {
+      const unsigned long long *row = keys + e.lane * 32;
+      unsigned long long best = row[0];
+#pragma unroll 4
+      for (int j = 1; j < n1; ++j) {
+        const unsigned long long k = row[j];
+        if (k < best) {
+          best = k;
+          idx = j;
+        }
+      }
+      const double2 ev = P0[e.scratch[e.lane]];
+      const double ex = ev.x, ey = ev.y;
+      const double sx = M.m0 * ex + M.m1 * ey + M.m2;
+      const double sy = M.m3 * ex + M.m4 * ey + M.m5;
+      const double d0x = ex - sx, d0y = ey - sy;
+      const double2 w1 = P1[idx], w2 = P1[(idx + 1 == n1) ? 0 : idx + 1];
+      const double e1x = w2.x - w1.x, e1y = w2.y - w1.y;
+      const double den = (d0x * e1y - d0y * e1x) + EPS_INTERP;
+      const double qx = w1.x - sx, qy = w1.y - sy;
+      const double Bc = (qx * d0y - qy * d0x) / den;
+      A = ((Bc >= 0) && (Bc <= 1)) ? (qx * e1y - qy * e1x) / den : -INFINITY;
+      cpx = sx + A * (ex - sx);
+      cpy = sy + A * (ey - sy);
+      dfx = ex - cpx;
+      dfy = ey - cpy;
+      dist = norm_ax(dfx, dfy);
+      if (dist == INFINITY) dist = 0.0;
+    }
+    // stage C: np.argmax over this tile's vertices: first NaN wins, else first maximum
+    unsigned long long k2 = !vact ? 0ull : (isnan(dist) ? ~0ull : (unsigned long long)__double_as_longlong(dist) + 1ull);
+    const unsigned hi = (unsigned)(k2 >> 32), lo = (unsigned)k2;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    const bool t1 = hi == mhi;
+    const unsigned mlo = __reduce_max_sync(FULL, t1 ? lo : 0u);
+    const int wl = __ffs(__ballot_sync(FULL, t1 && lo == mlo)) - 1;
+    const double wdist = shfl_d(dist, wl);
+    const bool take = !have || (!isnan(b_dist) && (isnan(wdist) || wdist > b_dist));
     if (take) {
       have = true;
-      b_dist = dist; b_cpx = cpx; b_cpy = cpy; b_dfx = dfx; b_dfy = dfy; b_a = A; b_edge = idx;
+      b_dist = wdist;
+      b_cpx = shfl_d(cpx, wl); b_cpy = shfl_d(cpy, wl);
+      b_dfx = shfl_d(dfx, wl); b_dfy = shfl_d(dfy, wl);
+      b_a = shfl_d(A, wl);
+      b_edge = __shfl_sync(FULL, idx, wl);
     }
+    wsync();
   }
+  const bool any_cross = __any_sync(FULL, my_cross) != 0;
   if (!any_cross) return;  // collisions.py:177-179
   o.has_point = 1;
   o.has_since = 1;
@@ -966,8 +1045,10 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
     } else {
       ov = overlaps(e, s0, s1);
     }
+#ifndef MOOG_PROFILE_PHASES
     ctr_add(e, CT_NARROW, 1);
     ctr_add(e, CT_CYC_NARROW, clock64() - t0);
+#endif
     if (!ov) return changed;
     long long t1 = clock64();
     double dt = 1.0 / e.K;
@@ -978,7 +1059,7 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
       changed |= symmetric ? 3 : 1;
     } else {
       if (cv.future) {
-        ctr_add(e, CT_CYC_RESOLVE, clock64() - t1);
+        PROF_RESOLVE(e, t1);
         return changed;
       }
       ctr_add(e, CT_COLL, 1);
@@ -997,7 +1078,7 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
       else
         collide_without_update_angle_vel(e, s0, s1, cv, op->p[0], symmetric);
     }
-    ctr_add(e, CT_CYC_RESOLVE, clock64() - t1);
+    PROF_RESOLVE(e, t1);
     depth += 1;
   }
 }
@@ -1031,84 +1112,105 @@ __device__ __forceinline__ bool pair_candidate(const Env &e, int a, int b, bool 
   return c;
 }
 
-// row `i` of the matrix of force op `f`: lane = sprite_1
-__device__ inline void candidate_row(const Env &e, const moog_op *op, int f, int i) {
-  const int la = op->i[0], lb = op->i[1];
-  const int nb = e.cnt[lb], sb = LOFF(e, lb), s0 = LOFF(e, la) + i;
-  const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
-  for (int w = 0; w * 32 < nb; ++w) {
-    int j = w * 32 + e.lane;
-    unsigned m = __ballot_sync(FULL, pair_candidate(e, s0, sb + j, j < nb && sb + j != s0));
-    if (e.lane == 0) e.cmask[e.cmoff[f] + i * wpr + w] = m;
-  }
-}
+// Near list ("Verlet list with a skin").  Evaluating every pair every substep is
+// wasted on pairs that are far apart, so the pairs whose boxes come within
+// NEAR_SKIN of each other are listed once, together with a snapshot of the boxes;
+// the list stays a superset of all possible candidates for as long as no box
+// coordinate has drifted by NEAR_SKIN / 2 since the snapshot.  Each refresh of
+// the candidate matrices then tests 32 listed pairs per warp pass.
 
-// column `j` of the matrix of force op `f`: lane = sprite_0, every lane patches its own row word
-__device__ inline void candidate_col(const Env &e, const moog_op *op, int f, int j) {
-  const int la = op->i[0], lb = op->i[1];
-  const int na = e.cnt[la], sa = LOFF(e, la), s1 = LOFF(e, lb) + j;
-  const int wpr = (LOFF(e, lb + 1) - LOFF(e, lb) + 31) >> 5;
-  for (int base = 0; base < na; base += 32) {
-    int i = base + e.lane;
-    bool c = pair_candidate(e, sa + i, s1, i < na && sa + i != s1);
-    if (i < na) {
-      unsigned *w = &e.cmask[e.cmoff[f] + i * wpr + (j >> 5)];
-      *w = (*w & ~(1u << (j & 31))) | ((unsigned)c << (j & 31));
-    }
-  }
-}
-
-// all matrices, from scratch (start of a substep)
-__device__ inline void build_candidates(const Env &e) {
+// entry = slot a | slot b << 8 | (bit index in cmask) << 16
+__device__ __noinline__ void rebuild_near(const Env &) {
+  const Env e = env_view();
   const int32_t *h = e.hdr;
-  wsync();
+  for (int i = e.lane; i < 4 * e.S; i += 32) e.aabb0[i] = e.aabb[i];
+  int count = 0;
+  bool overflow = false;
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
     const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
     if (op->kind != MOOG_F_COLLISION) continue;
     const int la = op->i[0], lb = op->i[1];
-    const int na = e.cnt[la], nb = e.cnt[lb];
-    if (nb >= na) {
-      for (int i = 0; i < na; ++i) candidate_row(e, op, f, i);
-    } else {
-      // fewer second sprites than first ones: lane = sprite_0, loop over sprite_1
-      const int sa = LOFF(e, la), sb = LOFF(e, lb);
-      const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
-      for (int base = 0; base < na; base += 32) {
-        int i = base + e.lane;
-        for (int w = 0; w * 32 < nb; ++w) {
-          unsigned m = 0;
-          int jend = min(nb - w * 32, 32);
-          for (int jj = 0; jj < jend; ++jj) {
-            int s1 = sb + w * 32 + jj;
-            m |= (unsigned)pair_candidate(e, sa + i, s1, i < na && sa + i != s1) << jj;
-          }
-          if (i < na) e.cmask[e.cmoff[f] + i * wpr + w] = m;
+    const int na = e.cnt[la], nb = e.cnt[lb], sa = LOFF(e, la), sb = LOFF(e, lb);
+    const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
+#pragma unroll 1
+    for (int i = 0; i < na && !overflow; ++i) {
+      const int s0 = sa + i;
+      const double x0 = BOX(e, 0, s0) - NEAR_SKIN, y0 = BOX(e, 1, s0) - NEAR_SKIN;
+      const double x1 = BOX(e, 2, s0) + NEAR_SKIN, y1 = BOX(e, 3, s0) + NEAR_SKIN;
+#pragma unroll 1
+      for (int w = 0; w * 32 < nb; ++w) {
+        const int j = w * 32 + e.lane;
+        const int s1 = (j < nb) ? sb + j : s0;
+        // NaN boxes compare false everywhere -> near
+        const bool near = j < nb && s1 != s0 &&
+                          !(x1 < BOX(e, 0, s1) || BOX(e, 2, s1) < x0 || y1 < BOX(e, 1, s1) || BOX(e, 3, s1) < y0);
+        const unsigned m = __ballot_sync(FULL, near);
+        const int n = __popc(m);
+        if (count + n > NEAR_CAP) {
+          overflow = true;
+          break;
         }
+        if (near)
+          e.nearp[count + __popc(m & ((1u << e.lane) - 1u))] =
+              (unsigned)s0 | ((unsigned)s1 << 8) | ((unsigned)((e.cmoff[f] + i * wpr + w) * 32 + e.lane) << 16);
+        count += n;
       }
     }
   }
+  if (e.lane == 0) e.ctr[CT_NEAR] = overflow ? -1 : count;
   wsync();
 }
 
-// sprite `s` moved: refresh its row / column in every matrix
-__device__ inline void update_candidates(const Env &e, int s) {
+// every pair of every Collision entry (fallback when the near list overflowed)
+__device__ __noinline__ void build_candidates_full(const Env &) {
+  const Env e = env_view();
   const int32_t *h = e.hdr;
-  wsync();
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
     const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
     if (op->kind != MOOG_F_COLLISION) continue;
     const int la = op->i[0], lb = op->i[1];
-    int i = s - LOFF(e, la), j = s - LOFF(e, lb);
-    if (i >= 0 && i < e.cnt[la]) candidate_row(e, op, f, i);
-    wsync();
-    if (j >= 0 && j < e.cnt[lb]) candidate_col(e, op, f, j);
-    wsync();
+    const int na = e.cnt[la], nb = e.cnt[lb], sa = LOFF(e, la), sb = LOFF(e, lb);
+    const int wpr = (LOFF(e, lb + 1) - sb + 31) >> 5;
+#pragma unroll 1
+    for (int i = 0; i < na; ++i)
+#pragma unroll 1
+      for (int w = 0; w * 32 < nb; ++w) {
+        const int j = w * 32 + e.lane;
+        unsigned m = __ballot_sync(FULL, pair_candidate(e, sa + i, sb + j, j < nb && sb + j != sa + i));
+        if (e.lane == 0) e.cmask[e.cmoff[f] + i * wpr + w] = m;
+      }
   }
+  wsync();
+}
+
+// Bring the candidate matrices up to date with the current positions (start of
+// a substep, and after every resolved contact).
+__device__ inline void refresh_candidates(const Env &e, int n_cmask_words) {
+  wsync();
+  // has any box drifted too far since the near list was built?  (NaN -> yes)
+  bool bad = false;
+  for (int i = e.lane; i < 4 * e.S; i += 32) bad |= !(fabs(e.aabb[i] - e.aabb0[i]) < 0.5 * NEAR_SKIN);
+  if (__any_sync(FULL, bad) || e.ctr[CT_NEAR] == -2) rebuild_near(e);
+  const int n_near = (int)e.ctr[CT_NEAR];
+  if (n_near < 0) {
+    build_candidates_full(e);
+    return;
+  }
+  for (int i = e.lane; i < n_cmask_words; i += 32) e.cmask[i] = 0u;
+  wsync();
+#pragma unroll 1
+  for (int base = 0; base < n_near; base += 32) {
+    const int k = base + e.lane;
+    const unsigned ent = e.nearp[k < n_near ? k : 0];
+    const bool c = pair_candidate(e, (int)(ent & 255u), (int)((ent >> 8) & 255u), k < n_near);
+    if (c) atomicOr(&e.cmask[ent >> 21], 1u << ((ent >> 16) & 31u));
+  }
+  wsync();
 }
 
 // One Collision entry (physics.py:92-108 for a Collision force): the candidate
 // pairs of its matrix in row-major order = itertools.product order.
-__device__ inline void collision_op(const Env &e, const moog_op *op, int f) {
+__device__ inline void collision_op(const Env &e, const moog_op *op, int f, int n_cmask_words) {
   const int la = op->i[0], lb = op->i[1];
   const int na = e.cnt[la], nb = e.cnt[lb];
   const int sa = LOFF(e, la), sb = LOFF(e, lb);
@@ -1137,8 +1239,7 @@ __device__ inline void collision_op(const Env &e, const moog_op *op, int f) {
         ctr_add(e, CT_CALLS, -1);  // collision_step counts this pair's first call itself
         int moved = collision_step(e, op, s0, s1, true);
         if (moved) {
-          if (moved & 1) update_candidates(e, s0);
-          if (moved & 2) update_candidates(e, s1);
+          refresh_candidates(e, n_cmask_words);
           // continue after (i, w, l) with the refreshed matrix
           m = M[wi] & ~((2u << l) - 1u);
           nz = __ballot_sync(FULL, widx < nwords && M[widx] != 0u) & ~((2u << t) - 1u);
@@ -1210,7 +1311,7 @@ __device__ inline void force_unary_layer(const Env &e, const moog_op *op) {
       }
       if (!done && isfinite(m)) {  // abstract_force.py:64-74
         double den = m * (double)e.K;
-        double nvx = vx + fx / den, nvy = vy + fy / den;
+        double nvx = vx + div_z(fx, den), nvy = vy + div_z(fy, den);
         if (v32) {
           nvx = f32r(nvx);
           nvy = f32r(nvy);
@@ -1505,23 +1606,37 @@ __device__ inline void integrate_all(const Env &e) {
 }
 
 // physics.py:88-117 Physics.apply_physics (one substep)
-__device__ inline void apply_physics(const Env &e) {
+__device__ inline void apply_physics(const Env &e, int n_cmask_words) {
   const int32_t *h = e.hdr;
-  build_candidates(e);
+#ifdef MOOG_PROFILE_PHASES
+  long long t0 = clock64();
+#endif
+  refresh_candidates(e, n_cmask_words);
+#ifdef MOOG_PROFILE_PHASES
+  long long t1 = clock64();
+  ctr_add(e, CT_NARROW, t1 - t0);
+#endif
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
     const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
     int la = op->i[0], lb = op->i[1];
     if (lb < 0) {
       force_unary_layer(e, op);
     } else if (op->kind == MOOG_F_COLLISION) {
-      collision_op(e, op, f);
+      collision_op(e, op, f, n_cmask_words);
     } else {
       for (int i = 0; i < e.cnt[la]; ++i)
         for (int j = 0; j < e.cnt[lb]; ++j) force_binary(e, op, LOFF(e, la) + i, LOFF(e, lb) + j);
     }
   }
   for (int c = 0; c < h[MOOG_H_N_CORR]; ++c) corrective(e, e.ops + h[MOOG_H_CORR] + c);
+#ifdef MOOG_PROFILE_PHASES
+  long long t2 = clock64();
+  ctr_add(e, CT_CYC_NARROW, t2 - t1);
+#endif
   integrate_all(e);
+#ifdef MOOG_PROFILE_PHASES
+  ctr_add(e, CT_CYC_RESOLVE, clock64() - t2);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -1992,7 +2107,7 @@ __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
   {
     int *h = (int *)(base + lay.hdr);
     for (int i = lane; i < MOOG_HDR_WORDS; i += 32) h[i] = pv.hdr[i];
-    if (lane < 10) ((long long *)(base + lay.ctr))[lane] = 0;
+    if (lane < 12) ((long long *)(base + lay.ctr))[lane] = lane == CT_NEAR ? -2 : 0;
     if (lane == 0) {
       EnvRec *r = (EnvRec *)(base + lay.rec);
       r->lay = lay;
@@ -2082,7 +2197,7 @@ __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
       wsync();
       if (lane == 0) e.ctr[CT_SUBSTEP] = k;
       wsync();
-      apply_physics(e);
+      apply_physics(e, a.CMW);
     }
     if (full_step) {
       int sc = e.envi[MOOG_EI_STEP_COUNT] + 1;

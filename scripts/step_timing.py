@@ -9,7 +9,8 @@ scene = sys.argv[1] if len(sys.argv) > 1 else 'falling_balls20'
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 cfg = bench._scene_config(scene)
-states = bench._host_states(cfg, 64, 1234)
+POOL = int(os.environ.get('POOL', '64'))
+states = bench._host_states(cfg, POOL, 1234)
 env = BatchedEnvironment(**cfg, num_envs=E, device='cuda:0', seed=1, initial_states=states)
 env.reset()
 eng = env.engine
