@@ -11,6 +11,12 @@ struct moog_program {
   void *dev_blob;
   size_t nbytes;
   int32_t hdr[MOOG_HDR_WORDS];
+  // scheduling scratch owned by the program (the only device memory besides the
+  // blob the library allocates): per-env cost of the previous step and the
+  // dispatch order derived from it
+  int *sched;  // [2][sched_cap]: cost, order
+  int sched_cap;
+  const void *sched_state;  // the state the costs belong to
 };
 
 namespace {
@@ -67,6 +73,7 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
 void moog_program_destroy(moog_program *p) {
   if (!p) return;
   if (p->dev_blob) cudaFree(p->dev_blob);
+  if (p->sched) cudaFree(p->sched);
   free(p);
 }
 
@@ -90,7 +97,30 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   a.layer_b = layer_b;
   a.overlap_out = overlap_out;
   int launches = 0;
-  cudaError_t err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches);
+  cudaError_t err = cudaSuccess;
+  if ((mode == moog::MODE_ENV_STEP || mode == moog::MODE_PHYSICS) && n_envs >= 1024) {
+    // longest-processing-time-first dispatch from the costs of the previous call
+    if (p->sched_cap < n_envs) {
+      if (p->sched) cudaFree(p->sched);
+      p->sched = nullptr;
+      p->sched_cap = 0;
+      err = cudaMalloc((void **)&p->sched, sizeof(int) * 2 * (size_t)n_envs);
+      if (err != cudaSuccess) return cuda_fail(err);
+      p->sched_cap = n_envs;
+      p->sched_state = nullptr;
+    }
+    int *cost = p->sched, *order = p->sched + p->sched_cap;
+    if (p->sched_state != (const void *)st->dyn) {  // another batch: no history yet
+      err = cudaMemsetAsync(cost, 0, sizeof(int) * (size_t)n_envs, (cudaStream_t)stream);
+      if (err != cudaSuccess) return cuda_fail(err);
+      p->sched_state = (const void *)st->dyn;
+    }
+    err = moog::launch_order(cost, order, n_envs, (cudaStream_t)stream, &launches);
+    if (err != cudaSuccess) return cuda_fail(err);
+    a.order = order;
+    a.cost = cost;
+  }
+  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches);
   g_launches += launches;
   return err == cudaSuccess ? 0 : cuda_fail(err);
 }

@@ -35,6 +35,8 @@ struct StepArgs {
   int n_envs;
   int mode;
   int S, L, K, VT, NF, CMW;  // program dimensions (filled in by launch_step from the header)
+  const int *order;          // [n_envs] env handled by CTA i, or nullptr = identity
+  int *cost;                 // [n_envs] SM cycles >> 6 this call cost each env, or nullptr
   moog_step_io io;
   moog_state pool;  // valid iff io.pool != nullptr
   // MODE_OVERLAP
@@ -54,6 +56,7 @@ constexpr int kMaxForceOps = 32;
 int env_smem_bytes(const int32_t *hdr);
 int candidate_matrix_words(const void *host_blob);
 cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
+cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream, int *n_launches);
 cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
 
 }  // namespace moog

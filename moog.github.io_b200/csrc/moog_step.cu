@@ -2096,8 +2096,11 @@ __device__ inline void post_reset(const Env &e) {
 __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
-  const int n = blockIdx.x;
-  if (n >= a.n_envs) return;
+  if ((int)blockIdx.x >= a.n_envs) return;
+  // CTAs are dispatched in blockIdx order: with `order` the envs that were the most
+  // expensive on the previous call go first, so the longest-running env does not
+  // start in the last wave (longest-processing-time-first)
+  const int n = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const long long t_begin = clock64();
 
   ProgramView pv = view_of(a.blob);
@@ -2219,6 +2222,10 @@ __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
   wsync();
   if (a.mode != MODE_OVERLAP) store_env(e, a.st, (size_t)n);
   if (lane == 0) {
+    if (a.cost) {
+      long long c = (clock64() - t_begin) >> 6;
+      a.cost[n] = c > 0x7fffffffll ? 0x7fffffff : (int)c;
+    }
     if (a.io.reward) a.io.reward[n] = (float)reward;
     if (a.io.step_type) a.io.step_type[n] = step_type;
     if (a.io.discount)
@@ -2244,6 +2251,44 @@ __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
       }
     }
   }
+}
+
+// order[] = env indices by decreasing cost[] (bucket sort; the order inside a bucket
+// is arbitrary, which only affects scheduling, never results).  One CTA.
+#define ORDER_BUCKETS 256
+__global__ void __launch_bounds__(1024) moog_order_kernel(const int *cost, int *order, int n) {
+  __shared__ int hist[ORDER_BUCKETS];
+  __shared__ int start[ORDER_BUCKETS];
+  __shared__ int smax;
+  const int t = threadIdx.x;
+  if (t < ORDER_BUCKETS) hist[t] = 0;
+  if (t == 0) smax = 0;
+  __syncthreads();
+  int m = 0;
+  for (int i = t; i < n; i += blockDim.x) m = max(m, cost[i]);
+  atomicMax(&smax, m);
+  __syncthreads();
+  const int shift_div = smax / ORDER_BUCKETS + 1;
+  for (int i = t; i < n; i += blockDim.x) atomicAdd(&hist[min(cost[i] / shift_div, ORDER_BUCKETS - 1)], 1);
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int b = ORDER_BUCKETS - 1; b >= 0; --b) {
+      start[b] = acc;
+      acc += hist[b];
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += blockDim.x) {
+    int b = min(cost[i] / shift_div, ORDER_BUCKETS - 1);
+    order[atomicAdd(&start[b], 1)] = i;
+  }
+}
+
+cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream, int *n_launches) {
+  moog_order_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
