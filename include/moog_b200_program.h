@@ -75,11 +75,20 @@ enum { MOOG_M_SHAPE = 0, MOOG_M_FLAGS, MOOG_M_NV };
 #define MOOG_SF_VEL32 2
 #define MOOG_SF_ANGVEL_SHIFT 2 /* 2 bits */
 #define MOOG_SF_ANG_SHIFT 4    /* 2 bits */
+/* Velocity-array aliasing.  `Tether(update_angle_vel=False)` assigns ONE ndarray
+ * object to every tethered sprite (`s.velocity = total_velocity`,
+ * tether_physics.py:86-91; the setter keeps the object, sprite.py:639-643), so a
+ * later in-place `sprite.velocity += dv` of any force (abstract_force.py:64-74,
+ * collisions.py) changes all of them.  The reference's own tether known-answer
+ * test depends on it.  Sprites whose flags carry the same non-zero alias id share
+ * their velocity; an assignment (`sprite.velocity = v`) clears the id. */
+#define MOOG_SF_VALIAS_SHIFT 8 /* 23 bits */
+#define MOOG_SF_VALIAS_MASK 0x7fffff
 
 #define MOOG_ENVI_WORDS 8
 enum {
   MOOG_EI_STEP_COUNT = 0, MOOG_EI_RESET_NEXT, MOOG_EI_ERR, MOOG_EI_EPISODES,
-  MOOG_EI_RNG0, MOOG_EI_RNG1, MOOG_EI_LAST_RESET, MOOG_EI_SPARE
+  MOOG_EI_RNG0, MOOG_EI_RNG1, MOOG_EI_LAST_RESET, MOOG_EI_VALIAS_NEXT /* last alias id handed out */
 };
 
 /* error bits (data-dependent reference exceptions, raised lazily by the host) */

@@ -254,26 +254,49 @@ __device__ __forceinline__ void set_angvel_kind(const Env &e, int s, int k) {
   wsync();
 }
 
-// `sprite.velocity += dv` (float64 dv; a float32 velocity array keeps its dtype)
+__device__ __forceinline__ int valias(const Env &e, int s) {
+  return (META(e, MOOG_M_FLAGS, s) >> MOOG_SF_VALIAS_SHIFT) & MOOG_SF_VALIAS_MASK;
+}
+// `sprite.velocity += dv` (float64 dv; a float32 velocity array keeps its dtype).
+// The ndarray may be shared with other sprites (MOOG_SF_VALIAS_SHIFT in
+// moog_b200_program.h): the in-place add then shows in all of them.
 __device__ inline void add_velocity(const Env &e, int s, double dvx, double dvy) {
   double vx = DYN(e, MOOG_D_VX, s) + dvx, vy = DYN(e, MOOG_D_VY, s) + dvy;
   if (vel32(e, s)) {
     vx = f32r(vx);
     vy = f32r(vy);
   }
+  const int id = valias(e, s);
   wsync();
-  put(e, &DYN(e, MOOG_D_VX, s), vx);
-  put(e, &DYN(e, MOOG_D_VY, s), vy);
+  if (id) {
+    for (int t = e.lane; t < e.S; t += 32)
+      if (valias(e, t) == id) {
+        DYN(e, MOOG_D_VX, t) = vx;
+        DYN(e, MOOG_D_VY, t) = vy;
+      }
+  } else {
+    put(e, &DYN(e, MOOG_D_VX, s), vx);
+    put(e, &DYN(e, MOOG_D_VY, s), vy);
+  }
   wsync();
 }
-// `sprite.velocity = value` replaces the array by a float64 one
+// `sprite.velocity = value` replaces the array by a new float64 one
 __device__ inline void assign_velocity(const Env &e, int s, double vx, double vy) {
-  int fl = META(e, MOOG_M_FLAGS, s) & ~MOOG_SF_VEL32;
+  int fl = META(e, MOOG_M_FLAGS, s) & ~(MOOG_SF_VEL32 | (MOOG_SF_VALIAS_MASK << MOOG_SF_VALIAS_SHIFT));
   wsync();
   put(e, &DYN(e, MOOG_D_VX, s), vx);
   put(e, &DYN(e, MOOG_D_VY, s), vy);
   puti(e, &META(e, MOOG_M_FLAGS, s), fl);
   wsync();
+}
+// a fresh alias id for an array object that several sprites are about to share
+__device__ inline int new_valias(const Env &e) {
+  int id = e.envi[MOOG_EI_VALIAS_NEXT] + 1;
+  if (id > MOOG_SF_VALIAS_MASK || id < 1) id = 1;
+  wsync();
+  puti(e, &e.envi[MOOG_EI_VALIAS_NEXT], id);
+  wsync();
+  return id;
 }
 // `sprite.angle_vel += dw` with an np.float64 dw
 __device__ inline void add_angvel(const Env &e, int s, double dw) {
@@ -1261,9 +1284,16 @@ __device__ inline double noise_at(const Env &e, int col) {
 // lane = sprite of the layer; a unary force only touches its own sprite's velocity
 __device__ inline void force_unary_layer(const Env &e, const moog_op *op) {
   int la = op->i[0], n = e.cnt[la];
-  for (int base = 0; base < n; base += 32) {
-    int idx = base + e.lane;
-    if (idx < n) {
+  // Sprites that share their velocity array (valias) see each other's in-place
+  // updates: a layer that holds any is visited one sprite at a time.
+  bool shared = false;
+  for (int idx = e.lane; idx < n; idx += 32) shared |= valias(e, LOFF(e, la) + idx) != 0;
+  const bool sequential = __any_sync(FULL, shared) != 0;
+  const int stride = sequential ? 1 : 32;
+  for (int base = 0; base < n; base += stride) {
+    int idx = sequential ? base : base + e.lane;
+    if (sequential) wsync();
+    if (idx < n && (!sequential || e.lane == 0)) {
       int s = LOFF(e, la) + idx;
       double m = STAT(e, MOOG_S_MASS, s);
       double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
@@ -1316,8 +1346,17 @@ __device__ inline void force_unary_layer(const Env &e, const moog_op *op) {
           nvx = f32r(nvx);
           nvy = f32r(nvy);
         }
-        DYN(e, MOOG_D_VX, s) = nvx;
-        DYN(e, MOOG_D_VY, s) = nvy;
+        const int id = valias(e, s);
+        if (id) {  // (sequential mode, lane 0)
+          for (int t = 0; t < e.S; ++t)
+            if (valias(e, t) == id) {
+              DYN(e, MOOG_D_VX, t) = nvx;
+              DYN(e, MOOG_D_VY, t) = nvy;
+            }
+        } else {
+          DYN(e, MOOG_D_VX, s) = nvx;
+          DYN(e, MOOG_D_VY, s) = nvy;
+        }
       }
     }
   }
@@ -1439,9 +1478,12 @@ __device__ inline void tether_sprites(const Env &e, Pick pick, int n, bool updat
       set_angvel_kind(e, s, KIND_F64);
     }
   } else {
+    // `s.velocity = total_velocity`: the SAME ndarray object for every sprite
+    const int id = new_valias(e);
     for (int i = 0; i < n; ++i) {
       int s = pick(i);
       assign_velocity(e, s, tvx, tvy);
+      puti(e, &META(e, MOOG_M_FLAGS, s), META(e, MOOG_M_FLAGS, s) | (id << MOOG_SF_VALIAS_SHIFT));
       put(e, &DYN(e, MOOG_D_ANGVEL, s), 0.);
       set_angvel_kind(e, s, KIND_WEAK);
     }

@@ -252,21 +252,42 @@ static inline void set_angvel_kind(env_t *e, int s, int k) {
 static inline void set_ang_kind(env_t *e, int s, int k) {
   META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (k << MOOG_SF_ANG_SHIFT);
 }
-/* `sprite.velocity += dv` with a float64 dv (ndarray in-place add keeps the dtype) */
+static inline int valias(const env_t *e, int s) {
+  return (META(e, MOOG_M_FLAGS, s) >> MOOG_SF_VALIAS_SHIFT) & MOOG_SF_VALIAS_MASK;
+}
+/* `sprite.velocity += dv` with a float64 dv (ndarray in-place add keeps the dtype).
+ * The array may be shared with other sprites (MOOG_SF_VALIAS_SHIFT): the in-place
+ * add then shows in all of them (sprite.py:639-643, tether_physics.py:86-91). */
 static inline void add_velocity(env_t *e, int s, double dvx, double dvy) {
   double vx = DYN(e, MOOG_D_VX, s) + dvx, vy = DYN(e, MOOG_D_VY, s) + dvy;
   if (vel32(e, s)) {
     vx = f32r(vx);
     vy = f32r(vy);
   }
+  int id = valias(e, s);
+  if (id) {
+    for (int t = 0; t < e->S; ++t)
+      if (valias(e, t) == id) {
+        DYN(e, MOOG_D_VX, t) = vx;
+        DYN(e, MOOG_D_VY, t) = vy;
+      }
+    return;
+  }
   DYN(e, MOOG_D_VX, s) = vx;
   DYN(e, MOOG_D_VY, s) = vy;
 }
-/* `sprite.velocity = value` replaces the array by a float64 one */
+/* `sprite.velocity = value` replaces the array by a new float64 one */
 static inline void assign_velocity(env_t *e, int s, double vx, double vy) {
   DYN(e, MOOG_D_VX, s) = vx;
   DYN(e, MOOG_D_VY, s) = vy;
-  META(e, MOOG_M_FLAGS, s) &= ~MOOG_SF_VEL32;
+  META(e, MOOG_M_FLAGS, s) &= ~(MOOG_SF_VEL32 | (MOOG_SF_VALIAS_MASK << MOOG_SF_VALIAS_SHIFT));
+}
+/* a fresh alias id for an array object that several sprites are about to share */
+static inline int new_valias(env_t *e) {
+  int id = e->envi[MOOG_EI_VALIAS_NEXT] + 1;
+  if (id > MOOG_SF_VALIAS_MASK || id < 1) id = 1;
+  e->envi[MOOG_EI_VALIAS_NEXT] = id;
+  return id;
 }
 /* `sprite.angle_vel += dw` with an np.float64 dw */
 static inline void add_angvel(env_t *e, int s, double dw) {
@@ -907,8 +928,11 @@ static void tether_sprites(env_t *e, const int *sp, int n, int update_angle_vel,
       set_angvel_kind(e, sp[i], KIND_F64);
     }
   } else {
+    /* `s.velocity = total_velocity`: the SAME ndarray object for every sprite */
+    int id = new_valias(e);
     for (int i = 0; i < n; ++i) {
       assign_velocity(e, sp[i], tvx, tvy);
+      META(e, MOOG_M_FLAGS, sp[i]) |= id << MOOG_SF_VALIAS_SHIFT;
       DYN(e, MOOG_D_ANGVEL, sp[i]) = 0.;
       set_angvel_kind(e, sp[i], KIND_WEAK);
     }
