@@ -179,6 +179,167 @@ __device__ inline void polygon_row(const int2 *xy, int count, int y, int ymax_c,
   if (has_horizontal) draw_horizontal_lines(xy, count, closing, y, &x_pos, row, W, row_visible, ink);
 }
 
+// ---------------------------------------------------------------------------
+// Pillow's edge list, built ONCE per sprite (ImagingDrawPolygon, Draw.c): the
+// consecutive collinear horizontal edges are merged exactly as Pillow merges
+// them, dx is divided once.  A row then only reads records.
+// ---------------------------------------------------------------------------
+struct ERec {
+  int x0, y0, ymin, ymax;  // horizontal edge: x0 = xmin, ymin == ymax == y
+  float dx;
+  int xmax_h;              // horizontal edge: xmax
+};
+
+__device__ __forceinline__ ERec make_rec(int2 a, int2 b) {
+  ERec r;
+  r.ymin = min(a.y, b.y);
+  r.ymax = max(a.y, b.y);
+  if (a.y == b.y) {
+    r.x0 = min(a.x, b.x);
+    r.y0 = a.y;
+    r.dx = 0.0f;
+    r.xmax_h = max(a.x, b.x);
+  } else {
+    r.x0 = a.x;
+    r.y0 = a.y;
+    r.dx = __fdiv_rn((float)(b.x - a.x), (float)(b.y - a.y));
+    r.xmax_h = 0;
+  }
+  return r;
+}
+
+// returns the number of records written to E (<= count)
+__device__ inline int build_edge_list(const int2 *xy, int count, ERec *E, int *has_horizontal) {
+  int ne = 0, hz = 0;
+  for (int i = 0; i < count - 1; ++i) {
+    int2 a = xy[i], b = xy[i + 1];
+    if (a.y == b.y) {
+      hz = 1;
+      if (i != 0 && a.y == xy[i - 1].y) {
+        int xp = xy[i - 1].x;
+        if (b.x > a.x && a.x > xp) {
+          E[ne - 1].xmax_h = b.x;
+          continue;
+        } else if (b.x < a.x && a.x < xp) {
+          E[ne - 1].x0 = b.x;
+          continue;
+        }
+      }
+    }
+    E[ne++] = make_rec(a, b);
+  }
+  if (count > 0 && (xy[count - 1].x != xy[0].x || xy[count - 1].y != xy[0].y)) {
+    if (xy[count - 1].y == xy[0].y) hz = 1;
+    E[ne++] = make_rec(xy[count - 1], xy[0]);
+  }
+  *has_horizontal = hz;
+  return ne;
+}
+
+// Where polygon_generic's hline calls go.  BlendSink blends straight into the row
+// (hline32rgba); SpanSink records the clipped spans of one (sprite, row) item so
+// that the rows can be filled later, in z-order, by another thread.
+struct BlendSink {
+  unsigned *row;
+  int W;
+  unsigned ink;
+  __device__ __forceinline__ void hline(int x0, int x1) { moog::hline(row, W, x0, x1, ink); }
+};
+
+#define ITEM_SPANS 3          /* spans stored per item; more -> the item is redone directly */
+#define ITEM_OVERFLOW 0xffu
+struct SpanSink {
+  unsigned *item;  // [1 + ITEM_SPANS] words: count, then x0 | x1 << 16
+  int W;
+  int n;
+  __device__ __forceinline__ void hline(int x0, int x1) {
+    if (x0 < 0) x0 = 0; else if (x0 >= W) return;   // hline32rgba's clipping
+    if (x1 < 0) return; else if (x1 >= W) x1 = W - 1;
+    if (x0 > x1) return;
+    if (n < ITEM_SPANS) item[1 + n] = (unsigned)x0 | ((unsigned)x1 << 16);
+    n++;
+  }
+};
+
+template <class Sink>
+__device__ inline void draw_horizontal_lines_rec(const ERec *E, int ne, int y, int *x_pos, Sink &sink) {
+  for (int i = 0; i < ne; ++i) {
+    const ERec e = E[i];
+    if (e.ymin != e.ymax || e.ymin != y) continue;
+    int xmin = e.x0;
+    if (*x_pos != -1 && *x_pos < xmin) continue;
+    int xmax = e.xmax_h;
+    if (*x_pos > xmin) {
+      xmin = *x_pos;
+      if (xmax < xmin) continue;
+    }
+    if (xmin <= xmax) sink.hline(xmin, xmax);
+    *x_pos = xmax + 1;
+  }
+}
+
+// Draw.c polygon_generic, the iteration of its scanline loop for row y, on the
+// prebuilt edge list.
+template <class Sink>
+__device__ inline void polygon_row_rec(const ERec *E, int ne, int y, int ymax_c, bool has_horizontal, Sink &sink) {
+  float xx[MAX_XX];
+  int j = 0;
+  for (int i = 0; i < ne; ++i) {
+    const ERec cur = E[i];
+    if (cur.ymin == cur.ymax) continue;  // horizontal edges are deferred when blending
+    if (y >= cur.ymin && y <= cur.ymax) {
+      xx[j++] = edge_x(cur.x0, cur.y0, cur.dx, y);
+      if (y == cur.ymax && y < ymax_c) {
+        xx[j] = xx[j - 1];
+        j++;
+      } else if ((y == cur.ymin || y == cur.ymax) && cur.dx != 0) {
+        for (int k = 0; k < i; ++k) {
+          const ERec oth = E[k];
+          if (oth.ymin == oth.ymax) continue;
+          if ((y != oth.ymin && y != oth.ymax) || oth.dx == 0) continue;
+          if (roundf(xx[j - 1]) == roundf(edge_x(oth.x0, oth.y0, oth.dx, y))) {
+            int off = (y == ymax_c) ? -1 : 1;
+            if (y + off >= oth.ymin && y + off <= oth.ymax) {
+              float adj = edge_x(cur.x0, cur.y0, cur.dx, y + off);
+              float oadj = edge_x(oth.x0, oth.y0, oth.dx, y + off);
+              if (xx[j - 1] > adj + 1 && xx[j - 1] > oadj + 1)
+                xx[j - 1] = roundf(fmaxf(adj, oadj)) + 1;
+              else if (xx[j - 1] < adj - 1 && xx[j - 1] < oadj - 1)
+                xx[j - 1] = roundf(fminf(adj, oadj)) - 1;
+              break;
+            }
+          }
+        }
+      }
+    }
+  }
+  // qsort ascending
+  for (int a = 1; a < j; ++a) {
+    float v = xx[a];
+    int b = a;
+    while (b > 0 && xx[b - 1] > v) {
+      xx[b] = xx[b - 1];
+      --b;
+    }
+    xx[b] = v;
+  }
+  int x_pos = (j == 0) ? -1 : 0;
+  for (int i = 1; i < j; i += 2) {
+    int x_end = round_down_(xx[i]);
+    if (x_end < x_pos) continue;
+    if (has_horizontal) draw_horizontal_lines_rec(E, ne, y, &x_pos, sink);
+    if (x_end < x_pos) continue;
+    int x_start = round_up_(xx[i - 1]);
+    if (x_pos > x_start) {
+      x_start = x_pos;
+      if (x_end < x_start) continue;
+    }
+    if (x_start <= x_end) sink.hline(x_start, x_end);
+    x_pos = x_end + 1;
+  }
+  if (has_horizontal) draw_horizontal_lines_rec(E, ne, y, &x_pos, sink);
+}
+
 // color_maps.py:21-23 (CPython colorsys.hsv_to_rgb, x255, astype(uint8))
 __device__ __forceinline__ unsigned to_u8(double v) { return (unsigned)(unsigned char)(long long)v; }
 
@@ -211,7 +372,8 @@ __device__ inline unsigned color_to_ink(int cmap, double c0, double c1, double c
   return r8 | (g8 << 8) | (b8 << 16) | (to_u8(opacity) << 24);
 }
 
-struct RenderLayout { int canvas, ivtx, ink, ymin, ymax, horiz, total; };
+#define ITEM_CAP 768 /* (sprite, row) items whose spans are precomputed, per env */
+struct RenderLayout { int canvas, ivtx, erec, items, ink, ymin, ymax, horiz, nedge, ibase, total; };
 
 __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int VT) {
   RenderLayout L;
@@ -219,10 +381,14 @@ __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int V
   L.canvas = o; o += 4 * H * (W + 1);
   o = (o + 7) & ~7;
   L.ivtx = o;   o += 8 * VT;
+  L.erec = o;   o += 24 * VT;
+  L.items = o;  o += 4 * (1 + ITEM_SPANS) * ITEM_CAP;
   L.ink = o;    o += 4 * S;
   L.ymin = o;   o += 4 * S;
   L.ymax = o;   o += 4 * S;
   L.horiz = o;  o += 4 * S;
+  L.nedge = o;  o += 4 * S;
+  L.ibase = o;  o += 4 * (S + 1);
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -245,6 +411,9 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
   int2 *ivtx = (int2 *)(base + lay.ivtx);
   unsigned *ink = (unsigned *)(base + lay.ink);
   int *symin = (int *)(base + lay.ymin), *symax = (int *)(base + lay.ymax), *shoriz = (int *)(base + lay.horiz);
+  int *snedge = (int *)(base + lay.nedge), *sibase = (int *)(base + lay.ibase);
+  ERec *erec = (ERec *)(base + lay.erec);
+  unsigned *items = (unsigned *)(base + lay.items);
   const int stride = W + 1;
 
   if (live) {
@@ -281,12 +450,60 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
       for (int i = 0; i < nv; ++i) {
         lo = min(lo, xy[i].y);
         hi = max(hi, xy[i].y);
-        if (xy[i].y == xy[(i + 1 == nv) ? 0 : i + 1].y) hz = 1;
       }
+      snedge[s] = nv > 0 ? build_edge_list(xy, nv, erec + pv.voff[s], &hz) : 0;
       symin[s] = lo; symax[s] = hi; shoriz[s] = hz;
     }
   }
+  // z-order list of the live sprites and the (sprite, row) item ranges
+  if (live && t == 0) {
+    const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
+    const int32_t *cnt = a.st.cnt + (size_t)n * MOOG_MAX_LAYERS;
+    int acc = 0;
+    for (int s = 0; s < S; ++s) sibase[s] = -1;
+    for (int l = 0; l < L; ++l) {
+      int c = cnt[l];
+      for (int k = 0; k < c; ++k) {
+        int s = hdr[MOOG_H_LAYER_OFF + l] + k;
+        if (meta[MOOG_M_NV * S + s] <= 0) continue;
+        // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
+        int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
+        int rows = hi >= lo ? hi - lo + 1 : 0;
+        if (rows > 0 && acc + rows <= ITEM_CAP) {
+          sibase[s] = acc;
+          acc += rows;
+        }
+      }
+    }
+    sibase[S] = acc;
+  }
   __syncthreads();
+  // phase 1: one (sprite, row) item per thread pass -> clipped spans
+  if (live) {
+    const int n_items = sibase[S];
+    int s = 0;
+    for (int it = t; it < n_items; it += T) {
+      // items are sprite-major; find the sprite that owns item `it`
+      for (;;) {
+        int b0 = sibase[s];
+        if (b0 >= 0) {
+          int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
+          if (it < b0 + (hi - lo + 1)) break;
+        }
+        ++s;
+      }
+      const int lo = max(symin[s], 0);
+      const int y = lo + (it - sibase[s]);
+      SpanSink sink;
+      sink.item = items + (size_t)it * (1 + ITEM_SPANS);
+      sink.W = W;
+      sink.n = 0;
+      polygon_row_rec(erec + pv.voff[s], snedge[s], y, min(symax[s], H), shoriz[s] != 0, sink);
+      sink.item[0] = sink.n <= ITEM_SPANS ? (unsigned)sink.n : ITEM_OVERFLOW;
+    }
+  }
+  __syncthreads();
+  // phase 2: one row per thread, sprites in z-order
   if (live && t < H) {
     const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
     const int32_t *cnt = a.st.cnt + (size_t)n * MOOG_MAX_LAYERS;
@@ -296,12 +513,30 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
       int c = cnt[l];
       for (int k = 0; k < c; ++k) {
         int s = hdr[MOOG_H_LAYER_OFF + l] + k;
-        int nv = meta[MOOG_M_NV * S + s];
-        if (nv <= 0) continue;
-        // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H)
+        if (meta[MOOG_M_NV * S + s] <= 0) continue;
         int ymin_c = max(symin[s], 0), ymax_c = min(symax[s], H);
         if (y < ymin_c || y > ymax_c) continue;
-        polygon_row(ivtx + pv.voff[s], nv, y, ymax_c, shoriz[s] != 0, row, W, true, ink[s]);
+        const unsigned color = ink[s];
+        const int b0 = sibase[s];
+        unsigned cntw = ITEM_OVERFLOW;
+        const unsigned *item = nullptr;
+        if (b0 >= 0) {
+          item = items + (size_t)(b0 + (y - ymin_c)) * (1 + ITEM_SPANS);
+          cntw = item[0];
+        }
+        if (cntw != ITEM_OVERFLOW) {
+          for (unsigned q = 0; q < cntw; ++q) {
+            unsigned sp = item[1 + q];
+            int x0 = (int)(sp & 0xffffu), x1 = (int)(sp >> 16);
+            for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], color);
+          }
+        } else {
+          BlendSink sink;
+          sink.row = row;
+          sink.W = W;
+          sink.ink = color;
+          polygon_row_rec(erec + pv.voff[s], snedge[s], y, ymax_c, shoriz[s] != 0, sink);
+        }
       }
     }
   }
@@ -309,27 +544,28 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
   if (live) {
     // pil_renderer.py:118-120: np.flipud -> output row j is canvas row H-1-j
     unsigned char *out = a.frames + (size_t)n * H * W * 3;
-    const int nbytes = H * W * 3;
-    if ((nbytes & 15) == 0) {
+    if ((W & 15) == 0) {
+      // 16 pixels of one row -> 48 bytes = three 16-byte stores
       uint4 *out4 = (uint4 *)out;
-      for (int q = t; q < nbytes / 16; q += T) {
-        unsigned w[4];
+      const int groups = H * (W >> 4);
+      for (int q = t; q < groups; q += T) {
+        const int j = q / (W >> 4), c0 = (q - j * (W >> 4)) << 4;
+        const unsigned *src = canvas + (H - 1 - j) * stride + c0;
+        unsigned w[12];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          unsigned word = 0;
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            int b = q * 16 + u * 4 + bb;
-            int p = b / 3, ch = b - 3 * p;
-            int j = p / W, col = p - j * W;
-            unsigned px = canvas[(H - 1 - j) * stride + col];
-            word |= ((px >> (8 * ch)) & 255u) << (8 * bb);
-          }
-          w[u] = word;
+        for (int u = 0; u < 4; ++u) {  // 4 pixels (RGBX words) -> 3 packed words
+          const unsigned p0 = src[4 * u] & 0xffffffu, p1 = src[4 * u + 1] & 0xffffffu;
+          const unsigned p2 = src[4 * u + 2] & 0xffffffu, p3 = src[4 * u + 3] & 0xffffffu;
+          w[3 * u] = p0 | (p1 << 24);
+          w[3 * u + 1] = (p1 >> 8) | (p2 << 16);
+          w[3 * u + 2] = (p2 >> 16) | (p3 << 8);
         }
-        out4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        out4[3 * q] = make_uint4(w[0], w[1], w[2], w[3]);
+        out4[3 * q + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        out4[3 * q + 2] = make_uint4(w[8], w[9], w[10], w[11]);
       }
     } else {
+      const int nbytes = H * W * 3;
       for (int b = t; b < nbytes; b += T) {
         int p = b / 3, ch = b - 3 * p;
         int j = p / W, col = p - j * W;
