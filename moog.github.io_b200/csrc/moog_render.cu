@@ -243,7 +243,14 @@ struct BlendSink {
   unsigned *row;
   int W;
   unsigned ink;
-  __device__ __forceinline__ void hline(int x0, int x1) { moog::hline(row, W, x0, x1, ink); }
+  int xlo, xhi;  // the columns this thread owns
+  __device__ __forceinline__ void hline(int x0, int x1) {
+    if (x0 < 0) x0 = 0; else if (x0 >= W) return;   // hline32rgba's clipping
+    if (x1 < 0) return; else if (x1 >= W) x1 = W - 1;
+    x0 = max(x0, xlo);
+    x1 = min(x1, xhi);
+    for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], ink);
+  }
 };
 
 #define ITEM_SPANS 3          /* spans stored per item; more -> the item is redone directly */
@@ -261,9 +268,16 @@ struct SpanSink {
   }
 };
 
+#define MAX_HROW 8 /* horizontal edges of one polygon on one scanline kept in registers */
+
+// Draw.c draw_horizontal_lines for row y over the horizontal records of that row
+// (hrow[0..nh): indices into E, in list order; nh < 0: scan the whole list)
 template <class Sink>
-__device__ inline void draw_horizontal_lines_rec(const ERec *E, int ne, int y, int *x_pos, Sink &sink) {
-  for (int i = 0; i < ne; ++i) {
+__device__ inline void draw_horizontal_lines_rec(const ERec *E, int ne, const unsigned char *hrow, int nh, int y,
+                                                 int *x_pos, Sink &sink) {
+  const int n = nh >= 0 ? nh : ne;
+  for (int q = 0; q < n; ++q) {
+    const int i = nh >= 0 ? hrow[q] : q;
     const ERec e = E[i];
     if (e.ymin != e.ymax || e.ymin != y) continue;
     int xmin = e.x0;
@@ -283,10 +297,16 @@ __device__ inline void draw_horizontal_lines_rec(const ERec *E, int ne, int y, i
 template <class Sink>
 __device__ inline void polygon_row_rec(const ERec *E, int ne, int y, int ymax_c, bool has_horizontal, Sink &sink) {
   float xx[MAX_XX];
-  int j = 0;
+  unsigned char hrow[MAX_HROW];
+  int j = 0, nh = 0;
   for (int i = 0; i < ne; ++i) {
     const ERec cur = E[i];
-    if (cur.ymin == cur.ymax) continue;  // horizontal edges are deferred when blending
+    if (cur.ymin == cur.ymax) {  // horizontal edges are deferred when blending
+      if (cur.ymin == y) {
+        if (nh >= 0 && nh < MAX_HROW) hrow[nh++] = (unsigned char)i; else nh = -1;
+      }
+      continue;
+    }
     if (y >= cur.ymin && y <= cur.ymax) {
       xx[j++] = edge_x(cur.x0, cur.y0, cur.dx, y);
       if (y == cur.ymax && y < ymax_c) {
@@ -313,6 +333,7 @@ __device__ inline void polygon_row_rec(const ERec *E, int ne, int y, int ymax_c,
       }
     }
   }
+  has_horizontal = has_horizontal && nh != 0;
   // qsort ascending
   for (int a = 1; a < j; ++a) {
     float v = xx[a];
@@ -327,7 +348,7 @@ __device__ inline void polygon_row_rec(const ERec *E, int ne, int y, int ymax_c,
   for (int i = 1; i < j; i += 2) {
     int x_end = round_down_(xx[i]);
     if (x_end < x_pos) continue;
-    if (has_horizontal) draw_horizontal_lines_rec(E, ne, y, &x_pos, sink);
+    if (has_horizontal) draw_horizontal_lines_rec(E, ne, hrow, nh, y, &x_pos, sink);
     if (x_end < x_pos) continue;
     int x_start = round_up_(xx[i - 1]);
     if (x_pos > x_start) {
@@ -337,7 +358,7 @@ __device__ inline void polygon_row_rec(const ERec *E, int ne, int y, int ymax_c,
     if (x_start <= x_end) sink.hline(x_start, x_end);
     x_pos = x_end + 1;
   }
-  if (has_horizontal) draw_horizontal_lines_rec(E, ne, y, &x_pos, sink);
+  if (has_horizontal) draw_horizontal_lines_rec(E, ne, hrow, nh, y, &x_pos, sink);
 }
 
 // color_maps.py:21-23 (CPython colorsys.hsv_to_rgb, x255, astype(uint8))
@@ -372,7 +393,7 @@ __device__ inline unsigned color_to_ink(int cmap, double c0, double c1, double c
   return r8 | (g8 << 8) | (b8 << 16) | (to_u8(opacity) << 24);
 }
 
-#define ITEM_CAP 768 /* (sprite, row) items whose spans are precomputed, per env */
+#define ITEM_CAP 512 /* (sprite, row) items whose spans are precomputed, per env */
 struct RenderLayout { int canvas, ivtx, erec, items, ink, ymin, ymax, horiz, nedge, ibase, total; };
 
 __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int VT) {
@@ -380,9 +401,14 @@ __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int V
   int o = 0;
   L.canvas = o; o += 4 * H * (W + 1);
   o = (o + 7) & ~7;
-  L.ivtx = o;   o += 8 * VT;
   L.erec = o;   o += 24 * VT;
-  L.items = o;  o += 4 * (1 + ITEM_SPANS) * ITEM_CAP;
+  // the int vertices are dead once the edge lists exist: the item spans reuse their space
+  L.ivtx = o;
+  L.items = o;
+  {
+    int a = 8 * VT, b = 4 * (1 + ITEM_SPANS) * ITEM_CAP;
+    o += a > b ? a : b;
+  }
   L.ink = o;    o += 4 * S;
   L.ymin = o;   o += 4 * S;
   L.ymax = o;   o += 4 * S;
@@ -394,7 +420,7 @@ __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int V
 }
 
 // blockDim.x = envs_per_block * T, T = threads of one env (>= H, multiple of 32)
-__global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
+__global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ProgramView pv = view_of(a.blob);
   const int32_t *hdr = pv.hdr;
@@ -504,10 +530,11 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
   }
   __syncthreads();
   // phase 2: one row per thread, sprites in z-order
-  if (live && t < H) {
+  if (live && t < H * P) {
     const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
     const int32_t *cnt = a.st.cnt + (size_t)n * MOOG_MAX_LAYERS;
-    const int y = t;
+    const int part = t / H, y = t - part * H;
+    const int xlo = (W * part) / P, xhi = (W * (part + 1)) / P - 1;  // P threads share a row
     unsigned *row = canvas + y * stride;
     for (int l = 0; l < L; ++l) {
       int c = cnt[l];
@@ -527,14 +554,20 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
         if (cntw != ITEM_OVERFLOW) {
           for (unsigned q = 0; q < cntw; ++q) {
             unsigned sp = item[1 + q];
-            int x0 = (int)(sp & 0xffffu), x1 = (int)(sp >> 16);
-            for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], color);
+            int x0 = max((int)(sp & 0xffffu), xlo), x1 = min((int)(sp >> 16), xhi);
+            if ((color >> 24) == 255u) {  // DIV255(fg * 255) == fg: opaque ink overwrites
+              for (int x = x0; x <= x1; ++x) row[x] = color & 0xffffffu;
+            } else {
+              for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], color);
+            }
           }
         } else {
           BlendSink sink;
           sink.row = row;
           sink.W = W;
           sink.ink = color;
+          sink.xlo = xlo;
+          sink.xhi = xhi;
           polygon_row_rec(erec + pv.voff[s], snedge[s], y, ymax_c, shoriz[s] != 0, sink);
         }
       }
@@ -578,7 +611,8 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block) {
 cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
   if (a.n_envs <= 0) return cudaSuccess;
   int H = hdr[MOOG_H_R_HEIGHT], W = hdr[MOOG_H_R_WIDTH], S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
-  int T = (H + 31) & ~31;
+  const int P = (H <= 128) ? 2 : 1;  // threads per canvas row (they split its columns)
+  const int T = (H * P + 31) & ~31;
   RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1);
   int epb = 256 / T;
   if (epb < 1) epb = 1;
@@ -592,7 +626,7 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
     configured = smem;
   }
   int blocks = (a.n_envs + epb - 1) / epb;
-  moog_render_kernel<<<blocks, epb * T, smem, stream>>>(a, T, epb);
+  moog_render_kernel<<<blocks, epb * T, smem, stream>>>(a, T, epb, P);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
