@@ -348,10 +348,59 @@ class _StateLowering(object):
                 layer = self._layer_of(node.args[0])
                 ls, ln = prog.add_list([layer])
                 return ('op', prog.emit(SC_COUNT, 0, (ls, ln, -1)))
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name):
+            known = self._known_helper(node)
+            if known is not None:
+                return known
         if isinstance(node, ast.Constant) and isinstance(
                 node.value, (bool, int, float)):
             return ('const', float(node.value))
         self.fail(node)
+
+    # -- helpers of shipped configs that cannot be traced (data-dependent
+    #    Python control flow) and have a declarative device equivalent ---------
+    _AGENTS_CONTACTING_LAYER = (
+        "def agents_contacting_layer(state, layer, value):\n"
+        "    n_contact = 0\n"
+        "    for s in state[layer]:\n"
+        "        if s.c2 != value:\n"
+        "            continue\n"
+        "        n_contact += s.overlaps_sprite(state['agent_0'][0]) or "
+        "s.overlaps_sprite(state['agent_1'][0]) or "
+        "s.overlaps_sprite(state['agent_2'][0])\n"
+        "    return n_contact")
+
+    def _known_helper(self, node):
+        """`agents_contacting_layer(state, layer, value)` of cleanup.py:183-193:
+        the number of `layer` sprites with c2 == value that overlap any agent
+        (Python `or`: the agents are tried in order until one overlaps) ->
+        MOOG_SC_CONTACT_ANY_COUNT.  The helper's source must match verbatim
+        (modulo formatting), otherwise the condition is rejected."""
+        fn = self.ns.get(node.func.id)
+        if fn is None or getattr(fn, '__name__', '') != 'agents_contacting_layer':
+            return None
+        try:
+            src = textwrap.dedent(inspect.getsource(fn))
+            got = ast.dump(ast.parse(src).body[0])
+            want = ast.dump(ast.parse(self._AGENTS_CONTACTING_LAYER).body[0])
+        except (OSError, TypeError, SyntaxError):
+            return None
+        if got != want or len(node.args) != 3:
+            return None
+        if not (isinstance(node.args[0], ast.Name) and node.args[0].id == self.state_name):
+            return None
+        try:
+            layer, value = [eval(compile(ast.Expression(a), '<cond>', 'eval'), self.ns)  # pylint: disable=eval-used
+                            for a in node.args[1:]]
+        except Exception:  # pylint: disable=broad-except
+            return None
+        SC_CONTACT_ANY_COUNT = 164
+        prog = self.prog
+        ls, ln = prog.add_list([layer])
+        as_, an = prog.add_list(['agent_0', 'agent_1', 'agent_2'])
+        filt = (SymSprite(0).c2 == float(value))
+        return ('op', prog.emit(SC_CONTACT_ANY_COUNT, 0,
+                                (ls, ln, as_, an, prog.add_expr(Sym.lift(filt).code))))
 
 
 def compile_state_condition(cond, prog):

@@ -62,7 +62,37 @@ SCENES = {
     # reference's argmax picks the NaN entry (collisions.py:207-209) and the sprite's
     # position becomes NaN for the rest of the episode
     'falling_balls20_nan': ('moog_b200.configs.falling_balls20', None, 297, 8, 2),
+    # contact-triggered rules (ConditionalRule x ModifySprites(sample_one), ModifyOnContact),
+    # ContactReward with a pair condition, Composite of 3 Joysticks; the agents are
+    # steered towards fruits / fountains so that the rules actually fire
+    'cleanup': ('moog_demos.example_configs.cleanup', None, 6, 150, 25),
 }
+
+
+def _sample_one_rules(rules):
+    """ModifySprites(sample_one=True) rules in the compiler's traversal order
+    (= the order of their rule-noise columns)."""
+    out = []
+    for r in rules:
+        if type(r).__name__ == 'ConditionalRule':
+            out += _sample_one_rules(r._rules)  # pylint: disable=protected-access
+        elif type(r).__name__ == 'ModifySprites' and r._sample_one:  # pylint: disable=protected-access
+            out.append(r)
+    return out
+
+
+def _seek_action(env, t):
+    """cleanup: every agent heads for the nearest fruit (even steps of 40) or
+    fountain, full stick."""
+    act = {}
+    for k, name in enumerate(('agent_0', 'agent_1', 'agent_2')):
+        a = env.state[name][0]
+        targets = env.state['fruits'] if ((t // 40) + k) % 2 == 0 else env.state['fountains']
+        d = [np.array(s.position) - np.array(a.position) for s in targets]
+        d = min(d, key=lambda v: float(np.dot(v, v)))
+        n = float(np.linalg.norm(d))
+        act[name] = d / n if n > 0 else np.zeros(2)   # float64, like random_action()
+    return act
 
 
 def _slot_map(prog, state):
@@ -110,24 +140,52 @@ def generate(name, out_dir):
         draws.append(u)
         return low + (high - low) * u
 
+    # the uniform behind ModifySprites(sample_one)'s np.random.choice
+    # (modify_sprites.py:48-49): element int(u * len) of the filtered list
+    so_rules = _sample_one_rules(config.get('game_rules', ()))
+    rule_draws = {}
+    current_rule = [None]
+    orig_choice = np.random.choice
+
+    def _choice(seq, *args, **kwargs):
+        if current_rule[0] is None or args or kwargs:
+            return orig_choice(seq, *args, **kwargs)
+        u = np.random.random_sample()
+        col = so_rules.index(current_rule[0])
+        assert col not in rule_draws, 'a sample_one rule fired twice in one step'
+        rule_draws[col] = u
+        return seq[min(int(u * len(seq)), len(seq) - 1)]
+
+    for r in so_rules:
+        def _wrapped(state, meta_state, _r=r, _orig=r.step):
+            current_rule[0] = _r
+            try:
+                return _orig(state, meta_state)
+            finally:
+                current_rule[0] = None
+        r.step = _wrapped
+
     rec = {k: [] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt', 'reward', 'last',
-                           'actions', 'noise', 'n_calls', 'n_true', 'true_hash')}
+                           'actions', 'noise', 'rule_noise', 'n_calls', 'n_true', 'true_hash')}
     frames, frame_steps = [], []
     if renderer is not None:
         frames.append(np.asarray(ts.observation['image']))
         frame_steps.append(-1)
     K, nd = prog.K, prog.noise_dim
     for t in range(T):
-        action = env.action_space.random_action()
+        action = _seek_action(env, t) if name == 'cleanup' else env.action_space.random_action()
         flat = _flat_action(prog, action)
         slots = _slot_map(prog, env.state)
         del draws[:]
+        rule_draws.clear()
         np.random.uniform = _uniform
+        np.random.choice = _choice
         try:
             with refenv.OverlapLog() as log:
                 ts = env.step(action)
         finally:
             np.random.uniform = orig_uniform
+            np.random.choice = orig_choice
         h, n_true = 0, 0
         for a, b, r in log.calls:
             if r:
@@ -146,6 +204,10 @@ def generate(name, out_dir):
         rec['last'].append(bool(ts.last()))
         rec['actions'].append(flat)
         rec['noise'].append(noise)
+        rn = np.zeros(max(prog.rule_noise_dim, 1))
+        for col, u in rule_draws.items():
+            rn[col] = u
+        rec['rule_noise'].append(rn)
         rec['n_calls'].append(len(log.calls))
         rec['n_true'].append(n_true)
         rec['true_hash'].append(np.uint64(h))

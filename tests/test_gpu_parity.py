@@ -68,7 +68,8 @@ def test_cuda_follows_reference_trajectory(scene):
     T = len(g['reward'])
     for t in range(T):
         noise = g['noise'][t][None] if prog.noise_dim else None
-        eng.env_step(g['actions'][t][None], noise=noise, auto_reset=False, want_counters=True)
+        eng.env_step(g['actions'][t][None], noise=noise, rule_noise=util.rule_noise_at(g, t), auto_reset=False,
+                     want_counters=True)
         dev = eng.state.download()
         assert np.array_equal(dev['cnt'][0], g['cnt'][t]), (scene, t)
         ref = {k: g[k][t][None] for k in ('dyn', 'stat', 'vtx', 'meta')}
@@ -109,12 +110,13 @@ def test_cuda_matches_oracle_batched(scene):
         else:
             actions = rng.uniform(-1, 1, size=(n, ad))
         noise = rng.uniform(size=(n, prog.K, prog.noise_dim)) if prog.noise_dim else None
+        rule_noise = rng.uniform(size=(n, prog.rule_noise_dim)) if prog.rule_noise_dim else None
         if not exact:
             st = orc.arrays()
             st = {k: v.copy() for k, v in st.items()}
             eng.state.upload(st)
-        r_ref, st_ref = orc.step(actions, noise=noise)
-        eng.env_step(actions, noise=noise, auto_reset=False, want_counters=True)
+        r_ref, st_ref = orc.step(actions, noise=noise, rule_noise=rule_noise)
+        eng.env_step(actions, noise=noise, rule_noise=rule_noise, auto_reset=False, want_counters=True)
         dev = eng.state.download()
         assert np.array_equal(dev['cnt'], orc.cnt), (scene, step)
         _compare_state(scene, step, prog, dev, orc.arrays(), orc.cnt, exact)

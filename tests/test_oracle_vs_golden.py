@@ -26,7 +26,7 @@ def test_oracle_follows_reference_trajectory(scene):
     worst = 0.0
     for t in range(T):
         noise = g['noise'][t][None] if prog.noise_dim else None
-        reward, step_type = orc.step(g['actions'][t][None], noise=noise)
+        reward, step_type = orc.step(g['actions'][t][None], noise=noise, rule_noise=util.rule_noise_at(g, t))
         assert np.array_equal(orc.cnt[0], g['cnt'][t]), (scene, t)
         live = util.live_mask(prog, g['cnt'][t])
         for k in ('dyn', 'stat'):

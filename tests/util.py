@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 SCENES = ['pong', 'falling_balls', 'falling_balls20', 'colliding_predators',
-          'predators_arena', 'synthetic32', 'falling_balls20_nan']
+          'predators_arena', 'synthetic32', 'falling_balls20_nan', 'cleanup']
 # scenes whose step() uses no sin/cos of a non-zero angle: every operation on
 # the path is IEEE-exact (+ - * / sqrt fma), so the CUDA path must be bit-exact
 EXACT_SCENES = ['pong', 'falling_balls', 'falling_balls20', 'falling_balls20_nan']
@@ -52,6 +52,14 @@ def load_golden(name):
     g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
     g['program'] = ProgramStub(g['blob'], g['layer_names'])
     return g
+
+
+def rule_noise_at(g, t):
+    """[1, rule_noise_dim] uniforms behind ModifySprites(sample_one) at step t, or None."""
+    prog = g['program']
+    if not prog.rule_noise_dim or 'rule_noise' not in g:
+        return None
+    return np.asarray(g['rule_noise'][t], dtype=np.float64)[None, :prog.rule_noise_dim]
 
 
 def state_at(g, t, prefix=None):
