@@ -181,3 +181,46 @@ def check_state(case, prog, dyn, step, name=''):
         assert np.allclose(got_vel, vel, atol=ATOL), (name, step, idx, 'velocity', got_vel, vel)
         if w is not None:
             assert np.allclose(got_w, w, atol=ATOL), (name, step, idx, 'angle_vel', got_w, w)
+
+
+# ---------------------------------------------------------------------------
+# rarely-hit Collision branches: values recorded from the reference itself
+# (oracle/gen_kat_extra.py -> tests/golden/kat_rare_branches.json)
+# ---------------------------------------------------------------------------
+RARE_ATOL = 1e-12
+
+
+def rare_branch_cases():
+    import json
+    import os
+    _, _, physics_lib, _, sprite, _ = _libs()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kat_rare_branches.json')
+    with open(path) as f:
+        data = json.load(f)
+    out = []
+    for name in sorted(data):
+        case = data[name]
+
+        def _sprite(kw):
+            kw = dict(kw)
+            if not isinstance(kw['shape'], str):
+                kw['shape'] = np.array(kw['shape'])
+            return sprite.Sprite(**kw)
+
+        s0, s1 = _sprite(case['s0']), _sprite(case['s1'])
+        force = physics_lib.Collision(**case['collision'])
+        state = collections.OrderedDict([('a', [s0]), ('b', [s1])])
+        physics = physics_lib.Physics((force, 'a', 'b'), updates_per_env_step=1)
+        config, layers = _config(physics, state)
+        out.append((name, dict(config=config, layers=layers, steps=1,
+                               where={0: ('a', 0), 1: ('b', 0)}, expected=case['expected'])))
+    return out
+
+
+def check_rare(case, prog, dyn, name=''):
+    exp = case['expected']
+    for idx, (pk, vk) in enumerate((('pos0', 'vel0'), ('pos1', 'vel1'))):
+        layer, k = case['where'][idx]
+        s = prog.layer_off[prog.layer_index(layer)] + k
+        assert np.allclose(dyn[0:2, s], exp[pk], rtol=0, atol=RARE_ATOL), (name, idx, 'position', dyn[0:2, s], exp[pk])
+        assert np.allclose(dyn[2:4, s], exp[vk], rtol=0, atol=RARE_ATOL), (name, idx, 'velocity', dyn[2:4, s], exp[vk])

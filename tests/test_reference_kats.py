@@ -32,6 +32,36 @@ def test_oracle_reproduces_reference_kat(name):
             kat.check_state(case, prog, orc.dyn[0], step, name)
 
 
+def test_oracle_reproduces_rare_collision_branches():
+    """_make_disjoint / _position_correction (crossed bars) and the un-negated
+    perpendicular (App. A, C7): values recorded from the reference."""
+    from oracle.oracle import Oracle
+    for name, case in kat.rare_branch_cases():
+        prog, arrays = kat.compile_case(case)
+        orc = Oracle(prog, arrays)
+        orc.post_reset()
+        orc.step(None)
+        kat.check_rare(case, prog, orc.dyn[0], name)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_rare_collision_branches():
+    from moog_b200.batched_env import Engine
+    from oracle.oracle import Oracle
+    for name, case in kat.rare_branch_cases():
+        prog, arrays = kat.compile_case(case)
+        eng = Engine(prog, 1, 'cuda:0')
+        eng.state.upload(arrays)
+        eng.post_reset()
+        eng.env_step(None, auto_reset=False, want_counters=True)
+        dev = eng.state.download()
+        kat.check_rare(case, prog, dev['dyn'][0], name)
+        orc = Oracle(prog, arrays)
+        orc.post_reset()
+        orc.step(None)
+        assert np.array_equal(eng.counters.cpu().numpy()[0, :4], orc.counters[0]), name
+
+
 @pytest.mark.gpu
 def test_cuda_reproduces_reference_kats():
     """All KAT cases at once, one engine per case; the CUDA state must satisfy the
