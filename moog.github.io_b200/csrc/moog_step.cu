@@ -662,30 +662,31 @@ struct CVec {
 
 // collisions.py:62-98 _relative_motion_trajectory (matrix only)
 __device__ inline Aff rel_motion_matrix(const Env &e, int ps, int as, double dt) {
+  const double th1 = scaled_angvel(e, ps, -1.0, dt);
+  const double tx2 = scaled_vel(e, ps, MOOG_D_VX, -1.0, dt), ty2 = scaled_vel(e, ps, MOOG_D_VY, -1.0, dt);
+  const double th3 = angvel_kind(e, as) == KIND_F32 ? f32mul(DYN(e, MOOG_D_ANGVEL, as), dt)
+                                                    : DYN(e, MOOG_D_ANGVEL, as) * dt;
+  const double tx4 = vel32(e, as) ? f32mul(DYN(e, MOOG_D_VX, as), dt) : DYN(e, MOOG_D_VX, as) * dt;
+  const double ty4 = vel32(e, as) ? f32mul(DYN(e, MOOG_D_VY, as), dt) : DYN(e, MOOG_D_VY, as) * dt;
+  const double x1 = DYN(e, MOOG_D_X, ps), y1 = DYN(e, MOOG_D_Y, ps);
+  const double x3 = DYN(e, MOOG_D_X, as), y3 = DYN(e, MOOG_D_Y, as);
+  if (th1 == 0.0 && th3 == 0.0 && isfinite(x1) && isfinite(y1) && isfinite(x3) && isfinite(y3) && isfinite(tx2) &&
+      isfinite(ty2) && isfinite(tx4) && isfinite(ty4)) {
+    // Neither sprite rotates: rotate_around(x, y, +-0) is exactly the identity for finite
+    // (x, y), and the general product below collapses to one rounded sum per
+    // translation component (the + 0.0 is the product's -0 -> +0 normalisation).
+    Aff m = {1., 0., tx4 + (tx2 + 0.0), 0., 1., ty4 + (ty2 + 0.0)};
+    return m;
+  }
   Aff m1 = aff_identity(), m2 = aff_identity(), m3 = aff_identity(), m4 = aff_identity();
-  aff_rotate_around(m1, DYN(e, MOOG_D_X, ps), DYN(e, MOOG_D_Y, ps), scaled_angvel(e, ps, -1.0, dt));
-  aff_translate(m2, scaled_vel(e, ps, MOOG_D_VX, -1.0, dt), scaled_vel(e, ps, MOOG_D_VY, -1.0, dt));
-  aff_rotate_around(m3, DYN(e, MOOG_D_X, as), DYN(e, MOOG_D_Y, as),
-                    angvel_kind(e, as) == KIND_F32 ? f32mul(DYN(e, MOOG_D_ANGVEL, as), dt)
-                                                   : DYN(e, MOOG_D_ANGVEL, as) * dt);
-  aff_translate(m4, vel32(e, as) ? f32mul(DYN(e, MOOG_D_VX, as), dt) : DYN(e, MOOG_D_VX, as) * dt,
-                vel32(e, as) ? f32mul(DYN(e, MOOG_D_VY, as), dt) : DYN(e, MOOG_D_VY, as) * dt);
+  aff_rotate_around(m1, x1, y1, th1);
+  aff_translate(m2, tx2, ty2);
+  aff_rotate_around(m3, x3, y3, th3);
+  aff_translate(m4, tx4, ty4);
   Aff t12 = aff_then(m1, m2);
   Aff t123 = aff_then(t12, m3);
   return aff_then(t123, m4);
 }
-
-// np.argmin order: a NaN beats everything, then the smaller value, then the smaller index
-__device__ __forceinline__ bool argmin_better(double v2, int i2, double v1, int i1) {
-  bool n1 = isnan(v1), n2 = isnan(v2);
-  if (n1 || n2) return (n1 && n2) ? (i2 < i1) : n2;
-  if (v2 < v1) return true;
-  if (v2 > v1) return false;
-  return i2 < i1;
-}
-
-// collisions.py:101-232 _directed_collision_vectors(sprite_0=s0, sprite_1=s1):
-// vertices of s0 that lie inside s1, traced back along the relative motion.
 __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, int s0, int s1, double dt, CVec &o) {
   o.has_point = o.future = o.has_since = 0;
   o.px = o.py = o.nx = o.ny = o.sx = o.sy = o.qx = o.qy = 0.0;
@@ -706,15 +707,19 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
 
   Aff M = rel_motion_matrix(e, s0, s1, dt);
 
-  // lane = edge j of s1
-  bool eact = e.lane < n1;
-  double2 q1 = P1[eact ? e.lane : 0];
-  double2 q2 = P1[eact ? ((e.lane + 1 == n1) ? 0 : e.lane + 1) : 0];
+  // Lanes are tiled as (vertices per pass) x (edges of s1): an outline with few
+  // edges -- a wall -- takes several contained vertices per pass.
+  const int E = n1 <= 4 ? 4 : (n1 <= 8 ? 8 : (n1 <= 16 ? 16 : 32));
+  const int V = 32 / E;
+  const int ej = e.lane & (E - 1), tl = e.lane / E;
+  bool eact = ej < n1;
+  double2 q1 = P1[eact ? ej : 0];
+  double2 q2 = P1[eact ? ((ej + 1 == n1) ? 0 : ej + 1) : 0];
   double d1x = q2.x - q1.x, d1y = q2.y - q1.y;
 
-  // Stage A (lane = edge of s1, one contained vertex after the other, no
-  // cross-lane traffic so consecutive vertices overlap in the pipeline): the
-  // argmin key of every (vertex, edge) goes to a shared-memory tile.
+  // Stage A (lane = (vertex, edge of s1); no cross-lane traffic, so consecutive
+  // passes overlap in the pipeline): the argmin key of every (vertex, edge) goes
+  // to a shared-memory tile.
   // Stage B (lane = vertex): each lane scans its row of the tile for np.argmin
   // (first index on ties), recomputes the winning edge's coefficient -- the same
   // IEEE operations, hence the same bits -- and the penetration length.
@@ -724,24 +729,30 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
   double b_dist = 0, b_cpx = 0, b_cpy = 0, b_dfx = 0, b_dfy = 0, b_a = 0;
   int b_edge = 0;
   unsigned long long *keys = e.kscr;
-  while (mask) {
-    int cnt = 0;
+  // contained vertex indices, ascending, in the scratch bytes
+  const int n_in = __popc(mask);
+  wsync();
+  if ((mask >> e.lane) & 1u) e.scratch[__popc(mask & ((1u << e.lane) - 1u))] = (unsigned char)e.lane;
+  wsync();
+  for (int vbase = 0; vbase < n_in; vbase += DCV_TILE) {
+    const int cnt = min(DCV_TILE, n_in - vbase);
 #pragma unroll 2
-    for (; cnt < DCV_TILE && mask; ++cnt) {
-      const int c = __ffs(mask) - 1;
-      mask &= mask - 1;
+    for (int t0 = 0; t0 < cnt; t0 += V) {
+      const int t = t0 + tl;
+      const bool valid = t < cnt;
+      const int c = e.scratch[vbase + (valid ? t : cnt - 1)];
       const double2 ev = P0[c];  // traj[:,1]
       const double ex = ev.x, ey = ev.y;
       const double sx = M.m0 * ex + M.m1 * ey + M.m2;  // traj[:,0]
       const double sy = M.m3 * ex + M.m4 * ey + M.m5;
       const double d0x = ex - sx, d0y = ey - sy;
-      // sprite.py:145-161 segment_crossing_coefficients against edge `lane`
+      // sprite.py:145-161 segment_crossing_coefficients against edge `ej`
       const double den = (d0x * d1y - d0y * d1x) + EPS_INTERP;
       const double qx = q1.x - sx, qy = q1.y - sy;
-      // (lanes past the last edge skip the divisions: their zero numerators would
-      // send the whole warp through the fp64 division slow path)
+      // (idle lanes skip the divisions: their zero numerators would send the whole
+      // warp through the fp64 division slow path)
       double A = -INFINITY;
-      if (eact) {
+      if (eact && valid) {
         const double Bc = (qx * d0y - qy * d0x) / den;
         if ((Bc >= 0) && (Bc <= 1)) {
           my_cross = true;
@@ -752,9 +763,7 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
       // np.argmin order: a NaN beats everything, then the smaller value (ab >= 0, so
       // its bit pattern orders like the value), then the smaller index
       unsigned long long key = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
-      if (!eact) key = ~0ull;
-      keys[cnt * 32 + e.lane] = key;
-      if (e.lane == 0) e.scratch[cnt] = (unsigned char)c;
+      if (eact && valid) keys[t * 32 + ej] = key;
     }
     wsync();
     // stage B
@@ -772,7 +781,7 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
           idx = j;
         }
       }
-      const double2 ev = P0[e.scratch[e.lane]];
+      const double2 ev = P0[e.scratch[vbase + e.lane]];
       const double ex = ev.x, ey = ev.y;
       const double sx = M.m0 * ex + M.m1 * ey + M.m2;
       const double sy = M.m3 * ex + M.m4 * ey + M.m5;
