@@ -24,7 +24,8 @@ NVCC_FLAGS = [
     '-std=c++17', '-fmad=false', '-prec-div=true', '-prec-sqrt=true',
     '--expt-extended-lambda', '-Xcompiler', '-fPIC,-ffp-contract=off',
     '-Wno-deprecated-gpu-targets',
-] + (['-DMOOG_PROFILE_PHASES'] if os.environ.get('MOOG_PROFILE_PHASES') else [])
+] + (['-DMOOG_PROFILE_PHASES'] if os.environ.get('MOOG_PROFILE_PHASES') else []) + (
+    ['-DMOOG_PROFILE_DCV'] if os.environ.get('MOOG_PROFILE_DCV') else [])
 
 
 def _nvcc():

@@ -176,7 +176,7 @@ __device__ __forceinline__ Env env_view() {
   return e;
 }
 
-#ifdef MOOG_PROFILE_PHASES
+#if defined(MOOG_PROFILE_PHASES) || defined(MOOG_PROFILE_DCV)
 #define PROF_RESOLVE(e, t1)
 #else
 #define PROF_RESOLVE(e, t1) ctr_add(e, CT_CYC_RESOLVE, clock64() - (t1))
@@ -690,6 +690,9 @@ __device__ inline Aff rel_motion_matrix(const Env &e, int ps, int as, double dt)
 __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, int s0, int s1, double dt, CVec &o) {
   o.has_point = o.future = o.has_since = 0;
   o.px = o.py = o.nx = o.ny = o.sx = o.sy = o.qx = o.qy = 0.0;
+#ifdef MOOG_PROFILE_DCV
+  long long tp0 = clock64();
+#endif
   const double2 *P0 = e.vtx + e.voff[s0];
   const double2 *P1 = e.vtx + e.voff[s1];
   int n0 = META(e, MOOG_M_NV, s0), n1 = META(e, MOOG_M_NV, s1);
@@ -734,38 +737,55 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
   wsync();
   if ((mask >> e.lane) & 1u) e.scratch[__popc(mask & ((1u << e.lane) - 1u))] = (unsigned char)e.lane;
   wsync();
+#ifdef MOOG_PROFILE_DCV
+  ctr_add(e, CT_NARROW, clock64() - tp0);
+  ctr_add(e, CT_COLL, n_in);
+#endif
   for (int vbase = 0; vbase < n_in; vbase += DCV_TILE) {
     const int cnt = min(DCV_TILE, n_in - vbase);
-#pragma unroll 2
-    for (int t0 = 0; t0 < cnt; t0 += V) {
-      const int t = t0 + tl;
-      const bool valid = t < cnt;
-      const int c = e.scratch[vbase + (valid ? t : cnt - 1)];
-      const double2 ev = P0[c];  // traj[:,1]
-      const double ex = ev.x, ey = ev.y;
-      const double sx = M.m0 * ex + M.m1 * ey + M.m2;  // traj[:,0]
-      const double sy = M.m3 * ex + M.m4 * ey + M.m5;
-      const double d0x = ex - sx, d0y = ey - sy;
-      // sprite.py:145-161 segment_crossing_coefficients against edge `ej`
-      const double den = (d0x * d1y - d0y * d1x) + EPS_INTERP;
-      const double qx = q1.x - sx, qy = q1.y - sy;
-      // (idle lanes skip the divisions: their zero numerators would send the whole
-      // warp through the fp64 division slow path)
-      double A = -INFINITY;
-      if (eact && valid) {
-        const double Bc = (qx * d0y - qy * d0x) / den;
-        if ((Bc >= 0) && (Bc <= 1)) {
-          my_cross = true;
-          A = (qx * d1y - qy * d1x) / den;
-        }
+#ifdef MOOG_PROFILE_DCV
+    long long tp1 = clock64();
+#endif
+    // two passes per iteration, branch-free (idle lanes divide 1 by 1: a zero
+    // numerator would send the whole warp through the fp64 division slow path), so
+    // that the four divisions of an iteration are in flight together
+    for (int t0 = 0; t0 < cnt; t0 += 2 * V) {
+      unsigned long long key2[2];
+      bool ok2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + u * V + tl;
+        const bool valid = t < cnt;
+        const bool on = eact && valid;
+        const int c = e.scratch[vbase + (valid ? t : cnt - 1)];
+        const double2 ev = P0[c];  // traj[:,1]
+        const double ex = ev.x, ey = ev.y;
+        const double sx = M.m0 * ex + M.m1 * ey + M.m2;  // traj[:,0]
+        const double sy = M.m3 * ex + M.m4 * ey + M.m5;
+        const double d0x = ex - sx, d0y = ey - sy;
+        // sprite.py:145-161 segment_crossing_coefficients against edge `ej`
+        const double den = on ? (d0x * d1y - d0y * d1x) + EPS_INTERP : 1.0;
+        const double qx = q1.x - sx, qy = q1.y - sy;
+        const double Bc = (on ? (qx * d0y - qy * d0x) : 1.0) / den;
+        double A = (on ? (qx * d1y - qy * d1x) : 1.0) / den;
+        const bool crossing = on && (Bc >= 0) && (Bc <= 1);
+        my_cross |= crossing;
+        if (!crossing) A = -INFINITY;
+        const double ab = fabs(1.0 - A);
+        // np.argmin order: a NaN beats everything, then the smaller value (ab >= 0, so
+        // its bit pattern orders like the value), then the smaller index
+        key2[u] = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
+        ok2[u] = on;
       }
-      const double ab = fabs(1.0 - A);
-      // np.argmin order: a NaN beats everything, then the smaller value (ab >= 0, so
-      // its bit pattern orders like the value), then the smaller index
-      unsigned long long key = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
-      if (eact && valid) keys[t * 32 + ej] = key;
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (ok2[u]) keys[(t0 + u * V + tl) * 32 + ej] = key2[u];
     }
     wsync();
+#ifdef MOOG_PROFILE_DCV
+    long long tp2 = clock64();
+    ctr_add(e, CT_CYC_NARROW, tp2 - tp1);
+#endif
     // stage B
     const bool vact = e.lane < cnt;
     int idx = 0;
@@ -817,6 +837,9 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
       b_edge = __shfl_sync(FULL, idx, wl);
     }
     wsync();
+#ifdef MOOG_PROFILE_DCV
+    ctr_add(e, CT_CYC_RESOLVE, clock64() - tp2);
+#endif
   }
   const bool any_cross = __any_sync(FULL, my_cross) != 0;
   if (!any_cross) return;  // collisions.py:177-179
@@ -1077,7 +1100,7 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
     } else {
       ov = overlaps(e, s0, s1);
     }
-#ifndef MOOG_PROFILE_PHASES
+#if !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV)
     ctr_add(e, CT_NARROW, 1);
     ctr_add(e, CT_CYC_NARROW, clock64() - t0);
 #endif
@@ -1221,7 +1244,10 @@ __device__ inline void refresh_candidates(const Env &e, int n_cmask_words) {
   wsync();
   // has any box drifted too far since the near list was built?  (NaN -> yes)
   bool bad = false;
-  for (int i = e.lane; i < 4 * e.S; i += 32) bad |= !(fabs(e.aabb[i] - e.aabb0[i]) < 0.5 * NEAR_SKIN);
+  for (int i = e.lane; i < 4 * e.S; i += 32) {
+    const double b1 = e.aabb[i], b0 = e.aabb0[i];  // (+-inf == +-inf: the all-covering box of a NaN sprite)
+    bad |= !(fabs(b1 - b0) < 0.5 * NEAR_SKIN) && !(b1 == b0);
+  }
   if (__any_sync(FULL, bad) || e.ctr[CT_NEAR] == -2) rebuild_near(e);
   const int n_near = (int)e.ctr[CT_NEAR];
   if (n_near < 0) {
