@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "moog_common.cuh"
 
@@ -17,6 +18,9 @@ struct moog_program {
   int *sched;  // [2][sched_cap]: cost, order
   int sched_cap;
   const void *sched_state;  // the state the costs belong to
+  // anti_aliasing > 1: Lanczos coefficient tables (Resample.c), built on first use
+  int *resample;
+  int ksize_h, ksize_v;
 };
 
 namespace {
@@ -74,6 +78,7 @@ void moog_program_destroy(moog_program *p) {
   if (!p) return;
   if (p->dev_blob) cudaFree(p->dev_blob);
   if (p->sched) cudaFree(p->sched);
+  if (p->resample) cudaFree(p->resample);
   free(p);
 }
 
@@ -157,12 +162,27 @@ int moog_overlap_pairs(moog_program *p, const moog_state *st, int n_envs, int la
 int moog_render(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream) {
   if (!p || !valid_state(st) || !frames || n_envs < 0) return MOOG_E_INVAL;
   if (!p->hdr[MOOG_H_R_ENABLED]) return MOOG_E_INVAL;
-  if (p->hdr[MOOG_H_R_AA] != 1 || p->hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS) return MOOG_E_UNSUPPORTED;
+  if (p->hdr[MOOG_H_R_AA] < 1 || p->hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS) return MOOG_E_UNSUPPORTED;
   moog::RenderArgs a;
+  memset(&a, 0, sizeof(a));
   a.blob = p->dev_blob;
   a.st = *st;
   a.n_envs = n_envs;
   a.frames = frames;
+  if (p->hdr[MOOG_H_R_AA] > 1) {
+    if (!p->resample) {
+      const int OH = p->hdr[MOOG_H_R_HEIGHT], OW = p->hdr[MOOG_H_R_WIDTH], aa = p->hdr[MOOG_H_R_AA];
+      std::vector<int> table;
+      int n = moog::resample_tables(aa * OH, aa * OW, OH, OW, table, &p->ksize_h, &p->ksize_v);
+      cudaError_t err = cudaMalloc((void **)&p->resample, sizeof(int) * (size_t)n);
+      if (err == cudaSuccess)
+        err = cudaMemcpy(p->resample, table.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice);
+      if (err != cudaSuccess) return cuda_fail(err);
+    }
+    a.resample = p->resample;
+    a.ksize_h = p->ksize_h;
+    a.ksize_v = p->ksize_v;
+  }
   int launches = 0;
   cudaError_t err = moog::launch_render(a, p->hdr, (cudaStream_t)stream, &launches);
   g_launches += launches;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/moog_b200.h"
 
 namespace moog {
@@ -49,6 +51,8 @@ struct RenderArgs {
   moog_state st;
   int n_envs;
   uint8_t *frames;
+  const int *resample;  // anti_aliasing > 1: device copy of resample_tables()
+  int ksize_h, ksize_v;
 };
 
 // host-side launchers (defined in the .cu files)
@@ -57,6 +61,7 @@ int env_smem_bytes(const int32_t *hdr);
 int candidate_matrix_words(const void *host_blob);
 cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
 cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream, int *n_launches);
+int resample_tables(int H, int W, int OH, int OW, std::vector<int> &table, int *ksize_h, int *ksize_v);
 cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
 
 }  // namespace moog

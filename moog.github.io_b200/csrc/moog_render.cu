@@ -13,6 +13,8 @@
 // flipped, as coalesced 16-byte stores.
 #include <math.h>
 
+#include <vector>
+
 #include "moog_common.cuh"
 
 namespace moog {
@@ -24,6 +26,12 @@ namespace moog {
 // out-of-range values give INT_MIN (CUDA's conversion would saturate / give 0)
 __device__ __forceinline__ int c_int_cast(double v) {
   return (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
+}
+
+// Resample.c clip8: fixed point (22 fractional bits) -> uint8
+__device__ __forceinline__ unsigned clip8(int v) {
+  v >>= 22;
+  return (unsigned)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
 __device__ __forceinline__ unsigned div255(unsigned a) { return (((a + 128) >> 8) + (a + 128)) >> 8; }
@@ -394,9 +402,10 @@ __device__ inline unsigned color_to_ink(int cmap, double c0, double c1, double c
 }
 
 #define ITEM_CAP 512 /* (sprite, row) items whose spans are precomputed, per env */
-struct RenderLayout { int canvas, ivtx, erec, items, ink, ymin, ymax, horiz, nedge, ibase, total; };
+struct RenderLayout { int canvas, ivtx, erec, items, ink, ymin, ymax, horiz, nedge, ibase, tmp, total; };
 
-__host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int VT) {
+// H, W: canvas size (anti_aliasing x image size); OW: image width
+__host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int VT, int OW) {
   RenderLayout L;
   int o = 0;
   L.canvas = o; o += 4 * H * (W + 1);
@@ -415,6 +424,13 @@ __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int V
   L.horiz = o;  o += 4 * S;
   L.nedge = o;  o += 4 * S;
   L.ibase = o;  o += 4 * (S + 1);
+  // anti_aliasing > 1: the horizontally resampled image [H][OW] reuses everything
+  // after the canvas (dead by then); the final image reuses the canvas
+  L.tmp = L.erec;
+  if (OW != W) {
+    int end = L.tmp + 4 * H * OW;
+    if (end > o) o = end;
+  }
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -425,13 +441,15 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
   ProgramView pv = view_of(a.blob);
   const int32_t *hdr = pv.hdr;
   const int S = hdr[MOOG_H_N_SLOTS], L = hdr[MOOG_H_N_LAYERS], VT = hdr[MOOG_H_N_VTX];
-  const int H = hdr[MOOG_H_R_HEIGHT], W = hdr[MOOG_H_R_WIDTH];
+  // pil_renderer.py:65-66: the canvas is anti_aliasing x the image size
+  const int OH = hdr[MOOG_H_R_HEIGHT], OW = hdr[MOOG_H_R_WIDTH], aa = hdr[MOOG_H_R_AA];
+  const int H = aa * OH, W = aa * OW;
   const unsigned bgc = (unsigned)hdr[MOOG_H_R_BG] & 0xffffffu;
   const int cmap = hdr[MOOG_H_R_COLORMAP], pmod = hdr[MOOG_H_R_MODIFIER], pml = hdr[MOOG_H_R_MOD_LAYER];
   const int g = threadIdx.x / T, t = threadIdx.x - g * T;
   const int n = blockIdx.x * envs_per_block + g;
   const bool live = n < a.n_envs;
-  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1);
+  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1, OW);
   unsigned char *base = smem_raw + (size_t)g * lay.total;
   unsigned *canvas = (unsigned *)(base + lay.canvas);
   int2 *ivtx = (int2 *)(base + lay.ivtx);
@@ -574,16 +592,62 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
     }
   }
   __syncthreads();
+  const unsigned *img = canvas;  // the image to write out: [OH][img_stride] RGBX words
+  int img_stride = stride;
+  if (aa > 1) {
+    // Image.resize(LANCZOS) (Resample.c, 8 bpc): horizontal pass into an 8-bit
+    // intermediate, then vertical pass; fixed-point coefficients from the host
+    const int *bh = a.resample, *kh = bh + 2 * OW;
+    const int *bv = kh + OW * a.ksize_h, *kv = bv + 2 * OH;
+    unsigned *tmp = (unsigned *)(base + lay.tmp);
+    if (live) {
+      for (int i = t; i < H * OW; i += T) {
+        const int yy = i / OW, xx = i - yy * OW;
+        const int xmin = bh[2 * xx], xmax = bh[2 * xx + 1];
+        const int *k = kh + xx * a.ksize_h;
+        const unsigned *src = canvas + yy * stride + xmin;
+        int r = 1 << 21, gch = 1 << 21, b = 1 << 21;
+        for (int x = 0; x < xmax; ++x) {
+          const unsigned px = src[x];
+          const int c = k[x];
+          r += (int)(px & 255u) * c;
+          gch += (int)((px >> 8) & 255u) * c;
+          b += (int)((px >> 16) & 255u) * c;
+        }
+        tmp[i] = clip8(r) | (clip8(gch) << 8) | (clip8(b) << 16);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      unsigned *small = canvas;  // the canvas is dead
+      for (int i = t; i < OH * OW; i += T) {
+        const int yy = i / OW, xx = i - yy * OW;
+        const int ymin = bv[2 * yy], ymax = bv[2 * yy + 1];
+        const int *k = kv + yy * a.ksize_v;
+        int r = 1 << 21, gch = 1 << 21, b = 1 << 21;
+        for (int y = 0; y < ymax; ++y) {
+          const unsigned px = tmp[(y + ymin) * OW + xx];
+          const int c = k[y];
+          r += (int)(px & 255u) * c;
+          gch += (int)((px >> 8) & 255u) * c;
+          b += (int)((px >> 16) & 255u) * c;
+        }
+        small[i] = clip8(r) | (clip8(gch) << 8) | (clip8(b) << 16);
+      }
+    }
+    __syncthreads();
+    img_stride = OW;
+  }
   if (live) {
-    // pil_renderer.py:118-120: np.flipud -> output row j is canvas row H-1-j
-    unsigned char *out = a.frames + (size_t)n * H * W * 3;
-    if ((W & 15) == 0) {
+    // pil_renderer.py:118-120: np.flipud -> output row j is image row OH-1-j
+    unsigned char *out = a.frames + (size_t)n * OH * OW * 3;
+    if ((OW & 15) == 0) {
       // 16 pixels of one row -> 48 bytes = three 16-byte stores
       uint4 *out4 = (uint4 *)out;
-      const int groups = H * (W >> 4);
+      const int groups = OH * (OW >> 4);
       for (int q = t; q < groups; q += T) {
-        const int j = q / (W >> 4), c0 = (q - j * (W >> 4)) << 4;
-        const unsigned *src = canvas + (H - 1 - j) * stride + c0;
+        const int j = q / (OW >> 4), c0 = (q - j * (OW >> 4)) << 4;
+        const unsigned *src = img + (OH - 1 - j) * img_stride + c0;
         unsigned w[12];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {  // 4 pixels (RGBX words) -> 3 packed words
@@ -598,27 +662,84 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
         out4[3 * q + 2] = make_uint4(w[8], w[9], w[10], w[11]);
       }
     } else {
-      const int nbytes = H * W * 3;
+      const int nbytes = OH * OW * 3;
       for (int b = t; b < nbytes; b += T) {
         int p = b / 3, ch = b - 3 * p;
-        int j = p / W, col = p - j * W;
-        out[b] = (unsigned char)((canvas[(H - 1 - j) * stride + col] >> (8 * ch)) & 255u);
+        int j = p / OW, col = p - j * OW;
+        out[b] = (unsigned char)((img[(OH - 1 - j) * img_stride + col] >> (8 * ch)) & 255u);
       }
     }
   }
 }
 
+// ---------------------------------------------------------------------------
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter
+// (SURVEY App. B.6), on the host: the coefficients go through libm's sin() like
+// Pillow's, then to 22-bit fixed point.  Layout of the returned table:
+//   bounds_h[2*OW] coeff_h[OW*ksize_h] bounds_v[2*OH] coeff_v[OH*ksize_v]
+// ---------------------------------------------------------------------------
+static double lanczos_weight(double x) {
+  if (!(-3.0 <= x && x < 3.0)) return 0.0;
+  auto sinc = [](double v) {
+    if (v == 0.0) return 1.0;
+    v = v * M_PI;
+    return sin(v) / v;
+  };
+  return sinc(x) * sinc(x / 3);
+}
+
+static int resample_axis(int in_size, int out_size, std::vector<int> &bounds, std::vector<int> &coeffs) {
+  double scale = (double)in_size / out_size, filterscale = scale < 1.0 ? 1.0 : scale;
+  double support = 3.0 * filterscale;
+  int ksize = (int)ceil(support) * 2 + 1;
+  bounds.assign(2 * (size_t)out_size, 0);
+  coeffs.assign((size_t)out_size * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    double center = (xx + 0.5) * scale, ww = 0.0, ss = 1.0 / filterscale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      k[x] = lanczos_weight((x + xmin - center + 0.5) * ss);
+      ww += k[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      double w = ww != 0.0 ? k[x] / ww : k[x];
+      coeffs[(size_t)xx * ksize + x] = w < 0 ? (int)(-0.5 + w * (1 << 22)) : (int)(0.5 + w * (1 << 22));
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+
+int resample_tables(int H, int W, int OH, int OW, std::vector<int> &table, int *ksize_h, int *ksize_v) {
+  std::vector<int> bh, kh, bv, kv;
+  *ksize_h = resample_axis(W, OW, bh, kh);
+  *ksize_v = resample_axis(H, OH, bv, kv);
+  table.clear();
+  table.insert(table.end(), bh.begin(), bh.end());
+  table.insert(table.end(), kh.begin(), kh.end());
+  table.insert(table.end(), bv.begin(), bv.end());
+  table.insert(table.end(), kv.begin(), kv.end());
+  return (int)table.size();
+}
+
 cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
   if (a.n_envs <= 0) return cudaSuccess;
-  int H = hdr[MOOG_H_R_HEIGHT], W = hdr[MOOG_H_R_WIDTH], S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
+  const int OH = hdr[MOOG_H_R_HEIGHT], OW = hdr[MOOG_H_R_WIDTH], aa = hdr[MOOG_H_R_AA];
+  const int H = aa * OH, W = aa * OW, S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
   const int P = (H <= 128) ? 2 : 1;  // threads per canvas row (they split its columns)
   const int T = (H * P + 31) & ~31;
-  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1);
+  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1, OW);
   int epb = 256 / T;
   if (epb < 1) epb = 1;
   while (epb > 1 && (size_t)lay.total * epb > 100 * 1024) --epb;
   size_t smem = (size_t)lay.total * epb;
-  if (smem > 220 * 1024 || T > 1024) return cudaErrorInvalidConfiguration;
+  if (smem > 224 * 1024 || T > 1024) return cudaErrorInvalidConfiguration;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(moog_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

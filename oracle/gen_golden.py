@@ -111,6 +111,24 @@ def _flat_action(prog, action):
     return out
 
 
+AA_SCENES = ('pong', 'falling_balls20', 'colliding_predators', 'cleanup')
+AA_FACTORS = (2, 3)
+
+
+def _aa_renderers(renderer):
+    """The scene's PILRenderer again, with anti_aliasing 2 and 3
+    (pil_renderer.py:37-86: supersampled canvas + Image.resize(LANCZOS))."""
+    from moog.observers import pil_renderer
+    out = {}
+    for aa in AA_FACTORS:
+        out[aa] = pil_renderer.PILRenderer(
+            image_size=tuple(renderer._image_size), anti_aliasing=aa,  # pylint: disable=protected-access
+            bg_color=renderer._canvas_bg.getpixel((0, 0)),  # pylint: disable=protected-access
+            color_to_rgb=renderer.color_to_rgb,
+            polygon_modifier=renderer._polygon_modifier)  # pylint: disable=protected-access
+    return out
+
+
 def generate(name, out_dir):
     module, level, seed, T, frame_every = SCENES[name]
     np.random.seed(seed)
@@ -168,9 +186,13 @@ def generate(name, out_dir):
     rec = {k: [] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt', 'reward', 'last',
                            'actions', 'noise', 'rule_noise', 'n_calls', 'n_true', 'true_hash')}
     frames, frame_steps = [], []
+    aa_r = _aa_renderers(renderer) if (renderer is not None and name in AA_SCENES) else {}
+    aa_frames = {aa: [] for aa in aa_r}
     if renderer is not None:
         frames.append(np.asarray(ts.observation['image']))
         frame_steps.append(-1)
+        for aa, r in aa_r.items():
+            aa_frames[aa].append(np.asarray(r(env.state)))
     K, nd = prog.K, prog.noise_dim
     for t in range(T):
         action = _seek_action(env, t) if name == 'cleanup' else env.action_space.random_action()
@@ -214,6 +236,8 @@ def generate(name, out_dir):
         if renderer is not None and (t % frame_every == 0 or ts.last()):
             frames.append(np.asarray(ts.observation['image']))
             frame_steps.append(t)
+            for aa, r in aa_r.items():
+                aa_frames[aa].append(np.asarray(r(env.state)))
         if ts.last():
             break
 
@@ -233,6 +257,17 @@ def generate(name, out_dir):
     for k, v in rec.items():
         out[k] = np.array(v)
     path = os.path.join(out_dir, name + '.npz')
+    if os.environ.get('MOOG_GOLDEN_AA_ONLY'):
+        # anti-aliased frames only, for the states the main fixture already holds
+        assert aa_r, name
+        prev = np.load(path)
+        assert np.array_equal(prev['frames'], out['frames']) and np.array_equal(prev['dyn'], out['dyn']), \
+            'the trajectory changed; regenerate the main fixture first'
+        path = os.path.join(out_dir, name + '_aa.npz')
+        np.savez_compressed(path, frame_steps=out['frame_steps'],
+                            **{'frames_aa%d' % aa: np.array(v, dtype=np.uint8) for aa, v in aa_frames.items()})
+        print('{:22s} {} anti-aliased frames x {} -> {}'.format(name, len(frame_steps), list(aa_frames), path))
+        return
     np.savez_compressed(path, **out)
     print('{:22s} T={:3d} slots={:3d} vtx={:4d} true/step={:.1f} -> {} ({} KB)'.format(
         name, len(rec['reward']), prog.n_slots, prog.n_vtx,

@@ -162,3 +162,19 @@ def test_cuda_overlap_pairs_match_oracle(scene):
                 continue
             out = eng.overlap_pairs(a, b).cpu().numpy()
             assert np.array_equal(out, ref), (scene, a, b)
+
+
+@pytest.mark.parametrize('aa', [2, 3])
+@pytest.mark.parametrize('scene', util.AA_SCENES)
+def test_cuda_render_matches_reference_antialiased_frames(scene, aa):
+    g = util.load_golden(scene)
+    ga = util.load_golden_aa(scene)
+    prog = util.with_anti_aliasing(g, aa)
+    parts = [util.state_at(g, int(t)) for t in ga['frame_steps']]
+    arrays = {k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}
+    eng = _engine(prog, arrays)
+    out = eng.render().cpu().numpy()
+    ref = ga['frames_aa%d' % aa]
+    assert out.shape == ref.shape
+    bad = int((out != ref).sum())
+    assert bad == 0, (scene, aa, bad)

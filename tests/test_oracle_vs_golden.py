@@ -52,3 +52,16 @@ def test_oracle_render_matches_reference_frames(scene):
         out = orc.render()[0]
         assert out.shape == f.shape
         assert np.array_equal(out, f), (scene, int(t), int((out != f).sum()))
+
+
+@pytest.mark.parametrize('aa', [2, 3])
+@pytest.mark.parametrize('scene', util.AA_SCENES)
+def test_oracle_render_matches_reference_antialiased_frames(scene, aa):
+    """PILRenderer(anti_aliasing=aa): supersampled canvas + Image.resize(LANCZOS)
+    (pil_renderer.py:65-66,113); frames recorded from the reference renderer."""
+    g = util.load_golden(scene)
+    ga = util.load_golden_aa(scene)
+    prog = util.with_anti_aliasing(g, aa)
+    for f, t in zip(ga['frames_aa%d' % aa], ga['frame_steps']):
+        out = Oracle(prog, util.state_at(g, int(t))).render()[0]
+        assert np.array_equal(out, f), (scene, aa, int(t), int((out != f).sum()))

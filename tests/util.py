@@ -100,3 +100,21 @@ def rel_err(a, b):
     e = np.where(np.isnan(a) & np.isnan(b), 0.0, e)
     e = np.where((a == b), 0.0, e)
     return float(np.nanmax(e)) if not np.all(np.isnan(e)) else float('inf')
+
+
+AA_SCENES = ['pong', 'falling_balls20', 'colliding_predators', 'cleanup']
+
+
+def with_anti_aliasing(g, aa):
+    """The scene's program with PILRenderer(anti_aliasing=aa): the header word
+    MOOG_H_R_AA of the stored blob is patched (compiler.py writes the same word
+    from `renderer._anti_aliasing`)."""
+    from moog_b200 import compiler as C
+    blob = np.frombuffer(bytes(bytearray(g['blob'])), dtype=np.uint8).copy()
+    hdr = blob[:C.HDR_WORDS * 4].view('<i4')
+    hdr[C.H_R_AA] = aa
+    return ProgramStub(blob, g['layer_names'])
+
+
+def load_golden_aa(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '_aa.npz')))
