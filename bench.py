@@ -58,6 +58,23 @@ def _json_default(o):
     raise TypeError(type(o).__name__)
 
 
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
+    committed `ncu --set full` summary of this round (profiles/), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r01_{}_ncu.json'.format(kernel))
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        total = 0.0
+        for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            val, unit = d[key].split()
+            total += float(val) * scale[unit]
+        return total
+    except Exception:  # pylint: disable=broad-except
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -361,10 +378,16 @@ def run_ours(args):
                    'phases': 'uniform mix of episode phases after {} burn-in steps with staggered resets'.format(args.burn_in),
                    'state_record_bytes': int(record_bytes)},
         'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
-                     'unit': 'GB/s', 'frac': step_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                     'unit': 'GB/s', 'frac': step_gbs / peak,
+                     'traffic': _ncu_traffic('step_kernel') if args.scene == 'falling_balls20' and E == 4096 else None,
+                     'traffic_note': 'bytes per launch, ncu --set full of this workload (profiles/r01_step_kernel_ncu.json)',
+                     'algorithmic_bytes_per_launch': E * ab['state'],
+                     'peak_source': peak_src,
                      'algorithmic_bytes_per_env_step': ab['state'], 'kernel_ms': step_ms,
                      'render_kernel': {'kernel': 'moog_render_kernel', 'achieved': rend_gbs, 'frac': rend_gbs / peak,
                                        'algorithmic_bytes_per_env_step': ab['frame'] + prog.n_slots * 32,
+                                       'traffic': (_ncu_traffic('render_kernel')
+                                                   if args.scene == 'falling_balls20' and E == 4096 else None),
                                        'kernel_ms': rend_ms},
                      'share_of_step': {'moog_step_kernel': step_ms / (step_ms + rend_ms),
                                        'moog_render_kernel': rend_ms / (step_ms + rend_ms)}},
