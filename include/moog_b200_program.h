@@ -169,7 +169,12 @@ enum {
   MOOG_SC_CONTACT_COUNT,   /* i0 layer0 i1 layer1: len(get_contact_indices)    contact_rules.py:38-51 */
   MOOG_SC_CONTACT_ANY_COUNT, /* i0,i1 list of sprites' layers; i2,i3 other list; i4 filter expr:
                                 count of list-0 sprites passing the filter that overlap any list-1 sprite */
-  MOOG_SC_CONST            /* p0                                                */
+  MOOG_SC_CONST,           /* p0                                                */
+  MOOG_SC_BINARY,          /* i0, i1 operand condition ops; i2 = MOOG_X_* binary opcode.  MOOG_X_AND /
+                              MOOG_X_OR follow Python: the right operand is only evaluated when needed
+                              (matters for the overlap calls a contact count makes) and the value is
+                              that of the deciding operand */
+  MOOG_SC_NOT              /* i0 operand condition op: python `not`             */
 };
 
 /* op flags */
@@ -198,7 +203,9 @@ enum {
   MOOG_X_AND, MOOG_X_OR, MOOG_X_NOT,
   MOOG_X_ADD, MOOG_X_SUB, MOOG_X_MUL, MOOG_X_DIV, MOOG_X_NEG, MOOG_X_ABS,
   MOOG_X_MOD,        /* python float modulo                                  */
-  MOOG_X_STORE       /* pop -> attribute `arg` of sprite 0 (modifier programs) */
+  MOOG_X_STORE,      /* pop -> attribute `arg` of sprite 0 (modifier programs) */
+  MOOG_X_STORE_POS   /* pop y, pop x -> sprite 0 `.position = (x, y)`: one translation of the cached
+                        outline (sprite.py:616-633) */
 };
 
 /* attribute ids for the expression VM (Sprite.FACTOR_NAMES, sprite.py:237-253) */

@@ -25,7 +25,8 @@ NVCC_FLAGS = [
     '--expt-extended-lambda', '-Xcompiler', '-fPIC,-ffp-contract=off',
     '-Wno-deprecated-gpu-targets',
 ] + (['-DMOOG_PROFILE_PHASES'] if os.environ.get('MOOG_PROFILE_PHASES') else []) + (
-    ['-DMOOG_PROFILE_DCV'] if os.environ.get('MOOG_PROFILE_DCV') else [])
+    ['-DMOOG_PROFILE_DCV'] if os.environ.get('MOOG_PROFILE_DCV') else []) + (
+    ['-DMOOG_PROFILE_ICACHE'] if os.environ.get('MOOG_PROFILE_ICACHE') else [])
 
 
 def _nvcc():

@@ -57,8 +57,8 @@ R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
     R_MODIFY_SPRITES, R_COND_BEGIN = 64, 65, 66, 67, 68
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
-SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST = \
-    160, 161, 162, 163, 164, 165
+SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
+    SC_BINARY, SC_NOT = 160, 161, 162, 163, 164, 165, 166, 167
 
 FL_SYMMETRIC = 1
 FL_UPDATE_ANGLE_VEL = 2

@@ -125,7 +125,28 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
     a.order = order;
     a.cost = cost;
   }
-  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches);
+  // The step ends when its longest-running env does, and a warp runs ~2.4x slower next to 11
+  // others than alone (profiles/README.md): with the envs dispatched longest-first, capping
+  // the envs resident per SM at about n_envs / (9 x SMs) -- nine waves -- finishes the step
+  // sooner than filling the SMs (4096 envs on 148 SMs: 3 per SM, 5.5 ms instead of 6.1 ms).
+  // In that regime the SMs have registers to spare, and every env gets a helper warp that
+  // computes one of the two directions of _get_collision_vectors (MOOG_HELPER=0/1 overrides).
+  int resident = 0;
+  bool helper = false;
+  {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > 0) {
+      resident = (n_envs + 9 * sms / 2) / (9 * sms);
+      if (resident < 2) resident = 2;
+      helper = resident <= 6;
+    }
+    if (!a.order) resident = 0;
+    const char *h = getenv("MOOG_HELPER");
+    if (h) helper = atoi(h) != 0;
+  }
+  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches, 0, -1, resident, helper);
   g_launches += launches;
   return err == cudaSuccess ? 0 : cuda_fail(err);
 }
@@ -162,7 +183,7 @@ int moog_overlap_pairs(moog_program *p, const moog_state *st, int n_envs, int la
 int moog_render(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream) {
   if (!p || !valid_state(st) || !frames || n_envs < 0) return MOOG_E_INVAL;
   if (!p->hdr[MOOG_H_R_ENABLED]) return MOOG_E_INVAL;
-  if (p->hdr[MOOG_H_R_AA] < 1 || p->hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS) return MOOG_E_UNSUPPORTED;
+  if (p->hdr[MOOG_H_R_AA] < 1) return MOOG_E_UNSUPPORTED;
   moog::RenderArgs a;
   memset(&a, 0, sizeof(a));
   a.blob = p->dev_blob;

@@ -38,6 +38,7 @@ struct StepArgs {
   int mode;
   int S, L, K, VT, NF, CMW;  // program dimensions (filled in by launch_step from the header)
   const int *order;          // [n_envs] env handled by CTA i, or nullptr = identity
+  int first, count;          // this launch covers dispatch positions [first, first + count)
   int *cost;                 // [n_envs] SM cycles >> 6 this call cost each env, or nullptr
   moog_step_io io;
   moog_state pool;  // valid iff io.pool != nullptr
@@ -59,7 +60,12 @@ struct RenderArgs {
 constexpr int kMaxForceOps = 32;
 int env_smem_bytes(const int32_t *hdr);
 int candidate_matrix_words(const void *host_blob);
-cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
+// [first, first + count): dispatch positions covered by this launch (count < 0: all);
+// resident_envs_per_sm > 0 pads the shared-memory request so that at most that many envs
+// share an SM; helper: every env's CTA gets a second warp that runs one direction of
+// _get_collision_vectors next to its owner
+cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches,
+                        int first = 0, int count = -1, int resident_envs_per_sm = 0, bool helper = false);
 cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream, int *n_launches);
 int resample_tables(int H, int W, int OH, int OW, std::vector<int> &table, int *ksize_h, int *ksize_v);
 cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);

@@ -449,7 +449,11 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
   const int g = threadIdx.x / T, t = threadIdx.x - g * T;
   const int n = blockIdx.x * envs_per_block + g;
   const bool live = n < a.n_envs;
-  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1, OW);
+  // polygon_modifiers.py:88-96 TorusGeometry: every sprite is drawn as 9 copies shifted by
+  // (i, j), i outer / j inner over (-1, 0, 1); copy c of slot s is the virtual slot s * C + c
+  // and its vertices live at c * VT + voff[s]
+  const int C = pmod == MOOG_PMOD_TORUS ? 9 : 1;
+  RenderLayout lay = render_layout(H, W, S * C, (VT > 0 ? VT : 1) * C, OW);
   unsigned char *base = smem_raw + (size_t)g * lay.total;
   unsigned *canvas = (unsigned *)(base + lay.canvas);
   int2 *ivtx = (int2 *)(base + lay.ivtx);
@@ -473,10 +477,12 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
       oy = 0.5 - dyn[MOOG_D_Y * S + s];
     }
     // int-truncated canvas vertices (C cast toward zero), per-slot extents and ink
-    for (int v = t; v < VT; v += T) {
-      double2 p = vtx[v];
+    for (int v = t; v < C * VT; v += T) {
+      const int c = v / VT;
+      double2 p = vtx[v - c * VT];
       double x = p.x, y = p.y;
-      if (pmod != MOOG_PMOD_NONE) { x = x + ox; y = y + oy; }
+      if (pmod == MOOG_PMOD_TORUS) { x = x + (double)(c / 3 - 1); y = y + (double)(c % 3 - 1); }
+      else if (pmod != MOOG_PMOD_NONE) { x = x + ox; y = y + oy; }
       ivtx[v] = make_int2(c_int_cast((double)W * x), c_int_cast((double)H * y));
     }
     for (int s = t; s < S; s += T)
@@ -487,16 +493,17 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
   __syncthreads();
   if (live) {
     const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
-    for (int s = t; s < S; s += T) {
+    for (int vs = t; vs < S * C; vs += T) {
+      const int s = vs / C, vo = (vs - s * C) * VT + pv.voff[s];
       int nv = meta[MOOG_M_NV * S + s];
-      const int2 *xy = ivtx + pv.voff[s];
+      const int2 *xy = ivtx + vo;
       int lo = 0x7fffffff, hi = -0x7fffffff, hz = 0;
       for (int i = 0; i < nv; ++i) {
         lo = min(lo, xy[i].y);
         hi = max(hi, xy[i].y);
       }
-      snedge[s] = nv > 0 ? build_edge_list(xy, nv, erec + pv.voff[s], &hz) : 0;
-      symin[s] = lo; symax[s] = hi; shoriz[s] = hz;
+      snedge[vs] = nv > 0 ? build_edge_list(xy, nv, erec + vo, &hz) : 0;
+      symin[vs] = lo; symax[vs] = hi; shoriz[vs] = hz;
     }
   }
   // z-order list of the live sprites and the (sprite, row) item ranges
@@ -504,28 +511,30 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
     const int32_t *meta = a.st.meta + (size_t)n * MOOG_META_FIELDS * S;
     const int32_t *cnt = a.st.cnt + (size_t)n * MOOG_MAX_LAYERS;
     int acc = 0;
-    for (int s = 0; s < S; ++s) sibase[s] = -1;
+    for (int s = 0; s < S * C; ++s) sibase[s] = -1;
     for (int l = 0; l < L; ++l) {
       int c = cnt[l];
       for (int k = 0; k < c; ++k) {
-        int s = hdr[MOOG_H_LAYER_OFF + l] + k;
-        if (meta[MOOG_M_NV * S + s] <= 0) continue;
-        // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
-        int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
-        int rows = hi >= lo ? hi - lo + 1 : 0;
-        if (rows > 0 && acc + rows <= ITEM_CAP) {
-          sibase[s] = acc;
-          acc += rows;
+        int s0 = hdr[MOOG_H_LAYER_OFF + l] + k;
+        if (meta[MOOG_M_NV * S + s0] <= 0) continue;
+        for (int s = s0 * C; s < (s0 + 1) * C; ++s) {
+          // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
+          int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
+          int rows = hi >= lo ? hi - lo + 1 : 0;
+          if (rows > 0 && acc + rows <= ITEM_CAP) {
+            sibase[s] = acc;
+            acc += rows;
+          }
         }
       }
     }
-    sibase[S] = acc;
+    sibase[S * C] = acc;
   }
   __syncthreads();
   // phase 1: one (sprite, row) item per thread pass -> clipped spans
   if (live) {
-    const int n_items = sibase[S];
-    int s = 0;
+    const int n_items = sibase[S * C];
+    int s = 0;  // virtual slot
     for (int it = t; it < n_items; it += T) {
       // items are sprite-major; find the sprite that owns item `it`
       for (;;) {
@@ -542,7 +551,7 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
       sink.item = items + (size_t)it * (1 + ITEM_SPANS);
       sink.W = W;
       sink.n = 0;
-      polygon_row_rec(erec + pv.voff[s], snedge[s], y, min(symax[s], H), shoriz[s] != 0, sink);
+      polygon_row_rec(erec + (s % C) * VT + pv.voff[s / C], snedge[s], y, min(symax[s], H), shoriz[s] != 0, sink);
       sink.item[0] = sink.n <= ITEM_SPANS ? (unsigned)sink.n : ITEM_OVERFLOW;
     }
   }
@@ -557,11 +566,12 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
     for (int l = 0; l < L; ++l) {
       int c = cnt[l];
       for (int k = 0; k < c; ++k) {
-        int s = hdr[MOOG_H_LAYER_OFF + l] + k;
-        if (meta[MOOG_M_NV * S + s] <= 0) continue;
+        const int s0 = hdr[MOOG_H_LAYER_OFF + l] + k;
+        if (meta[MOOG_M_NV * S + s0] <= 0) continue;
+        const unsigned color = ink[s0];
+        for (int s = s0 * C; s < (s0 + 1) * C; ++s) {
         int ymin_c = max(symin[s], 0), ymax_c = min(symax[s], H);
         if (y < ymin_c || y > ymax_c) continue;
-        const unsigned color = ink[s];
         const int b0 = sibase[s];
         unsigned cntw = ITEM_OVERFLOW;
         const unsigned *item = nullptr;
@@ -586,7 +596,8 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
           sink.ink = color;
           sink.xlo = xlo;
           sink.xhi = xhi;
-          polygon_row_rec(erec + pv.voff[s], snedge[s], y, ymax_c, shoriz[s] != 0, sink);
+          polygon_row_rec(erec + (s - s0 * C) * VT + pv.voff[s0], snedge[s], y, ymax_c, shoriz[s] != 0, sink);
+        }
         }
       }
     }
@@ -734,7 +745,8 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
   const int H = aa * OH, W = aa * OW, S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
   const int P = (H <= 128) ? 2 : 1;  // threads per canvas row (they split its columns)
   const int T = (H * P + 31) & ~31;
-  RenderLayout lay = render_layout(H, W, S, VT > 0 ? VT : 1, OW);
+  const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;  // TorusGeometry: 9 copies per sprite
+  RenderLayout lay = render_layout(H, W, S * C, (VT > 0 ? VT : 1) * C, OW);
   int epb = 256 / T;
   if (epb < 1) epb = 1;
   while (epb > 1 && (size_t)lay.total * epb > 100 * 1024) --epb;

@@ -25,6 +25,7 @@
 // oracle/moog_oracle.c), because contact decisions and argmin / argmax ties are
 // decided by the last bit.
 #include <math.h>
+#include <stdlib.h>
 
 #include "moog_common.cuh"
 
@@ -48,13 +49,14 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, aabb0, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, kscr, total;
+  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, kscr, kscr_bytes, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
 #define DCV_TILE 8     /* contained vertices per pass of _directed_collision_vectors */
 #define NEAR_SKIN 0.02
-#define NEAR_CAP 384  /* near-list entries; more near pairs than this -> every pair is tested */
+#define STEP_WARPS 2   /* warps of an env's CTA: the owner and (optionally) its helper, see moog_step_kernel */
+#define NEAR_CAP 256  /* near-list entries; more near pairs than this -> every pair is tested */
 
 __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW) {
   SmemLayout L;
@@ -63,13 +65,14 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.dyn = o;   o += 8 * MOOG_DYN_FIELDS * S;
   L.stat = o;  o += 8 * MOOG_STAT_FIELDS * S;
   L.aabb = o;  o += 8 * 4 * S;
-  L.aabb0 = o; o += 8 * 4 * S;
-  L.tmp = o;   o += 8 * 8 * S;
-  L.vtx = o;   o += 16 * VT;
+  L.vtx = o;   o += 16 * VT;     // 16-byte aligned: everything before it is a multiple of 16
+  L.tmp = o;   o += 8 * 3 * S;  // tether scratch (3 fields)
   L.envf = o;  o += 8 * NF;
   L.ctr = o;   o += 8 * 12;
   L.meta = o;  o += 4 * MOOG_META_FIELDS * S;
   L.sflag = o; o += 4 * S;
+  L.aabb0 = o; o += 4 * 4 * S;  // float: box snapshot of the near list
+  L.nskin = o; o += 4 * S;      // float: drift allowance per slot
   L.voff = o;  o += 4 * (S + 1);
   L.cnt = o;   o += 4 * MOOG_MAX_LAYERS;
   L.envi = o;  o += 4 * MOOG_ENVI_WORDS;
@@ -77,9 +80,11 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.cmask = o; o += 4 * (CMW > 0 ? CMW : 1);
   L.nearp = o; o += CMW > 0 ? 4 * NEAR_CAP : 4;
   L.hdr = o;   o += 4 * MOOG_HDR_WORDS;
-  L.scratch = o; o += 64;
+  L.scratch = o; o += 64 * STEP_WARPS;  // one per warp (main, helper)
   o = (o + 7) & ~7;
-  L.kscr = o;  o += CMW > 0 ? 8 * 32 * DCV_TILE : 8;
+  L.xchg = o;  o += 128;                  // main <-> helper: request words, the helper's CVec
+  L.kscr_bytes = CMW > 0 ? 8 * 32 * DCV_TILE : 8;
+  L.kscr = o;  o += L.kscr_bytes * STEP_WARPS;
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -105,12 +110,14 @@ int candidate_matrix_words(const void *host_blob) {
 
 struct Env {
   // shared memory
-  double *dyn, *stat, *aabb, *aabb0, *tmp, *envf;
+  double *dyn, *stat, *aabb, *tmp, *envf;
+  float *aabb0, *nskin;
   double2 *vtx;
   int *meta, *sflag, *voff, *cnt, *envi, *cmoff;
   unsigned *cmask, *nearp;
   unsigned char *scratch;
   unsigned long long *kscr;
+  unsigned char *xchg;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -151,7 +158,8 @@ __device__ __forceinline__ Env env_view() {
   e.dyn = (double *)(base + r->lay.dyn);
   e.stat = (double *)(base + r->lay.stat);
   e.aabb = (double *)(base + r->lay.aabb);
-  e.aabb0 = (double *)(base + r->lay.aabb0);
+  e.aabb0 = (float *)(base + r->lay.aabb0);
+  e.nskin = (float *)(base + r->lay.nskin);
   e.tmp = (double *)(base + r->lay.tmp);
   e.vtx = (double2 *)(base + r->lay.vtx);
   e.envf = (double *)(base + r->lay.envf);
@@ -165,11 +173,13 @@ __device__ __forceinline__ Env env_view() {
   e.cmask = (unsigned *)(base + r->lay.cmask);
   e.nearp = (unsigned *)(base + r->lay.nearp);
   e.hdr = (const int32_t *)(base + r->lay.hdr);
-  e.scratch = base + r->lay.scratch;
-  e.kscr = (unsigned long long *)(base + r->lay.kscr);
+  const int warp = threadIdx.x >> 5;
+  e.scratch = base + r->lay.scratch + 64 * warp;
+  e.kscr = (unsigned long long *)(base + r->lay.kscr + r->lay.kscr_bytes * warp);
+  e.xchg = base + r->lay.xchg;
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
-  e.lane = threadIdx.x;
+  e.lane = threadIdx.x & 31;
   e.noise = r->noise; e.rule_noise = r->rule_noise;
   e.seed = r->seed;
   e.env_id = r->env_id;
@@ -655,6 +665,24 @@ __device__ inline bool overlaps(const Env &e, int a, int b) {
 // ---------------------------------------------------------------------------
 // collisions.py
 // ---------------------------------------------------------------------------
+// (fl(n / d) >= 0 && fl(n / d) <= 1) without the division, for the crossing test of
+// sprite.py:171-175.  Rounding to nearest is monotone and 0 and 1 are representable, so for
+// finite operands whose quotient neither overflows nor underflows
+//   fl(n/d) <= 1  <=>  n/d <= 1   (the smallest quotient above 1, (d + ulp)/d, is > 1 + 2^-53
+//                                  and rounds to 1 + 2^-52)
+//   fl(n/d) >= 0  <=>  n/d >= 0 or n == -0.0  (-0.0 >= 0 is true)
+// and d == 0 gives +-inf or NaN, false either way.  `exact` is false when the operands are
+// outside that regime; the caller then divides.
+__device__ __forceinline__ bool unit_ratio(double n, double d, bool &exact) {
+  const double an = fabs(n), ad = fabs(d);
+  exact = (an == 0.0 || (an >= 1e-290 && an <= 1e290)) && ad <= 1e10 && (ad >= 1e-290 || ad == 0.0);
+  return d > 0.0 ? (n >= 0.0 && n <= d) : (d < 0.0 && n <= 0.0 && n >= d);
+}
+
+enum { HELPER_EXIT = 0, HELPER_DCV = 1 };
+// named barrier over the owner and helper warps of the CTA (also orders their shared-memory traffic)
+__device__ __forceinline__ void cta_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 struct CVec {
   int has_point, future, has_since;
   double px, py, nx, ny, sx, sy, qx, qy;  // point, normal, since, perp
@@ -766,9 +794,15 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
         // sprite.py:145-161 segment_crossing_coefficients against edge `ej`
         const double den = on ? (d0x * d1y - d0y * d1x) + EPS_INTERP : 1.0;
         const double qx = q1.x - sx, qy = q1.y - sy;
-        const double Bc = (on ? (qx * d0y - qy * d0x) : 1.0) / den;
+        const double nB = on ? (qx * d0y - qy * d0x) : 1.0;
+        bool exact;
+        bool in_unit = unit_ratio(nB, den, exact);
+        if (__any_sync(FULL, !exact)) {  // out-of-range operands somewhere in the warp: divide
+          const double Bc = nB / den;
+          in_unit = (Bc >= 0) && (Bc <= 1);
+        }
         double A = (on ? (qx * d1y - qy * d1x) : 1.0) / den;
-        const bool crossing = on && (Bc >= 0) && (Bc <= 1);
+        const bool crossing = on && in_unit;
         my_cross |= crossing;
         if (!crossing) A = -INFINITY;
         const double ab = fabs(1.0 - A);
@@ -786,32 +820,46 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
     long long tp2 = clock64();
     ctr_add(e, CT_CYC_NARROW, tp2 - tp1);
 #endif
-    // stage B
+    // stage B (lane = edge of s1): np.argmin of every vertex's row of keys by two warp
+    // minima (high word, then low word among the lanes that hold the minimum high word) and
+    // the first such lane; the rows are independent, so the reductions pipeline.  Lane v
+    // keeps the winner of vertex v.
     const bool vact = e.lane < cnt;
     int idx = 0;
-    double A = 0, cpx = 0, cpy = 0, dfx = 0, dfy = 0, dist = 0;
-    if (vact) {
-      const unsigned long long *row = keys + e.lane * 32;
-      unsigned long long best = row[0];
+    {
+      const bool kact = e.lane < n1;
 #pragma unroll 4
-      for (int j = 1; j < n1; ++j) {
-        const unsigned long long k = row[j];
-        if (k < best) {
-          best = k;
-          idx = j;
-        }
+      for (int v = 0; v < cnt; ++v) {
+        const unsigned long long k = kact ? keys[v * 32 + e.lane] : ~0ull;
+        const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+        const unsigned mhi = __reduce_min_sync(FULL, hi);
+        const bool th = kact && hi == mhi;
+        const unsigned mlo = __reduce_min_sync(FULL, th ? lo : 0xffffffffu);
+        const int win = __ffs(__ballot_sync(FULL, th && lo == mlo)) - 1;
+        if (e.lane == v) idx = win;
       }
-      const double2 ev = P0[e.scratch[vbase + e.lane]];
+    }
+    double A = 0, cpx = 0, cpy = 0, dfx = 0, dfy = 0, dist = 0;
+    {
+      // the winning edge's coefficient again -- the same IEEE operations, hence the same bits
+      const double2 ev = P0[e.scratch[vbase + (vact ? e.lane : 0)]];
       const double ex = ev.x, ey = ev.y;
       const double sx = M.m0 * ex + M.m1 * ey + M.m2;
       const double sy = M.m3 * ex + M.m4 * ey + M.m5;
       const double d0x = ex - sx, d0y = ey - sy;
       const double2 w1 = P1[idx], w2 = P1[(idx + 1 == n1) ? 0 : idx + 1];
       const double e1x = w2.x - w1.x, e1y = w2.y - w1.y;
-      const double den = (d0x * e1y - d0y * e1x) + EPS_INTERP;
+      const double den = vact ? (d0x * e1y - d0y * e1x) + EPS_INTERP : 1.0;
       const double qx = w1.x - sx, qy = w1.y - sy;
-      const double Bc = (qx * d0y - qy * d0x) / den;
-      A = ((Bc >= 0) && (Bc <= 1)) ? (qx * e1y - qy * e1x) / den : -INFINITY;
+      const double nB = vact ? (qx * d0y - qy * d0x) : 1.0;
+      bool exact;
+      bool in_unit = unit_ratio(nB, den, exact);
+      if (__any_sync(FULL, !exact)) {
+        const double Bc = nB / den;
+        in_unit = (Bc >= 0) && (Bc <= 1);
+      }
+      A = (vact ? (qx * e1y - qy * e1x) : 1.0) / den;
+      if (!in_unit) A = -INFINITY;
       cpx = sx + A * (ex - sx);
       cpy = sy + A * (ey - sy);
       dfx = ex - cpx;
@@ -870,8 +918,20 @@ __device__ __noinline__ void directed_collision_vectors(const Env &, int s0, int
 // collisions.py:235-289 _get_collision_vectors
 __device__ inline void get_collision_vectors(const Env &e, int s0, int s1, double dt, CVec &o) {
   CVec c0, c1;
-  directed_collision_vectors(e, s1, s0, dt, c0);
-  directed_collision_vectors(e, s0, s1, dt, c1);
+  if (blockDim.x == 64) {
+    // the helper warp computes the second direction while this warp computes the first
+    int *req = (int *)e.xchg;
+    wsync();
+    if (e.lane == 0) { req[0] = HELPER_DCV; req[1] = s0; req[2] = s1; }
+    cta_bar(1);                                       // request visible, helper released
+    directed_collision_vectors(e, s1, s0, dt, c0);
+    cta_bar(2);                                       // helper's result visible
+    c1 = *(const CVec *)(e.xchg + 16);
+    wsync();
+  } else {
+    directed_collision_vectors(e, s1, s0, dt, c0);
+    directed_collision_vectors(e, s0, s1, dt, c1);
+  }
   double s0x = 0, s0y = 0, s1x = 0, s1y = 0;
   if (c0.has_point) {
     if (!c0.future) {
@@ -1168,17 +1228,31 @@ __device__ __forceinline__ bool pair_candidate(const Env &e, int a, int b, bool 
 }
 
 // Near list ("Verlet list with a skin").  Evaluating every pair every substep is
-// wasted on pairs that are far apart, so the pairs whose boxes come within
-// NEAR_SKIN of each other are listed once, together with a snapshot of the boxes;
-// the list stays a superset of all possible candidates for as long as no box
-// coordinate has drifted by NEAR_SKIN / 2 since the snapshot.  Each refresh of
-// the candidate matrices then tests 32 listed pairs per warp pass.
+// wasted on pairs that are far apart, so the pairs whose boxes could meet are
+// listed once, together with a snapshot of the boxes.  Every slot s gets a drift
+// allowance nskin[s] -- at least NEAR_SKIN / 2, and enough for the way it travels
+// at its current velocity in what is left of this env-step, so that a sprite that
+// was kicked out of the arena does not force a rebuild every substep -- and the
+// pair (a, b) is listed when the boxes come within nskin[a] + nskin[b] of each
+// other.  The list stays a superset of all possible candidates for as long as no
+// box coordinate of s has drifted by nskin[s] since the snapshot.  Each refresh
+// of the candidate matrices then tests 32 listed pairs per warp pass.
 
 // entry = slot a | slot b << 8 | (bit index in cmask) << 16
 __device__ __noinline__ void rebuild_near(const Env &) {
   const Env e = env_view();
   const int32_t *h = e.hdr;
-  for (int i = e.lane; i < 4 * e.S; i += 32) e.aabb0[i] = e.aabb[i];
+  for (int i = e.lane; i < 4 * e.S; i += 32) e.aabb0[i] = (float)e.aabb[i];
+  {
+    const double rem = (double)(e.K - (int)e.ctr[CT_SUBSTEP]) / (double)e.K;
+    for (int s = e.lane; s < e.S; s += 32) {
+      const double vmax = fmax(fabs(DYN(e, MOOG_D_VX, s)), fabs(DYN(e, MOOG_D_VY, s)));  // fmax drops a NaN operand
+      const bool fin = isfinite(DYN(e, MOOG_D_VX, s)) && isfinite(DYN(e, MOOG_D_VY, s));
+      // rounded up to float; the snapshot's own float rounding (<= 2^-24 relative) is far inside the margin
+      e.nskin[s] = fin ? __double2float_ru(fmax(0.5 * NEAR_SKIN, 1.2 * vmax * rem + 0.1 * NEAR_SKIN)) : INFINITY;
+    }
+  }
+  wsync();
   int count = 0;
   bool overflow = false;
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
@@ -1190,13 +1264,16 @@ __device__ __noinline__ void rebuild_near(const Env &) {
 #pragma unroll 1
     for (int i = 0; i < na && !overflow; ++i) {
       const int s0 = sa + i;
-      const double x0 = BOX(e, 0, s0) - NEAR_SKIN, y0 = BOX(e, 1, s0) - NEAR_SKIN;
-      const double x1 = BOX(e, 2, s0) + NEAR_SKIN, y1 = BOX(e, 3, s0) + NEAR_SKIN;
+      const double k0 = (double)e.nskin[s0];
+      const double bx0 = BOX(e, 0, s0) - k0, by0 = BOX(e, 1, s0) - k0;
+      const double bx1 = BOX(e, 2, s0) + k0, by1 = BOX(e, 3, s0) + k0;
 #pragma unroll 1
       for (int w = 0; w * 32 < nb; ++w) {
         const int j = w * 32 + e.lane;
         const int s1 = (j < nb) ? sb + j : s0;
         // NaN boxes compare false everywhere -> near
+        const double k1 = (double)e.nskin[s1];
+        const double x0 = bx0 - k1, y0 = by0 - k1, x1 = bx1 + k1, y1 = by1 + k1;
         const bool near = j < nb && s1 != s0 &&
                           !(x1 < BOX(e, 0, s1) || BOX(e, 2, s1) < x0 || y1 < BOX(e, 1, s1) || BOX(e, 3, s1) < y0);
         const unsigned m = __ballot_sync(FULL, near);
@@ -1245,8 +1322,9 @@ __device__ inline void refresh_candidates(const Env &e, int n_cmask_words) {
   // has any box drifted too far since the near list was built?  (NaN -> yes)
   bool bad = false;
   for (int i = e.lane; i < 4 * e.S; i += 32) {
-    const double b1 = e.aabb[i], b0 = e.aabb0[i];  // (+-inf == +-inf: the all-covering box of a NaN sprite)
-    bad |= !(fabs(b1 - b0) < 0.5 * NEAR_SKIN) && !(b1 == b0);
+    const double b1 = e.aabb[i], b0 = (double)e.aabb0[i];  // (+-inf == +-inf: the all-covering box of a NaN sprite)
+    // the allowance is charged for the float rounding of the snapshot (<= 2^-24 |b0|)
+    bad |= !(fabs(b1 - b0) < (double)e.nskin[i >> 2] - (1.2e-7 * fabs(b0) + 1e-9)) && !(b1 == b0);
   }
   if (__any_sync(FULL, bad) || e.ctr[CT_NEAR] == -2) rebuild_near(e);
   const int n_near = (int)e.ctr[CT_NEAR];
@@ -1560,6 +1638,21 @@ __device__ __noinline__ void corrective(const Env &, const moog_op *op) {
       for (int i = 0; i < n; ++i) {
         int s = list_slot(e, op->i[0], op->i[1], i);
         double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
+        if (vel32(e, s)) {
+          // a float32 velocity array: np.linalg.norm is sqrt(x.dot(x)) in float32 (products and
+          // sum each rounded, no fma) and `speed * velocity / norm` stays float32
+          const float fx = (float)vx, fy = (float)vy;
+          const float nf = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+          if (nf != 0) {
+            const float sp32 = (float)op->p[0];
+            assign_velocity(e, s, (double)__fdiv_rn(__fmul_rn(sp32, fx), nf), (double)__fdiv_rn(__fmul_rn(sp32, fy), nf));
+            const int fl = META(e, MOOG_M_FLAGS, s) | MOOG_SF_VEL32;
+            wsync();
+            puti(e, &META(e, MOOG_M_FLAGS, s), fl);
+            wsync();
+          }
+          continue;
+        }
         double nv = norm1(vx, vy);
         if (nv != 0) assign_velocity(e, s, op->p[0] * vx / nv, op->p[0] * vy / nv);
       }
@@ -1577,82 +1670,84 @@ __device__ __noinline__ void corrective(const Env &, const moog_op *op) {
 
 __device__ inline void integrate_all(const Env &e) {
   double dt = 1. / e.K;
-  // phase 1: lane = slot.  New position / angle and the affine update of the outline.
-  for (int s = e.lane; s < e.S; s += 32) {
-    int vs_layer_live = 0;
-    // live?  slots of layer l are [LOFF(l), LOFF(l) + cnt[l])
-    for (int l = 0; l < e.L; ++l)
-      if (s >= LOFF(e, l) && s < LOFF(e, l) + e.cnt[l]) vs_layer_live = 1;
-    int flag = 0;
-    if (vs_layer_live) {
-      bool v32 = vel32(e, s);
-      double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
-      double dx = v32 ? f32mul(dt, vx) : dt * vx;
-      double dy = v32 ? f32mul(dt, vy) : dt * vy;
-      double ox = DYN(e, MOOG_D_X, s), oy = DYN(e, MOOG_D_Y, s);
-      double nx = ox + dx, ny = oy + dy;
-      double tx = nx - ox, ty = ny - oy;
-      DYN(e, MOOG_D_X, s) = nx;
-      DYN(e, MOOG_D_Y, s) = ny;
-      TMP(e, 0, s) = tx;
-      TMP(e, 1, s) = ty;
-      if (!(tx == 0.0 && ty == 0.0)) {
-        flag |= TF_MOVE;
-        BOX(e, 0, s) = BOX(e, 0, s) + tx;
-        BOX(e, 1, s) = BOX(e, 1, s) + ty;
-        BOX(e, 2, s) = BOX(e, 2, s) + tx;
-        BOX(e, 3, s) = BOX(e, 3, s) + ty;
-      }
-      double w = DYN(e, MOOG_D_ANGVEL, s);
-      if (w != 0) {  // `if self._angle_vel:` (NaN is truthy)
-        int wk = angvel_kind(e, s), ak = ang_kind(e, s);
-        double t = (wk == KIND_F32) ? f32mul(dt, w) : dt * w;
-        double a = DYN(e, MOOG_D_ANG, s), na;
-        int nk;
-        if (ak == KIND_F64 || wk == KIND_F64) { na = a + t; nk = KIND_F64; }
-        else if (ak == KIND_WEAK && wk == KIND_WEAK) { na = a + t; nk = KIND_WEAK; }
-        else { na = f32add(a, t); nk = KIND_F32; }
-        // sprite.py:531-540: rotate_around(x, y, a_new - a_old) about the NEW position
-        double dth = (nk == KIND_F32 && ak != KIND_F64) ? f32sub(na, a) : na - a;
-        Aff m = aff_identity();
-        aff_rotate_around(m, nx, ny, dth);
-        TMP(e, 2, s) = m.m0; TMP(e, 3, s) = m.m1; TMP(e, 4, s) = m.m2;
-        TMP(e, 5, s) = m.m3; TMP(e, 6, s) = m.m4; TMP(e, 7, s) = m.m5;
-        DYN(e, MOOG_D_ANG, s) = na;
-        META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (nk << MOOG_SF_ANG_SHIFT);
-        flag |= TF_ROT;
-      }
-    }
-    if (vs_layer_live && !(isfinite(TMP(e, 0, s)) && isfinite(TMP(e, 1, s)))) flag |= TF_CLASSIFY;
-    if ((flag & TF_ROT) && (e.sflag[s] & SLF_NONFINITE)) flag |= TF_CLASSIFY;
-    e.sflag[s] = (e.sflag[s] & SLF_MASK) | (flag << 8);
-  }
-  wsync();
-  // phase 2: one moved slot at a time, lane = vertex of its outline
   for (int base = 0; base < e.S; base += 32) {
-    const int sl = base + e.lane;
-    unsigned mv = __ballot_sync(FULL, sl < e.S && (e.sflag[sl] >> 8) != 0);
+    // phase 1: lane = slot.  New position / angle and the affine update of the outline
+    // (kept in this lane's registers; phase 2 fetches them by shuffle).
+    const int s = base + e.lane;
+    int flag = 0;
+    double tx = 0.0, ty = 0.0;
+    Aff m = aff_identity();
+    if (s < e.S) {
+      int vs_layer_live = 0;
+      // live?  slots of layer l are [LOFF(l), LOFF(l) + cnt[l])
+      for (int l = 0; l < e.L; ++l)
+        if (s >= LOFF(e, l) && s < LOFF(e, l) + e.cnt[l]) vs_layer_live = 1;
+      if (vs_layer_live) {
+        bool v32 = vel32(e, s);
+        double vx = DYN(e, MOOG_D_VX, s), vy = DYN(e, MOOG_D_VY, s);
+        double dx = v32 ? f32mul(dt, vx) : dt * vx;
+        double dy = v32 ? f32mul(dt, vy) : dt * vy;
+        double ox = DYN(e, MOOG_D_X, s), oy = DYN(e, MOOG_D_Y, s);
+        double nx = ox + dx, ny = oy + dy;
+        tx = nx - ox;
+        ty = ny - oy;
+        DYN(e, MOOG_D_X, s) = nx;
+        DYN(e, MOOG_D_Y, s) = ny;
+        if (!(tx == 0.0 && ty == 0.0)) {
+          flag |= TF_MOVE;
+          BOX(e, 0, s) = BOX(e, 0, s) + tx;
+          BOX(e, 1, s) = BOX(e, 1, s) + ty;
+          BOX(e, 2, s) = BOX(e, 2, s) + tx;
+          BOX(e, 3, s) = BOX(e, 3, s) + ty;
+        }
+        double w = DYN(e, MOOG_D_ANGVEL, s);
+        if (w != 0) {  // `if self._angle_vel:` (NaN is truthy)
+          int wk = angvel_kind(e, s), ak = ang_kind(e, s);
+          double t = (wk == KIND_F32) ? f32mul(dt, w) : dt * w;
+          double a = DYN(e, MOOG_D_ANG, s), na;
+          int nk;
+          if (ak == KIND_F64 || wk == KIND_F64) { na = a + t; nk = KIND_F64; }
+          else if (ak == KIND_WEAK && wk == KIND_WEAK) { na = a + t; nk = KIND_WEAK; }
+          else { na = f32add(a, t); nk = KIND_F32; }
+          // sprite.py:531-540: rotate_around(x, y, a_new - a_old) about the NEW position
+          double dth = (nk == KIND_F32 && ak != KIND_F64) ? f32sub(na, a) : na - a;
+          aff_rotate_around(m, nx, ny, dth);
+          DYN(e, MOOG_D_ANG, s) = na;
+          META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (nk << MOOG_SF_ANG_SHIFT);
+          flag |= TF_ROT;
+        }
+        if (!(isfinite(tx) && isfinite(ty))) flag |= TF_CLASSIFY;
+      }
+      if ((flag & TF_ROT) && (e.sflag[s] & SLF_NONFINITE)) flag |= TF_CLASSIFY;
+      e.sflag[s] = (e.sflag[s] & SLF_MASK) | (flag << 8);
+    }
+    // phase 2: one moved slot at a time, lane = vertex of its outline
+    unsigned mv = __ballot_sync(FULL, flag != 0);
+    const unsigned rot = __ballot_sync(FULL, (flag & TF_ROT) != 0);
     while (mv) {
-      const int s = base + __ffs(mv) - 1;
+      const int src = __ffs(mv) - 1;
       mv &= mv - 1;
-      const int flag = e.sflag[s] >> 8;
-      const int n = META(e, MOOG_M_NV, s);
-      double2 *v = e.vtx + e.voff[s];
-      const double tx = TMP(e, 0, s), ty = TMP(e, 1, s);
+      const int s2 = base + src;
+      const int n = META(e, MOOG_M_NV, s2);
+      double2 *v = e.vtx + e.voff[s2];
+      const double ttx = shfl_d(tx, src), tty = shfl_d(ty, src);
+      double x = 0.0, y = 0.0;
       if (e.lane < n) {
         double2 p = v[e.lane];
         // Affine2D().translate(tx, ty): 1.0 * x is exact, the 0.0 * y term keeps the
         // reference's NaN / signed-zero behaviour
-        double x = (p.x + 0.0 * p.y) + tx;
-        double y = (0.0 * p.x + p.y) + ty;
-        if (flag & TF_ROT) {
-          double rx = TMP(e, 2, s) * x + TMP(e, 3, s) * y + TMP(e, 4, s);
-          double ry = TMP(e, 5, s) * x + TMP(e, 6, s) * y + TMP(e, 7, s);
-          x = rx;
-          y = ry;
-        }
-        v[e.lane] = make_double2(x, y);
+        x = (p.x + 0.0 * p.y) + ttx;
+        y = (0.0 * p.x + p.y) + tty;
       }
+      if ((rot >> src) & 1u) {
+        const double r0 = shfl_d(m.m0, src), r1 = shfl_d(m.m1, src), r2 = shfl_d(m.m2, src);
+        const double r3 = shfl_d(m.m3, src), r4 = shfl_d(m.m4, src), r5 = shfl_d(m.m5, src);
+        const double rx = r0 * x + r1 * y + r2;
+        const double ry = r3 * x + r4 * y + r5;
+        x = rx;
+        y = ry;
+      }
+      if (e.lane < n) v[e.lane] = make_double2(x, y);
     }
   }
   wsync();
@@ -1740,7 +1835,11 @@ __device__ inline double *attr_ptr(const Env &e, int s, int at) {
 
 __device__ inline double py_fmod(double a, double b) {
   double r = fmod(a, b);
-  if (r != 0 && ((r < 0) != (b < 0))) r += b;
+  if (r != 0) {
+    if ((r < 0) != (b < 0)) r += b;
+  } else {
+    r = copysign(0.0, b);  // CPython float_rem / numpy remainder
+  }
   return r;
 }
 
@@ -1758,6 +1857,11 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
       case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
       case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
       case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      case MOOG_X_STORE_POS: {
+        const double ny = st[--sp], nx = st[--sp];
+        set_position(e, s0, nx, ny);
+        break;
+      }
       case MOOG_X_STORE: {
         double v = st[--sp];
         wsync();
@@ -1789,7 +1893,7 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
   return sp ? st[sp - 1] : 1.0;
 }
 
-__device__ __noinline__ double eval_condition(const Env &, int op_index) {
+__device__ __noinline__ double eval_condition_leaf(const Env &, int op_index) {
   const Env e = env_view();
   const moog_op *op = e.ops + op_index;
   switch (op->kind) {
@@ -1828,6 +1932,67 @@ __device__ __noinline__ double eval_condition(const Env &, int op_index) {
     }
   }
   return 0;
+}
+
+
+// MOOG_SC_BINARY / MOOG_SC_NOT nodes over the leaves above, evaluated with an explicit
+// stack (no device recursion); the compiler bounds the nesting at MOOG_MAX_SC_DEPTH
+#define MOOG_MAX_SC_DEPTH 8
+__device__ __noinline__ double eval_condition(const Env &, int op_index) {
+  const Env e = env_view();
+  int idx[MOOG_MAX_SC_DEPTH], stage[MOOG_MAX_SC_DEPTH];
+  double lhs[MOOG_MAX_SC_DEPTH];
+  int sp = 1;
+  double ret = 0.0;
+  idx[0] = op_index;
+  stage[0] = 0;
+  while (sp > 0) {
+    const moog_op *op = e.ops + idx[sp - 1];
+    const int st = stage[sp - 1];
+    if (op->kind == MOOG_SC_NOT) {
+      if (st == 0 && sp < MOOG_MAX_SC_DEPTH) {
+        stage[sp - 1] = 1;
+        idx[sp] = op->i[0]; stage[sp] = 0; ++sp;
+      } else {
+        ret = !(ret != 0);
+        --sp;
+      }
+    } else if (op->kind == MOOG_SC_BINARY) {
+      const int x = op->i[2];
+      if (st == 0 && sp < MOOG_MAX_SC_DEPTH) {
+        stage[sp - 1] = 1;
+        idx[sp] = op->i[0]; stage[sp] = 0; ++sp;
+      } else if (st == 1) {
+        const double a = ret;
+        if ((x == MOOG_X_AND && !(a != 0)) || (x == MOOG_X_OR && a != 0)) {
+          --sp;  // python and / or: the deciding operand is the value
+        } else {
+          lhs[sp - 1] = a;
+          stage[sp - 1] = 2;
+          idx[sp] = op->i[1]; stage[sp] = 0; ++sp;
+        }
+      } else {
+        const double a = lhs[sp - 1], b = ret;
+        switch (x) {
+          case MOOG_X_LT: ret = a < b; break;
+          case MOOG_X_LE: ret = a <= b; break;
+          case MOOG_X_GT: ret = a > b; break;
+          case MOOG_X_GE: ret = a >= b; break;
+          case MOOG_X_EQ: ret = a == b; break;
+          case MOOG_X_NE: ret = a != b; break;
+          case MOOG_X_ADD: ret = a + b; break;
+          case MOOG_X_SUB: ret = a - b; break;
+          case MOOG_X_MUL: ret = a * b; break;
+          default: ret = b; break;  // and / or: the right operand decided
+        }
+        --sp;
+      }
+    } else {
+      ret = eval_condition_leaf(e, idx[sp - 1]);
+      --sp;
+    }
+  }
+  return ret;
 }
 
 // ---------------------------------------------------------------------------
@@ -2170,14 +2335,30 @@ __device__ inline void post_reset(const Env &e) {
 // CTA-uniform offset from the dynamic shared-memory base, and the program's
 // dimensions arrive in the parameter bank, so address arithmetic stays on the
 // uniform datapath instead of occupying vector registers.
-__global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
-  if ((int)blockIdx.x >= a.n_envs) return;
+  const int lane = threadIdx.x & 31;
+  if ((int)blockIdx.x >= a.count) return;
+  if (threadIdx.x >= 32) {
+    // Helper warp (launched when the step is bound by its longest-running env and the SMs
+    // have registers to spare): sleeps on a named barrier until the owner posts a request,
+    // runs one direction of _get_collision_vectors (collisions.py:268-283: the two directed
+    // computations are independent) on the env's shared-memory record, posts the result.
+    for (;;) {
+      cta_bar(1);
+      const Env e = env_view();
+      const int *req = (const int *)e.xchg;
+      if (req[0] == HELPER_EXIT) return;
+      CVec out;
+      directed_collision_vectors(e, req[1], req[2], 1.0 / e.K, out);
+      if (e.lane == 0) *(CVec *)(e.xchg + 16) = out;
+      cta_bar(2);
+    }
+  }
   // CTAs are dispatched in blockIdx order: with `order` the envs that were the most
   // expensive on the previous call go first, so the longest-running env does not
   // start in the last wave (longest-processing-time-first)
-  const int n = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+  const int n = a.order ? a.order[a.first + blockIdx.x] : a.first + (int)blockIdx.x;
   const long long t_begin = clock64();
 
   ProgramView pv = view_of(a.blob);
@@ -2297,6 +2478,10 @@ __global__ void __launch_bounds__(32) moog_step_kernel(const StepArgs a) {
     }
   }
   wsync();
+  if (blockDim.x == 64) {  // release the helper warp
+    if (lane == 0) ((int *)e.xchg)[0] = HELPER_EXIT;
+    cta_bar(1);
+  }
   if (a.mode != MODE_OVERLAP) store_env(e, a.st, (size_t)n);
   if (lane == 0) {
     if (a.cost) {
@@ -2368,26 +2553,47 @@ cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream
   return cudaGetLastError();
 }
 
-cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches) {
-  if (a.n_envs <= 0) return cudaSuccess;
+cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches, int first,
+                        int count, int resident_envs_per_sm, bool helper) {
+  if (count < 0) count = a.n_envs - first;
+  if (a.n_envs <= 0 || count <= 0) return cudaSuccess;
   int per_env = env_smem_bytes(hdr);
   const int warps = 1;
   size_t smem = (size_t)per_env * warps;
+  {
+    // Resident CTAs (= envs) per SM.  The step is bound by its longest-running env, and a
+    // warp runs ~2.4x slower next to 11 others than alone (profiles/README.md), so beyond
+    // the point where every SM has work, fewer co-resident envs finish the step sooner.  The
+    // dynamic shared-memory request is padded to cap the residency (MOOG_CTAS_PER_SM
+    // overrides; MOOG_SMEM_PAD=<bytes> pads directly).
+    static const char *pad = getenv("MOOG_SMEM_PAD");
+    static const char *cps = getenv("MOOG_CTAS_PER_SM");
+    int target = cps ? atoi(cps) : resident_envs_per_sm;
+    if (pad) {
+      smem += (size_t)atoi(pad);
+    } else if (target > 0) {
+      size_t per_cta = (size_t)233472 / (size_t)target;  // 228 KB per SM, 1 KB of it reserved per CTA
+      if (per_cta > 1024 + smem) smem = ((per_cta - 1024) & ~(size_t)127);
+      if (smem > 227 * 1024) smem = 227 * 1024;
+    }
+  }
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(moog_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  int blocks = (a.n_envs + warps - 1) / warps;
+  int blocks = count;
   StepArgs b = a;
+  b.first = first;
+  b.count = count;
   b.S = hdr[MOOG_H_N_SLOTS];
   b.L = hdr[MOOG_H_N_LAYERS];
   b.K = hdr[MOOG_H_K];
   b.VT = hdr[MOOG_H_N_VTX];
   b.NF = hdr[MOOG_H_N_ENVF];
   b.CMW = hdr[MOOG_H_CMASK_WORDS];
-  moog_step_kernel<<<blocks, warps * 32, smem, stream>>>(b);
+  moog_step_kernel<<<blocks, helper ? 64 : 32, smem, stream>>>(b);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

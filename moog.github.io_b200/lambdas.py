@@ -24,8 +24,8 @@ import inspect
 import textwrap
 
 (X_END, X_CONST, X_ATTR0, X_ATTR1, X_LT, X_LE, X_GT, X_GE, X_EQ, X_NE, X_AND,
- X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE) = \
-    range(21)
+ X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE,
+ X_STORE_POS) = range(22)
 
 ATTRS = ('x', 'y', 'x_vel', 'y_vel', 'angle', 'angle_vel', 'mass', 'scale',
          'aspect_ratio', 'c0', 'c1', 'c2', 'opacity')
@@ -119,6 +119,9 @@ class SymSprite(object):
     def __setattr__(self, name, value):
         if self._stores is None:
             raise LoweringError('this callable may not modify sprites')
+        if name == 'position':
+            self._stores.append(('position', (Sym.lift(value[0]), Sym.lift(value[1]))))
+            return
         if name == 'velocity':
             self._stores.append(('x_vel', Sym.lift(value[0])))
             self._stores.append(('y_vel', Sym.lift(value[1])))
@@ -200,6 +203,9 @@ def compile_modifier(fn):
     fn(SymSprite(0, stores))
     code = []
     for name, value in stores:
+        if name == 'position':
+            code += value[0].code + value[1].code + [(X_STORE_POS, 0, 0.0)]
+            continue
         code += value.code + [(X_STORE, ATTRS.index(name), 0.0)]
     # Leave a value on the stack so the VM has a defined result.
     return code + [(X_CONST, 0, 1.0)]
@@ -355,7 +361,42 @@ class _StateLowering(object):
         if isinstance(node, ast.Constant) and isinstance(
                 node.value, (bool, int, float)):
             return ('const', float(node.value))
+        # comparisons / not / and / or / + - * over the forms above
+        SC_BINARY, SC_NOT = 166, 167
+        if isinstance(node, ast.Compare) and len(node.ops) == 1:
+            x = {ast.Lt: X_LT, ast.LtE: X_LE, ast.Gt: X_GT, ast.GtE: X_GE,
+                 ast.Eq: X_EQ, ast.NotEq: X_NE}.get(type(node.ops[0]))
+            if x is not None:
+                a = self._as_op(self.lower(node.left))
+                b = self._as_op(self.lower(node.comparators[0]))
+                return ('op', prog.emit(SC_BINARY, 0, (a, b, x)))
+        if isinstance(node, ast.BoolOp):
+            x = X_AND if isinstance(node.op, ast.And) else X_OR
+            acc = self._as_op(self.lower(node.values[0]))
+            for v in node.values[1:]:
+                acc = prog.emit(SC_BINARY, 0,
+                                (acc, self._as_op(self.lower(v)), x))
+            return ('op', acc)
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, ast.Not):
+            return ('op', prog.emit(
+                SC_NOT, 0, (self._as_op(self.lower(node.operand)),)))
+        if isinstance(node, ast.BinOp):
+            x = {ast.Add: X_ADD, ast.Sub: X_SUB, ast.Mult: X_MUL}.get(
+                type(node.op))
+            if x is not None:
+                a = self._as_op(self.lower(node.left))
+                b = self._as_op(self.lower(node.right))
+                return ('op', prog.emit(SC_BINARY, 0, (a, b, x)))
+        if isinstance(node, ast.Name) and node.id in self.ns and isinstance(
+                self.ns[node.id], (bool, int, float)):
+            return ('const', float(self.ns[node.id]))
         self.fail(node)
+
+    def _as_op(self, lowered):
+        kind, value = lowered
+        if kind == 'const':
+            return self.prog.emit(165, 0, (), (value,))  # MOOG_SC_CONST
+        return value
 
     # -- helpers of shipped configs that cannot be traced (data-dependent
     #    Python control flow) and have a declarative device equivalent ---------

@@ -66,6 +66,10 @@ SCENES = {
     # ContactReward with a pair condition, Composite of 3 Joysticks; the agents are
     # steered towards fruits / fountains so that the rules actually fire
     'cleanup': ('moog_demos.example_configs.cleanup', None, 6, 150, 25),
+    # TorusGeometry renderer (9 copies per sprite), ModifySprites assigning `position`
+    # (np.remainder wrap), ConstantSpeed, RandomForce, Joystick(control_velocity),
+    # Reset on `len(state['prey']) == 0`; the agent chases the prey so that it vanishes
+    'chase_avoid_torus': ('moog_demos.example_configs.chase_avoid_torus', 0, 7, 120, 5),
 }
 
 
@@ -93,6 +97,18 @@ def _seek_action(env, t):
         n = float(np.linalg.norm(d))
         act[name] = d / n if n > 0 else np.zeros(2)   # float64, like random_action()
     return act
+
+
+def _chase_action(env, t):
+    """chase_avoid_torus: full stick towards the first prey (away from it every
+    fourth step, so that the path crosses the arena edge)."""
+    a = env.state['agent'][0]
+    if not env.state['prey']:
+        return np.zeros(2)
+    d = np.array(env.state['prey'][0].position) - np.array(a.position)
+    n = float(np.linalg.norm(d))
+    d = d / n if n > 0 else np.zeros(2)
+    return -d if t % 4 == 3 else d
 
 
 def _slot_map(prog, state):
@@ -195,7 +211,12 @@ def generate(name, out_dir):
             aa_frames[aa].append(np.asarray(r(env.state)))
     K, nd = prog.K, prog.noise_dim
     for t in range(T):
-        action = _seek_action(env, t) if name == 'cleanup' else env.action_space.random_action()
+        if name == 'cleanup':
+            action = _seek_action(env, t)
+        elif name == 'chase_avoid_torus':
+            action = _chase_action(env, t)
+        else:
+            action = env.action_space.random_action()
         flat = _flat_action(prog, action)
         slots = _slot_map(prog, env.state)
         del draws[:]

@@ -976,6 +976,21 @@ static void corrective(env_t *e, const moog_op *op) {
       int n = gather_layers(e, op->i[0], op->i[1], sp);
       for (int i = 0; i < n; ++i) {
         double vx = DYN(e, MOOG_D_VX, sp[i]), vy = DYN(e, MOOG_D_VY, sp[i]);
+        if (vel32(e, sp[i])) {
+          /* a float32 velocity array: np.linalg.norm is sqrt(x.dot(x)) in float32 (the two
+           * products and the sum each rounded to float32, no fma), and
+           * `speed * velocity / norm` stays float32 (the python float is a weak scalar) */
+          float fx = (float)vx, fy = (float)vy;
+          float xx = fx * fx, yy = fy * fy;
+          float nf = sqrtf(xx + yy);
+          if (nf != 0) {
+            float sp32 = (float)op->p[0];
+            float ax = sp32 * fx, ay = sp32 * fy;
+            assign_velocity(e, sp[i], (double)(ax / nf), (double)(ay / nf));
+            META(e, MOOG_M_FLAGS, sp[i]) |= MOOG_SF_VEL32;
+          }
+          continue;
+        }
         double nv = norm1(vx, vy);
         if (nv != 0) { /* NaN is truthy in Python, and NaN != 0 here too */
           assign_velocity(e, sp[i], op->p[0] * vx / nv, op->p[0] * vy / nv);
@@ -1056,7 +1071,11 @@ static double *attr_ptr(env_t *e, int s, int at) {
 
 static double py_fmod(double a, double b) {
   double r = fmod(a, b);
-  if (r != 0 && ((r < 0) != (b < 0))) r += b;
+  if (r != 0) {
+    if ((r < 0) != (b < 0)) r += b;
+  } else {
+    r = copysign(0.0, b); /* CPython float_rem / numpy remainder */
+  }
   return r;
 }
 
@@ -1075,6 +1094,11 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
       case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
       case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
       case MOOG_X_STORE: *attr_ptr(e, s0, x->arg) = st[--sp]; break;
+      case MOOG_X_STORE_POS: {
+        double ny = st[--sp], nx = st[--sp];
+        set_position(e, s0, nx, ny);
+        break;
+      }
       default:
         b = st[--sp];
         a = st[--sp];
@@ -1133,6 +1157,25 @@ static double eval_condition(env_t *e, int op_index) {
       }
       return cnt;
     }
+    case MOOG_SC_BINARY: {
+      double a = eval_condition(e, op->i[0]);
+      if (op->i[2] == MOOG_X_AND) return a != 0 ? eval_condition(e, op->i[1]) : a;
+      if (op->i[2] == MOOG_X_OR) return a != 0 ? a : eval_condition(e, op->i[1]);
+      double b = eval_condition(e, op->i[1]);
+      switch (op->i[2]) {
+        case MOOG_X_LT: return a < b;
+        case MOOG_X_LE: return a <= b;
+        case MOOG_X_GT: return a > b;
+        case MOOG_X_GE: return a >= b;
+        case MOOG_X_EQ: return a == b;
+        case MOOG_X_NE: return a != b;
+        case MOOG_X_ADD: return a + b;
+        case MOOG_X_SUB: return a - b;
+        case MOOG_X_MUL: return a * b;
+      }
+      return 0;
+    }
+    case MOOG_SC_NOT: return !(eval_condition(e, op->i[0]) != 0);
   }
   return 0;
 }

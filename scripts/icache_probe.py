@@ -1,0 +1,19 @@
+"""MOOG_PROFILE_ICACHE build: cycles of a directed_collision_vectors call vs the same call repeated."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from moog_b200.batched_env import BatchedEnvironment
+E = 4096
+cfg = bench._scene_config('falling_balls20')
+states = bench._host_states(cfg, 256, 1234)
+env = BatchedEnvironment(**cfg, num_envs=E, device='cuda:0', seed=1234, initial_states=states)
+eng = env.engine
+act = torch.zeros((E, env.action_dim), dtype=torch.float64, device='cuda:0')
+env.reset()
+for t in range(45):
+    eng.env_step(act)
+eng.env_step(act, want_counters=True); torch.cuda.synchronize()
+c = eng.counters.cpu().numpy().astype(np.float64)
+n = c[:, 5].sum()
+print('pairs %d  first call %.0f cycles, repeated call %.0f cycles (mean per call)' % (n, c[:, 6].sum() / n, c[:, 7].sum() / n))

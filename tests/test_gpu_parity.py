@@ -88,11 +88,15 @@ def test_cuda_follows_reference_trajectory(scene):
             eng.state.upload(st)
 
 
+@pytest.mark.parametrize('helper', ['1', '0'])
 @pytest.mark.parametrize('scene', util.SCENES)
-def test_cuda_matches_oracle_batched(scene):
+def test_cuda_matches_oracle_batched(scene, helper, monkeypatch):
     """Every state of the golden trajectory becomes one env of a batch; CUDA and
-    the oracle advance the batch 3 steps with the same seeded actions / noise."""
+    the oracle advance the batch 3 steps with the same seeded actions / noise.
+    Run with and without the helper warp (second direction of
+    _get_collision_vectors computed next to the owner warp)."""
     from oracle.oracle import Oracle
+    monkeypatch.setenv('MOOG_HELPER', helper)
     g = util.load_golden(scene)
     prog = g['program']
     T = len(g['reward'])
