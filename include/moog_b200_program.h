@@ -96,6 +96,7 @@ enum {
 #define MOOG_ERR_DISJOINT_LOOP   2u  /* collisions.py:740 loop would not end     */
 #define MOOG_ERR_TETHER_ZIP      4u  /* tether_physics.py:192-196 ValueError     */
 #define MOOG_ERR_LAYER_OVERFLOW  8u  /* layer capacity exceeded                  */
+#define MOOG_ERR_OFF_MAZE_GRID   16u /* maze_physics.py:93-104 ValueError (sprite not on the maze grid) */
 
 /* header words */
 #define MOOG_HDR_WORDS 64
@@ -138,11 +139,17 @@ enum {
   MOOG_F_DIST_LINEAR,       /* p0 intercept p1 slope p2 horizon  distance_fn_force.py:48-74 */
   MOOG_F_DIST_SPRING,       /* p0 k p1 equilibrium distance_fn_force.py:77-89 */
   MOOG_F_COLLISION,         /* p0 elasticity; i[2] max_recursion  collisions.py:494-584 */
+  MOOG_F_MAZE_WALK,         /* RandomMazeWalk: p0 speed; i[2] noise column (4 per sprite of the layer's
+                               capacity: np.random.rand(2, 2)); i[3] envf offset of the maze record;
+                               flags PREVENT_BACKTRACKING / ALLOW_WALL_BACKTRACKING / ONLY_TURN_AT_WALL
+                               maze_walk.py:97-196 */
 
   /* corrective physics: i[0]=ipool start of layer list, i[1]=count */
   MOOG_C_TETHER = 32,       /* p0,p1 anchor        tether_physics.py:126-140  */
   MOOG_C_TETHER_ZIPPED,     /*                     tether_physics.py:186-201  */
   MOOG_C_CONSTANT_SPEED,    /* p0 speed            constant_speed.py:34-46    */
+  MOOG_C_MAZE_PHYSICS,      /* i0,i1 avatar layer list; i[2] envf offset of the maze record; p0 constant_speed,
+                               p1 max_speed (NaN = None)   maze_physics.py:19-211 */
 
   /* rules */
   MOOG_R_VANISH_ON_CONTACT = 64, /* i0 vanishing layer, i1 contacting layer  vanish.py:66-86 */
@@ -174,7 +181,9 @@ enum {
                               MOOG_X_OR follow Python: the right operand is only evaluated when needed
                               (matters for the overlap calls a contact count makes) and the value is
                               that of the deciding operand */
-  MOOG_SC_NOT              /* i0 operand condition op: python `not`             */
+  MOOG_SC_NOT,             /* i0 operand condition op: python `not`             */
+  MOOG_SC_FIRST            /* i0,i1 layer list; i2 sprite expr evaluated on the FIRST sprite of the list
+                              (`state[layer][0]`); 0 when the list is empty      */
 };
 
 /* op flags */
@@ -186,6 +195,15 @@ enum {
 #define MOOG_FL_CONSTRAINED_LR   32
 #define MOOG_FL_CONTROL_VELOCITY 64
 #define MOOG_FL_SAMPLE_ONE       128
+#define MOOG_FL_PREVENT_BACKTRACKING    256
+#define MOOG_FL_ALLOW_WALL_BACKTRACKING 512
+#define MOOG_FL_ONLY_TURN_AT_WALL       1024
+
+/* Maze record in envf (maze_lib/maze.py:20-35, Maze.from_state :38-84, evaluated by the host when
+ * a state is packed -- the wall sprites never move): [0] = maze_size N (<= MOOG_MAX_MAZE),
+ * [1 + j] = row j as an integer whose bit i is maze[j, i] (1 = wall). */
+#define MOOG_MAX_MAZE 32
+#define MOOG_MAZE_WORDS (1 + MOOG_MAX_MAZE)
 
 /* expression VM ------------------------------------------------------------ */
 typedef struct {

@@ -51,14 +51,14 @@ H_LAYER_OFF = 32
 H_N_VTX = 49
 
 F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
-    F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION = range(1, 9)
-C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED = 32, 33, 34
+    F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION, F_MAZE_WALK = range(1, 10)
+C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED, C_MAZE_PHYSICS = 32, 33, 34, 35
 R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
     R_MODIFY_SPRITES, R_COND_BEGIN = 64, 65, 66, 67, 68
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
-    SC_BINARY, SC_NOT = 160, 161, 162, 163, 164, 165, 166, 167
+    SC_BINARY, SC_NOT, SC_FIRST = 160, 161, 162, 163, 164, 165, 166, 167, 168
 
 FL_SYMMETRIC = 1
 FL_UPDATE_ANGLE_VEL = 2
@@ -68,6 +68,9 @@ FL_HAS_ANCHOR = 16
 FL_CONSTRAINED_LR = 32
 FL_CONTROL_VELOCITY = 64
 FL_SAMPLE_ONE = 128
+FL_PREVENT_BACKTRACKING = 256
+FL_ALLOW_WALL_BACKTRACKING = 512
+FL_ONLY_TURN_AT_WALL = 1024
 
 CMAP_NONE, CMAP_HSV = 0, 1
 PMOD_NONE, PMOD_FIRST_PERSON, PMOD_TORUS = 0, 1, 2
@@ -102,6 +105,7 @@ class Program(object):
         self.expr = []           # list of (op, arg, c)
         self.sections = {}
         self.n_envf = 0
+        self.maze_offsets = {}   # maze layer name -> envf offset of its maze record
         self.action_dim = 0
         self.action_layout = []  # (key or None, kind, offset, width)
         self.noise_dim = 0
@@ -139,6 +143,14 @@ class Program(object):
         self.expr.extend(code)
         self.expr.append((lambdas.X_END, 0, 0.0))
         return start
+
+    def maze_record(self, layer):
+        """envf offset of the maze record of `layer` (host_maze.maze_record)."""
+        from . import host_maze
+        if layer not in self.maze_offsets:
+            self.layer_index(layer)
+            self.maze_offsets[layer] = self.alloc_envf(host_maze.MAZE_WORDS)
+        return self.maze_offsets[layer]
 
     def alloc_envf(self, n):
         start = self.n_envf
@@ -251,7 +263,7 @@ def _emit_force(prog, force, layers):
     lb = prog.layer_index(layers[1]) if len(layers) > 1 else -1
     arity = {'Drag': 1, 'KineticFriction': 1, 'DownGravity': 1,
              'RandomForce': 1, 'Gravity': 2, 'DistanceForce': 2,
-             'Collision': 2}.get(k)
+             'Collision': 2, 'RandomMazeWalk': 1}.get(k)
     if arity is None:
         raise CompileError('unsupported force {}'.format(k))
     if arity != len(layers):
@@ -267,6 +279,16 @@ def _emit_force(prog, force, layers):
         col = prog.noise_dim
         prog.noise_dim += 2 * prog.layer_cap[la]
         prog.emit(F_RANDOM, 0, (la, -1, col), (force._max_force_magnitude,))
+    elif k == 'RandomMazeWalk':
+        # maze_walk.py:97-196; np.random.rand(2, 2) -> 4 noise columns per sprite
+        col = prog.noise_dim
+        prog.noise_dim += 4 * prog.layer_cap[la]
+        fl = (FL_PREVENT_BACKTRACKING if force._prevent_backtracking else 0) | (
+            FL_ALLOW_WALL_BACKTRACKING if force._allow_wall_backtracking else 0) | (
+            FL_ONLY_TURN_AT_WALL if force._only_turn_at_wall else 0)
+        prog.emit(F_MAZE_WALK, fl,
+                  (la, -1, col, prog.maze_record(force._maze_layer)),
+                  (float(force._speed),))
     elif k == 'Gravity':
         prog.emit(F_GRAVITY, FL_SYMMETRIC if force._symmetric else 0,
                   (la, lb), (force._g,))
@@ -316,6 +338,15 @@ def _compile_physics(prog, physics):
         elif ck == 'ConstantSpeed':
             ls, ln = prog.add_list(cp._layer_names)
             prog.emit(C_CONSTANT_SPEED, 0, (ls, ln), (cp._speed,))
+        elif ck == 'MazePhysics':
+            # maze_physics.py:19-211 (its own updates_per_env_step must be 1)
+            if prog.K != 1:
+                raise CompileError('MazePhysics needs updates_per_env_step == 1 (maze_physics.py:207-208)')
+            ls, ln = prog.add_list(list(cp._avatar_layers))
+            none = float('nan')
+            prog.emit(C_MAZE_PHYSICS, 0, (ls, ln, prog.maze_record(cp._maze_layer)),
+                      (none if cp._constant_speed is None else float(cp._constant_speed),
+                       none if cp._max_speed is None else float(cp._max_speed)))
         else:
             raise CompileError(
                 'corrective physics {} is not on the accelerated path'
@@ -708,6 +739,11 @@ def pack_states(prog, states, shape_table=None):
                 vtx[e, prog.voff[s]:prog.voff[s] + len(world)] = world
     envi = np.zeros((n, ENVI_WORDS), dtype=np.int32)
     envf = np.zeros((n, max(prog.n_envf, 1)))
+    if prog.maze_offsets:
+        from . import host_maze
+        for e, st in enumerate(states):
+            for layer, off in prog.maze_offsets.items():
+                envf[e, off:off + host_maze.MAZE_WORDS] = host_maze.maze_record(st[layer])
     shape_verts, shape_nv = table.arrays()
     return dict(dyn=dyn, stat=stat, meta=meta, vtx=vtx, cnt=cnt, envi=envi,
                 envf=envf, shape_verts=shape_verts, shape_nv=shape_nv,

@@ -127,8 +127,9 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   }
   // The step ends when its longest-running env does, and a warp runs ~2.4x slower next to 11
   // others than alone (profiles/README.md): with the envs dispatched longest-first, capping
-  // the envs resident per SM at about n_envs / (9 x SMs) -- nine waves -- finishes the step
-  // sooner than filling the SMs (4096 envs on 148 SMs: 3 per SM, 5.5 ms instead of 6.1 ms).
+  // the envs resident per SM at about n_envs / (7 x SMs) -- seven waves -- finishes the step
+  // sooner than filling the SMs (4096 envs on 148 SMs: 4 per SM; measured 3: 4.93 ms,
+  // 4: 4.77 ms, 12: 5.6 ms with the helper warp).
   // In that regime the SMs have registers to spare, and every env gets a helper warp that
   // computes one of the two directions of _get_collision_vectors (MOOG_HELPER=0/1 overrides).
   int resident = 0;
@@ -138,7 +139,7 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > 0) {
-      resident = (n_envs + 9 * sms / 2) / (9 * sms);
+      resident = (n_envs + 7 * sms / 2) / (7 * sms);
       if (resident < 2) resident = 2;
       helper = resident <= 6;
     }

@@ -1603,9 +1603,291 @@ __device__ inline void tether_sprites(const Env &e, Pick pick, int n, bool updat
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// maze_lib.Maze, RandomMazeWalk, MazePhysics.  Per-sprite scalar logic on values every
+// lane reads from shared memory: all lanes compute the same thing, lane 0 stores.
+// ---------------------------------------------------------------------------
+#define MAZE_EPS 1e-5 /* maze_physics.py:15, maze_walk.py:14 */
+
+struct MazeV { int n; const double *rows; double grid, half; };
+
+__device__ __forceinline__ MazeV maze_of(const Env &e, int off) {
+  MazeV m;
+  m.n = (int)e.envf[off];
+  m.rows = e.envf + off + 1;
+  m.grid = 1. / m.n;      // maze.py:32
+  m.half = 0.5 * m.grid;  // maze.py:33
+  return m;
+}
+// maze.py:113-118
+__device__ __forceinline__ double maze_open(const MazeV &m, int i, int j) {
+  if (i < 0 || j < 0 || i >= m.n || j >= m.n) return 0.0;
+  return (((unsigned long long)m.rows[j] >> i) & 1ull) ? 0.0 : 1.0;
+}
+// maze.py:120-126: v[2 * axis + dir]
+__device__ inline void maze_valid(const MazeV &m, int i, int j, double *v) {
+  v[0] = maze_open(m, i - 1, j); v[1] = maze_open(m, i + 1, j);
+  v[2] = maze_open(m, i, j - 1); v[3] = maze_open(m, i, j + 1);
+}
+// numpy floor_divide for doubles (npy_divmod)
+__device__ inline double np_floor_divide(double a, double b) {
+  if (b == 0) return a / b;
+  double mod = fmod(a, b);
+  double div = (a - mod) / b;
+  if (mod != 0) {
+    if ((b < 0) != (mod < 0)) div -= 1.0;
+  }
+  double fl;
+  if (div != 0) {
+    fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+  } else {
+    fl = copysign(0.0, a / b);
+  }
+  return fl;
+}
+
+// maze_walk.py:159-196 RandomMazeWalk._step_sprite (+ _get_pos_vel :46-79, _update_valid_directions :122-157)
+__device__ __noinline__ void maze_walk_layer(const Env &, const moog_op *op) {
+  const Env e = env_view();
+  const int la = op->i[0];
+  const MazeV m = maze_of(e, op->i[3]);
+  const double speed = op->p[0];
+  const double K = (double)e.K;
+  for (int idx = 0; idx < e.cnt[la]; ++idx) {
+    const int s = LOFF(e, la) + idx;
+    if (isinf(STAT(e, MOOG_S_MASS, s))) continue;
+    double pos[2] = {DYN(e, MOOG_D_X, s), DYN(e, MOOG_D_Y, s)};
+    double vel[2] = {speed * sign_(DYN(e, MOOG_D_VX, s)), speed * sign_(DYN(e, MOOG_D_VY, s))};
+    double nxt[2] = {pos[0] + vel[0] / K, pos[1] + vel[1] / K};
+    int near_[2];
+    double inter[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      near_[a] = (int)rint(pos[a] / m.grid - 0.5);
+      inter[a] = m.grid * near_[a] + m.half;
+    }
+    const double d_next_cur = fabs(nxt[0] - pos[0]) + fabs(nxt[1] - pos[1]);
+    const double d_int_next = fabs(nxt[0] - inter[0]) + fabs(nxt[1] - inter[1]);
+    const bool entering = d_next_cur > d_int_next;  // the reference compares against the same quantity twice
+    double valid[4];
+    if (entering) {
+      maze_valid(m, near_[0], near_[1], valid);
+      if (op->flags & MOOG_FL_PREVENT_BACKTRACKING) {
+        const int axis = fabs(vel[1]) > fabs(vel[0]) ? 1 : 0;  // np.argmax: first maximum
+        const double direction = sign_(axis ? vel[1] : vel[0]);
+        if (direction != 0) {
+          const int fwd = (int)(0.5 * (1 + direction)), back = (int)(0.5 * (1 - direction));
+          const bool can_continue = valid[2 * axis + fwd] != 0;
+          if (!can_continue && (op->flags & MOOG_FL_ALLOW_WALL_BACKTRACKING)) {
+          } else if (can_continue && (op->flags & MOOG_FL_ONLY_TURN_AT_WALL)) {
+            valid[0] = valid[1] = valid[2] = valid[3] = 0;
+            valid[2 * axis + fwd] = 1;
+          } else {
+            valid[2 * axis + back] = 0;
+          }
+        }
+      }
+    } else if (vel[0] == 0. && vel[1] == 0.) {
+      const bool on0 = fabs((m.half + near_[0] * m.grid) - pos[0]) < MAZE_EPS;
+      const bool on1 = fabs((m.half + near_[1] * m.grid) - pos[1]) < MAZE_EPS;
+      if (on0 && on1) {
+        maze_valid(m, near_[0], near_[1], valid);
+      } else {
+        const int row = 1 - (on0 ? 0 : (on1 ? 1 : 0));  // 1 - np.argmax(on_grid)
+        valid[0] = valid[1] = valid[2] = valid[3] = 0;
+        valid[2 * row] = valid[2 * row + 1] = 1;
+      }
+    } else {
+      assign_velocity(e, s, vel[0], vel[1]);
+      continue;
+    }
+    // sample = valid_directions * np.random.rand(2, 2); argmax of the ravel (first maximum)
+    int best = 0;
+    double bv = valid[0] * noise_at(e, op->i[2] + 4 * idx);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const double v = valid[k] * noise_at(e, op->i[2] + 4 * idx + k);
+      if (v > bv) { bv = v; best = k; }
+    }
+    const double nvv = (1 + MAZE_EPS) * speed * (2 * (best % 2) - 1);
+    if (best / 2 == 0) vel[0] = nvv; else vel[1] = nvv;
+    assign_velocity(e, s, vel[0], vel[1]);
+  }
+}
+
+// maze_physics.py:51-112 _get_position_affordances -> aff[2 * axis + dir]; false when off the grid
+__device__ inline bool maze_affordances(const MazeV &m, double p0, double p1, double *aff) {
+  int near_[2], inds[2];
+  bool on[2];
+  const double pos[2] = {p0, p1};
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    near_[a] = (int)rint(pos[a] / m.grid - 0.5);
+    const double rounded = m.half + near_[a] * m.grid;
+    on[a] = fabs(rounded - pos[a]) < MAZE_EPS;
+    inds[a] = (int)np_floor_divide(pos[a] - m.half, m.grid);
+    if (on[a]) inds[a] = near_[a];
+  }
+  aff[0] = aff[1] = aff[2] = aff[3] = 0;
+  if (!on[0] && !on[1]) return false;
+  if (on[0] && on[1]) {
+    double v[4];
+    maze_valid(m, inds[0], inds[1], v);
+    aff[0] = v[0] * m.grid * -1.; aff[1] = v[1] * m.grid * 1.;
+    aff[2] = v[2] * m.grid * -1.; aff[3] = v[3] * m.grid * 1.;
+  } else {
+    const int i = on[0] ? 1 : 0;
+    const double pi_ = i ? p1 : p0;
+    aff[2 * i] = inds[i] * m.grid + m.half - pi_;
+    aff[2 * i + 1] = (inds[i] + 1) * m.grid + m.half - pi_;
+  }
+  return true;
+}
+
+// maze_physics.py:114-167 _get_new_velocity, the recursion unrolled: every vertex the sprite
+// passes pushes the part of the velocity spent on the way there (`velocity *= scaling;
+// velocity[1 - axis] = 0`); the sums `velocity += velocity_post_vertex` are taken innermost first.
+#define MAZE_MAX_VERTICES 6
+__device__ inline bool maze_new_velocity(const MazeV &m, double p0, double p1, double v0, double v1, double *aff0,
+                                         double *out) {
+  double pre[MAZE_MAX_VERTICES][2];
+  int depth = 0;
+  double pos[2] = {p0, p1}, vel[2] = {v0, v1};
+  double aff[4] = {aff0[0], aff0[1], aff0[2], aff0[3]};
+  double r0 = 0, r1 = 0;
+  int axis = -1;
+  for (int guard = 0; guard < 4 * MAZE_MAX_VERTICES; ++guard) {
+    if (axis < 0) axis = fabs(vel[1]) > fabs(vel[0]) ? 1 : 0;
+    const double va = axis ? vel[1] : vel[0];
+    if (aff[2 * axis] <= va && va <= aff[2 * axis + 1]) {
+      if (axis) vel[0] = 0; else vel[1] = 0;
+      r0 = vel[0]; r1 = vel[1];
+      goto unwind;
+    }
+    int direction = va > 0 ? 1 : 0;  // int(0.5 + 0.5 * sign)
+    if (aff[2 * axis + direction] == 0) {
+      axis = 1 - axis;
+      const double vb = axis ? vel[1] : vel[0];
+      direction = vb > 0 ? 1 : 0;
+      if (aff[2 * axis + direction] == 0 || vb == 0) {
+        r0 = r1 = 0.;
+        goto unwind;
+      }
+      continue;  // _get_new_velocity(position, velocity, affordances, axis=axis)
+    }
+    if (depth >= MAZE_MAX_VERTICES) return false;
+    const double step = aff[2 * axis + direction];
+    if (axis) pos[1] += step; else pos[0] += step;
+    double vaff[4];
+    if (!maze_affordances(m, pos[0], pos[1], vaff)) return false;
+    const double scaling = step / va;
+    const double rem0 = (1. - scaling) * vel[0], rem1 = (1. - scaling) * vel[1];
+    vel[0] *= scaling; vel[1] *= scaling;
+    if (axis) vel[0] = 0; else vel[1] = 0;
+    pre[depth][0] = vel[0]; pre[depth][1] = vel[1];
+    ++depth;
+    vel[0] = rem0; vel[1] = rem1;
+    aff[0] = vaff[0]; aff[1] = vaff[1]; aff[2] = vaff[2]; aff[3] = vaff[3];
+    axis = -1;
+  }
+  return false;
+unwind:
+  while (depth > 0) {
+    --depth;
+    r0 = pre[depth][0] + r0;
+    r1 = pre[depth][1] + r1;
+  }
+  out[0] = r0; out[1] = r1;
+  return true;
+}
+
+// sprite.py:531-540 angle setter (`sprite.angle = a`, a an np.float64): rotate_around(x, y, a - angle)
+__device__ inline void set_angle_f64(const Env &e, int s, double a) {
+  Aff mtx = aff_identity();
+  aff_rotate_around(mtx, DYN(e, MOOG_D_X, s), DYN(e, MOOG_D_Y, s), a - DYN(e, MOOG_D_ANG, s));
+  const int n = META(e, MOOG_M_NV, s);
+  double2 *v = e.vtx + e.voff[s];
+  wsync();
+  double2 q = make_double2(0., 0.);
+  if (e.lane < n) {
+    const double2 p = v[e.lane];
+    q = make_double2(mtx.m0 * p.x + mtx.m1 * p.y + mtx.m2, mtx.m3 * p.x + mtx.m4 * p.y + mtx.m5);
+    v[e.lane] = q;
+  }
+  // the rotated outline's box and NaN / inf classification
+  const bool act = e.lane < n;
+  const bool fin = !act || (isfinite(q.x) && isfinite(q.y));
+  double xmin = act ? q.x : INFINITY, xmax = act ? q.x : -INFINITY, ymin = act ? q.y : INFINITY, ymax = act ? q.y : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fmin(xmin, shflx_d(xmin, o)); xmax = fmax(xmax, shflx_d(xmax, o));
+    ymin = fmin(ymin, shflx_d(ymin, o)); ymax = fmax(ymax, shflx_d(ymax, o));
+  }
+  const bool nonfinite = !__all_sync(FULL, fin);
+  const bool allnan = n > 0 && __all_sync(FULL, !act || (isnan(q.x) && isnan(q.y)));
+  if (e.lane == 0) {
+    DYN(e, MOOG_D_ANG, s) = a;
+    META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (KIND_F64 << MOOG_SF_ANG_SHIFT);
+    e.sflag[s] = (e.sflag[s] & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite);
+  }
+  wsync();
+}
+
+// maze_physics.py:189-211 _update_sprite_in_maze (+ _update_sprite_angle :169-187) for the avatar layers
+__device__ __noinline__ void maze_physics(const Env &, const moog_op *op) {
+  const Env e = env_view();
+  const MazeV m = maze_of(e, op->i[2]);
+  const int n = list_count(e, op->i[0], op->i[1]);
+  for (int q = 0; q < n; ++q) {
+    const int s = list_slot(e, op->i[0], op->i[1], q);
+    double v0 = DYN(e, MOOG_D_VX, s), v1 = DYN(e, MOOG_D_VY, s);
+    if ((v0 == 0 && v1 == 0) || isnan(v0) || isnan(v1)) continue;
+    if (!isnan(op->p[1])) {  // np.clip(velocity, -max_speed, max_speed)
+      v0 = fmin(fmax(v0, -op->p[1]), op->p[1]);
+      v1 = fmin(fmax(v1, -op->p[1]), op->p[1]);
+    }
+    if (!isnan(op->p[0])) {
+      v0 += sign_(v0); v0 *= op->p[0];
+      v1 += sign_(v1); v1 *= op->p[0];
+    }
+    const double p0 = DYN(e, MOOG_D_X, s), p1 = DYN(e, MOOG_D_Y, s);
+    double aff[4], nv[2];
+    bool ok = maze_affordances(m, p0, p1, aff);
+    if (ok) {
+      set_position(e, s, p0, p1);  // sprite.position = np.copy(position): a translation by exactly zero
+      ok = maze_new_velocity(m, p0, p1, v0, v1, aff, nv);
+    }
+    if (!ok) {
+      const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_OFF_MAZE_GRID;
+      wsync();
+      puti(e, &e.envi[MOOG_EI_ERR], err);
+      wsync();
+      continue;
+    }
+    double new_angle;
+    if (nv[0] == 0 && nv[1] == 0) {
+      new_angle = NAN;
+    } else if (nv[1] == 0) {
+      new_angle = -0.5 * sign_(nv[0]) * M_PI;
+    } else if (sign_(nv[1]) > 0) {
+      new_angle = atan(-nv[0] / nv[1]);
+    } else {
+      new_angle = M_PI + atan(-nv[0] / nv[1]);
+    }
+    if (!isnan(new_angle) && fabs(new_angle - DYN(e, MOOG_D_ANG, s)) > MAZE_EPS) set_angle_f64(e, s, new_angle);
+    assign_velocity(e, s, nv[0], nv[1]);
+  }
+}
+
 __device__ __noinline__ void corrective(const Env &, const moog_op *op) {
   const Env e = env_view();
   switch (op->kind) {
+    case MOOG_C_MAZE_PHYSICS:  // maze_physics.py:205-211
+      maze_physics(e, op);
+      break;
     case MOOG_C_TETHER: {  // tether_physics.py:126-140
       int st = op->i[0], nl = op->i[1];
       int n = list_count(e, st, nl);
@@ -1791,7 +2073,9 @@ __device__ inline void apply_physics(const Env &e, int n_cmask_words) {
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
     const moog_op *op = e.ops + h[MOOG_H_FORCES] + f;
     int la = op->i[0], lb = op->i[1];
-    if (lb < 0) {
+    if (op->kind == MOOG_F_MAZE_WALK) {
+      maze_walk_layer(e, op);
+    } else if (lb < 0) {
       force_unary_layer(e, op);
     } else if (op->kind == MOOG_F_COLLISION) {
       collision_op(e, op, f, n_cmask_words);
@@ -1910,6 +2194,10 @@ __device__ __noinline__ double eval_condition_leaf(const Env &, int op_index) {
       if (op->kind == MOOG_SC_ALL) return cnt == n;
       if (op->kind == MOOG_SC_ANY) return cnt > 0;
       return cnt;
+    }
+    case MOOG_SC_FIRST: {
+      const int n = list_count(e, op->i[0], op->i[1]);
+      return n > 0 ? eval_expr(e, op->i[2], list_slot(e, op->i[0], op->i[1], 0), list_slot(e, op->i[0], op->i[1], 0)) : 0.0;
     }
     case MOOG_SC_CONTACT_COUNT: {  // contact_rules.py:15-51
       int la = op->i[0], lb = op->i[1], cnt = 0;

@@ -133,6 +133,73 @@ class SymSprite(object):
         self._stores.append((name, Sym.lift(value)))
 
 
+class SymVec(object):
+    """A traced 2-vector (`sprite.velocity`, `sprite.position`) inside a state
+    condition: comparisons are elementwise, `np.all` / `np.any` reduce."""
+
+    def __init__(self, elems):
+        self.elems = list(elems)
+
+    def _cmp(self, other, name):
+        others = other.elems if isinstance(other, SymVec) else [other] * len(self.elems)
+        return SymVec([getattr(a, name)(b) for a, b in zip(self.elems, others)])
+
+    def __eq__(self, o): return self._cmp(o, '__eq__')
+    def __ne__(self, o): return self._cmp(o, '__ne__')
+    def __lt__(self, o): return self._cmp(o, '__lt__')
+    def __le__(self, o): return self._cmp(o, '__le__')
+    def __gt__(self, o): return self._cmp(o, '__gt__')
+    def __ge__(self, o): return self._cmp(o, '__ge__')
+    __hash__ = None
+
+    def __getitem__(self, k):
+        return self.elems[k]
+
+    def all(self, *_, **__):       # np.all(vec) dispatches here
+        out = self.elems[0]
+        for x in self.elems[1:]:
+            out = out & x
+        return out
+
+    def any(self, *_, **__):       # np.any(vec)
+        out = self.elems[0]
+        for x in self.elems[1:]:
+            out = out | x
+        return out
+
+
+class _SymFirstSprite(SymSprite):
+    """`state[layer][0]` while tracing a state condition."""
+
+    def __getattr__(self, name):
+        if name == 'position':
+            return SymVec([SymSprite.__getattr__(self, 'x'), SymSprite.__getattr__(self, 'y')])
+        if name == 'velocity':
+            return SymVec([SymSprite.__getattr__(self, 'x_vel'), SymSprite.__getattr__(self, 'y_vel')])
+        return SymSprite.__getattr__(self, name)
+
+
+class _SymLayer(object):
+    def __init__(self, owner, name):
+        self._owner, self._name = owner, name
+
+    def __getitem__(self, k):
+        if k != 0:
+            raise LoweringError('only state[layer][0] can be read in a state condition')
+        self._owner.layers.append(self._name)
+        return _SymFirstSprite(0)
+
+
+class SymState(object):
+    """Stand-in for the environment state while tracing `state[layer][0].attr`."""
+
+    def __init__(self):
+        self.layers = []
+
+    def __getitem__(self, name):
+        return _SymLayer(self, name)
+
+
 def _n_params(fn):
     return len(inspect.signature(fn).parameters)
 
@@ -390,7 +457,32 @@ class _StateLowering(object):
         if isinstance(node, ast.Name) and node.id in self.ns and isinstance(
                 self.ns[node.id], (bool, int, float)):
             return ('const', float(self.ns[node.id]))
+        first = self._trace_first(node)
+        if first is not None:
+            return first
         self.fail(node)
+
+    def _trace_first(self, node):
+        """An expression over `state[layer][0]` (one layer), e.g. pacman.py's
+        `np.all(state['agent'][0].velocity == 0)` -> MOOG_SC_FIRST."""
+        sym_state = SymState()
+        ns = dict(self.ns)
+        ns[self.state_name] = sym_state
+        try:
+            expr = ast.Expression(node)
+            ast.fix_missing_locations(expr)
+            out = eval(compile(expr, '<cond>', 'eval'), ns)  # pylint: disable=eval-used
+        except LoweringError:
+            raise
+        except Exception:  # pylint: disable=broad-except
+            return None
+        if isinstance(out, SymVec):
+            return None
+        layers = set(sym_state.layers)
+        if len(layers) != 1 or not isinstance(out, Sym):
+            return None
+        ls, ln = self.prog.add_list([layers.pop()])
+        return ('op', self.prog.emit(168, 0, (ls, ln, self.prog.add_expr(out.code))))  # MOOG_SC_FIRST
 
     def _as_op(self, lowered):
         kind, value = lowered

@@ -70,6 +70,12 @@ SCENES = {
     # (np.remainder wrap), ConstantSpeed, RandomForce, Joystick(control_velocity),
     # Reset on `len(state['prey']) == 0`; the agent chases the prey so that it vanishes
     'chase_avoid_torus': ('moog_demos.example_configs.chase_avoid_torus', 0, 7, 120, 5),
+    # BASELINE config 4: pacman.get_config(0) with the PILRenderer at 64x64 (BASELINE.json
+    # quotes the maze tasks at 64x64; the shipped 256x256 canvas exceeds one CTA's shared
+    # memory): RandomMazeWalk (np.random.rand(2, 2) recorded as noise), MazePhysics
+    # (constant_speed, turning sprites), Grid(control_velocity), VanishOnContact,
+    # ConditionalRule on `state['agent'][0].velocity`
+    'pacman': ('moog_demos.example_configs.pacman', 0, 12, 120, 10),
 }
 
 
@@ -111,6 +117,13 @@ def _chase_action(env, t):
     return -d if t % 4 == 3 else d
 
 
+def _pacman_action(env, t):
+    """pacman: hold a Grid direction for 6 steps, cycling left, up, right, down,
+    so that the agent runs into walls, turns at intersections and eats prey."""
+    del env
+    return [0, 3, 1, 2][(t // 6) % 4] if t % 23 != 22 else 4
+
+
 def _slot_map(prog, state):
     m = {}
     for l, name in enumerate(prog.layer_names):
@@ -150,6 +163,10 @@ def generate(name, out_dir):
     np.random.seed(seed)
     mod = importlib.import_module(module)
     config = mod.get_config(level)
+    if name == 'pacman':
+        from moog.observers import pil_renderer
+        config['observers'] = {'image': pil_renderer.PILRenderer(
+            image_size=(64, 64), anti_aliasing=1, color_to_rgb='hsv_to_rgb')}
     env = environment.Environment(**config)
 
     # capture the state initializer's output before the reference steps rules
@@ -199,6 +216,39 @@ def generate(name, out_dir):
                 current_rule[0] = None
         r.step = _wrapped
 
+    # RandomMazeWalk (maze_walk.py:185-186): the four np.random.rand(2, 2) uniforms of a
+    # sprite that picks a new direction go to the noise columns [col + 4 k, col + 4 k + 4)
+    # of sprite k of the walking layer
+    walk_draws = {}
+    walkers = []
+    f_maze_walk = compiler.F_MAZE_WALK
+    walk_ops = [o for o in prog.ops if o['kind'] == f_maze_walk]
+    walk_forces = [entry[0] for entry in config['physics']._forces  # pylint: disable=protected-access
+                   if type(entry[0]).__name__ == 'RandomMazeWalk']
+    assert len(walk_ops) == len(walk_forces), 'one layer per RandomMazeWalk entry expected'
+    current_walk = [None]
+    orig_rand = np.random.rand
+
+    def _rand(*shape):
+        if current_walk[0] is None or shape != (2, 2):
+            return orig_rand(*shape)
+        u = np.random.random_sample(4)
+        col, k = current_walk[0]
+        walk_draws[col + 4 * k] = u
+        return u.reshape(2, 2)
+
+    for wf, wo in zip(walk_forces, walk_ops):
+        def _wrapped_walk(sprite_, updates_per_env_step=1, _orig=wf._step_sprite, _op=wo):  # pylint: disable=protected-access
+            layer = prog.layer_names[_op['i'][0]]
+            k = [id(x) for x in env.state[layer]].index(id(sprite_))
+            current_walk[0] = (_op['i'][2], k)
+            try:
+                return _orig(sprite_, updates_per_env_step=updates_per_env_step)
+            finally:
+                current_walk[0] = None
+        wf._step_sprite = _wrapped_walk  # pylint: disable=protected-access
+        walkers.append(wf)
+
     rec = {k: [] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt', 'reward', 'last',
                            'actions', 'noise', 'rule_noise', 'n_calls', 'n_true', 'true_hash')}
     frames, frame_steps = [], []
@@ -215,27 +265,36 @@ def generate(name, out_dir):
             action = _seek_action(env, t)
         elif name == 'chase_avoid_torus':
             action = _chase_action(env, t)
+        elif name == 'pacman':
+            action = _pacman_action(env, t)
         else:
             action = env.action_space.random_action()
         flat = _flat_action(prog, action)
         slots = _slot_map(prog, env.state)
         del draws[:]
         rule_draws.clear()
+        walk_draws.clear()
         np.random.uniform = _uniform
         np.random.choice = _choice
+        np.random.rand = _rand
         try:
             with refenv.OverlapLog() as log:
                 ts = env.step(action)
         finally:
             np.random.uniform = orig_uniform
             np.random.choice = orig_choice
+            np.random.rand = orig_rand
         h, n_true = 0, 0
         for a, b, r in log.calls:
             if r:
                 n_true += 1
                 h = true_event_hash(h, slots[id(a)], slots[id(b)])
         noise = np.zeros((K, max(nd, 1)))
-        if nd:
+        if walk_ops:
+            assert K == 1 and not draws
+            for col, u in walk_draws.items():
+                noise[0, col:col + 4] = u
+        elif nd:
             # draws arrive substep by substep, in force order, 2 per sprite
             per = len(draws) // K
             assert per * K == len(draws) and per <= nd, (per, nd, len(draws))

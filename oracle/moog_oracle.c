@@ -948,9 +948,232 @@ static int gather_layers(const env_t *e, int start, int n, int *out) {
   return k;
 }
 
+
+/* ------------------------------------------------------------------------ */
+/* maze_lib.Maze, RandomMazeWalk, MazePhysics                                 */
+/* ------------------------------------------------------------------------ */
+#define MAZE_EPS 1e-5 /* maze_physics.py:15, maze_walk.py:14 */
+
+typedef struct { int n; const double *rows; double grid, half; } maze_t;
+
+static maze_t maze_of(const env_t *e, int off) {
+  maze_t m;
+  m.n = (int)e->envf[off];
+  m.rows = e->envf + off + 1;
+  m.grid = 1. / m.n;        /* maze.py:32 */
+  m.half = 0.5 * m.grid;    /* maze.py:33 */
+  return m;
+}
+/* maze.py:113-118 */
+static int maze_open(const maze_t *m, int i, int j) {
+  if (i < 0 || j < 0 || i >= m->n || j >= m->n) return 0;
+  return !(((unsigned long long)m->rows[j] >> i) & 1ull);
+}
+/* maze.py:120-126: v[axis][dir] */
+static void maze_valid(const maze_t *m, int i, int j, double v[2][2]) {
+  v[0][0] = maze_open(m, i - 1, j); v[0][1] = maze_open(m, i + 1, j);
+  v[1][0] = maze_open(m, i, j - 1); v[1][1] = maze_open(m, i, j + 1);
+}
+static double np_sign(double x) { return isnan(x) ? x : (double)((x > 0) - (x < 0)); }
+/* numpy floor_divide for doubles (npy_divmod) */
+static double np_floor_divide(double a, double b) {
+  if (b == 0) return a / b;
+  double mod = fmod(a, b);
+  double div = (a - mod) / b;
+  if (mod != 0) {
+    if ((b < 0) != (mod < 0)) div -= 1.0;
+  }
+  double fl;
+  if (div != 0) {
+    fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+  } else {
+    fl = copysign(0.0, a / b);
+  }
+  return fl;
+}
+
+/* maze_walk.py:159-196 RandomMazeWalk._step_sprite (+ _get_pos_vel :46-79, _update_valid_directions :122-157) */
+static void maze_walk_sprite(env_t *e, const moog_op *op, int s, int idx_in_layer) {
+  if (isinf(STAT(e, MOOG_S_MASS, s))) return;
+  maze_t m = maze_of(e, op->i[3]);
+  const double speed = op->p[0];
+  double px = DYN(e, MOOG_D_X, s), py = DYN(e, MOOG_D_Y, s);
+  double pos[2] = {px, py};
+  double vel[2] = {speed * np_sign(DYN(e, MOOG_D_VX, s)), speed * np_sign(DYN(e, MOOG_D_VY, s))};
+  double K = (double)e->K;
+  double nxt[2] = {pos[0] + vel[0] / K, pos[1] + vel[1] / K};
+  int near_[2];
+  double inter[2];
+  for (int a = 0; a < 2; ++a) {
+    near_[a] = (int)rint(pos[a] / m.grid - 0.5);
+    inter[a] = m.grid * near_[a] + m.half;
+  }
+  double d_next_cur = fabs(nxt[0] - pos[0]) + fabs(nxt[1] - pos[1]);
+  double d_int_next = fabs(nxt[0] - inter[0]) + fabs(nxt[1] - inter[1]);
+  int entering = d_next_cur > d_int_next; /* the reference compares against the same quantity twice */
+  double valid[2][2];
+  if (entering) {
+    maze_valid(&m, near_[0], near_[1], valid);
+    if (op->flags & MOOG_FL_PREVENT_BACKTRACKING) {
+      int axis = fabs(vel[1]) > fabs(vel[0]) ? 1 : 0; /* np.argmax: first maximum */
+      double direction = np_sign(vel[axis]);
+      if (direction != 0) {
+        int fwd = (int)(0.5 * (1 + direction)), back = (int)(0.5 * (1 - direction));
+        int can_continue = valid[axis][fwd] != 0;
+        if (!can_continue && (op->flags & MOOG_FL_ALLOW_WALL_BACKTRACKING)) {
+        } else if (can_continue && (op->flags & MOOG_FL_ONLY_TURN_AT_WALL)) {
+          valid[0][0] = valid[0][1] = valid[1][0] = valid[1][1] = 0;
+          valid[axis][fwd] = 1;
+        } else {
+          valid[axis][back] = 0;
+        }
+      }
+    }
+  } else if (vel[0] == 0. && vel[1] == 0.) {
+    int on[2];
+    for (int a = 0; a < 2; ++a) on[a] = fabs((m.half + near_[a] * m.grid) - pos[a]) < MAZE_EPS;
+    if (on[0] && on[1]) {
+      maze_valid(&m, near_[0], near_[1], valid);
+    } else {
+      valid[0][0] = valid[0][1] = valid[1][0] = valid[1][1] = 0;
+      int row = 1 - (on[0] ? 0 : (on[1] ? 1 : 0)); /* 1 - np.argmax(on_grid) */
+      valid[row][0] = valid[row][1] = 1;
+    }
+  } else {
+    assign_velocity(e, s, vel[0], vel[1]);
+    return;
+  }
+  /* sample = valid_directions * np.random.rand(2, 2); argmax of the ravel (first maximum) */
+  double u[4] = {0, 0, 0, 0};
+  if (e->noise) {
+    const double *nz = e->noise + (size_t)e->substep * e->hdr[MOOG_H_NOISE_DIM] + op->i[2] + 4 * idx_in_layer;
+    for (int k = 0; k < 4; ++k) u[k] = nz[k];
+  }
+  int best = 0;
+  double bv = valid[0][0] * u[0];
+  for (int k = 1; k < 4; ++k) {
+    double v = valid[k >> 1][k & 1] * u[k];
+    if (v > bv) { bv = v; best = k; }
+  }
+  vel[best / 2] = (1 + MAZE_EPS) * speed * (2 * (best % 2) - 1);
+  assign_velocity(e, s, vel[0], vel[1]);
+}
+
+/* maze_physics.py:51-112 _get_position_affordances; returns 0 when the position is off the grid */
+static int maze_affordances(const maze_t *m, const double pos[2], double aff[2][2]) {
+  int near_[2], inds[2], on[2];
+  for (int a = 0; a < 2; ++a) {
+    near_[a] = (int)rint(pos[a] / m->grid - 0.5);
+    double rounded = m->half + near_[a] * m->grid;
+    on[a] = fabs(rounded - pos[a]) < MAZE_EPS;
+    inds[a] = (int)np_floor_divide(pos[a] - m->half, m->grid);
+    if (on[a]) inds[a] = near_[a];
+  }
+  aff[0][0] = aff[0][1] = aff[1][0] = aff[1][1] = 0;
+  if (!on[0] && !on[1]) return 0;
+  if (on[0] && on[1]) {
+    double v[2][2];
+    maze_valid(m, inds[0], inds[1], v);
+    for (int a = 0; a < 2; ++a) {
+      aff[a][0] = v[a][0] * m->grid * -1.;
+      aff[a][1] = v[a][1] * m->grid * 1.;
+    }
+  } else {
+    int i = 1 - (on[0] ? 0 : 1);
+    aff[i][0] = inds[i] * m->grid + m->half - pos[i];
+    aff[i][1] = (inds[i] + 1) * m->grid + m->half - pos[i];
+  }
+  return 1;
+}
+
+/* maze_physics.py:114-167 _get_new_velocity; `pos` and `vel` are mutated like the reference's arrays.
+ * Returns 0 when a vertex reached on the way is off the grid. */
+static int maze_new_velocity(const maze_t *m, double pos[2], double vel[2], double aff[2][2], int axis,
+                             double out[2], int depth) {
+  if (depth > 16) return 0;
+  if (axis < 0) axis = fabs(vel[1]) > fabs(vel[0]) ? 1 : 0;
+  if (aff[axis][0] <= vel[axis] && vel[axis] <= aff[axis][1]) {
+    vel[1 - axis] = 0;
+    out[0] = vel[0]; out[1] = vel[1];
+    return 1;
+  }
+  int direction = vel[axis] > 0 ? 1 : 0; /* int(0.5 + 0.5 * sign) */
+  if (aff[axis][direction] == 0) {
+    axis = 1 - axis;
+    direction = vel[axis] > 0 ? 1 : 0;
+    if (aff[axis][direction] == 0 || vel[axis] == 0) {
+      out[0] = out[1] = 0.;
+      return 1;
+    }
+    return maze_new_velocity(m, pos, vel, aff, axis, out, depth + 1);
+  }
+  pos[axis] += aff[axis][direction];
+  double vaff[2][2];
+  if (!maze_affordances(m, pos, vaff)) return 0;
+  double scaling = aff[axis][direction] / vel[axis];
+  double rem[2] = {(1. - scaling) * vel[0], (1. - scaling) * vel[1]};
+  double post[2];
+  if (!maze_new_velocity(m, pos, rem, vaff, -1, post, depth + 1)) return 0;
+  vel[0] *= scaling; vel[1] *= scaling;
+  vel[1 - axis] = 0;
+  vel[0] += post[0]; vel[1] += post[1];
+  out[0] = vel[0]; out[1] = vel[1];
+  return 1;
+}
+
+/* maze_physics.py:189-203 _update_sprite_in_maze (+ _update_sprite_angle :169-187) */
+static void maze_physics_sprite(env_t *e, const moog_op *op, int s) {
+  double vel[2] = {DYN(e, MOOG_D_VX, s), DYN(e, MOOG_D_VY, s)};
+  if ((vel[0] == 0 && vel[1] == 0) || isnan(vel[0]) || isnan(vel[1])) return;
+  maze_t m = maze_of(e, op->i[2]);
+  if (!isnan(op->p[1])) { /* np.clip(velocity, -max_speed, max_speed) */
+    for (int a = 0; a < 2; ++a) vel[a] = fmin(fmax(vel[a], -op->p[1]), op->p[1]);
+  }
+  if (!isnan(op->p[0])) {
+    for (int a = 0; a < 2; ++a) {
+      vel[a] += np_sign(vel[a]);
+      vel[a] *= op->p[0];
+    }
+  }
+  double pos[2] = {DYN(e, MOOG_D_X, s), DYN(e, MOOG_D_Y, s)};
+  double aff[2][2];
+  if (!maze_affordances(&m, pos, aff)) {
+    e->envi[MOOG_EI_ERR] |= MOOG_ERR_OFF_MAZE_GRID;
+    return;
+  }
+  /* sprite.position = np.copy(position): a translation by exactly zero */
+  set_position(e, s, pos[0], pos[1]);
+  double nv[2];
+  if (!maze_new_velocity(&m, pos, vel, aff, -1, nv, 0)) {
+    e->envi[MOOG_EI_ERR] |= MOOG_ERR_OFF_MAZE_GRID;
+    return;
+  }
+  double new_angle;
+  if (nv[0] == 0 && nv[1] == 0) {
+    new_angle = NAN;
+  } else if (nv[1] == 0) {
+    new_angle = -0.5 * np_sign(nv[0]) * M_PI;
+  } else if (np_sign(nv[1]) > 0) {
+    new_angle = atan(-nv[0] / nv[1]);
+  } else {
+    new_angle = M_PI + atan(-nv[0] / nv[1]);
+  }
+  if (!isnan(new_angle) && fabs(new_angle - DYN(e, MOOG_D_ANG, s)) > MAZE_EPS) {
+    set_angle(e, s, new_angle, 0);
+    set_ang_kind(e, s, KIND_F64);
+  }
+  assign_velocity(e, s, nv[0], nv[1]);
+}
+
 static void corrective(env_t *e, const moog_op *op) {
   int sp[MOOG_MAX_SLOTS];
   switch (op->kind) {
+    case MOOG_C_MAZE_PHYSICS: { /* maze_physics.py:205-211 */
+      int n = gather_layers(e, op->i[0], op->i[1], sp);
+      for (int i = 0; i < n; ++i) maze_physics_sprite(e, op, sp[i]);
+      break;
+    }
     case MOOG_C_TETHER: { /* tether_physics.py:126-140 */
       int n = gather_layers(e, op->i[0], op->i[1], sp);
       tether_sprites(e, sp, n, (op->flags & MOOG_FL_UPDATE_ANGLE_VEL) != 0,
@@ -1007,7 +1230,9 @@ static void apply_physics(env_t *e) {
   for (int f = 0; f < h[MOOG_H_N_FORCES]; ++f) {
     const moog_op *op = e->ops + h[MOOG_H_FORCES] + f;
     int la = op->i[0], lb = op->i[1];
-    if (lb < 0) {
+    if (op->kind == MOOG_F_MAZE_WALK) {
+      for (int i = 0; i < e->cnt[la]; ++i) maze_walk_sprite(e, op, LOFF(e, la) + i, i);
+    } else if (lb < 0) {
       for (int i = 0; i < e->cnt[la]; ++i) force_unary(e, op, LOFF(e, la) + i, i);
     } else {
       for (int i = 0; i < e->cnt[la]; ++i)
@@ -1176,6 +1401,10 @@ static double eval_condition(env_t *e, int op_index) {
       return 0;
     }
     case MOOG_SC_NOT: return !(eval_condition(e, op->i[0]) != 0);
+    case MOOG_SC_FIRST: {
+      int n = gather_layers(e, op->i[0], op->i[1], sp);
+      return n > 0 ? eval_expr(e, op->i[2], sp[0], sp[0]) : 0.0;
+    }
   }
   return 0;
 }

@@ -31,10 +31,7 @@ def _compare_state(scene, t, prog, dev, ref_arrays, cnt, exact):
         live = util.live_mask(prog, cnt[e])
         for k in ('dyn', 'stat'):
             worst = max(worst, util.rel_err(dev[k][e][:, live], ref_arrays[k][e][:, live]))
-        vlive = np.zeros(prog.n_vtx, dtype=bool)
-        voff = prog_voff(prog)
-        for s in np.nonzero(live)[0]:
-            vlive[voff[s]:voff[s] + int(ref_arrays['meta'][e][2, s])] = True
+        vlive = util.live_vertex_mask(prog, cnt[e], ref_arrays['meta'][e])
         worst = max(worst, util.rel_err(dev['vtx'][e][vlive], ref_arrays['vtx'][e][vlive]))
         assert np.array_equal(dev['meta'][e][:, live], ref_arrays['meta'][e][:, live]), (scene, t, 'meta')
     if exact:
@@ -44,14 +41,7 @@ def _compare_state(scene, t, prog, dev, ref_arrays, cnt, exact):
     return worst
 
 
-def prog_voff(prog):
-    from moog_b200 import compiler as C
-    blob = np.frombuffer(prog.blob, dtype=np.uint8)
-    hdr = np.frombuffer(prog.blob[:C.HDR_WORDS * 4], dtype='<i4')
-    n_ops = int(hdr[C.H_N_OPS])
-    start = C.HDR_WORDS * 4 + 80 * n_ops
-    ipool = np.frombuffer(blob[start:start + 4 * int(hdr[C.H_N_IPOOL])].tobytes(), dtype='<i4')
-    return ipool[int(hdr[C.H_VOFF]):int(hdr[C.H_VOFF]) + prog.n_slots + 1]
+prog_voff = util.prog_voff
 
 
 @pytest.mark.parametrize('scene', util.SCENES)
@@ -62,8 +52,8 @@ def test_cuda_follows_reference_trajectory(scene):
     eng = _engine(prog, util.state_at(g, None, prefix='init'))
     eng.post_reset()
     dev = eng.state.download()
-    for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta'):
-        assert np.array_equal(dev[k][0], g['reset_' + k]), 'reset ' + k
+    util.assert_live_equal(prog, {k: dev[k][0] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')},
+                           {k: g['reset_' + k] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')}, 'reset')
     exact = scene in util.EXACT_SCENES
     T = len(g['reward'])
     for t in range(T):

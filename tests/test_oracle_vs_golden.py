@@ -20,8 +20,8 @@ def test_oracle_follows_reference_trajectory(scene):
     prog = g['program']
     orc = Oracle(prog, util.state_at(g, None, prefix='init'))
     orc.post_reset()
-    for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta'):
-        assert np.array_equal(getattr(orc, k)[0], g['reset_' + k]), 'reset ' + k
+    util.assert_live_equal(prog, {k: getattr(orc, k)[0] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')},
+                           {k: g['reset_' + k] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')}, 'reset')
     T = len(g['reward'])
     worst = 0.0
     for t in range(T):
@@ -31,7 +31,8 @@ def test_oracle_follows_reference_trajectory(scene):
         live = util.live_mask(prog, g['cnt'][t])
         for k in ('dyn', 'stat'):
             worst = max(worst, util.rel_err(getattr(orc, k)[0][:, live], g[k][t][:, live]))
-        worst = max(worst, util.rel_err(orc.vtx[0], g['vtx'][t]))
+        vlive = util.live_vertex_mask(prog, g['cnt'][t], g['meta'][t])
+        worst = max(worst, util.rel_err(orc.vtx[0][vlive], g['vtx'][t][vlive]))
         assert reward[0] == g['reward'][t], (scene, t)
         assert bool(step_type[0] == 2) == bool(g['last'][t]), (scene, t)
         n_calls, n_true, _, h = orc.counters[0]

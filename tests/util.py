@@ -8,7 +8,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 SCENES = ['pong', 'falling_balls', 'falling_balls20', 'colliding_predators',
           'predators_arena', 'synthetic32', 'falling_balls20_nan', 'cleanup',
-          'chase_avoid_torus']
+          'chase_avoid_torus', 'pacman']
 # scenes whose step() uses no sin/cos of a non-zero angle: every operation on
 # the path is IEEE-exact (+ - * / sqrt fma), so the CUDA path must be bit-exact
 EXACT_SCENES = ['pong', 'falling_balls', 'falling_balls20', 'falling_balls20_nan']
@@ -86,6 +86,39 @@ def live_mask(prog, cnt):
     for l in range(prog.n_layers):
         m[prog.layer_off[l]:prog.layer_off[l] + int(cnt[l])] = True
     return m
+
+
+def prog_voff(prog):
+    """voff[S+1] (first cached vertex of each slot) read back from the program blob."""
+    from moog_b200 import compiler as C
+    blob = np.frombuffer(prog.blob, dtype=np.uint8)
+    hdr = np.frombuffer(prog.blob[:C.HDR_WORDS * 4], dtype='<i4')
+    n_ops = int(hdr[C.H_N_OPS])
+    start = C.HDR_WORDS * 4 + 80 * n_ops
+    ipool = np.frombuffer(blob[start:start + 4 * int(hdr[C.H_N_IPOOL])].tobytes(), dtype='<i4')
+    return ipool[int(hdr[C.H_VOFF]):int(hdr[C.H_VOFF]) + prog.n_slots + 1]
+
+
+def live_vertex_mask(prog, cnt, meta):
+    """[VT] bool: cached vertices that belong to a live sprite (a slot freed by
+    VanishOnContact keeps stale data on the device; the fixtures hold zeros)."""
+    live = live_mask(prog, cnt)
+    voff = prog_voff(prog)
+    vlive = np.zeros(max(prog.n_vtx, 1), dtype=bool)
+    for s in np.nonzero(live)[0]:
+        vlive[voff[s]:voff[s] + int(meta[2, s])] = True
+    return vlive
+
+
+def assert_live_equal(prog, got, want, what):
+    """Bit-equality of two state records (dicts of [fields, S] arrays / vtx /
+    cnt) over the live sprites."""
+    assert np.array_equal(got['cnt'], want['cnt']), what + ' cnt'
+    live = live_mask(prog, want['cnt'])
+    for k in ('dyn', 'stat', 'meta'):
+        assert np.array_equal(got[k][:, live], want[k][:, live]), what + ' ' + k
+    vlive = live_vertex_mask(prog, want['cnt'], want['meta'])
+    assert np.array_equal(got['vtx'][vlive], want['vtx'][vlive]), what + ' vtx'
 
 
 def rel_err(a, b):
