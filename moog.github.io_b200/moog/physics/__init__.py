@@ -200,3 +200,30 @@ class ConstantSpeed(AbstractPhysics):
         super().__init__(updates_per_env_step=1)
         self._layer_names = _as_list(layer_names)
         self._speed = speed
+
+
+class MazePhysics(AbstractPhysics):
+    """Constrains the sprites of `avatar_layers` to the grid of the maze whose
+    wall sprites are in `maze_layer` (maze_physics.py:19-211).  Must be the last
+    corrective physics and needs updates_per_env_step == 1."""
+
+    def __init__(self, maze_layer='walls', avatar_layers=(),
+                 constant_speed=None, max_speed=None):
+        super().__init__(updates_per_env_step=1)
+        self._maze_layer = maze_layer
+        self._avatar_layers = avatar_layers
+        self._constant_speed = constant_speed
+        self._max_speed = max_speed
+
+
+class RandomMazeWalk(AbstractForce):
+    """Walks sprites through the maze at constant speed, turning at random at
+    corners and intersections (maze_walk.py:97-196)."""
+
+    def __init__(self, speed, maze_layer='walls', prevent_backtracking=True,
+                 allow_wall_backtracking=False, only_turn_at_wall=False):
+        self._speed = speed
+        self._maze_layer = maze_layer
+        self._prevent_backtracking = prevent_backtracking
+        self._allow_wall_backtracking = allow_wall_backtracking
+        self._only_turn_at_wall = only_turn_at_wall

@@ -184,3 +184,92 @@ def test_shard_range_partitions():
                 assert a[1] == b[0]
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_maze_record_round_trips_through_wall_sprites():
+    """Maze -> wall sprites -> host_maze.maze_matrix (Maze.from_state restated,
+    maze.py:38-84) gives the maze back; the record packs rows as bit masks."""
+    import moog_b200  # noqa: F401
+    from moog import maze_lib
+    from moog_b200 import host_maze
+    np.random.seed(11)
+    for size, ambient in ((8, 12), (10, 12), (6, 7)):
+        m = maze_lib.generate_random_maze_matrix(size=size, ambient_size=ambient)
+        # generator contract (maze_generators.py:96-110): no open 2x2 block, no dead end
+        opened = 1 - m
+        assert not (opened[:-1, :-1] * opened[1:, :-1] * opened[:-1, 1:] * opened[1:, 1:]).any()
+        pad = np.pad(opened, 1)
+        nb = pad[:-2, 1:-1] + pad[2:, 1:-1] + pad[1:-1, :-2] + pad[1:-1, 2:]
+        assert (nb[opened == 1] >= 2).all()
+        maze = maze_lib.Maze(np.flip(m, axis=0))
+        walls = maze.to_sprites(c0=0., c1=0., c2=0.8)
+        got = host_maze.maze_matrix(walls)
+        assert np.array_equal(got, maze.maze.astype(int)), (size, ambient)
+        rec = host_maze.maze_record(walls)
+        assert rec[0] == ambient
+        for j in range(ambient):
+            assert int(rec[1 + j]) == sum(int(maze.maze[j, i]) << i for i in range(ambient))
+
+
+def test_pacman64_compiles_and_steps_on_the_oracle():
+    """BASELINE config 4 through this repo's own MOOG-compatible host package:
+    RandomMazeWalk / MazePhysics / Grid / VanishOnContact / the `unglue`
+    ConditionalRule lower to device ops, and the CPU oracle steps the packed
+    states without leaving the maze grid (maze_physics.py:93-104)."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from moog_b200.configs import pacman64
+    from oracle.oracle import Oracle
+    np.random.seed(5)
+    cfg = pacman64.get_config(0)
+    states = [cfg['state_initializer']() for _ in range(3)]
+    prog = compiler.compile_config(cfg, states)
+    assert prog.layer_names == ['walls', 'prey', 'ghosts', 'agent'] and prog.K == 1
+    assert prog.noise_dim == 4 * 2 and 'walls' in prog.maze_offsets
+    kinds = [o['kind'] for o in prog.ops]
+    assert compiler.F_MAZE_WALK in kinds and compiler.C_MAZE_PHYSICS in kinds and compiler.SC_FIRST in kinds
+    arr = compiler.pack_states(prog, states)
+    orc = Oracle(prog, arr)
+    orc.post_reset()
+    rng = np.random.RandomState(0)
+    prey0 = orc.cnt[:, 1].copy()
+    moved = np.zeros(3, dtype=bool)
+    for _ in range(80):
+        p0 = orc.dyn[:, 0:2, prog.layer_off[3]].copy()
+        orc.step(rng.randint(0, 4, size=(3, 1)).astype(np.float64), noise=rng.uniform(size=(3, 1, prog.noise_dim)))
+        moved |= (orc.dyn[:, 0:2, prog.layer_off[3]] != p0).any(axis=1)
+    assert (orc.envi[:, 2] == 0).all()          # no MOOG_ERR_* flag
+    assert moved.all() and (orc.cnt[:, 1] < prey0).all()   # the agents move and eat prey
+    # the agent stays on the maze grid: one coordinate on a grid line
+    grid = 1. / 12
+    pos = orc.dyn[:, 0:2, prog.layer_off[3]]
+    off = np.abs((pos / grid - 0.5) - np.round(pos / grid - 0.5))
+    assert (off.min(axis=1) < 1e-3).all()
+
+
+@pytest.mark.reference
+def test_host_maze_matches_reference_from_state():
+    """Build container only: host_maze.maze_matrix == the reference's
+    Maze.from_state on the reference's own pacman initial states."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+from oracle import refenv
+refenv.activate()
+import numpy as np, importlib
+import moog_b200
+from moog_b200 import host_maze
+from moog import maze_lib
+np.random.seed(21)
+for level in (0, 1):
+    cfg = importlib.import_module('moog_demos.example_configs.pacman').get_config(level)
+    for _ in range(3):
+        st = cfg['state_initializer']()
+        ref = maze_lib.Maze.from_state(st, maze_layer='walls').maze
+        assert np.array_equal(host_maze.maze_matrix(st['walls']), ref)
+print('OK')
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
