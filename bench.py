@@ -376,7 +376,9 @@ def run_ours(args):
                    'substeps': prog.K, 'image': '{}x{}x3'.format(H, W), 'parallelism': 'env-sharded x{}'.format(world),
                    'l2': 'flushed between timed iterations (256 MiB fill, untimed)',
                    'phases': 'uniform mix of episode phases after {} burn-in steps with staggered resets'.format(args.burn_in),
-                   'state_record_bytes': int(record_bytes)},
+                   'state_record_bytes': int(record_bytes),
+                   'step_launch': dict(zip(('resident_envs_per_sm', 'warps_per_env', 'smem_bytes_per_env'),
+                                           eng.dev_program.step_launch_info(E)))},
         'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak,
                      'traffic': _ncu_traffic('step_kernel') if args.scene == 'falling_balls20' and E == 4096 else None,

@@ -124,6 +124,11 @@ const char *moog_strerror(int code);
 const char *moog_last_cuda_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t moog_launch_count(void);
+/* How moog_env_step launches a batch of n_envs on the current device: envs resident per SM
+ * (0 = as many as fit), warps per env (2 = owner + helper warp), dynamic shared memory per
+ * env in bytes.  The step is bound by its longest-running env; see DESIGN.md section 3.1. */
+int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_per_sm, int *warps_per_env,
+                          int *smem_bytes_per_env);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ SYMBOLS = ('moog_program_create', 'moog_program_destroy',
            'moog_env_post_reset', 'moog_physics_step', 'moog_overlap_pairs',
            'moog_render', 'moog_strerror', 'moog_last_cuda_error',
            'moog_launch_count', 'moog_host_paths_overlap',
-           'moog_host_points_in_path')
+           'moog_host_points_in_path', 'moog_step_launch_info')
 
 
 class MoogError(RuntimeError):
@@ -90,6 +90,8 @@ def lib():
     L.moog_host_paths_overlap.restype = ci
     L.moog_host_points_in_path.argtypes = [vp, ci, vp, ci, vp]
     L.moog_host_points_in_path.restype = None
+    L.moog_step_launch_info.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.moog_step_launch_info.restype = ci
     L.moog_launch_count.argtypes = []
     L.moog_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -123,6 +125,12 @@ class DeviceProgram(object):
 
     def env_smem_bytes(self):
         return int(lib().moog_program_env_smem_bytes(self._h))
+
+    def step_launch_info(self, n_envs):
+        """(envs resident per SM, warps per env, shared-memory bytes per env)."""
+        r, w, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(lib().moog_step_launch_info(self._h, int(n_envs), ctypes.byref(r), ctypes.byref(w), ctypes.byref(s)))
+        return r.value, w.value, s.value
 
     def close(self):
         if self._h:

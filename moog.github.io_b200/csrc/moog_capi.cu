@@ -84,6 +84,37 @@ void moog_program_destroy(moog_program *p) {
 
 int moog_program_env_smem_bytes(const moog_program *p) { return p ? moog::env_smem_bytes(p->hdr) : MOOG_E_INVAL; }
 
+// envs resident per SM / helper warp for a batch of n_envs (see the comment in run_step)
+static void launch_policy(int n_envs, bool ordered, int *resident, bool *helper) {
+  *resident = 0;
+  *helper = false;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > 0) {
+    *resident = (n_envs + 7 * sms / 2) / (7 * sms);
+    if (*resident < 2) *resident = 2;
+    *helper = *resident <= 6;
+  }
+  if (!ordered) *resident = 0;
+  const char *h = getenv("MOOG_HELPER");
+  if (h) *helper = atoi(h) != 0;
+  const char *c = getenv("MOOG_CTAS_PER_SM");
+  if (c && atoi(c) > 0) *resident = atoi(c);
+}
+
+int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_per_sm, int *warps_per_env,
+                          int *smem_bytes_per_env) {
+  if (!p || n_envs < 0) return MOOG_E_INVAL;
+  int resident = 0;
+  bool helper = false;
+  launch_policy(n_envs, n_envs >= 1024, &resident, &helper);
+  if (resident_envs_per_sm) *resident_envs_per_sm = resident;
+  if (warps_per_env) *warps_per_env = helper ? 2 : 1;
+  if (smem_bytes_per_env) *smem_bytes_per_env = moog::env_smem_bytes(p->hdr);
+  return 0;
+}
+
 static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode, const moog_step_io *io,
                     int layer_a, int layer_b, uint8_t *overlap_out, void *stream) {
   if (!p || !valid_state(st) || n_envs < 0) return MOOG_E_INVAL;
@@ -134,19 +165,7 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   // computes one of the two directions of _get_collision_vectors (MOOG_HELPER=0/1 overrides).
   int resident = 0;
   bool helper = false;
-  {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms > 0) {
-      resident = (n_envs + 7 * sms / 2) / (7 * sms);
-      if (resident < 2) resident = 2;
-      helper = resident <= 6;
-    }
-    if (!a.order) resident = 0;
-    const char *h = getenv("MOOG_HELPER");
-    if (h) helper = atoi(h) != 0;
-  }
+  launch_policy(n_envs, a.order != nullptr, &resident, &helper);
   err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches, 0, -1, resident, helper);
   g_launches += launches;
   return err == cudaSuccess ? 0 : cuda_fail(err);

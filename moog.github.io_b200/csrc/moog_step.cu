@@ -49,11 +49,11 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, kscr, kscr_bytes, total;
+  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, plist, kscr, kscr_bytes, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
-#define DCV_TILE 8     /* contained vertices per pass of _directed_collision_vectors */
+#define DCV_TILE 32     /* contained vertices per pass of _directed_collision_vectors */
 #define NEAR_SKIN 0.02
 #define STEP_WARPS 2   /* warps of an env's CTA: the owner and (optionally) its helper, see moog_step_kernel */
 #define NEAR_CAP 256  /* near-list entries; more near pairs than this -> every pair is tested */
@@ -83,6 +83,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.scratch = o; o += 64 * STEP_WARPS;  // one per warp (main, helper)
   o = (o + 7) & ~7;
   L.xchg = o;  o += 128;                  // main <-> helper: request words, the helper's CVec
+  L.plist = o; o += CMW > 0 ? 2 * 32 * DCV_TILE * STEP_WARPS : 8;  // crossing (vertex, edge) pairs, per warp
   L.kscr_bytes = CMW > 0 ? 8 * 32 * DCV_TILE : 8;
   L.kscr = o;  o += L.kscr_bytes * STEP_WARPS;
   L.total = (o + 15) & ~15;
@@ -118,6 +119,7 @@ struct Env {
   unsigned char *scratch;
   unsigned long long *kscr;
   unsigned char *xchg;
+  unsigned short *plist;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -177,6 +179,7 @@ __device__ __forceinline__ Env env_view() {
   e.scratch = base + r->lay.scratch + 64 * warp;
   e.kscr = (unsigned long long *)(base + r->lay.kscr + r->lay.kscr_bytes * warp);
   e.xchg = base + r->lay.xchg;
+  e.plist = (unsigned short *)(base + r->lay.plist) + 32 * DCV_TILE * warp;
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x & 31;
@@ -774,12 +777,17 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
 #ifdef MOOG_PROFILE_DCV
     long long tp1 = clock64();
 #endif
-    // two passes per iteration, branch-free (idle lanes divide 1 by 1: a zero
-    // numerator would send the whole warp through the fp64 division slow path), so
-    // that the four divisions of an iteration are in flight together
+    // Stage A1 (no division): which (vertex, edge) pairs cross, i.e. 0 <= cross_b <= 1
+    // (sprite.py:171-175).  A line meets a convex outline in two edges, so only a couple
+    // of pairs per vertex do; they are compacted into a list, every other pair's key is
+    // |1 - (-inf)| = +inf.  Two passes per iteration for instruction-level parallelism.
+    const unsigned long long KEY_INF = (unsigned long long)__double_as_longlong(INFINITY) + 1ull;
+    const unsigned lt = (1u << e.lane) - 1u;
+    int n_pairs = 0;
     for (int t0 = 0; t0 < cnt; t0 += 2 * V) {
-      unsigned long long key2[2];
-      bool ok2[2];
+      bool cr[2], inexact = false;
+      double nB2[2], den2[2];
+      bool on2[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int t = t0 + u * V + tl;
@@ -796,24 +804,49 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
         const double qx = q1.x - sx, qy = q1.y - sy;
         const double nB = on ? (qx * d0y - qy * d0x) : 1.0;
         bool exact;
-        bool in_unit = unit_ratio(nB, den, exact);
-        if (__any_sync(FULL, !exact)) {  // out-of-range operands somewhere in the warp: divide
-          const double Bc = nB / den;
-          in_unit = (Bc >= 0) && (Bc <= 1);
+        const bool in_unit = unit_ratio(nB, den, exact);
+        inexact |= !exact;
+        cr[u] = on && in_unit;
+        nB2[u] = nB; den2[u] = den; on2[u] = on;
+        if (on) keys[t * 32 + ej] = KEY_INF;
+      }
+      if (__any_sync(FULL, inexact)) {  // out-of-range operands somewhere in the warp: divide
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const double Bc = nB2[u] / den2[u];
+          cr[u] = on2[u] && (Bc >= 0) && (Bc <= 1);
         }
-        double A = (on ? (qx * d1y - qy * d1x) : 1.0) / den;
-        const bool crossing = on && in_unit;
-        my_cross |= crossing;
-        if (!crossing) A = -INFINITY;
-        const double ab = fabs(1.0 - A);
-        // np.argmin order: a NaN beats everything, then the smaller value (ab >= 0, so
-        // its bit pattern orders like the value), then the smaller index
-        key2[u] = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
-        ok2[u] = on;
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (ok2[u]) keys[(t0 + u * V + tl) * 32 + ej] = key2[u];
+      for (int u = 0; u < 2; ++u) {
+        const unsigned cm = __ballot_sync(FULL, cr[u]);
+        if (cr[u]) e.plist[n_pairs + __popc(cm & lt)] = (unsigned short)(((t0 + u * V + tl) << 8) | ej);
+        n_pairs += __popc(cm);
+      }
+    }
+    my_cross |= n_pairs > 0;
+    wsync();
+    // Stage A2: cross_a of the crossing pairs, 32 pairs per pass -- the same IEEE operations
+    // on the same operands as above and as the reference, hence the same bits
+    for (int base = 0; base < n_pairs; base += 32) {
+      const int k = base + e.lane;
+      const bool act2 = k < n_pairs;
+      const unsigned ent = e.plist[act2 ? k : 0];
+      const int t = (int)(ent >> 8), ed = (int)(ent & 255u);
+      const double2 ev = P0[e.scratch[vbase + t]];
+      const double ex = ev.x, ey = ev.y;
+      const double sx = M.m0 * ex + M.m1 * ey + M.m2;
+      const double sy = M.m3 * ex + M.m4 * ey + M.m5;
+      const double d0x = ex - sx, d0y = ey - sy;
+      const double2 w1 = P1[ed], w2 = P1[(ed + 1 == n1) ? 0 : ed + 1];
+      const double e1x = w2.x - w1.x, e1y = w2.y - w1.y;
+      const double den = act2 ? (d0x * e1y - d0y * e1x) + EPS_INTERP : 1.0;
+      const double qx = w1.x - sx, qy = w1.y - sy;
+      const double A = (act2 ? (qx * e1y - qy * e1x) : 1.0) / den;
+      const double ab = fabs(1.0 - A);
+      // np.argmin order: a NaN beats everything, then the smaller value (ab >= 0, so
+      // its bit pattern orders like the value), then the smaller index
+      if (act2) keys[t * 32 + ed] = isnan(ab) ? 0ull : (unsigned long long)__double_as_longlong(ab) + 1ull;
     }
     wsync();
 #ifdef MOOG_PROFILE_DCV
