@@ -12,6 +12,7 @@
 // z-order by every row thread, and the finished canvas is written to HBM once,
 // flipped, as coalesced 16-byte stores.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -747,9 +748,20 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
   const int T = (H * P + 31) & ~31;
   const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;  // TorusGeometry: 9 copies per sprite
   RenderLayout lay = render_layout(H, W, S * C, (VT > 0 ? VT : 1) * C, OW);
-  int epb = 256 / T;
-  if (epb < 1) epb = 1;
-  while (epb > 1 && (size_t)lay.total * epb > 100 * 1024) --epb;
+  // envs per CTA: the split that keeps the most envs resident per SM (228 KB of shared
+  // memory, 1 KB of it reserved per CTA); ties go to the larger CTA
+  int epb = 1;
+  {
+    int best = 0;
+    for (int c = 1; c * T <= 256 || c == 1; ++c) {
+      const size_t per_cta = (size_t)lay.total * c + 1024;
+      if (per_cta > 228 * 1024) break;
+      const int envs = (int)(233472 / per_cta) * c;
+      if (envs >= best) { best = envs; epb = c; }
+    }
+    static const char *epb_env = getenv("MOOG_RENDER_EPB");
+    if (epb_env && atoi(epb_env) > 0) epb = atoi(epb_env);
+  }
   size_t smem = (size_t)lay.total * epb;
   if (smem > 224 * 1024 || T > 1024) return cudaErrorInvalidConfiguration;
   static size_t configured = 0;
