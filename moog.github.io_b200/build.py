@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     '-Wno-deprecated-gpu-targets',
 ] + (['-DMOOG_PROFILE_PHASES'] if os.environ.get('MOOG_PROFILE_PHASES') else []) + (
     ['-DMOOG_PROFILE_DCV'] if os.environ.get('MOOG_PROFILE_DCV') else []) + (
-    ['-DMOOG_PROFILE_ICACHE'] if os.environ.get('MOOG_PROFILE_ICACHE') else [])
+    ['-DMOOG_PROFILE_GCV'] if os.environ.get('MOOG_PROFILE_GCV') else [])
 
 
 def _nvcc():

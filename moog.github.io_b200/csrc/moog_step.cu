@@ -56,7 +56,7 @@ struct SmemLayout {
 #define DCV_TILE 32     /* contained vertices per pass of _directed_collision_vectors */
 #define NEAR_SKIN 0.02
 #define STEP_WARPS 2   /* warps of an env's CTA: the owner and (optionally) its helper, see moog_step_kernel */
-#define NEAR_CAP 256  /* near-list entries; more near pairs than this -> every pair is tested */
+#define NEAR_CAP 512  /* near-list entries; more near pairs than this -> every pair is tested */
 
 __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW) {
   SmemLayout L;
@@ -189,7 +189,7 @@ __device__ __forceinline__ Env env_view() {
   return e;
 }
 
-#if defined(MOOG_PROFILE_PHASES) || defined(MOOG_PROFILE_DCV)
+#if defined(MOOG_PROFILE_PHASES) || defined(MOOG_PROFILE_DCV) || defined(MOOG_PROFILE_GCV)
 #define PROF_RESOLVE(e, t1)
 #else
 #define PROF_RESOLVE(e, t1) ctr_add(e, CT_CYC_RESOLVE, clock64() - (t1))
@@ -956,9 +956,20 @@ __device__ inline void get_collision_vectors(const Env &e, int s0, int s1, doubl
     int *req = (int *)e.xchg;
     wsync();
     if (e.lane == 0) { req[0] = HELPER_DCV; req[1] = s0; req[2] = s1; }
+#ifdef MOOG_PROFILE_GCV
+    long long ta = clock64();
+#endif
     cta_bar(1);                                       // request visible, helper released
     directed_collision_vectors(e, s1, s0, dt, c0);
+#ifdef MOOG_PROFILE_GCV
+    long long tb = clock64();
+#endif
     cta_bar(2);                                       // helper's result visible
+#ifdef MOOG_PROFILE_GCV
+    ctr_add(e, CT_NARROW, 1);
+    ctr_add(e, CT_CYC_NARROW, tb - ta);
+    ctr_add(e, CT_CYC_RESOLVE, clock64() - tb);
+#endif
     c1 = *(const CVec *)(e.xchg + 16);
     wsync();
   } else {
@@ -1193,7 +1204,7 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
     } else {
       ov = overlaps(e, s0, s1);
     }
-#if !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV)
+#if !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV) && !defined(MOOG_PROFILE_GCV)
     ctr_add(e, CT_NARROW, 1);
     ctr_add(e, CT_CYC_NARROW, clock64() - t0);
 #endif

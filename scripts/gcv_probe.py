@@ -1,4 +1,4 @@
-"""MOOG_PROFILE_ICACHE build: cycles of a directed_collision_vectors call vs the same call repeated."""
+"""MOOG_PROFILE_GCV build: cycles inside _get_collision_vectors vs the rest of a handled overlap."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -16,4 +16,5 @@ for t in range(45):
 eng.env_step(act, want_counters=True); torch.cuda.synchronize()
 c = eng.counters.cpu().numpy().astype(np.float64)
 n = c[:, 5].sum()
-print('pairs %d  first call %.0f cycles, repeated call %.0f cycles (mean per call)' % (n, c[:, 6].sum() / n, c[:, 7].sum() / n))
+print('true overlaps %d resolved %d: owner DCV (incl. release barrier) %.0f cycles, then waiting for the helper %.0f cycles; env cycles mean %.3g max %.3g' % (
+    n, c[:, 2].sum(), c[:, 6].sum() / n, c[:, 7].sum() / n, c[:, 4].mean(), c[:, 4].max()))
