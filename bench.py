@@ -337,19 +337,20 @@ def run_ours(args):
     value = world * E * args.steps / (ms_total_max * 1e-3)
 
     # ---- end-to-end arm: host actions in, host TimeStep (frames included) out --
+    from moog_b200.batched_env import TimeStep
+    host_ts = TimeStep(host_step_type, host_reward, None, {'image': host_frames})
     for _ in range(2):
-        ts = env.step(host_actions)
+        env.step_to_host(host_actions, host_ts)
     torch.cuda.synchronize()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        ts = env.step(host_actions)                       # H2D of the actions inside
-        host_frames.copy_(ts.observation['image'], non_blocking=True)
-        host_reward.copy_(ts.reward, non_blocking=True)
-        host_step_type.copy_(ts.step_type, non_blocking=True)
-        torch.cuda.current_stream().synchronize()         # the caller owns the TimeStep now
+        # H2D of the actions, the step, the frames rendered in 4 env ranges with the D2H
+        # copy of each range overlapping the next one's render; returns when the host
+        # buffers hold the whole TimeStep (the caller owns it now)
+        env.step_to_host(host_actions, host_ts)
     e1.record()
     torch.cuda.synchronize()
     e2e_value = world * E * args.steps / (mdist.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3)

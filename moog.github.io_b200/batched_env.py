@@ -89,8 +89,13 @@ class DeviceState(object):
         for k in self.KEYS:
             getattr(self, k).copy_(getattr(other, k))
 
-    def struct(self):
-        return capi.MoogState(*[getattr(self, k).data_ptr() for k in self.KEYS])
+    def struct(self, first=0):
+        """`moog_state` of the envs [first, n): the row pointers of env `first`."""
+        ptrs = []
+        for k in self.KEYS:
+            t = getattr(self, k)
+            ptrs.append(t.data_ptr() + first * t.stride(0) * t.element_size())
+        return capi.MoogState(*ptrs)
 
     def nbytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size() for k in self.KEYS)
@@ -204,14 +209,19 @@ class Engine(object):
                 self.dev_program.handle, ctypes.byref(st), self.n, la, lb, _ptr(out), self._stream()))
         return out
 
-    def render(self, out=None):
+    def render(self, out=None, first=0, count=None):
+        """Frames of the envs [first, first + count) into out[first:first + count]."""
         if self.frames is None:
             raise capi.MoogError('the program has no PILRenderer observer')
         out = self.frames if out is None else out
-        st = self.state.struct()
+        count = self.n - first if count is None else count
+        if first < 0 or count < 0 or first + count > self.n:
+            raise ValueError('env range [{}, {}) is outside [0, {})'.format(first, first + count, self.n))
+        st = self.state.struct(first)
+        dst = ctypes.c_void_p(out.data_ptr() + first * out.stride(0) * out.element_size())
         with torch.cuda.device(self.device):
             capi.check(capi.lib().moog_render(
-                self.dev_program.handle, ctypes.byref(st), self.n, _ptr(out), self._stream()))
+                self.dev_program.handle, ctypes.byref(st), count, dst, self._stream()))
         return out
 
 
@@ -245,6 +255,8 @@ class BatchedEnvironment(object):
                 self._image_key = k
         self._rng = np.random.RandomState(seed)
         self._started = False
+        self._copy_stream = None
+        self._copy_events = None
 
     # -- dm_env-like protocol -------------------------------------------------
     def reset(self):
@@ -271,6 +283,46 @@ class BatchedEnvironment(object):
             return self.reset()
         self.engine.env_step(self._flatten_action(action))
         return self._timestep()
+
+    def step_to_host(self, action, host, chunks=4):
+        """`step(action)` whose TimeStep lands in the caller's pinned host buffers:
+        `host` is a TimeStep of CPU tensors (step_type int32[N], reward float32[N],
+        discount float32[N] or None, observation {'image': uint8[N,H,W,3]}).  The
+        frames are rendered in `chunks` env ranges; the device-to-host copy of one
+        range runs on a second stream while the next range is rendered.  Returns
+        `host` once everything has arrived (the caller owns the TimeStep)."""
+        if not self._started:
+            self.reset()
+        else:
+            self.engine.env_step(self._flatten_action(action))
+        e = self.engine
+        main = torch.cuda.current_stream(e.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=e.device)
+            self._copy_events = [torch.cuda.Event() for _ in range(64)]
+        copy = self._copy_stream
+        host.step_type.copy_(e.step_type, non_blocking=True)
+        host.reward.copy_(e.reward, non_blocking=True)
+        if host.discount is not None:
+            host.discount.copy_(e.discount, non_blocking=True)
+        if self._image_key is not None:
+            dst = host.observation[self._image_key]
+            chunks = max(1, min(int(chunks), len(self._copy_events), self.num_envs))
+            step = (self.num_envs + chunks - 1) // chunks
+            for c in range(chunks):
+                first = c * step
+                count = min(step, self.num_envs - first)
+                if count <= 0:
+                    break
+                e.render(first=first, count=count)
+                ev = self._copy_events[c]
+                ev.record(main)
+                copy.wait_event(ev)
+                with torch.cuda.stream(copy):
+                    dst[first:first + count].copy_(e.frames[first:first + count], non_blocking=True)
+        copy.synchronize()
+        main.synchronize()
+        return host
 
     def observation(self):
         obs = {}

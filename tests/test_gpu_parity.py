@@ -172,3 +172,42 @@ def test_cuda_render_matches_reference_antialiased_frames(scene, aa):
     assert out.shape == ref.shape
     bad = int((out != ref).sum())
     assert bad == 0, (scene, aa, bad)
+
+
+@pytest.mark.gpu
+def test_render_env_ranges_and_step_to_host():
+    """Frames rendered range by range equal the whole-batch render, and
+    `BatchedEnvironment.step_to_host` (chunked render, device-to-host copies on
+    a second stream) delivers the same TimeStep as `step` + explicit copies."""
+    import torch
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment, TimeStep
+    from moog_b200.configs import falling_balls20
+    g = util.load_golden('falling_balls20')
+    prog = g['program']
+    T = len(g['reward'])
+    parts = [util.state_at(g, t) for t in range(-1, T - 1)]
+    arrays = {k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}
+    eng = _engine(prog, arrays)
+    whole = eng.render().cpu().numpy().copy()
+    eng.frames.zero_()
+    n = eng.n
+    for first, count in ((0, 7), (7, n - 20), (n - 13, 13)):
+        eng.render(first=first, count=count)
+    assert np.array_equal(eng.frames.cpu().numpy(), whole)
+
+    cfg = falling_balls20.get_config()
+    np.random.seed(4)
+    states = [cfg['state_initializer']() for _ in range(8)]
+    envs = [BatchedEnvironment(**cfg, num_envs=50, device='cuda:0', seed=9, initial_states=states) for _ in range(2)]
+    H = W = 64
+    host = TimeStep(torch.empty(50, dtype=torch.int32).pin_memory(), torch.empty(50, dtype=torch.float32).pin_memory(),
+                    torch.empty(50, dtype=torch.float32).pin_memory(),
+                    {'image': torch.empty((50, H, W, 3), dtype=torch.uint8).pin_memory()})
+    act = torch.zeros((50, 1), dtype=torch.float64)
+    for step in range(4):
+        ts = envs[0].step(act)
+        got = envs[1].step_to_host(act, host, chunks=3)
+        assert torch.equal(ts.observation['image'].cpu(), got.observation['image']), step
+        assert torch.equal(ts.step_type.cpu(), got.step_type), step
+        assert torch.equal(torch.nan_to_num(ts.reward.cpu(), nan=-7.), torch.nan_to_num(got.reward, nan=-7.)), step
