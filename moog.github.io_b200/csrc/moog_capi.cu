@@ -111,7 +111,7 @@ int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_
   launch_policy(n_envs, n_envs >= 1024, &resident, &helper);
   if (resident_envs_per_sm) *resident_envs_per_sm = resident;
   if (warps_per_env) *warps_per_env = helper ? 2 : 1;
-  if (smem_bytes_per_env) *smem_bytes_per_env = moog::env_smem_bytes(p->hdr);
+  if (smem_bytes_per_env) *smem_bytes_per_env = moog::env_smem_bytes(p->hdr, helper);
   return 0;
 }
 

@@ -37,6 +37,7 @@ struct StepArgs {
   int n_envs;
   int mode;
   int S, L, K, VT, NF, CMW;  // program dimensions (filled in by launch_step from the header)
+  int dcv_tile;              // contained vertices per pass of the directed search (launch_step)
   const int *order;          // [n_envs] env handled by CTA i, or nullptr = identity
   int first, count;          // this launch covers dispatch positions [first, first + count)
   int *cost;                 // [n_envs] SM cycles >> 6 this call cost each env, or nullptr
@@ -58,7 +59,7 @@ struct RenderArgs {
 
 // host-side launchers (defined in the .cu files)
 constexpr int kMaxForceOps = 32;
-int env_smem_bytes(const int32_t *hdr);
+int env_smem_bytes(const int32_t *hdr, bool helper = true);
 int candidate_matrix_words(const void *host_blob);
 // [first, first + count): dispatch positions covered by this launch (count < 0: all);
 // resident_envs_per_sm > 0 pads the shared-memory request so that at most that many envs

@@ -49,16 +49,19 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, plist, kscr, kscr_bytes, total;
+  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, plist, kscr, kscr_bytes, tile, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
-#define DCV_TILE 32     /* contained vertices per pass of _directed_collision_vectors */
+/* contained vertices per pass of _directed_collision_vectors: one pass covers any outline when the
+   step is bound by its longest env (few envs per SM, shared memory to spare); the small tile keeps
+   the record small when the batch is large and residency is what counts */
+#define DCV_TILE_MAX 32
+#define DCV_TILE_MIN 8
 #define NEAR_SKIN 0.02
-#define STEP_WARPS 2   /* warps of an env's CTA: the owner and (optionally) its helper, see moog_step_kernel */
 #define NEAR_CAP 512  /* near-list entries; more near pairs than this -> every pair is tested */
 
-__host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW) {
+__host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW, int warps, int tile) {
   SmemLayout L;
   int o = 0;
   L.rec = o;   o += 224;  // EnvRec (static_assert below)
@@ -80,19 +83,20 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.cmask = o; o += 4 * (CMW > 0 ? CMW : 1);
   L.nearp = o; o += CMW > 0 ? 4 * NEAR_CAP : 4;
   L.hdr = o;   o += 4 * MOOG_HDR_WORDS;
-  L.scratch = o; o += 64 * STEP_WARPS;  // one per warp (main, helper)
+  L.scratch = o; o += 64 * warps;  // one per warp (owner, helper)
   o = (o + 7) & ~7;
   L.xchg = o;  o += 128;                  // main <-> helper: request words, the helper's CVec
-  L.plist = o; o += CMW > 0 ? 2 * 32 * DCV_TILE * STEP_WARPS : 8;  // crossing (vertex, edge) pairs, per warp
-  L.kscr_bytes = CMW > 0 ? 8 * 32 * DCV_TILE : 8;
-  L.kscr = o;  o += L.kscr_bytes * STEP_WARPS;
+  L.tile = tile;
+  L.plist = o; o += CMW > 0 ? 2 * 32 * tile * warps : 8;  // crossing (vertex, edge) pairs, per warp
+  L.kscr_bytes = CMW > 0 ? 8 * 32 * tile : 8;
+  L.kscr = o;  o += L.kscr_bytes * warps;
   L.total = (o + 15) & ~15;
   return L;
 }
 
-int env_smem_bytes(const int32_t *hdr) {
+int env_smem_bytes(const int32_t *hdr, bool helper) {
   return smem_layout(hdr[MOOG_H_N_SLOTS], hdr[MOOG_H_N_VTX] > 0 ? hdr[MOOG_H_N_VTX] : 1, hdr[MOOG_H_N_ENVF],
-                     hdr[MOOG_H_CMASK_WORDS]).total;
+                     hdr[MOOG_H_CMASK_WORDS], helper ? 2 : 1, helper ? DCV_TILE_MAX : DCV_TILE_MIN).total;
 }
 
 // words of the candidate matrices of all collision ops (see MOOG_H_CMASK_WORDS)
@@ -120,6 +124,7 @@ struct Env {
   unsigned long long *kscr;
   unsigned char *xchg;
   unsigned short *plist;
+  int dcv_tile;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -179,7 +184,8 @@ __device__ __forceinline__ Env env_view() {
   e.scratch = base + r->lay.scratch + 64 * warp;
   e.kscr = (unsigned long long *)(base + r->lay.kscr + r->lay.kscr_bytes * warp);
   e.xchg = base + r->lay.xchg;
-  e.plist = (unsigned short *)(base + r->lay.plist) + 32 * DCV_TILE * warp;
+  e.plist = (unsigned short *)(base + r->lay.plist) + 32 * r->lay.tile * warp;
+  e.dcv_tile = r->lay.tile;
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x & 31;
@@ -718,6 +724,7 @@ __device__ inline Aff rel_motion_matrix(const Env &e, int ps, int as, double dt)
   Aff t123 = aff_then(t12, m3);
   return aff_then(t123, m4);
 }
+template <int TILE>
 __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, int s0, int s1, double dt, CVec &o) {
   o.has_point = o.future = o.has_since = 0;
   o.px = o.py = o.nx = o.ny = o.sx = o.sy = o.qx = o.qy = 0.0;
@@ -772,8 +779,8 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
   ctr_add(e, CT_NARROW, clock64() - tp0);
   ctr_add(e, CT_COLL, n_in);
 #endif
-  for (int vbase = 0; vbase < n_in; vbase += DCV_TILE) {
-    const int cnt = min(DCV_TILE, n_in - vbase);
+  for (int vbase = 0; vbase < (TILE >= MAXV ? 1 : n_in); vbase += TILE) {  // TILE >= MAXV: one pass covers any outline
+    const int cnt = min(TILE, n_in - vbase);
 #ifdef MOOG_PROFILE_DCV
     long long tp1 = clock64();
 #endif
@@ -945,7 +952,10 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
 
 __device__ __noinline__ void directed_collision_vectors(const Env &, int s0, int s1, double dt, CVec &o) {
   const Env e = env_view();
-  directed_collision_vectors_impl(e, s0, s1, dt, o);
+  if (e.dcv_tile == DCV_TILE_MAX)
+    directed_collision_vectors_impl<DCV_TILE_MAX>(e, s0, s1, dt, o);
+  else
+    directed_collision_vectors_impl<DCV_TILE_MIN>(e, s0, s1, dt, o);
 }
 
 // collisions.py:235-289 _get_collision_vectors
@@ -2695,7 +2705,7 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
 
   ProgramView pv = view_of(a.blob);
   const int NF = a.NF;
-  const SmemLayout lay = smem_layout(a.S, a.VT > 0 ? a.VT : 1, NF, a.CMW);
+  const SmemLayout lay = smem_layout(a.S, a.VT > 0 ? a.VT : 1, NF, a.CMW, (int)(blockDim.x >> 5), a.dcv_tile);
   unsigned char *base = smem_raw;
   {
     int *h = (int *)(base + lay.hdr);
@@ -2889,7 +2899,7 @@ cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stre
                         int count, int resident_envs_per_sm, bool helper) {
   if (count < 0) count = a.n_envs - first;
   if (a.n_envs <= 0 || count <= 0) return cudaSuccess;
-  int per_env = env_smem_bytes(hdr);
+  int per_env = env_smem_bytes(hdr, helper);
   const int warps = 1;
   size_t smem = (size_t)per_env * warps;
   {
@@ -2925,6 +2935,7 @@ cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stre
   b.VT = hdr[MOOG_H_N_VTX];
   b.NF = hdr[MOOG_H_N_ENVF];
   b.CMW = hdr[MOOG_H_CMASK_WORDS];
+  b.dcv_tile = helper ? DCV_TILE_MAX : DCV_TILE_MIN;
   moog_step_kernel<<<blocks, helper ? 64 : 32, smem, stream>>>(b);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
