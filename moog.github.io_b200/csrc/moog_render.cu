@@ -402,8 +402,10 @@ __device__ inline unsigned color_to_ink(int cmap, double c0, double c1, double c
   return r8 | (g8 << 8) | (b8 << 16) | (to_u8(opacity) << 24);
 }
 
-#define ITEM_CAP 512 /* (sprite, row) items whose spans are precomputed, per env */
-struct RenderLayout { int canvas, ivtx, erec, items, ink, ymin, ymax, horiz, nedge, ibase, tmp, total; };
+/* (sprite, row) items whose spans are precomputed, per env: 512, more for scenes with many
+   sprites (a pacman maze has ~180), the rest is scan-converted by the row threads directly */
+__host__ __device__ inline int item_cap(int S) { return S * 8 < 512 ? 512 : (S * 8 > 2048 ? 2048 : S * 8); }
+struct RenderLayout { int canvas, ivtx, erec, items, ink, ymin, ymax, horiz, nedge, ibase, tmp, cap, total; };
 
 // H, W: canvas size (anti_aliasing x image size); OW: image width
 __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int VT, int OW) {
@@ -416,7 +418,8 @@ __host__ __device__ inline RenderLayout render_layout(int H, int W, int S, int V
   L.ivtx = o;
   L.items = o;
   {
-    int a = 8 * VT, b = 4 * (1 + ITEM_SPANS) * ITEM_CAP;
+    L.cap = item_cap(S);
+    int a = 8 * VT, b = 4 * (1 + ITEM_SPANS) * L.cap;
     o += a > b ? a : b;
   }
   L.ink = o;    o += 4 * S;
@@ -522,7 +525,7 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
           // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
           int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
           int rows = hi >= lo ? hi - lo + 1 : 0;
-          if (rows > 0 && acc + rows <= ITEM_CAP) {
+          if (rows > 0 && acc + rows <= lay.cap) {
             sibase[s] = acc;
             acc += rows;
           }
