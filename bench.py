@@ -340,7 +340,7 @@ def run_ours(args):
     from moog_b200.batched_env import TimeStep
     host_ts = TimeStep(host_step_type, host_reward, None, {'image': host_frames})
     for _ in range(2):
-        env.step_to_host(host_actions, host_ts)
+        env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks)
     torch.cuda.synchronize()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -350,7 +350,7 @@ def run_ours(args):
         # H2D of the actions, the step, the frames rendered in 4 env ranges with the D2H
         # copy of each range overlapping the next one's render; returns when the host
         # buffers hold the whole TimeStep (the caller owns it now)
-        env.step_to_host(host_actions, host_ts)
+        env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks)
     e1.record()
     torch.cuda.synchronize()
     e2e_value = world * E * args.steps / (mdist.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3)
@@ -425,6 +425,7 @@ def main():
     ap.add_argument('--episode', type=int, default=100, help='episode length used to stagger phases')
     ap.add_argument('--burn-in', type=int, default=130, help='untimed steps before the timed region')
     ap.add_argument('--no-clocks', action='store_true')
+    ap.add_argument('--e2e-chunks', type=int, default=4, help='env ranges the e2e arm renders / copies in')
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
