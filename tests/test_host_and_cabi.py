@@ -273,3 +273,30 @@ print('OK')
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and 'OK' in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize('name,slots,K,action_dim', [
+    ('colliding_predators84', 10, 10, 2), ('cleanup64', 31, 5, 6), ('synthetic32', 32, 10, 1)])
+def test_baseline_configs_of_this_package_compile_and_step(name, slots, K, action_dim):
+    """The BASELINE.json configs shipped in moog_b200/configs (this repo's own
+    MOOG-compatible host package, no reference needed) compile and step on the oracle."""
+    import importlib
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+    cfg = importlib.import_module('moog_b200.configs.' + name).get_config()
+    np.random.seed(2)
+    states = [cfg['state_initializer']() for _ in range(3)]
+    prog = compiler.compile_config(cfg, states)
+    assert (prog.n_slots, prog.K, max(prog.action_dim, 1)) == (slots, K, action_dim)
+    arr = compiler.pack_states(prog, states)
+    orc = Oracle(prog, arr)
+    orc.post_reset()
+    rng = np.random.RandomState(1)
+    before = orc.dyn.copy()
+    for _ in range(5):
+        orc.step(rng.uniform(-1, 1, size=(3, action_dim)),
+                 rule_noise=rng.uniform(size=(3, max(prog.rule_noise_dim, 1))) if prog.rule_noise_dim else None)
+    assert (orc.envi[:, 2] == 0).all() and not np.array_equal(orc.dyn, before)
+    if prog.render is not None:
+        assert orc.render().shape == (3, prog.render['height'], prog.render['width'], 3)
