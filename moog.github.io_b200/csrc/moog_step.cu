@@ -49,7 +49,7 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, plist, kscr, kscr_bytes, tile, total;
+  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, mbar, plist, kscr, kscr_bytes, tile, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
@@ -86,6 +86,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.scratch = o; o += 64 * warps;  // one per warp (owner, helper)
   o = (o + 7) & ~7;
   L.xchg = o;  o += 128;                  // main <-> helper: request words, the helper's CVec
+  L.mbar = o;  o += 16;                   // mbarrier of the bulk (TMA) loads of the record
   L.tile = tile;
   L.plist = o; o += CMW > 0 ? 2 * 32 * tile * warps : 8;  // crossing (vertex, edge) pairs, per warp
   L.kscr_bytes = CMW > 0 ? 8 * 32 * tile : 8;
@@ -125,6 +126,7 @@ struct Env {
   unsigned char *xchg;
   unsigned short *plist;
   int dcv_tile;
+  unsigned long long *mbar;
   // program (global memory, read-only)
   const int32_t *hdr;
   const moog_op *ops;
@@ -186,6 +188,7 @@ __device__ __forceinline__ Env env_view() {
   e.xchg = base + r->lay.xchg;
   e.plist = (unsigned short *)(base + r->lay.plist) + 32 * r->lay.tile * warp;
   e.dcv_tile = r->lay.tile;
+  e.mbar = (unsigned long long *)(base + r->lay.mbar);
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x & 31;
@@ -2640,26 +2643,88 @@ __device__ __noinline__ void copy_i(int *dst, const int *src, int n, int lane) {
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
+// Bulk asynchronous copies (TMA, `cp.async.bulk`, SASS UBLKCP): the big arrays of the record --
+// dyn, stat and the cached vertices, whose rows are multiples of 16 bytes -- move between HBM
+// and shared memory without going through the warp's registers; one lane issues them, the copy
+// engine completes them on an mbarrier (loads) or a bulk group (stores).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool bulk_ok(const void *g, const void *sm, size_t bytes) {
+  return bytes >= 16 && (((size_t)g | (size_t)smem_u32(sm) | bytes) & 15) == 0;
+}
+__device__ __forceinline__ void bulk_load(void *sm, const void *g, unsigned bytes, unsigned long long *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(sm)),
+               "l"(g), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *g, const void *sm, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(smem_u32(sm)), "r"(bytes)
+               : "memory");
+}
+
 __device__ inline void load_env(const Env &e, const moog_state &st, size_t n, bool with_envi) {
-  int S = e.S, NF = e.hdr[MOOG_H_N_ENVF];
-  copy_d(e.dyn, st.dyn + n * MOOG_DYN_FIELDS * S, MOOG_DYN_FIELDS * S, e.lane);
-  copy_d(e.stat, st.stat + n * MOOG_STAT_FIELDS * S, MOOG_STAT_FIELDS * S, e.lane);
+  const int S = e.S, NF = e.hdr[MOOG_H_N_ENVF], VT = e.hdr[MOOG_H_N_VTX];
+  const double *gdyn = st.dyn + n * MOOG_DYN_FIELDS * S, *gstat = st.stat + n * MOOG_STAT_FIELDS * S;
+  const double *gvtx = st.vtx + n * 2 * (size_t)VT;
+  const size_t bdyn = 8 * (size_t)MOOG_DYN_FIELDS * S, bstat = 8 * (size_t)MOOG_STAT_FIELDS * S, bvtx = 16 * (size_t)VT;
+  const bool kd = bulk_ok(gdyn, e.dyn, bdyn), ks = bulk_ok(gstat, e.stat, bstat), kv = bulk_ok(gvtx, e.vtx, bvtx);
+  const unsigned mb = smem_u32(e.mbar);
+  if (e.lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned tx = (unsigned)((kd ? bdyn : 0) + (ks ? bstat : 0) + (kv ? bvtx : 0));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tx) : "memory");
+    if (kd) bulk_load(e.dyn, gdyn, (unsigned)bdyn, e.mbar);
+    if (ks) bulk_load(e.stat, gstat, (unsigned)bstat, e.mbar);
+    if (kv) bulk_load(e.vtx, gvtx, (unsigned)bvtx, e.mbar);
+  }
+  wsync();
+  // the small / oddly sized arrays go through the lanes while the bulk copies are in flight
+  if (!kd) copy_d(e.dyn, gdyn, MOOG_DYN_FIELDS * S, e.lane);
+  if (!ks) copy_d(e.stat, gstat, MOOG_STAT_FIELDS * S, e.lane);
   copy_i(e.meta, st.meta + n * MOOG_META_FIELDS * S, MOOG_META_FIELDS * S, e.lane);
   copy_i(e.cnt, st.cnt + n * MOOG_MAX_LAYERS, MOOG_MAX_LAYERS, e.lane);
   copy_d(e.envf, st.envf + n * NF, NF, e.lane);
-  copy_d((double *)e.vtx, st.vtx + n * 2 * (size_t)e.hdr[MOOG_H_N_VTX], 2 * e.hdr[MOOG_H_N_VTX], e.lane);
+  if (!kv) copy_d((double *)e.vtx, gvtx, 2 * VT, e.lane);
   if (with_envi) copy_i(e.envi, st.envi + n * MOOG_ENVI_WORDS, MOOG_ENVI_WORDS, e.lane);
+  // wait for the bytes (phase 0 of the barrier: this is its only use in the launch)
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MOOG_LOAD_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra MOOG_LOAD_DONE;\n"
+      "bra MOOG_LOAD_WAIT;\n"
+      "MOOG_LOAD_DONE:\n"
+      "}" ::"r"(mb)
+      : "memory");
+  wsync();
 }
 
 __device__ inline void store_env(const Env &e, const moog_state &st, size_t n) {
-  int S = e.S, NF = e.hdr[MOOG_H_N_ENVF];
-  copy_d(st.dyn + n * MOOG_DYN_FIELDS * S, e.dyn, MOOG_DYN_FIELDS * S, e.lane);
-  copy_d(st.stat + n * MOOG_STAT_FIELDS * S, e.stat, MOOG_STAT_FIELDS * S, e.lane);
+  const int S = e.S, NF = e.hdr[MOOG_H_N_ENVF], VT = e.hdr[MOOG_H_N_VTX];
+  double *gdyn = st.dyn + n * MOOG_DYN_FIELDS * S, *gstat = st.stat + n * MOOG_STAT_FIELDS * S;
+  double *gvtx = st.vtx + n * 2 * (size_t)VT;
+  const size_t bdyn = 8 * (size_t)MOOG_DYN_FIELDS * S, bstat = 8 * (size_t)MOOG_STAT_FIELDS * S, bvtx = 16 * (size_t)VT;
+  const bool kd = bulk_ok(gdyn, e.dyn, bdyn), ks = bulk_ok(gstat, e.stat, bstat), kv = bulk_ok(gvtx, e.vtx, bvtx);
+  // the lanes' shared-memory writes become visible to the copy engine (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  wsync();
+  if (e.lane == 0) {
+    if (kd) bulk_store(gdyn, e.dyn, (unsigned)bdyn);
+    if (ks) bulk_store(gstat, e.stat, (unsigned)bstat);
+    if (kv) bulk_store(gvtx, e.vtx, (unsigned)bvtx);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  if (!kd) copy_d(gdyn, e.dyn, MOOG_DYN_FIELDS * S, e.lane);
+  if (!ks) copy_d(gstat, e.stat, MOOG_STAT_FIELDS * S, e.lane);
   copy_i(st.meta + n * MOOG_META_FIELDS * S, e.meta, MOOG_META_FIELDS * S, e.lane);
   copy_i(st.cnt + n * MOOG_MAX_LAYERS, e.cnt, MOOG_MAX_LAYERS, e.lane);
   copy_d(st.envf + n * NF, e.envf, NF, e.lane);
-  copy_d(st.vtx + n * 2 * (size_t)e.hdr[MOOG_H_N_VTX], (const double *)e.vtx, 2 * e.hdr[MOOG_H_N_VTX], e.lane);
+  if (!kv) copy_d(gvtx, (const double *)e.vtx, 2 * VT, e.lane);
   copy_i(st.envi + n * MOOG_ENVI_WORDS, e.envi, MOOG_ENVI_WORDS, e.lane);
+  if (e.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // done before the CTA retires
+  wsync();
 }
 
 // environment.py:88-96: task / action reset, every rule reset and stepped once
