@@ -268,7 +268,8 @@ def run_ours(args):
     E = args.envs
     seed = mdist.rank_seed(1234, rank)
     states = _host_states(config, args.pool, seed)
-    env = BatchedEnvironment(**config, num_envs=E, device=dev, seed=seed, initial_states=states)
+    env = BatchedEnvironment(**config, num_envs=E, device=dev, seed=seed, initial_states=states,
+                             reset_mode=args.reset_mode)
     eng = env.engine
     prog = env.program
     ad = env.action_dim
@@ -294,7 +295,7 @@ def run_ours(args):
         if t < episode:
             eng.state.envi[:, 1] = torch.where(phase == t, torch.ones_like(phase, dtype=torch.int32),
                                                eng.state.envi[:, 1])
-        eng.env_step(dev_actions)
+        eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'))
     eng.stats.zero_()
     torch.cuda.synchronize()
 
@@ -304,7 +305,7 @@ def run_ours(args):
 
     # ---- device-resident arm ------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        eng.env_step(dev_actions)
+        eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'))
         eng.render()
     torch.cuda.synchronize()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -318,7 +319,7 @@ def run_ours(args):
     for k in range(args.steps):
         flush.fill_(k & 255)          # evict L2 between timed iterations (untimed)
         ev[k][0].record()
-        eng.env_step(dev_actions)
+        eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'))
         ev[k][1].record()
         eng.render()
         ev[k][2].record()
@@ -378,6 +379,8 @@ def run_ours(args):
                    'l2': 'flushed between timed iterations (256 MiB fill, untimed)',
                    'phases': 'uniform mix of episode phases after {} burn-in steps with staggered resets'.format(args.burn_in),
                    'state_record_bytes': int(record_bytes),
+                   'resets': ('device-side sampler' if args.reset_mode == 'device' else
+                              'pool of {} host-generated initial states'.format(len(states))),
                    'step_launch': dict(zip(('resident_envs_per_sm', 'warps_per_env', 'smem_bytes_per_env'),
                                            eng.dev_program.step_launch_info(E)))},
         'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
@@ -425,6 +428,8 @@ def main():
     ap.add_argument('--episode', type=int, default=100, help='episode length used to stagger phases')
     ap.add_argument('--burn-in', type=int, default=130, help='untimed steps before the timed region')
     ap.add_argument('--no-clocks', action='store_true')
+    ap.add_argument('--reset-mode', default='pool', choices=['pool', 'device'],
+                    help="'device': resetting envs draw their generated sprites on the GPU")
     ap.add_argument('--e2e-chunks', type=int, default=4, help='env ranges the e2e arm renders / copies in')
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')

@@ -72,6 +72,10 @@ typedef struct {
                           events, SM cycles the env's warp spent in the kernel, 3 spare          */
   double *stats;       /* [4]  += sum reward, sum finished-episode length, finished episodes,
                           env-steps; the only quantity ever reduced across GPUs                 */
+  int32_t sample_resets; /* non-zero (and the program has MOOG_Z_* ops): an env that resets takes
+                            pool entry 0 as its template and draws its generated sprites afresh on
+                            the device (Philox keyed by seed, env, episode) instead of copying a
+                            whole pool entry                                                       */
 } moog_step_io;
 
 /* Upload a compiled program (host pointer to the blob).  Replaces nothing in the

@@ -11,6 +11,8 @@
  *     moog_op ops[hdr[MOOG_H_N_OPS]]
  *     int32   ipool[hdr[MOOG_H_N_IPOOL]]      (padded to a multiple of 2)
  *     moog_ex expr[hdr[MOOG_H_N_EXPR]]
+ *     double  dpool[hdr[MOOG_H_N_DPOOL]]      (shape table and sampler parameters of the
+ *                                              device-side reset sampler; may be empty)
  *
  * Sections of `ops` (forces, correctives, rules, tasks, actions, conditions)
  * are addressed by (start, count) pairs in the header.  Layer lists live in
@@ -112,6 +114,10 @@ enum {
   MOOG_H_VOFF,           /* index in ipool of voff[S+1]: first cached vertex of each slot */
   MOOG_H_LAYER_OFF = 32, /* MOOG_MAX_LAYERS+1 words */
   MOOG_H_N_VTX = 49,     /* VT: cached vertices per env */
+  MOOG_H_RESET = 51,      /* first MOOG_Z_* op of the device-side reset sampler */
+  MOOG_H_N_RESET = 52,    /* number of them (0: resets draw from the caller's pool only) */
+  MOOG_H_N_DPOOL = 53,    /* doubles in dpool */
+  MOOG_H_SHAPE_TAB = 54,  /* index in ipool of shape_off[n_shapes]: offset in dpool of each shape record */
   MOOG_H_CMASK_WORDS = 50 /* 32-bit words of the per-env broad-phase candidate matrices of all
                              MOOG_F_COLLISION ops (rows = capacity of layer a, ceil(capacity of
                              layer b / 32) words per row).  Derived: moog_program_create fills
@@ -169,6 +175,13 @@ enum {
   MOOG_A_GRID,             /* p0 scaling p1 momentum      grid.py:52-70        */
   MOOG_A_SET_POSITION,     /* p0 inertia                  set_position.py:34-47 */
 
+  /* device-side reset sampler (state_initialization/sprite_generators.py:26-105 for initializers
+   * made of fixed sprites and generate_sprites groups): i0 first slot, i1 number of sprites,
+   * i2,i3 ipool list of the slots the new sprites must not overlap (`without_overlapping`),
+   * i4 ipool index of the sampler table (MOOG_Z_N_ATTRS entries of 3 ints: kind, dpool index, n),
+   * flags MOOG_FL_DISJOINT / MOOG_FL_FAIL_GRACEFULLY, p0 max_recursion_depth */
+  MOOG_Z_GENERATE = 192,
+
   /* state conditions (value = double; used by MOOG_T_RESET / MOOG_R_COND_BEGIN) */
   MOOG_SC_ALL = 160,       /* i0,i1 layer list; i2 sprite expr: all(expr(s))   */
   MOOG_SC_ANY,             /* any(expr(s))                                     */
@@ -198,6 +211,22 @@ enum {
 #define MOOG_FL_PREVENT_BACKTRACKING    256
 #define MOOG_FL_ALLOW_WALL_BACKTRACKING 512
 #define MOOG_FL_ONLY_TURN_AT_WALL       1024
+#define MOOG_FL_DISJOINT                2048
+#define MOOG_FL_FAIL_GRACEFULLY         4096
+
+/* Sampler table of a MOOG_Z_GENERATE op: one entry per sprite factor in the order of the
+ * MOOG_AT_* attribute ids, then the shape.  kind: constant (dpool[idx]); uniform: value =
+ * float32(lo + (hi - lo) * u), lo = dpool[idx], hi = dpool[idx + 1] (distributions.py:71-90,
+ * Continuous samples are float32); discrete: one of the n values dpool[idx ..] with equal
+ * probability (for the shape entry the values are shape ids).
+ * Shape record in dpool (one per distinct outline, sprite.py:329-424): [0] number of vertices nv,
+ * [1] 1 if the shape is named 'circle', [2],[3] rotational inertia per unit mass about the centroid
+ * (x, y parts), [4],[5] centroid of the raw outline (added to the position, sprite.py:389-406),
+ * [6 ...] the nv centroid-centred vertices (x, y). */
+#define MOOG_Z_N_ATTRS 14
+#define MOOG_Z_SHAPE_ATTR 13
+enum { MOOG_ZK_CONST = 0, MOOG_ZK_UNIFORM32 = 1, MOOG_ZK_DISCRETE = 2 };
+#define MOOG_ERR_RESET_REJECTED  32u /* sprite_generators.py:92-98 RecursionError (no room for a sprite) */
 
 /* Maze record in envf (maze_lib/maze.py:20-35, Maze.from_state :38-84, evaluated by the host when
  * a state is packed -- the wall sprites never move): [0] = maze_size N (<= MOOG_MAX_MAZE),

@@ -163,7 +163,7 @@ class Engine(object):
                 self.dev_program.handle, ctypes.byref(st), self.n, _ptr(rn), self._stream()))
 
     def env_step(self, actions=None, noise=None, rule_noise=None, auto_reset=True,
-                 reset_index=None, want_counters=False):
+                 reset_index=None, want_counters=False, sample_resets=False):
         p = self.program
         act = self._as_f64(actions, max(p.action_dim, 1)) if actions is not None else None
         nz = self._as_f64(noise, p.K * p.noise_dim) if (noise is not None and p.noise_dim) else None
@@ -180,6 +180,7 @@ class Engine(object):
             io.pool = ctypes.pointer(pool_struct)
             io.pool_size = self.pool.n
         io.reset_index = _ptr(ri)
+        io.sample_resets = 1 if sample_resets else 0
         io.seed = (self.seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
         io.reward, io.step_type, io.discount = _ptr(self.reward), _ptr(self.step_type), _ptr(self.discount)
         io.counters = _ptr(self.counters) if want_counters else None
@@ -231,7 +232,7 @@ class BatchedEnvironment(object):
     def __init__(self, state_initializer, physics, task, action_space, observers,
                  game_rules=(), meta_state_initializer=None, *, num_envs,
                  device='cuda', pool_size=None, seed=0, layer_capacity=None,
-                 initial_states=None):
+                 initial_states=None, reset_mode='pool'):
         if meta_state_initializer is not None and meta_state_initializer() is not None:
             raise compiler.CompileError(
                 'meta_state is an arbitrary Python object in MOOG; the device '
@@ -243,7 +244,14 @@ class BatchedEnvironment(object):
         if initial_states is None:
             pool_size = int(pool_size or min(self.num_envs, 256))
             initial_states = [state_initializer() for _ in range(pool_size)]
-        self.program = compiler.compile_config(config, initial_states, layer_capacity)
+        if reset_mode not in ('pool', 'device'):
+            raise ValueError("reset_mode must be 'pool' or 'device'")
+        self.reset_mode = reset_mode
+        self.program = compiler.compile_config(config, initial_states, layer_capacity,
+                                               reset_sampler=(reset_mode == 'device'))
+        if reset_mode == 'device':
+            # pool entry 0 is the template the device sampler starts every reset from
+            initial_states = [self.program.reset_template] + list(initial_states)
         self._pool_arrays = compiler.pack_states(self.program, initial_states)
         self.engine = Engine(self.program, self.num_envs, device, seed)
         self.engine.set_pool(self._pool_arrays)
@@ -262,6 +270,16 @@ class BatchedEnvironment(object):
     def reset(self):
         """environment.py:82-96 for every env."""
         e = self.engine
+        if self.reset_mode == 'device':
+            # every env is marked terminated; the step kernel then resets it (environment.py:100-101)
+            # and draws its generated sprites on the device
+            for k in DeviceState.KEYS:
+                getattr(e.state, k).copy_(getattr(e.pool, k)[0:1].expand_as(getattr(e.state, k)))
+            e.state.envi.zero_()
+            e.state.envi[:, 1] = 1
+            e.env_step(None, sample_resets=True)
+            self._started = True
+            return self._timestep()
         idx = torch.from_numpy(self._rng.randint(0, e.pool.n, size=self.num_envs)).to(e.device)
         for k in DeviceState.KEYS:
             if k == 'envi':
@@ -281,7 +299,7 @@ class BatchedEnvironment(object):
         concatenation in the order of `program.action_layout`)."""
         if not self._started:
             return self.reset()
-        self.engine.env_step(self._flatten_action(action))
+        self.engine.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'))
         return self._timestep()
 
     def step_to_host(self, action, host, chunks=4):
@@ -294,7 +312,7 @@ class BatchedEnvironment(object):
         if not self._started:
             self.reset()
         else:
-            self.engine.env_step(self._flatten_action(action))
+            self.engine.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'))
         e = self.engine
         main = torch.cuda.current_stream(e.device)
         if self._copy_stream is None:

@@ -29,7 +29,7 @@ class MoogStepIO(ctypes.Structure):
                 ('reset_index', ctypes.c_void_p), ('seed', ctypes.c_uint64),
                 ('reward', ctypes.c_void_p), ('step_type', ctypes.c_void_p),
                 ('discount', ctypes.c_void_p), ('counters', ctypes.c_void_p),
-                ('stats', ctypes.c_void_p)]
+                ('stats', ctypes.c_void_p), ('sample_resets', ctypes.c_int32)]
 
 
 # every symbol include/moog_b200.h declares

@@ -49,6 +49,7 @@ H_RULE_NOISE_DIM = 30
 H_VOFF = 31
 H_LAYER_OFF = 32
 H_N_VTX = 49
+H_RESET, H_N_RESET, H_N_DPOOL, H_SHAPE_TAB = 51, 52, 53, 54
 
 F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
     F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION, F_MAZE_WALK = range(1, 10)
@@ -59,6 +60,9 @@ T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
     SC_BINARY, SC_NOT, SC_FIRST = 160, 161, 162, 163, 164, 165, 166, 167, 168
+Z_GENERATE = 192
+Z_N_ATTRS, Z_SHAPE_ATTR = 14, 13
+ZK_CONST, ZK_UNIFORM32, ZK_DISCRETE = 0, 1, 2
 
 FL_SYMMETRIC = 1
 FL_UPDATE_ANGLE_VEL = 2
@@ -71,6 +75,8 @@ FL_SAMPLE_ONE = 128
 FL_PREVENT_BACKTRACKING = 256
 FL_ALLOW_WALL_BACKTRACKING = 512
 FL_ONLY_TURN_AT_WALL = 1024
+FL_DISJOINT = 2048
+FL_FAIL_GRACEFULLY = 4096
 
 CMAP_NONE, CMAP_HSV = 0, 1
 PMOD_NONE, PMOD_FIRST_PERSON, PMOD_TORUS = 0, 1, 2
@@ -103,6 +109,8 @@ class Program(object):
         self.ops = []            # list of dict(kind, flags, i, p)
         self.ipool = []
         self.expr = []           # list of (op, arg, c)
+        self.dpool = []          # doubles: shape table / sampler parameters of the reset sampler
+        self.reset_shapes = []   # shape candidates of the reset sampler, by shape id
         self.sections = {}
         self.n_envf = 0
         self.maze_offsets = {}   # maze layer name -> envf offset of its maze record
@@ -224,7 +232,12 @@ class Program(object):
             hdr[H_R_MODIFIER] = r['modifier']
             hdr[H_R_MOD_LAYER] = r['modifier_layer']
         hdr[H_LAYER_OFF:H_LAYER_OFF + len(self.layer_off)] = self.layer_off
-        blob = hdr.tobytes() + ops.tobytes() + ipool.tobytes() + expr.tobytes()
+        start, count = self.sections.get('reset', (0, 0))
+        hdr[H_RESET], hdr[H_N_RESET] = start, count
+        hdr[H_N_DPOOL] = len(self.dpool)
+        hdr[H_SHAPE_TAB] = getattr(self, 'shape_tab', 0)
+        dpool = np.array(self.dpool, dtype='<f8')
+        blob = hdr.tobytes() + ops.tobytes() + ipool.tobytes() + expr.tobytes() + dpool.tobytes()
         hdr[H_BYTES] = len(blob)
         self.blob = hdr.tobytes() + blob[HDR_WORDS * 4:]
         self.header = hdr
@@ -582,7 +595,7 @@ def _compile_render(prog, observers):
 # entry points
 # ---------------------------------------------------------------------------
 
-def compile_config(config, sample_states, layer_capacity=None):
+def compile_config(config, sample_states, layer_capacity=None, reset_sampler=False):
     """Compile a MOOG config dict.
 
     Args:
@@ -629,7 +642,162 @@ def compile_config(config, sample_states, layer_capacity=None):
     _compile_actions(prog, config['action_space'])
     _compile_rules(prog, config.get('game_rules', ()))
     _compile_render(prog, config.get('observers', {}))
+    if reset_sampler:
+        _compile_reset_sampler(prog, config['state_initializer'])
     return prog.finalize()
+
+
+# ---------------------------------------------------------------------------
+# device-side reset sampler
+# ---------------------------------------------------------------------------
+
+_ATTR_KEYS = ('x', 'y', 'x_vel', 'y_vel', 'angle', 'angle_vel', 'mass', 'scale',
+              'aspect_ratio', 'c0', 'c1', 'c2', 'opacity')
+
+
+def _flatten_distribution(dist):
+    """Product / Continuous / Discrete tree -> {key: ('uniform', lo, hi) |
+    ('discrete', [values])}; anything else cannot run on the device."""
+    k = _kind(dist)
+    if k == 'Product':
+        out = {}
+        for c in dist.components:
+            out.update(_flatten_distribution(c))
+        return out
+    if k == 'Continuous':
+        if str(dist.dtype) != 'float32':
+            raise CompileError('the device sampler draws float32 Continuous factors only')
+        return {dist.key: ('uniform', float(dist.minval), float(dist.maxval))}
+    if k == 'Discrete':
+        if getattr(dist, 'probs', None) is not None:
+            raise CompileError('Discrete with explicit probabilities is not on the device sampler yet')
+        return {dist.key: ('discrete', list(dist.candidates))}
+    raise CompileError(
+        'factor distribution {} cannot be sampled on the device (supported: Product of '
+        'Continuous / Discrete / constants); use the host pool (reset_sampler=False)'.format(k))
+
+
+def _shape_record(shape):
+    """Shape record of include/moog_b200_program.h for one shape candidate."""
+    from moog import sprite as sprite_lib
+    sp = sprite_lib.Sprite(x=0., y=0., shape=shape)
+    base = np.asarray(sp._shape_path.vertices[:-1], dtype=np.float64)  # pylint: disable=protected-access
+    if len(base) > MAX_VERTS:
+        raise CompileError('sprite outline has {} vertices; the device path supports at most {}'.format(
+            len(base), MAX_VERTS))
+    ixy = np.asarray(sp._x_y_rotational_inertia, dtype=np.float64)  # pylint: disable=protected-access
+    centroid = np.asarray(sp.position, dtype=np.float64)             # (0, 0) + raw centroid
+    rec = [float(len(base)), 1.0 if (isinstance(shape, str) and shape == 'circle') else 0.0,
+           float(ixy[0]), float(ixy[1]), float(centroid[0]), float(centroid[1])]
+    rec += [float(v) for v in base.reshape(-1)]
+    return rec
+
+
+def _compile_reset_sampler(prog, state_initializer):
+    """Traces the state initializer (this repo's sprite_generators record what they
+    are asked for) and lowers every generate_sprites group to a MOOG_Z_GENERATE op."""
+    import inspect
+    from moog import sprite as sprite_lib
+    from moog.state_initialization import sprite_generators as sg
+    if not hasattr(sg, 'recording'):
+        raise CompileError('the device reset sampler needs this repo\'s moog.state_initialization package')
+    with sg.recording() as records:
+        state = state_initializer()
+    if list(state.keys()) != prog.layer_names:
+        raise CompileError('state initializer changed its layer set')
+    slot_of, layer_of = {}, {}
+    for l, name in enumerate(prog.layer_names):
+        for k, sp in enumerate(state[name]):
+            slot_of[id(sp)] = prog.layer_off[l] + k
+            layer_of[id(sp)] = l
+    defaults = {k: p.default for k, p in inspect.signature(sprite_lib.Sprite.__init__).parameters.items()
+                if p.default is not inspect.Parameter.empty}
+    shape_ids, shape_recs = {}, []
+
+    def shape_id(shape):
+        key = shape if isinstance(shape, str) else np.asarray(shape, dtype=np.float64).tobytes()
+        if key not in shape_ids:
+            shape_ids[key] = len(shape_recs)
+            shape_recs.append(_shape_record(shape))
+            prog.reset_shapes.append(shape)
+        return shape_ids[key]
+
+    specs = []
+    for rec in records:
+        if callable(rec['num_sprites']):
+            raise CompileError('a random number of generated sprites is not on the device sampler yet')
+        if len(rec['out']) != rec['num_sprites']:
+            raise CompileError('the traced initializer produced fewer sprites than asked for')
+        if not rec['out']:
+            continue
+        try:
+            slots = [slot_of[id(s)] for s in rec['out']]
+            avoid = [slot_of[id(s)] for s in rec['avoid']]
+        except KeyError:
+            raise CompileError('a generated or avoided sprite is not part of the returned state')
+        if slots != list(range(slots[0], slots[0] + len(slots))):
+            raise CompileError('the sprites of one generate_sprites call must stay together, in order, in one layer')
+        if len({layer_of[id(s)] for s in rec['out']}) != 1:
+            raise CompileError('the sprites of one generate_sprites call must stay in one layer')
+        if any(a >= slots[0] for a in avoid):
+            raise CompileError('generated sprites can only avoid sprites in earlier slots')
+        flat = _flatten_distribution(rec['factor_dist'])
+        lay = layer_of[id(rec['out'][0])]
+        if slots[0] + len(slots) != prog.layer_off[lay] + len(state[prog.layer_names[lay]]):
+            raise CompileError('generated sprites must be the last sprites of their layer')
+        table, meta_flags = [], 0
+        sampled32 = set()
+        for key in _ATTR_KEYS + ('shape',):
+            kind, payload = 'discrete', [defaults[key]]
+            if key in flat:
+                kind, payload = flat[key][0], list(flat[key][1:]) if flat[key][0] == 'uniform' else flat[key][1]
+            if kind == 'uniform':
+                table.append((ZK_UNIFORM32, payload))
+                sampled32.add(key)
+            else:
+                values = [shape_id(v) for v in payload] if key == 'shape' else [float(v) for v in payload]
+                if key == 'shape':
+                    for sid in values:
+                        if int(shape_recs[sid][0]) > prog.layer_vcap[lay]:
+                            raise CompileError(
+                                'a shape candidate has {} vertices, more than the sample states showed for layer '
+                                '{!r} ({}); pass more sample states'.format(
+                                    int(shape_recs[sid][0]), prog.layer_names[lay], prog.layer_vcap[lay]))
+                table.append((ZK_CONST if len(values) == 1 else ZK_DISCRETE, values))
+        if {'x_vel', 'y_vel'} <= sampled32:
+            meta_flags |= SF_VEL32
+        if 'angle_vel' in sampled32:
+            meta_flags |= 1 << SF_ANGVEL_SHIFT
+        if 'angle' in sampled32:
+            meta_flags |= 1 << SF_ANG_SHIFT
+        specs.append(dict(first=slots[0], count=len(slots), avoid=avoid, table=table, meta_flags=meta_flags,
+                          flags=(FL_DISJOINT if rec['disjoint'] else 0) | (
+                              FL_FAIL_GRACEFULLY if rec['fail_gracefully'] else 0),
+                          max_depth=float(rec['max_recursion_depth'])))
+    if not specs:
+        raise CompileError('the state initializer never called generate_sprites: nothing to sample on the device')
+    # covered slots of every layer must form the tail the template leaves to the sampler
+    shape_off = []
+    for rec_ in shape_recs:
+        shape_off.append(len(prog.dpool))
+        prog.dpool.extend(rec_)
+    prog.shape_tab = prog.add_ints(shape_off)
+    emitted = []
+    for sp_ in specs:
+        tab = []
+        for kind, values in sp_['table']:
+            tab += [kind, len(prog.dpool), len(values)]
+            prog.dpool.extend(float(v) for v in values)
+        a_start = prog.add_ints(sp_['avoid'])
+        t_start = prog.add_ints(tab)
+        emitted.append((sp_, a_start, t_start))
+    start = len(prog.ops)
+    for sp_, a_start, t_start in emitted:
+        prog.emit(Z_GENERATE, sp_['flags'],
+                  (sp_['first'], sp_['count'], a_start, len(sp_['avoid']), t_start, sp_['meta_flags']),
+                  (sp_['max_depth'],))
+    prog.sections['reset'] = (start, len(prog.ops) - start)
+    prog.reset_template = state
 
 
 def _scalar_kind(v):

@@ -48,7 +48,8 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
       hdr[MOOG_H_K] < 1)
     return MOOG_E_INVAL;
   size_t need = sizeof(int32_t) * MOOG_HDR_WORDS + sizeof(moog_op) * (size_t)hdr[MOOG_H_N_OPS] +
-                sizeof(int32_t) * (size_t)((hdr[MOOG_H_N_IPOOL] + 1) & ~1) + sizeof(moog_ex) * (size_t)hdr[MOOG_H_N_EXPR];
+                sizeof(int32_t) * (size_t)((hdr[MOOG_H_N_IPOOL] + 1) & ~1) + sizeof(moog_ex) * (size_t)hdr[MOOG_H_N_EXPR] +
+                sizeof(double) * (size_t)hdr[MOOG_H_N_DPOOL];
   if (need != nbytes) return MOOG_E_INVAL;
   if (hdr[MOOG_H_N_FORCES] > moog::kMaxForceOps) return MOOG_E_TOO_BIG;
   moog_program *p = (moog_program *)calloc(1, sizeof(moog_program));

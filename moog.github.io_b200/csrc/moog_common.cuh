@@ -16,6 +16,7 @@ struct ProgramView {
   const int32_t *ipool;
   const moog_ex *expr;
   const int32_t *voff;
+  const double *dpool;
 };
 
 __host__ __device__ inline ProgramView view_of(const void *blob) {
@@ -26,6 +27,7 @@ __host__ __device__ inline ProgramView view_of(const void *blob) {
   int npool = (v.hdr[MOOG_H_N_IPOOL] + 1) & ~1;
   v.expr = (const moog_ex *)(v.ipool + npool);
   v.voff = v.ipool + v.hdr[MOOG_H_VOFF];
+  v.dpool = (const double *)(v.expr + v.hdr[MOOG_H_N_EXPR]);
   return v;
 }
 

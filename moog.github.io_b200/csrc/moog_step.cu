@@ -2727,6 +2727,112 @@ __device__ inline void store_env(const Env &e, const moog_state &st, size_t n) {
   wsync();
 }
 
+// ---------------------------------------------------------------------------
+// Device-side reset sampler: one generate_sprites group
+// (state_initialization/sprite_generators.py:26-105) for this env.  Factors are drawn from
+// the Philox stream keyed by (seed, env, episode, slot, try, factor); the sprite is built
+// like Sprite.__init__ does on the host (sprite.py:261-424: centroid-centred outline scaled
+// by (scale, scale * aspect_ratio), rotated, translated; position += raw centroid;
+// circumscribed radius; inertia * scale^2) and redrawn while it overlaps a sprite it must avoid.
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void reset_generate(const Env &, const moog_op *op, const double *dpool,
+                                            const int32_t *shape_off, uint64_t seed) {
+  const Env e = env_view();
+  const int first = op->i[0], count = op->i[1];
+  const int32_t *avoid = e.ipool + op->i[2];
+  const int n_avoid = op->i[3];
+  const int32_t *tab = e.ipool + op->i[4];
+  int layer = 0;
+  for (int l = 0; l < e.L; ++l)
+    if (first >= LOFF(e, l) && first < LOFF(e, l + 1)) layer = l;
+  const int max_depth = (int)fmin(op->p[0], 1048575.0);
+  const uint32_t episode = (uint32_t)e.envi[MOOG_EI_EPISODES];
+  int placed = 0;
+  for (int k = 0; k < count; ++k) {
+    const int s = first + k;
+    bool stop = false;
+    for (int tries = 0;; ++tries) {
+      double v[MOOG_Z_N_ATTRS];
+#pragma unroll 1
+      for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
+        const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
+        if (kind == MOOG_ZK_CONST) {
+          v[a] = dpool[idx];
+        } else {
+          const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
+                                          ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | (uint32_t)a);
+          if (kind == MOOG_ZK_UNIFORM32) {
+            v[a] = (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);  // np.float32(rng.uniform(lo, hi))
+          } else {
+            int pick = (int)(u * n);
+            v[a] = dpool[idx + (pick < n ? pick : n - 1)];
+          }
+        }
+      }
+      const double *R = dpool + shape_off[(int)v[MOOG_Z_SHAPE_ATTR]];
+      const int nv = (int)R[0];
+      const double px = v[MOOG_AT_X] + R[4], py = v[MOOG_AT_Y] + R[5];
+      const double sx = v[MOOG_AT_SCALE], sy = v[MOOG_AT_SCALE] * v[MOOG_AT_ASPECT_RATIO];
+      double c = 1.0, sn = v[MOOG_AT_ANGLE];
+      if (v[MOOG_AT_ANGLE] != 0.0) {
+        const double2 cs = cos_sin_ol(v[MOOG_AT_ANGLE]);
+        c = cs.x;
+        sn = cs.y;
+      }
+      const double m00 = c * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = c * sy;
+      wsync();
+      double r = 0.0;
+      if (e.lane < nv) {
+        const double bx = R[6 + 2 * e.lane], by = R[7 + 2 * e.lane];
+        const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
+        e.vtx[e.voff[s] + e.lane] = make_double2(wx, wy);
+        const double rx = wx - px, ry = wy - py;
+        r = sqrt(rx * rx + ry * ry);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r = fmax(r, shflx_d(r, o));
+      if (e.lane == 0) {
+        DYN(e, MOOG_D_X, s) = px; DYN(e, MOOG_D_Y, s) = py;
+        DYN(e, MOOG_D_VX, s) = v[MOOG_AT_X_VEL]; DYN(e, MOOG_D_VY, s) = v[MOOG_AT_Y_VEL];
+        DYN(e, MOOG_D_ANG, s) = v[MOOG_AT_ANGLE]; DYN(e, MOOG_D_ANGVEL, s) = v[MOOG_AT_ANGLE_VEL];
+        STAT(e, MOOG_S_MASS, s) = v[MOOG_AT_MASS]; STAT(e, MOOG_S_SCALE, s) = v[MOOG_AT_SCALE];
+        STAT(e, MOOG_S_ASPECT, s) = v[MOOG_AT_ASPECT_RATIO];
+        STAT(e, MOOG_S_IX, s) = R[2] * (sx * sx); STAT(e, MOOG_S_IY, s) = R[3] * (sy * sy);
+        STAT(e, MOOG_S_MAXR, s) = r;
+        STAT(e, MOOG_S_C0, s) = v[MOOG_AT_C0]; STAT(e, MOOG_S_C1, s) = v[MOOG_AT_C1];
+        STAT(e, MOOG_S_C2, s) = v[MOOG_AT_C2]; STAT(e, MOOG_S_OPACITY, s) = v[MOOG_AT_OPACITY];
+        META(e, MOOG_M_SHAPE, s) = (int)v[MOOG_Z_SHAPE_ATTR];
+        META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
+        META(e, MOOG_M_NV, s) = nv;
+        e.cnt[layer] = s - LOFF(e, layer) + 1;
+      }
+      wsync();
+      refresh_all_boxes(e);
+      bool hit = false;
+      for (int q = 0; q < n_avoid; ++q) hit |= overlaps(e, s, avoid[q]);  // every pair is evaluated
+      if (op->flags & MOOG_FL_DISJOINT)
+        for (int j = first; j < s; ++j) hit |= overlaps(e, s, j);
+      if (!hit) break;
+      if (tries > max_depth) {  // sprite_generators.py:92-98
+        if (op->flags & MOOG_FL_FAIL_GRACEFULLY) {
+          stop = true;
+        } else {
+          const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_RESET_REJECTED;
+          wsync();
+          puti(e, &e.envi[MOOG_EI_ERR], err);
+          wsync();
+        }
+        break;
+      }
+    }
+    if (stop) break;
+    placed = k + 1;
+  }
+  wsync();
+  puti(e, &e.cnt[layer], first - LOFF(e, layer) + placed);
+  wsync();
+}
+
 // environment.py:88-96: task / action reset, every rule reset and stepped once
 __device__ inline void post_reset(const Env &e) {
   wsync();
@@ -2822,6 +2928,7 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
         idx = (int)(u * a.io.pool_size);
       }
       idx = idx < 0 ? 0 : (idx >= a.io.pool_size ? a.io.pool_size - 1 : idx);
+      if (a.io.sample_resets && pv.hdr[MOOG_H_N_RESET] > 0) idx = 0;  // pool entry 0 is the template
       src = &a.pool;
       row = (size_t)idx;
     }
@@ -2829,6 +2936,11 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
   }
   wsync();
   refresh_all_boxes(e);
+  if (do_reset && a.io.sample_resets && pv.hdr[MOOG_H_N_RESET] > 0) {
+    // the generated sprites of the template are drawn afresh for this env and episode
+    for (int z = 0; z < pv.hdr[MOOG_H_N_RESET]; ++z)
+      reset_generate(e, pv.ops + pv.hdr[MOOG_H_RESET] + z, pv.dpool, pv.ipool + pv.hdr[MOOG_H_SHAPE_TAB], a.io.seed);
+  }
 
   double reward = 0.0;
   int step_type = MOOG_STEP_MID;

@@ -4,9 +4,26 @@ a factor distribution, with optional rejection against overlap.
 Reference: moog/state_initialization/sprite_generators.py:26-190.
 """
 
+import contextlib
+
 import numpy as np
 
 from moog import sprite as sprite_lib
+
+# While a `recording()` block is active every generator call appends a record of what it was
+# asked to do and which sprites it produced.  moog_b200.compiler traces a state initializer with
+# it to lower the initializer to the device-side reset sampler.
+_RECORDS = None
+
+
+@contextlib.contextmanager
+def recording():
+    global _RECORDS
+    previous, _RECORDS = _RECORDS, []
+    try:
+        yield _RECORDS
+    finally:
+        _RECORDS = previous
 
 
 def generate_sprites(factor_dist, num_sprites=1, max_recursion_depth=int(1e4),
@@ -36,6 +53,11 @@ def generate_sprites(factor_dist, num_sprites=1, max_recursion_depth=int(1e4),
             out.append(candidate)
             if disjoint:
                 avoid = avoid + [candidate]
+        if _RECORDS is not None:
+            _RECORDS.append(dict(
+                factor_dist=factor_dist, num_sprites=num_sprites, disjoint=bool(disjoint),
+                avoid=list(without_overlapping), out=list(out),
+                max_recursion_depth=max_recursion_depth, fail_gracefully=bool(fail_gracefully)))
         return out
 
     return _generate

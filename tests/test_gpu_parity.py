@@ -262,3 +262,95 @@ def test_full_size_batch_matches_oracle_on_a_sample():
 def torch_index(a):
     import torch
     return torch.as_tensor(a, device='cuda:0')
+
+
+@pytest.mark.gpu
+def test_device_side_reset_sampler():
+    """reset_mode='device' (SURVEY section 8 f1): every resetting env draws its generated sprites
+    on the device.  The draws respect the factor distributions, the sprites are built like the
+    host Sprite builds them (sprite.py:329-424) and the rejection loop of
+    sprite_generators.py:69-105 leaves no forbidden overlap."""
+    import torch
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler as C
+    from moog_b200.batched_env import BatchedEnvironment
+    from moog_b200.configs import colliding_predators84
+    cfg = colliding_predators84.get_config()
+    np.random.seed(12)
+    states = [cfg['state_initializer']() for _ in range(8)]
+    N = 512
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=5, initial_states=states, reset_mode='device')
+    ts = env.reset()
+    assert bool((ts.step_type == 0).all())
+    eng, prog = env.engine, env.program
+    st = eng.state.download()
+    assert (st['envi'][:, 2] == 0).all(), 'error flags'
+    assert (st['cnt'][:, :3] == [4, 5, 1]).all()
+    lo = prog.layer_off
+    pred = slice(lo[1], lo[1] + 5)
+    agent = lo[2]
+    # factor ranges (colliding_predators.py:29-52); float32 draws
+    x, y = st['dyn'][:, 0, pred], st['dyn'][:, 1, pred]
+    scale, aspect = st['stat'][:, 1, pred], st['stat'][:, 2, pred]
+    ang, vx, w = st['dyn'][:, 4, pred], st['dyn'][:, 2, pred], st['dyn'][:, 5, pred]
+    assert scale.min() >= 0.1 and scale.max() < 0.15 and aspect.min() >= 0.75 and aspect.max() < 1.25
+    assert ang.min() >= 0 and ang.max() < 2 * np.pi + 1e-6 and np.abs(vx).max() <= 0.03 and np.abs(w).max() <= 0.05
+    for a in (scale, aspect, ang, vx, w):
+        assert np.array_equal(a, a.astype(np.float32).astype(np.float64)), 'Continuous factors are float32'
+    assert len(np.unique(scale)) > 0.9 * scale.size, 'the envs draw different sprites'
+    assert (st['stat'][:, 6:10, pred] == np.array([0., 1., 0.8, 255.])[None, :, None]).all()
+    assert (st['meta'][:, 1, pred] & 0x3f == 22).all()          # float32 velocity / angle_vel / angle
+    shapes = st['meta'][:, 0, pred]
+    assert set(np.unique(shapes)) == {0, 1, 2, 3, 4}, 'all five shape candidates occur'
+    # construction: world vertices, circumscribed radius, inertia as the host Sprite computes them
+    hdr = prog.header
+    blob = np.frombuffer(prog.blob, dtype=np.uint8)
+    n_ops, n_ip, n_ex = int(hdr[C.H_N_OPS]), (int(hdr[C.H_N_IPOOL]) + 1) & ~1, int(hdr[C.H_N_EXPR])
+    off = C.HDR_WORDS * 4 + 80 * n_ops
+    ipool = np.frombuffer(blob[off:off + 4 * n_ip].tobytes(), dtype='<i4')
+    dpool = np.frombuffer(blob[off + 4 * n_ip + 16 * n_ex:].tobytes(), dtype='<f8')
+    shape_off = ipool[int(hdr[C.H_SHAPE_TAB]):]
+    voff = util.prog_voff(prog)
+    worst = 0.0
+    for e in range(0, N, 37):
+        for s in range(lo[1], lo[1] + 5):
+            R = dpool[shape_off[st['meta'][e, 0, s]]:]
+            nv = int(R[0])
+            assert st['meta'][e, 2, s] == nv
+            base = R[6:6 + 2 * nv].reshape(nv, 2)
+            px, py = st['dyn'][e, 0, s], st['dyn'][e, 1, s]
+            sx = st['stat'][e, 1, s]
+            sy = sx * st['stat'][e, 2, s]
+            c, sn = np.cos(st['dyn'][e, 4, s]), np.sin(st['dyn'][e, 4, s])
+            want = np.stack([c * sx * base[:, 0] + -(sn * sy) * base[:, 1] + px,
+                             sn * sx * base[:, 0] + c * sy * base[:, 1] + py], axis=1)
+            got = st['vtx'][e, voff[s]:voff[s] + nv]
+            worst = max(worst, float(np.abs(got - want).max()))
+            rel = want - [px, py]
+            assert abs(st['stat'][e, 5, s] - np.sqrt((rel * rel).sum(axis=1)).max()) < 1e-14
+            assert abs(st['stat'][e, 3, s] - R[2] * sx * sx) < 1e-18 and abs(st['stat'][e, 4, s] - R[3] * sy * sy) < 1e-18
+    assert worst < 1e-15, worst      # cos / sin of the device vs libm: last-bit differences at most
+    # rejection: predators are mutually disjoint and clear of the walls, the agent is clear of both
+    pp = eng.overlap_pairs('predators', 'predators').cpu().numpy()
+    assert not (pp & ~np.eye(5, dtype=bool)[None]).any()
+    assert not eng.overlap_pairs('predators', 'walls').cpu().numpy().any()
+    assert not eng.overlap_pairs('agent', 'predators').cpu().numpy().any()
+    assert not eng.overlap_pairs('agent', 'walls').cpu().numpy().any()
+    # episodes end (timeout 200 / contact) and the envs are re-initialised with NEW draws
+    first_scale = scale.copy()
+    act = torch.zeros((N, 2), dtype=torch.float64)
+    for _ in range(205):
+        ts = env.step(act)
+    st2 = eng.state.download()
+    assert (st2['envi'][:, 3] >= 1).all(), 'every env finished at least one episode'
+    assert (st2['envi'][:, 2] == 0).all()
+    assert (st2['stat'][:, 1, pred] != first_scale).mean() > 0.95
+    # same seed -> same draws
+    env2 = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=5, initial_states=states, reset_mode='device')
+    env2.reset()
+    st3 = env2.engine.state.download()
+    for k in ('dyn', 'stat', 'meta', 'cnt'):
+        assert np.array_equal(st3[k], st[k]), k
+    for e in range(0, N, 61):     # (the vertex slots beyond a sprite's nv keep the template's stale values)
+        vlive = util.live_vertex_mask(prog, st['cnt'][e], st['meta'][e])
+        assert np.array_equal(st3['vtx'][e][vlive], st['vtx'][e][vlive])

@@ -300,3 +300,39 @@ def test_baseline_configs_of_this_package_compile_and_step(name, slots, K, actio
     assert (orc.envi[:, 2] == 0).all() and not np.array_equal(orc.dyn, before)
     if prog.render is not None:
         assert orc.render().shape == (3, prog.render['height'], prog.render['width'], 3)
+
+
+def test_reset_sampler_lowering():
+    """compile_config(reset_sampler=True) traces the state initializer (this repo's
+    sprite_generators record their calls) and lowers every generate_sprites group to a
+    MOOG_Z_GENERATE op; what cannot run on the device is refused at compile time."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler as C
+    from moog_b200.configs import colliding_predators84, pacman64
+    np.random.seed(8)
+    cfg = colliding_predators84.get_config()
+    states = [cfg['state_initializer']() for _ in range(6)]
+    prog = C.compile_config(cfg, states, reset_sampler=True)
+    start, count = prog.sections['reset']
+    ops = prog.ops[start:start + count]
+    assert [o['kind'] for o in ops] == [C.Z_GENERATE, C.Z_GENERATE]
+    pred, agent = ops
+    assert pred['i'][0] == prog.layer_off[1] and pred['i'][1] == 5 and pred['i'][3] == 4 and pred['flags'] & C.FL_DISJOINT
+    assert agent['i'][0] == prog.layer_off[2] and agent['i'][1] == 1 and agent['i'][3] == 9 and not agent['flags'] & C.FL_DISJOINT
+    assert pred['i'][5] == C.SF_VEL32 | (1 << C.SF_ANGVEL_SHIFT) | (1 << C.SF_ANG_SHIFT) and agent['i'][5] == 0
+    assert len(prog.reset_shapes) == 6          # 5 predator candidates + the agent's circle
+    tab = prog.ipool[pred['i'][4]:pred['i'][4] + 3 * C.Z_N_ATTRS]
+    kinds = tab[0::3]
+    assert kinds[0] == C.ZK_UNIFORM32 and kinds[C.Z_SHAPE_ATTR] == C.ZK_DISCRETE and kinds[6] == C.ZK_CONST
+    lo_hi = prog.dpool[tab[3 * 7 + 1]:tab[3 * 7 + 1] + 2]       # scale ~ U[0.1, 0.15)
+    assert lo_hi == [0.1, 0.15]
+    hdr = np.frombuffer(prog.blob[:256], dtype='<i4')
+    assert hdr[C.H_N_RESET] == 2 and hdr[C.H_N_DPOOL] == len(prog.dpool) and hdr[C.H_BYTES] == len(prog.blob)
+    # a program compiled without the sampler carries no reset section (old blobs stay valid)
+    plain = C.compile_config(cfg, states)
+    assert np.frombuffer(plain.blob[:256], dtype='<i4')[C.H_N_RESET] == 0
+    # an initializer that never calls generate_sprites (pacman builds its sprites by hand) is refused
+    pcfg = pacman64.get_config(0)
+    pstates = [pcfg['state_initializer']() for _ in range(2)]
+    with pytest.raises(C.CompileError):
+        C.compile_config(pcfg, pstates, reset_sampler=True)
