@@ -163,6 +163,10 @@ enum {
   MOOG_R_MODIFY_ON_CONTACT,      /* i0,i1 list0; i2,i3 list1; i4 -> ipool[4]: mod0 filt0 mod1 filt1  contact_rules.py:54-120 */
   MOOG_R_MODIFY_SPRITES,         /* i0,i1 list; i2 modifier, i3 filter; SAMPLE_ONE; i4 noise column  modify_sprites.py:35-52 */
   MOOG_R_COND_BEGIN,             /* i0 condition op index, i1 number of following rule ops guarded   conditional.py:55-58 */
+  MOOG_R_TIMED_BEGIN,            /* TimedRule / DelayedRule / TemporaryRule: i1 number of following rule ops guarded,
+                                    i2 envf slot of (steps_until_start, steps_until_stop), p0,p1 the interval
+                                    they are reset to                                                   timing.py:15-107 */
+  MOOG_R_KEEP_NEAR_CENTER,       /* i0 agent layer, i1,i2 list of the layers to move, p0,p1 grid cell    re_center.py:13-76 */
 
   /* tasks: i[5] = envf slot of the countdown */
   MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps  contact_reward.py:70-102 */

@@ -55,7 +55,7 @@ F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
     F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION, F_MAZE_WALK = range(1, 10)
 C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED, C_MAZE_PHYSICS = 32, 33, 34, 35
 R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
-    R_MODIFY_SPRITES, R_COND_BEGIN = 64, 65, 66, 67, 68
+    R_MODIFY_SPRITES, R_COND_BEGIN, R_TIMED_BEGIN, R_KEEP_NEAR_CENTER = 64, 65, 66, 67, 68, 69, 70
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
@@ -514,6 +514,22 @@ def _rule_specs(prog, rule, out):
         out.append(dict(kind=R_COND_BEGIN, cond=rule._condition,
                         i=[0, len(sub)]))
         out.extend(sub)
+    elif k in ('TimedRule', 'DelayedRule', 'TemporaryRule'):
+        # timing.py:15-107; a random interval (user callable) cannot be lowered
+        draws = [tuple(float(v) for v in rule._step_interval()) for _ in range(4)]
+        if len(set(draws)) != 1:
+            raise CompileError('{} with a random step interval is not on the accelerated path'.format(k))
+        sub = []
+        for r in rule._rules:
+            _rule_specs(prog, r, sub)
+        out.append(dict(kind=R_TIMED_BEGIN, i=[0, len(sub), prog.alloc_envf(2)], p=draws[0]))
+        out.extend(sub)
+    elif k == 'KeepNearCenter':
+        layers = list(rule._layers_to_center)
+        ls, ln = prog.add_list(layers)
+        grid = rule._grid_cell
+        out.append(dict(kind=R_KEEP_NEAR_CENTER, i=(prog.layer_index(rule._agent_layer), ls, ln),
+                        p=(float(grid[0]), float(grid[1]))))
     else:
         raise CompileError(
             'game rule {} is not on the accelerated path'.format(k))

@@ -2381,6 +2381,23 @@ __device__ __noinline__ void rule_leaf(const Env &, int r) {
   const moog_op *op = e.ops + r;
   unsigned flag[MOOG_MAX_SLOTS / 32];
   switch (op->kind) {
+    case MOOG_R_KEEP_NEAR_CENTER: {  // re_center.py:60-76
+      const int la = op->i[0];
+      if (e.cnt[la] < 1) return;
+      const int a = LOFF(e, la);
+      const double px = DYN(e, MOOG_D_X, a) - 0.5, py = DYN(e, MOOG_D_Y, a) - 0.5;
+      const double gx = op->p[0], gy = op->p[1];
+      const double dx = -1. * gx * (double)(px > gx) + gx * (double)(px < -1. * gx);
+      const double dy = -1. * gy * (double)(py > gy) + gy * (double)(py < -1. * gy);
+      if (dx != 0 || dy != 0) {
+        const int n = list_count(e, op->i[1], op->i[2]);
+        for (int i = 0; i < n; ++i) {
+          const int s = list_slot(e, op->i[1], op->i[2], i);
+          set_position(e, s, DYN(e, MOOG_D_X, s) + dx, DYN(e, MOOG_D_Y, s) + dy);
+        }
+      }
+      return;
+    }
     case MOOG_R_VANISH_ON_CONTACT: {  // vanish.py:66-86, contact_rules.py:28-35
       int la = op->i[0], lb = op->i[1];
       for (int w = 0; w < MOOG_MAX_SLOTS / 32; ++w) flag[w] = 0;
@@ -2474,8 +2491,18 @@ __device__ __noinline__ void rules_step(const Env &) {
     }
     if (depth == 0 && r >= end) break;
     const moog_op *op = e.ops + r;
-    if (op->kind == MOOG_R_COND_BEGIN) {
-      int times = (int)eval_condition(e, op->i[0]);
+    if (op->kind == MOOG_R_COND_BEGIN || op->kind == MOOG_R_TIMED_BEGIN) {
+      int times;
+      if (op->kind == MOOG_R_TIMED_BEGIN) {  // timing.py:50-56; the guarded rules never read the countdowns
+        const double c0 = e.envf[op->i[2]], c1 = e.envf[op->i[2] + 1];
+        times = (c0 <= 0 && c1 > 0) ? 1 : 0;
+        wsync();
+        put(e, &e.envf[op->i[2]], c0 - 1);
+        put(e, &e.envf[op->i[2] + 1], c1 - 1);
+        wsync();
+      } else {
+        times = (int)eval_condition(e, op->i[0]);
+      }
       int nsub = op->i[1];
       if (times <= 0 || nsub <= 0 || depth == MOOG_MAX_COND_DEPTH) {
         r += 1 + nsub;
@@ -2841,6 +2868,18 @@ __device__ inline void post_reset(const Env &e) {
   wsync();
   tasks_reset(e);
   actions_reset(e);
+  {  // AbstractRule.reset of the rules that keep state: TimedRule re-arms its interval (timing.py:45-48)
+    const int32_t *h = e.hdr;
+    wsync();
+    for (int r = h[MOOG_H_RULES]; r < h[MOOG_H_RULES] + h[MOOG_H_N_RULES]; ++r) {
+      const moog_op *op = e.ops + r;
+      if (op->kind == MOOG_R_TIMED_BEGIN) {
+        put(e, &e.envf[op->i[2]], op->p[0]);
+        put(e, &e.envf[op->i[2] + 1], op->p[1]);
+      }
+    }
+    wsync();
+  }
   rules_step(e);
 }
 

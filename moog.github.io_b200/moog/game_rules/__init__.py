@@ -3,13 +3,16 @@
 On the hot path (lowered to device ops by moog_b200.compiler):
 `VanishOnContact`, `VanishByFilter`, `ModifyOnContact`, `ModifySprites`,
 `ConditionalRule`, plus the `get_contact_indices` / `get_contact_counter`
-condition builders.  The psychophysics trial-structure rules of the reference
-(Phase*, TimedRule, Fixation, Portal, CreateSprites, ...) are outside the
-accelerated path; constructing one raises so that a config never silently
-loses a rule.
+condition builders, `TimedRule` / `DelayedRule` / `TemporaryRule` with fixed
+intervals and `KeepNearCenter`.  The remaining psychophysics trial-structure
+rules of the reference (Phase*, Fixation, Portal, CreateSprites, ...) are
+outside the accelerated path; constructing one raises so that a config never
+silently loses a rule.
 """
 
 import abc
+
+import numpy as np
 
 
 def _as_tuple(x):
@@ -101,6 +104,49 @@ class ConditionalRule(AbstractRule):
             rules]
 
 
+class TimedRule(AbstractRule):
+    """Steps `rules` only while the call count since reset lies in
+    `step_interval = (start, stop)` (timing.py:15-56)."""
+
+    def __init__(self, step_interval, rules):
+        self._step_interval = step_interval if callable(step_interval) else (lambda: step_interval)
+        self._rules = list(rules) if isinstance(rules, (list, tuple)) else [rules]
+
+
+class DelayedRule(TimedRule):
+    """Starts after `steps_until_start` calls, runs for `duration` (timing.py:59-86)."""
+
+    def __init__(self, steps_until_start, rules, duration=np.inf):
+        start = steps_until_start if callable(steps_until_start) else (lambda: steps_until_start)
+        length = duration if callable(duration) else (lambda: duration)
+
+        def _interval():
+            t0 = start()
+            return (t0, t0 + length())
+        super().__init__(_interval, rules)
+
+
+class TemporaryRule(TimedRule):
+    """Runs from the reset for `steps_until_stop` calls (timing.py:89-107)."""
+
+    def __init__(self, steps_until_stop, rules):
+        stop = steps_until_stop if callable(steps_until_stop) else (lambda: steps_until_stop)
+        super().__init__(lambda: (0, stop()), rules)
+
+
+class KeepNearCenter(AbstractRule):
+    """Snaps the agent and the listed layers back by one grid cell whenever the agent is
+    more than a cell away from (0.5, 0.5) (re_center.py:13-76)."""
+
+    def __init__(self, agent_layer, layers_to_center, grid_x, grid_y=None):
+        self._agent_layer = agent_layer
+        layers_to_center = list(layers_to_center)
+        if agent_layer not in set(layers_to_center):
+            layers_to_center = layers_to_center + [agent_layer]
+        self._layers_to_center = layers_to_center
+        self._grid_cell = np.array([grid_x, grid_x if grid_y is None else grid_y])
+
+
 def _out_of_scope(name, where):
     def _ctor(*args, **kwargs):
         raise NotImplementedError(
@@ -118,9 +164,5 @@ ModifyMetaState = _out_of_scope('ModifyMetaState', 'modify_meta_state.py')
 UpdateMetaStateValue = _out_of_scope(
     'UpdateMetaStateValue', 'modify_meta_state.py')
 Portal = _out_of_scope('Portal', 'portal.py')
-KeepNearCenter = _out_of_scope('KeepNearCenter', 're_center.py')
 Phase = _out_of_scope('Phase', 'task_phases.py')
 PhaseSequence = _out_of_scope('PhaseSequence', 'task_phases.py')
-DelayedRule = _out_of_scope('DelayedRule', 'timing.py')
-TemporaryRule = _out_of_scope('TemporaryRule', 'timing.py')
-TimedRule = _out_of_scope('TimedRule', 'timing.py')

@@ -76,6 +76,8 @@ SCENES = {
     # (constant_speed, turning sprites), Grid(control_velocity), VanishOnContact,
     # ConditionalRule on `state['agent'][0].velocity`
     'pacman': ('moog_demos.example_configs.pacman', 0, 12, 120, 10),
+    # TimedRule / TemporaryRule / DelayedRule, KeepNearCenter, FirstPersonAgent renderer
+    'timed_center': ('moog_b200.configs.timed_center', None, 13, 40, 3),
 }
 
 
@@ -267,6 +269,8 @@ def generate(name, out_dir):
             action = _chase_action(env, t)
         elif name == 'pacman':
             action = _pacman_action(env, t)
+        elif name == 'timed_center':
+            action = np.array([1.0, 0.6]) if t < 25 else np.array([-1.0, -1.0])   # leaves the centre cell repeatedly
         else:
             action = env.action_space.random_action()
         flat = _flat_action(prog, action)

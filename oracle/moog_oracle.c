@@ -1491,6 +1491,33 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
       }
       return 1;
     }
+    case MOOG_R_TIMED_BEGIN: { /* timing.py:50-56 */
+      double *cd = e->envf + op->i[2];
+      int nsub = op->i[1];
+      if (cd[0] <= 0 && cd[1] > 0) {
+        int q = r + 1;
+        while (q < r + 1 + nsub) q += rule_step(e, q, rule_noise);
+      }
+      cd[0] -= 1;
+      cd[1] -= 1;
+      return 1 + nsub;
+    }
+    case MOOG_R_KEEP_NEAR_CENTER: { /* re_center.py:60-76 */
+      int la = op->i[0];
+      if (e->cnt[la] < 1) return 1;
+      int a = LOFF(e, la);
+      double d[2];
+      for (int c = 0; c < 2; ++c) {
+        double pos = DYN(e, c ? MOOG_D_Y : MOOG_D_X, a) - 0.5, g = op->p[c];
+        d[c] = -1. * g * (double)(pos > g) + g * (double)(pos < -1. * g);
+      }
+      if (d[0] != 0 || d[1] != 0) {
+        int n = gather_layers(e, op->i[1], op->i[2], sp);
+        for (int i = 0; i < n; ++i)
+          set_position(e, sp[i], DYN(e, MOOG_D_X, sp[i]) + d[0], DYN(e, MOOG_D_Y, sp[i]) + d[1]);
+      }
+      return 1;
+    }
     case MOOG_R_COND_BEGIN: { /* conditional.py:55-58 */
       int times = (int)eval_condition(e, op->i[0]);
       int nsub = op->i[1];
@@ -1502,6 +1529,18 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
     }
   }
   return 1;
+}
+
+/* AbstractRule.reset of the rules that keep state: TimedRule re-arms its interval (timing.py:45-48) */
+static void rules_reset(env_t *e) {
+  const int32_t *h = e->hdr;
+  for (int r = h[MOOG_H_RULES]; r < h[MOOG_H_RULES] + h[MOOG_H_N_RULES]; ++r) {
+    const moog_op *op = e->ops + r;
+    if (op->kind == MOOG_R_TIMED_BEGIN) {
+      e->envf[op->i[2]] = op->p[0];
+      e->envf[op->i[2] + 1] = op->p[1];
+    }
+  }
 }
 
 static void rules_step(env_t *e, const double *rule_noise) {
@@ -1662,6 +1701,7 @@ void orc_env_post_reset(const void *blob, const orc_state *st, int n_envs, const
     e.envi[MOOG_EI_RESET_NEXT] = 0;
     tasks_reset(&e);
     actions_reset(&e);
+    rules_reset(&e);
     int nrn = 0; /* rule noise columns */
     (void)nrn;
     rules_step(&e, rule_noise);
