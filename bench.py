@@ -50,6 +50,29 @@ def _host_states(config, n, seed):
     return [config['state_initializer']() for _ in range(n)]
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything written to fd 1 from here on (NCCL's own "NCCL version ..." banner, library
+    chatter) goes to stderr; the one JSON line is written to the real stdout by _emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    text = json.dumps(line, default=_json_default) + '\n'
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def _json_default(o):
     if isinstance(o, (np.integer,)):
         return int(o)
@@ -240,7 +263,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line, default=_json_default))
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -411,7 +434,7 @@ def run_ours(args):
             'value': v, 'unit': UNIT, 'cores': arm.threads, 'kind': 'port',
             'sample': '{} env-steps of {} incl. render: {} threads x 8 envs x one whole {}-step episode each '
                       '(uniform phase mix), {:.1f} s'.format(n, args.scene, arm.threads, args.episode, dt)}
-    print(json.dumps(line, default=_json_default))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -434,6 +457,7 @@ def main():
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
