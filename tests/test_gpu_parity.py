@@ -354,3 +354,36 @@ def test_device_side_reset_sampler():
     for e in range(0, N, 61):     # (the vertex slots beyond a sprite's nv keep the template's stale values)
         vlive = util.live_vertex_mask(prog, st['cnt'][e], st['meta'][e])
         assert np.array_equal(st3['vtx'][e][vlive], st['vtx'][e][vlive])
+
+
+@pytest.mark.gpu
+def test_vector_gym_wrapper_and_simulation_snapshot():
+    """env_wrappers: the Gym-style protocol over a batch and snapshot / restore
+    (reference gym_wrapper.py:48-140, simulation.py:55-83)."""
+    import torch
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment
+    from moog_b200.configs import colliding_predators84
+    from moog_b200.env_wrappers import BatchedSimulation, VectorGymWrapper
+    cfg = colliding_predators84.get_config(dict(image_size=(64, 64)))
+    np.random.seed(3)
+    states = [cfg['state_initializer']() for _ in range(4)]
+    env = BatchedEnvironment(**cfg, num_envs=32, device='cuda:0', seed=1, initial_states=states)
+    gym = VectorGymWrapper(env)
+    assert gym.action_space == [dict(key=None, type='Box', low=-1., high=1., shape=(2,), dtype='float32')]
+    assert gym.observation_space['image']['shape'] == (64, 64, 3)
+    obs = gym.reset()
+    assert obs['image'].shape == (32, 64, 64, 3) and obs['image'].dtype == torch.uint8
+    act = torch.full((32, 2), 0.5, dtype=torch.float64)
+    obs, reward, done, info = gym.step(act)
+    assert reward.shape == (32,) and done.dtype == torch.bool and not bool(done.any())
+    assert torch.equal(info['discount'], torch.ones(32, device='cuda:0'))
+    sim = BatchedSimulation(env)
+    sim.push()
+    before = env.engine.state.dyn.clone()
+    rollout = [sim.step(act).reward.clone() for _ in range(5)]
+    assert not torch.equal(env.engine.state.dyn, before)
+    sim.pop()
+    assert torch.equal(env.engine.state.dyn, before)
+    again = [sim.step(act).reward.clone() for _ in range(5)]
+    assert all(torch.equal(a, b) for a, b in zip(rollout, again)), 'a restored batch replays identically'
