@@ -56,7 +56,10 @@ extern "C" {
 #define MOOG_VERSION 1
 
 #define MOOG_MAX_LAYERS 16
-#define MOOG_MAX_VERTS 32   /* per sprite; 'circle' is a 30-gon (moog/shapes.py:17) */
+#define MOOG_MAX_VERTS 32   /* per sprite that takes part in overlap tests / collisions (lane = vertex);
+                               'circle' is a 30-gon (moog/shapes.py:17) */
+#define MOOG_MAX_OUTLINE 128 /* per sprite that is only moved and drawn (e.g. the 102-vertex annulus occluder of
+                               the first-person configs, shapes.py:170-188) */
 #define MOOG_MAX_SLOTS 256
 
 #define MOOG_DYN_FIELDS 6

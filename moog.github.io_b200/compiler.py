@@ -28,7 +28,8 @@ from . import lambdas
 MAGIC = 0x474F4F4D
 VERSION = 1
 MAX_LAYERS = 16
-MAX_VERTS = 32
+MAX_VERTS = 32       # MOOG_MAX_VERTS: outlines that take part in overlap tests / collisions
+MAX_OUTLINE = 128    # MOOG_MAX_OUTLINE: outlines that are only moved and drawn
 MAX_SLOTS = 256
 DYN_FIELDS = 6
 STAT_FIELDS = 10
@@ -642,10 +643,10 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     for name in prog.layer_names:
         nvs = [len(sp.vertices) for st in sample_states for sp in st[name]]
         vcap.append(max(nvs) if nvs else 0)
-    if max(vcap + [0]) > MAX_VERTS:
+    if max(vcap + [0]) > MAX_OUTLINE:
         raise CompileError(
             'a sprite outline has {} vertices; the device path supports at '
-            'most {}'.format(max(vcap), MAX_VERTS))
+            'most {}'.format(max(vcap), MAX_OUTLINE))
     prog.layer_vcap = vcap
     voff = [0]
     for cap, vc in zip(caps, vcap):
@@ -660,6 +661,7 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     _compile_render(prog, config.get('observers', {}))
     if reset_sampler:
         _compile_reset_sampler(prog, config['state_initializer'])
+    _check_outline_caps(prog)
     return prog.finalize()
 
 
@@ -698,9 +700,9 @@ def _shape_record(shape):
     from moog import sprite as sprite_lib
     sp = sprite_lib.Sprite(x=0., y=0., shape=shape)
     base = np.asarray(sp._shape_path.vertices[:-1], dtype=np.float64)  # pylint: disable=protected-access
-    if len(base) > MAX_VERTS:
+    if len(base) > MAX_OUTLINE:
         raise CompileError('sprite outline has {} vertices; the device path supports at most {}'.format(
-            len(base), MAX_VERTS))
+            len(base), MAX_OUTLINE))
     ixy = np.asarray(sp._x_y_rotational_inertia, dtype=np.float64)  # pylint: disable=protected-access
     centroid = np.asarray(sp.position, dtype=np.float64)             # (0, 0) + raw centroid
     rec = [float(len(base)), 1.0 if (isinstance(shape, str) and shape == 'circle') else 0.0,
@@ -816,6 +818,32 @@ def _compile_reset_sampler(prog, state_initializer):
     prog.reset_template = state
 
 
+def _check_outline_caps(prog):
+    """Outlines with more than MOOG_MAX_VERTS vertices (up to MOOG_MAX_OUTLINE) can be moved
+    and drawn, but the overlap / collision kernels spend one lane per vertex: a layer that holds
+    such a sprite must not appear in any op that tests overlaps."""
+    def layers_of_list(start, count):
+        return [prog.ipool[start + k] for k in range(count)]
+
+    geom = set()
+    for o in prog.ops:
+        k, i = o['kind'], o['i']
+        if k in (F_COLLISION, R_VANISH_ON_CONTACT, SC_CONTACT_COUNT):
+            geom.update(i[0:2])
+        elif k in (R_MODIFY_ON_CONTACT, T_CONTACT_REWARD, SC_CONTACT_ANY_COUNT):
+            geom.update(layers_of_list(i[0], i[1]) + layers_of_list(i[2], i[3]))
+        elif k == Z_GENERATE:
+            slots = [i[0]] + [prog.ipool[i[2] + q] for q in range(i[3])]
+            for s in slots:
+                geom.add(max(l for l in range(prog.n_layers) if prog.layer_off[l] <= s))
+    for l in sorted(geom):
+        if prog.layer_vcap[l] > MAX_VERTS:
+            raise CompileError(
+                'layer {!r} holds a sprite with {} vertices and takes part in overlap tests; '
+                'only outlines of at most {} vertices can (larger ones, up to {}, can be moved and drawn)'.format(
+                    prog.layer_names[l], prog.layer_vcap[l], MAX_VERTS, MAX_OUTLINE))
+
+
 def _scalar_kind(v):
     """0 python number (weak), 1 float32, 2 float64 -- how NumPy will promote
     the value in `angle + dt * angle_vel` (sprite.py:426-430)."""
@@ -848,14 +876,14 @@ class ShapeTable(object):
         sid = self._index.get(key)
         if sid is None:
             n = len(outline)
-            if n > MAX_VERTS:
+            if n > MAX_OUTLINE:
                 raise CompileError(
                     'sprite outline has {} vertices; the device path supports '
-                    'at most {}'.format(n, MAX_VERTS))
+                    'at most {}'.format(n, MAX_OUTLINE))
             if n < 3:
                 raise CompileError('sprite outline needs at least 3 vertices')
             sid = len(self.nv)
-            padded = np.zeros((MAX_VERTS, 2))
+            padded = np.zeros((MAX_OUTLINE, 2))
             padded[:n] = outline
             self.verts.append(padded)
             self.nv.append(n)
@@ -864,7 +892,7 @@ class ShapeTable(object):
 
     def arrays(self):
         n = max(len(self.nv), 1)
-        verts = np.zeros((n, MAX_VERTS, 2))
+        verts = np.zeros((n, MAX_OUTLINE, 2))
         nv = np.zeros(n, dtype=np.int32)
         if self.nv:
             verts[:len(self.nv)] = np.stack(self.verts)

@@ -21,6 +21,8 @@ struct moog_program {
   // anti_aliasing > 1: Lanczos coefficient tables (Resample.c), built on first use
   int *resample;
   int ksize_h, ksize_v;
+  // largest outline a slot of each layer can hold (from the blob's voff table)
+  int layer_vcap[MOOG_MAX_LAYERS];
 };
 
 namespace {
@@ -56,6 +58,13 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
   if (!p) return MOOG_E_INVAL;
   memcpy(p->hdr, hdr, sizeof(p->hdr));
   p->hdr[MOOG_H_CMASK_WORDS] = moog::candidate_matrix_words(blob);
+  {
+    moog::ProgramView pv = moog::view_of(blob);
+    for (int l = 0; l < hdr[MOOG_H_N_LAYERS]; ++l) {
+      const int a = hdr[MOOG_H_LAYER_OFF + l], b = hdr[MOOG_H_LAYER_OFF + l + 1];
+      p->layer_vcap[l] = b > a ? pv.voff[a + 1] - pv.voff[a] : 0;
+    }
+  }
   if (moog::env_smem_bytes(p->hdr) > 220 * 1024 || p->hdr[MOOG_H_CMASK_WORDS] > 2048) {
     free(p);
     return MOOG_E_TOO_BIG;
@@ -198,6 +207,8 @@ int moog_overlap_pairs(moog_program *p, const moog_state *st, int n_envs, int la
   if (!p || !out) return MOOG_E_INVAL;
   int L = p->hdr[MOOG_H_N_LAYERS];
   if (layer_a < 0 || layer_a >= L || layer_b < 0 || layer_b >= L) return MOOG_E_INVAL;
+  // outlines beyond MOOG_MAX_VERTS are draw-only: the overlap kernels spend one lane per vertex
+  if (p->layer_vcap[layer_a] > MOOG_MAX_VERTS || p->layer_vcap[layer_b] > MOOG_MAX_VERTS) return MOOG_E_UNSUPPORTED;
   return run_step(p, st, n_envs, moog::MODE_OVERLAP, nullptr, layer_a, layer_b, out, stream);
 }
 

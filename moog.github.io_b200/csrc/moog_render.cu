@@ -20,7 +20,7 @@
 
 namespace moog {
 
-#define MAXV MOOG_MAX_VERTS
+#define MAXV MOOG_MAX_OUTLINE
 #define MAX_XX (2 * MAXV + 8)
 
 // C `(int)double` as the reference's host executes it (x86-64 cvttsd2si): NaN and

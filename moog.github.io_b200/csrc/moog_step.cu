@@ -366,10 +366,12 @@ __device__ __forceinline__ void store_box(const Env &e, int s, double xmin, doub
 __device__ inline void classify_slot(const Env &e, int s) {
   int n = META(e, MOOG_M_NV, s);
   const double2 *v = e.vtx + e.voff[s];
-  bool act = e.lane < n;
-  double2 p = act ? v[e.lane] : make_double2(0., 0.);
-  bool nonfinite = act && !(isfinite(p.x) && isfinite(p.y));
-  bool nan2 = !act || (isnan(p.x) && isnan(p.y));
+  bool nonfinite = false, nan2 = true;
+  for (int i = e.lane; i < n; i += 32) {
+    const double2 p = v[i];
+    nonfinite |= !(isfinite(p.x) && isfinite(p.y));
+    nan2 &= isnan(p.x) && isnan(p.y);
+  }
   unsigned nf = __ballot_sync(FULL, nonfinite);
   bool allnan = __all_sync(FULL, nan2) && n > 0;
   int fl = (e.sflag[s] & ~(SLF_NONFINITE | SLF_ALLNAN)) | (nf ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
@@ -412,6 +414,26 @@ __device__ __forceinline__ bool boxes_apart(const Env &e, int a, int b) {
 // position / angle setters (sprite.py:531-540, 616-633): the cached outline is
 // transformed incrementally, exactly like the reference's Sprite._path
 // ---------------------------------------------------------------------------
+// Vertices 32 .. n-1 of a big draw-only outline (MOOG_MAX_OUTLINE): the translation (and
+// rotation) the callers apply to the first 32 themselves.  Out of line: the hot paths only
+// pay a never-taken branch for it.
+__device__ __noinline__ void outline_tail(double2 *v, int n, int lane, double tx, double ty, bool rotates, double r0,
+                                          double r1, double r2, double r3, double r4, double r5) {
+#pragma unroll 1
+  for (int i = lane + 32; i < n; i += 32) {
+    const double2 p = v[i];
+    double x = (1.0 * p.x + 0.0 * p.y) + tx;
+    double y = (0.0 * p.x + 1.0 * p.y) + ty;
+    if (rotates) {
+      const double rx = r0 * x + r1 * y + r2;
+      const double ry = r3 * x + r4 * y + r5;
+      x = rx;
+      y = ry;
+    }
+    v[i] = make_double2(x, y);
+  }
+}
+
 __device__ __forceinline__ void set_position_impl(const Env &e, int s, double nx, double ny) {
   double tx = nx - DYN(e, MOOG_D_X, s), ty = ny - DYN(e, MOOG_D_Y, s);
   int n = META(e, MOOG_M_NV, s);
@@ -424,6 +446,7 @@ __device__ __forceinline__ void set_position_impl(const Env &e, int s, double nx
     double y = 0.0 * p.x + 1.0 * p.y + ty;
     v[e.lane] = make_double2(x, y);
   }
+  if (n > 32) outline_tail(v, n, e.lane, tx, ty, false, 1., 0., 0., 0., 1., 0.);
   if (e.lane == 0) {
     DYN(e, MOOG_D_X, s) = nx;
     DYN(e, MOOG_D_Y, s) = ny;
@@ -1867,23 +1890,25 @@ __device__ inline void set_angle_f64(const Env &e, int s, double a) {
   const int n = META(e, MOOG_M_NV, s);
   double2 *v = e.vtx + e.voff[s];
   wsync();
-  double2 q = make_double2(0., 0.);
-  if (e.lane < n) {
-    const double2 p = v[e.lane];
-    q = make_double2(mtx.m0 * p.x + mtx.m1 * p.y + mtx.m2, mtx.m3 * p.x + mtx.m4 * p.y + mtx.m5);
-    v[e.lane] = q;
+  // the rotated outline, its box and NaN / inf classification
+  bool fin = true, nan_all = true;
+  double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int i = e.lane; i < n; i += 32) {
+    const double2 p = v[i];
+    const double2 q = make_double2(mtx.m0 * p.x + mtx.m1 * p.y + mtx.m2, mtx.m3 * p.x + mtx.m4 * p.y + mtx.m5);
+    v[i] = q;
+    fin &= isfinite(q.x) && isfinite(q.y);
+    nan_all &= isnan(q.x) && isnan(q.y);
+    xmin = fmin(xmin, q.x); xmax = fmax(xmax, q.x);
+    ymin = fmin(ymin, q.y); ymax = fmax(ymax, q.y);
   }
-  // the rotated outline's box and NaN / inf classification
-  const bool act = e.lane < n;
-  const bool fin = !act || (isfinite(q.x) && isfinite(q.y));
-  double xmin = act ? q.x : INFINITY, xmax = act ? q.x : -INFINITY, ymin = act ? q.y : INFINITY, ymax = act ? q.y : -INFINITY;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     xmin = fmin(xmin, shflx_d(xmin, o)); xmax = fmax(xmax, shflx_d(xmax, o));
     ymin = fmin(ymin, shflx_d(ymin, o)); ymax = fmax(ymax, shflx_d(ymax, o));
   }
   const bool nonfinite = !__all_sync(FULL, fin);
-  const bool allnan = n > 0 && __all_sync(FULL, !act || (isnan(q.x) && isnan(q.y)));
+  const bool allnan = n > 0 && __all_sync(FULL, nan_all);
   if (e.lane == 0) {
     DYN(e, MOOG_D_ANG, s) = a;
     META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (KIND_F64 << MOOG_SF_ANG_SHIFT);
@@ -2078,15 +2103,18 @@ __device__ inline void integrate_all(const Env &e) {
         x = (p.x + 0.0 * p.y) + ttx;
         y = (0.0 * p.x + p.y) + tty;
       }
-      if ((rot >> src) & 1u) {
-        const double r0 = shfl_d(m.m0, src), r1 = shfl_d(m.m1, src), r2 = shfl_d(m.m2, src);
-        const double r3 = shfl_d(m.m3, src), r4 = shfl_d(m.m4, src), r5 = shfl_d(m.m5, src);
+      const bool rotates = (rot >> src) & 1u;
+      double r0 = 1, r1 = 0, r2 = 0, r3 = 0, r4 = 1, r5 = 0;
+      if (rotates) {
+        r0 = shfl_d(m.m0, src); r1 = shfl_d(m.m1, src); r2 = shfl_d(m.m2, src);
+        r3 = shfl_d(m.m3, src); r4 = shfl_d(m.m4, src); r5 = shfl_d(m.m5, src);
         const double rx = r0 * x + r1 * y + r2;
         const double ry = r3 * x + r4 * y + r5;
         x = rx;
         y = ry;
       }
       if (e.lane < n) v[e.lane] = make_double2(x, y);
+      if (n > 32) outline_tail(v, n, e.lane, ttx, tty, rotates, r0, r1, r2, r3, r4, r5);
     }
   }
   wsync();
@@ -2351,7 +2379,7 @@ __device__ inline void copy_slot(const Env &e, int dst, int src) {
   if (e.lane < MOOG_META_FIELDS) META(e, e.lane, dst) = META(e, e.lane, src);
   if (e.lane < 4) BOX(e, e.lane, dst) = BOX(e, e.lane, src);
   if (e.lane == 0) e.sflag[dst] = e.sflag[src];
-  if (e.lane < nv) e.vtx[e.voff[dst] + e.lane] = e.vtx[e.voff[src] + e.lane];
+  for (int i = e.lane; i < nv; i += 32) e.vtx[e.voff[dst] + i] = e.vtx[e.voff[src] + i];
   wsync();
 }
 
@@ -2809,12 +2837,12 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
       const double m00 = c * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = c * sy;
       wsync();
       double r = 0.0;
-      if (e.lane < nv) {
-        const double bx = R[6 + 2 * e.lane], by = R[7 + 2 * e.lane];
+      for (int i = e.lane; i < nv; i += 32) {
+        const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
         const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
-        e.vtx[e.voff[s] + e.lane] = make_double2(wx, wy);
+        e.vtx[e.voff[s] + i] = make_double2(wx, wy);
         const double rx = wx - px, ry = wy - py;
-        r = sqrt(rx * rx + ry * ry);
+        r = fmax(r, sqrt(rx * rx + ry * ry));
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) r = fmax(r, shflx_d(r, o));

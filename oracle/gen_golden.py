@@ -78,6 +78,10 @@ SCENES = {
     'pacman': ('moog_demos.example_configs.pacman', 0, 12, 120, 10),
     # TimedRule / TemporaryRule / DelayedRule, KeepNearCenter, FirstPersonAgent renderer
     'timed_center': ('moog_b200.configs.timed_center', None, 13, 40, 3),
+    # a shipped first-person config: Tether corrective, KeepNearCenter, ModifyOnContact,
+    # FirstPersonAgent renderer, grid-line sprites and the 102-vertex annulus occluder
+    # (a draw-only outline, MOOG_MAX_OUTLINE)
+    'parallelogram_catch': ('moog_demos.example_configs.parallelogram_catch', 0, 14, 90, 6),
 }
 
 

@@ -152,7 +152,7 @@ typedef struct {
 
 typedef struct {
   int n;               /* number of distinct vertices */
-  double v[MAXV + 1][2]; /* closed: v[n] == v[0]  (sprite.py:394) */
+  double v[MOOG_MAX_OUTLINE + 1][2]; /* closed: v[n] == v[0]  (sprite.py:394) */
 } poly_t;
 
 static void bind_program(env_t *e, const void *blob) {
@@ -1779,7 +1779,7 @@ void orc_overlap_pairs(const void *blob, const orc_state *st, int n_envs, int la
   }
 }
 
-/* world vertices of every slot: out[n][S][MAXV][2], nv[n][S] */
+/* world vertices of every slot: out[n][S][MOOG_MAX_OUTLINE][2], nv[n][S] */
 void orc_world_vertices(const void *blob, const orc_state *st, int n_envs, double *out, int32_t *nv) {
   for (int n = 0; n < n_envs; ++n) {
     env_t e;
@@ -1790,7 +1790,7 @@ void orc_world_vertices(const void *blob, const orc_state *st, int n_envs, doubl
         poly_t P;
         world_path(&e, s, &P);
         nv[(size_t)n * e.S + s] = P.n;
-        memcpy(out + ((size_t)n * e.S + s) * MAXV * 2, &P.v[0][0], sizeof(double) * 2 * P.n);
+        memcpy(out + ((size_t)n * e.S + s) * MOOG_MAX_OUTLINE * 2, &P.v[0][0], sizeof(double) * 2 * P.n);
       }
   }
 }

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, '_build', 'libmoog_oracle.so')
 
 MAX_LAYERS = 16
-MAX_VERTS = 32
+MAX_VERTS = 128   # MOOG_MAX_OUTLINE
 
 
 def build(force=False):

@@ -23,7 +23,7 @@
 
 #include "../include/moog_b200_program.h"
 
-#define MAXV MOOG_MAX_VERTS
+#define MAXV MOOG_MAX_OUTLINE
 
 typedef struct {
   int d;
