@@ -37,6 +37,9 @@ _ERR_TEXT = {
     2: 'RuntimeError: _position_correction would not terminate (collisions.py:740)',
     4: 'ValueError: TetherZippedLayers layers differ in length (tether_physics.py:192-196)',
     8: 'RuntimeError: layer capacity exceeded',
+    16: 'ValueError: Object is not on the maze grid (maze_physics.py:93-104)',
+    32: 'RecursionError: max_recursion_depth exceeded trying to initialize a non-overlapping sprite '
+        '(sprite_generators.py:92-98)',
 }
 
 _STATE_DTYPES = dict(dyn=torch.float64, stat=torch.float64, meta=torch.int32,
