@@ -172,7 +172,8 @@ enum {
   MOOG_R_KEEP_NEAR_CENTER,       /* i0 agent layer, i1,i2 list of the layers to move, p0,p1 grid cell    re_center.py:13-76 */
 
   /* tasks: i[5] = envf slot of the countdown */
-  MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps  contact_reward.py:70-102 */
+  MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps; p2 > 0: the
+                                 reward is the expression p2 - 1 of (sprite_0, sprite_1) instead of p0  contact_reward.py:70-102 */
   MOOG_T_RESET,               /* i0 condition op index; p0 steps_after p1 reward   reset.py:48-61  */
   MOOG_T_STAY_ALIVE,          /* p0 period p1 value                          stay_alive.py:22-32   */
   MOOG_T_TIMEOUT,             /* p0 timeout_steps                            composite_task.py:35  */

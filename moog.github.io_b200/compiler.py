@@ -391,14 +391,15 @@ def _compile_task(prog, task, out):
                         p=(float(task._reward_period),
                            float(task._reward_value))))
     elif k == 'ContactReward':
-        reward = lambdas.constant_reward(task._reward_fn)
+        reward, reward_code = lambdas.pair_reward(task._reward_fn)
         cond = lambdas.compile_pair_condition(task._condition)
         l0s, l0n = prog.add_list(_as_list(task._layers_0))
         l1s, l1n = prog.add_list(_as_list(task._layers_1))
         out.append(dict(
             kind=T_CONTACT_REWARD,
             i=(l0s, l0n, l1s, l1n, prog.add_expr(cond), prog.alloc_envf(1)),
-            p=(float(reward), float(task._reset_steps_after_contact))))
+            p=(float(reward), float(task._reset_steps_after_contact),
+               float(prog.add_expr(reward_code) + 1) if reward_code is not None else 0.0)))
     elif k == 'Reset':
         reward = lambdas.constant_state_reward(task._reward_fn)
         out.append(dict(

@@ -2652,7 +2652,7 @@ __device__ __noinline__ void tasks_reward(const Env &, int step_count, double *r
             int sb = list_slot(e, op->i[2], op->i[3], j);
             if (eval_expr(e, op->i[4], sa, sb) == 0) continue;
             if (overlaps(e, sa, sb)) {
-              r = op->p[0];
+              r = op->p[2] > 0 ? eval_expr(e, (int)op->p[2] - 1, sa, sb) : op->p[0];
               if (cd == INFINITY) cd = op->p[1];
             }
           }

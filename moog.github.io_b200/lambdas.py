@@ -293,6 +293,27 @@ def constant_reward(reward_fn):
             'ContactReward reward_fn must be a constant on the device path')
 
 
+def pair_reward(reward_fn):
+    """ContactReward reward_fn -> (constant, None) or (0.0, postfix code of
+    `reward_fn(sprite_0, sprite_1)` over the two sprites' factors)."""
+    try:
+        return constant_reward(reward_fn), None
+    except LoweringError:
+        pass
+    fn = _unwrap(reward_fn, 'reward_fn')
+    try:
+        out = fn(SymSprite(0), SymSprite(1))
+    except LoweringError:
+        raise
+    except Exception as exc:  # pylint: disable=broad-except
+        raise LoweringError(
+            'ContactReward reward_fn cannot be traced to an expression over the two sprites\' '
+            'factors ({}: {})'.format(type(exc).__name__, exc))
+    if not isinstance(out, Sym):
+        raise LoweringError('ContactReward reward_fn must return a number or an expression of sprite factors')
+    return 0.0, out.code
+
+
 def constant_state_reward(reward_fn):
     """Reset reward_fn -> float (reset.py:41-43 defaults to `lambda _: 0.`)."""
     if reward_fn is None:

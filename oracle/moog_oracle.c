@@ -1640,7 +1640,7 @@ static void tasks_reward(env_t *e, int step_count, double *reward, int *should_r
           for (int j = 0; j < m; ++j) {
             if (eval_expr(e, op->i[4], sp[i], sq[j]) == 0) continue;
             if (overlaps(e, sp[i], sq[j])) {
-              r = op->p[0];
+              r = op->p[2] > 0 ? eval_expr(e, (int)op->p[2] - 1, sp[i], sq[j]) : op->p[0];
               if (*cd == INFINITY) *cd = op->p[1];
             }
           }

@@ -436,3 +436,39 @@ def test_full_size_batch_is_independent_of_the_launch_mode(monkeypatch):
                 same = (ta == tb) | (ta.isnan() & tb.isnan())
                 assert bool(same.all()), (step, k)
             assert bool((a.counters[:, :4] == b.counters[:, :4]).all()), (step, 'overlap pair sets')
+
+
+@pytest.mark.gpu
+def test_contact_reward_expression_matches_oracle():
+    """ContactReward whose reward_fn reads the two sprites (e.g. first_person_predators_prey.py:133-146,
+    `-2. * predator.scale`): traced to an expression, evaluated on the LAST overlapping pair
+    (contact_reward.py:86-94) by the CUDA path exactly as by the oracle."""
+    import moog_b200  # noqa: F401
+    from moog import tasks
+    from moog_b200 import compiler
+    from moog_b200.configs import colliding_predators84
+    from oracle.oracle import Oracle
+    cfg = colliding_predators84.get_config(dict(image_size=(64, 64)))
+    cfg['task'] = tasks.CompositeTask(
+        tasks.ContactReward(reward_fn=lambda s_a, s_p: -2. * s_p.scale + s_a.c0,
+                            layers_0='agent', layers_1='predators'), timeout_steps=200)
+    np.random.seed(31)
+    states = [cfg['state_initializer']() for _ in range(24)]
+    prog = compiler.compile_config(cfg, states)
+    arr = compiler.pack_states(prog, states)
+    arr['stat'][:, 1, prog.layer_off[2]] = 0.3      # a big agent: contacts within a few steps
+    orc = Oracle(prog, arr)
+    orc.post_reset()
+    eng = _engine(prog, arr)
+    eng.post_reset()
+    rng = np.random.RandomState(3)
+    nonzero = 0
+    for step in range(40):
+        act = rng.uniform(-1, 1, size=(24, 2))
+        eng.state.upload({k: v.copy() for k, v in orc.arrays().items()})   # sin / cos scenes: re-sync each step
+        r_ref, _ = orc.step(act)
+        eng.env_step(act, auto_reset=False)
+        got = eng.reward.cpu().numpy()
+        assert np.array_equal(got, r_ref.astype(np.float32)), step
+        nonzero += int((r_ref != 0).sum())
+    assert nonzero > 10

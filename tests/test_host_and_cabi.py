@@ -336,3 +336,18 @@ def test_reset_sampler_lowering():
     pstates = [pcfg['state_initializer']() for _ in range(2)]
     with pytest.raises(C.CompileError):
         C.compile_config(pcfg, pstates, reset_sampler=True)
+
+
+def test_reward_function_lowering():
+    """constant rewards stay constants; functions of the two sprites become expressions;
+    anything else (metadata, Python branches on sprite values) is refused."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import lambdas
+    assert lambdas.pair_reward(-5) == (-5.0, None)
+    assert lambdas.pair_reward(lambda a, b: 1.5) == (1.5, None)
+    const, code = lambdas.pair_reward(lambda a, b: -2. * b.scale)
+    assert const == 0.0 and [c[0] for c in code] == [lambdas.X_CONST, lambdas.X_ATTR1, lambdas.X_MUL]
+    with pytest.raises(lambdas.LoweringError):
+        lambdas.pair_reward(lambda a, b: 1. if b.c0 < 128 else -1.)
+    with pytest.raises(lambdas.LoweringError):
+        lambdas.pair_reward(lambda a, b: a.metadata['true_contact_color'])
