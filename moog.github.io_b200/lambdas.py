@@ -110,9 +110,9 @@ class SymSprite(object):
             op = X_ATTR0 if self._which == 0 else X_ATTR1
             return Sym([(op, ATTRS.index(name), 0.0)])
         if name == 'position':
-            return (self.x, self.y)
+            return SymVec([self.x, self.y])
         if name == 'velocity':
-            return (self.x_vel, self.y_vel)
+            return SymVec([self.x_vel, self.y_vel])
         raise LoweringError(
             'sprite attribute {!r} is not available on the device'.format(name))
 
@@ -134,49 +134,99 @@ class SymSprite(object):
 
 
 class SymVec(object):
-    """A traced 2-vector (`sprite.velocity`, `sprite.position`) inside a state
-    condition: comparisons are elementwise, `np.all` / `np.any` reduce."""
+    """A traced 2-vector (`sprite.velocity`, `sprite.position`): arithmetic and comparisons are
+    elementwise (with scalars, sequences of two numbers or other SymVecs), NumPy ufuncs applied
+    to it are mapped to the same operators, `np.all` / `np.any` (and, after the AST rewrite of
+    `_symbolic_call`, the builtins `all` / `any`) reduce with & / |."""
+
+    __array_priority__ = 1000
+    __hash__ = None
 
     def __init__(self, elems):
         self.elems = list(elems)
 
-    def _cmp(self, other, name):
-        others = other.elems if isinstance(other, SymVec) else [other] * len(self.elems)
-        return SymVec([getattr(a, name)(b) for a, b in zip(self.elems, others)])
+    def _zip(self, other):
+        if isinstance(other, SymVec):
+            others = other.elems
+        elif hasattr(other, '__len__') and not isinstance(other, (str, bytes)):
+            others = list(other)
+            if len(others) != len(self.elems):
+                raise LoweringError('cannot combine a sprite 2-vector with a sequence of {} values'.format(len(others)))
+        else:
+            others = [other] * len(self.elems)
+        return zip(self.elems, others)
 
-    def __eq__(self, o): return self._cmp(o, '__eq__')
-    def __ne__(self, o): return self._cmp(o, '__ne__')
-    def __lt__(self, o): return self._cmp(o, '__lt__')
-    def __le__(self, o): return self._cmp(o, '__le__')
-    def __gt__(self, o): return self._cmp(o, '__gt__')
-    def __ge__(self, o): return self._cmp(o, '__ge__')
-    __hash__ = None
+    def _map(self, other, fn):
+        return SymVec([fn(Sym.lift(a), b) for a, b in self._zip(other)])
+
+    def __eq__(self, o): return self._map(o, lambda a, b: a == b)
+    def __ne__(self, o): return self._map(o, lambda a, b: a != b)
+    def __lt__(self, o): return self._map(o, lambda a, b: a < b)
+    def __le__(self, o): return self._map(o, lambda a, b: a <= b)
+    def __gt__(self, o): return self._map(o, lambda a, b: a > b)
+    def __ge__(self, o): return self._map(o, lambda a, b: a >= b)
+    def __add__(self, o): return self._map(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._map(o, lambda a, b: b + a)
+    def __sub__(self, o): return self._map(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._map(o, lambda a, b: b - a)
+    def __mul__(self, o): return self._map(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._map(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._map(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._map(o, lambda a, b: b / a)
+    def __mod__(self, o): return self._map(o, lambda a, b: a % b)
+    def __and__(self, o): return self._map(o, lambda a, b: a & b)
+    def __or__(self, o): return self._map(o, lambda a, b: a | b)
+    def __neg__(self): return SymVec([-Sym.lift(a) for a in self.elems])
+    def __abs__(self): return SymVec([abs(Sym.lift(a)) for a in self.elems])
+    def __invert__(self): return SymVec([~Sym.lift(a) for a in self.elems])
+
+    _UFUNCS = {'add': '__add__', 'subtract': '__sub__', 'multiply': '__mul__', 'true_divide': '__truediv__',
+               'divide': '__truediv__', 'remainder': '__mod__', 'mod': '__mod__', 'less': '__lt__',
+               'less_equal': '__le__', 'greater': '__gt__', 'greater_equal': '__ge__', 'equal': '__eq__',
+               'not_equal': '__ne__', 'logical_and': '__and__', 'logical_or': '__or__',
+               'bitwise_and': '__and__', 'bitwise_or': '__or__'}
+    _UNARY = {'negative': '__neg__', 'absolute': '__abs__', 'logical_not': '__invert__'}
+    _REVERSED = {'__add__': '__radd__', '__sub__': '__rsub__', '__mul__': '__rmul__', '__truediv__': '__rtruediv__'}
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != '__call__' or kwargs:
+            return NotImplemented
+        name = ufunc.__name__
+        if name in self._UNARY and len(inputs) == 1:
+            return getattr(self, self._UNARY[name])()
+        if name in self._UFUNCS and len(inputs) == 2:
+            op = self._UFUNCS[name]
+            if inputs[0] is self:
+                return getattr(self, op)(inputs[1])
+            if op in self._REVERSED:
+                return getattr(self, self._REVERSED[op])(inputs[0])
+            return getattr(SymVec(list(inputs[0]) if hasattr(inputs[0], '__len__') else [inputs[0]] * len(self.elems)),
+                           op)(self)
+        raise LoweringError('numpy.{} of a sprite vector is not available on the device'.format(name))
+
+    def __len__(self):
+        return len(self.elems)
+
+    def __iter__(self):
+        return iter(self.elems)
 
     def __getitem__(self, k):
         return self.elems[k]
 
     def all(self, *_, **__):       # np.all(vec) dispatches here
-        out = self.elems[0]
+        out = Sym.lift(self.elems[0])
         for x in self.elems[1:]:
             out = out & x
         return out
 
     def any(self, *_, **__):       # np.any(vec)
-        out = self.elems[0]
+        out = Sym.lift(self.elems[0])
         for x in self.elems[1:]:
             out = out | x
         return out
 
 
-class _SymFirstSprite(SymSprite):
-    """`state[layer][0]` while tracing a state condition."""
-
-    def __getattr__(self, name):
-        if name == 'position':
-            return SymVec([SymSprite.__getattr__(self, 'x'), SymSprite.__getattr__(self, 'y')])
-        if name == 'velocity':
-            return SymVec([SymSprite.__getattr__(self, 'x_vel'), SymSprite.__getattr__(self, 'y_vel')])
-        return SymSprite.__getattr__(self, name)
+_SymFirstSprite = SymSprite   # `state[layer][0]` while tracing a state condition
 
 
 class _SymLayer(object):
@@ -241,11 +291,107 @@ def _code_of(value):
 # sprite-level callables
 # ---------------------------------------------------------------------------
 
+def _sym_any(x):
+    if isinstance(x, SymVec):
+        return x.any()
+    items = list(x)
+    if any(isinstance(v, (Sym, SymVec)) for v in items):
+        out = Sym.lift(items[0].any() if isinstance(items[0], SymVec) else items[0])
+        for v in items[1:]:
+            out = out | (v.any() if isinstance(v, SymVec) else v)
+        return out
+    return any(items)
+
+
+def _sym_all(x):
+    if isinstance(x, SymVec):
+        return x.all()
+    items = list(x)
+    if any(isinstance(v, (Sym, SymVec)) for v in items):
+        out = Sym.lift(items[0].all() if isinstance(items[0], SymVec) else items[0])
+        for v in items[1:]:
+            out = out & (v.all() if isinstance(v, SymVec) else v)
+        return out
+    return all(items)
+
+
+def _sym_not(x):
+    return ~x if isinstance(x, (Sym, SymVec)) else (not x)
+
+
+def _sym_and(a, b):
+    return a & b if isinstance(a, (Sym, SymVec)) or isinstance(b, (Sym, SymVec)) else (a and b)
+
+
+def _sym_or(a, b):
+    return a | b if isinstance(a, (Sym, SymVec)) or isinstance(b, (Sym, SymVec)) else (a or b)
+
+
+class _BoolRewriter(ast.NodeTransformer):
+    """`a and b` / `a or b` / `not a` / `any(v)` / `all(v)` -> calls that build expressions when an
+    operand is symbolic.  (Both operands of and / or are evaluated: a per-sprite expression has no
+    side effect to short-circuit.)"""
+
+    def visit_BoolOp(self, node):
+        self.generic_visit(node)
+        fn = '_moog_and' if isinstance(node.op, ast.And) else '_moog_or'
+        out = node.values[0]
+        for v in node.values[1:]:
+            out = ast.Call(func=ast.Name(id=fn, ctx=ast.Load()), args=[out, v], keywords=[])
+        return out
+
+    def visit_UnaryOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Not):
+            return ast.Call(func=ast.Name(id='_moog_not', ctx=ast.Load()), args=[node.operand], keywords=[])
+        return node
+
+    def visit_Call(self, node):
+        self.generic_visit(node)
+        if isinstance(node.func, ast.Name) and node.func.id in ('any', 'all') and len(node.args) == 1:
+            node.func = ast.Name(id='_moog_' + node.func.id, ctx=ast.Load())
+        return node
+
+
+def _rewritten(fn):
+    """`fn` recompiled with _BoolRewriter applied (same globals and closure values)."""
+    node = _lambda_ast(fn)
+    node = _BoolRewriter().visit(node)
+    ns = dict(getattr(fn, '__globals__', {}))
+    ns.update(closure_vars(fn))
+    ns.update(_moog_any=_sym_any, _moog_all=_sym_all, _moog_not=_sym_not, _moog_and=_sym_and, _moog_or=_sym_or)
+    if isinstance(node, ast.Lambda):
+        expr = ast.Expression(node)
+        ast.fix_missing_locations(expr)
+        return eval(compile(expr, '<lowered>', 'eval'), ns)  # pylint: disable=eval-used
+    node.decorator_list = []
+    mod = ast.Module(body=[node], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, '<lowered>', 'exec'), ns)  # pylint: disable=exec-used
+    return ns[node.name]
+
+
+def _symbolic_call(fn, *args):
+    """fn(*args) on symbolic sprites; when the callable uses Python's `and` / `or` / `not` /
+    `any` / `all` on per-sprite values (which plain tracing cannot see), it is recompiled with
+    those constructs turned into expression builders and traced again."""
+    try:
+        return fn(*args)
+    except (LoweringError, TypeError):
+        try:
+            return _rewritten(fn)(*args)
+        except LoweringError:
+            raise
+        except Exception as exc:  # pylint: disable=broad-except
+            raise LoweringError('cannot lower {!r} to a device expression ({}: {})'.format(
+                getattr(fn, '__name__', fn), type(exc).__name__, exc))
+
+
 def compile_sprite_predicate(fn):
     """`fn(sprite) -> bool`  ->  postfix code, or None for "always true"."""
     if fn is None:
         return None
-    out = fn(SymSprite(0))
+    out = _symbolic_call(fn, SymSprite(0))
     if out is True:
         return None
     return _code_of(out)
@@ -258,7 +404,7 @@ def compile_pair_condition(fn):
         return None
     n = _n_params(fn)
     args = (SymSprite(0), SymSprite(1)) + ((None,) if n >= 3 else ())
-    out = fn(*args)
+    out = _symbolic_call(fn, *args)
     if out is True:
         return None
     return _code_of(out)
@@ -267,7 +413,7 @@ def compile_pair_condition(fn):
 def compile_modifier(fn):
     """`fn(sprite)` mutating the sprite -> postfix code of its stores."""
     stores = []
-    fn(SymSprite(0, stores))
+    _symbolic_call(fn, SymSprite(0, stores))
     code = []
     for name, value in stores:
         if name == 'position':
@@ -302,7 +448,7 @@ def pair_reward(reward_fn):
         pass
     fn = _unwrap(reward_fn, 'reward_fn')
     try:
-        out = fn(SymSprite(0), SymSprite(1))
+        out = _symbolic_call(fn, SymSprite(0), SymSprite(1))
     except LoweringError:
         raise
     except Exception as exc:  # pylint: disable=broad-except

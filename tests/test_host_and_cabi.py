@@ -351,3 +351,62 @@ def test_reward_function_lowering():
         lambdas.pair_reward(lambda a, b: 1. if b.c0 < 128 else -1.)
     with pytest.raises(lambdas.LoweringError):
         lambdas.pair_reward(lambda a, b: a.metadata['true_contact_color'])
+
+
+_VANISH_RANGE = [-1.2, 2.2]
+
+
+def _should_vanish(s):
+    """first_person_predators_prey.py:196-199 verbatim in structure: vector comparisons,
+    products of masks, builtin any(), Python `or`."""
+    pos_too_small = (s.position < _VANISH_RANGE[0]) * (s.velocity < 0.)
+    pos_too_large = (s.position > _VANISH_RANGE[1]) * (s.velocity > 0.)
+    return any(pos_too_small) or any(pos_too_large)
+
+
+def _wrap_position(s):
+    s.position = np.remainder(s.position, 1)
+
+
+def test_vector_valued_and_boolean_lambdas_lower_to_expressions():
+    """Sprite callables that use position / velocity as vectors, NumPy ufuncs on them, the
+    builtins any / all and Python's and / or / not are traced (after an AST rewrite of the
+    boolean constructs) to the postfix VM; evaluated here with a tiny interpreter."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import lambdas as L
+
+    def run(code, attrs):
+        st = []
+        for op, arg, c in code:
+            if op == L.X_CONST:
+                st.append(c)
+            elif op == L.X_ATTR0:
+                st.append(attrs[L.ATTRS[arg]])
+            elif op == L.X_NOT:
+                st.append(float(not st.pop()))
+            elif op == L.X_STORE:
+                attrs[L.ATTRS[arg]] = st.pop()
+            elif op == L.X_STORE_POS:
+                attrs['y'] = st.pop()
+                attrs['x'] = st.pop()
+            else:
+                b, a = st.pop(), st.pop()
+                st.append(float({L.X_LT: a < b, L.X_LE: a <= b, L.X_GT: a > b, L.X_GE: a >= b, L.X_EQ: a == b,
+                                 L.X_NE: a != b, L.X_AND: bool(a) and bool(b), L.X_OR: bool(a) or bool(b),
+                                 L.X_ADD: a + b, L.X_SUB: a - b, L.X_MUL: a * b, L.X_DIV: a / b if b else 0.,
+                                 L.X_MOD: a % b if b else 0.}[op]))
+        return st[-1] if st else None
+
+    code = L.compile_sprite_predicate(_should_vanish)
+    base = dict(x=0.5, y=0.5, x_vel=0.01, y_vel=-0.01)
+    assert run(code, dict(base)) == 0.0
+    assert run(code, dict(base, y=-1.3)) == 1.0           # below the range and moving down
+    assert run(code, dict(base, y=-1.3, y_vel=0.01)) == 0.0
+    assert run(code, dict(base, x=2.3)) == 1.0            # right of the range and moving right
+    attrs = dict(x=1.25, y=-0.25)
+    run(L.compile_modifier(_wrap_position), attrs)
+    assert attrs == dict(x=0.25, y=0.75)
+    code = L.compile_sprite_predicate(lambda s: s.c2 > 0.6 and not s.mass == 1)
+    assert run(code, dict(c2=0.7, mass=2.)) == 1.0 and run(code, dict(c2=0.7, mass=1.)) == 0.0
+    with pytest.raises(L.LoweringError):
+        L.compile_sprite_predicate(lambda s: 1. if s.c0 < 128 else -1.)   # a Python branch on a sprite value
