@@ -227,6 +227,11 @@ enum {
  * float32(lo + (hi - lo) * u), lo = dpool[idx], hi = dpool[idx + 1] (distributions.py:71-90,
  * Continuous samples are float32); discrete: one of the n values dpool[idx ..] with equal
  * probability (for the shape entry the values are shape ids).
+ * The table is followed by the extension program of the factors that are not drawn independently:
+ * n_ext, then per component either [1, n_alt, dpool index of the cumulative probabilities, then per
+ * alternative: n_leaves, (attr, kind, dpool index, n) ...] for a Mixture, or [2, keep_if_inside,
+ * n_leaves, leaves ..., n_box, (attr, dpool index of lo hi) ...] for SetMinus (0) / Selection (1): the
+ * base leaves are redrawn until the draw is outside / inside the box of Continuous ranges.
  * Shape record in dpool (one per distinct outline, sprite.py:329-424): [0] number of vertices nv,
  * [1] 1 if the shape is named 'circle', [2],[3] rotational inertia per unit mass about the centroid
  * (x, y parts), [4],[5] centroid of the raw outline (added to the position, sprite.py:389-406),

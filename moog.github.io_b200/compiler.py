@@ -696,6 +696,36 @@ def _flatten_distribution(dist):
         'Continuous / Discrete / constants); use the host pool (reset_sampler=False)'.format(k))
 
 
+def _lower_distribution(dist):
+    """Factor distribution -> (leaves, extensions).  `leaves` is the flat part
+    ({key: leaf}, see _flatten_distribution); `extensions` are the components of the top-level
+    Product that are not flat: ('mixture', [leaves of each alternative], probs) and
+    ('filtered', leaves of the base, [(key, lo, hi) of the Continuous box it is tested against],
+    keep_if_inside) for Selection / SetMinus (distributions.py: Mixture, SetMinus, Selection)."""
+    k = _kind(dist)
+    if k == 'Product':
+        leaves, ext = {}, []
+        for c in dist.components:
+            l2, e2 = _lower_distribution(c)
+            leaves.update(l2)
+            ext.extend(e2)
+        return leaves, ext
+    if k == 'Mixture':
+        alts = [_flatten_distribution(c) for c in dist.components]
+        keys = set(alts[0])
+        if any(set(a) != keys for a in alts):
+            raise CompileError('the alternatives of a Mixture must produce the same factors')
+        probs = [float(v) for v in dist.probs]
+        return {}, [('mixture', alts, probs)]
+    if k in ('SetMinus', 'Selection'):
+        base = _flatten_distribution(dist.base)
+        box = _flatten_distribution(dist._other)  # pylint: disable=protected-access
+        if any(v[0] != 'uniform' for v in box.values()):
+            raise CompileError('{} against anything but a box of Continuous factors is not on the device sampler'.format(k))
+        return {}, [('filtered', base, [(key, v[1], v[2]) for key, v in box.items()], k == 'Selection')]
+    return _flatten_distribution(dist), []
+
+
 def _shape_record(shape):
     """Shape record of include/moog_b200_program.h for one shape candidate."""
     from moog import sprite as sprite_lib
@@ -760,7 +790,7 @@ def _compile_reset_sampler(prog, state_initializer):
             raise CompileError('the sprites of one generate_sprites call must stay in one layer')
         if any(a >= slots[0] for a in avoid):
             raise CompileError('generated sprites can only avoid sprites in earlier slots')
-        flat = _flatten_distribution(rec['factor_dist'])
+        flat, extensions = _lower_distribution(rec['factor_dist'])
         lay = layer_of[id(rec['out'][0])]
         if slots[0] + len(slots) != prog.layer_off[lay] + len(state[prog.layer_names[lay]]):
             raise CompileError('generated sprites must be the last sprites of their layer')
@@ -783,13 +813,38 @@ def _compile_reset_sampler(prog, state_initializer):
                                 '{!r} ({}); pass more sample states'.format(
                                     int(shape_recs[sid][0]), prog.layer_names[lay], prog.layer_vcap[lay]))
                 table.append((ZK_CONST if len(values) == 1 else ZK_DISCRETE, values))
+        # factors drawn by the extensions: float32 iff every alternative draws them from a Continuous
+        ext_specs = []
+        for comp in extensions:
+            groups = comp[1] if comp[0] == 'mixture' else [comp[1]]
+            for key in groups[0]:
+                if key == 'shape':
+                    raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
+                kinds = {g[key][0] for g in groups}
+                if kinds == {'uniform'}:
+                    sampled32.add(key)
+                elif key in ('x_vel', 'y_vel', 'angle', 'angle_vel') and 'uniform' in kinds:
+                    raise CompileError('factor {!r} is float32 in some Mixture alternatives only'.format(key))
+
+            def enc(leaves_):
+                out_ = []
+                for key_, leaf in leaves_.items():
+                    values = list(leaf[1:]) if leaf[0] == 'uniform' else [float(v) for v in leaf[1]]
+                    kind_ = ZK_UNIFORM32 if leaf[0] == 'uniform' else (ZK_CONST if len(values) == 1 else ZK_DISCRETE)
+                    out_.append((_ATTR_KEYS.index(key_), kind_, values))
+                return out_
+            if comp[0] == 'mixture':
+                ext_specs.append(dict(kind=1, alts=[enc(a) for a in comp[1]], probs=comp[2]))
+            else:
+                ext_specs.append(dict(kind=2, base=enc(comp[1]), keep=bool(comp[3]),
+                                      box=[(_ATTR_KEYS.index(key), lo_, hi_) for key, lo_, hi_ in comp[2]]))
         if {'x_vel', 'y_vel'} <= sampled32:
             meta_flags |= SF_VEL32
         if 'angle_vel' in sampled32:
             meta_flags |= 1 << SF_ANGVEL_SHIFT
         if 'angle' in sampled32:
             meta_flags |= 1 << SF_ANG_SHIFT
-        specs.append(dict(first=slots[0], count=len(slots), avoid=avoid, table=table, meta_flags=meta_flags,
+        specs.append(dict(first=slots[0], count=len(slots), avoid=avoid, table=table, meta_flags=meta_flags, ext=ext_specs,
                           flags=(FL_DISJOINT if rec['disjoint'] else 0) | (
                               FL_FAIL_GRACEFULLY if rec['fail_gracefully'] else 0),
                           max_depth=float(rec['max_recursion_depth'])))
@@ -807,6 +862,28 @@ def _compile_reset_sampler(prog, state_initializer):
         for kind, values in sp_['table']:
             tab += [kind, len(prog.dpool), len(values)]
             prog.dpool.extend(float(v) for v in values)
+
+        def put_leaves(leaves_):
+            out_ = [len(leaves_)]
+            for attr, kind, values in leaves_:
+                out_ += [attr, kind, len(prog.dpool), len(values)]
+                prog.dpool.extend(float(v) for v in values)
+            return out_
+        # extension program: [n_ext, then per component: 1, n_alt, probs dpool index, alternatives... |
+        #                     2, keep_if_inside, base leaves, n_box, (attr, dpool index of lo hi)...]
+        tab.append(len(sp_['ext']))
+        for comp in sp_['ext']:
+            if comp['kind'] == 1:
+                cum = list(np.cumsum(comp['probs']))
+                tab += [1, len(comp['alts']), len(prog.dpool)]
+                prog.dpool.extend(float(v) for v in cum)
+                for alt in comp['alts']:
+                    tab += put_leaves(alt)
+            else:
+                tab += [2, 1 if comp['keep'] else 0] + put_leaves(comp['base']) + [len(comp['box'])]
+                for attr, lo_, hi_ in comp['box']:
+                    tab += [attr, len(prog.dpool)]
+                    prog.dpool.extend([float(lo_), float(hi_)])
         a_start = prog.add_ints(sp_['avoid'])
         t_start = prog.add_ints(tab)
         emitted.append((sp_, a_start, t_start))

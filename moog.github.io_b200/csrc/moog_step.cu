@@ -2790,6 +2790,14 @@ __device__ inline void store_env(const Env &e, const moog_state &st, size_t n) {
 // by (scale, scale * aspect_ratio), rotated, translated; position += raw centroid;
 // circumscribed radius; inertia * scale^2) and redrawn while it overlaps a sprite it must avoid.
 // ---------------------------------------------------------------------------
+// one factor from a leaf sampler (MOOG_ZK_*): a constant, np.float32(rng.uniform(lo, hi)), or one of n values
+__device__ __forceinline__ double sample_leaf(const double *dpool, int kind, int idx, int n, double u) {
+  if (kind == MOOG_ZK_CONST) return dpool[idx];
+  if (kind == MOOG_ZK_UNIFORM32) return (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);
+  const int pick = (int)(u * n);
+  return dpool[idx + (pick < n ? pick : n - 1)];
+}
+
 __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, const double *dpool,
                                             const int32_t *shape_off, uint64_t seed) {
   const Env e = env_view();
@@ -2811,16 +2819,56 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
 #pragma unroll 1
       for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
         const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
-        if (kind == MOOG_ZK_CONST) {
-          v[a] = dpool[idx];
-        } else {
-          const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                          ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | (uint32_t)a);
-          if (kind == MOOG_ZK_UNIFORM32) {
-            v[a] = (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);  // np.float32(rng.uniform(lo, hi))
+        const double u = kind == MOOG_ZK_CONST ? 0.0
+                                               : philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
+                                                                ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | (uint32_t)a);
+        v[a] = sample_leaf(dpool, kind, idx, n, u);
+      }
+      {
+        // extension components of the factor distribution (distributions.py: Mixture picks one
+        // alternative; SetMinus / Selection redraw their base until it is outside / inside a box)
+        const int32_t *x = tab + 3 * MOOG_Z_N_ATTRS;
+        const int n_ext = *x++;
+        uint32_t draw = 32;
+        for (int c = 0; c < n_ext; ++c) {
+          const int kind = *x++;
+          if (kind == 1) {
+            const int n_alt = *x++;
+            const double *cum = dpool + *x++;
+            const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
+                                            ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | draw++);
+            int pick = 0;
+            while (pick < n_alt - 1 && !(u < cum[pick])) ++pick;   // rng.choice(n, p=probs)
+            for (int a = 0; a < n_alt; ++a) {
+              const int n_leaves = *x++;
+              for (int q = 0; q < n_leaves; ++q, x += 4) {
+                if (a != pick) continue;
+                const double uu = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
+                                                 ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | draw++);
+                v[x[0]] = sample_leaf(dpool, x[1], x[2], x[3], uu);
+              }
+            }
           } else {
-            int pick = (int)(u * n);
-            v[a] = dpool[idx + (pick < n ? pick : n - 1)];
+            const int keep_inside = *x++;
+            const int n_leaves = *x++;
+            const int32_t *leaves = x;
+            x += 4 * n_leaves;
+            const int n_box = *x++;
+            const int32_t *box = x;
+            x += 2 * n_box;
+            for (int inner = 0; inner < 64; ++inner) {
+              for (int q = 0; q < n_leaves; ++q) {
+                const double uu = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
+                                                 ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | draw++);
+                v[leaves[4 * q]] = sample_leaf(dpool, leaves[4 * q + 1], leaves[4 * q + 2], leaves[4 * q + 3], uu);
+              }
+              bool inside = true;
+              for (int q = 0; q < n_box; ++q) {
+                const double val = v[box[2 * q]], lo = dpool[box[2 * q + 1]], hi = dpool[box[2 * q + 1] + 1];
+                inside = inside && val >= lo && val < hi;   // Continuous.contains
+              }
+              if (inside == (keep_inside != 0)) break;
+            }
           }
         }
       }

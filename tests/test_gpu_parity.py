@@ -472,3 +472,60 @@ def test_contact_reward_expression_matches_oracle():
         assert np.array_equal(got, r_ref.astype(np.float32)), step
         nonzero += int((r_ref != 0).sum())
     assert nonzero > 10
+
+
+@pytest.mark.gpu
+def test_device_reset_sampler_mixture_and_setminus():
+    """The factor distributions of first_person_predators_prey.py:37-66 on the device sampler: a
+    Mixture of four boundary segments for the position and a SetMinus (square annulus) for the
+    velocity."""
+    import collections
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, observers, physics as physics_lib, sprite, tasks
+    from moog.state_initialization import distributions as distribs
+    from moog.state_initialization import sprite_generators
+    from moog_b200.batched_env import BatchedEnvironment
+    lo, hi = -0.2, 1.2
+    position = distribs.Mixture([
+        distribs.Product([distribs.Continuous('y', lo, hi)], x=lo),
+        distribs.Product([distribs.Continuous('y', lo, hi)], x=hi),
+        distribs.Product([distribs.Continuous('x', lo, hi)], y=lo),
+        distribs.Product([distribs.Continuous('x', lo, hi)], y=hi)])
+    velocity = distribs.SetMinus(
+        distribs.Product([distribs.Continuous('x_vel', -0.03, 0.03), distribs.Continuous('y_vel', -0.03, 0.03)]),
+        hold_out=distribs.Product([distribs.Continuous('x_vel', -0.01, 0.01), distribs.Continuous('y_vel', -0.01, 0.01)]))
+    factors = distribs.Product([position, velocity, distribs.Continuous('scale', 0.05, 0.1)],
+                               shape='square', c0=0.3, c1=1., c2=1.)
+    gen = sprite_generators.generate_sprites(factors, num_sprites=6)
+
+    def state_initializer():
+        agent = [sprite.Sprite(x=0.5, y=0.5, shape='circle', scale=0.05, c0=0.6, c1=1., c2=1.)]
+        return collections.OrderedDict([('agent', agent), ('movers', gen())])
+
+    cfg = dict(state_initializer=state_initializer,
+               physics=physics_lib.Physics((physics_lib.Drag(coeff_friction=0.1), 'agent'), updates_per_env_step=2),
+               task=tasks.CompositeTask(timeout_steps=20),
+               action_space=action_spaces.Joystick(scaling_factor=0.01, action_layers='agent'),
+               observers={'image': observers.PILRenderer(image_size=(64, 64), color_to_rgb='hsv_to_rgb')})
+    np.random.seed(2)
+    states = [state_initializer() for _ in range(2)]
+    N = 1024
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=3, initial_states=states, reset_mode='device')
+    env.reset()
+    st = env.engine.state.download()
+    assert (st['envi'][:, 2] == 0).all() and (st['cnt'][:, :2] == [1, 6]).all()
+    s0 = env.program.layer_off[1]
+    x, y = st['dyn'][:, 0, s0:s0 + 6].ravel(), st['dyn'][:, 1, s0:s0 + 6].ravel()
+    vx, vy = st['dyn'][:, 2, s0:s0 + 6].ravel(), st['dyn'][:, 3, s0:s0 + 6].ravel()
+    f32 = lambda a: np.array_equal(a, a.astype(np.float32).astype(np.float64))
+    near = lambda a, b: np.abs(a - b) < 1e-12     # (the position is x + the outline's raw centroid, ~1e-17)
+    on = np.stack([near(x, lo), near(x, hi), near(y, lo), near(y, hi)], axis=1)
+    assert (on.sum(axis=1) == 1).all(), 'every position lies on exactly one boundary segment'
+    share = on.mean(axis=0)
+    assert np.all(np.abs(share - 0.25) < 0.03), share
+    free = np.where(on[:, 0] | on[:, 1], y, x)
+    assert free.min() >= lo - 1e-12 and free.max() < hi + 1e-12
+    assert np.abs(vx).max() < 0.03 and np.abs(vy).max() < 0.03 and f32(vx) and f32(vy)
+    assert not ((np.abs(vx) < 0.01) & (np.abs(vy) < 0.01)).any(), 'the hold-out box is empty'
+    assert ((np.abs(vx) < 0.01) | (np.abs(vy) < 0.01)).mean() > 0.3      # ... but only the box, not the cross
+    assert (st['meta'][:, 1, s0:s0 + 6] & 0x3f == 2).all()               # float32 velocity array
