@@ -327,9 +327,24 @@ def run_ours(args):
             dist.barrier()
 
     # ---- device-resident arm ------------------------------------------------
+    # --render auto: the step call is asked for the frames (moog_step_io.frames) and the library
+    # draws them inside the step kernel when a canvas fits next to the env record at no cost in
+    # residency, else with the render kernel; --render separate: step call, then render call
+    fused = args.render == 'auto' and eng.dev_program.step_draws_frames(E)
+
+    def device_step():
+        if args.render == 'auto':
+            eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'), frames=True)
+        else:
+            eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'))
+
+    def device_render():
+        if args.render != 'auto':
+            eng.render()
+
     for _ in range(max(args.warmup, 3)):
-        eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'))
-        eng.render()
+        device_step()
+        device_render()
     torch.cuda.synchronize()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
@@ -342,9 +357,9 @@ def run_ours(args):
     for k in range(args.steps):
         flush.fill_(k & 255)          # evict L2 between timed iterations (untimed)
         ev[k][0].record()
-        eng.env_step(dev_actions, sample_resets=(args.reset_mode == 'device'))
+        device_step()
         ev[k][1].record()
-        eng.render()
+        device_render()
         ev[k][2].record()
     stats = env.episode_stats(reduce=True)   # the only collective: 4 doubles
     torch.cuda.synchronize()
@@ -364,17 +379,17 @@ def run_ours(args):
     from moog_b200.batched_env import TimeStep
     host_ts = TimeStep(host_step_type, host_reward, None, {'image': host_frames})
     for _ in range(2):
-        env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks)
+        env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks, frames=args.e2e_frames)
     torch.cuda.synchronize()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        # H2D of the actions, the step, the frames rendered in 4 env ranges with the D2H
-        # copy of each range overlapping the next one's render; returns when the host
-        # buffers hold the whole TimeStep (the caller owns it now)
-        env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks)
+        # H2D of the actions, the step, the frames into the pinned host image (written by the
+        # kernels themselves over PCIe as the envs finish -- 'mapped' -- or drawn in HBM and
+        # copied); returns when the host buffers hold the whole TimeStep (the caller owns it)
+        env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks, frames=args.e2e_frames)
     e1.record()
     torch.cuda.synchronize()
     e2e_value = world * E * args.steps / (mdist.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3)
@@ -390,8 +405,13 @@ def run_ours(args):
     ab = ALGO_BYTES.get(args.scene, dict(state=prog.n_slots * 96 + 20, frame=H * W * 3))
     step_ms = float(np.mean(ms_step_k))
     rend_ms = float(np.mean(ms_rend_k))
-    step_gbs = E * ab['state'] / (step_ms * 1e-3) / 1e9
-    rend_gbs = E * (ab['frame'] + prog.n_slots * 32) / (rend_ms * 1e-3) / 1e9
+    # algorithmic bytes of one step-kernel launch: the record in and out, plus the frame when the
+    # kernel draws it (the renderer then reads the record in shared memory, not in HBM)
+    step_bytes = ab['state'] + (ab['frame'] if fused else 0)
+    step_gbs = E * step_bytes / (step_ms * 1e-3) / 1e9
+    if args.render == 'auto':
+        rend_ms = 0.0   # the frames were drawn inside the step call: its interval covers both
+    rend_gbs = E * (ab['frame'] + prog.n_slots * 32) / (rend_ms * 1e-3) / 1e9 if rend_ms > 0 else None
     record_bytes = eng.state.nbytes() // E
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -405,19 +425,24 @@ def run_ours(args):
                    'resets': ('device-side sampler' if args.reset_mode == 'device' else
                               'pool of {} host-generated initial states'.format(len(states))),
                    'step_launch': dict(zip(('resident_envs_per_sm', 'warps_per_env', 'smem_bytes_per_env'),
-                                           eng.dev_program.step_launch_info(E)))},
+                                           eng.dev_program.step_launch_info(E))),
+                   'frames': ('drawn inside moog_step_kernel, env by env as they finish' if fused else
+                              'moog_render_kernel after moog_step_kernel'),
+                   'e2e_frames': args.e2e_frames},
         'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak,
-                     'traffic': _ncu_traffic('step_kernel') if args.scene == 'falling_balls20' and E == 4096 else None,
-                     'traffic_note': 'bytes per launch, ncu --set full of this workload (profiles/r01_step_kernel_ncu.json)',
-                     'algorithmic_bytes_per_launch': E * ab['state'],
+                     'traffic': (_ncu_traffic('step_fused_kernel' if fused else 'step_kernel')
+                                 if args.scene == 'falling_balls20' and E == 4096 else None),
+                     'traffic_note': 'bytes per launch, ncu --set full of this workload (profiles/)',
+                     'algorithmic_bytes_per_launch': E * step_bytes,
                      'peak_source': peak_src,
-                     'algorithmic_bytes_per_env_step': ab['state'], 'kernel_ms': step_ms,
-                     'render_kernel': {'kernel': 'moog_render_kernel', 'achieved': rend_gbs, 'frac': rend_gbs / peak,
-                                       'algorithmic_bytes_per_env_step': ab['frame'] + prog.n_slots * 32,
-                                       'traffic': (_ncu_traffic('render_kernel')
-                                                   if args.scene == 'falling_balls20' and E == 4096 else None),
-                                       'kernel_ms': rend_ms},
+                     'algorithmic_bytes_per_env_step': step_bytes, 'kernel_ms': step_ms,
+                     'render_kernel': (None if rend_gbs is None else
+                                       {'kernel': 'moog_render_kernel', 'achieved': rend_gbs, 'frac': rend_gbs / peak,
+                                        'algorithmic_bytes_per_env_step': ab['frame'] + prog.n_slots * 32,
+                                        'traffic': (_ncu_traffic('render_kernel')
+                                                    if args.scene == 'falling_balls20' and E == 4096 else None),
+                                        'kernel_ms': rend_ms}),
                      'share_of_step': {'moog_step_kernel': step_ms / (step_ms + rend_ms),
                                        'moog_render_kernel': rend_ms / (step_ms + rend_ms)}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
@@ -453,7 +478,13 @@ def main():
     ap.add_argument('--no-clocks', action='store_true')
     ap.add_argument('--reset-mode', default='pool', choices=['pool', 'device'],
                     help="'device': resetting envs draw their generated sprites on the GPU")
-    ap.add_argument('--e2e-chunks', type=int, default=4, help='env ranges the e2e arm renders / copies in')
+    ap.add_argument('--e2e-chunks', type=int, default=4,
+                    help="env ranges the e2e arm renders / copies in (--e2e-frames chunked)")
+    ap.add_argument('--render', default='auto', choices=['auto', 'separate'],
+                    help="'auto': the step call draws the frames (inside the step kernel when they fit); "
+                         "'separate': step call, then render call")
+    ap.add_argument('--e2e-frames', default='auto', choices=['auto', 'mapped', 'device', 'chunked'],
+                    help='how the e2e arm brings the frames to the host (BatchedEnvironment.step_to_host)')
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()

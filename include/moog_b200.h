@@ -76,6 +76,12 @@ typedef struct {
                             pool entry 0 as its template and draws its generated sprites afresh on
                             the device (Philox keyed by seed, env, episode) instead of copying a
                             whole pool entry                                                       */
+  uint8_t *frames;     /* [N][H][W][3] or NULL: PILRenderer.__call__ (pil_renderer.py:88-120) of the state
+                          every env is left in, as moog_render would draw it after this call.  When the
+                          canvas fits next to the env record in shared memory the step kernel draws it
+                          itself, env by env as they finish, otherwise the render kernel follows.  Any
+                          device-accessible address: HBM, or pinned host memory (cudaHostAlloc /
+                          cudaHostRegister under unified addressing) for frames the host reads          */
 } moog_step_io;
 
 /* Upload a compiled program (host pointer to the blob).  Replaces nothing in the
@@ -133,6 +139,11 @@ int64_t moog_launch_count(void);
  * env in bytes.  The step is bound by its longest-running env; see DESIGN.md section 3.1. */
 int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_per_sm, int *warps_per_env,
                           int *smem_bytes_per_env);
+
+/* 1 when moog_env_step with io->frames draws the frames of a batch of n_envs inside the step
+ * kernel (the canvas fits next to the env record without costing residency), 0 when the render
+ * kernel follows the step kernel. */
+int moog_step_draws_frames(const moog_program *p, int n_envs);
 
 #ifdef __cplusplus
 }

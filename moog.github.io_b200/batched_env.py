@@ -166,8 +166,25 @@ class Engine(object):
                 self.dev_program.handle, ctypes.byref(st), self.n, _ptr(rn), self._stream()))
 
     def env_step(self, actions=None, noise=None, rule_noise=None, auto_reset=True,
-                 reset_index=None, want_counters=False, sample_resets=False):
+                 reset_index=None, want_counters=False, sample_resets=False, frames=None):
+        """`moog_env_step`.  frames: None, True (draw the frame of the state every env is left in
+        into `self.frames`) or a uint8 [N, H, W, 3] tensor to draw into -- on this device, or a
+        pinned CPU tensor, which the kernels then write over PCIe as the envs finish."""
         p = self.program
+        if frames is True:
+            frames = self.frames
+        if frames is not None:
+            if self.frames is None:
+                raise capi.MoogError('the program has no PILRenderer observer')
+            if (frames.dtype != torch.uint8 or tuple(frames.shape) != tuple(self.frames.shape)
+                    or not frames.is_contiguous()):
+                raise ValueError('frames must be a contiguous uint8 tensor of shape {}'.format(
+                    tuple(self.frames.shape)))
+            if frames.device.type == 'cpu':
+                if not frames.is_pinned():
+                    raise ValueError('host frames must live in pinned memory')
+            elif frames.device != self.state.dyn.device:
+                raise ValueError('frames are on {}, the envs on {}'.format(frames.device, self.state.dyn.device))
         act = self._as_f64(actions, max(p.action_dim, 1)) if actions is not None else None
         nz = self._as_f64(noise, p.K * p.noise_dim) if (noise is not None and p.noise_dim) else None
         rn = self._as_f64(rule_noise, p.rule_noise_dim) if (
@@ -188,6 +205,7 @@ class Engine(object):
         io.reward, io.step_type, io.discount = _ptr(self.reward), _ptr(self.step_type), _ptr(self.discount)
         io.counters = _ptr(self.counters) if want_counters else None
         io.stats = _ptr(self.stats)
+        io.frames = _ptr(frames)
         st = self.state.struct()
         with torch.cuda.device(self.device):
             capi.check(capi.lib().moog_env_step(
@@ -302,22 +320,49 @@ class BatchedEnvironment(object):
         concatenation in the order of `program.action_layout`)."""
         if not self._started:
             return self.reset()
-        self.engine.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'))
-        return self._timestep()
+        # the observation is drawn by the step call itself (inside the step kernel when a canvas
+        # fits next to the env record, see include/moog_b200.h `frames`)
+        self.engine.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'),
+                             frames=True if self._image_key is not None else None)
+        return self._timestep(rendered=True)
 
-    def step_to_host(self, action, host, chunks=4):
+    def step_to_host(self, action, host, chunks=4, frames='auto'):
         """`step(action)` whose TimeStep lands in the caller's pinned host buffers:
         `host` is a TimeStep of CPU tensors (step_type int32[N], reward float32[N],
-        discount float32[N] or None, observation {'image': uint8[N,H,W,3]}).  The
-        frames are rendered in `chunks` env ranges; the device-to-host copy of one
-        range runs on a second stream while the next range is rendered.  Returns
-        `host` once everything has arrived (the caller owns the TimeStep)."""
-        if not self._started:
-            self.reset()
-        else:
-            self.engine.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'))
+        discount float32[N] or None, observation {'image': uint8[N,H,W,3]}).  Returns
+        `host` once everything has arrived (the caller owns the TimeStep).
+
+        frames = 'mapped': the step call draws every env's frame straight into the pinned host
+        image (the kernels' stores cross PCIe while other envs are still being stepped; no
+        device copy of the frames exists).  'device': the step call draws into device memory,
+        one device-to-host copy follows.  'chunked': the step, then the frames rendered in
+        `chunks` env ranges, the device-to-host copy of one range running on a second stream
+        while the next range is rendered.  'auto': 'mapped' when the host image is pinned,
+        else 'device'."""
+        img = host.observation[self._image_key] if self._image_key is not None else None
+        if frames == 'auto':
+            frames = 'mapped' if (img is not None and img.is_pinned()) else 'device'
+        if frames not in ('mapped', 'device', 'chunked'):
+            raise ValueError("frames must be 'auto', 'mapped', 'device' or 'chunked'")
         e = self.engine
         main = torch.cuda.current_stream(e.device)
+        if frames != 'chunked' or not self._started:
+            if not self._started:
+                self.reset()
+                if img is not None:
+                    img.copy_(e.frames, non_blocking=True)
+            else:
+                dst = None if img is None else (img if frames == 'mapped' else True)
+                e.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'), frames=dst)
+                if img is not None and frames == 'device':
+                    img.copy_(e.frames, non_blocking=True)
+            host.step_type.copy_(e.step_type, non_blocking=True)
+            host.reward.copy_(e.reward, non_blocking=True)
+            if host.discount is not None:
+                host.discount.copy_(e.discount, non_blocking=True)
+            main.synchronize()
+            return host
+        self.engine.env_step(self._flatten_action(action), sample_resets=(self.reset_mode == 'device'))
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=e.device)
             self._copy_events = [torch.cuda.Event() for _ in range(64)]
@@ -356,9 +401,13 @@ class BatchedEnvironment(object):
             obs[self._image_key] = self.engine.render()
         return obs
 
-    def _timestep(self):
+    def _timestep(self, rendered=False):
         e = self.engine
-        return TimeStep(e.step_type, e.reward, e.discount, self.observation())
+        if rendered:
+            obs = {self._image_key: e.frames} if self._image_key is not None else {}
+        else:
+            obs = self.observation()
+        return TimeStep(e.step_type, e.reward, e.discount, obs)
 
     def _flatten_action(self, action):
         if action is None:

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, 'csrc')
 LIB = os.environ.get('MOOG_B200_LIB') or os.path.join(_PKG, 'lib', 'libmoog_b200.so')   # override: A/B runs
 SOURCES = ['moog_step.cu', 'moog_render.cu', 'moog_capi.cu', 'moog_host_geom.cpp']
-HEADERS = [os.path.join(CSRC, 'moog_common.cuh'),
+HEADERS = [os.path.join(CSRC, 'moog_common.cuh'), os.path.join(CSRC, 'moog_render_dev.cuh'),
            os.path.join(_PKG, '..', 'include', 'moog_b200.h'),
            os.path.join(_PKG, '..', 'include', 'moog_b200_program.h')]
 

@@ -29,7 +29,8 @@ class MoogStepIO(ctypes.Structure):
                 ('reset_index', ctypes.c_void_p), ('seed', ctypes.c_uint64),
                 ('reward', ctypes.c_void_p), ('step_type', ctypes.c_void_p),
                 ('discount', ctypes.c_void_p), ('counters', ctypes.c_void_p),
-                ('stats', ctypes.c_void_p), ('sample_resets', ctypes.c_int32)]
+                ('stats', ctypes.c_void_p), ('sample_resets', ctypes.c_int32),
+                ('frames', ctypes.c_void_p)]
 
 
 # every symbol include/moog_b200.h declares
@@ -38,7 +39,8 @@ SYMBOLS = ('moog_program_create', 'moog_program_destroy',
            'moog_env_post_reset', 'moog_physics_step', 'moog_overlap_pairs',
            'moog_render', 'moog_strerror', 'moog_last_cuda_error',
            'moog_launch_count', 'moog_host_paths_overlap',
-           'moog_host_points_in_path', 'moog_step_launch_info')
+           'moog_host_points_in_path', 'moog_step_launch_info',
+           'moog_step_draws_frames')
 
 
 class MoogError(RuntimeError):
@@ -92,6 +94,8 @@ def lib():
     L.moog_host_points_in_path.restype = None
     L.moog_step_launch_info.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
     L.moog_step_launch_info.restype = ci
+    L.moog_step_draws_frames.argtypes = [vp, ci]
+    L.moog_step_draws_frames.restype = ci
     L.moog_launch_count.argtypes = []
     L.moog_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -131,6 +135,13 @@ class DeviceProgram(object):
         r, w, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         check(lib().moog_step_launch_info(self._h, int(n_envs), ctypes.byref(r), ctypes.byref(w), ctypes.byref(s)))
         return r.value, w.value, s.value
+
+    def step_draws_frames(self, n_envs):
+        """Whether `moog_env_step` with frames draws them inside the step kernel."""
+        r = int(lib().moog_step_draws_frames(self._h, int(n_envs)))
+        if r < 0:
+            check(r)
+        return bool(r)
 
     def close(self):
         if self._h:

@@ -18,6 +18,8 @@ struct moog_program {
   int *sched;  // [2][sched_cap]: cost, order
   int sched_cap;
   const void *sched_state;  // the state the costs belong to
+  int *done;                // [1 + done_cap]: envs in the order the running step finishes them
+  int done_cap;
   // anti_aliasing > 1: Lanczos coefficient tables (Resample.c), built on first use
   int *resample;
   int ksize_h, ksize_v;
@@ -88,6 +90,7 @@ void moog_program_destroy(moog_program *p) {
   if (!p) return;
   if (p->dev_blob) cudaFree(p->dev_blob);
   if (p->sched) cudaFree(p->sched);
+  if (p->done) cudaFree(p->done);
   if (p->resample) cudaFree(p->resample);
   free(p);
 }
@@ -124,6 +127,27 @@ int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_
   if (smem_bytes_per_env) *smem_bytes_per_env = moog::env_smem_bytes(p->hdr, helper);
   return 0;
 }
+
+// How moog_env_step produces io->frames for a batch of n_envs: 2 = inside the step kernel when one
+// CTA can hold the canvas (small batches: every env has an SM to itself, one launch and no second
+// pass over the state), 1 = by the render kernel.
+static int frames_mode(int n_envs) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return n_envs <= 2 * sms ? 2 : 1;
+}
+
+int moog_step_draws_frames(const moog_program *p, int n_envs) {
+  if (!p || n_envs < 0) return MOOG_E_INVAL;
+  int resident = 0;
+  bool helper = false;
+  launch_policy(n_envs, n_envs >= 1024, &resident, &helper);
+  return moog::plan_step(p->hdr, resident, helper, frames_mode(n_envs)).fuse ? 1 : 0;
+}
+
+static int render_impl(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream,
+                       int *done, int tail_mode, long long *trace = nullptr);
 
 static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode, const moog_step_io *io,
                     int layer_a, int layer_b, uint8_t *overlap_out, void *stream) {
@@ -176,9 +200,49 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   int resident = 0;
   bool helper = false;
   launch_policy(n_envs, a.order != nullptr, &resident, &helper);
-  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches, 0, -1, resident, helper);
+  bool fused = false;
+  if (a.io.frames && (mode != moog::MODE_ENV_STEP || !p->hdr[MOOG_H_R_ENABLED] || p->hdr[MOOG_H_R_AA] < 1))
+    return MOOG_E_INVAL;
+  const int fmode = a.io.frames ? frames_mode(n_envs) : 0;
+  // Frames of a large batch: the step ends when its longest-running env does, and long before
+  // that most SMs have no env left to step.  The render kernel is launched behind the step kernel
+  // with programmatic stream serialization, starts as soon as the last env has got an SM, and
+  // draws the envs in the order they finish (the `done` list) on the SMs the step left idle
+  // (MOOG_TAIL_RENDER=0: the render kernel waits for the whole step instead).
+  bool tail = a.io.frames && a.order != nullptr &&
+              !moog::plan_step(p->hdr, resident, helper, fmode).fuse;
+  int tail_mode = 2;
+  {
+    const char *t = getenv("MOOG_TAIL_RENDER");
+    if (t) tail_mode = atoi(t);
+    if (tail_mode <= 0) tail = false;
+  }
+  if (tail) {
+    if (p->done_cap < n_envs) {
+      if (p->done) cudaFree(p->done);
+      p->done = nullptr;
+      p->done_cap = 0;
+      err = cudaMalloc((void **)&p->done, sizeof(int) * (1 + (size_t)n_envs + moog::kTailExtraInts));
+      if (err != cudaSuccess) return cuda_fail(err);
+      p->done_cap = n_envs;
+    }
+    // count, finished list [n_envs], ticket, envs being stepped per SM [256]
+    err = cudaMemsetAsync(p->done, 0, sizeof(int) * (1 + (size_t)n_envs + moog::kTailExtraInts), (cudaStream_t)stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+    a.done = p->done;
+    if (tail_mode == 2) a.sm_active = p->done + 1 + n_envs + 1;
+  }
+  {
+    const char *t = getenv("MOOG_TRACE_TIMES");  // diagnostic: per-env timeline in io.counters
+    a.trace = (t && atoi(t) != 0 && a.io.counters) ? 1 : 0;
+  }
+  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches, 0, -1, resident, helper, fmode, &fused);
   g_launches += launches;
-  return err == cudaSuccess ? 0 : cuda_fail(err);
+  if (err != cudaSuccess) return cuda_fail(err);
+  if (a.io.frames && !fused)
+    return render_impl(p, st, n_envs, a.io.frames, stream, tail ? p->done : nullptr, tail_mode,
+                       a.trace ? (long long *)a.io.counters : nullptr);
+  return 0;
 }
 
 int moog_env_step(moog_program *p, const moog_state *st, int n_envs, const moog_step_io *io, void *stream) {
@@ -213,6 +277,11 @@ int moog_overlap_pairs(moog_program *p, const moog_state *st, int n_envs, int la
 }
 
 int moog_render(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream) {
+  return render_impl(p, st, n_envs, frames, stream, nullptr, 0);
+}
+
+static int render_impl(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream,
+                       int *done, int tail_mode, long long *trace) {
   if (!p || !valid_state(st) || !frames || n_envs < 0) return MOOG_E_INVAL;
   if (!p->hdr[MOOG_H_R_ENABLED]) return MOOG_E_INVAL;
   if (p->hdr[MOOG_H_R_AA] < 1) return MOOG_E_UNSUPPORTED;
@@ -222,6 +291,7 @@ int moog_render(moog_program *p, const moog_state *st, int n_envs, uint8_t *fram
   a.st = *st;
   a.n_envs = n_envs;
   a.frames = frames;
+  a.trace = trace;
   if (p->hdr[MOOG_H_R_AA] > 1) {
     if (!p->resample) {
       const int OH = p->hdr[MOOG_H_R_HEIGHT], OW = p->hdr[MOOG_H_R_WIDTH], aa = p->hdr[MOOG_H_R_AA];
@@ -237,7 +307,7 @@ int moog_render(moog_program *p, const moog_state *st, int n_envs, uint8_t *fram
     a.ksize_v = p->ksize_v;
   }
   int launches = 0;
-  cudaError_t err = moog::launch_render(a, p->hdr, (cudaStream_t)stream, &launches);
+  cudaError_t err = moog::launch_render(a, p->hdr, (cudaStream_t)stream, &launches, done, n_envs, tail_mode);
   g_launches += launches;
   return err == cudaSuccess ? 0 : cuda_fail(err);
 }

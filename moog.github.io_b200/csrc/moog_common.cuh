@@ -43,7 +43,14 @@ struct StepArgs {
   const int *order;          // [n_envs] env handled by CTA i, or nullptr = identity
   int first, count;          // this launch covers dispatch positions [first, first + count)
   int *cost;                 // [n_envs] SM cycles >> 6 this call cost each env, or nullptr
+  int *done;                 // nullptr or [1 + n_envs], zeroed: count, then env + 1 in finishing order
+  int *sm_active;            // nullptr or [256], zeroed: envs being stepped on each SM right now
+  int trace;                 // MOOG_TRACE_TIMES=1: io.counters[n][6..7] = globaltimer at start / finish
   moog_step_io io;
+  // io.frames, drawn by the step kernel itself (launch_step decides): shared-memory offset of
+  // the renderer's buffers behind the part of the env record it reads
+  int fused_render, render_off;
+  uint8_t *frames;
   moog_state pool;  // valid iff io.pool != nullptr
   // MODE_OVERLAP
   int layer_a, layer_b;
@@ -55,6 +62,7 @@ struct RenderArgs {
   moog_state st;
   int n_envs;
   uint8_t *frames;
+  long long *trace;     // MOOG_TRACE_TIMES=1: the step's counters; [n][4..5] = globaltimer at render start / end
   const int *resample;  // anti_aliasing > 1: device copy of resample_tables()
   int ksize_h, ksize_v;
 };
@@ -67,10 +75,22 @@ int candidate_matrix_words(const void *host_blob);
 // resident_envs_per_sm > 0 pads the shared-memory request so that at most that many envs
 // share an SM; helper: every env's CTA gets a second warp that runs one direction of
 // _get_collision_vectors next to its owner
+struct StepPlan { size_t smem; bool fuse; int render_off; };
+// frames_mode: 0 no frames, 1 frames (fused only when MOOG_FUSED_RENDER=1), 2 frames, fused preferred
+StepPlan plan_step(const int32_t *host_hdr, int resident_envs_per_sm, bool helper, int frames_mode);
+// *fused (optional): whether the kernel also drew a.io.frames (else the caller runs launch_render)
 cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches,
-                        int first = 0, int count = -1, int resident_envs_per_sm = 0, bool helper = false);
+                        int first = 0, int count = -1, int resident_envs_per_sm = 0, bool helper = false,
+                        int frames_mode = 0, bool *fused = nullptr);
 cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream, int *n_launches);
 int resample_tables(int H, int W, int OH, int OW, std::vector<int> &table, int *ksize_h, int *ksize_v);
-cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches);
+// done: nullptr, or the finished-env list of the step kernel launched just before on `stream`
+// (StepArgs::done): the render kernel is then launched with programmatic stream serialization,
+// starts while the last envs are still being stepped and draws the envs in finishing order
+cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches,
+                          int *done = nullptr, int n_done = 0, int tail_mode = 1);
+// ints behind the finished list that launch_render's tail kernels use: a ticket counter and the
+// per-SM count of envs being stepped
+constexpr int kTailExtraInts = 1 + 256;
 
 }  // namespace moog

@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include "moog_common.cuh"
+#include "moog_render_dev.cuh"
 
 namespace moog {
 
@@ -2963,31 +2964,19 @@ __device__ inline void post_reset(const Env &e) {
 // CTA-uniform offset from the dynamic shared-memory base, and the program's
 // dimensions arrive in the parameter bank, so address arithmetic stays on the
 // uniform datapath instead of occupying vector registers.
-__global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  if ((int)blockIdx.x >= a.count) return;
-  if (threadIdx.x >= 32) {
-    // Helper warp (launched when the step is bound by its longest-running env and the SMs
-    // have registers to spare): sleeps on a named barrier until the owner posts a request,
-    // runs one direction of _get_collision_vectors (collisions.py:268-283: the two directed
-    // computations are independent) on the env's shared-memory record, posts the result.
-    for (;;) {
-      cta_bar(1);
-      const Env e = env_view();
-      const int *req = (const int *)e.xchg;
-      if (req[0] == HELPER_EXIT) return;
-      CVec out;
-      directed_collision_vectors(e, req[1], req[2], 1.0 / e.K, out);
-      if (e.lane == 0) *(CVec *)(e.xchg + 16) = out;
-      cta_bar(2);
-    }
-  }
+__device__ __forceinline__ void owner_warp(const StepArgs &a, unsigned char *smem_raw, const int lane) {
   // CTAs are dispatched in blockIdx order: with `order` the envs that were the most
   // expensive on the previous call go first, so the longest-running env does not
   // start in the last wave (longest-processing-time-first)
   const int n = a.order ? a.order[a.first + blockIdx.x] : a.first + (int)blockIdx.x;
   const long long t_begin = clock64();
+  unsigned long long trace_t0 = 0;
+  if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+  unsigned smid = 0;
+  if (a.sm_active) {
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (lane == 0) atomicAdd(a.sm_active + (smid & 255), 1);
+  }
 
   ProgramView pv = view_of(a.blob);
   const int NF = a.NF;
@@ -3117,6 +3106,14 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
     cta_bar(1);
   }
   if (a.mode != MODE_OVERLAP) store_env(e, a.st, (size_t)n);
+  if (a.done && lane == 0) {
+    // this env's record is in HBM (store_env waited for its bulk stores): append the env to the
+    // list of finished envs, release order, for the render CTA that waits on that entry
+    __threadfence();
+    const int k = atomicAdd(a.done, 1);
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.done + 1 + k), "r"(n + 1) : "memory");
+    if (a.sm_active) atomicSub(a.sm_active + (smid & 255), 1);
+  }
   if (lane == 0) {
     if (a.cost) {
       long long c = (clock64() - t_begin) >> 6;
@@ -3135,6 +3132,12 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
       a.io.counters[MOOG_N_COUNTERS * (size_t)n + 5] = e.ctr[CT_NARROW];
       a.io.counters[MOOG_N_COUNTERS * (size_t)n + 6] = e.ctr[CT_CYC_NARROW];
       a.io.counters[MOOG_N_COUNTERS * (size_t)n + 7] = e.ctr[CT_CYC_RESOLVE];
+      if (a.trace) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        a.io.counters[MOOG_N_COUNTERS * (size_t)n + 6] = (long long)trace_t0;
+        a.io.counters[MOOG_N_COUNTERS * (size_t)n + 7] = (long long)t1;
+      }
     }
     if (a.io.stats && a.mode == MODE_ENV_STEP) {
       if (step_type != MOOG_STEP_FIRST) {
@@ -3146,6 +3149,55 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
         atomicAdd(&a.io.stats[2], ep_done);
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  // A kernel launched behind this one with programmatic stream serialization (the tail render
+  // kernel, moog_render.cu) may start as soon as every CTA of this grid has got here, i.e. once
+  // no env is waiting for an SM any more; it consumes the envs in the order they finish (a.done).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if ((int)blockIdx.x >= a.count) return;
+  if (threadIdx.x >= 32) {
+    // Helper warp (launched when the step is bound by its longest-running env and the SMs
+    // have registers to spare): sleeps on a named barrier until the owner posts a request,
+    // runs one direction of _get_collision_vectors (collisions.py:268-283: the two directed
+    // computations are independent) on the env's shared-memory record, posts the result.
+    for (;;) {
+      cta_bar(1);
+      const Env e = env_view();
+      const int *req = (const int *)e.xchg;
+      if (req[0] == HELPER_EXIT) break;
+      CVec out;
+      directed_collision_vectors(e, req[1], req[2], 1.0 / e.K, out);
+      if (e.lane == 0) *(CVec *)(e.xchg + 16) = out;
+      cta_bar(2);
+    }
+  } else {
+    owner_warp(a, smem_raw, lane);
+  }
+  if (!a.fused_render) return;
+  // PILRenderer.__call__ (pil_renderer.py:88-120) of the state the env was left in, by every
+  // thread of the CTA, from the record that is still in shared memory: the canvas, edge lists and
+  // int vertices go where the step's scratch was, the item spans into the vertex cache once the
+  // int vertices exist (the owner's bulk stores have completed: store_env waits for them).
+  // Frames leave the SM while the longest-running envs of the batch are still being stepped.
+  __syncthreads();
+  {
+    const Env e = env_view();
+    const int OH = e.hdr[MOOG_H_R_HEIGHT], OW = e.hdr[MOOG_H_R_WIDTH];
+    const int C = e.hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;
+    const int VTr = a.VT > 0 ? a.VT : 1;
+    const RenderLayout lay = render_layout(OH, OW, a.S * C, VTr * C, OW, 16 * VTr);
+    RenderSrc src;
+    src.dyn = e.dyn; src.stat = e.stat; src.meta = e.meta; src.cnt = e.cnt;
+    src.vtx = e.vtx; src.hdr = e.hdr; src.voff = e.voff;
+    const int T = (int)blockDim.x;
+    const int P = (OH * 2 <= T) ? 2 : 1;
+    render_env(src, lay, smem_raw + a.render_off, (unsigned *)e.vtx, (int)threadIdx.x, T, P, true,
+               a.frames + (size_t)e.env_id * OH * OW * 3, nullptr, 0, 0, [] { __syncthreads(); });
   }
 }
 
@@ -3187,21 +3239,18 @@ cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream
   return cudaGetLastError();
 }
 
-cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches, int first,
-                        int count, int resident_envs_per_sm, bool helper) {
-  if (count < 0) count = a.n_envs - first;
-  if (a.n_envs <= 0 || count <= 0) return cudaSuccess;
-  int per_env = env_smem_bytes(hdr, helper);
-  const int warps = 1;
-  size_t smem = (size_t)per_env * warps;
+// Shared-memory request of one step CTA and whether the CTA also draws its env's frame.
+StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, int frames_mode) {
+  StepPlan plan;
+  size_t smem = (size_t)env_smem_bytes(hdr, helper);
   {
     // Resident CTAs (= envs) per SM.  The step is bound by its longest-running env, and a
     // warp runs ~2.4x slower next to 11 others than alone (profiles/README.md), so beyond
     // the point where every SM has work, fewer co-resident envs finish the step sooner.  The
     // dynamic shared-memory request is padded to cap the residency (MOOG_CTAS_PER_SM
     // overrides; MOOG_SMEM_PAD=<bytes> pads directly).
-    static const char *pad = getenv("MOOG_SMEM_PAD");
-    static const char *cps = getenv("MOOG_CTAS_PER_SM");
+    const char *pad = getenv("MOOG_SMEM_PAD");
+    const char *cps = getenv("MOOG_CTAS_PER_SM");
     int target = cps ? atoi(cps) : resident_envs_per_sm;
     if (pad) {
       smem += (size_t)atoi(pad);
@@ -3211,6 +3260,47 @@ cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stre
       if (smem > 227 * 1024) smem = 227 * 1024;
     }
   }
+  // The frame of the state the env is left in (io.frames), drawn by the env's own CTA right after
+  // its step: the renderer reads the record where it lies in shared memory and builds its canvas
+  // where the step's scratch was.  frames_mode 2 = the caller prefers it (small batches: one
+  // launch, no second pass over the state), 1 = frames wanted but the render kernel is the better
+  // choice: measured on 4096 falling_balls20 envs, two warps per env drawing between the steps of
+  // their neighbours cost more (6.0 ms) than the render kernel behind the step (4.3 + 0.55 ms).
+  // MOOG_FUSED_RENDER=0 never fuses, =1 fuses whenever one CTA can hold a canvas.
+  plan.render_off = 0;
+  plan.fuse = false;
+  if (frames_mode > 0 && hdr[MOOG_H_R_ENABLED] && hdr[MOOG_H_R_AA] == 1) {
+    const int VTr = hdr[MOOG_H_N_VTX] > 0 ? hdr[MOOG_H_N_VTX] : 1;
+    const SmemLayout sl = smem_layout(hdr[MOOG_H_N_SLOTS], VTr, hdr[MOOG_H_N_ENVF], hdr[MOOG_H_CMASK_WORDS],
+                                      helper ? 2 : 1, helper ? DCV_TILE_MAX : DCV_TILE_MIN);
+    const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;
+    const RenderLayout rl = render_layout(hdr[MOOG_H_R_HEIGHT], hdr[MOOG_H_R_WIDTH], hdr[MOOG_H_N_SLOTS] * C, VTr * C,
+                                          hdr[MOOG_H_R_WIDTH], 16 * VTr);
+    plan.render_off = (sl.scratch + 15) & ~15;  // everything from the warps' scratch on is dead after the step
+    const size_t need = (size_t)plan.render_off + (size_t)rl.total;
+    const char *fr = getenv("MOOG_FUSED_RENDER");
+    bool want = frames_mode == 2;
+    if (fr) want = atoi(fr) != 0;
+    if (want && need <= 227 * 1024) {
+      plan.fuse = true;
+      if (smem < need) smem = need;
+    }
+  }
+  plan.smem = smem;
+  return plan;
+}
+
+cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches, int first,
+                        int count, int resident_envs_per_sm, bool helper, int frames_mode, bool *fused) {
+  if (fused) *fused = false;
+  if (count < 0) count = a.n_envs - first;
+  if (a.n_envs <= 0 || count <= 0) return cudaSuccess;
+  const StepPlan plan = plan_step(hdr, resident_envs_per_sm, helper,
+                                  a.io.frames != nullptr && a.mode == MODE_ENV_STEP ? frames_mode : 0);
+  const size_t smem = plan.smem;
+  const bool fuse = plan.fuse;
+  const int render_off = plan.render_off;
+  if (fused) *fused = fuse;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(moog_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -3228,6 +3318,9 @@ cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stre
   b.NF = hdr[MOOG_H_N_ENVF];
   b.CMW = hdr[MOOG_H_CMASK_WORDS];
   b.dcv_tile = helper ? DCV_TILE_MAX : DCV_TILE_MIN;
+  b.fused_render = fuse ? 1 : 0;
+  b.render_off = render_off;
+  b.frames = fuse ? a.io.frames : nullptr;
   moog_step_kernel<<<blocks, helper ? 64 : 32, smem, stream>>>(b);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();

@@ -529,3 +529,77 @@ def test_device_reset_sampler_mixture_and_setminus():
     assert not ((np.abs(vx) < 0.01) & (np.abs(vy) < 0.01)).any(), 'the hold-out box is empty'
     assert ((np.abs(vx) < 0.01) | (np.abs(vy) < 0.01)).mean() > 0.3      # ... but only the box, not the cross
     assert (st['meta'][:, 1, s0:s0 + 6] & 0x3f == 2).all()               # float32 velocity array
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('helper', ['1', '0'])
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_step_kernel_draws_the_same_frames_as_the_render_kernel(scene, helper, monkeypatch):
+    """`moog_env_step` with `frames`: the step kernel draws the frame of the state it leaves an
+    env in from the record in shared memory (owner + helper warp, or the owner alone).  Along
+    the golden trajectory the frames must equal what `moog_render` draws from the stored state
+    afterwards -- which the tests above pin to PILRenderer's output -- and the state must not
+    notice.  MOOG_FUSED_RENDER=1 forces the fused path wherever one CTA can hold a canvas; where
+    it cannot (big canvases, TorusGeometry's 9 copies, anti-aliasing) the call falls back to the
+    render kernel, and the frames must be the same as well."""
+    g = util.load_golden(scene)
+    prog = g['program']
+    if prog.render is None:
+        pytest.skip('scene has no renderer')
+    monkeypatch.setenv('MOOG_FUSED_RENDER', '1')
+    monkeypatch.setenv('MOOG_HELPER', helper)
+    T = min(len(g['reward']), 30)
+    n = 5
+    arrays = {k: np.concatenate([util.state_at(g, None, prefix='init')[k]] * n, axis=0) for k in util.STATE_KEYS}
+    engines = [_engine(prog, arrays), _engine(prog, arrays)]
+    for eng in engines:
+        eng.post_reset()
+    host = torch.zeros(tuple(engines[0].frames.shape), dtype=torch.uint8).pin_memory()
+    for t in range(T):
+        noise = np.repeat(g['noise'][t][None], n, axis=0) if prog.noise_dim else None
+        rn = util.rule_noise_at(g, t)
+        rn = None if rn is None else np.repeat(rn, n, axis=0)
+        act = np.repeat(g['actions'][t][None], n, axis=0)
+        # engine 0: frames by the step call, alternately into HBM and into pinned host memory
+        dst = host if t % 2 else True
+        engines[0].env_step(act, noise=noise, rule_noise=rn, auto_reset=False, frames=dst)
+        engines[1].env_step(act, noise=noise, rule_noise=rn, auto_reset=False)
+        torch.cuda.synchronize()
+        got = host.numpy() if t % 2 else engines[0].frames.cpu().numpy()
+        ref = engines[1].render().cpu().numpy()
+        assert np.array_equal(got, ref), (scene, t, int((got != ref).sum()))
+        for k in ('dyn', 'vtx', 'stat'):
+            a, b = getattr(engines[0].state, k), getattr(engines[1].state, k)
+            assert bool(((a == b) | (a.isnan() & b.isnan())).all()), (scene, t, k)
+
+
+@pytest.mark.gpu
+def test_full_size_batch_frames_from_the_step_call():
+    """The bench's launch (4096 falling_balls20 envs: 4 envs per SM, helper warp) with frames:
+    the render kernel is launched behind the step kernel with programmatic stream serialization
+    and draws the envs in the order they finish, into HBM or straight into pinned host memory;
+    the frames equal those of a render call after the step, and `step_to_host` delivers the same
+    TimeStep whichever way the frames travel.  Small batches draw inside the step kernel."""
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment, TimeStep
+    from moog_b200.configs import falling_balls20
+    cfg = falling_balls20.get_config()
+    np.random.seed(79)
+    states = [cfg['state_initializer']() for _ in range(64)]
+    N = 4096
+    envs = {m: BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=11, initial_states=states)
+            for m in ('mapped', 'device', 'chunked')}
+    assert not envs['mapped'].engine.dev_program.step_draws_frames(N)
+    assert envs['mapped'].engine.dev_program.step_draws_frames(100)
+    hosts = {m: TimeStep(torch.empty(N, dtype=torch.int32).pin_memory(), torch.empty(N, dtype=torch.float32).pin_memory(),
+                         None, {'image': torch.zeros((N, 64, 64, 3), dtype=torch.uint8).pin_memory()})
+             for m in envs}
+    act = torch.zeros((N, 1), dtype=torch.float64).pin_memory()
+    for step in range(45):
+        for m, env in envs.items():
+            env.step_to_host(act, hosts[m], frames=m)
+        if step % 11 == 0 or step == 44:
+            ref = envs['chunked'].engine.render().cpu()
+            for m in envs:
+                assert torch.equal(hosts[m].observation['image'], ref), (step, m)
+                assert torch.equal(hosts[m].step_type, hosts['chunked'].step_type), (step, m)
