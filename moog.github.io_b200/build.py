@@ -19,8 +19,9 @@ HEADERS = [os.path.join(CSRC, 'moog_common.cuh'), os.path.join(CSRC, 'moog_rende
            os.path.join(_PKG, '..', 'include', 'moog_b200.h'),
            os.path.join(_PKG, '..', 'include', 'moog_b200_program.h')]
 
+# MOOG_NVCC_OPT: optimisation flags of an experimental build (A/B runs together with MOOG_B200_LIB)
 NVCC_FLAGS = [
-    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo'] + os.environ.get('MOOG_NVCC_OPT', '-O3').split() + [
     '-std=c++17', '-fmad=false', '-prec-div=true', '-prec-sqrt=true',
     '--expt-extended-lambda', '-Xcompiler', '-fPIC,-ffp-contract=off',
     '-Wno-deprecated-gpu-targets',

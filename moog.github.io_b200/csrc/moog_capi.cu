@@ -105,7 +105,7 @@ static void launch_policy(int n_envs, bool ordered, int *resident, bool *helper)
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms > 0) {
-    *resident = (n_envs + 7 * sms / 2) / (7 * sms);
+    *resident = (2 * n_envs + 11 * sms / 2) / (11 * sms);  // n_envs / (5.5 x SMs), rounded
     if (*resident < 2) *resident = 2;
     *helper = *resident <= 6;
   }
@@ -192,9 +192,10 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   }
   // The step ends when its longest-running env does, and a warp runs ~2.4x slower next to 11
   // others than alone (profiles/README.md): with the envs dispatched longest-first, capping
-  // the envs resident per SM at about n_envs / (7 x SMs) -- seven waves -- finishes the step
-  // sooner than filling the SMs (4096 envs on 148 SMs: 4 per SM; measured 3: 4.93 ms,
-  // 4: 4.77 ms, 12: 5.6 ms with the helper warp).
+  // the envs resident per SM at about n_envs / (5.5 x SMs) finishes the step sooner than filling
+  // the SMs (4096 envs on 148 SMs: 5 per SM; measured with the frames drawn behind the step, step
+  // + render per 4096 envs: 3: 5.33 ms, 4: 4.66 ms, 5: 4.46 ms -- the most the 39 KB records of the
+  // helper mode allow -- and 5.6 ms at 12 with one warp per env).
   // In that regime the SMs have registers to spare, and every env gets a helper warp that
   // computes one of the two directions of _get_collision_vectors (MOOG_HELPER=0/1 overrides).
   int resident = 0;
