@@ -473,11 +473,12 @@ def run_ours(args):
     if not args.no_cpu:
         arm = CpuArm(args.scene, envs_per_thread=8, episode=args.episode)
         arm.stagger()
-        v, dt, n = arm.run(args.episode)     # every env walks one whole episode
+        v, dt, n = arm.run(args.episode * args.cpu_episodes)     # every env walks whole episodes
         line['cpu_baseline'] = {
             'value': v, 'unit': UNIT, 'cores': arm.threads, 'kind': 'port',
-            'sample': '{} env-steps of {} incl. render: {} threads x 8 envs x one whole {}-step episode each '
-                      '(uniform phase mix), {:.1f} s'.format(n, args.scene, arm.threads, args.episode, dt)}
+            'sample': '{} env-steps of {} incl. render: {} threads x 8 envs x {} whole {}-step episodes each '
+                      '(uniform phase mix), {:.1f} s'.format(n, args.scene, arm.threads, args.cpu_episodes,
+                                                             args.episode, dt)}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -506,6 +507,8 @@ def main():
                     help='how the e2e arm brings the frames to the host (BatchedEnvironment.step_to_host)')
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--cpu-episodes', type=int, default=6,
+                    help='whole episodes every env of the cpu_baseline leg walks (6: about 10 s on 16 threads)')
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == 'reference':

@@ -57,7 +57,9 @@ struct SmemLayout {
 /* contained vertices per pass of _directed_collision_vectors: one pass covers any outline when the
    step is bound by its longest env (few envs per SM, shared memory to spare); the small tile keeps
    the record small when the batch is large and residency is what counts */
+#ifndef DCV_TILE_MAX
 #define DCV_TILE_MAX 32
+#endif
 #define DCV_TILE_MIN 8
 #define NEAR_SKIN 0.02
 #define NEAR_CAP 512  /* near-list entries; more near pairs than this -> every pair is tested */
