@@ -395,7 +395,7 @@ def run_ours(args):
     # ---- end-to-end arm: host actions in, host TimeStep (frames included) out --
     from moog_b200.batched_env import TimeStep
     host_ts = TimeStep(host_step_type, host_reward, None, {'image': host_frames})
-    for _ in range(2):
+    for _ in range(10):   # warm-up; with --e2e-frames auto these calls also pick the frame path
         env.step_to_host(host_actions, host_ts, chunks=args.e2e_chunks, frames=args.e2e_frames)
     torch.cuda.synchronize()
     barrier()
@@ -445,7 +445,7 @@ def run_ours(args):
                               'drawn inside moog_step_kernel' if fused else
                               'render kernel launched behind the step kernel (programmatic stream serialization), '
                               'drawing the envs in finishing order while the longest envs are still stepped'),
-                   'e2e_frames': args.e2e_frames},
+                   'e2e_frames': (env._auto_choice or 'device') if args.e2e_frames == 'auto' else args.e2e_frames},
         'roofline': {'bound': 'hbm', 'kernel': 'moog_step_kernel', 'achieved': step_gbs, 'peak': peak,
                      'unit': 'GB/s', 'frac': step_gbs / peak,
                      'traffic': (_ncu_traffic('step_kernel')

@@ -105,7 +105,11 @@ static void launch_policy(int n_envs, bool ordered, int *resident, bool *helper)
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms > 0) {
-    *resident = (2 * n_envs + 11 * sms / 2) / (11 * sms);  // n_envs / (5.5 x SMs), rounded
+    *resident = (n_envs + 7 * sms / 2) / (7 * sms);  // n_envs / (7 x SMs), rounded
+    // helper-warp regime (few envs per SM): one more env per SM pays once the frames are drawn
+    // behind the step (4096 envs: 4 -> 5 per SM, 4.66 -> 4.46 ms); larger batches keep 7 waves
+    // (8192 / 32768 envs measured slower at 10 / 40 per SM than at 8 / 32)
+    if (*resident <= 4) *resident = (2 * n_envs + 11 * sms / 2) / (11 * sms);
     if (*resident < 2) *resident = 2;
     *helper = *resident <= 6;
   }
@@ -192,7 +196,7 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   }
   // The step ends when its longest-running env does, and a warp runs ~2.4x slower next to 11
   // others than alone (profiles/README.md): with the envs dispatched longest-first, capping
-  // the envs resident per SM at about n_envs / (5.5 x SMs) finishes the step sooner than filling
+  // the envs resident per SM at about n_envs / (5.5 .. 7 x SMs) finishes the step sooner than filling
   // the SMs (4096 envs on 148 SMs: 5 per SM; measured with the frames drawn behind the step, step
   // + render per 4096 envs: 3: 5.33 ms, 4: 4.66 ms, 5: 4.46 ms -- the most the 39 KB records of the
   // helper mode allow -- and 5.6 ms at 12 with one warp per env).

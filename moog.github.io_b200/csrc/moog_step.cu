@@ -3180,6 +3180,9 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
   } else {
     owner_warp(a, smem_raw, lane);
   }
+#ifdef MOOG_NO_FUSED_RENDER  // diagnostic build: the step kernel without the renderer's code
+  return;
+#else
   if (!a.fused_render) return;
   // PILRenderer.__call__ (pil_renderer.py:88-120) of the state the env was left in, by every
   // thread of the CTA, from the record that is still in shared memory: the canvas, edge lists and
@@ -3201,6 +3204,7 @@ __global__ void __launch_bounds__(64) moog_step_kernel(const StepArgs a) {
     render_env(src, lay, smem_raw + a.render_off, (unsigned *)e.vtx, (int)threadIdx.x, T, P, true,
                a.frames + (size_t)e.env_id * OH * OW * 3, nullptr, 0, 0, [] { __syncthreads(); });
   }
+#endif
 }
 
 // order[] = env indices by decreasing cost[] (bucket sort; the order inside a bucket
@@ -3283,6 +3287,9 @@ StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, in
     const char *fr = getenv("MOOG_FUSED_RENDER");
     bool want = frames_mode == 2;
     if (fr) want = atoi(fr) != 0;
+#ifdef MOOG_NO_FUSED_RENDER
+    want = false;
+#endif
     if (want && need <= 227 * 1024) {
       plan.fuse = true;
       if (smem < need) smem = need;

@@ -588,7 +588,7 @@ def test_full_size_batch_frames_from_the_step_call():
     states = [cfg['state_initializer']() for _ in range(64)]
     N = 4096
     envs = {m: BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=11, initial_states=states)
-            for m in ('mapped', 'device', 'chunked')}
+            for m in ('mapped', 'device', 'chunked', 'auto')}
     assert not envs['mapped'].engine.dev_program.step_draws_frames(N)
     assert envs['mapped'].engine.dev_program.step_draws_frames(100)
     hosts = {m: TimeStep(torch.empty(N, dtype=torch.int32).pin_memory(), torch.empty(N, dtype=torch.float32).pin_memory(),
@@ -603,3 +603,5 @@ def test_full_size_batch_frames_from_the_step_call():
             for m in envs:
                 assert torch.equal(hosts[m].observation['image'], ref), (step, m)
                 assert torch.equal(hosts[m].step_type, hosts['chunked'].step_type), (step, m)
+    # 'auto' timed both transports during its first calls and kept one
+    assert envs['auto']._auto_choice in ('mapped', 'chunked')
