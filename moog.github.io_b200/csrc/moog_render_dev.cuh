@@ -360,10 +360,20 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
                             stat[MOOG_S_OPACITY * S + s]);
   }
   sync();
+  // Draw order = layer order, then list order inside a layer (environment.py:20-25), which is
+  // slot order over the LIVE slots (layer l owns the slots [LAYER_OFF[l], LAYER_OFF[l] + cnt[l])).
+  // A slot that is not live or has no outline gets an empty row range, so that everything below
+  // can walk the slots 0 .. S*C-1 without looking at layers again.
   if (live) {
     for (int vs = t; vs < S * C; vs += T) {
       const int s = vs / C, vo = (vs - s * C) * VT + src.voff[s];
       int nv = meta[MOOG_M_NV * S + s];
+      bool drawn = false;
+      for (int l = 0; l < L; ++l) {
+        const int first = hdr[MOOG_H_LAYER_OFF + l];
+        drawn = drawn || (s >= first && s < first + cnt[l]);
+      }
+      if (!drawn) nv = 0;
       const int2 *xy = ivtx + vo;
       int lo = 0x7fffffff, hi = -0x7fffffff, hz = 0;
       for (int i = 0; i < nv; ++i) {
@@ -374,28 +384,46 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
       symin[vs] = lo; symax[vs] = hi; shoriz[vs] = hz;
     }
   }
-  sync();  // thread 0 reads every slot's extents
-  // z-order list of the live sprites and the (sprite, row) item ranges
-  if (live && t == 0) {
+  sync();  // the scan below reads every slot's extents
+  // (sprite, row) item ranges: exclusive prefix sum of the visible rows per slot by the first
+  // warp; when the items do not all fit (lay.cap) thread 0 assigns them greedily instead and
+  // the sprites left without a range are scan-converted by the row threads directly
+  if (live && t < 32) {
     int acc = 0;
-    for (int s = 0; s < S * C; ++s) sibase[s] = -1;
-    for (int l = 0; l < L; ++l) {
-      int c = cnt[l];
-      for (int k = 0; k < c; ++k) {
-        int s0 = hdr[MOOG_H_LAYER_OFF + l] + k;
-        if (meta[MOOG_M_NV * S + s0] <= 0) continue;
-        for (int s = s0 * C; s < (s0 + 1) * C; ++s) {
-          // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
-          int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
-          int rows = hi >= lo ? hi - lo + 1 : 0;
+    for (int b = 0; b < S * C; b += 32) {
+      const int vs = b + t;
+      int rows = 0;
+      if (vs < S * C) {
+        // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
+        const int lo = max(symin[vs], 0), hi = min(symax[vs], H - 1);
+        rows = hi >= lo ? hi - lo + 1 : 0;
+      }
+      int x = rows;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (t >= d) x += y;
+      }
+      if (vs < S * C) sibase[vs] = rows > 0 ? acc + x - rows : -1;
+      acc += __shfl_sync(0xffffffffu, x, 31);
+    }
+    __syncwarp();
+    if (t == 0) {
+      if (acc > lay.cap) {
+        acc = 0;
+        for (int s = 0; s < S * C; ++s) {
+          const int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
+          const int rows = hi >= lo ? hi - lo + 1 : 0;
           if (rows > 0 && acc + rows <= lay.cap) {
             sibase[s] = acc;
             acc += rows;
+          } else {
+            sibase[s] = -1;
           }
         }
       }
+      sibase[S * C] = acc;
     }
-    sibase[S * C] = acc;
   }
   sync();
   // phase 1: one (sprite, row) item per thread pass -> clipped spans
@@ -429,42 +457,36 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
       const int part = w / H, y = w - part * H;
       const int xlo = (W * part) / P, xhi = (W * (part + 1)) / P - 1;  // P threads share a row
       unsigned *row = canvas + y * stride;
-      for (int l = 0; l < L; ++l) {
-        int c = cnt[l];
-        for (int k = 0; k < c; ++k) {
-          const int s0 = hdr[MOOG_H_LAYER_OFF + l] + k;
-          if (meta[MOOG_M_NV * S + s0] <= 0) continue;
-          const unsigned color = ink[s0];
-          for (int s = s0 * C; s < (s0 + 1) * C; ++s) {
-            int ymin_c = max(symin[s], 0), ymax_c = min(symax[s], H);
-            if (y < ymin_c || y > ymax_c) continue;
-            const int b0 = sibase[s];
-            unsigned cntw = ITEM_OVERFLOW;
-            const unsigned *item = nullptr;
-            if (b0 >= 0) {
-              item = items + (size_t)(b0 + (y - ymin_c)) * (1 + ITEM_SPANS);
-              cntw = item[0];
-            }
-            if (cntw != ITEM_OVERFLOW) {
-              for (unsigned q = 0; q < cntw; ++q) {
-                unsigned sp = item[1 + q];
-                int x0 = max((int)(sp & 0xffffu), xlo), x1 = min((int)(sp >> 16), xhi);
-                if ((color >> 24) == 255u) {  // DIV255(fg * 255) == fg: opaque ink overwrites
-                  for (int x = x0; x <= x1; ++x) row[x] = color & 0xffffffu;
-                } else {
-                  for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], color);
-                }
-              }
+      for (int s = 0; s < S * C; ++s) {
+        const int ymin_c = max(symin[s], 0), ymax_c = min(symax[s], H);
+        if (y < ymin_c || y > ymax_c) continue;
+        const int s0 = C == 1 ? s : s / C;
+        const unsigned color = ink[s0];
+        const int b0 = sibase[s];
+        unsigned cntw = ITEM_OVERFLOW;
+        const unsigned *item = nullptr;
+        if (b0 >= 0) {
+          item = items + (size_t)(b0 + (y - ymin_c)) * (1 + ITEM_SPANS);
+          cntw = item[0];
+        }
+        if (cntw != ITEM_OVERFLOW) {
+          for (unsigned q = 0; q < cntw; ++q) {
+            unsigned sp = item[1 + q];
+            int x0 = max((int)(sp & 0xffffu), xlo), x1 = min((int)(sp >> 16), xhi);
+            if ((color >> 24) == 255u) {  // DIV255(fg * 255) == fg: opaque ink overwrites
+              for (int x = x0; x <= x1; ++x) row[x] = color & 0xffffffu;
             } else {
-              BlendSink sink;
-              sink.row = row;
-              sink.W = W;
-              sink.ink = color;
-              sink.xlo = xlo;
-              sink.xhi = xhi;
-              polygon_row_rec(erec + (s - s0 * C) * VT + src.voff[s0], snedge[s], y, ymax_c, shoriz[s] != 0, sink);
+              for (int x = x0; x <= x1; ++x) row[x] = blend_px(row[x], color);
             }
           }
+        } else {
+          BlendSink sink;
+          sink.row = row;
+          sink.W = W;
+          sink.ink = color;
+          sink.xlo = xlo;
+          sink.xhi = xhi;
+          polygon_row_rec(erec + (s - s0 * C) * VT + src.voff[s0], snedge[s], y, ymax_c, shoriz[s] != 0, sink);
         }
       }
     }
