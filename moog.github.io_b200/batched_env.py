@@ -19,6 +19,7 @@ PyTorch is used for device memory and streams only.  All arithmetic happens in
 libmoog_b200.so (include/moog_b200.h); there is no fallback path.
 """
 import collections
+import contextlib
 import ctypes
 import time
 
@@ -95,6 +96,14 @@ class DeviceState(object):
 
     def struct(self, first=0):
         """`moog_state` of the envs [first, n): the row pointers of env `first`."""
+        if first == 0:
+            # the tensors are allocated once and only ever written in place
+            key = tuple(getattr(self, k).data_ptr() for k in self.KEYS)
+            cached = getattr(self, '_struct0', None)
+            if cached is None or cached[0] != key:
+                cached = (key, capi.MoogState(*key))
+                self._struct0 = cached
+            return cached[1]
         ptrs = []
         for k in self.KEYS:
             t = getattr(self, k)
@@ -103,6 +112,9 @@ class DeviceState(object):
 
     def nbytes(self):
         return sum(getattr(self, k).numel() * getattr(self, k).element_size() for k in self.KEYS)
+
+
+_NULL_CONTEXT = contextlib.nullcontext()
 
 
 def _ptr(t):
@@ -138,8 +150,16 @@ class Engine(object):
             self.frames = torch.zeros((self.n, r['height'], r['width'], 3),
                                       dtype=torch.uint8, device=self.device)
         self._calls = 0
+        self._pinned_ok = set()
 
     # -- helpers -----------------------------------------------------------
+    def _on_device(self):
+        """Context that makes this engine's GPU current (free when it already is)."""
+        index = self.device.index
+        if index is None or torch.cuda.current_device() == index:
+            return _NULL_CONTEXT
+        return torch.cuda.device(self.device)
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -182,8 +202,10 @@ class Engine(object):
                 raise ValueError('frames must be a contiguous uint8 tensor of shape {}'.format(
                     tuple(self.frames.shape)))
             if frames.device.type == 'cpu':
-                if not frames.is_pinned():
-                    raise ValueError('host frames must live in pinned memory')
+                if frames.data_ptr() not in self._pinned_ok:
+                    if not frames.is_pinned():
+                        raise ValueError('host frames must live in pinned memory')
+                    self._pinned_ok.add(frames.data_ptr())
             elif frames.device != self.state.dyn.device:
                 raise ValueError('frames are on {}, the envs on {}'.format(frames.device, self.state.dyn.device))
         act = self._as_f64(actions, max(p.action_dim, 1)) if actions is not None else None
@@ -208,7 +230,7 @@ class Engine(object):
         io.stats = _ptr(self.stats)
         io.frames = _ptr(frames)
         st = self.state.struct()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             capi.check(capi.lib().moog_env_step(
                 self.dev_program.handle, ctypes.byref(st), self.n, ctypes.byref(io), self._stream()))
         self._calls += 1
