@@ -2091,6 +2091,31 @@ __device__ inline void integrate_all(const Env &e) {
     // phase 2: one moved slot at a time, lane = vertex of its outline
     unsigned mv = __ballot_sync(FULL, flag != 0);
     const unsigned rot = __ballot_sync(FULL, (flag & TF_ROT) != 0);
+#ifndef MOOG_NO_SIMPLE_MOVE
+    {
+      // slots that only translate (the common case): the outline's size and address come by
+      // shuffle from the lane that owns the slot, and the loop body has no rotation in it
+      const int my_n = s < e.S ? META(e, MOOG_M_NV, s) : 0;
+      const int my_vo = s < e.S ? e.voff[s] : 0;
+      unsigned simple = mv & ~rot;
+      mv &= rot;
+#pragma unroll 1
+      while (simple) {
+        const int src = __ffs(simple) - 1;
+        simple &= simple - 1;
+        const int n = __shfl_sync(FULL, my_n, src);
+        double2 *v = e.vtx + __shfl_sync(FULL, my_vo, src);
+        const double ttx = shfl_d(tx, src), tty = shfl_d(ty, src);
+        if (e.lane < n) {
+          const double2 p = v[e.lane];
+          // Affine2D().translate(tx, ty): 1.0 * x is exact, the 0.0 * y term keeps the
+          // reference's NaN / signed-zero behaviour
+          v[e.lane] = make_double2((p.x + 0.0 * p.y) + ttx, (0.0 * p.x + p.y) + tty);
+        }
+        if (n > 32) outline_tail(v, n, e.lane, ttx, tty, false, 1, 0, 0, 0, 1, 0);
+      }
+    }
+#endif
     while (mv) {
       const int src = __ffs(mv) - 1;
       mv &= mv - 1;

@@ -605,3 +605,46 @@ def test_full_size_batch_frames_from_the_step_call():
                 assert torch.equal(hosts[m].step_type, hosts['chunked'].step_type), (step, m)
     # 'auto' timed both transports during its first calls and kept one
     assert envs['auto']._auto_choice in ('mapped', 'chunked')
+
+
+@pytest.mark.gpu
+def test_frames_edge_cases():
+    """Edge cases of the frames path: an empty batch, wrong frame buffers, an env whose layers
+    are all empty (only the background is drawn), and one env next to 4095 others."""
+    import ctypes
+    from moog_b200 import capi
+    g = util.load_golden('falling_balls20')
+    prog = g['program']
+    arrays = util.state_at(g, None, prefix='init')
+    eng = _engine(prog, arrays)
+    eng.post_reset()
+    # n_envs = 0: every entry point accepts it and launches nothing
+    st = eng.state.struct()
+    io = capi.MoogStepIO()
+    io.frames = ctypes.c_void_p(eng.frames.data_ptr())
+    before = capi.launch_count()
+    capi.check(capi.lib().moog_env_step(eng.dev_program.handle, ctypes.byref(st), 0, ctypes.byref(io), None))
+    capi.check(capi.lib().moog_render(eng.dev_program.handle, ctypes.byref(st), 0,
+                                      ctypes.c_void_p(eng.frames.data_ptr()), None))
+    assert capi.launch_count() == before
+    # wrong buffers are refused on the host
+    with pytest.raises(ValueError):
+        eng.env_step(None, frames=torch.zeros((1, 64, 64, 4), dtype=torch.uint8, device='cuda:0'))
+    with pytest.raises(ValueError):
+        eng.env_step(None, frames=torch.zeros((1, 64, 64, 3), dtype=torch.uint8))      # pageable host memory
+    # an env without a single live sprite: background only, through every frame path
+    empty = {k: v.copy() for k, v in arrays.items()}
+    empty['cnt'][:] = 0
+    for n in (1, 4096):
+        big = {k: np.repeat(v, n, axis=0) for k, v in (empty if n == 1 else arrays).items()}
+        if n > 1:
+            big['cnt'][17] = 0
+        e2 = _engine(prog, big)
+        e2.post_reset()
+        e2.env_step(None, auto_reset=False, frames=True)
+        torch.cuda.synchronize()
+        ref = e2.render(out=torch.zeros_like(e2.frames)).cpu().numpy()
+        got = e2.frames.cpu().numpy()
+        assert np.array_equal(got, ref), n
+        bg = got[0 if n == 1 else 17]
+        assert (bg == bg[0, 0]).all(), 'an env without sprites shows the background colour only'
