@@ -712,8 +712,11 @@ __device__ inline bool overlaps(const Env &e, int a, int b) {
 // and d == 0 gives +-inf or NaN, false either way.  `exact` is false when the operands are
 // outside that regime; the caller then divides.
 __device__ __forceinline__ bool unit_ratio(double n, double d, bool &exact) {
-  const double an = fabs(n), ad = fabs(d);
-  exact = (an == 0.0 || (an >= 1e-290 && an <= 1e290)) && ad <= 1e10 && (ad >= 1e-290 || ad == 0.0);
+  // the regime test on the exponent fields (high words): |n| in [2^-959, 2^961) or n == 0, and
+  // |d| in [2^-959, 2^33) or d == 0 -- inside [1e-290, 1e290] and [1e-290, 1e10]; NaN / inf fail
+  const unsigned hn = (unsigned)__double2hiint(n) & 0x7fffffffu, hd = (unsigned)__double2hiint(d) & 0x7fffffffu;
+  exact = ((hn - (64u << 20)) < ((1984u - 64u) << 20) || n == 0.0) &&
+          ((hd - (64u << 20)) < ((1056u - 64u) << 20) || d == 0.0);
   return d > 0.0 ? (n >= 0.0 && n <= d) : (d < 0.0 && n <= 0.0 && n >= d);
 }
 
@@ -1304,7 +1307,13 @@ __device__ __forceinline__ bool pair_candidate(const Env &e, int a, int b, bool 
       const int fl = e.sflag[a] | e.sflag[b];
       double dx = DYN(e, MOOG_D_X, a) - DYN(e, MOOG_D_X, b);
       double dy = DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, b);
-      c = !(fl & SLF_ALLNAN) && !(norm1(dx, dy) > STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b));
+      // sprite.py:464-466 returns False when |centre distance| > r_a + r_b.  A candidate only has
+      // to cover every pair for which that test could fail, so the square root is skipped: the
+      // pair is dropped when the squared distance exceeds (r_a + r_b)^2 by more than any rounding
+      // of either side (1e-9 relative); NaN compares false and stays a candidate, and overlaps()
+      // repeats the reference's own test on whatever is left
+      const double rr = STAT(e, MOOG_S_MAXR, a) + STAT(e, MOOG_S_MAXR, b);
+      c = !(fl & SLF_ALLNAN) && !(dx * dx + dy * dy > rr * rr * (1.0 + 1e-9) && rr >= 0.0);
     }
   }
   return c;
