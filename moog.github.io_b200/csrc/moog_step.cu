@@ -1436,6 +1436,38 @@ __device__ inline void refresh_candidates(const Env &e, int n_cmask_words) {
   wsync();
 }
 
+// The same after a resolved contact, which moved s0 (moved & 1) and / or s1 (moved & 2) and
+// nothing else: only their boxes can have drifted past the near list's allowance, and only the
+// listed pairs they are part of can have changed their bit.
+__device__ inline void refresh_candidates_moved(const Env &e, int n_cmask_words, int s0, int s1, int moved) {
+  wsync();
+  const int ma = (moved & 1) ? s0 : s1, mb = (moved & 2) ? s1 : ma;
+  bool bad = false;
+  if (e.lane < 8) {
+    const int i = 4 * (e.lane < 4 ? ma : mb) + (e.lane & 3);
+    const double b1 = e.aabb[i], b0 = (double)e.aabb0[i];
+    bad = !(fabs(b1 - b0) < (double)e.nskin[i >> 2] - (1.2e-7 * fabs(b0) + 1e-9)) && !(b1 == b0);
+  }
+  const int n_near = (int)e.ctr[CT_NEAR];
+  if (__any_sync(FULL, bad) || n_near < 0) {  // rebuild the list / no list: the general path
+    refresh_candidates(e, n_cmask_words);
+    return;
+  }
+#pragma unroll 1
+  for (int base = 0; base < n_near; base += 32) {
+    const int k = base + e.lane;
+    const unsigned ent = e.nearp[k < n_near ? k : 0];
+    const int a = (int)(ent & 255u), b = (int)((ent >> 8) & 255u);
+    const bool inv = k < n_near && (a == ma || a == mb || b == ma || b == mb);
+    const bool c = pair_candidate(e, a, b, inv);
+    if (inv) {
+      const unsigned bit = 1u << ((ent >> 16) & 31u);
+      if (c) atomicOr(&e.cmask[ent >> 21], bit); else atomicAnd(&e.cmask[ent >> 21], ~bit);
+    }
+  }
+  wsync();
+}
+
 // One Collision entry (physics.py:92-108 for a Collision force): the candidate
 // pairs of its matrix in row-major order = itertools.product order.
 __device__ inline void collision_op(const Env &e, const moog_op *op, int f, int n_cmask_words) {
@@ -1467,7 +1499,11 @@ __device__ inline void collision_op(const Env &e, const moog_op *op, int f, int 
         ctr_add(e, CT_CALLS, -1);  // collision_step counts this pair's first call itself
         int moved = collision_step(e, op, s0, s1, true);
         if (moved) {
+#ifdef MOOG_FULL_REFRESH  // diagnostic build: every listed pair re-evaluated after a contact
           refresh_candidates(e, n_cmask_words);
+#else
+          refresh_candidates_moved(e, n_cmask_words, s0, s1, moved);
+#endif
           // continue after (i, w, l) with the refreshed matrix
           m = M[wi] & ~((2u << l) - 1u);
           nz = __ballot_sync(FULL, widx < nwords && M[widx] != 0u) & ~((2u << t) - 1u);
