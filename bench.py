@@ -119,12 +119,13 @@ class ClockSampler(object):
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -134,6 +135,10 @@ class ClockSampler(object):
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """Samples from here on (and the one just before, taken under the same load) count."""
+        self.first = max(len(self.lines) - 1, 0)
 
     def stop(self):
         if self.proc is None:
@@ -145,7 +150,7 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 6:
                 continue
@@ -342,14 +347,25 @@ def run_ours(args):
         if args.render != 'auto':
             eng.render()
 
+    # nvidia-smi needs a moment to deliver its first line: the sampler starts before the warm-up,
+    # the warm-up goes on (bounded) until a sample taken under this load has arrived, and the
+    # samples from that one on are the ones reported
+    sampler = ClockSampler(local_rank)
+    if not args.no_clocks:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         device_step()
         device_render()
     torch.cuda.synchronize()
+    if not args.no_clocks and sampler.proc is not None:
+        t_wait = time.perf_counter()
+        n_before = len(sampler.lines)
+        while len(sampler.lines) < n_before + 2 and time.perf_counter() - t_wait < 3.0:
+            device_step()
+            device_render()
+            torch.cuda.synchronize()
+        sampler.mark()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if not args.no_clocks:
-        sampler.start()
     launches0 = capi.launch_count()
     barrier()
     torch.cuda.synchronize()
