@@ -410,3 +410,28 @@ def test_vector_valued_and_boolean_lambdas_lower_to_expressions():
     assert run(code, dict(c2=0.7, mass=2.)) == 1.0 and run(code, dict(c2=0.7, mass=1.)) == 0.0
     with pytest.raises(L.LoweringError):
         L.compile_sprite_predicate(lambda s: 1. if s.c0 < 128 else -1.)   # a Python branch on a sprite value
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port on the host cores, the one place besides the tests
+    where bench.py executes oracle/) prints exactly one JSON line with the keys the driver reads;
+    under torchrun every rank but 0 exits without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'env-steps/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1
+    assert d['config']['workload'] == 'falling_balls20'
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value'] == d['e2e']['value']
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ''
