@@ -67,6 +67,11 @@ class AbstractDistribution(abc.ABC):
     def __str__(self):
         return self.to_str(indent=0)
 
+    def _get_rng(self, rng=None):
+        """np.random unless a generator is given (user subclasses call this, e.g. red_green.py's
+        RadialVelocity; reference distributions.py:69-71)."""
+        return np.random if rng is None else rng
+
 
 class Continuous(AbstractDistribution):
     """Uniform on [minval, maxval); float32 by default, like the reference."""
