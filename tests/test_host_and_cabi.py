@@ -435,3 +435,37 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ''
+
+
+def test_step_to_host_auto_policy_keeps_the_faster_transport():
+    """Host logic of `step_to_host(frames='auto')` (no GPU needed): the first calls alternate
+    between the mapped host image and chunked copies, the first call of each is a warm-up, and
+    the transport with the smaller best time is kept; pageable host images always use 'device'."""
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment
+
+    class Img(object):
+        def __init__(self, pinned):
+            self._p = pinned
+
+        def is_pinned(self):
+            return self._p
+
+    def fresh():
+        env = object.__new__(BatchedEnvironment)
+        env._auto_choice, env._auto_calls = None, 0
+        env._auto_times = {'mapped': [], 'chunked': []}
+        return env
+
+    for cost, winner in (({'mapped': 5.0, 'chunked': 5.5}, 'mapped'), ({'mapped': 16.6, 'chunked': 11.0}, 'chunked')):
+        env = fresh()
+        seen = []
+        for call in range(12):
+            mode = env._auto_frames(Img(True))
+            seen.append(mode)
+            # the very first call of each transport is slow (allocations, first launches)
+            env._auto_record(mode, cost[mode] * (10.0 if call < 2 else 1.0))
+        assert seen[:8] == ['mapped', 'chunked'] * 4
+        assert env._auto_choice == winner and seen[8:] == [winner] * 4
+    assert fresh()._auto_frames(Img(False)) == 'device'
+    assert fresh()._auto_frames(None) == 'device'
