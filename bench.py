@@ -466,7 +466,9 @@ def run_ours(args):
                      'unit': 'GB/s', 'frac': step_gbs / peak,
                      'traffic': (_ncu_traffic('step_kernel')
                                  if args.scene == 'falling_balls20' and E == 4096 else None),
-                     'traffic_note': 'bytes per launch, ncu --set full of this workload (profiles/)',
+                     'traffic_note': ('bytes per launch, ncu --set full of this workload (profiles/): one read of the '
+                                      '13.4 KB env records (9.9 KB of each is the cached world vertices, state that the '
+                                      'algorithmic figure does not count) + the written-back part that left L2; no re-reads'),
                      'algorithmic_bytes_per_launch': E * step_bytes,
                      'peak_source': peak_src,
                      'algorithmic_bytes_per_env_step': step_bytes, 'kernel_ms': step_ms,
