@@ -324,6 +324,29 @@ void orc_set_overlap_log(uint8_t *buf, int64_t cap) {
 }
 int64_t orc_overlap_log_len(void) { return g_log_len; }
 
+/* Row-order experiment (test infrastructure for the next kernel design, see collision_op_rows
+ * below): while a row of a Collision entry is processed out of order, the True events of its
+ * overlaps() calls are logged per row instead of being folded into the order-sensitive hash. */
+static int g_row_mode = 0, g_row_cur = -1;
+static int64_t g_row_stats[4]; /* entries handled, rows, waves, sprites that outran the margin */
+typedef struct { int n, cap; int *ab; } row_log_t;
+static row_log_t *g_row_logs = NULL;
+static void row_log_event(int row, int a, int b) {
+  row_log_t *L = &g_row_logs[row];
+  if (L->n == L->cap) {
+    L->cap = L->cap ? 2 * L->cap : 16;
+    L->ab = (int *)realloc(L->ab, sizeof(int) * 2 * (size_t)L->cap);
+  }
+  L->ab[2 * L->n] = a;
+  L->ab[2 * L->n + 1] = b;
+  L->n++;
+}
+void orc_set_row_mode(int mode) {
+  g_row_mode = mode;
+  memset(g_row_stats, 0, sizeof(g_row_stats));
+}
+void orc_row_stats(int64_t out[4]) { memcpy(out, g_row_stats, sizeof(g_row_stats)); }
+
 /* sprite.py:462-484 Sprite.overlaps_sprite */
 static int overlaps(env_t *e, int a, int b) {
   int r = 0;
@@ -344,9 +367,13 @@ static int overlaps(env_t *e, int a, int b) {
     g_log[g_log_len + 2] = (uint8_t)r;
   }
   g_log_len += 3;
-  if (r) /* order-sensitive hash of the True events only (cheap enough to keep on the device) */
-    e->overlap_hash = (e->overlap_hash ^ (uint64_t)((a * 1315423911u) ^ (b * 2654435761u) ^ 1u)) *
-                      1099511628211ull;
+  if (r) { /* order-sensitive hash of the True events only (cheap enough to keep on the device) */
+    if (g_row_cur >= 0)
+      row_log_event(g_row_cur, a, b); /* rows run out of order: folded in row order afterwards */
+    else
+      e->overlap_hash = (e->overlap_hash ^ (uint64_t)((a * 1315423911u) ^ (b * 2654435761u) ^ 1u)) *
+                        1099511628211ull;
+  }
   return r;
 }
 
@@ -1224,6 +1251,101 @@ static void corrective(env_t *e, const moog_op *op) {
   }
 }
 
+/* Row-order experiment: do the rows of one Collision entry commute the way the next kernel
+ * design assumes ("Next" (1))?  The reference visits the pairs (i, j) of an entry in
+ * itertools.product order (physics.py:92-108).  A visit can only act when the circle test of
+ * sprite.py:464-466 passes, it reads both sprites and writes sprite_0 (and sprite_1 when the
+ * entry is symmetric).  With near(i) = the sprites of layer 1 within reach of row i's sprite plus
+ * a margin for what contacts may move them during this entry, row k may run before / next to an
+ * earlier row i when
+ *     asymmetric entry:  s0(k) not in near(i)  and  s0(i) not in near(k)
+ *     symmetric entry:   ({s0(i)} + near(i)) and ({s0(k)} + near(k)) are disjoint.
+ * This function executes the entry in waves: a wave holds every remaining row without an earlier
+ * remaining row in conflict, and the rows of a wave are processed in REVERSE order.  If the rule
+ * holds the state after the entry is bit-identical to the reference order (the golden tests run
+ * in this mode too); the order-sensitive hash is folded from the per-row logs in row order.
+ * The margin of a sprite is a fixed allowance plus twice the way it travels per substep;
+ * g_row_stats[3] counts sprites that moved further than that during one entry (a kernel would
+ * have to fall back to the reference order for such an entry). */
+#define ORC_ROW_MARGIN 0.02
+static void collision_op_rows(env_t *e, const moog_op *op) {
+  const int la = op->i[0], lb = op->i[1];
+  const int na = e->cnt[la], nb = e->cnt[lb], sa = LOFF(e, la), sb = LOFF(e, lb), S = e->S;
+  const int symmetric = (op->flags & MOOG_FL_SYMMETRIC) != 0;
+  if (na <= 1) {
+    for (int i = 0; i < na; ++i)
+      for (int j = 0; j < nb; ++j) collision_step(e, op, sa + i, sb + j, 0);
+    return;
+  }
+  uint8_t *near = (uint8_t *)calloc((size_t)na * (size_t)S, 1); /* near[i][slot] incl. the row's own sprite */
+  uint8_t *done = (uint8_t *)calloc((size_t)na, 1);
+  int *wave = (int *)malloc(sizeof(int) * (size_t)na);
+  double *p0 = (double *)malloc(sizeof(double) * 3 * (size_t)S); /* position and margin at entry start */
+  for (int s = 0; s < S; ++s) {
+    p0[3 * s] = DYN(e, MOOG_D_X, s);
+    p0[3 * s + 1] = DYN(e, MOOG_D_Y, s);
+    /* what a contact may move a sprite: a fixed allowance plus twice the way it travels per substep */
+    const double v = norm1(DYN(e, MOOG_D_VX, s), DYN(e, MOOG_D_VY, s));
+    p0[3 * s + 2] = ORC_ROW_MARGIN + (isfinite(v) ? 2.0 * v / (double)e->K : INFINITY);
+  }
+  for (int i = 0; i < na; ++i) {
+    const int s0 = sa + i;
+    near[(size_t)i * S + s0] = 1;
+    for (int j = 0; j < nb; ++j) {
+      const int s1 = sb + j;
+      if (s1 == s0) continue;
+      const double d = norm1(DYN(e, MOOG_D_X, s0) - DYN(e, MOOG_D_X, s1), DYN(e, MOOG_D_Y, s0) - DYN(e, MOOG_D_Y, s1));
+      /* NaN compares false: a sprite without a position is near everything */
+      if (!(d > STAT(e, MOOG_S_MAXR, s0) + STAT(e, MOOG_S_MAXR, s1) + p0[3 * s0 + 2] + p0[3 * s1 + 2]))
+        near[(size_t)i * S + s1] = 1;
+    }
+  }
+  g_row_logs = (row_log_t *)calloc((size_t)na, sizeof(row_log_t));
+  int remaining = na;
+  while (remaining > 0) {
+    int nw = 0;
+    for (int k = 0; k < na; ++k) {
+      if (done[k]) continue;
+      int ok = 1;
+      for (int i = 0; i < k && ok; ++i) {
+        if (done[i]) continue;
+        const uint8_t *ni = near + (size_t)i * S, *nk = near + (size_t)k * S;
+        if (symmetric) {
+          for (int s = 0; s < S && ok; ++s) ok = !(ni[s] && nk[s]);
+        } else {
+          ok = !(ni[sa + k] || nk[sa + i]);
+        }
+      }
+      if (ok) wave[nw++] = k;
+    }
+    for (int w = nw - 1; w >= 0; --w) { /* any order inside a wave must do: take the reverse one */
+      const int i = wave[w];
+      g_row_cur = i;
+      for (int j = 0; j < nb; ++j) collision_step(e, op, sa + i, sb + j, 0);
+      g_row_cur = -1;
+    }
+    for (int w = 0; w < nw; ++w) done[wave[w]] = 1;
+    remaining -= nw;
+    g_row_stats[2]++;
+  }
+  for (int i = 0; i < na; ++i) { /* the hash as the reference order would have folded it */
+    for (int q = 0; q < g_row_logs[i].n; ++q) {
+      const int a = g_row_logs[i].ab[2 * q], b = g_row_logs[i].ab[2 * q + 1];
+      e->overlap_hash = (e->overlap_hash ^ (uint64_t)((a * 1315423911u) ^ (b * 2654435761u) ^ 1u)) * 1099511628211ull;
+    }
+    free(g_row_logs[i].ab);
+  }
+  free(g_row_logs);
+  g_row_logs = NULL;
+  for (int s = 0; s < S; ++s) {
+    const double d = norm1(DYN(e, MOOG_D_X, s) - p0[3 * s], DYN(e, MOOG_D_Y, s) - p0[3 * s + 1]);
+    if (d > p0[3 * s + 2]) g_row_stats[3]++;
+  }
+  g_row_stats[0]++;
+  g_row_stats[1] += na;
+  free(near); free(done); free(wave); free(p0);
+}
+
 /* physics.py:88-117 Physics.apply_physics (one substep) */
 static void apply_physics(env_t *e) {
   const int32_t *h = e->hdr;
@@ -1234,6 +1356,8 @@ static void apply_physics(env_t *e) {
       for (int i = 0; i < e->cnt[la]; ++i) maze_walk_sprite(e, op, LOFF(e, la) + i, i);
     } else if (lb < 0) {
       for (int i = 0; i < e->cnt[la]; ++i) force_unary(e, op, LOFF(e, la) + i, i);
+    } else if (op->kind == MOOG_F_COLLISION && g_row_mode) {
+      collision_op_rows(e, op);
     } else {
       for (int i = 0; i < e->cnt[la]; ++i)
         for (int j = 0; j < e->cnt[lb]; ++j) {

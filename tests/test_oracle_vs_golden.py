@@ -66,3 +66,34 @@ def test_oracle_render_matches_reference_antialiased_frames(scene, aa):
     for f, t in zip(ga['frames_aa%d' % aa], ga['frame_steps']):
         out = Oracle(prog, util.state_at(g, int(t))).render()[0]
         assert np.array_equal(out, f), (scene, aa, int(t), int((out != f).sum()))
+
+
+@pytest.mark.parametrize('scene', util.SCENES)
+def test_rows_of_a_collision_entry_commute(scene):
+    """The rule the next kernel design rests on ("Next" (1)), checked on the reference's
+    own trajectories: with the oracle's row-order mode on, every Collision entry is executed in
+    waves of mutually independent rows, each wave in REVERSE row order (oracle/moog_oracle.c
+    `collision_op_rows`).  State, rewards and the overlap statistics -- the order-sensitive hash of
+    the True pairs is folded from per-row logs in row order -- must still equal the golden
+    trajectory bit for bit, and no sprite may outrun the margin the independence test allows."""
+    import ctypes
+    from oracle import oracle as orc_mod
+    L = orc_mod.lib()
+    L.orc_set_row_mode.argtypes = [ctypes.c_int]
+    L.orc_row_stats.argtypes = [ctypes.c_void_p]
+    L.orc_set_row_mode(1)
+    try:
+        test_oracle_follows_reference_trajectory(scene)
+        stats = (ctypes.c_int64 * 4)()
+        L.orc_row_stats(stats)
+    finally:
+        L.orc_set_row_mode(0)
+    entries, rows, waves, outran = list(stats)
+    if entries:
+        # the schedule is not the sequential one (fewer waves than rows), and entries in which a
+        # sprite outran its margin -- where a kernel would fall back to the reference order --
+        # are the exception
+        assert waves <= rows, (scene, entries, rows, waves)
+        assert outran <= 0.05 * entries, (scene, entries, outran)
+        print('%s: %d entries with several rows, %.2f rows per wave, %d sprites outran their margin' % (
+            scene, entries, rows / waves, outran))
