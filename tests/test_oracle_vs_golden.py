@@ -97,3 +97,42 @@ def test_rows_of_a_collision_entry_commute(scene):
         assert outran <= 0.05 * entries, (scene, entries, outran)
         print('%s: %d entries with several rows, %.2f rows per wave, %d sprites outran their margin' % (
             scene, entries, rows / waves, outran))
+
+
+def test_rows_commute_in_heavy_piles():
+    """The same rule where it matters most: whole 100-step episodes of falling_balls20 (first
+    impacts of 20 balls, settled piles with up to a few hundred overlapping pairs per env-step --
+    far more than the golden trajectory reaches) stepped by the oracle in the reference's order
+    and in the row-order mode from identical initial states must agree bit for bit after every
+    step, overlap statistics and the order-sensitive pair hash included."""
+    import ctypes
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from moog_b200.configs import falling_balls20
+    from oracle import oracle as orc_mod
+    cfg = falling_balls20.get_config()
+    np.random.seed(5)
+    states = [cfg['state_initializer']() for _ in range(6)]
+    prog = compiler.compile_config(cfg, states)
+    arrays = compiler.pack_states(prog, states)
+    L = orc_mod.lib()
+    L.orc_set_row_mode.argtypes = [ctypes.c_int]
+    L.orc_row_stats.argtypes = [ctypes.c_void_p]
+    a, b = Oracle(prog, arrays), Oracle(prog, arrays)
+    a.post_reset()
+    b.post_reset()
+    actions = np.zeros((len(states), max(prog.action_dim, 1)))
+    most = 0
+    for t in range(100):
+        L.orc_set_row_mode(0)
+        a.step(actions)
+        L.orc_set_row_mode(1)
+        try:
+            b.step(actions)
+        finally:
+            L.orc_set_row_mode(0)
+        for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta'):
+            assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=(k in ('dyn', 'stat', 'vtx'))), (t, k)
+        assert np.array_equal(a.counters, b.counters), (t, 'overlap statistics / pair hash')
+        most = max(most, int(a.counters[:, 1].max()))
+    assert most >= 100, 'the episodes never reached a contact-heavy pile (%d)' % most
