@@ -99,8 +99,10 @@ def test_rows_of_a_collision_entry_commute(scene):
             scene, entries, rows / waves, outran))
 
 
-def test_rows_commute_in_heavy_piles():
-    """The same rule where it matters most: whole 100-step episodes of falling_balls20 (first
+@pytest.mark.parametrize('name,floor', [('falling_balls20', 100), ('synthetic32', 0), ('colliding_predators84', 0)])
+def test_rows_commute_in_heavy_piles(name, floor):
+    """The same rule where it matters most (and, with synthetic32 / colliding_predators84, for
+    symmetric entries that also exchange spin, under random actions): whole 100-step episodes of falling_balls20 (first
     impacts of 20 balls, settled piles with up to a few hundred overlapping pairs per env-step --
     far more than the golden trajectory reaches) stepped by the oracle in the reference's order
     and in the row-order mode from identical initial states must agree bit for bit after every
@@ -108,9 +110,9 @@ def test_rows_commute_in_heavy_piles():
     import ctypes
     import moog_b200  # noqa: F401
     from moog_b200 import compiler
-    from moog_b200.configs import falling_balls20
+    import importlib
     from oracle import oracle as orc_mod
-    cfg = falling_balls20.get_config()
+    cfg = importlib.import_module('moog_b200.configs.' + name).get_config()
     np.random.seed(5)
     states = [cfg['state_initializer']() for _ in range(6)]
     prog = compiler.compile_config(cfg, states)
@@ -121,9 +123,12 @@ def test_rows_commute_in_heavy_piles():
     a, b = Oracle(prog, arrays), Oracle(prog, arrays)
     a.post_reset()
     b.post_reset()
-    actions = np.zeros((len(states), max(prog.action_dim, 1)))
+    rng = np.random.RandomState(3)
     most = 0
     for t in range(100):
+        actions = rng.uniform(-1, 1, size=(len(states), max(prog.action_dim, 1)))
+        if name == 'falling_balls20':
+            actions = np.zeros_like(actions)
         L.orc_set_row_mode(0)
         a.step(actions)
         L.orc_set_row_mode(1)
@@ -135,4 +140,4 @@ def test_rows_commute_in_heavy_piles():
             assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=(k in ('dyn', 'stat', 'vtx'))), (t, k)
         assert np.array_equal(a.counters, b.counters), (t, 'overlap statistics / pair hash')
         most = max(most, int(a.counters[:, 1].max()))
-    assert most >= 100, 'the episodes never reached a contact-heavy pile (%d)' % most
+    assert most >= floor, 'the episodes never reached a contact-heavy pile (%d)' % most
