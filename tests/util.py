@@ -127,13 +127,15 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     if a.size == 0:
         return 0.0
-    d = np.abs(a - b)
-    scale = np.maximum(np.abs(b), ATOL_FLOOR / RTOL)
-    with np.errstate(invalid='ignore'):
-        e = d / scale
-    e = np.where(np.isnan(a) & np.isnan(b), 0.0, e)
-    e = np.where((a == b), 0.0, e)
-    return float(np.nanmax(e)) if not np.all(np.isnan(e)) else float('inf')
+    same = (a == b) | (np.isnan(a) & np.isnan(b))      # equal values (infinities included) or NaN on both sides
+    finite = np.isfinite(a) & np.isfinite(b)
+    if np.any(~same & ~finite):
+        return float('inf')                            # NaN / inf on one side only, or infinities of opposite sign
+    with np.errstate(invalid='ignore', over='ignore'):
+        d = np.abs(np.where(finite, a, 0.0) - np.where(finite, b, 0.0))
+        scale = np.maximum(np.abs(np.where(finite, b, 0.0)), ATOL_FLOOR / RTOL)
+        e = np.where(same, 0.0, d / scale)
+    return float(e.max())
 
 
 AA_SCENES = ['pong', 'falling_balls20', 'colliding_predators', 'cleanup']
