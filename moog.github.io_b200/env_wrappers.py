@@ -78,26 +78,62 @@ class VectorGymWrapper(object):
 
 
 class BatchedSimulation(object):
-    """Snapshot / restore of a whole batch (simulation.py:55-83)."""
+    """Snapshot / restore of a whole batch (simulation.py:55-83): `SimulationEnvironment`'s
+    protocol -- `reset`, `step`, `sim_step`, `sim_pop(index)` -- plus explicit `push` / `pop`.
+    A snapshot is every array of the state record (task / action-space / rule memory lives in
+    it: `envf`, `envi`) and the last TimeStep's scalars."""
 
     def __init__(self, env):
         self._env = env
         self._stack = []
 
-    def push(self):
+    def _snapshot(self):
         e = self._env.engine
-        self._stack.append((self._env.state_dict(), e.reward.clone(), e.step_type.clone(), e.discount.clone()))
-        return len(self._stack)
+        return (self._env.state_dict(), e.reward.clone(), e.step_type.clone(), e.discount.clone())
 
-    def pop(self):
-        if not self._stack:
-            raise IndexError('no snapshot to restore')
-        sd, reward, step_type, discount = self._stack.pop()
+    def _restore(self, snap):
+        sd, reward, step_type, discount = snap
         self._env.load_state_dict(sd)
         e = self._env.engine
         e.reward.copy_(reward)
         e.step_type.copy_(step_type)
         e.discount.copy_(discount)
 
+    def push(self):
+        self._stack.append(self._snapshot())
+        return len(self._stack)
+
+    def pop(self):
+        if not self._stack:
+            raise IndexError('no snapshot to restore')
+        self._restore(self._stack.pop())
+
+    def reset(self):
+        """simulation.py:60-62"""
+        self._stack = []
+        return self._env.reset()
+
     def step(self, action):
+        """simulation.py:64-69: a real step first discards every simulated one."""
+        if self._stack:
+            self.sim_pop(index=0)
+        self._stack = []
         return self._env.step(action)
+
+    def sim_step(self, action):
+        """simulation.py:71-87: snapshot, then step.  The reference refuses to simulate across an
+        episode boundary (returns None when the env is about to reset); for a batch that is
+        `None` as soon as ANY env is pending a reset."""
+        if bool((self._env.engine.state.envi[:, 1] != 0).any()):    # MOOG_EI_RESET_NEXT
+            return None
+        self._stack.append(self._snapshot())
+        return self._env.step(action)
+
+    def sim_pop(self, index=-1):
+        """simulation.py:89-100: restore snapshot `index`, drop it and everything after it."""
+        self._restore(self._stack[index])
+        self._stack = self._stack[:index]
+
+    @property
+    def stack_depth(self):
+        return len(self._stack)

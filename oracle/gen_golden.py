@@ -82,6 +82,9 @@ SCENES = {
     # FirstPersonAgent renderer, grid-line sprites and the 102-vertex annulus occluder
     # (a draw-only outline, MOOG_MAX_OUTLINE)
     'parallelogram_catch': ('moog_demos.example_configs.parallelogram_catch', 0, 14, 90, 6),
+    # pairwise Gravity (incl. its dist == 0 branch), KineticFriction (rest / infinite mass / overshoot),
+    # DistanceForce(spring_force_fn), TetherZippedLayers (both modes), SetPosition with inertia
+    'forces_zoo': ('moog_b200.configs.forces_zoo', None, 15, 40, 5),
 }
 
 

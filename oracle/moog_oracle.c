@@ -1853,10 +1853,36 @@ void orc_physics_step(const void *blob, const orc_state *st, int n_envs, const d
   }
 }
 
+/* environment.py:102-126: one transition of an env that is not pending a reset */
+static void env_step_one(env_t *e, const double *action, const double *rule_noise, double *reward,
+                         int32_t *step_type) {
+  rules_step(e, rule_noise);
+  actions_step(e, action);
+  for (int k = 0; k < e->K; ++k) {
+    e->substep = k;
+    apply_physics(e);
+  }
+  e->envi[MOOG_EI_STEP_COUNT] += 1;
+  double r;
+  int reset;
+  tasks_reward(e, e->envi[MOOG_EI_STEP_COUNT], &r, &reset);
+  *reward = r;
+  *step_type = reset ? MOOG_STEP_LAST : MOOG_STEP_MID;
+  e->envi[MOOG_EI_RESET_NEXT] = reset;
+}
+
+static void put_counters(const env_t *e, int64_t *counters, int n) {
+  if (!counters) return;
+  counters[4 * n + 0] = e->n_overlap_calls;
+  counters[4 * n + 1] = e->n_overlap_true;
+  counters[4 * n + 2] = e->n_collisions;
+  counters[4 * n + 3] = (int64_t)e->overlap_hash;
+}
+
 /* environment.py:98-126 Environment.step for envs that are not pending a
  * reset (the host handles `_reset_next_step` by re-initialising the state and
- * calling orc_env_post_reset).  action: [N][action_dim]; noise: [N][K][noise_dim]
- * uniforms for RandomForce; rule_noise: [N][..] uniforms for sample_one rules. */
+ * calling orc_env_post_reset; orc_env_step_auto below does it itself).  action: [N][action_dim];
+ * noise: [N][K][noise_dim] uniforms for RandomForce; rule_noise: [N][..] uniforms for sample_one rules. */
 void orc_env_step(const void *blob, const orc_state *st, int n_envs, const double *action,
                   const double *noise, const double *rule_noise, int n_rule_noise, double *reward,
                   int32_t *step_type, int64_t *counters) {
@@ -1866,25 +1892,58 @@ void orc_env_step(const void *blob, const orc_state *st, int n_envs, const doubl
     int nd = e.hdr[MOOG_H_NOISE_DIM];
     int ad = e.hdr[MOOG_H_ACTION_DIM];
     e.noise = noise ? noise + (size_t)n * e.K * nd : NULL;
-    rules_step(&e, rule_noise ? rule_noise + (size_t)n * n_rule_noise : NULL);
-    actions_step(&e, action + (size_t)n * ad);
-    for (int k = 0; k < e.K; ++k) {
-      e.substep = k;
-      apply_physics(&e);
+    env_step_one(&e, action + (size_t)n * ad, rule_noise ? rule_noise + (size_t)n * n_rule_noise : NULL,
+                 &reward[n], &step_type[n]);
+    put_counters(&e, counters, n);
+  }
+}
+
+/* Environment.step INCLUDING its first two lines (environment.py:100-101): an env whose previous
+ * transition was a termination ignores the action and runs reset() instead (environment.py:82-96).
+ * The state initializer's result is row reset_index[n] of a pool of initial states (the batched
+ * environment keeps the config's own state_initializer() results in such a pool; which row an env
+ * receives is the caller's draw): every array of the record but the env's integer words is
+ * replaced, the episode counter advances, then task / action space / rules are reset and every
+ * rule is stepped once.  Such a step returns dm_env.restart(): step_type FIRST, reward None (NaN
+ * here), discount None (NaN); MID gives discount 1, LAST 0 (dm_env.transition / termination). */
+void orc_env_step_auto(const void *blob, const orc_state *st, int n_envs, const orc_state *pool, int pool_size,
+                       const int32_t *reset_index, const double *action, const double *noise,
+                       const double *rule_noise, int n_rule_noise, double *reward, int32_t *step_type,
+                       double *discount, int64_t *counters) {
+  for (int n = 0; n < n_envs; ++n) {
+    env_t e;
+    bind_env(&e, blob, st, n);
+    int nd = e.hdr[MOOG_H_NOISE_DIM];
+    int ad = e.hdr[MOOG_H_ACTION_DIM];
+    const double *rn = rule_noise ? rule_noise + (size_t)n * n_rule_noise : NULL;
+    e.noise = noise ? noise + (size_t)n * e.K * nd : NULL;
+    if (e.envi[MOOG_EI_RESET_NEXT] != 0) {
+      int idx = reset_index[n];
+      idx = idx < 0 ? 0 : (idx >= pool_size ? pool_size - 1 : idx);
+      env_t p;
+      bind_env(&p, blob, pool, idx);
+      const int S = e.S, NF = e.hdr[MOOG_H_N_ENVF], VT = e.hdr[MOOG_H_N_VTX];
+      memcpy(e.dyn, p.dyn, sizeof(double) * MOOG_DYN_FIELDS * S);
+      memcpy(e.stat, p.stat, sizeof(double) * MOOG_STAT_FIELDS * S);
+      memcpy(e.meta, p.meta, sizeof(int32_t) * MOOG_META_FIELDS * S);
+      memcpy(e.cnt, p.cnt, sizeof(int32_t) * MOOG_MAX_LAYERS);
+      memcpy(e.envf, p.envf, sizeof(double) * NF);
+      memcpy(e.vtx, p.vtx, sizeof(double) * 2 * VT);
+      e.envi[MOOG_EI_EPISODES] += 1;
+      e.envi[MOOG_EI_STEP_COUNT] = 0;
+      e.envi[MOOG_EI_RESET_NEXT] = 0;
+      tasks_reset(&e);
+      actions_reset(&e);
+      rules_reset(&e);
+      rules_step(&e, rn);
+      reward[n] = NAN;
+      step_type[n] = MOOG_STEP_FIRST;
+    } else {
+      env_step_one(&e, action + (size_t)n * ad, rn, &reward[n], &step_type[n]);
     }
-    e.envi[MOOG_EI_STEP_COUNT] += 1;
-    double r;
-    int reset;
-    tasks_reward(&e, e.envi[MOOG_EI_STEP_COUNT], &r, &reset);
-    reward[n] = r;
-    step_type[n] = reset ? MOOG_STEP_LAST : MOOG_STEP_MID;
-    e.envi[MOOG_EI_RESET_NEXT] = reset;
-    if (counters) {
-      counters[4 * n + 0] = e.n_overlap_calls;
-      counters[4 * n + 1] = e.n_overlap_true;
-      counters[4 * n + 2] = e.n_collisions;
-      counters[4 * n + 3] = (int64_t)e.overlap_hash;
-    }
+    if (discount)
+      discount[n] = step_type[n] == MOOG_STEP_FIRST ? NAN : (step_type[n] == MOOG_STEP_LAST ? 0.0 : 1.0);
+    put_counters(&e, counters, n);
   }
 }
 

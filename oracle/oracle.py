@@ -114,6 +114,29 @@ class Oracle(object):
             _ptr(reward), _ptr(step_type), _ptr(self.counters))
         return reward, step_type
 
+    def step_auto(self, actions, pool, reset_index, noise=None, rule_noise=None):
+        """Environment.step with its auto-reset (environment.py:98-126 incl. :100-101,
+        reset() :82-96): envs whose previous transition terminated take row
+        reset_index[n] of `pool` (another Oracle holding initial states) as the
+        state initializer's result.  Returns (reward, step_type, discount)."""
+        ad = max(self.program.action_dim, 1)
+        act = np.zeros((self.n, ad)) if actions is None else _c(
+            np.asarray(actions, dtype=np.float64).reshape(self.n, ad),
+            np.float64)
+        nz = _c(noise, np.float64)
+        rn = _c(rule_noise, np.float64)
+        ri = _c(np.asarray(reset_index).reshape(self.n), np.int32)
+        reward = np.zeros(self.n)
+        discount = np.zeros(self.n)
+        step_type = np.zeros(self.n, dtype=np.int32)
+        st, pst = self._state(), pool._state()
+        lib().orc_env_step_auto(
+            _ptr(self.blob), ctypes.byref(st), ctypes.c_int(self.n),
+            ctypes.byref(pst), ctypes.c_int(pool.n), _ptr(ri), _ptr(act),
+            _ptr(nz), _ptr(rn), ctypes.c_int(self.program.rule_noise_dim),
+            _ptr(reward), _ptr(step_type), _ptr(discount), _ptr(self.counters))
+        return reward, step_type, discount
+
     def overlap_pairs(self, layer_a, layer_b):
         p = self.program
         la, lb = p.layer_index(layer_a), p.layer_index(layer_b)

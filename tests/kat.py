@@ -224,3 +224,39 @@ def check_rare(case, prog, dyn, name=''):
         s = prog.layer_off[prog.layer_index(layer)] + k
         assert np.allclose(dyn[0:2, s], exp[pk], rtol=0, atol=RARE_ATOL), (name, idx, 'position', dyn[0:2, s], exp[pk])
         assert np.allclose(dyn[2:4, s], exp[vk], rtol=0, atol=RARE_ATOL), (name, idx, 'velocity', dyn[2:4, s], exp[vk])
+
+
+# ---------------------------------------------------------------------------
+# Episode timing: /root/reference/tests/moog/env_wrappers/test_simulation.py:35-128
+# ---------------------------------------------------------------------------
+# testStep (:68-78): with these Grid actions the agent (0.1 per step, control_velocity) reaches
+# the target at the 4th action; ContactReward(reset_steps_after_contact=2) then terminates the
+# episode at the 6th and at no earlier step.  testSimStepSimPop (:80-128) replays prefixes of the
+# same sequence through sim_step / sim_pop and expects the same timing after every restore.
+SIM_ACTIONS = [1, 4, 3, 1, 2, 0]
+SIM_INIT = [1, 4, 3]             # :82
+SIM_POP_0 = [-1]                 # :83
+SIM_REWARD_0 = [3, 1, 2, 0]      # :84
+SIM_POP_1 = [-1, -2]             # :85
+SIM_REWARD_1 = [1, 2, 0]         # :86
+
+
+def simulation_timing_config():
+    """get_env() of test_simulation.py:35-63 built from this repo's MOOG-compatible classes; the
+    ModifyMetaState rule is left out (meta_state is host-side Python in MOOG and plays no part
+    in the timing)."""
+    action_spaces, observers, physics_lib, _, sprite, tasks = _libs()
+
+    def _state_initializer():
+        agent = sprite.Sprite(x=0.5, y=0.5, scale=0.1, c0=128)
+        target = sprite.Sprite(x=0.75, y=0.5, scale=0.1, c1=128)
+        return collections.OrderedDict([('agent', [agent]), ('target', [target])])
+
+    return dict(
+        state_initializer=_state_initializer,
+        physics=physics_lib.Physics(),
+        task=tasks.ContactReward(1., 'agent', 'target', reset_steps_after_contact=2),
+        action_space=action_spaces.Grid(0.1, action_layers='agent', control_velocity=True),
+        observers={'image': observers.PILRenderer(image_size=(64, 64))},
+        game_rules=(),
+    )

@@ -388,14 +388,22 @@ def test_vector_gym_wrapper_and_simulation_snapshot():
     assert reward.shape == (32,) and done.dtype == torch.bool and not bool(done.any())
     assert torch.equal(info['discount'], torch.ones(32, device='cuda:0'))
     sim = BatchedSimulation(env)
-    sim.push()
     before = env.engine.state.dyn.clone()
-    rollout = [sim.step(act).reward.clone() for _ in range(5)]
-    assert not torch.equal(env.engine.state.dyn, before)
-    sim.pop()
-    assert torch.equal(env.engine.state.dyn, before)
-    again = [sim.step(act).reward.clone() for _ in range(5)]
+    rollout = [sim.sim_step(act).reward.clone() for _ in range(5)]
+    assert not torch.equal(env.engine.state.dyn, before) and sim.stack_depth == 5
+    sim.sim_pop(0)
+    assert torch.equal(env.engine.state.dyn, before) and sim.stack_depth == 0
+    again = [sim.sim_step(act).reward.clone() for _ in range(5)]
     assert all(torch.equal(a, b) for a, b in zip(rollout, again)), 'a restored batch replays identically'
+    # a real step discards the simulated ones first (simulation.py:64-69)
+    first_real = sim.step(act).reward.clone()
+    assert sim.stack_depth == 0 and torch.equal(first_real, rollout[0])
+    # explicit push / pop
+    sim.push()
+    mid = env.engine.state.dyn.clone()
+    env.step(act)
+    sim.pop()
+    assert torch.equal(env.engine.state.dyn, mid)
 
 
 @pytest.mark.gpu
