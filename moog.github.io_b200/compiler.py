@@ -40,6 +40,9 @@ SF_CIRCLE = 1
 SF_VEL32 = 2
 SF_ANGVEL_SHIFT = 2
 SF_ANG_SHIFT = 4
+SF_VALIAS_SHIFT = 8      # MOOG_SF_VALIAS_SHIFT
+SF_VALIAS_MASK = 0x7fffff
+EI_VALIAS_NEXT = 7       # MOOG_EI_VALIAS_NEXT
 
 (H_MAGIC, H_VERSION, H_BYTES, H_N_LAYERS, H_N_SLOTS, H_K, H_N_OPS, H_N_IPOOL,
  H_N_EXPR, H_N_ENVF, H_FORCES, H_N_FORCES, H_CORR, H_N_CORR, H_RULES,
@@ -996,7 +999,10 @@ def pack_states(prog, states, shape_table=None):
     meta = np.zeros((n, META_FIELDS, S), dtype=np.int32)
     vtx = np.zeros((n, max(prog.n_vtx, 1), 2))
     cnt = np.zeros((n, MAX_LAYERS), dtype=np.int32)
+    shared_per_env = []
     for e, st in enumerate(states):
+        shared = {}
+        shared_per_env.append(shared)
         for l, name in enumerate(prog.layer_names):
             sprites = st[name]
             if len(sprites) > prog.layer_cap[l]:
@@ -1027,7 +1033,20 @@ def pack_states(prog, states, shape_table=None):
                             name, len(world), prog.layer_vcap[l]))
                 meta[e, 2, s] = len(world)
                 vtx[e, prog.voff[s]:prog.voff[s] + len(world)] = world
+                if isinstance(vel, np.ndarray):
+                    shared.setdefault(id(vel), []).append(s)
     envi = np.zeros((n, ENVI_WORDS), dtype=np.int32)
+    # Sprites that hold the SAME velocity ndarray object (`Tether(update_angle_vel=False)` hands one
+    # array to every tethered sprite, tether_physics.py:86-91) share later in-place updates: they
+    # get a common alias id (MOOG_SF_VALIAS_SHIFT), numbered in slot order
+    for e in range(n):
+        next_id = 0
+        for slots in sorted(shared_per_env[e].values(), key=min):
+            if len(slots) > 1:
+                next_id += 1
+                for s in slots:
+                    meta[e, 1, s] |= next_id << SF_VALIAS_SHIFT
+        envi[e, EI_VALIAS_NEXT] = next_id
     envf = np.zeros((n, max(prog.n_envf, 1)))
     if prog.maze_offsets:
         from . import host_maze

@@ -70,8 +70,8 @@ def _check_state(g, t, arrays, tol, what):
     if len(f):
         f = int(f[0])
         err = max(err, util.rel_err(arrays['stat'][0][:, live], g['stat'][f][:, live]))
-        assert np.array_equal(_meta_for_comparison(arrays['meta'][0], arrays['dyn'][0])[:, live],
-                              _meta_for_comparison(g['meta'][f], g['dyn'][t])[:, live]), (what, t, 'meta')
+        assert np.array_equal(util.canonical_meta(_meta_for_comparison(arrays['meta'][0], arrays['dyn'][0]), live),
+                              util.canonical_meta(_meta_for_comparison(g['meta'][f], g['dyn'][t]), live)), (what, t, 'meta')
         vlive = util.live_vertex_mask(prog, g['cnt'][t], g['meta'][f])
         err = max(err, util.rel_err(arrays['vtx'][0][vlive], g['vtx'][f][vlive]))
     assert err <= tol, (what, t, err)

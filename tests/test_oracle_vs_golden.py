@@ -33,6 +33,7 @@ def test_oracle_follows_reference_trajectory(scene):
             worst = max(worst, util.rel_err(getattr(orc, k)[0][:, live], g[k][t][:, live]))
         vlive = util.live_vertex_mask(prog, g['cnt'][t], g['meta'][t])
         worst = max(worst, util.rel_err(orc.vtx[0][vlive], g['vtx'][t][vlive]))
+        assert np.array_equal(util.canonical_meta(orc.meta[0], live), util.canonical_meta(g['meta'][t], live)), (scene, t, 'meta')
         assert reward[0] == g['reward'][t], (scene, t)
         assert bool(step_type[0] == 2) == bool(g['last'][t]), (scene, t)
         n_calls, n_true, _, h = orc.counters[0]

@@ -110,13 +110,35 @@ def live_vertex_mask(prog, cnt, meta):
     return vlive
 
 
+def canonical_meta(meta, live):
+    """meta[3, S] of the live slots with the velocity-alias ids (MOOG_SF_VALIAS_SHIFT) renumbered
+    1, 2, ... in slot order: the ids only name groups of sprites sharing one velocity ndarray
+    (tether_physics.py:86-91); which number a group carries is an implementation detail (the
+    device hands out fresh ids every substep, a packed reference state numbers them per state)."""
+    out = np.array(meta[:, live], dtype=np.int64)
+    ids = (out[1] >> 8) & 0x7fffff
+    remap, nxt = {0: 0}, 0
+    for k, i in enumerate(ids):
+        if int(i) not in remap:
+            nxt += 1
+            remap[int(i)] = nxt
+        out[1, k] = (out[1, k] & 0xff) | (remap[int(i)] << 8)
+    # a group of one is no sharing at all
+    new_ids = (out[1] >> 8) & 0x7fffff
+    for i in set(new_ids.tolist()) - {0}:
+        if (new_ids == i).sum() == 1:
+            out[1, new_ids == i] &= 0xff
+    return out
+
+
 def assert_live_equal(prog, got, want, what):
     """Bit-equality of two state records (dicts of [fields, S] arrays / vtx /
     cnt) over the live sprites."""
     assert np.array_equal(got['cnt'], want['cnt']), what + ' cnt'
     live = live_mask(prog, want['cnt'])
-    for k in ('dyn', 'stat', 'meta'):
+    for k in ('dyn', 'stat'):
         assert np.array_equal(got[k][:, live], want[k][:, live]), what + ' ' + k
+    assert np.array_equal(canonical_meta(got['meta'], live), canonical_meta(want['meta'], live)), what + ' meta'
     vlive = live_vertex_mask(prog, want['cnt'], want['meta'])
     assert np.array_equal(got['vtx'][vlive], want['vtx'][vlive]), what + ' vtx'
 
