@@ -477,8 +477,14 @@ def _compile_actions(prog, action_space):
 # rules
 # ---------------------------------------------------------------------------
 
-def _rule_specs(prog, rule, out):
+MAX_COND_DEPTH = 4   # MOOG_MAX_COND_DEPTH (csrc/moog_step.cu rules_step: explicit block stack)
+
+
+def _rule_specs(prog, rule, out, depth=0):
     k = _kind(rule)
+    if k in ('ConditionalRule', 'TimedRule', 'DelayedRule', 'TemporaryRule') and depth >= MAX_COND_DEPTH:
+        raise CompileError('conditional / timed rules nested deeper than {} are not on the accelerated '
+                           'path'.format(MAX_COND_DEPTH))
     if k == 'VanishOnContact':
         gci = rule._get_contact_indices
         l0, l1 = lambdas.contact_layers(gci)
@@ -515,18 +521,24 @@ def _rule_specs(prog, rule, out):
     elif k == 'ConditionalRule':
         sub = []
         for r in rule._rules:
-            _rule_specs(prog, r, sub)
+            _rule_specs(prog, r, sub, depth + 1)
         out.append(dict(kind=R_COND_BEGIN, cond=rule._condition,
                         i=[0, len(sub)]))
         out.extend(sub)
     elif k in ('TimedRule', 'DelayedRule', 'TemporaryRule'):
         # timing.py:15-107; a random interval (user callable) cannot be lowered
-        draws = [tuple(float(v) for v in rule._step_interval()) for _ in range(4)]
-        if len(set(draws)) != 1:
+        # (sampling the callable a few times would misclassify one that picks among few values;
+        # it is called with every module-level random draw refused instead)
+        try:
+            with lambdas.no_randomness('{} step interval'.format(k)):
+                draws = [tuple(float(v) for v in rule._step_interval()) for _ in range(2)]
+        except lambdas.ImpureCallable:
             raise CompileError('{} with a random step interval is not on the accelerated path'.format(k))
+        if len(set(draws)) != 1:
+            raise CompileError('{} with a varying step interval is not on the accelerated path'.format(k))
         sub = []
         for r in rule._rules:
-            _rule_specs(prog, r, sub)
+            _rule_specs(prog, r, sub, depth + 1)
         out.append(dict(kind=R_TIMED_BEGIN, i=[0, len(sub), prog.alloc_envf(2)], p=draws[0]))
         out.extend(sub)
     elif k == 'KeepNearCenter':

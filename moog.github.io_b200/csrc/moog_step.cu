@@ -45,7 +45,16 @@ namespace moog {
 #define SLF_SHORT_EDGE 1  // slot flag: some edge is shorter than 1e-4 -> serial matplotlib path
 #define SLF_NONFINITE 2   // some cached vertex coordinate is NaN / inf -> no culling at all
 #define SLF_ALLNAN 4      // every cached vertex coordinate is NaN -> overlaps nothing
-#define SLF_MASK 7
+// Some edge is vertical up to rounding but not exactly (0 < |dx| <= STEEP_DX).  matplotlib's
+// segments_intersect calls two nearly parallel, nearly collinear segments intersecting when their
+// X-INTERVALS overlap (unless x1 == x2 == x3 exactly, then the y-intervals decide): for such an edge
+// the x-interval is a few ulps wide and the rule fires for segments that are far apart in y.  A
+// collinearity tolerance of 1e-13 / |edge| bridges a gap of at most 1e-13 / |dx| along the line, so
+// edges with |dx| > STEEP_DX stay inside the boxes' padding; a slot that has a steeper one gets a
+// box that covers every y (culling on x stays exact) and the serial matplotlib path.
+#define SLF_STEEP 8
+#define SLF_MASK 15
+#define STEEP_DX 1e-5
 
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
@@ -357,11 +366,15 @@ __device__ __forceinline__ double moment_of_inertia(const Env &e, int s) {
 
 // A slot with a NaN / inf coordinate gets an all-covering box: it is never culled.
 __device__ __forceinline__ void store_box(const Env &e, int s, double xmin, double ymin, double xmax, double ymax,
-                                          bool nonfinite) {
+                                          bool nonfinite, bool steep = false) {
   BOX(e, 0, s) = nonfinite ? -INFINITY : xmin;
-  BOX(e, 1, s) = nonfinite ? -INFINITY : ymin;
+  BOX(e, 1, s) = (nonfinite || steep) ? -INFINITY : ymin;
   BOX(e, 2, s) = nonfinite ? INFINITY : xmax + AABB_PAD;
-  BOX(e, 3, s) = nonfinite ? INFINITY : ymax + AABB_PAD;
+  BOX(e, 3, s) = (nonfinite || steep) ? INFINITY : ymax + AABB_PAD;
+}
+__device__ __forceinline__ bool steep_edge(double x0, double x1) {
+  const double dx = x1 - x0;
+  return dx != 0.0 && fabs(dx) <= STEEP_DX;
 }
 
 // lane-parallel over the vertices of slot s: NaN / inf classification (called
@@ -390,7 +403,7 @@ __device__ inline void refresh_all_boxes(const Env &e) {
     int n = META(e, MOOG_M_NV, s);
     const double2 *v = e.vtx + e.voff[s];
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-    bool sh = n < 3, nonfinite = false, allnan = n > 0;
+    bool sh = n < 3, nonfinite = false, allnan = n > 0, steep = false;
     double2 prev = n > 0 ? v[n - 1] : make_double2(0., 0.);
     for (int i = 0; i < n; ++i) {
       double2 p = v[i];
@@ -398,12 +411,14 @@ __device__ inline void refresh_all_boxes(const Env &e) {
       ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
       double len2 = (p.x - prev.x) * (p.x - prev.x) + (p.y - prev.y) * (p.y - prev.y);
       sh |= !(len2 > SHORT_EDGE2);
+      steep |= steep_edge(prev.x, p.x);
       nonfinite |= !(isfinite(p.x) && isfinite(p.y));
       allnan &= isnan(p.x) && isnan(p.y);
       prev = p;
     }
-    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite);
-    e.sflag[s] = (sh ? SLF_SHORT_EDGE : 0) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite, steep);
+    e.sflag[s] = (sh ? SLF_SHORT_EDGE : 0) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0) |
+                 (steep ? SLF_STEEP : 0);
   }
   wsync();
 }
@@ -597,8 +612,8 @@ __device__ __forceinline__ bool path_intersects_filled_impl(const Env &e, int a,
   // is contained in nothing: every segment test has a NaN denominator, every
   // crossing-number comparison is false
   if (fl & SLF_ALLNAN) return false;
-  const bool nocull = (fl & SLF_NONFINITE) != 0;  // boxes are meaningless with NaN / inf around
-  bool serial = (fl & (SLF_SHORT_EDGE | SLF_NONFINITE)) != 0;
+  const bool nocull = (fl & (SLF_NONFINITE | SLF_STEEP)) != 0;  // boxes are meaningless with NaN / inf around
+  bool serial = (fl & (SLF_SHORT_EDGE | SLF_NONFINITE | SLF_STEEP)) != 0;
   if (serial) {
     if (path_intersects_path_serial(A, nA, B, nB)) return true;
   } else {
@@ -1957,11 +1972,16 @@ __device__ inline void set_angle_f64(const Env &e, int s, double a) {
   }
   const bool nonfinite = !__all_sync(FULL, fin);
   const bool allnan = n > 0 && __all_sync(FULL, nan_all);
+  wsync();
+  bool st = false;
+  for (int i = e.lane; i < n; i += 32) st |= steep_edge(v[i].x, v[(i + 1 == n) ? 0 : i + 1].x);
+  const bool steep = __any_sync(FULL, st) != 0;
   if (e.lane == 0) {
     DYN(e, MOOG_D_ANG, s) = a;
     META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (KIND_F64 << MOOG_SF_ANG_SHIFT);
-    e.sflag[s] = (e.sflag[s] & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
-    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite);
+    e.sflag[s] = (e.sflag[s] & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0) |
+                 (steep ? SLF_STEEP : 0);
+    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite, steep);
   }
   wsync();
 }
@@ -2199,7 +2219,8 @@ __device__ inline void integrate_all(const Env &e) {
       int n = META(e, MOOG_M_NV, s);
       const double2 *v = e.vtx + e.voff[s];
       double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-      bool nonfinite = false, allnan = n > 0;
+      bool nonfinite = false, allnan = n > 0, steep = false;
+      double px = n > 0 ? v[n - 1].x : 0.0;
 #pragma unroll 1
       for (int i = 0; i < n; ++i) {
         double2 p = v[i];
@@ -2207,10 +2228,13 @@ __device__ inline void integrate_all(const Env &e) {
         ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
         nonfinite |= !(isfinite(p.x) && isfinite(p.y));
         allnan &= isnan(p.x) && isnan(p.y);
+        steep |= steep_edge(px, p.x);
+        px = p.x;
       }
       if (flag & TF_CLASSIFY)
-        low = (low & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
-      store_box(e, s, xmin, ymin, xmax, ymax, (low & SLF_NONFINITE) != 0);
+        low = (low & (SLF_SHORT_EDGE | SLF_STEEP)) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0);
+      low = (low & ~SLF_STEEP) | (steep ? SLF_STEEP : 0);
+      store_box(e, s, xmin, ymin, xmax, ymax, (low & SLF_NONFINITE) != 0, steep);
     }
     e.sflag[s] = low;
   }
@@ -2894,7 +2918,7 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
         const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
         const double u = kind == MOOG_ZK_CONST ? 0.0
                                                : philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                                                ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | (uint32_t)a);
+                                                                ((uint32_t)s << 20) | (uint32_t)tries, (0x5Au << 24) | (uint32_t)a);
         v[a] = sample_leaf(dpool, kind, idx, n, u);
       }
       {
@@ -2902,14 +2926,14 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
         // alternative; SetMinus / Selection redraw their base until it is outside / inside a box)
         const int32_t *x = tab + 3 * MOOG_Z_N_ATTRS;
         const int n_ext = *x++;
-        uint32_t draw = 32;
+        uint32_t draw = 0;
         for (int c = 0; c < n_ext; ++c) {
           const int kind = *x++;
           if (kind == 1) {
             const int n_alt = *x++;
             const double *cum = dpool + *x++;
             const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                            ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | draw++);
+                                            ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
             int pick = 0;
             while (pick < n_alt - 1 && !(u < cum[pick])) ++pick;   // rng.choice(n, p=probs)
             for (int a = 0; a < n_alt; ++a) {
@@ -2917,7 +2941,7 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
               for (int q = 0; q < n_leaves; ++q, x += 4) {
                 if (a != pick) continue;
                 const double uu = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                                 ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | draw++);
+                                                 ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
                 v[x[0]] = sample_leaf(dpool, x[1], x[2], x[3], uu);
               }
             }
@@ -2929,10 +2953,13 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
             const int n_box = *x++;
             const int32_t *box = x;
             x += 2 * n_box;
-            for (int inner = 0; inner < 64; ++inner) {
+            // distributions.py:341-349, 394-404: redraw the base until it is outside / inside the box,
+            // at most _MAX_TRIES = 1e5 times, then raise
+            bool accepted = false;
+            for (int inner = 0; inner < 100000 && !accepted; ++inner) {
               for (int q = 0; q < n_leaves; ++q) {
                 const double uu = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                                 ((uint32_t)s << 20) | (uint32_t)tries, 0x5A00u | draw++);
+                                                 ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
                 v[leaves[4 * q]] = sample_leaf(dpool, leaves[4 * q + 1], leaves[4 * q + 2], leaves[4 * q + 3], uu);
               }
               bool inside = true;
@@ -2940,7 +2967,13 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
                 const double val = v[box[2 * q]], lo = dpool[box[2 * q + 1]], hi = dpool[box[2 * q + 1] + 1];
                 inside = inside && val >= lo && val < hi;   // Continuous.contains
               }
-              if (inside == (keep_inside != 0)) break;
+              accepted = inside == (keep_inside != 0);
+            }
+            if (!accepted) {  // the reference raises ValueError here; the env carries the error bit
+              const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_RESET_REJECTED;
+              wsync();
+              puti(e, &e.envi[MOOG_EI_ERR], err);
+              wsync();
             }
           }
         }

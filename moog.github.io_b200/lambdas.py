@@ -20,8 +20,11 @@ there is no per-step Python fallback.
 """
 
 import ast
+import contextlib
 import inspect
 import textwrap
+
+import numpy as np
 
 (X_END, X_CONST, X_ATTR0, X_ATTR1, X_LT, X_LE, X_GT, X_GE, X_EQ, X_NE, X_AND,
  X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE,
@@ -371,20 +374,63 @@ def _rewritten(fn):
     return ns[node.name]
 
 
+_NP_RANDOM_FNS = ('uniform', 'rand', 'randn', 'randint', 'random', 'random_sample', 'ranf', 'sample', 'choice',
+                  'normal', 'standard_normal', 'permutation', 'shuffle', 'binomial', 'poisson', 'exponential',
+                  'beta', 'gamma', 'triangular', 'vonmises', 'laplace', 'lognormal', 'bytes')
+_PY_RANDOM_FNS = ('random', 'uniform', 'randint', 'randrange', 'choice', 'choices', 'sample', 'shuffle', 'gauss',
+                  'normalvariate', 'triangular', 'betavariate', 'expovariate', 'getrandbits')
+
+
+class ImpureCallable(LoweringError):
+    """A config callable drew a random number while it was being traced."""
+
+
+@contextlib.contextmanager
+def no_randomness(what='callable'):
+    """While a config callable is traced ONCE into a device expression, any random draw it makes
+    would be frozen into a constant for every env, step and episode (e.g. match_to_sample.py:227-228
+    `s.velocity = np.random.uniform(-0.25, 0.25, size=(2,))`).  Inside this context the module-level
+    draws of `numpy.random` and `random` raise instead, so such a config is refused loudly."""
+    import random as _pyrandom
+
+    def _refuse(name):
+        def _raise(*args, **kwargs):
+            raise ImpureCallable(
+                '{} calls {} while being lowered: a random draw cannot be traced to a device '
+                'expression (it would be frozen to one value for every env and step)'.format(what, name))
+        return _raise
+
+    saved = []
+    for mod, names, prefix in ((np.random, _NP_RANDOM_FNS, 'numpy.random.'), (_pyrandom, _PY_RANDOM_FNS, 'random.')):
+        for n in names:
+            if hasattr(mod, n):
+                saved.append((mod, n, getattr(mod, n)))
+                setattr(mod, n, _refuse(prefix + n))
+    try:
+        yield
+    finally:
+        for mod, n, fn in saved:
+            setattr(mod, n, fn)
+
+
 def _symbolic_call(fn, *args):
     """fn(*args) on symbolic sprites; when the callable uses Python's `and` / `or` / `not` /
     `any` / `all` on per-sprite values (which plain tracing cannot see), it is recompiled with
-    those constructs turned into expression builders and traced again."""
-    try:
-        return fn(*args)
-    except (LoweringError, TypeError):
+    those constructs turned into expression builders and traced again.  Random draws are refused
+    (`no_randomness`)."""
+    with no_randomness(repr(getattr(fn, '__name__', fn))):
         try:
-            return _rewritten(fn)(*args)
-        except LoweringError:
+            return fn(*args)
+        except ImpureCallable:
             raise
-        except Exception as exc:  # pylint: disable=broad-except
-            raise LoweringError('cannot lower {!r} to a device expression ({}: {})'.format(
-                getattr(fn, '__name__', fn), type(exc).__name__, exc))
+        except (LoweringError, TypeError):
+            try:
+                return _rewritten(fn)(*args)
+            except LoweringError:
+                raise
+            except Exception as exc:  # pylint: disable=broad-except
+                raise LoweringError('cannot lower {!r} to a device expression ({}: {})'.format(
+                    getattr(fn, '__name__', fn), type(exc).__name__, exc))
 
 
 def compile_sprite_predicate(fn):
@@ -432,8 +478,11 @@ def constant_reward(reward_fn):
     if set(cv) == {'reward_fn'} and not callable(cv['reward_fn']):
         return float(cv['reward_fn'])
     try:
-        out = reward_fn(SymSprite(0), SymSprite(1))
+        with no_randomness('ContactReward reward_fn'):
+            out = reward_fn(SymSprite(0), SymSprite(1))
         return float(out)
+    except ImpureCallable:
+        raise
     except (LoweringError, TypeError):
         raise LoweringError(
             'ContactReward reward_fn must be a constant on the device path')
@@ -465,7 +514,10 @@ def constant_state_reward(reward_fn):
     if reward_fn is None:
         return 0.0
     try:
-        return float(reward_fn(None))
+        with no_randomness('Reset reward_fn'):
+            return float(reward_fn(None))
+    except ImpureCallable:
+        raise
     except Exception:  # pylint: disable=broad-except
         raise LoweringError(
             'Reset reward_fn must not depend on the state on the device path')

@@ -469,3 +469,42 @@ def test_step_to_host_auto_policy_keeps_the_faster_transport():
         assert env._auto_choice == winner and seen[8:] == [winner] * 4
     assert fresh()._auto_frames(Img(False)) == 'device'
     assert fresh()._auto_frames(None) == 'device'
+
+
+def test_impure_config_callables_are_refused():
+    """A modifier / reward / interval that draws random numbers would be traced ONCE and frozen into
+    a constant for every env and step (round-1 advisor finding; e.g. match_to_sample.py:227-228).
+    The compiler refuses it; deterministic callables still lower."""
+    import moog_b200  # noqa: F401
+    from moog import game_rules
+    from moog_b200 import compiler, lambdas
+    from moog_b200.configs import timed_center
+
+    def _kick(s):
+        s.velocity = np.random.uniform(-0.25, 0.25, size=(2,))
+
+    with pytest.raises(lambdas.LoweringError, match='random'):
+        lambdas.compile_modifier(_kick)
+    with pytest.raises(lambdas.LoweringError, match='random'):
+        lambdas.pair_reward(lambda a, b: np.random.rand())
+    state = np.random.get_state()
+    lambdas.compile_modifier(lambda s: setattr(s, 'opacity', 128))
+    assert np.random.get_state()[1].tolist() == state[1].tolist(), 'tracing consumes no random numbers'
+    assert np.random.uniform.__name__ == 'uniform', 'numpy.random is restored after tracing'
+
+    cfg = timed_center.get_config()
+    np.random.seed(1)
+    states = [cfg['state_initializer']()]
+    compiler.compile_config(cfg, states)                       # fixed intervals: fine
+    rules = list(cfg['game_rules'])
+    rules[1] = game_rules.TimedRule(lambda: (5, 6) if np.random.rand() < 0.5 else (7, 8), game_rules.VanishByFilter('cue'))
+    cfg['game_rules'] = tuple(rules)
+    with pytest.raises(compiler.CompileError, match='random step interval'):
+        compiler.compile_config(cfg, states)
+    # rules nested deeper than the device's block stack are refused instead of silently skipped
+    inner = game_rules.VanishByFilter('cue')
+    for _ in range(5):
+        inner = game_rules.ConditionalRule(lambda state: True, inner)
+    cfg['game_rules'] = (inner,)
+    with pytest.raises(compiler.CompileError, match='nested deeper'):
+        compiler.compile_config(cfg, states)
