@@ -27,7 +27,8 @@ NVCC_FLAGS = [
     '-Wno-deprecated-gpu-targets',
 ] + (['-DMOOG_PROFILE_PHASES'] if os.environ.get('MOOG_PROFILE_PHASES') else []) + (
     ['-DMOOG_PROFILE_DCV'] if os.environ.get('MOOG_PROFILE_DCV') else []) + (
-    ['-DMOOG_PROFILE_GCV'] if os.environ.get('MOOG_PROFILE_GCV') else [])
+    ['-DMOOG_PROFILE_GCV'] if os.environ.get('MOOG_PROFILE_GCV') else []) + (
+    ['-DMOOG_PROFILE_INTEG'] if os.environ.get('MOOG_PROFILE_INTEG') else [])
 
 
 def _nvcc():

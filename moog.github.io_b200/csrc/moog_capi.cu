@@ -25,6 +25,9 @@ struct moog_program {
   int ksize_h, ksize_v;
   // largest outline a slot of each layer can hold (from the blob's voff table)
   int layer_vcap[MOOG_MAX_LAYERS];
+  // cached vertex -> (slot << 8 | index within the slot's outline), [VT]: the Euler pass of the step
+  // kernel walks the vertex cache flat, lane = vertex
+  uint16_t *dev_vmap;
 };
 
 namespace {
@@ -77,8 +80,21 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
   if (err == cudaSuccess)  // the derived header word, in the device copy too
     err = cudaMemcpy((int32_t *)p->dev_blob + MOOG_H_CMASK_WORDS, &p->hdr[MOOG_H_CMASK_WORDS], sizeof(int32_t),
                      cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && hdr[MOOG_H_N_VTX] > 0) {
+    moog::ProgramView pv = moog::view_of(blob);
+    std::vector<uint16_t> vmap((size_t)hdr[MOOG_H_N_VTX], 0xffffu);
+    for (int sl = 0; sl < hdr[MOOG_H_N_SLOTS]; ++sl)
+      for (int v = pv.voff[sl]; v < pv.voff[sl + 1] && v < hdr[MOOG_H_N_VTX]; ++v) {
+        const int k = v - pv.voff[sl];
+        vmap[(size_t)v] = (uint16_t)((sl << 8) | (k < 255 ? k : 255));  // (MOOG_MAX_OUTLINE = 128 < 255)
+      }
+    err = cudaMalloc((void **)&p->dev_vmap, sizeof(uint16_t) * vmap.size());
+    if (err == cudaSuccess)
+      err = cudaMemcpy(p->dev_vmap, vmap.data(), sizeof(uint16_t) * vmap.size(), cudaMemcpyHostToDevice);
+  }
   if (err != cudaSuccess) {
     if (p->dev_blob) cudaFree(p->dev_blob);
+    if (p->dev_vmap) cudaFree(p->dev_vmap);
     free(p);
     return cuda_fail(err);
   }
@@ -89,6 +105,7 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
 void moog_program_destroy(moog_program *p) {
   if (!p) return;
   if (p->dev_blob) cudaFree(p->dev_blob);
+  if (p->dev_vmap) cudaFree(p->dev_vmap);
   if (p->sched) cudaFree(p->sched);
   if (p->done) cudaFree(p->done);
   if (p->resample) cudaFree(p->resample);
@@ -159,6 +176,7 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   moog::StepArgs a;
   memset(&a, 0, sizeof(a));
   a.blob = p->dev_blob;
+  a.vmap = p->dev_vmap;
   a.st = *st;
   a.n_envs = n_envs;
   a.mode = mode;

@@ -35,6 +35,7 @@ enum StepMode { MODE_ENV_STEP = 0, MODE_PHYSICS = 1, MODE_POST_RESET = 2, MODE_O
 
 struct StepArgs {
   const void *blob;  // device copy of the program
+  const uint16_t *vmap;  // [VT] cached vertex -> slot << 8 | index within the slot's outline (255: beyond 254)
   moog_state st;
   int n_envs;
   int mode;

@@ -59,7 +59,7 @@ namespace moog {
 enum { KIND_WEAK = 0, KIND_F32 = 1, KIND_F64 = 2 };
 
 struct SmemLayout {
-  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, mbar, plist, kscr, kscr_bytes, tile, total;
+  int rec, dyn, stat, aabb, aabb0, nskin, tmp, vtx, envf, ctr, meta, sflag, voff, cnt, envi, cmoff, cmask, nearp, hdr, scratch, xchg, mbar, plist, kscr, kscr_bytes, tile, vmap, total;
 };
 
 #define MOOG_MAX_FORCE_OPS 32
@@ -103,6 +103,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.plist = o; o += CMW > 0 ? 2 * 32 * tile * warps : 8;  // crossing (vertex, edge) pairs, per warp
   L.kscr_bytes = CMW > 0 ? 8 * 32 * tile : 8;
   L.kscr = o;  o += L.kscr_bytes * warps;
+  L.vmap = o;  o += 2 * VT;  // cached vertex -> slot << 8 | index within the outline (integrate_all)
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -144,6 +145,7 @@ struct Env {
   const moog_op *ops;
   const int32_t *ipool;
   const moog_ex *expr;
+  const uint16_t *vmap;      // program constant: cached vertex -> slot << 8 | index in the outline
   int S, L, K, VT, lane;
   const double *noise;       // [K][noise_dim] of this env or nullptr
   const double *rule_noise;  // [rule_noise_dim] of this env or nullptr
@@ -167,6 +169,7 @@ struct EnvRec {
   const int32_t *ipool;
   const moog_ex *expr;
   const double *noise, *rule_noise;
+  const uint16_t *vmap;
   uint64_t seed;
 };
 static_assert(sizeof(EnvRec) <= 224, "EnvRec must fit its shared-memory slot");
@@ -202,6 +205,7 @@ __device__ __forceinline__ Env env_view() {
   e.dcv_tile = r->lay.tile;
   e.mbar = (unsigned long long *)(base + r->lay.mbar);
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
+  e.vmap = r->vmap ? (const uint16_t *)(base + r->lay.vmap) : nullptr;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x & 31;
   e.noise = r->noise; e.rule_noise = r->rule_noise;
@@ -210,7 +214,7 @@ __device__ __forceinline__ Env env_view() {
   return e;
 }
 
-#if defined(MOOG_PROFILE_PHASES) || defined(MOOG_PROFILE_DCV) || defined(MOOG_PROFILE_GCV)
+#if defined(MOOG_PROFILE_PHASES) || defined(MOOG_PROFILE_DCV) || defined(MOOG_PROFILE_GCV) || defined(MOOG_PROFILE_INTEG)
 #define PROF_RESOLVE(e, t1)
 #else
 #define PROF_RESOLVE(e, t1) ctr_add(e, CT_CYC_RESOLVE, clock64() - (t1))
@@ -1261,7 +1265,7 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
     } else {
       ov = overlaps(e, s0, s1);
     }
-#if !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV) && !defined(MOOG_PROFILE_GCV)
+#if !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV) && !defined(MOOG_PROFILE_GCV) && !defined(MOOG_PROFILE_INTEG)
     ctr_add(e, CT_NARROW, 1);
     ctr_add(e, CT_CYC_NARROW, clock64() - t0);
 #endif
@@ -2100,8 +2104,11 @@ __device__ __noinline__ void corrective(const Env &, const moog_op *op) {
 #define TF_ROT 2
 #define TF_CLASSIFY 4
 
-__device__ inline void integrate_all(const Env &e) {
+__device__ __forceinline__ void integrate_all_impl(const Env &e) {
   double dt = 1. / e.K;
+#ifdef MOOG_PROFILE_INTEG
+  long long ti0 = clock64(), ti1 = 0;
+#endif
   for (int base = 0; base < e.S; base += 32) {
     // phase 1: lane = slot.  New position / angle and the affine update of the outline
     // (kept in this lane's registers; phase 2 fetches them by shuffle).
@@ -2153,34 +2160,17 @@ __device__ inline void integrate_all(const Env &e) {
       if ((flag & TF_ROT) && (e.sflag[s] & SLF_NONFINITE)) flag |= TF_CLASSIFY;
       e.sflag[s] = (e.sflag[s] & SLF_MASK) | (flag << 8);
     }
-    // phase 2: one moved slot at a time, lane = vertex of its outline
+#ifdef MOOG_PROFILE_INTEG
+    ti1 = clock64();
+    ctr_add(e, CT_NARROW, ti1 - ti0);
+#endif
+    // phase 2a: the slots that also rotate, one at a time, lane = vertex of the outline (the
+    // translate-only slots -- the common case -- are left to the flat pass below)
     unsigned mv = __ballot_sync(FULL, flag != 0);
     const unsigned rot = __ballot_sync(FULL, (flag & TF_ROT) != 0);
-#ifndef MOOG_NO_SIMPLE_MOVE
-    {
-      // slots that only translate (the common case): the outline's size and address come by
-      // shuffle from the lane that owns the slot, and the loop body has no rotation in it
-      const int my_n = s < e.S ? META(e, MOOG_M_NV, s) : 0;
-      const int my_vo = s < e.S ? e.voff[s] : 0;
-      unsigned simple = mv & ~rot;
-      mv &= rot;
-#pragma unroll 1
-      while (simple) {
-        const int src = __ffs(simple) - 1;
-        simple &= simple - 1;
-        const int n = __shfl_sync(FULL, my_n, src);
-        double2 *v = e.vtx + __shfl_sync(FULL, my_vo, src);
-        const double ttx = shfl_d(tx, src), tty = shfl_d(ty, src);
-        if (e.lane < n) {
-          const double2 p = v[e.lane];
-          // Affine2D().translate(tx, ty): 1.0 * x is exact, the 0.0 * y term keeps the
-          // reference's NaN / signed-zero behaviour
-          v[e.lane] = make_double2((p.x + 0.0 * p.y) + ttx, (0.0 * p.x + p.y) + tty);
-        }
-        if (n > 32) outline_tail(v, n, e.lane, ttx, tty, false, 1, 0, 0, 0, 1, 0);
-      }
-    }
-#endif
+    if (s < e.S) ((double2 *)e.tmp)[s] = make_double2(tx, ty);
+    if (e.lane == 0) ((unsigned *)e.scratch)[base >> 5] = mv & ~rot;
+    mv &= rot;
     while (mv) {
       const int src = __ffs(mv) - 1;
       mv &= mv - 1;
@@ -2196,21 +2186,64 @@ __device__ inline void integrate_all(const Env &e) {
         x = (p.x + 0.0 * p.y) + ttx;
         y = (0.0 * p.x + p.y) + tty;
       }
-      const bool rotates = (rot >> src) & 1u;
-      double r0 = 1, r1 = 0, r2 = 0, r3 = 0, r4 = 1, r5 = 0;
-      if (rotates) {
-        r0 = shfl_d(m.m0, src); r1 = shfl_d(m.m1, src); r2 = shfl_d(m.m2, src);
-        r3 = shfl_d(m.m3, src); r4 = shfl_d(m.m4, src); r5 = shfl_d(m.m5, src);
-        const double rx = r0 * x + r1 * y + r2;
-        const double ry = r3 * x + r4 * y + r5;
-        x = rx;
-        y = ry;
-      }
-      if (e.lane < n) v[e.lane] = make_double2(x, y);
-      if (n > 32) outline_tail(v, n, e.lane, ttx, tty, rotates, r0, r1, r2, r3, r4, r5);
+      const double r0 = shfl_d(m.m0, src), r1 = shfl_d(m.m1, src), r2 = shfl_d(m.m2, src);
+      const double r3 = shfl_d(m.m3, src), r4 = shfl_d(m.m4, src), r5 = shfl_d(m.m5, src);
+      const double rx = r0 * x + r1 * y + r2;
+      const double ry = r3 * x + r4 * y + r5;
+      if (e.lane < n) v[e.lane] = make_double2(rx, ry);
+      if (n > 32) outline_tail(v, n, e.lane, ttx, tty, true, r0, r1, r2, r3, r4, r5);
     }
   }
   wsync();
+  // phase 2b: every vertex of every slot that only translates, lane = cached vertex.  Which slot a
+  // vertex belongs to is a constant of the program (vmap); the iterations are independent, so
+  // their shared-memory round trips overlap instead of queueing behind one another slot by slot.
+  if (e.vmap) {
+    const unsigned *smask = (const unsigned *)e.scratch;
+    const double2 *tt = (const double2 *)e.tmp;
+    const uint16_t *vmap = e.vmap;
+    const int *nvs = &META(e, MOOG_M_NV, 0);
+    double2 *vtx = e.vtx;
+    const int VT = e.VT, S = e.S;
+    // four vertices per lane and trip, every load issued before the first use and no branch but
+    // the stores' predicates: straight-line code whose shared-memory round trips overlap
+#pragma unroll 1
+    for (int v0 = e.lane; v0 < VT; v0 += 128) {
+      unsigned u[4], sl[4], word[4];
+      int nv[4];
+      bool ok[4];
+      double2 p[4], t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = v0 + 32 * q;
+        ok[q] = v < VT;
+        u[q] = vmap[ok[q] ? v : 0];
+        p[q] = vtx[ok[q] ? v : 0];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned raw = u[q] >> 8;
+        sl[q] = raw < (unsigned)S ? raw : 0u;
+        ok[q] = ok[q] & (raw < (unsigned)S);
+        word[q] = smask[sl[q] >> 5];
+        nv[q] = nvs[sl[q]];
+        t[q] = tt[sl[q]];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ok[q] = ok[q] & (((word[q] >> (sl[q] & 31u)) & 1u) != 0u) & ((int)(u[q] & 255u) < nv[q]);
+        // Affine2D().translate(tx, ty): 1.0 * x is exact, the 0.0 * y term keeps the
+        // reference's NaN / signed-zero behaviour
+        const double2 o = make_double2((p[q].x + 0.0 * p[q].y) + t[q].x, (0.0 * p[q].x + p[q].y) + t[q].y);
+        if (ok[q]) vtx[v0 + 32 * q] = o;
+      }
+    }
+  }
+  wsync();
+#ifdef MOOG_PROFILE_INTEG
+  const long long ti2 = clock64();
+  ctr_add(e, CT_CYC_NARROW, ti2 - ti1);
+#endif
   // phase 3: boxes of rotated outlines, NaN / inf classification (lane = slot)
   for (int s = e.lane; s < e.S; s += 32) {
     const int flag = e.sflag[s] >> 8;
@@ -2239,7 +2272,18 @@ __device__ inline void integrate_all(const Env &e) {
     e.sflag[s] = low;
   }
   wsync();
+#ifdef MOOG_PROFILE_INTEG
+  ctr_add(e, CT_CYC_RESOLVE, clock64() - ti2);
+#endif
 }
+
+// out of line, with its own view of the env: the pass keeps its pointers in registers instead of
+// sharing the register file with everything apply_physics inlines
+__device__ __noinline__ void integrate_all_ol() {
+  const Env e = env_view();
+  integrate_all_impl(e);
+}
+__device__ __forceinline__ void integrate_all(const Env &) { integrate_all_ol(); }
 
 // physics.py:88-117 Physics.apply_physics (one substep)
 __device__ inline void apply_physics(const Env &e, int n_cmask_words) {
@@ -3097,6 +3141,7 @@ __device__ __forceinline__ void owner_warp(const StepArgs &a, unsigned char *sme
       r->S = a.S; r->L = a.L; r->K = a.K; r->VT = a.VT;
       r->env_id = n;
       r->ops = pv.ops; r->ipool = pv.ipool; r->expr = pv.expr;
+      r->vmap = a.vmap;
       const int ND = pv.hdr[MOOG_H_NOISE_DIM], RND = pv.hdr[MOOG_H_RULE_NOISE_DIM];
       r->noise = a.io.noise ? a.io.noise + (size_t)n * a.K * ND : nullptr;
       r->rule_noise = a.io.rule_noise ? a.io.rule_noise + (size_t)n * RND : nullptr;
@@ -3108,6 +3153,10 @@ __device__ __forceinline__ void owner_warp(const StepArgs &a, unsigned char *sme
 
   // slot -> first cached vertex
   for (int s = lane; s <= e.S; s += 32) e.voff[s] = pv.voff[s];
+  if (a.vmap) {
+    uint16_t *vm = (uint16_t *)(base + lay.vmap);
+    for (int v = lane; v < a.VT; v += 32) vm[v] = a.vmap[v];
+  }
   wsync();
 
   if (lane == 0) {  // offsets of the candidate matrices of the Collision entries
