@@ -1,12 +1,23 @@
-# the other BASELINE configs through bench.py (not the headline line): device-resident + e2e
-run() { python bench.py --no-clocks --no-cpu "$@" 2>gpurun_out/other.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print(json.dumps({'scene': d['config']['workload'], 'envs': d['config']['envs_per_gpu'], 'sprites': d['config']['sprites'], 'substeps': d['config']['substeps'], 'image': d['config']['image'], 'value': round(d['value']), 'e2e': round(d['e2e']['value']), 'step_ms': round(d['roofline']['kernel_ms'],3), 'render_ms': round(d['roofline']['render_kernel']['kernel_ms'],3), 'launch': d['config']['step_launch']}))" || tail -3 gpurun_out/other.err; }
-run --scene falling_balls20 --envs 4096
-run --scene falling_balls20 --envs 32768
-run --scene colliding_predators84 --envs 16384 --episode 200 --burn-in 60 --pool 512
-run --scene cleanup64 --envs 8192 --episode 200 --burn-in 60 --pool 256
-run --scene pacman64 --envs 8192 --episode 200 --burn-in 60 --pool 256
-run --scene synthetic32 --envs 4096 --episode 200 --burn-in 60
-run --scene synthetic32 --envs 65536 --episode 200 --burn-in 60 --pool 512
+# every BASELINE.json config through bench.py's own arms (same code path as the headline line):
+# one JSON line per scene -> profiles/r02_other_scenes.jsonl
+OUT=${OUT:-gpurun_out/r02_other_scenes.jsonl}
+: > $OUT
+run() { python bench.py --no-clocks "$@" 2>gpurun_out/other.err >> $OUT || { echo "FAILED: $@"; tail -5 gpurun_out/other.err; }; }
+run --scene falling_balls20
+run --scene falling_balls20 --envs 32768 --no-cpu
+run --scene colliding_predators84
+run --scene cleanup64
+run --scene pacman64
+run --scene synthetic32
+run --scene synthetic32 --state-only
+run --scene synthetic32 --envs 4096 --no-cpu
+python - <<'PY'
+import json, os
+for line in open(os.environ.get('OUT', 'gpurun_out/r02_other_scenes.jsonl')):
+    d = json.loads(line)
+    c = d['config']
+    print('%-22s %6d envs %-10s value %9.0f e2e %9.0f (one step per call %9.0f) step %.3f ms render %s ms cpu %s launch %s' % (
+        c['workload'], c['envs_per_gpu'], c['image'], d['value'], d['e2e']['value'], d['e2e_one_step_per_call']['value'],
+        d['roofline']['kernel_ms'], d['roofline']['render_kernel']['kernel_ms'],
+        round(d['cpu_baseline']['value']) if 'cpu_baseline' in d else '-', c['step_launch']))
+PY

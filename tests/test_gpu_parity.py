@@ -657,3 +657,54 @@ def test_frames_edge_cases():
         assert np.array_equal(got, ref), n
         bg = got[0 if n == 1 else 17]
         assert (bg == bg[0, 0]).all(), 'an env without sprites shows the background colour only'
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('frames', ['mapped', 'device'])
+def test_host_pipeline_delivers_the_same_timesteps(frames):
+    """`HostPipeline` (step k+1 enqueued before the host reads step k, TimeSteps in pinned host
+    slots) against plain `BatchedEnvironment.step` on a twin environment: every TimeStep of 40
+    steps identical, auto-resets included, whichever way the frames travel, at depth 1, 2 and 3."""
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment
+    from moog_b200.configs import colliding_predators84
+    cfg = colliding_predators84.get_config(dict(image_size=(64, 64)))
+    np.random.seed(8)
+    states = [cfg['state_initializer']() for _ in range(6)]
+    N = 1500
+    rng = np.random.RandomState(0)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, size=(N, 2))).pin_memory() for _ in range(40)]
+    ref_env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=21, initial_states=states)
+    ref_env.engine.state.envi[:, 0] = 0
+    ref = []
+    ref_env.reset()
+    ref_env.engine.state.envi[:, 0] = torch.arange(N, device='cuda:0', dtype=torch.int32) % 190   # time-outs at every step
+    for a in acts:
+        ts = ref_env.step(a)
+        ref.append((ts.step_type.cpu().clone(), ts.reward.cpu().clone(), ts.discount.cpu().clone(),
+                    ts.observation['image'].cpu().clone()))
+    assert any(int((r[0] == 0).sum()) > 0 for r in ref[1:]), 'auto-resets happen inside the run'
+    for depth in (1, 2, 3):
+        env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=21, initial_states=states)
+        env.reset()
+        env.engine.state.envi[:, 0] = torch.arange(N, device='cuda:0', dtype=torch.int32) % 190
+        pipe = env.host_pipeline(depth=depth, frames=frames)
+        got = []
+        scratch = torch.empty_like(acts[0]).pin_memory()
+        for k, a in enumerate(acts):
+            if k >= depth:
+                ts = pipe.collect()
+                got.append((ts.step_type.clone(), ts.reward.clone(), ts.discount.clone(), ts.observation['image'].clone()))
+            scratch.copy_(a)
+            pipe.submit(scratch)
+            scratch.fill_(7.0)          # the caller's buffer is free again as soon as submit returns
+        while len(got) < len(acts):
+            ts = pipe.collect()
+            got.append((ts.step_type.clone(), ts.reward.clone(), ts.discount.clone(), ts.observation['image'].clone()))
+        for k, (r, g2) in enumerate(zip(ref, got)):
+            assert torch.equal(r[0], g2[0]), (depth, k, 'step_type')
+            for i in (1, 2):
+                assert torch.equal(torch.nan_to_num(r[i], nan=-7.), torch.nan_to_num(g2[i], nan=-7.)), (depth, k, i)
+            assert torch.equal(r[3], g2[3]), (depth, k, 'frames')
+        with pytest.raises(RuntimeError):
+            pipe.collect()
