@@ -50,9 +50,9 @@ def main():
     t0 = time.perf_counter()
     r = subprocess.run([sys.executable, 'runtime_benchmark.py', '--config=moog_demos.example_configs.pong'],
                        cwd=os.path.join(REF, 'tests'), env=env, capture_output=True, text=True, timeout=3600)
-    text = r.stdout + r.stderr
+    text = r.stdout if r.returncode == 0 else r.stdout + r.stderr      # (stderr holds tqdm's progress bars)
     out['runtime_benchmark_pong'] = {'seconds': time.perf_counter() - t0, 'returncode': r.returncode,
-                                     'output': [l for l in text.splitlines() if l.strip()][-40:]}
+                                     'output': [l for l in text.splitlines() if l.strip() and '%|' not in l][-60:]}
     scene, steps = 'falling_balls20', int(os.environ.get('REF_STEPS', '100'))
     workers = os.cpu_count() or 1
     t0 = time.perf_counter()
