@@ -677,6 +677,7 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     _compile_render(prog, config.get('observers', {}))
     if reset_sampler:
         _compile_reset_sampler(prog, config['state_initializer'])
+    _emit_shape_table_if_needed(prog, sample_states, reset_sampler)
     _check_outline_caps(prog)
     return prog.finalize()
 
@@ -739,6 +740,32 @@ def _lower_distribution(dist):
             raise CompileError('{} against anything but a box of Continuous factors is not on the device sampler'.format(k))
         return {}, [('filtered', base, [(key, v[1], v[2]) for key, v in box.items()], k == 'Selection')]
     return _flatten_distribution(dist), []
+
+
+def _emit_shape_table_if_needed(prog, sample_states, reset_sampler):
+    """A modifier that assigns `scale` / `aspect_ratio` makes the device re-derive the sprite's outline
+    from its shape (sprite.py:411-424): the COM-centred unit outlines of every shape the sample states
+    show go into the blob (shape records, MOOG_H_SHAPE_TAB), and pack_states numbers the sprites'
+    shapes by that table."""
+    reshaping = {lambdas.ATTRS.index(a) for a in lambdas.RESHAPING}
+    needs = any(op == lambdas.X_STORE and arg in reshaping for op, arg, _ in prog.expr)
+    prog.shape_table = None
+    if not needs:
+        return
+    if reset_sampler:
+        raise CompileError('rules that assign scale / aspect_ratio are not combined with the device reset sampler yet')
+    table = ShapeTable()
+    for st in sample_states:
+        for name in prog.layer_names:
+            for sp in st[name]:
+                table.add(sp._shape_path.vertices[:-1])  # pylint: disable=protected-access
+    shape_off = []
+    for verts, nv in zip(table.verts, table.nv):
+        shape_off.append(len(prog.dpool))
+        prog.dpool.extend([float(nv), 0.0, 0.0, 0.0, 0.0, 0.0] + [float(v) for v in verts[:nv].reshape(-1)])
+    prog.shape_tab = prog.add_ints(shape_off)
+    prog.shape_table = table
+    prog.n_table_shapes = len(table.nv)
 
 
 def _shape_record(shape):
@@ -1001,6 +1028,9 @@ def pack_states(prog, states, shape_table=None):
     mass, scale, aspect_ratio, color, opacity, shape, max_radius and the
     private `_shape_path.vertices` / `_x_y_rotational_inertia`.
     """
+    fixed_table = getattr(prog, 'shape_table', None)
+    if fixed_table is not None and shape_table is None:
+        shape_table = fixed_table
     table = ShapeTable() if shape_table is None else shape_table
     n, S, L = len(states), prog.n_slots, prog.n_layers
     dyn = np.zeros((n, DYN_FIELDS, S))
@@ -1036,6 +1066,10 @@ def pack_states(prog, states, shape_table=None):
                                  float(sp.opacity))
                 base = sp._shape_path.vertices[:-1]  # pylint: disable=protected-access
                 meta[e, 0, s] = table.add(base)
+                if fixed_table is not None and table is fixed_table and meta[e, 0, s] >= prog.n_table_shapes:
+                    raise CompileError(
+                        'a sprite of layer {!r} has a shape no sample state showed at compile time; rules that '
+                        'assign scale / aspect_ratio need every shape in the program\'s shape table'.format(name))
                 meta[e, 1, s] = _sprite_flags(sp)
                 world = np.asarray(sp.vertices, dtype=np.float64)
                 if len(world) > prog.layer_vcap[l]:

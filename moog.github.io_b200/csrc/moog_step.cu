@@ -146,6 +146,7 @@ struct Env {
   const int32_t *ipool;
   const moog_ex *expr;
   const uint16_t *vmap;      // program constant: cached vertex -> slot << 8 | index in the outline
+  const double *dpool;       // shape records / reset-sampler parameters of the blob
   int S, L, K, VT, lane;
   const double *noise;       // [K][noise_dim] of this env or nullptr
   const double *rule_noise;  // [rule_noise_dim] of this env or nullptr
@@ -170,6 +171,7 @@ struct EnvRec {
   const moog_ex *expr;
   const double *noise, *rule_noise;
   const uint16_t *vmap;
+  const double *dpool;
   uint64_t seed;
 };
 static_assert(sizeof(EnvRec) <= 224, "EnvRec must fit its shared-memory slot");
@@ -206,6 +208,7 @@ __device__ __forceinline__ Env env_view() {
   e.mbar = (unsigned long long *)(base + r->lay.mbar);
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
   e.vmap = r->vmap ? (const uint16_t *)(base + r->lay.vmap) : nullptr;
+  e.dpool = r->dpool;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x & 31;
   e.noise = r->noise; e.rule_noise = r->rule_noise;
@@ -1951,7 +1954,7 @@ unwind:
 }
 
 // sprite.py:531-540 angle setter (`sprite.angle = a`, a an np.float64): rotate_around(x, y, a - angle)
-__device__ inline void set_angle_f64(const Env &e, int s, double a) {
+__device__ inline void set_angle_f64(const Env &e, int s, double a, int kind = KIND_F64) {
   Aff mtx = aff_identity();
   aff_rotate_around(mtx, DYN(e, MOOG_D_X, s), DYN(e, MOOG_D_Y, s), a - DYN(e, MOOG_D_ANG, s));
   const int n = META(e, MOOG_M_NV, s);
@@ -1982,7 +1985,7 @@ __device__ inline void set_angle_f64(const Env &e, int s, double a) {
   const bool steep = __any_sync(FULL, st) != 0;
   if (e.lane == 0) {
     DYN(e, MOOG_D_ANG, s) = a;
-    META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (KIND_F64 << MOOG_SF_ANG_SHIFT);
+    META(e, MOOG_M_FLAGS, s) = (META(e, MOOG_M_FLAGS, s) & ~(3 << MOOG_SF_ANG_SHIFT)) | (kind << MOOG_SF_ANG_SHIFT);
     e.sflag[s] = (e.sflag[s] & SLF_SHORT_EDGE) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0) |
                  (steep ? SLF_STEEP : 0);
     store_box(e, s, xmin, ymin, xmax, ymax, nonfinite, steep);
@@ -2321,6 +2324,72 @@ __device__ inline void apply_physics(const Env &e, int n_cmask_words) {
 #endif
 }
 
+// sprite.py:411-424 Sprite._set_path, what the `scale` / `aspect_ratio` setters (:546-558) call:
+// the outline is re-derived from the COM-centred shape (shape record of the blob) by
+//   Affine2D().scale(s, s * aspect) + Affine2D().rotate(angle) + Affine2D().translate(*position)
+// (two 3x3 numpy products, then x' = m00 x + m01 y + m02 unfused), the circumscribed radius is
+// re-measured and the rotational inertia multiplied by the squared scales -- again on every call:
+// the reference's inertia compounds.  Lane = vertex; box and flags of the slot are rebuilt.
+__device__ __noinline__ void set_path(const Env &, int s) {
+  const Env e = env_view();
+  const int32_t *shape_off = e.ipool + e.hdr[MOOG_H_SHAPE_TAB];
+  const double *R = e.dpool + shape_off[META(e, MOOG_M_SHAPE, s)];
+  const int nv = (int)R[0];
+  const double sx = STAT(e, MOOG_S_SCALE, s), sy = STAT(e, MOOG_S_SCALE, s) * STAT(e, MOOG_S_ASPECT, s);
+  const double px = DYN(e, MOOG_D_X, s), py = DYN(e, MOOG_D_Y, s);
+  Aff S = {1.0 * sx, 0.0 * sx, 0.0 * sx, 0.0 * sy, 1.0 * sy, 0.0 * sy};
+  Aff Rm = aff_identity();
+  aff_rotate(Rm, DYN(e, MOOG_D_ANG, s));
+  Aff T = aff_identity();
+  aff_translate(T, px, py);
+  const Aff M = aff_then(aff_then(S, Rm), T);
+  double2 *v = e.vtx + e.voff[s];
+  wsync();
+  double r = -INFINITY;
+  bool rnan = false;
+  double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  bool fin = true, nan_all = true;
+  for (int i = e.lane; i < nv; i += 32) {
+    const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
+    const double2 q = make_double2(M.m0 * bx + M.m1 * by + M.m2, M.m3 * bx + M.m4 * by + M.m5);
+    v[i] = q;
+    const double d = norm_ax(q.x - px, q.y - py);
+    rnan |= isnan(d);
+    r = fmax(r, d);
+    fin &= isfinite(q.x) && isfinite(q.y);
+    nan_all &= isnan(q.x) && isnan(q.y);
+    xmin = fmin(xmin, q.x); xmax = fmax(xmax, q.x);
+    ymin = fmin(ymin, q.y); ymax = fmax(ymax, q.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r = fmax(r, shflx_d(r, o));
+    xmin = fmin(xmin, shflx_d(xmin, o)); xmax = fmax(xmax, shflx_d(xmax, o));
+    ymin = fmin(ymin, shflx_d(ymin, o)); ymax = fmax(ymax, shflx_d(ymax, o));
+  }
+  if (__any_sync(FULL, rnan)) r = NAN;  // np.max propagates a NaN
+  const bool nonfinite = !__all_sync(FULL, fin);
+  const bool allnan = nv > 0 && __all_sync(FULL, nan_all);
+  wsync();
+  bool st = false, sh = nv < 3;
+  for (int i = e.lane; i < nv; i += 32) {
+    const double2 p = v[i], q = v[(i + 1 == nv) ? 0 : i + 1];
+    st |= steep_edge(p.x, q.x);
+    sh |= !((q.x - p.x) * (q.x - p.x) + (q.y - p.y) * (q.y - p.y) > SHORT_EDGE2);
+  }
+  const bool steep = __any_sync(FULL, st) != 0, shortedge = __any_sync(FULL, sh) != 0;
+  if (e.lane == 0) {
+    META(e, MOOG_M_NV, s) = nv;
+    STAT(e, MOOG_S_MAXR, s) = r;
+    STAT(e, MOOG_S_IX, s) = STAT(e, MOOG_S_IX, s) * (sx * sx);
+    STAT(e, MOOG_S_IY, s) = STAT(e, MOOG_S_IY, s) * (sy * sy);
+    e.sflag[s] = (shortedge ? SLF_SHORT_EDGE : 0) | (nonfinite ? SLF_NONFINITE : 0) | (allnan ? SLF_ALLNAN : 0) |
+                 (steep ? SLF_STEEP : 0);
+    store_box(e, s, xmin, ymin, xmax, ymax, nonfinite, steep);
+  }
+  wsync();
+}
+
 // ---------------------------------------------------------------------------
 // expression VM (config lambdas compiled by the host)
 // ---------------------------------------------------------------------------
@@ -2374,9 +2443,14 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
       }
       case MOOG_X_STORE: {
         double v = st[--sp];
+        if (x->arg == MOOG_AT_ANGLE) {  // sprite.py:531-540; x->c: NumPy kind of the assigned value
+          set_angle_f64(e, s0, v, (int)x->c);
+          break;
+        }
         wsync();
         put(e, attr_ptr(e, s0, x->arg), v);
         wsync();
+        if (x->arg == MOOG_AT_SCALE || x->arg == MOOG_AT_ASPECT_RATIO) set_path(e, s0);
         break;
       }
       default:
@@ -3142,6 +3216,7 @@ __device__ __forceinline__ void owner_warp(const StepArgs &a, unsigned char *sme
       r->env_id = n;
       r->ops = pv.ops; r->ipool = pv.ipool; r->expr = pv.expr;
       r->vmap = a.vmap;
+      r->dpool = pv.dpool;
       const int ND = pv.hdr[MOOG_H_NOISE_DIM], RND = pv.hdr[MOOG_H_RULE_NOISE_DIM];
       r->noise = a.io.noise ? a.io.noise + (size_t)n * a.K * ND : nullptr;
       r->rule_noise = a.io.rule_noise ? a.io.rule_noise + (size_t)n * RND : nullptr;

@@ -32,8 +32,11 @@ import numpy as np
 
 ATTRS = ('x', 'y', 'x_vel', 'y_vel', 'angle', 'angle_vel', 'mass', 'scale',
          'aspect_ratio', 'c0', 'c1', 'c2', 'opacity')
+# `scale` / `aspect_ratio` assignments re-derive the outline from the shape (sprite.py:546-558 ->
+# _set_path :411-424, inertia compounding included), `angle` rotates the cached outline (:531-540)
 _WRITABLE = ('x_vel', 'y_vel', 'angle_vel', 'mass', 'c0', 'c1', 'c2',
-             'opacity')
+             'opacity', 'scale', 'aspect_ratio', 'angle')
+RESHAPING = ('scale', 'aspect_ratio')
 
 
 class LoweringError(ValueError):
@@ -465,7 +468,10 @@ def compile_modifier(fn):
         if name == 'position':
             code += value[0].code + value[1].code + [(X_STORE_POS, 0, 0.0)]
             continue
-        code += value.code + [(X_STORE, ATTRS.index(name), 0.0)]
+        # c: NumPy kind of the stored value as far as the device tracks it (angle: a pure constant is a
+        # python float, anything computed from sprite factors counts as np.float64)
+        has_attr = any(op in (X_ATTR0, X_ATTR1) for op, _, _ in value.code)
+        code += value.code + [(X_STORE, ATTRS.index(name), 2.0 if has_attr else 0.0)]
     # Leave a value on the stack so the VM has a defined result.
     return code + [(X_CONST, 0, 1.0)]
 

@@ -85,6 +85,9 @@ SCENES = {
     # pairwise Gravity (incl. its dist == 0 branch), KineticFriction (rest / infinite mass / overshoot),
     # DistanceForce(spring_force_fn), TetherZippedLayers (both modes), SetPosition with inertia
     'forces_zoo': ('moog_b200.configs.forces_zoo', None, 15, 40, 5),
+    # modifiers assigning scale / aspect_ratio / angle: the outline is rebuilt from the shape and the
+    # rotational inertia compounds (sprite.py:411-424, 516-558)
+    'reshape_zoo': ('moog_b200.configs.reshape_zoo', None, 16, 40, 5),
 }
 
 

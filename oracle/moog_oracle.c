@@ -138,6 +138,7 @@ typedef struct {
   double *envf;
   double *vtx;          /* [VT][2] cached world vertices of this env */
   const int32_t *voff;  /* [S+1] first vertex of each slot          */
+  const double *dpool;  /* shape records / sampler parameters       */
   const double *noise; /* [K][noise_dim] uniforms in [0,1) for this step, or NULL */
   int substep;
   /* instrumentation for parity tests */
@@ -164,6 +165,7 @@ static void bind_program(env_t *e, const void *blob) {
   e->expr = (const moog_ex *)(e->ipool + npool);
   e->S = hdr[MOOG_H_N_SLOTS];
   e->voff = e->ipool + hdr[MOOG_H_VOFF];
+  e->dpool = (const double *)(e->expr + hdr[MOOG_H_N_EXPR]);
   e->L = hdr[MOOG_H_N_LAYERS];
   e->K = hdr[MOOG_H_K];
 }
@@ -1428,6 +1430,43 @@ static double py_fmod(double a, double b) {
   return r;
 }
 
+/* sprite.py:411-424 Sprite._set_path, what the `scale` / `aspect_ratio` setters (:546-558) call: the
+ * outline is re-derived from the COM-centred shape (shape record of the blob),
+ *   Affine2D().scale(s, s * aspect) + Affine2D().rotate(angle) + Affine2D().translate(*position),
+ * the circumscribed radius is re-measured and the rotational inertia is multiplied by the square
+ * of the scales -- AGAIN, on every call: the inertia compounds (Appendix A2 of SURVEY.md). */
+static void set_path(env_t *e, int s) {
+  const int32_t *shape_off = e->ipool + e->hdr[MOOG_H_SHAPE_TAB];
+  const double *R = e->dpool + shape_off[META(e, MOOG_M_SHAPE, s)];
+  const int nv = (int)R[0];
+  const double sx = STAT(e, MOOG_S_SCALE, s), sy = STAT(e, MOOG_S_SCALE, s) * STAT(e, MOOG_S_ASPECT, s);
+  const double px = DYN(e, MOOG_D_X, s), py = DYN(e, MOOG_D_Y, s);
+  double S[9], Rm[9], T[9], SR[9], M[9];
+  aff_identity(S);
+  S[0] *= sx; S[1] *= sx; S[2] *= sx;
+  S[3] *= sy; S[4] *= sy; S[5] *= sy;
+  aff_identity(Rm);
+  aff_rotate(Rm, DYN(e, MOOG_D_ANG, s));
+  aff_identity(T);
+  aff_translate(T, px, py);
+  aff_then(S, Rm, SR);
+  aff_then(SR, T, M);
+  double *v = e->vtx + 2 * (size_t)e->voff[s];
+  double r = -INFINITY;
+  for (int i = 0; i < nv; ++i) {
+    const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
+    const double wx = M[0] * bx + M[1] * by + M[2], wy = M[3] * bx + M[4] * by + M[5];
+    v[2 * i] = wx;
+    v[2 * i + 1] = wy;
+    const double d = norm_ax(wx - px, wy - py);
+    if (d > r || isnan(d)) r = d; /* np.max propagates NaN */
+  }
+  META(e, MOOG_M_NV, s) = nv;
+  STAT(e, MOOG_S_MAXR, s) = r;
+  STAT(e, MOOG_S_IX, s) *= sx * sx;
+  STAT(e, MOOG_S_IY, s) *= sy * sy;
+}
+
 /* Runs the postfix program at `start`; returns top of stack (or 1.0 when start < 0). */
 static double eval_expr(env_t *e, int start, int s0, int s1) {
   if (start < 0) return 1.0;
@@ -1442,7 +1481,17 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
       case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
       case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
       case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
-      case MOOG_X_STORE: *attr_ptr(e, s0, x->arg) = st[--sp]; break;
+      case MOOG_X_STORE: {
+        const double v = st[--sp];
+        if (x->arg == MOOG_AT_ANGLE) { /* sprite.py:531-540; x->c: kind of the assigned value */
+          set_angle(e, s0, v, 0);
+          set_ang_kind(e, s0, (int)x->c);
+        } else {
+          *attr_ptr(e, s0, x->arg) = v;
+          if (x->arg == MOOG_AT_SCALE || x->arg == MOOG_AT_ASPECT_RATIO) set_path(e, s0);
+        }
+        break;
+      }
       case MOOG_X_STORE_POS: {
         double ny = st[--sp], nx = st[--sp];
         set_position(e, s0, nx, ny);
