@@ -758,7 +758,7 @@ def _emit_shape_table_if_needed(prog, sample_states, reset_sampler):
     for st in sample_states:
         for name in prog.layer_names:
             for sp in st[name]:
-                table.add(sp._shape_path.vertices[:-1])  # pylint: disable=protected-access
+                table.add(sp._shape_path.vertices[:-1], getattr(sp, 'shape', None))  # pylint: disable=protected-access
     shape_off = []
     for verts, nv in zip(table.verts, table.nv):
         shape_off.append(len(prog.dpool))
@@ -989,8 +989,9 @@ class ShapeTable(object):
         self._index = {}
         self.verts = []
         self.nv = []
+        self.names = []     # Sprite.shape of the first sprite that showed the outline ('square', ..., 'custom')
 
-    def add(self, outline):
+    def add(self, outline, name=None):
         outline = np.ascontiguousarray(outline, dtype=np.float64)
         key = outline.tobytes()
         sid = self._index.get(key)
@@ -1007,6 +1008,7 @@ class ShapeTable(object):
             padded[:n] = outline
             self.verts.append(padded)
             self.nv.append(n)
+            self.names.append(name if isinstance(name, str) else 'custom')
             self._index[key] = sid
         return sid
 
@@ -1065,7 +1067,7 @@ def pack_states(prog, states, shape_table=None):
                                  float(col[1]), float(col[2]),
                                  float(sp.opacity))
                 base = sp._shape_path.vertices[:-1]  # pylint: disable=protected-access
-                meta[e, 0, s] = table.add(base)
+                meta[e, 0, s] = table.add(base, getattr(sp, 'shape', None))
                 if fixed_table is not None and table is fixed_table and meta[e, 0, s] >= prog.n_table_shapes:
                     raise CompileError(
                         'a sprite of layer {!r} has a shape no sample state showed at compile time; rules that '

@@ -261,3 +261,49 @@ def test_cuda_reference_termination_timing_and_simulation_kat():
     run_to_reward(sim.sim_step, kat.SIM_REWARD_1)
     run_to_reward(sim.step, kat.SIM_ACTIONS)      # the real steps start from the state before any simulated one
     assert sim.stack_depth == 0
+
+
+@pytest.mark.gpu
+def test_cuda_logger_writes_the_reference_wire_format(tmp_path):
+    """`BatchedLoggingEnvironment` against tests/golden/logger_sim_timing.json, which is what the
+    UNMODIFIED reference's LoggingEnvironment wrote for the same environment and actions
+    (oracle/gen_golden_logger.py; moog/env_wrappers/logger.py:134-224): same files, same step
+    records -- reward (None on FIRST), step_type, action, layers, the 15 factors of every sprite,
+    vertices on the steps the reference logs them -- for every logged env of the batch."""
+    import json
+    import os
+    import torch
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment
+    from moog_b200.env_wrappers import BatchedLoggingEnvironment
+    gold = json.load(open(os.path.join(util.GOLDEN, 'logger_sim_timing.json')))
+    N = 5
+    env = BatchedEnvironment(**kat.simulation_timing_config(), num_envs=N, device='cuda:0', seed=0, pool_size=2)
+    log = BatchedLoggingEnvironment(env, log_dir=str(tmp_path), log_vertices='WHEN_NECESSARY', envs=(0, 3))
+    act = lambda a: torch.full((N, 1), float(a), dtype=torch.float64)
+    log.reset()
+    for _ in range(3):
+        for a in kat.SIM_ACTIONS:
+            log.step(act(a))
+        log.step(act(4))
+    for n in (0, 3):
+        d = os.path.join(log.log_dir, 'env_%d' % n)
+        assert json.load(open(os.path.join(d, 'attributes.txt'))) == gold['attributes']
+        assert open(os.path.join(d, 'description.txt')).read() == gold['description']
+        files = sorted(f for f in os.listdir(d) if f.isdigit())
+        assert files == ['%05d' % i for i in range(len(gold['episodes']))]
+        for fn, ref_ep in zip(files, gold['episodes']):
+            ep = json.load(open(os.path.join(d, fn)))
+            assert len(ep) == len(ref_ep), fn
+            for k, (step, ref) in enumerate(zip(ep, ref_ep)):
+                assert [x[0] for x in step[:5]] == ['time', 'reward', 'step_type', 'action', 'meta_state']
+                assert step[1] == ref[1] and step[2] == ref[2] and step[3] == ref[3] and step[4] == ref[4], (fn, k)
+                assert [l[0] for l in step[5]] == [l[0] for l in ref[5]], 'layers'
+                for layer, ref_layer in zip(step[5], ref[5]):
+                    assert len(layer[1]) == len(ref_layer[1])
+                    for sp, ref_sp in zip(layer[1], ref_layer[1]):
+                        assert len(sp) == len(ref_sp), (fn, k, 'vertices are logged on the same steps')
+                        assert sp[:14] == ref_sp[:14], (fn, k, sp[:14], ref_sp[:14])
+                        assert sp[14] is None          # metadata
+                        if len(sp) == 17:
+                            assert np.allclose(np.array(sp[16]), np.array(ref_sp[16]), rtol=0, atol=1e-15)
