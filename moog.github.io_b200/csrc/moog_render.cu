@@ -21,7 +21,7 @@
 namespace moog {
 
 // blockDim.x = envs_per_block * T, T = threads of one env (>= H, multiple of 32)
-__global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int P) {
+__global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int P, int band) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ProgramView pv = view_of(a.blob);
   const int32_t *hdr = pv.hdr;
@@ -31,7 +31,7 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
   const int n = blockIdx.x * envs_per_block + g;
   const bool live = n < a.n_envs;
   const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;
-  const RenderLayout lay = render_layout(aa * OH, aa * OW, S * C, (VT > 0 ? VT : 1) * C, OW);
+  const RenderLayout lay = render_layout(band > 0 ? band : aa * OH, aa * OW, S * C, (VT > 0 ? VT : 1) * C, OW);
   const size_t row = live ? (size_t)n : 0;
   RenderSrc src;
   src.dyn = a.st.dyn + row * MOOG_DYN_FIELDS * S;
@@ -42,7 +42,7 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
   src.hdr = hdr;
   src.voff = pv.voff;
   render_env(src, lay, smem_raw + (size_t)g * lay.total, nullptr, t, T, P, live,
-             a.frames + row * OH * OW * 3, a.resample, a.ksize_h, a.ksize_v, [] { __syncthreads(); });
+             a.frames + row * OH * OW * 3, a.resample, a.ksize_h, a.ksize_v, [] { __syncthreads(); }, band);
 }
 
 // The same for the envs of a step kernel that is still running (launched behind it with
@@ -51,7 +51,7 @@ __global__ void moog_render_kernel(RenderArgs a, int T, int envs_per_block, int 
 // thread 0 waits for entry b of the step kernel's finished list (acquire; the step kernel releases
 // it after the env's record is in HBM).  Every env it could wait for is running or done, so the
 // wait is bounded by the step itself; the poll limit only turns a broken launch into an error.
-__global__ void moog_render_tail_kernel(RenderArgs a, int T, int P, const int *done) {
+__global__ void moog_render_tail_kernel(RenderArgs a, int T, int P, const int *done, int band) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_env;
   if (threadIdx.x == 0) {
@@ -71,7 +71,7 @@ __global__ void moog_render_tail_kernel(RenderArgs a, int T, int P, const int *d
   const int S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
   const int OH = hdr[MOOG_H_R_HEIGHT], OW = hdr[MOOG_H_R_WIDTH], aa = hdr[MOOG_H_R_AA];
   const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;
-  const RenderLayout lay = render_layout(aa * OH, aa * OW, S * C, (VT > 0 ? VT : 1) * C, OW);
+  const RenderLayout lay = render_layout(band > 0 ? band : aa * OH, aa * OW, S * C, (VT > 0 ? VT : 1) * C, OW);
   const size_t row = (size_t)n;
   RenderSrc src;
   src.dyn = a.st.dyn + row * MOOG_DYN_FIELDS * S;
@@ -84,7 +84,7 @@ __global__ void moog_render_tail_kernel(RenderArgs a, int T, int P, const int *d
   unsigned long long tr0 = 0;
   if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
   render_env(src, lay, smem_raw, nullptr, (int)threadIdx.x, T, P, true, a.frames + row * OH * OW * 3, a.resample,
-             a.ksize_h, a.ksize_v, [] { __syncthreads(); });
+             a.ksize_h, a.ksize_v, [] { __syncthreads(); }, band);
   if (a.trace && threadIdx.x == 0) {
     unsigned long long tr1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr1));
@@ -100,7 +100,8 @@ __global__ void moog_render_tail_kernel(RenderArgs a, int T, int P, const int *d
 // CTA takes none while its own SM is still stepping envs (sm_active, kept by the step kernel) -- a
 // renderer next to a long-running env slows down exactly the env the whole step is waiting for.
 // The frames are drawn on the SMs the step has left, the last env's by whichever CTA is free.
-__global__ void moog_render_tail_persistent_kernel(RenderArgs a, int T, int P, int *done, int n_done, int busy_thr) {
+__global__ void moog_render_tail_persistent_kernel(RenderArgs a, int T, int P, int *done, int n_done, int busy_thr,
+                                                   int band) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_env;
   int *ticket = done + 1 + n_done;
@@ -112,7 +113,7 @@ __global__ void moog_render_tail_persistent_kernel(RenderArgs a, int T, int P, i
   const int S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
   const int OH = hdr[MOOG_H_R_HEIGHT], OW = hdr[MOOG_H_R_WIDTH], aa = hdr[MOOG_H_R_AA];
   const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;
-  const RenderLayout lay = render_layout(aa * OH, aa * OW, S * C, (VT > 0 ? VT : 1) * C, OW);
+  const RenderLayout lay = render_layout(band > 0 ? band : aa * OH, aa * OW, S * C, (VT > 0 ? VT : 1) * C, OW);
   bool last = false;
   for (;;) {
     if (threadIdx.x == 0) {
@@ -156,7 +157,7 @@ __global__ void moog_render_tail_persistent_kernel(RenderArgs a, int T, int P, i
     unsigned long long tr0 = 0;
     if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
     render_env(src, lay, smem_raw, nullptr, (int)threadIdx.x, T, P, true, a.frames + row * OH * OW * 3, a.resample,
-               a.ksize_h, a.ksize_v, [] { __syncthreads(); });
+               a.ksize_h, a.ksize_v, [] { __syncthreads(); }, band);
     __syncthreads();
     if (a.trace && threadIdx.x == 0) {
       unsigned long long tr1;
@@ -229,10 +230,19 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
   if (a.n_envs <= 0) return cudaSuccess;
   const int OH = hdr[MOOG_H_R_HEIGHT], OW = hdr[MOOG_H_R_WIDTH], aa = hdr[MOOG_H_R_AA];
   const int H = aa * OH, W = aa * OW, S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
-  const int P = (H <= 128) ? 2 : 1;  // threads per canvas row (they split its columns)
-  const int T = (H * P + 31) & ~31;
   const int C = hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_TORUS ? 9 : 1;  // TorusGeometry: 9 copies per sprite
-  RenderLayout lay = render_layout(H, W, S * C, (VT > 0 ? VT : 1) * C, OW);
+  // A canvas that does not fit next to the edge lists in one CTA's shared memory is drawn in bands
+  // of `band` rows (render_env): the largest band, a multiple of 8 rows, whose layout leaves room
+  // for two CTAs per SM.  Anti-aliased canvases are not banded (the Lanczos resize reads across rows).
+  int band = 0;
+  if (aa == 1 && render_layout(H, W, S * C, (VT > 0 ? VT : 1) * C, OW).total > 110 * 1024) {
+    band = H & ~7;
+    while (band > 8 && render_layout(band, W, S * C, (VT > 0 ? VT : 1) * C, OW).total > 110 * 1024) band -= 8;
+  }
+  const int HB = band > 0 ? band : H;
+  const int P = (HB <= 128) ? 2 : 1;  // threads per canvas row (they split its columns)
+  const int T = (HB * P + 31) & ~31;
+  RenderLayout lay = render_layout(HB, W, S * C, (VT > 0 ? VT : 1) * C, OW);
   // envs per CTA: the split that keeps the most envs resident per SM (228 KB of shared
   // memory, 1 KB of it reserved per CTA); ties go to the larger CTA
   int epb = 1;
@@ -300,15 +310,15 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
       int busy_thr = 1;  // envs being stepped on an SM from which its render CTAs stand back
       const char *b = getenv("MOOG_TAIL_BUSY_THR");
       if (b && atoi(b) > 0) busy_thr = atoi(b);
-      err = cudaLaunchKernelEx(&cfg, moog_render_tail_persistent_kernel, a, T, P, done, n_done, busy_thr);
+      err = cudaLaunchKernelEx(&cfg, moog_render_tail_persistent_kernel, a, T, P, done, n_done, busy_thr, band);
     } else {
-      err = cudaLaunchKernelEx(&cfg, moog_render_tail_kernel, a, T, P, (const int *)done);
+      err = cudaLaunchKernelEx(&cfg, moog_render_tail_kernel, a, T, P, (const int *)done, band);
     }
     if (n_launches) *n_launches += 1;
     return err;
   }
   int blocks = (a.n_envs + epb - 1) / epb;
-  moog_render_kernel<<<blocks, epb * T, smem, stream>>>(a, T, epb, P);
+  moog_render_kernel<<<blocks, epb * T, smem, stream>>>(a, T, epb, P, band);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

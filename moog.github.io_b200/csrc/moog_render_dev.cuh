@@ -311,10 +311,15 @@ struct RenderSrc {
 // CTA group that shares `base` calls it with the same arguments; `sync` is a barrier over exactly
 // those threads).  base: lay.total bytes of shared memory; ext_items: where the item spans go when
 // lay.items < 0.  P threads share a canvas row.  out: [OH][OW][3] bytes of this env's frame.
+// HB (0 = the whole canvas): rows per band.  A canvas that does not fit one CTA's shared memory
+// (the shipped pacman draws 256 x 256, tests/runtime_benchmark.py up to 1024 x 1024) is drawn in
+// bands of HB rows: `lay` is then the layout of an HB-row canvas, the edge lists are built once and
+// every band scan-converts, fills and writes out its own rows (anti_aliasing 1 only: the Lanczos
+// resize needs the rows around a band).
 template <class Sync>
 __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLayout &lay, unsigned char *base,
                                            unsigned *ext_items, int t, int T, int P, bool live, unsigned char *out,
-                                           const int *resample, int ksize_h, int ksize_v, Sync sync) {
+                                           const int *resample, int ksize_h, int ksize_v, Sync sync, int HB = 0) {
   const int32_t *hdr = src.hdr;
   const int S = hdr[MOOG_H_N_SLOTS], L = hdr[MOOG_H_N_LAYERS], VT = hdr[MOOG_H_N_VTX];
   // pil_renderer.py:65-66: the canvas is anti_aliasing x the image size
@@ -338,8 +343,8 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
   const int32_t *meta = src.meta, *cnt = src.cnt;
   const double2 *vtx = src.vtx;
 
+  if (HB <= 0 || HB > H || aa > 1) HB = H;
   if (live) {
-    for (int i = t; i < H * stride; i += T) canvas[i] = bgc;
     double ox = 0, oy = 0;
     if (pmod == MOOG_PMOD_FIRST_PERSON) {  // polygon_modifiers.py:54-63
       int s = hdr[MOOG_H_LAYER_OFF + pml];
@@ -385,6 +390,11 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
     }
   }
   sync();  // the scan below reads every slot's extents
+#pragma unroll 1
+  for (int y0 = 0; y0 < H; y0 += HB) {
+  const int y1 = min(H, y0 + HB);  // this band: canvas rows [y0, y1)
+  if (live)
+    for (int i = t; i < (y1 - y0) * stride; i += T) canvas[i] = bgc;
   // (sprite, row) item ranges: exclusive prefix sum of the visible rows per slot by the first
   // warp; when the items do not all fit (lay.cap) thread 0 assigns them greedily instead and
   // the sprites left without a range are scan-converted by the row threads directly
@@ -395,7 +405,7 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
       int rows = 0;
       if (vs < S * C) {
         // Draw.c polygon_generic: ymin = max(ymin, 0); ymax = min(ymax, H); rows >= H are clipped by hline
-        const int lo = max(symin[vs], 0), hi = min(symax[vs], H - 1);
+        const int lo = max(symin[vs], y0), hi = min(symax[vs], y1 - 1);
         rows = hi >= lo ? hi - lo + 1 : 0;
       }
       int x = rows;
@@ -412,7 +422,7 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
       if (acc > lay.cap) {
         acc = 0;
         for (int s = 0; s < S * C; ++s) {
-          const int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
+          const int lo = max(symin[s], y0), hi = min(symax[s], y1 - 1);
           const int rows = hi >= lo ? hi - lo + 1 : 0;
           if (rows > 0 && acc + rows <= lay.cap) {
             sibase[s] = acc;
@@ -435,12 +445,12 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
       for (;;) {
         int b0 = sibase[s];
         if (b0 >= 0) {
-          int lo = max(symin[s], 0), hi = min(symax[s], H - 1);
+          int lo = max(symin[s], y0), hi = min(symax[s], y1 - 1);
           if (it < b0 + (hi - lo + 1)) break;
         }
         ++s;
       }
-      const int lo = max(symin[s], 0);
+      const int lo = max(symin[s], y0);
       const int y = lo + (it - sibase[s]);
       SpanSink sink;
       sink.item = items + (size_t)it * (1 + ITEM_SPANS);
@@ -453,10 +463,11 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
   sync();
   // phase 2: P threads per row, sprites in z-order
   if (live) {
-    for (int w = t; w < H * P; w += T) {
-      const int part = w / H, y = w - part * H;
+    const int HBn = y1 - y0;
+    for (int w = t; w < HBn * P; w += T) {
+      const int part = w / HBn, y = y0 + (w - part * HBn);
       const int xlo = (W * part) / P, xhi = (W * (part + 1)) / P - 1;  // P threads share a row
-      unsigned *row = canvas + y * stride;
+      unsigned *row = canvas + (y - y0) * stride;
       for (int s = 0; s < S * C; ++s) {
         const int ymin_c = max(symin[s], 0), ymax_c = min(symax[s], H);
         if (y < ymin_c || y > ymax_c) continue;
@@ -466,7 +477,7 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
         unsigned cntw = ITEM_OVERFLOW;
         const unsigned *item = nullptr;
         if (b0 >= 0) {
-          item = items + (size_t)(b0 + (y - ymin_c)) * (1 + ITEM_SPANS);
+          item = items + (size_t)(b0 + (y - max(ymin_c, y0))) * (1 + ITEM_SPANS);
           cntw = item[0];
         }
         if (cntw != ITEM_OVERFLOW) {
@@ -540,15 +551,19 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
   }
   if (live) {
     // pil_renderer.py:118-120: np.flipud -> output row j is image row OH-1-j
+    // (a band holds the image rows [y0, y1), i.e. the output rows [OH - y1, OH - y0); with
+    // anti-aliasing there is one band and the resized image starts at row 0)
+    const int r0 = aa > 1 ? 0 : y0, r1 = aa > 1 ? OH : y1;
     if ((OW & 15) == 0) {
       // consecutive threads store consecutive 16-byte chunks of the frame (a row is OW * 3 / 16
       // of them); packed word m = 3u + r of a row holds bytes r.. of pixel 4u + r and the first
       // bytes of the next pixel
       uint4 *out4 = (uint4 *)out;
       const int cpr = (OW * 3) >> 4;
-      for (int q = t; q < OH * cpr; q += T) {
+      for (int q0 = t; q0 < (r1 - r0) * cpr; q0 += T) {
+        const int q = q0 + (OH - r1) * cpr;
         const int j = q / cpr, c = q - j * cpr;
-        const unsigned *srcp = img + (OH - 1 - j) * img_stride;
+        const unsigned *srcp = img + (OH - 1 - j - r0) * img_stride;
         unsigned w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -559,13 +574,16 @@ __device__ __forceinline__ void render_env(const RenderSrc &src, const RenderLay
         out4[q] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     } else {
-      const int nbytes = OH * OW * 3;
-      for (int b = t; b < nbytes; b += T) {
+      const int nbytes = (r1 - r0) * OW * 3;
+      for (int b0 = t; b0 < nbytes; b0 += T) {
+        const int b = b0 + (OH - r1) * OW * 3;
         int p = b / 3, ch = b - 3 * p;
         int j = p / OW, col = p - j * OW;
-        out[b] = (unsigned char)((img[(OH - 1 - j) * img_stride + col] >> (8 * ch)) & 255u);
+        out[b] = (unsigned char)((img[(OH - 1 - j - r0) * img_stride + col] >> (8 * ch)) & 255u);
       }
     }
+  }
+  if (y0 + HB < H) sync();  // the next band reuses the canvas and the item spans
   }
 }
 

@@ -170,6 +170,20 @@ def _aa_renderers(renderer):
     return out
 
 
+BIG_SCENES = ('pong', 'colliding_predators')
+BIG_SIZES = ((256, 256), (512, 512), (136, 200))      # (width, height); 64 x 64 x ... does not fit one CTA beyond ~128^2
+
+
+def _big_renderers(renderer):
+    """The scene's PILRenderer again at canvas sizes that exceed one CTA's shared memory (the shipped
+    pacman draws 256 x 256, tests/runtime_benchmark.py times up to 1024 x 1024)."""
+    from moog.observers import pil_renderer
+    return {size: pil_renderer.PILRenderer(
+        image_size=size, anti_aliasing=1, bg_color=renderer._canvas_bg.getpixel((0, 0)),  # pylint: disable=protected-access
+        color_to_rgb=renderer.color_to_rgb, polygon_modifier=renderer._polygon_modifier)  # pylint: disable=protected-access
+        for size in BIG_SIZES}
+
+
 def generate(name, out_dir):
     module, level, seed, T, frame_every = SCENES[name]
     np.random.seed(seed)
@@ -266,11 +280,16 @@ def generate(name, out_dir):
     frames, frame_steps = [], []
     aa_r = _aa_renderers(renderer) if (renderer is not None and name in AA_SCENES) else {}
     aa_frames = {aa: [] for aa in aa_r}
+    big_r = _big_renderers(renderer) if (renderer is not None and name in BIG_SCENES and
+                                          os.environ.get('MOOG_GOLDEN_BIG_ONLY')) else {}
+    big_frames = {size: [] for size in big_r}
     if renderer is not None:
         frames.append(np.asarray(ts.observation['image']))
         frame_steps.append(-1)
         for aa, r in aa_r.items():
             aa_frames[aa].append(np.asarray(r(env.state)))
+        for size, r in big_r.items():
+            big_frames[size].append(np.asarray(r(env.state)))
     K, nd = prog.K, prog.noise_dim
     for t in range(T):
         if name == 'cleanup':
@@ -332,6 +351,9 @@ def generate(name, out_dir):
             frame_steps.append(t)
             for aa, r in aa_r.items():
                 aa_frames[aa].append(np.asarray(r(env.state)))
+            if t % (3 * frame_every) == 0:
+                for size, r in big_r.items():
+                    big_frames[size].append(np.asarray(r(env.state)))
         if ts.last():
             break
 
@@ -351,6 +373,19 @@ def generate(name, out_dir):
     for k, v in rec.items():
         out[k] = np.array(v)
     path = os.path.join(out_dir, name + '.npz')
+    if os.environ.get('MOOG_GOLDEN_BIG_ONLY'):
+        # big-canvas frames only, for states the main fixture already holds
+        assert big_r, name
+        prev = np.load(path)
+        assert np.array_equal(prev['frames'], out['frames']) and np.array_equal(prev['dyn'], out['dyn']), \
+            'the trajectory changed; regenerate the main fixture first'
+        steps = [-1] + [t for t in out['frame_steps'][1:] if t % (3 * frame_every) == 0]
+        path = os.path.join(out_dir, name + '_big.npz')
+        np.savez_compressed(path, frame_steps=np.array(steps, dtype=np.int32),
+                            **{'frames_%dx%d' % size: np.array(v, dtype=np.uint8) for size, v in big_frames.items()})
+        print('{:22s} {} big-canvas frames x {} -> {} ({} KB)'.format(name, len(steps), list(big_frames), path,
+                                                                    os.path.getsize(path) // 1024))
+        return
     if os.environ.get('MOOG_GOLDEN_AA_ONLY'):
         # anti-aliased frames only, for the states the main fixture already holds
         assert aa_r, name

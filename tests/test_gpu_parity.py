@@ -184,6 +184,31 @@ def test_cuda_render_matches_reference_antialiased_frames(scene, aa):
     assert bad == 0, (scene, aa, bad)
 
 
+@pytest.mark.parametrize('size', util.BIG_SIZES)
+@pytest.mark.parametrize('scene', util.BIG_SCENES)
+def test_cuda_render_matches_reference_big_frames(scene, size):
+    """Canvases that do not fit one CTA's shared memory are drawn in bands of rows (render_env):
+    256 x 256 (the shipped pacman's size), 512 x 512 and a non-square 136 x 200 canvas against
+    frames recorded from the reference's PILRenderer; through `moog_render` and through the step
+    call's `frames`."""
+    g = util.load_golden(scene)
+    gb = util.load_golden_big(scene)
+    prog = util.with_image_size(g, *size)
+    parts = [util.state_at(g, int(t)) for t in gb['frame_steps']]
+    arrays = {k: np.concatenate([p[k] for p in parts], axis=0) for k in util.STATE_KEYS}
+    eng = _engine(prog, arrays)
+    ref = gb['frames_%dx%d' % size]
+    out = eng.render().cpu().numpy()
+    assert out.shape == ref.shape
+    assert int((out != ref).sum()) == 0, (scene, size)
+    # the step call's frames of the state it leaves the envs in == a render call afterwards
+    eng.frames.zero_()
+    eng.env_step(None, auto_reset=False, frames=True)
+    got = eng.frames.cpu().numpy().copy()
+    again = eng.render(out=torch.zeros_like(eng.frames)).cpu().numpy()
+    assert np.array_equal(got, again), (scene, size)
+
+
 @pytest.mark.gpu
 def test_render_env_ranges_and_step_to_host():
     """Frames rendered range by range equal the whole-batch render, and

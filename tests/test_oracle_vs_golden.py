@@ -69,6 +69,21 @@ def test_oracle_render_matches_reference_antialiased_frames(scene, aa):
         assert np.array_equal(out, f), (scene, aa, int(t), int((out != f).sum()))
 
 
+@pytest.mark.parametrize('size', util.BIG_SIZES)
+@pytest.mark.parametrize('scene', util.BIG_SCENES)
+def test_oracle_render_matches_reference_big_frames(scene, size):
+    """Canvases beyond one CTA's shared memory (the shipped pacman draws 256 x 256,
+    tests/runtime_benchmark.py:31-38 times 256 .. 1024), and a non-square one: frames recorded from
+    the reference renderer at those sizes."""
+    g = util.load_golden(scene)
+    gb = util.load_golden_big(scene)
+    prog = util.with_image_size(g, *size)
+    for f, t in zip(gb['frames_%dx%d' % size], gb['frame_steps']):
+        out = Oracle(prog, util.state_at(g, int(t))).render()[0]
+        assert out.shape == f.shape
+        assert np.array_equal(out, f), (scene, size, int(t), int((out != f).sum()))
+
+
 @pytest.mark.parametrize('scene', util.SCENES)
 def test_rows_of_a_collision_entry_commute(scene):
     """The rule the next kernel design rests on ("Next" (1)), checked on the reference's

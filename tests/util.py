@@ -177,3 +177,23 @@ def with_anti_aliasing(g, aa):
 
 def load_golden_aa(name):
     return dict(np.load(os.path.join(GOLDEN, name + '_aa.npz')))
+
+
+BIG_SCENES = ['pong', 'colliding_predators']
+BIG_SIZES = [(256, 256), (512, 512), (136, 200)]       # (width, height) as PILRenderer(image_size=...) takes them
+
+
+def with_image_size(g, width, height):
+    """The scene's program with PILRenderer(image_size=(width, height)): header words
+    MOOG_H_R_WIDTH / MOOG_H_R_HEIGHT of the stored blob patched (compiler.py writes them from
+    `renderer._image_size`)."""
+    from moog_b200 import compiler as C
+    blob = np.frombuffer(bytes(bytearray(g['blob'])), dtype=np.uint8).copy()
+    hdr = blob[:C.HDR_WORDS * 4].view('<i4')
+    hdr[C.H_R_WIDTH] = width
+    hdr[C.H_R_HEIGHT] = height
+    return ProgramStub(blob, g['layer_names'])
+
+
+def load_golden_big(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '_big.npz')))
