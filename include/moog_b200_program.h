@@ -78,6 +78,7 @@ enum { MOOG_M_SHAPE = 0, MOOG_M_FLAGS, MOOG_M_NV };
  * velocity is a float32 ndarray, a sampled angle_vel a float32 0-d array, and
  * the angle turns float32 with it.  kind: 0 python float, 1 float32, 2 float64. */
 #define MOOG_SF_VEL32 2
+#define MOOG_SF_TELEPORTING 64 /* Portal._currently_teleporting holds this sprite's id (portal.py:61-76) */
 #define MOOG_SF_ANGVEL_SHIFT 2 /* 2 bits */
 #define MOOG_SF_ANG_SHIFT 4    /* 2 bits */
 /* Velocity-array aliasing.  `Tether(update_angle_vel=False)` assigns ONE ndarray
@@ -170,6 +171,11 @@ enum {
                                     i2 envf slot of (steps_until_start, steps_until_stop), p0,p1 the interval
                                     they are reset to                                                   timing.py:15-107 */
   MOOG_R_KEEP_NEAR_CENTER,       /* i0 agent layer, i1,i2 list of the layers to move, p0,p1 grid cell    re_center.py:13-76 */
+  MOOG_R_PORTAL,                 /* i0 teleporting layer, i1 portal layer (paired in order); a sprite that has
+                                    teleported carries MOOG_SF_TELEPORTING until it is in no portal       portal.py:41-76 */
+  MOOG_R_CHANGE_LAYER,           /* i0 old layer, i1 new layer, i2 filter expr (-1: all): the flagged sprites
+                                    are appended to the new layer in order and popped from the old one
+                                                                                                 change_layer.py:34-45 */
 
   /* tasks: i[5] = envf slot of the countdown */
   MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps; p2 > 0: the
@@ -239,6 +245,7 @@ enum {
 #define MOOG_Z_N_ATTRS 14
 #define MOOG_Z_SHAPE_ATTR 13
 enum { MOOG_ZK_CONST = 0, MOOG_ZK_UNIFORM32 = 1, MOOG_ZK_DISCRETE = 2 };
+#define MOOG_ERR_PORTAL_ODD      64u /* portal.py:49-52 ValueError: odd number of portals */
 #define MOOG_ERR_RESET_REJECTED  32u /* sprite_generators.py:92-98 RecursionError (no room for a sprite) */
 
 /* Maze record in envf (maze_lib/maze.py:20-35, Maze.from_state :38-84, evaluated by the host when

@@ -41,7 +41,8 @@ _ERR_TEXT = {
     8: 'RuntimeError: layer capacity exceeded',
     16: 'ValueError: Object is not on the maze grid (maze_physics.py:93-104)',
     32: 'RecursionError: max_recursion_depth exceeded trying to initialize a non-overlapping sprite '
-        '(sprite_generators.py:92-98)',
+        '(sprite_generators.py:92-98) / ValueError: maximum number of tries exceeded (distributions.py:341-349)',
+    64: 'ValueError: There must be an even number of portals (portal.py:49-52)',
 }
 
 _STATE_DTYPES = dict(dyn=torch.float64, stat=torch.float64, meta=torch.int32,

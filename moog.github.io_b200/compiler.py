@@ -60,6 +60,7 @@ F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
 C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED, C_MAZE_PHYSICS = 32, 33, 34, 35
 R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
     R_MODIFY_SPRITES, R_COND_BEGIN, R_TIMED_BEGIN, R_KEEP_NEAR_CENTER = 64, 65, 66, 67, 68, 69, 70
+R_PORTAL, R_CHANGE_LAYER = 71, 72
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
@@ -541,6 +542,13 @@ def _rule_specs(prog, rule, out, depth=0):
             _rule_specs(prog, r, sub, depth + 1)
         out.append(dict(kind=R_TIMED_BEGIN, i=[0, len(sub), prog.alloc_envf(2)], p=draws[0]))
         out.extend(sub)
+    elif k == 'Portal':
+        out.append(dict(kind=R_PORTAL, i=(prog.layer_index(rule._teleporting_layer),
+                                          prog.layer_index(rule._portal_layer))))
+    elif k == 'ChangeLayer':
+        code = lambdas.compile_sprite_predicate(rule._filter_fn)
+        out.append(dict(kind=R_CHANGE_LAYER, i=(prog.layer_index(rule._old_layer), prog.layer_index(rule._new_layer),
+                                                prog.add_expr(code))))
     elif k == 'KeepNearCenter':
         layers = list(rule._layers_to_center)
         ls, ln = prog.add_list(layers)
@@ -550,6 +558,18 @@ def _rule_specs(prog, rule, out, depth=0):
     else:
         raise CompileError(
             'game rule {} is not on the accelerated path'.format(k))
+
+
+def _layer_moves(rules):
+    """(old_layer, new_layer) of every ChangeLayer rule, nested ones included."""
+    out = []
+    for r in (rules or ()):
+        k = _kind(r)
+        if k == 'ChangeLayer':
+            out.append((r._old_layer, r._new_layer))
+        elif hasattr(r, '_rules'):
+            out += _layer_moves(r._rules)
+    return out
 
 
 def _compile_rules(prog, rules):
@@ -649,6 +669,11 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
             raise CompileError('state initializer changed its layer set')
     caps = [max(len(st[name]) for st in sample_states)
             for name in prog.layer_names]
+    # ChangeLayer appends sprites of one layer to another (change_layer.py:34-45): the receiving layer
+    # gets room for every sprite that can arrive, and slots wide enough for their outlines
+    moves = _layer_moves(config.get('game_rules', ()))
+    for old, new in moves:
+        caps[prog.layer_names.index(new)] += caps[prog.layer_names.index(old)]
     for name, cap in (layer_capacity or {}).items():
         caps[prog.layer_index(name)] = max(cap, caps[prog.layer_index(name)])
     prog.layer_cap = [int(c) for c in caps]
@@ -663,6 +688,9 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
         raise CompileError(
             'a sprite outline has {} vertices; the device path supports at '
             'most {}'.format(max(vcap), MAX_OUTLINE))
+    for old, new in moves:
+        io, in_ = prog.layer_names.index(old), prog.layer_names.index(new)
+        vcap[in_] = max(vcap[in_], vcap[io])
     prog.layer_vcap = vcap
     voff = [0]
     for cap, vc in zip(caps, vcap):

@@ -2641,6 +2641,67 @@ __device__ __noinline__ void rule_leaf(const Env &, int r) {
       }
       return;
     }
+    case MOOG_R_PORTAL: {  // portal.py:41-76
+      const int la = op->i[0], lp = op->i[1], np_ = e.cnt[lp];
+      if (np_ & 1) {
+        const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_PORTAL_ODD;
+        wsync();
+        puti(e, &e.envi[MOOG_EI_ERR], err);
+        wsync();
+        return;
+      }
+      for (int i = 0; i < e.cnt[la]; ++i) {
+        const int s = LOFF(e, la) + i;
+        const double px = DYN(e, MOOG_D_X, s), py = DYN(e, MOOG_D_Y, s);
+        int first = -1;
+        for (int q = 0; q < np_; ++q) {  // in_portals: every portal is asked (sprite.py:432-440)
+          const int p = LOFF(e, lp) + q;
+          bool in;
+          if (is_symmetric_circle(e, p))
+            in = norm1(px - DYN(e, MOOG_D_X, p), py - DYN(e, MOOG_D_Y, p)) < STAT(e, MOOG_S_MAXR, p);
+          else
+            in = point_in_poly(px, py, e.vtx + e.voff[p], META(e, MOOG_M_NV, p));
+          if (in && first < 0) first = q;
+        }
+        const int fl = META(e, MOOG_M_FLAGS, s);
+        wsync();
+        if (first < 0) {
+          puti(e, &META(e, MOOG_M_FLAGS, s), fl & ~MOOG_SF_TELEPORTING);
+          wsync();
+          continue;
+        }
+        if (fl & MOOG_SF_TELEPORTING) continue;
+        const int ex = LOFF(e, lp) + ((first & 1) ? first - 1 : first + 1);
+        set_position(e, s, DYN(e, MOOG_D_X, ex), DYN(e, MOOG_D_Y, ex));
+        puti(e, &META(e, MOOG_M_FLAGS, s), fl | MOOG_SF_TELEPORTING);
+        wsync();
+      }
+      return;
+    }
+    case MOOG_R_CHANGE_LAYER: {  // change_layer.py:34-45
+      const int lo = op->i[0], ln = op->i[1], n = e.cnt[lo];
+      const int cap = LOFF(e, ln + 1) - LOFF(e, ln);
+      for (int w = 0; w < MOOG_MAX_SLOTS / 32; ++w) flag[w] = 0;
+      for (int i = 0; i < n; ++i)  // should_change is evaluated for every sprite before anything moves
+        if (op->i[2] < 0 || eval_expr(e, op->i[2], LOFF(e, lo) + i, LOFF(e, lo) + i) != 0) flag[i >> 5] |= 1u << (i & 31);
+      for (int i = 0; i < n; ++i) {
+        if (!((flag[i >> 5] >> (i & 31)) & 1u)) continue;
+        const int have = e.cnt[ln];
+        if (have >= cap) {
+          const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_LAYER_OVERFLOW;
+          wsync();
+          puti(e, &e.envi[MOOG_EI_ERR], err);
+          wsync();
+          flag[i >> 5] &= ~(1u << (i & 31));
+          continue;
+        }
+        copy_slot(e, LOFF(e, ln) + have, LOFF(e, lo) + i);
+        puti(e, &e.cnt[ln], have + 1);
+        wsync();
+      }
+      vanish(e, lo, flag);
+      return;
+    }
     case MOOG_R_VANISH_ON_CONTACT: {  // vanish.py:66-86, contact_rules.py:28-35
       int la = op->i[0], lb = op->i[1];
       for (int w = 0; w < MOOG_MAX_SLOTS / 32; ++w) flag[w] = 0;
@@ -3177,6 +3238,8 @@ __device__ inline void post_reset(const Env &e) {
         put(e, &e.envf[op->i[2]], op->p[0]);
         put(e, &e.envf[op->i[2] + 1], op->p[1]);
       }
+      if (op->kind == MOOG_R_PORTAL)  // portal.py:36-39: _currently_teleporting = set()
+        for (int s2 = e.lane; s2 < e.S; s2 += 32) META(e, MOOG_M_FLAGS, s2) &= ~MOOG_SF_TELEPORTING;
     }
     wsync();
   }

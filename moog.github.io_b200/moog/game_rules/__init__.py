@@ -4,8 +4,8 @@ On the hot path (lowered to device ops by moog_b200.compiler):
 `VanishOnContact`, `VanishByFilter`, `ModifyOnContact`, `ModifySprites`,
 `ConditionalRule`, plus the `get_contact_indices` / `get_contact_counter`
 condition builders, `TimedRule` / `DelayedRule` / `TemporaryRule` with fixed
-intervals and `KeepNearCenter`.  The remaining psychophysics trial-structure
-rules of the reference (Phase*, Fixation, Portal, CreateSprites, ...) are
+intervals, `KeepNearCenter`, `Portal` and `ChangeLayer`.  The remaining psychophysics trial-structure
+rules of the reference (Phase*, Fixation, CreateSprites, ...) are
 outside the accelerated path; constructing one raises so that a config never
 silently loses a rule.
 """
@@ -147,6 +147,26 @@ class KeepNearCenter(AbstractRule):
         self._grid_cell = np.array([grid_x, grid_x if grid_y is None else grid_y])
 
 
+class Portal(AbstractRule):
+    """A sprite of `teleporting_layer` whose position enters a portal sprite reappears at the
+    position of that portal's partner (portals are paired in order) and cannot teleport again
+    until it has left every portal (portal.py:14-76)."""
+
+    def __init__(self, teleporting_layer, portal_layer):
+        self._teleporting_layer = teleporting_layer
+        self._portal_layer = portal_layer
+
+
+class ChangeLayer(AbstractRule):
+    """Moves the sprites of `old_layer` that pass `filter_fn` to the end of `new_layer`
+    (change_layer.py:11-45)."""
+
+    def __init__(self, old_layer, new_layer, filter_fn=None):
+        self._old_layer = old_layer
+        self._new_layer = new_layer
+        self._filter_fn = filter_fn if filter_fn is not None else (lambda s: True)
+
+
 def _out_of_scope(name, where):
     def _ctor(*args, **kwargs):
         raise NotImplementedError(
@@ -157,12 +177,10 @@ def _out_of_scope(name, where):
     return _ctor
 
 
-ChangeLayer = _out_of_scope('ChangeLayer', 'change_layer.py')
 CreateSprites = _out_of_scope('CreateSprites', 'create_sprites.py')
 Fixation = _out_of_scope('Fixation', 'fixation.py')
 ModifyMetaState = _out_of_scope('ModifyMetaState', 'modify_meta_state.py')
 UpdateMetaStateValue = _out_of_scope(
     'UpdateMetaStateValue', 'modify_meta_state.py')
-Portal = _out_of_scope('Portal', 'portal.py')
 Phase = _out_of_scope('Phase', 'task_phases.py')
 PhaseSequence = _out_of_scope('PhaseSequence', 'task_phases.py')

@@ -88,6 +88,8 @@ SCENES = {
     # modifiers assigning scale / aspect_ratio / angle: the outline is rebuilt from the shape and the
     # rotational inertia compounds (sprite.py:411-424, 516-558)
     'reshape_zoo': ('moog_b200.configs.reshape_zoo', None, 16, 40, 5),
+    # Portal (square and circular portal pairs) and ChangeLayer into a layer that starts empty
+    'portal_zoo': ('moog_b200.configs.portal_zoo', None, 17, 45, 5),
 }
 
 
@@ -171,7 +173,7 @@ def _aa_renderers(renderer):
 
 
 BIG_SCENES = ('pong', 'colliding_predators')
-BIG_SIZES = ((256, 256), (512, 512), (136, 200))      # (width, height); 64 x 64 x ... does not fit one CTA beyond ~128^2
+BIG_SIZES = ((256, 256), (512, 512), (136, 200), (1024, 1024))      # (width, height); 64 x 64 x ... does not fit one CTA beyond ~128^2
 
 
 def _big_renderers(renderer):

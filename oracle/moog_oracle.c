@@ -1691,6 +1691,60 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
       }
       return 1;
     }
+    case MOOG_R_PORTAL: { /* portal.py:41-76 */
+      const int la = op->i[0], lp = op->i[1], np_ = e->cnt[lp];
+      if (np_ % 2 != 0) {
+        e->envi[MOOG_EI_ERR] |= MOOG_ERR_PORTAL_ODD;
+        return 1;
+      }
+      for (int i = 0; i < e->cnt[la]; ++i) {
+        const int s = LOFF(e, la) + i;
+        const double pt[2] = {DYN(e, MOOG_D_X, s), DYN(e, MOOG_D_Y, s)};
+        int first = -1;
+        for (int q = 0; q < np_; ++q) { /* in_portals: every portal is asked (sprite.py:432-440) */
+          const int p = LOFF(e, lp) + q;
+          int in;
+          if (is_symmetric_circle(e, p)) {
+            in = norm1(pt[0] - DYN(e, MOOG_D_X, p), pt[1] - DYN(e, MOOG_D_Y, p)) < STAT(e, MOOG_S_MAXR, p);
+          } else {
+            poly_t P;
+            uint8_t r;
+            world_path(e, p, &P);
+            orc_points_in_path(pt, 1, &P.v[0][0], P.n + 1, &r);
+            in = r;
+          }
+          if (in && first < 0) first = q;
+        }
+        if (first < 0) {
+          META(e, MOOG_M_FLAGS, s) &= ~MOOG_SF_TELEPORTING;
+          continue;
+        }
+        if (META(e, MOOG_M_FLAGS, s) & MOOG_SF_TELEPORTING) continue;
+        const int ex = LOFF(e, lp) + ((first % 2) ? first - 1 : first + 1);
+        set_position(e, s, DYN(e, MOOG_D_X, ex), DYN(e, MOOG_D_Y, ex));
+        META(e, MOOG_M_FLAGS, s) |= MOOG_SF_TELEPORTING;
+      }
+      return 1;
+    }
+    case MOOG_R_CHANGE_LAYER: { /* change_layer.py:34-45 */
+      const int lo = op->i[0], ln = op->i[1], n = e->cnt[lo];
+      const int cap = LOFF(e, ln + 1) - LOFF(e, ln);
+      uint8_t gone[MOOG_MAX_SLOTS];
+      for (int i = 0; i < n; ++i) /* should_change is evaluated for every sprite before anything moves */
+        gone[i] = op->i[2] < 0 || eval_expr(e, op->i[2], LOFF(e, lo) + i, LOFF(e, lo) + i) != 0;
+      for (int i = 0; i < n; ++i) {
+        if (!gone[i]) continue;
+        if (e->cnt[ln] >= cap) {
+          e->envi[MOOG_EI_ERR] |= MOOG_ERR_LAYER_OVERFLOW;
+          gone[i] = 0;
+          continue;
+        }
+        copy_slot(e, LOFF(e, ln) + e->cnt[ln], LOFF(e, lo) + i);
+        e->cnt[ln] += 1;
+      }
+      vanish(e, lo, gone);
+      return 1;
+    }
     case MOOG_R_COND_BEGIN: { /* conditional.py:55-58 */
       int times = (int)eval_condition(e, op->i[0]);
       int nsub = op->i[1];
@@ -1713,6 +1767,8 @@ static void rules_reset(env_t *e) {
       e->envf[op->i[2]] = op->p[0];
       e->envf[op->i[2] + 1] = op->p[1];
     }
+    if (op->kind == MOOG_R_PORTAL) /* portal.py:36-39: _currently_teleporting = set() */
+      for (int s2 = 0; s2 < e->S; ++s2) META(e, MOOG_M_FLAGS, s2) &= ~MOOG_SF_TELEPORTING;
   }
 }
 

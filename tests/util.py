@@ -9,7 +9,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 SCENES = ['pong', 'falling_balls', 'falling_balls20', 'colliding_predators',
           'predators_arena', 'synthetic32', 'falling_balls20_nan', 'cleanup',
           'chase_avoid_torus', 'pacman', 'timed_center', 'parallelogram_catch', 'forces_zoo',
-          'reshape_zoo']
+          'reshape_zoo', 'portal_zoo']
 # scenes whose step() uses no sin/cos of a non-zero angle: every operation on
 # the path is IEEE-exact (+ - * / sqrt fma), so the CUDA path must be bit-exact
 EXACT_SCENES = ['pong', 'falling_balls', 'falling_balls20', 'falling_balls20_nan']
@@ -117,6 +117,7 @@ def canonical_meta(meta, live):
     (tether_physics.py:86-91); which number a group carries is an implementation detail (the
     device hands out fresh ids every substep, a packed reference state numbers them per state)."""
     out = np.array(meta[:, live], dtype=np.int64)
+    out[1] &= ~64          # MOOG_SF_TELEPORTING: Portal's own bookkeeping (portal.py:36-76), not a sprite attribute
     ids = (out[1] >> 8) & 0x7fffff
     remap, nxt = {0: 0}, 0
     for k, i in enumerate(ids):
@@ -180,7 +181,7 @@ def load_golden_aa(name):
 
 
 BIG_SCENES = ['pong', 'colliding_predators']
-BIG_SIZES = [(256, 256), (512, 512), (136, 200)]       # (width, height) as PILRenderer(image_size=...) takes them
+BIG_SIZES = [(256, 256), (512, 512), (136, 200), (1024, 1024)]       # (width, height) as PILRenderer(image_size=...) takes them
 
 
 def with_image_size(g, width, height):
