@@ -40,7 +40,7 @@ SYMBOLS = ('moog_program_create', 'moog_program_destroy',
            'moog_render', 'moog_strerror', 'moog_last_cuda_error',
            'moog_launch_count', 'moog_host_paths_overlap',
            'moog_host_points_in_path', 'moog_step_launch_info',
-           'moog_step_draws_frames')
+           'moog_step_draws_frames', 'moog_program_set_option')
 
 
 class MoogError(RuntimeError):
@@ -96,6 +96,8 @@ def lib():
     L.moog_step_launch_info.restype = ci
     L.moog_step_draws_frames.argtypes = [vp, ci]
     L.moog_step_draws_frames.restype = ci
+    L.moog_program_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    L.moog_program_set_option.restype = ci
     L.moog_launch_count.argtypes = []
     L.moog_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -142,6 +144,10 @@ class DeviceProgram(object):
         if r < 0:
             check(r)
         return bool(r)
+
+    def set_option(self, name, value):
+        """One launch option of this program (include/moog_b200.h moog_program_set_option)."""
+        check(lib().moog_program_set_option(self._h, name.encode(), int(value)))
 
     def close(self):
         if self._h:

@@ -28,6 +28,7 @@ struct moog_program {
   // cached vertex -> (slot << 8 | index within the slot's outline), [VT]: the Euler pass of the step
   // kernel walks the vertex cache flat, lane = vertex
   uint16_t *dev_vmap;
+  moog::LaunchOptions opt;  // MOOG_* environment variables at creation time, then moog_program_set_option
 };
 
 namespace {
@@ -43,6 +44,37 @@ bool valid_state(const moog_state *st) {
   return st && st->dyn && st->stat && st->meta && st->cnt && st->envi && st->envf && st->vtx;
 }
 }  // namespace
+
+namespace moog {
+LaunchOptions launch_options_from_env() {
+  LaunchOptions o;
+  static const struct { const char *env, *name; } kVars[] = {
+      {"MOOG_HELPER", "helper"}, {"MOOG_CTAS_PER_SM", "ctas_per_sm"}, {"MOOG_SMEM_PAD", "smem_pad"},
+      {"MOOG_FUSED_RENDER", "fused_render"}, {"MOOG_TAIL_RENDER", "tail_render"},
+      {"MOOG_TAIL_CTAS_PER_SM", "tail_ctas_per_sm"}, {"MOOG_TAIL_BUSY_THR", "tail_busy_thr"},
+      {"MOOG_RENDER_EPB", "render_epb"}, {"MOOG_TRACE_TIMES", "trace_times"}};
+  for (const auto &v : kVars) {
+    const char *t = getenv(v.env);
+    if (t && *t) set_launch_option(o, v.name, atoi(t));
+  }
+  return o;
+}
+bool set_launch_option(LaunchOptions &o, const char *name, int value) {
+  if (!name) return false;
+  const std::string n(name);
+  if (n == "helper") o.helper = value;
+  else if (n == "ctas_per_sm") o.ctas_per_sm = value;
+  else if (n == "smem_pad") o.smem_pad = value;
+  else if (n == "fused_render") o.fused_render = value;
+  else if (n == "tail_render") o.tail_render = value;
+  else if (n == "tail_ctas_per_sm") o.tail_ctas_per_sm = value;
+  else if (n == "tail_busy_thr") o.tail_busy_thr = value;
+  else if (n == "render_epb") o.render_epb = value;
+  else if (n == "trace_times") o.trace_times = value;
+  else return false;
+  return true;
+}
+}  // namespace moog
 
 extern "C" {
 
@@ -62,6 +94,7 @@ int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
   moog_program *p = (moog_program *)calloc(1, sizeof(moog_program));
   if (!p) return MOOG_E_INVAL;
   memcpy(p->hdr, hdr, sizeof(p->hdr));
+  p->opt = moog::launch_options_from_env();
   p->hdr[MOOG_H_CMASK_WORDS] = moog::candidate_matrix_words(blob);
   {
     moog::ProgramView pv = moog::view_of(blob);
@@ -115,7 +148,7 @@ void moog_program_destroy(moog_program *p) {
 int moog_program_env_smem_bytes(const moog_program *p) { return p ? moog::env_smem_bytes(p->hdr) : MOOG_E_INVAL; }
 
 // envs resident per SM / helper warp for a batch of n_envs (see the comment in run_step)
-static void launch_policy(int n_envs, bool ordered, int *resident, bool *helper) {
+static void launch_policy(const moog::LaunchOptions &opt, int n_envs, bool ordered, int *resident, bool *helper) {
   *resident = 0;
   *helper = false;
   int dev = 0, sms = 0;
@@ -131,10 +164,13 @@ static void launch_policy(int n_envs, bool ordered, int *resident, bool *helper)
     *helper = *resident <= 6;
   }
   if (!ordered) *resident = 0;
-  const char *h = getenv("MOOG_HELPER");
-  if (h) *helper = atoi(h) != 0;
-  const char *c = getenv("MOOG_CTAS_PER_SM");
-  if (c && atoi(c) > 0) *resident = atoi(c);
+  if (opt.helper >= 0) *helper = opt.helper != 0;
+  if (opt.ctas_per_sm > 0) *resident = opt.ctas_per_sm;
+}
+
+int moog_program_set_option(moog_program *p, const char *name, int value) {
+  if (!p || !moog::set_launch_option(p->opt, name, value)) return MOOG_E_INVAL;
+  return 0;
 }
 
 int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_per_sm, int *warps_per_env,
@@ -142,7 +178,7 @@ int moog_step_launch_info(const moog_program *p, int n_envs, int *resident_envs_
   if (!p || n_envs < 0) return MOOG_E_INVAL;
   int resident = 0;
   bool helper = false;
-  launch_policy(n_envs, n_envs >= 1024, &resident, &helper);
+  launch_policy(p->opt, n_envs, n_envs >= 1024, &resident, &helper);
   if (resident_envs_per_sm) *resident_envs_per_sm = resident;
   if (warps_per_env) *warps_per_env = helper ? 2 : 1;
   if (smem_bytes_per_env) *smem_bytes_per_env = moog::env_smem_bytes(p->hdr, helper);
@@ -163,8 +199,8 @@ int moog_step_draws_frames(const moog_program *p, int n_envs) {
   if (!p || n_envs < 0) return MOOG_E_INVAL;
   int resident = 0;
   bool helper = false;
-  launch_policy(n_envs, n_envs >= 1024, &resident, &helper);
-  return moog::plan_step(p->hdr, resident, helper, frames_mode(n_envs)).fuse ? 1 : 0;
+  launch_policy(p->opt, n_envs, n_envs >= 1024, &resident, &helper);
+  return moog::plan_step(p->hdr, resident, helper, frames_mode(n_envs), p->opt).fuse ? 1 : 0;
 }
 
 static int render_impl(moog_program *p, const moog_state *st, int n_envs, uint8_t *frames, void *stream,
@@ -222,7 +258,7 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   // computes one of the two directions of _get_collision_vectors (MOOG_HELPER=0/1 overrides).
   int resident = 0;
   bool helper = false;
-  launch_policy(n_envs, a.order != nullptr, &resident, &helper);
+  launch_policy(p->opt, n_envs, a.order != nullptr, &resident, &helper);
   bool fused = false;
   if (a.io.frames && (mode != moog::MODE_ENV_STEP || !p->hdr[MOOG_H_R_ENABLED] || p->hdr[MOOG_H_R_AA] < 1))
     return MOOG_E_INVAL;
@@ -233,13 +269,9 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
   // draws the envs in the order they finish (the `done` list) on the SMs the step left idle
   // (MOOG_TAIL_RENDER=0: the render kernel waits for the whole step instead).
   bool tail = a.io.frames && a.order != nullptr &&
-              !moog::plan_step(p->hdr, resident, helper, fmode).fuse;
-  int tail_mode = 2;
-  {
-    const char *t = getenv("MOOG_TAIL_RENDER");
-    if (t) tail_mode = atoi(t);
-    if (tail_mode <= 0) tail = false;
-  }
+              !moog::plan_step(p->hdr, resident, helper, fmode, p->opt).fuse;
+  const int tail_mode = p->opt.tail_render;
+  if (tail_mode <= 0) tail = false;
   if (tail) {
     if (p->done_cap < n_envs) {
       if (p->done) cudaFree(p->done);
@@ -255,11 +287,8 @@ static int run_step(moog_program *p, const moog_state *st, int n_envs, int mode,
     a.done = p->done;
     if (tail_mode == 2) a.sm_active = p->done + 1 + n_envs + 1;
   }
-  {
-    const char *t = getenv("MOOG_TRACE_TIMES");  // diagnostic: per-env timeline in io.counters
-    a.trace = (t && atoi(t) != 0 && a.io.counters) ? 1 : 0;
-  }
-  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches, 0, -1, resident, helper, fmode, &fused);
+  a.trace = (p->opt.trace_times != 0 && a.io.counters) ? 1 : 0;  // diagnostic: per-env timeline in io.counters
+  err = moog::launch_step(a, p->hdr, (cudaStream_t)stream, &launches, 0, -1, resident, helper, fmode, &fused, p->opt);
   g_launches += launches;
   if (err != cudaSuccess) return cuda_fail(err);
   if (a.io.frames && !fused)
@@ -330,7 +359,7 @@ static int render_impl(moog_program *p, const moog_state *st, int n_envs, uint8_
     a.ksize_v = p->ksize_v;
   }
   int launches = 0;
-  cudaError_t err = moog::launch_render(a, p->hdr, (cudaStream_t)stream, &launches, done, n_envs, tail_mode);
+  cudaError_t err = moog::launch_render(a, p->hdr, (cudaStream_t)stream, &launches, done, n_envs, tail_mode, p->opt);
   g_launches += launches;
   return err == cudaSuccess ? 0 : cuda_fail(err);
 }

@@ -68,6 +68,22 @@ struct RenderArgs {
   int ksize_h, ksize_v;
 };
 
+// Launch options of one program (moog_program_set_option / the MOOG_* environment variables, which
+// are read ONCE, when the program is created).  -1 / 0 = decided by the library.
+struct LaunchOptions {
+  int helper = -1;            // "helper": second warp per env for one direction of _get_collision_vectors
+  int ctas_per_sm = 0;        // "ctas_per_sm": envs resident per SM (the shared-memory request is padded to cap it)
+  int smem_pad = 0;           // "smem_pad": bytes added to the request instead
+  int fused_render = -1;      // "fused_render": the step CTAs draw their env's frame themselves
+  int tail_render = 2;        // "tail_render": 0 render after the step, 1 / 2 behind it (programmatic launch; 2 persistent)
+  int tail_ctas_per_sm = 0;   // "tail_ctas_per_sm"
+  int tail_busy_thr = 1;      // "tail_busy_thr": envs stepped on an SM from which its render CTAs stand back
+  int render_epb = 0;         // "render_epb": envs per CTA of the stand-alone render kernel
+  int trace_times = 0;        // "trace_times": per-env globaltimer stamps in io.counters (diagnostic)
+};
+LaunchOptions launch_options_from_env();
+bool set_launch_option(LaunchOptions &o, const char *name, int value);
+
 // host-side launchers (defined in the .cu files)
 constexpr int kMaxForceOps = 32;
 int env_smem_bytes(const int32_t *hdr, bool helper = true);
@@ -78,18 +94,20 @@ int candidate_matrix_words(const void *host_blob);
 // _get_collision_vectors next to its owner
 struct StepPlan { size_t smem; bool fuse; int render_off; };
 // frames_mode: 0 no frames, 1 frames (fused only when MOOG_FUSED_RENDER=1), 2 frames, fused preferred
-StepPlan plan_step(const int32_t *host_hdr, int resident_envs_per_sm, bool helper, int frames_mode);
+StepPlan plan_step(const int32_t *host_hdr, int resident_envs_per_sm, bool helper, int frames_mode,
+                   const LaunchOptions &opt = LaunchOptions());
 // *fused (optional): whether the kernel also drew a.io.frames (else the caller runs launch_render)
 cudaError_t launch_step(const StepArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches,
                         int first = 0, int count = -1, int resident_envs_per_sm = 0, bool helper = false,
-                        int frames_mode = 0, bool *fused = nullptr);
+                        int frames_mode = 0, bool *fused = nullptr, const LaunchOptions &opt = LaunchOptions());
 cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream, int *n_launches);
 int resample_tables(int H, int W, int OH, int OW, std::vector<int> &table, int *ksize_h, int *ksize_v);
 // done: nullptr, or the finished-env list of the step kernel launched just before on `stream`
 // (StepArgs::done): the render kernel is then launched with programmatic stream serialization,
 // starts while the last envs are still being stepped and draws the envs in finishing order
 cudaError_t launch_render(const RenderArgs &a, const int32_t *host_hdr, cudaStream_t stream, int *n_launches,
-                          int *done = nullptr, int n_done = 0, int tail_mode = 1);
+                          int *done = nullptr, int n_done = 0, int tail_mode = 1,
+                          const LaunchOptions &opt = LaunchOptions());
 // ints behind the finished list that launch_render's tail kernels use: a ticket counter and the
 // per-SM count of envs being stepped
 constexpr int kTailExtraInts = 1 + 256;

@@ -226,7 +226,7 @@ int resample_tables(int H, int W, int OH, int OW, std::vector<int> &table, int *
 }
 
 cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches,
-                          int *done, int n_done, int tail_mode) {
+                          int *done, int n_done, int tail_mode, const LaunchOptions &opt) {
   if (a.n_envs <= 0) return cudaSuccess;
   const int OH = hdr[MOOG_H_R_HEIGHT], OW = hdr[MOOG_H_R_WIDTH], aa = hdr[MOOG_H_R_AA];
   const int H = aa * OH, W = aa * OW, S = hdr[MOOG_H_N_SLOTS], VT = hdr[MOOG_H_N_VTX];
@@ -254,8 +254,7 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
       const int envs = (int)(233472 / per_cta) * c;
       if (envs >= best) { best = envs; epb = c; }
     }
-    static const char *epb_env = getenv("MOOG_RENDER_EPB");
-    if (epb_env && atoi(epb_env) > 0) epb = atoi(epb_env);
+    if (opt.render_epb > 0) epb = opt.render_epb;
   }
   size_t smem = (size_t)lay.total * epb;
   if (smem > 224 * 1024 || T > 1024) return cudaErrorInvalidConfiguration;
@@ -302,14 +301,11 @@ cudaError_t launch_render(const RenderArgs &a, const int32_t *hdr, cudaStream_t 
       const int by_threads = 2048 / T;
       if (per_sm > by_threads) per_sm = by_threads;
       if (per_sm < 1) per_sm = 1;
-      const char *r = getenv("MOOG_TAIL_CTAS_PER_SM");
-      if (r && atoi(r) > 0 && atoi(r) < per_sm) per_sm = atoi(r);
+      if (opt.tail_ctas_per_sm > 0 && opt.tail_ctas_per_sm < per_sm) per_sm = opt.tail_ctas_per_sm;
       int grid = sms * per_sm;
       if (grid > n_done) grid = n_done;
       cfg.gridDim = dim3((unsigned)grid);
-      int busy_thr = 1;  // envs being stepped on an SM from which its render CTAs stand back
-      const char *b = getenv("MOOG_TAIL_BUSY_THR");
-      if (b && atoi(b) > 0) busy_thr = atoi(b);
+      const int busy_thr = opt.tail_busy_thr > 0 ? opt.tail_busy_thr : 1;  // envs being stepped on an SM from which its render CTAs stand back
       err = cudaLaunchKernelEx(&cfg, moog_render_tail_persistent_kernel, a, T, P, done, n_done, busy_thr, band);
     } else {
       err = cudaLaunchKernelEx(&cfg, moog_render_tail_kernel, a, T, P, (const int *)done, band);

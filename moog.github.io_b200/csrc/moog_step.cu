@@ -3536,20 +3536,18 @@ cudaError_t launch_order(const int *cost, int *order, int n, cudaStream_t stream
 }
 
 // Shared-memory request of one step CTA and whether the CTA also draws its env's frame.
-StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, int frames_mode) {
+StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, int frames_mode, const LaunchOptions &opt) {
   StepPlan plan;
   size_t smem = (size_t)env_smem_bytes(hdr, helper);
   {
     // Resident CTAs (= envs) per SM.  The step is bound by its longest-running env, and a
     // warp runs ~2.4x slower next to 11 others than alone (profiles/README.md), so beyond
     // the point where every SM has work, fewer co-resident envs finish the step sooner.  The
-    // dynamic shared-memory request is padded to cap the residency (MOOG_CTAS_PER_SM
-    // overrides; MOOG_SMEM_PAD=<bytes> pads directly).
-    const char *pad = getenv("MOOG_SMEM_PAD");
-    const char *cps = getenv("MOOG_CTAS_PER_SM");
-    int target = cps ? atoi(cps) : resident_envs_per_sm;
-    if (pad) {
-      smem += (size_t)atoi(pad);
+    // dynamic shared-memory request is padded to cap the residency (option "ctas_per_sm"
+    // overrides; "smem_pad" = <bytes> pads directly).
+    const int target = opt.ctas_per_sm > 0 ? opt.ctas_per_sm : resident_envs_per_sm;
+    if (opt.smem_pad > 0) {
+      smem += (size_t)opt.smem_pad;
     } else if (target > 0) {
       size_t per_cta = (size_t)233472 / (size_t)target;  // 228 KB per SM, 1 KB of it reserved per CTA
       if (per_cta > 1024 + smem) smem = ((per_cta - 1024) & ~(size_t)127);
@@ -3562,7 +3560,7 @@ StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, in
   // launch, no second pass over the state), 1 = frames wanted but the render kernel is the better
   // choice: measured on 4096 falling_balls20 envs, two warps per env drawing between the steps of
   // their neighbours cost more (6.0 ms) than the render kernel behind the step (4.3 + 0.55 ms).
-  // MOOG_FUSED_RENDER=0 never fuses, =1 fuses whenever one CTA can hold a canvas.
+  // Option "fused_render" = 0 never fuses, = 1 fuses whenever one CTA can hold a canvas.
   plan.render_off = 0;
   plan.fuse = false;
   if (frames_mode > 0 && hdr[MOOG_H_R_ENABLED] && hdr[MOOG_H_R_AA] == 1) {
@@ -3574,9 +3572,8 @@ StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, in
                                           hdr[MOOG_H_R_WIDTH], 16 * VTr);
     plan.render_off = (sl.scratch + 15) & ~15;  // everything from the warps' scratch on is dead after the step
     const size_t need = (size_t)plan.render_off + (size_t)rl.total;
-    const char *fr = getenv("MOOG_FUSED_RENDER");
     bool want = frames_mode == 2;
-    if (fr) want = atoi(fr) != 0;
+    if (opt.fused_render >= 0) want = opt.fused_render != 0;
 #ifdef MOOG_NO_FUSED_RENDER
     want = false;
 #endif
@@ -3590,12 +3587,13 @@ StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, in
 }
 
 cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stream, int *n_launches, int first,
-                        int count, int resident_envs_per_sm, bool helper, int frames_mode, bool *fused) {
+                        int count, int resident_envs_per_sm, bool helper, int frames_mode, bool *fused,
+                        const LaunchOptions &opt) {
   if (fused) *fused = false;
   if (count < 0) count = a.n_envs - first;
   if (a.n_envs <= 0 || count <= 0) return cudaSuccess;
   const StepPlan plan = plan_step(hdr, resident_envs_per_sm, helper,
-                                  a.io.frames != nullptr && a.mode == MODE_ENV_STEP ? frames_mode : 0);
+                                  a.io.frames != nullptr && a.mode == MODE_ENV_STEP ? frames_mode : 0, opt);
   const size_t smem = plan.smem;
   const bool fuse = plan.fuse;
   const int render_off = plan.render_off;

@@ -455,16 +455,16 @@ def test_full_size_batch_is_independent_of_the_launch_mode(monkeypatch):
     arrays = {k: np.ascontiguousarray(pool[k][idx]) for k in util.STATE_KEYS}
     arrays['dyn'][:, 2, 4:24] += (np.arange(N)[:, None] % 89) * 1e-5
     engines = []
-    for helper, cps in (('1', '4'), ('0', '12')):
+    for helper, cps in ((1, 4), (0, 12)):
         eng = Engine(prog, N, 'cuda:0')
+        eng.dev_program.set_option('helper', helper)
+        eng.dev_program.set_option('ctas_per_sm', cps)
         eng.state.upload(arrays)
         eng.post_reset()
         engines.append((eng, helper, cps))
     actions = np.zeros((N, max(prog.action_dim, 1)))
     for step in range(40):
         for eng, helper, cps in engines:
-            monkeypatch.setenv('MOOG_HELPER', helper)
-            monkeypatch.setenv('MOOG_CTAS_PER_SM', cps)
             eng.env_step(actions, auto_reset=False, want_counters=True)
         if step % 10 == 9:
             a, b = engines[0][0], engines[1][0]
