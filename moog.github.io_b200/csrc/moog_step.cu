@@ -81,7 +81,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.stat = o;  o += 8 * MOOG_STAT_FIELDS * S;
   L.aabb = o;  o += 8 * 4 * S;
   L.vtx = o;   o += 16 * VT;     // 16-byte aligned: everything before it is a multiple of 16
-  L.tmp = o;   o += 8 * 3 * S;  // tether scratch (3 fields)
+  L.tmp = -1;  // tether scratch (3 fields) / per-slot translations of the Euler pass: placed below
   L.envf = o;  o += 8 * NF;
   L.ctr = o;   o += 8 * 12;
   L.meta = o;  o += 4 * MOOG_META_FIELDS * S;
@@ -96,14 +96,23 @@ __host__ __device__ inline SmemLayout smem_layout(int S, int VT, int NF, int CMW
   L.nearp = o; o += CMW > 0 ? 4 * NEAR_CAP : 4;
   L.hdr = o;   o += 4 * MOOG_HDR_WORDS;
   L.scratch = o; o += 64 * warps;  // one per warp (owner, helper)
-  o = (o + 7) & ~7;
+  o = (o + 15) & ~15;
   L.xchg = o;  o += 128;                  // main <-> helper: request words, the helper's CVec
   L.mbar = o;  o += 16;                   // mbarrier of the bulk (TMA) loads of the record
   L.tile = tile;
   L.plist = o; o += CMW > 0 ? 2 * 32 * tile * warps : 8;  // crossing (vertex, edge) pairs, per warp
   L.kscr_bytes = CMW > 0 ? 8 * 32 * tile : 8;
   L.kscr = o;  o += L.kscr_bytes * warps;
-  L.vmap = o;  o += 2 * VT;  // cached vertex -> slot << 8 | index within the outline (integrate_all)
+  // the tether / Euler-pass scratch is never live together with a directed search: it shares the
+  // owner's key tile when it fits there
+  if (8 * 3 * S <= L.kscr_bytes) {
+    L.tmp = L.kscr;
+  } else {
+    o = (o + 15) & ~15;
+    L.tmp = o;
+    o += 8 * 3 * S;
+  }
+  L.vmap = o;  o += VT;  // cached vertex -> slot (integrate_all)
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -145,7 +154,7 @@ struct Env {
   const moog_op *ops;
   const int32_t *ipool;
   const moog_ex *expr;
-  const uint16_t *vmap;      // program constant: cached vertex -> slot << 8 | index in the outline
+  const uint8_t *vmap;       // program constant: cached vertex -> slot
   const double *dpool;       // shape records / reset-sampler parameters of the blob
   int S, L, K, VT, lane;
   const double *noise;       // [K][noise_dim] of this env or nullptr
@@ -170,7 +179,7 @@ struct EnvRec {
   const int32_t *ipool;
   const moog_ex *expr;
   const double *noise, *rule_noise;
-  const uint16_t *vmap;
+  const uint16_t *vmap;      // (global memory; staged into shared memory as one byte per vertex)
   const double *dpool;
   uint64_t seed;
 };
@@ -207,7 +216,7 @@ __device__ __forceinline__ Env env_view() {
   e.dcv_tile = r->lay.tile;
   e.mbar = (unsigned long long *)(base + r->lay.mbar);
   e.ops = r->ops; e.ipool = r->ipool; e.expr = r->expr;
-  e.vmap = r->vmap ? (const uint16_t *)(base + r->lay.vmap) : nullptr;
+  e.vmap = r->vmap ? (const uint8_t *)(base + r->lay.vmap) : nullptr;
   e.dpool = r->dpool;
   e.S = r->S; e.L = r->L; e.K = r->K; e.VT = r->VT;
   e.lane = threadIdx.x & 31;
@@ -2204,8 +2213,9 @@ __device__ __forceinline__ void integrate_all_impl(const Env &e) {
   if (e.vmap) {
     const unsigned *smask = (const unsigned *)e.scratch;
     const double2 *tt = (const double2 *)e.tmp;
-    const uint16_t *vmap = e.vmap;
+    const uint8_t *vmap = e.vmap;
     const int *nvs = &META(e, MOOG_M_NV, 0);
+    const int *voffs = e.voff;
     double2 *vtx = e.vtx;
     const int VT = e.VT, S = e.S;
     // four vertices per lane and trip, every load issued before the first use and no branch but
@@ -2213,7 +2223,7 @@ __device__ __forceinline__ void integrate_all_impl(const Env &e) {
 #pragma unroll 1
     for (int v0 = e.lane; v0 < VT; v0 += 128) {
       unsigned u[4], sl[4], word[4];
-      int nv[4];
+      int nv[4], vo[4];
       bool ok[4];
       double2 p[4], t[4];
 #pragma unroll
@@ -2225,16 +2235,17 @@ __device__ __forceinline__ void integrate_all_impl(const Env &e) {
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const unsigned raw = u[q] >> 8;
+        const unsigned raw = u[q];
         sl[q] = raw < (unsigned)S ? raw : 0u;
         ok[q] = ok[q] & (raw < (unsigned)S);
         word[q] = smask[sl[q] >> 5];
         nv[q] = nvs[sl[q]];
+        vo[q] = voffs[sl[q]];
         t[q] = tt[sl[q]];
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        ok[q] = ok[q] & (((word[q] >> (sl[q] & 31u)) & 1u) != 0u) & ((int)(u[q] & 255u) < nv[q]);
+        ok[q] = ok[q] & (((word[q] >> (sl[q] & 31u)) & 1u) != 0u) & (v0 + 32 * q - vo[q] < nv[q]);
         // Affine2D().translate(tx, ty): 1.0 * x is exact, the 0.0 * y term keeps the
         // reference's NaN / signed-zero behaviour
         const double2 o = make_double2((p[q].x + 0.0 * p[q].y) + t[q].x, (0.0 * p[q].x + p[q].y) + t[q].y);
@@ -3292,8 +3303,8 @@ __device__ __forceinline__ void owner_warp(const StepArgs &a, unsigned char *sme
   // slot -> first cached vertex
   for (int s = lane; s <= e.S; s += 32) e.voff[s] = pv.voff[s];
   if (a.vmap) {
-    uint16_t *vm = (uint16_t *)(base + lay.vmap);
-    for (int v = lane; v < a.VT; v += 32) vm[v] = a.vmap[v];
+    uint8_t *vm = (uint8_t *)(base + lay.vmap);
+    for (int v = lane; v < a.VT; v += 32) vm[v] = (uint8_t)(a.vmap[v] >> 8);
   }
   wsync();
 
@@ -3548,7 +3559,9 @@ StepPlan plan_step(const int32_t *hdr, int resident_envs_per_sm, bool helper, in
     const int target = opt.ctas_per_sm > 0 ? opt.ctas_per_sm : resident_envs_per_sm;
     if (opt.smem_pad > 0) {
       smem += (size_t)opt.smem_pad;
-    } else if (target > 0) {
+    } else if (target > 0 && (size_t)233472 / (smem + 1024) > (size_t)target) {
+      // (when the records alone allow exactly `target` envs nothing is padded, and the SM keeps
+      // the shared memory it does not need as L1: launch_step sets the carve-out)
       size_t per_cta = (size_t)233472 / (size_t)target;  // 228 KB per SM, 1 KB of it reserved per CTA
       if (per_cta > 1024 + smem) smem = ((per_cta - 1024) & ~(size_t)127);
       if (smem > 227 * 1024) smem = 227 * 1024;
@@ -3603,6 +3616,22 @@ cudaError_t launch_step(const StepArgs &a, const int32_t *hdr, cudaStream_t stre
     cudaError_t err = cudaFuncSetAttribute(moog_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = smem;
+  }
+  {
+    // Shared-memory carve-out: the smallest supported capacity (.. 100, 132, 164, 196, 228 KB) that
+    // holds the CTAs that will be resident; what is left of the SM's 256 KB serves as L1 for the
+    // spills and the program's ops / expressions in global memory
+    static int carve_set = -1;
+    const size_t per_sm = ((size_t)233472 / (smem + 1024)) * (smem + 1024);
+    const int caps[] = {100, 132, 164, 196, 228};
+    int pick = 228;
+    for (int c : caps)
+      if (per_sm <= (size_t)c * 1024) { pick = c; break; }
+    const int pct = pick == 228 ? 100 : (pick * 100) / 228;   // rounded down: the driver takes the next capacity up
+    if (pct != carve_set) {
+      cudaFuncSetAttribute(moog_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      carve_set = pct;
+    }
   }
   int blocks = count;
   StepArgs b = a;
