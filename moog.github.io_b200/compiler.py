@@ -767,6 +767,28 @@ def _lower_distribution(dist):
         if any(v[0] != 'uniform' for v in box.values()):
             raise CompileError('{} against anything but a box of Continuous factors is not on the device sampler'.format(k))
         return {}, [('filtered', base, [(key, v[1], v[2]) for key, v in box.items()], k == 'Selection')]
+    if k == 'Intersection':
+        # distributions.py:211-247: sample component `index_for_sampling`, reject unless every component
+        # contains the sample -- for Products of Continuous factors that is one box, the intersection
+        idx = int(dist.index_for_sampling)
+        base = _flatten_distribution(dist.components[idx])
+        lo, hi = {}, {}
+        for j, c in enumerate(dist.components):
+            if j == idx:
+                continue
+            for key, v in _flatten_distribution(c).items():
+                if v[0] != 'uniform':
+                    raise CompileError('Intersection with anything but boxes of Continuous factors is not on the device sampler')
+                lo[key] = max(lo.get(key, -np.inf), float(v[1]))
+                hi[key] = min(hi.get(key, np.inf), float(v[2]))
+        return {}, [('filtered', base, [(key, lo[key], hi[key]) for key in lo], True)]
+    if k == 'DependentDistribution':
+        # distributions.py:420-470: some factors are a deterministic function of the sampled ones; the
+        # function is traced once into expressions over the independent factors
+        indep = _flatten_distribution(dist._independent_distrib)  # pylint: disable=protected-access
+        codes = lambdas.compile_dependent_fn(dist._dependent_fn, list(indep), list(dist._dependent_fn_keys))  # pylint: disable=protected-access
+        f32 = {key for key, v in indep.items() if v[0] == 'uniform'}
+        return indep, [('dependent', {key: v for key, v in codes.items()}, f32)]
     return _flatten_distribution(dist), []
 
 
@@ -886,6 +908,18 @@ def _compile_reset_sampler(prog, state_initializer):
         # factors drawn by the extensions: float32 iff every alternative draws them from a Continuous
         ext_specs = []
         for comp in extensions:
+            if comp[0] == 'dependent':
+                deps = []
+                for key, (code, reads) in comp[1].items():
+                    if key == 'shape':
+                        raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
+                    # NumPy: an expression over float32 draws and python scalars stays float32
+                    is32 = bool(reads) and all(_ATTR_KEYS[a] in comp[2] for a in reads)
+                    if is32:
+                        sampled32.add(key)
+                    deps.append((_ATTR_KEYS.index(key), prog.add_expr(code), 1 if is32 else 0))
+                ext_specs.append(dict(kind=3, deps=deps))
+                continue
             groups = comp[1] if comp[0] == 'mixture' else [comp[1]]
             for key in groups[0]:
                 if key == 'shape':
@@ -943,6 +977,11 @@ def _compile_reset_sampler(prog, state_initializer):
         #                     2, keep_if_inside, base leaves, n_box, (attr, dpool index of lo hi)...]
         tab.append(len(sp_['ext']))
         for comp in sp_['ext']:
+            if comp['kind'] == 3:      # 3, n, (attr, expression start, float32?) ...
+                tab += [3, len(comp['deps'])]
+                for attr, start_, is32 in comp['deps']:
+                    tab += [attr, start_, is32]
+                continue
             if comp['kind'] == 1:
                 cum = list(np.cumsum(comp['probs']))
                 tab += [1, len(comp['alts']), len(prog.dpool)]

@@ -3085,6 +3085,44 @@ __device__ __forceinline__ double sample_leaf(const double *dpool, int kind, int
   return dpool[idx + (pick < n ? pick : n - 1)];
 }
 
+// A DependentDistribution's expression (distributions.py:420-470) over the factors drawn so far:
+// the arithmetic subset of the expression VM, X_ATTR0 reading factor `arg` of the sample
+__device__ inline double eval_factor_expr(const moog_ex *x, const double *v) {
+  double st[16];
+  int sp = 0;
+  for (; x->op != MOOG_X_END && sp < 15; ++x) {
+    double a, b;
+    switch (x->op) {
+      case MOOG_X_CONST: st[sp++] = x->c; break;
+      case MOOG_X_ATTR0: st[sp++] = v[x->arg]; break;
+      case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
+      case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      default:
+        if (sp < 2) return NAN;
+        b = st[--sp];
+        a = st[--sp];
+        switch (x->op) {
+          case MOOG_X_LT: a = a < b; break;
+          case MOOG_X_LE: a = a <= b; break;
+          case MOOG_X_GT: a = a > b; break;
+          case MOOG_X_GE: a = a >= b; break;
+          case MOOG_X_EQ: a = a == b; break;
+          case MOOG_X_NE: a = a != b; break;
+          case MOOG_X_AND: a = (a != 0) && (b != 0); break;
+          case MOOG_X_OR: a = (a != 0) || (b != 0); break;
+          case MOOG_X_ADD: a = a + b; break;
+          case MOOG_X_SUB: a = a - b; break;
+          case MOOG_X_MUL: a = a * b; break;
+          case MOOG_X_DIV: a = a / b; break;
+          default: a = NAN; break;
+        }
+        st[sp++] = a;
+    }
+  }
+  return sp ? st[sp - 1] : NAN;
+}
+
 __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, const double *dpool,
                                             const int32_t *shape_off, uint64_t seed) {
   const Env e = env_view();
@@ -3119,7 +3157,13 @@ __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, cons
         uint32_t draw = 0;
         for (int c = 0; c < n_ext; ++c) {
           const int kind = *x++;
-          if (kind == 1) {
+          if (kind == 3) {  // DependentDistribution: attr, expression, float32?
+            const int n_dep = *x++;
+            for (int q = 0; q < n_dep; ++q, x += 3) {
+              const double val = eval_factor_expr(e.expr + x[1], v);
+              v[x[0]] = x[2] ? (double)(float)val : val;
+            }
+          } else if (kind == 1) {
             const int n_alt = *x++;
             const double *cum = dpool + *x++;
             const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,

@@ -476,6 +476,25 @@ def compile_modifier(fn):
     return code + [(X_CONST, 0, 1.0)]
 
 
+def compile_dependent_fn(fn, indep_keys, dep_keys):
+    """`DependentDistribution.dependent_fn(sample_dict) -> dict` traced over the independent factors:
+    {dependent key: (postfix code reading factors as X_ATTR0, set of attribute indices it reads)}."""
+    sample = {}
+    for k in indep_keys:
+        if k not in ATTRS:
+            raise LoweringError('DependentDistribution over the factor {!r} is not on the device sampler'.format(k))
+        sample[k] = Sym([(X_ATTR0, ATTRS.index(k), 0.0)])
+    with no_randomness('DependentDistribution dependent_fn'):
+        out = fn(sample)
+    codes = {}
+    for k in dep_keys:
+        if k not in ATTRS:
+            raise LoweringError('a dependent factor {!r} is not on the device sampler'.format(k))
+        v = Sym.lift(out[k])
+        codes[k] = (v.code, {arg for op, arg, _ in v.code if op == X_ATTR0})
+    return codes
+
+
 def constant_reward(reward_fn):
     """ContactReward reward_fn -> float (contact_reward.py:48-51)."""
     if not callable(reward_fn):

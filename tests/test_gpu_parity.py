@@ -736,3 +736,54 @@ def test_host_pipeline_delivers_the_same_timesteps(frames):
             assert torch.equal(r[3], g2[3]), (depth, k, 'frames')
         with pytest.raises(RuntimeError):
             pipe.collect()
+
+
+@pytest.mark.gpu
+def test_device_reset_sampler_intersection_and_dependent():
+    """`Intersection` (distributions.py:211-247: sample one component, reject unless all contain
+    the sample) and `DependentDistribution` (:420-470: factors that are a function of the sampled
+    ones) on the device sampler."""
+    import collections
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, observers, physics as physics_lib, sprite, tasks
+    from moog.state_initialization import distributions as distribs
+    from moog.state_initialization import sprite_generators
+    from moog_b200.batched_env import BatchedEnvironment
+    box = lambda x0, x1, y0, y1: distribs.Product([distribs.Continuous('x', x0, x1), distribs.Continuous('y', y0, y1)])
+    position = distribs.Intersection([box(0.1, 0.7, 0.2, 0.9), box(0.4, 0.95, 0.05, 0.6), box(0.0, 1.0, 0.3, 1.0)],
+                                     index_for_sampling=0)
+    velocity = distribs.DependentDistribution(
+        distribs.Continuous('x_vel', -0.03, 0.03),
+        dependent_fn=lambda smp: {'y_vel': -0.5 * smp['x_vel'], 'angle_vel': 2. * smp['x_vel'] + 0.01},
+        dependent_fn_keys=['y_vel', 'angle_vel'])
+    factors = distribs.Product([position, velocity, distribs.Continuous('scale', 0.03, 0.05)], shape='triangle',
+                               c0=0.3, c1=1., c2=1.)
+    gen = sprite_generators.generate_sprites(factors, num_sprites=5)
+
+    def state_initializer():
+        return collections.OrderedDict([('agent', [sprite.Sprite(x=0.5, y=0.02, shape='square', scale=0.02)]),
+                                        ('movers', gen())])
+
+    cfg = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(timeout_steps=10),
+               action_space=action_spaces.Joystick(scaling_factor=0.01, action_layers='agent'),
+               observers={'image': observers.PILRenderer(image_size=(64, 64), color_to_rgb='hsv_to_rgb')})
+    np.random.seed(4)
+    states = [state_initializer() for _ in range(2)]
+    N = 2048
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=6, initial_states=states, reset_mode='device')
+    env.reset()
+    st = env.engine.state.download()
+    assert (st['envi'][:, 2] == 0).all() and (st['cnt'][:, :2] == [1, 5]).all()
+    s0 = env.program.layer_off[1]
+    x, y = st['dyn'][:, 0, s0:s0 + 5].ravel(), st['dyn'][:, 1, s0:s0 + 5].ravel()
+    vx, vy, w = (st['dyn'][:, k, s0:s0 + 5].ravel() for k in (2, 3, 5))
+    # the intersection of the three boxes is [0.4, 0.7) x [0.3, 0.6); every part of it is reached
+    assert x.min() >= 0.4 - 1e-6 and x.max() < 0.7 + 1e-6 and y.min() >= 0.3 - 1e-6 and y.max() < 0.6 + 1e-6
+    assert x.min() < 0.42 and x.max() > 0.68 and y.min() < 0.32 and y.max() > 0.58
+    # dependent factors: float32 arithmetic on the float32 draw, like NumPy's
+    f32 = lambda a: a.astype(np.float32)
+    assert np.abs(vx).max() <= 0.03 and len(np.unique(vx)) > 0.9 * vx.size
+    assert np.array_equal(f32(vy), f32(-0.5 * vx)) and np.array_equal(vy, f32(vy).astype(np.float64))
+    assert np.array_equal(f32(w), f32(2. * vx + 0.01))
+    assert (st['meta'][:, 1, s0:s0 + 5] & 0x3f == (2 | (1 << 2))).all()      # float32 velocity and angle_vel
