@@ -193,7 +193,9 @@ enum {
    * made of fixed sprites and generate_sprites groups): i0 first slot, i1 number of sprites,
    * i2,i3 ipool list of the slots the new sprites must not overlap (`without_overlapping`),
    * i4 ipool index of the sampler table (MOOG_Z_N_ATTRS entries of 3 ints: kind, dpool index, n),
-   * flags MOOG_FL_DISJOINT / MOOG_FL_FAIL_GRACEFULLY, p0 max_recursion_depth */
+   * flags MOOG_FL_DISJOINT / MOOG_FL_FAIL_GRACEFULLY, p0 max_recursion_depth; p2 > p1: the number of
+ * sprites is drawn from {p1, ..., p2 - 1} per env and episode (`num_sprites=lambda:
+ * np.random.randint(p1, p2)`), i1 being the largest count */
   MOOG_Z_GENERATE = 192,
 
   /* state conditions (value = double; used by MOOG_T_RESET / MOOG_R_COND_BEGIN) */

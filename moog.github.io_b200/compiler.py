@@ -865,9 +865,15 @@ def _compile_reset_sampler(prog, state_initializer):
 
     specs = []
     for rec in records:
+        count_range = None
         if callable(rec['num_sprites']):
-            raise CompileError('a random number of generated sprites is not on the device sampler yet')
-        if len(rec['out']) != rec['num_sprites']:
+            count_range = rec.get('count_range')
+            if count_range is None:
+                raise CompileError('a random number of generated sprites is only lowered when it is drawn as '
+                                   '`np.random.randint(lo, hi)`')
+            if len(rec['out']) != count_range[1] - 1:
+                raise CompileError('the traced initializer produced fewer sprites than the largest count')
+        elif len(rec['out']) != rec['num_sprites']:
             raise CompileError('the traced initializer produced fewer sprites than asked for')
         if not rec['out']:
             continue
@@ -948,12 +954,18 @@ def _compile_reset_sampler(prog, state_initializer):
             meta_flags |= 1 << SF_ANGVEL_SHIFT
         if 'angle' in sampled32:
             meta_flags |= 1 << SF_ANG_SHIFT
-        specs.append(dict(first=slots[0], count=len(slots), avoid=avoid, table=table, meta_flags=meta_flags, ext=ext_specs,
+        specs.append(dict(first=slots[0], count=len(slots), count_range=count_range, avoid=avoid, table=table,
+                          meta_flags=meta_flags, ext=ext_specs,
                           flags=(FL_DISJOINT if rec['disjoint'] else 0) | (
                               FL_FAIL_GRACEFULLY if rec['fail_gracefully'] else 0),
                           max_depth=float(rec['max_recursion_depth'])))
     if not specs:
         raise CompileError('the state initializer never called generate_sprites: nothing to sample on the device')
+    for sp_ in specs:      # a group of random size leaves the rest of its layer's slots empty: it must be the last one
+        if sp_['count_range']:
+            lay_ = max(l for l in range(prog.n_layers) if prog.layer_off[l] <= sp_['first'])
+            if any(o is not sp_ and sp_['first'] < o['first'] < prog.layer_off[lay_ + 1] for o in specs):
+                raise CompileError('a generate_sprites group with a random number of sprites must be the last one of its layer')
     # covered slots of every layer must form the tail the template leaves to the sampler
     shape_off = []
     for rec_ in shape_recs:
@@ -1000,7 +1012,7 @@ def _compile_reset_sampler(prog, state_initializer):
     for sp_, a_start, t_start in emitted:
         prog.emit(Z_GENERATE, sp_['flags'],
                   (sp_['first'], sp_['count'], a_start, len(sp_['avoid']), t_start, sp_['meta_flags']),
-                  (sp_['max_depth'],))
+                  (sp_['max_depth'],) + (tuple(float(v) for v in sp_['count_range']) if sp_['count_range'] else (0., 0.)))
     prog.sections['reset'] = (start, len(prog.ops) - start)
     prog.reset_template = state
 

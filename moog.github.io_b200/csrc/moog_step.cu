@@ -3126,7 +3126,16 @@ __device__ inline double eval_factor_expr(const moog_ex *x, const double *v) {
 __device__ __noinline__ void reset_generate(const Env &, const moog_op *op, const double *dpool,
                                             const int32_t *shape_off, uint64_t seed) {
   const Env e = env_view();
-  const int first = op->i[0], count = op->i[1];
+  const int first = op->i[0];
+  int count = op->i[1];
+  if (op->p[2] > op->p[1]) {  // num_sprites = np.random.randint(p1, p2): drawn per env and episode
+    const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_EPISODES],
+                                    ((uint32_t)first << 20) | 0xfffffu, (0x5Cu << 24));
+    const int lo = (int)op->p[1], hi = (int)op->p[2];
+    int c = lo + (int)(u * (double)(hi - lo));
+    if (c >= hi) c = hi - 1;
+    if (c < count) count = c < 0 ? 0 : c;
+  }
   const int32_t *avoid = e.ipool + op->i[2];
   const int n_avoid = op->i[3];
   const int32_t *tab = e.ipool + op->i[4];

@@ -34,8 +34,34 @@ def generate_sprites(factor_dist, num_sprites=1, max_recursion_depth=int(1e4),
         # Every pair is evaluated (no short-circuit), like the reference.
         return any([s.overlaps_sprite(o) for o in others]) if others else False
 
+    def _traced_count():
+        """While a state initializer is traced for the device sampler, a random sprite count of the form
+        `lambda: np.random.randint(lo, hi)` (functional_maze.py:146) is recorded as the range it is
+        drawn from and the trace produces the largest count."""
+        calls = []
+        real = np.random.randint
+
+        def _randint(low, high=None, size=None, **kwargs):
+            if size is not None or kwargs:
+                return real(low, high, size, **kwargs)
+            lo, hi = (0, low) if high is None else (low, high)
+            calls.append((int(lo), int(hi)))
+            return int(hi) - 1
+        np.random.randint = _randint
+        try:
+            value = num_sprites()
+        finally:
+            np.random.randint = real
+        if len(calls) == 1 and value == calls[0][1] - 1:
+            return value, calls[0]
+        return value, None
+
     def _generate(disjoint=False, without_overlapping=[]):
-        count = num_sprites() if callable(num_sprites) else num_sprites
+        count_range = None
+        if callable(num_sprites) and _RECORDS is not None:
+            count, count_range = _traced_count()
+        else:
+            count = num_sprites() if callable(num_sprites) else num_sprites
         avoid = list(without_overlapping)
         out = []
         for _ in range(count):
@@ -55,7 +81,7 @@ def generate_sprites(factor_dist, num_sprites=1, max_recursion_depth=int(1e4),
                 avoid = avoid + [candidate]
         if _RECORDS is not None:
             _RECORDS.append(dict(
-                factor_dist=factor_dist, num_sprites=num_sprites, disjoint=bool(disjoint),
+                factor_dist=factor_dist, num_sprites=num_sprites, count_range=count_range, disjoint=bool(disjoint),
                 avoid=list(without_overlapping), out=list(out),
                 max_recursion_depth=max_recursion_depth, fail_gracefully=bool(fail_gracefully)))
         return out

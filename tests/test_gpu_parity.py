@@ -787,3 +787,49 @@ def test_device_reset_sampler_intersection_and_dependent():
     assert np.array_equal(f32(vy), f32(-0.5 * vx)) and np.array_equal(vy, f32(vy).astype(np.float64))
     assert np.array_equal(f32(w), f32(2. * vx + 0.01))
     assert (st['meta'][:, 1, s0:s0 + 5] & 0x3f == (2 | (1 << 2))).all()      # float32 velocity and angle_vel
+
+
+@pytest.mark.gpu
+def test_device_reset_sampler_random_sprite_count():
+    """`generate_sprites(..., num_sprites=lambda: np.random.randint(2, 5))` (functional_maze.py:146):
+    the device sampler draws the count per env and episode."""
+    import collections
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, observers, physics as physics_lib, sprite, tasks
+    from moog.state_initialization import distributions as distribs
+    from moog.state_initialization import sprite_generators
+    from moog_b200.batched_env import BatchedEnvironment
+    factors = distribs.Product([distribs.Continuous('x', 0.1, 0.9), distribs.Continuous('y', 0.1, 0.9)],
+                               shape='square', scale=0.06, c0=0.5, c1=1., c2=1.)
+    gen = sprite_generators.generate_sprites(factors, num_sprites=lambda: np.random.randint(2, 5))
+
+    def state_initializer():
+        return collections.OrderedDict([('agent', [sprite.Sprite(x=0.5, y=0.02, shape='square', scale=0.02)]),
+                                        ('prey', gen(disjoint=True))])
+
+    cfg = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(timeout_steps=3),
+               action_space=action_spaces.Joystick(scaling_factor=0.01, action_layers='agent'),
+               observers={'image': observers.PILRenderer(image_size=(64, 64), color_to_rgb='hsv_to_rgb')})
+    np.random.seed(4)
+    states = [state_initializer() for _ in range(16)]
+    assert {len(s['prey']) for s in states} <= {2, 3, 4}
+    N = 3000
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=6, initial_states=states, reset_mode='device',
+                             layer_capacity={'prey': 4})
+    env.reset()
+    st = env.engine.state.download()
+    counts = st['cnt'][:, 1]
+    share = np.array([(counts == c).mean() for c in (2, 3, 4)])
+    assert share.sum() == 1.0 and np.all(np.abs(share - 1 / 3) < 0.04), share
+    # the sprites that exist are disjoint
+    pp = env.engine.overlap_pairs('prey', 'prey').cpu().numpy()
+    for e in range(0, N, 17):
+        c = counts[e]
+        assert not (pp[e, :c, :c] & ~np.eye(c, dtype=bool)).any()
+    first = counts.copy()
+    import torch
+    for _ in range(5):
+        env.step(torch.zeros((N, 2), dtype=torch.float64))
+    again = env.engine.state.download()['cnt'][:, 1]
+    assert (again != first).mean() > 0.5, 'a new count is drawn every episode'
