@@ -70,6 +70,9 @@ struct SmemLayout {
 #define DCV_TILE_MAX 32
 #endif
 #define DCV_TILE_MIN 8
+#ifndef DCV_U
+#define DCV_U 2 /* vertices (x edges) per trip of stage A1 of the directed search */
+#endif
 #define NEAR_SKIN 0.02
 #define NEAR_CAP 512  /* near-list entries; more near pairs than this -> every pair is tested */
 
@@ -228,8 +231,10 @@ __device__ __forceinline__ Env env_view() {
 
 #if defined(MOOG_PROFILE_PHASES) || defined(MOOG_PROFILE_DCV) || defined(MOOG_PROFILE_GCV) || defined(MOOG_PROFILE_INTEG)
 #define PROF_RESOLVE(e, t1)
-#else
+#elif defined(MOOG_CYCLE_COUNTERS)
 #define PROF_RESOLVE(e, t1) ctr_add(e, CT_CYC_RESOLVE, clock64() - (t1))
+#else
+#define PROF_RESOLVE(e, t1)
 #endif
 
 enum { CT_CALLS = 0, CT_TRUE, CT_COLL, CT_HASH, CT_CYCLES, CT_NARROW, CT_CYC_NARROW, CT_CYC_RESOLVE, CT_SUBSTEP,
@@ -541,21 +546,25 @@ __device__ __forceinline__ bool isclose_(double a, double b) {
   return fabs(a - b) <= fmax(1e-10 * fmax(fabs(a), fabs(b)), 1e-13);
 }
 
+// the parallel case of segments_intersect (rare: kept out of the callers' instruction stream)
+__device__ __noinline__ bool segments_parallel_case(double x1, double y1, double x2, double y2, double x3, double y3,
+                                                    double x4, double y4) {
+  double t_area = (x2 * y3 - x3 * y2) - x1 * (y3 - y2) + y1 * (x3 - x2);
+  if (isclose_(t_area, 0.0)) {
+    if (x1 == x2 && x2 == x3) {
+      return (fmin(y1, y2) <= fmin(y3, y4) && fmin(y3, y4) <= fmax(y1, y2)) ||
+             (fmin(y3, y4) <= fmin(y1, y2) && fmin(y1, y2) <= fmax(y3, y4));
+    }
+    return (fmin(x1, x2) <= fmin(x3, x4) && fmin(x3, x4) <= fmax(x1, x2)) ||
+           (fmin(x3, x4) <= fmin(x1, x2) && fmin(x1, x2) <= fmax(x3, x4));
+  }
+  return false;
+}
+
 __device__ inline bool segments_intersect(double x1, double y1, double x2, double y2, double x3, double y3,
                                           double x4, double y4) {
   double den = ((y4 - y3) * (x2 - x1)) - ((x4 - x3) * (y2 - y1));
-  if (isclose_(den, 0.0)) {
-    double t_area = (x2 * y3 - x3 * y2) - x1 * (y3 - y2) + y1 * (x3 - x2);
-    if (isclose_(t_area, 0.0)) {
-      if (x1 == x2 && x2 == x3) {
-        return (fmin(y1, y2) <= fmin(y3, y4) && fmin(y3, y4) <= fmax(y1, y2)) ||
-               (fmin(y3, y4) <= fmin(y1, y2) && fmin(y1, y2) <= fmax(y3, y4));
-      }
-      return (fmin(x1, x2) <= fmin(x3, x4) && fmin(x3, x4) <= fmax(x1, x2)) ||
-             (fmin(x3, x4) <= fmin(x1, x2) && fmin(x1, x2) <= fmax(x3, x4));
-    }
-    return false;
-  }
+  if (isclose_(den, 0.0)) return segments_parallel_case(x1, y1, x2, y2, x3, y3, x4, y4);
   double n1 = ((x4 - x3) * (y1 - y3)) - ((y4 - y3) * (x1 - x3));
   double n2 = ((x2 - x1) * (y1 - y3)) - ((y2 - y1) * (x1 - x3));
   double u1 = n1 / den;
@@ -616,6 +625,17 @@ __device__ inline bool all_points_in_poly(const Env &e, const double2 *P, int np
   double2 p = P[act ? e.lane : 0];
   bool in = point_in_poly(p.x, p.y, Q, nq);
   return __all_sync(FULL, in || !act);
+}
+
+// the path_in_path fall-backs of path_intersects_filled (boxes nest: rare)
+__device__ __noinline__ bool containment_fallback(int a, int b, bool try_b_in_a, bool try_a_in_b) {
+  const Env e = env_view();
+  const double2 *A = e.vtx + e.voff[a];
+  const double2 *B = e.vtx + e.voff[b];
+  const int nA = META(e, MOOG_M_NV, a), nB = META(e, MOOG_M_NV, b);
+  if (try_b_in_a && all_points_in_poly(e, B, nB, A, nA)) return true;  // b inside a
+  if (try_a_in_b && all_points_in_poly(e, A, nA, B, nB)) return true;  // a inside b
+  return false;
 }
 
 // Path.intersects_path(a, b, filled=True) as MOOG calls it (sprite.py:482-483)
@@ -693,10 +713,9 @@ __device__ __forceinline__ bool path_intersects_filled_impl(const Env &e, int a,
   // outside the outline, so "all inside" needs box containment first
   bool b_in_a_box = BOX(e, 0, b) >= BOX(e, 0, a) - AABB_PAD && BOX(e, 2, b) <= BOX(e, 2, a) + AABB_PAD &&
                     BOX(e, 1, b) >= BOX(e, 1, a) - AABB_PAD && BOX(e, 3, b) <= BOX(e, 3, a) + AABB_PAD;
-  if ((b_in_a_box || nocull) && all_points_in_poly(e, B, nB, A, nA)) return true;  // b inside a
   bool a_in_b_box = BOX(e, 0, a) >= BOX(e, 0, b) - AABB_PAD && BOX(e, 2, a) <= BOX(e, 2, b) + AABB_PAD &&
                     BOX(e, 1, a) >= BOX(e, 1, b) - AABB_PAD && BOX(e, 3, a) <= BOX(e, 3, b) + AABB_PAD;
-  if ((a_in_b_box || nocull) && all_points_in_poly(e, A, nA, B, nB)) return true;  // a inside b
+  if (b_in_a_box || a_in_b_box || nocull) return containment_fallback(a, b, b_in_a_box || nocull, a_in_b_box || nocull);
   return false;
 }
 
@@ -760,6 +779,19 @@ struct CVec {
   double px, py, nx, ny, sx, sy, qx, qy;  // point, normal, since, perp
 };
 
+// the four-transform product of _relative_motion_trajectory when a sprite rotates
+__device__ __noinline__ Aff rel_motion_general(double x1, double y1, double th1, double tx2, double ty2, double x3,
+                                               double y3, double th3, double tx4, double ty4) {
+  Aff m1 = aff_identity(), m2 = aff_identity(), m3 = aff_identity(), m4 = aff_identity();
+  aff_rotate_around(m1, x1, y1, th1);
+  aff_translate(m2, tx2, ty2);
+  aff_rotate_around(m3, x3, y3, th3);
+  aff_translate(m4, tx4, ty4);
+  Aff t12 = aff_then(m1, m2);
+  Aff t123 = aff_then(t12, m3);
+  return aff_then(t123, m4);
+}
+
 // collisions.py:62-98 _relative_motion_trajectory (matrix only)
 __device__ inline Aff rel_motion_matrix(const Env &e, int ps, int as, double dt) {
   const double th1 = scaled_angvel(e, ps, -1.0, dt);
@@ -778,14 +810,7 @@ __device__ inline Aff rel_motion_matrix(const Env &e, int ps, int as, double dt)
     Aff m = {1., 0., tx4 + (tx2 + 0.0), 0., 1., ty4 + (ty2 + 0.0)};
     return m;
   }
-  Aff m1 = aff_identity(), m2 = aff_identity(), m3 = aff_identity(), m4 = aff_identity();
-  aff_rotate_around(m1, x1, y1, th1);
-  aff_translate(m2, tx2, ty2);
-  aff_rotate_around(m3, x3, y3, th3);
-  aff_translate(m4, tx4, ty4);
-  Aff t12 = aff_then(m1, m2);
-  Aff t123 = aff_then(t12, m3);
-  return aff_then(t123, m4);
+  return rel_motion_general(x1, y1, th1, tx2, ty2, x3, y3, th3, tx4, ty4);
 }
 template <int TILE>
 __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, int s0, int s1, double dt, CVec &o) {
@@ -854,12 +879,12 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
     const unsigned long long KEY_INF = (unsigned long long)__double_as_longlong(INFINITY) + 1ull;
     const unsigned lt = (1u << e.lane) - 1u;
     int n_pairs = 0;
-    for (int t0 = 0; t0 < cnt; t0 += 2 * V) {
-      bool cr[2], inexact = false;
-      double nB2[2], den2[2];
-      bool on2[2];
+    for (int t0 = 0; t0 < cnt; t0 += DCV_U * V) {
+      bool cr[DCV_U], inexact = false;
+      double nB2[DCV_U], den2[DCV_U];
+      bool on2[DCV_U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < DCV_U; ++u) {
         const int t = t0 + u * V + tl;
         const bool valid = t < cnt;
         const bool on = eact && valid;
@@ -882,13 +907,13 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
       }
       if (__any_sync(FULL, inexact)) {  // out-of-range operands somewhere in the warp: divide
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < DCV_U; ++u) {
           const double Bc = nB2[u] / den2[u];
           cr[u] = on2[u] && (Bc >= 0) && (Bc <= 1);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < DCV_U; ++u) {
         const unsigned cm = __ballot_sync(FULL, cr[u]);
         if (cr[u]) e.plist[n_pairs + __popc(cm & lt)] = (unsigned short)(((t0 + u * V + tl) << 8) | ej);
         n_pairs += __popc(cm);
@@ -931,7 +956,7 @@ __device__ __forceinline__ void directed_collision_vectors_impl(const Env &e, in
     int idx = 0;
     {
       const bool kact = e.lane < n1;
-#pragma unroll 4
+#pragma unroll 1
       for (int v = 0; v < cnt; ++v) {
         const unsigned long long k = kact ? keys[v * 32 + e.lane] : ~0ull;
         const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
@@ -1277,7 +1302,7 @@ __device__ inline int collision_step(const Env &e, const moog_op *op, int s0, in
     } else {
       ov = overlaps(e, s0, s1);
     }
-#if !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV) && !defined(MOOG_PROFILE_GCV) && !defined(MOOG_PROFILE_INTEG)
+#if defined(MOOG_CYCLE_COUNTERS) && !defined(MOOG_PROFILE_PHASES) && !defined(MOOG_PROFILE_DCV) && !defined(MOOG_PROFILE_GCV) && !defined(MOOG_PROFILE_INTEG)
     ctr_add(e, CT_NARROW, 1);
     ctr_add(e, CT_CYC_NARROW, clock64() - t0);
 #endif
