@@ -176,6 +176,11 @@ enum {
   MOOG_R_CHANGE_LAYER,           /* i0 old layer, i1 new layer, i2 filter expr (-1: all): the flagged sprites
                                     are appended to the new layer in order and popped from the old one
                                                                                                  change_layer.py:34-45 */
+  MOOG_R_CREATE_SPRITES,         /* create_sprites.py:27-34: i0 layer the new sprites are appended to, i1 how many,
+                                    i2,i3 ipool list of the LAYERS they must not overlap, i4 sampler table
+                                    (as MOOG_Z_GENERATE), i5 dtype flags; MOOG_FL_DISJOINT / FAIL_GRACEFULLY,
+                                    p0 max_recursion_depth.  Drawn on the device (Philox keyed by seed, env,
+                                    episode, step) */
 
   /* tasks: i[5] = envf slot of the countdown */
   MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps; p2 > 0: the
@@ -211,8 +216,10 @@ enum {
                               (matters for the overlap calls a contact count makes) and the value is
                               that of the deciding operand */
   MOOG_SC_NOT,             /* i0 operand condition op: python `not`             */
-  MOOG_SC_FIRST            /* i0,i1 layer list; i2 sprite expr evaluated on the FIRST sprite of the list
+  MOOG_SC_FIRST,           /* i0,i1 layer list; i2 sprite expr evaluated on the FIRST sprite of the list
                               (`state[layer][0]`); 0 when the list is empty      */
+  MOOG_SC_BERNOULLI        /* `np.random.binomial(1, p)` as a condition (first_person_predators_prey.py:181,189):
+                              1 when the uniform in rule-noise column i0 is below p0 */
 };
 
 /* op flags */

@@ -115,6 +115,8 @@ class Program(object):
         self.ipool = []
         self.expr = []           # list of (op, arg, c)
         self.dpool = []          # doubles: shape table / sampler parameters of the reset sampler
+        self.z_shape_ids = {}    # device sampler: shape candidate -> index of its shape record
+        self.z_shape_recs = []
         self.reset_shapes = []   # shape candidates of the reset sampler, by shape id
         self.sections = {}
         self.n_envf = 0
@@ -705,7 +707,8 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     _compile_render(prog, config.get('observers', {}))
     if reset_sampler:
         _compile_reset_sampler(prog, config['state_initializer'])
-    _emit_shape_table_if_needed(prog, sample_states, reset_sampler)
+    _finish_z_shapes(prog)
+    _emit_shape_table_if_needed(prog, sample_states, bool(prog.z_shape_recs))
     _check_outline_caps(prog)
     return prog.finalize()
 
@@ -803,7 +806,8 @@ def _emit_shape_table_if_needed(prog, sample_states, reset_sampler):
     if not needs:
         return
     if reset_sampler:
-        raise CompileError('rules that assign scale / aspect_ratio are not combined with the device reset sampler yet')
+        raise CompileError('rules that assign scale / aspect_ratio are not combined with the device sampler '
+                           '(reset_mode=\'device\' / CreateSprites) yet')
     table = ShapeTable()
     for st in sample_states:
         for name in prog.layer_names:
@@ -834,6 +838,140 @@ def _shape_record(shape):
     return rec
 
 
+def _sprite_defaults():
+    import inspect
+    from moog import sprite as sprite_lib
+    return {k: p.default for k, p in inspect.signature(sprite_lib.Sprite.__init__).parameters.items()
+            if p.default is not inspect.Parameter.empty}
+
+
+def _z_shape_id(prog, shape):
+    """Index of a shape candidate in the blob's shape records (device sampler)."""
+    key = shape if isinstance(shape, str) else np.asarray(shape, dtype=np.float64).tobytes()
+    if key not in prog.z_shape_ids:
+        prog.z_shape_ids[key] = len(prog.z_shape_recs)
+        prog.z_shape_recs.append(_shape_record(shape))
+        prog.reset_shapes.append(shape)
+    return prog.z_shape_ids[key]
+
+
+def _sampler_group(prog, factor_dist, lay):
+    """One generate_sprites recipe -> (factor table, dtype flags of the sprites it makes, extension
+    components) for the device sampler (reset groups and CreateSprites rules)."""
+    defaults = _sprite_defaults()
+    flat, extensions = _lower_distribution(factor_dist)
+    table, meta_flags = [], 0
+    sampled32 = set()
+    for key in _ATTR_KEYS + ('shape',):
+        kind, payload = 'discrete', [defaults[key]]
+        if key in flat:
+            kind, payload = flat[key][0], list(flat[key][1:]) if flat[key][0] == 'uniform' else flat[key][1]
+        if kind == 'uniform':
+            table.append((ZK_UNIFORM32, payload))
+            sampled32.add(key)
+        else:
+            values = [_z_shape_id(prog, v) for v in payload] if key == 'shape' else [float(v) for v in payload]
+            if key == 'shape':
+                for sid in values:
+                    if int(prog.z_shape_recs[sid][0]) > prog.layer_vcap[lay]:
+                        raise CompileError(
+                            'a shape candidate has {} vertices, more than the sample states showed for layer '
+                            '{!r} ({}); pass more sample states'.format(
+                                int(prog.z_shape_recs[sid][0]), prog.layer_names[lay], prog.layer_vcap[lay]))
+            table.append((ZK_CONST if len(values) == 1 else ZK_DISCRETE, values))
+    # factors drawn by the extensions: float32 iff every alternative draws them from a Continuous
+    ext_specs = []
+    for comp in extensions:
+        if comp[0] == 'dependent':
+            deps = []
+            for key, (code, reads) in comp[1].items():
+                if key == 'shape':
+                    raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
+                # NumPy: an expression over float32 draws and python scalars stays float32
+                is32 = bool(reads) and all(_ATTR_KEYS[a] in comp[2] for a in reads)
+                if is32:
+                    sampled32.add(key)
+                deps.append((_ATTR_KEYS.index(key), prog.add_expr(code), 1 if is32 else 0))
+            ext_specs.append(dict(kind=3, deps=deps))
+            continue
+        groups = comp[1] if comp[0] == 'mixture' else [comp[1]]
+        for key in groups[0]:
+            if key == 'shape':
+                raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
+            kinds = {g[key][0] for g in groups}
+            if kinds == {'uniform'}:
+                sampled32.add(key)
+            elif key in ('x_vel', 'y_vel', 'angle', 'angle_vel') and 'uniform' in kinds:
+                raise CompileError('factor {!r} is float32 in some Mixture alternatives only'.format(key))
+
+        def enc(leaves_):
+            out_ = []
+            for key_, leaf in leaves_.items():
+                values = list(leaf[1:]) if leaf[0] == 'uniform' else [float(v) for v in leaf[1]]
+                kind_ = ZK_UNIFORM32 if leaf[0] == 'uniform' else (ZK_CONST if len(values) == 1 else ZK_DISCRETE)
+                out_.append((_ATTR_KEYS.index(key_), kind_, values))
+            return out_
+        if comp[0] == 'mixture':
+            ext_specs.append(dict(kind=1, alts=[enc(a) for a in comp[1]], probs=comp[2]))
+        else:
+            ext_specs.append(dict(kind=2, base=enc(comp[1]), keep=bool(comp[3]),
+                                  box=[(_ATTR_KEYS.index(key), lo_, hi_) for key, lo_, hi_ in comp[2]]))
+    if {'x_vel', 'y_vel'} <= sampled32:
+        meta_flags |= SF_VEL32
+    if 'angle_vel' in sampled32:
+        meta_flags |= 1 << SF_ANGVEL_SHIFT
+    if 'angle' in sampled32:
+        meta_flags |= 1 << SF_ANG_SHIFT
+    return table, meta_flags, ext_specs
+
+
+def _emit_sampler_table(prog, table, ext):
+    """Writes a group's factor table and extension program into the pools; returns the ipool start."""
+    tab = []
+    for kind, values in table:
+        tab += [kind, len(prog.dpool), len(values)]
+        prog.dpool.extend(float(v) for v in values)
+
+    def put_leaves(leaves_):
+        out_ = [len(leaves_)]
+        for attr, kind, values in leaves_:
+            out_ += [attr, kind, len(prog.dpool), len(values)]
+            prog.dpool.extend(float(v) for v in values)
+        return out_
+    # extension program: [n_ext, then per component: 1, n_alt, probs dpool index, alternatives... |
+    #                     2, keep_if_inside, base leaves, n_box, (attr, dpool index of lo hi)... |
+    #                     3, n, (attr, expression start, float32?)...]
+    tab.append(len(ext))
+    for comp in ext:
+        if comp['kind'] == 3:
+            tab += [3, len(comp['deps'])]
+            for attr, start_, is32 in comp['deps']:
+                tab += [attr, start_, is32]
+        elif comp['kind'] == 1:
+            cum = list(np.cumsum(comp['probs']))
+            tab += [1, len(comp['alts']), len(prog.dpool)]
+            prog.dpool.extend(float(v) for v in cum)
+            for alt in comp['alts']:
+                tab += put_leaves(alt)
+        else:
+            tab += [2, 1 if comp['keep'] else 0] + put_leaves(comp['base']) + [len(comp['box'])]
+            for attr, lo_, hi_ in comp['box']:
+                tab += [attr, len(prog.dpool)]
+                prog.dpool.extend([float(lo_), float(hi_)])
+    return prog.add_ints(tab)
+
+
+def _finish_z_shapes(prog):
+    """Shape records of every candidate shape the device sampler can draw (MOOG_H_SHAPE_TAB)."""
+    if not prog.z_shape_recs:
+        return
+    shape_off = []
+    for rec_ in prog.z_shape_recs:
+        shape_off.append(len(prog.dpool))
+        prog.dpool.extend(rec_)
+    prog.shape_tab = prog.add_ints(shape_off)
+
+
 def _compile_reset_sampler(prog, state_initializer):
     """Traces the state initializer (this repo's sprite_generators record what they
     are asked for) and lowers every generate_sprites group to a MOOG_Z_GENERATE op."""
@@ -851,18 +989,6 @@ def _compile_reset_sampler(prog, state_initializer):
         for k, sp in enumerate(state[name]):
             slot_of[id(sp)] = prog.layer_off[l] + k
             layer_of[id(sp)] = l
-    defaults = {k: p.default for k, p in inspect.signature(sprite_lib.Sprite.__init__).parameters.items()
-                if p.default is not inspect.Parameter.empty}
-    shape_ids, shape_recs = {}, []
-
-    def shape_id(shape):
-        key = shape if isinstance(shape, str) else np.asarray(shape, dtype=np.float64).tobytes()
-        if key not in shape_ids:
-            shape_ids[key] = len(shape_recs)
-            shape_recs.append(_shape_record(shape))
-            prog.reset_shapes.append(shape)
-        return shape_ids[key]
-
     specs = []
     for rec in records:
         count_range = None
@@ -888,72 +1014,10 @@ def _compile_reset_sampler(prog, state_initializer):
             raise CompileError('the sprites of one generate_sprites call must stay in one layer')
         if any(a >= slots[0] for a in avoid):
             raise CompileError('generated sprites can only avoid sprites in earlier slots')
-        flat, extensions = _lower_distribution(rec['factor_dist'])
         lay = layer_of[id(rec['out'][0])]
         if slots[0] + len(slots) != prog.layer_off[lay] + len(state[prog.layer_names[lay]]):
             raise CompileError('generated sprites must be the last sprites of their layer')
-        table, meta_flags = [], 0
-        sampled32 = set()
-        for key in _ATTR_KEYS + ('shape',):
-            kind, payload = 'discrete', [defaults[key]]
-            if key in flat:
-                kind, payload = flat[key][0], list(flat[key][1:]) if flat[key][0] == 'uniform' else flat[key][1]
-            if kind == 'uniform':
-                table.append((ZK_UNIFORM32, payload))
-                sampled32.add(key)
-            else:
-                values = [shape_id(v) for v in payload] if key == 'shape' else [float(v) for v in payload]
-                if key == 'shape':
-                    for sid in values:
-                        if int(shape_recs[sid][0]) > prog.layer_vcap[lay]:
-                            raise CompileError(
-                                'a shape candidate has {} vertices, more than the sample states showed for layer '
-                                '{!r} ({}); pass more sample states'.format(
-                                    int(shape_recs[sid][0]), prog.layer_names[lay], prog.layer_vcap[lay]))
-                table.append((ZK_CONST if len(values) == 1 else ZK_DISCRETE, values))
-        # factors drawn by the extensions: float32 iff every alternative draws them from a Continuous
-        ext_specs = []
-        for comp in extensions:
-            if comp[0] == 'dependent':
-                deps = []
-                for key, (code, reads) in comp[1].items():
-                    if key == 'shape':
-                        raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
-                    # NumPy: an expression over float32 draws and python scalars stays float32
-                    is32 = bool(reads) and all(_ATTR_KEYS[a] in comp[2] for a in reads)
-                    if is32:
-                        sampled32.add(key)
-                    deps.append((_ATTR_KEYS.index(key), prog.add_expr(code), 1 if is32 else 0))
-                ext_specs.append(dict(kind=3, deps=deps))
-                continue
-            groups = comp[1] if comp[0] == 'mixture' else [comp[1]]
-            for key in groups[0]:
-                if key == 'shape':
-                    raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
-                kinds = {g[key][0] for g in groups}
-                if kinds == {'uniform'}:
-                    sampled32.add(key)
-                elif key in ('x_vel', 'y_vel', 'angle', 'angle_vel') and 'uniform' in kinds:
-                    raise CompileError('factor {!r} is float32 in some Mixture alternatives only'.format(key))
-
-            def enc(leaves_):
-                out_ = []
-                for key_, leaf in leaves_.items():
-                    values = list(leaf[1:]) if leaf[0] == 'uniform' else [float(v) for v in leaf[1]]
-                    kind_ = ZK_UNIFORM32 if leaf[0] == 'uniform' else (ZK_CONST if len(values) == 1 else ZK_DISCRETE)
-                    out_.append((_ATTR_KEYS.index(key_), kind_, values))
-                return out_
-            if comp[0] == 'mixture':
-                ext_specs.append(dict(kind=1, alts=[enc(a) for a in comp[1]], probs=comp[2]))
-            else:
-                ext_specs.append(dict(kind=2, base=enc(comp[1]), keep=bool(comp[3]),
-                                      box=[(_ATTR_KEYS.index(key), lo_, hi_) for key, lo_, hi_ in comp[2]]))
-        if {'x_vel', 'y_vel'} <= sampled32:
-            meta_flags |= SF_VEL32
-        if 'angle_vel' in sampled32:
-            meta_flags |= 1 << SF_ANGVEL_SHIFT
-        if 'angle' in sampled32:
-            meta_flags |= 1 << SF_ANG_SHIFT
+        table, meta_flags, ext_specs = _sampler_group(prog, rec['factor_dist'], lay)
         specs.append(dict(first=slots[0], count=len(slots), count_range=count_range, avoid=avoid, table=table,
                           meta_flags=meta_flags, ext=ext_specs,
                           flags=(FL_DISJOINT if rec['disjoint'] else 0) | (
@@ -966,47 +1030,10 @@ def _compile_reset_sampler(prog, state_initializer):
             lay_ = max(l for l in range(prog.n_layers) if prog.layer_off[l] <= sp_['first'])
             if any(o is not sp_ and sp_['first'] < o['first'] < prog.layer_off[lay_ + 1] for o in specs):
                 raise CompileError('a generate_sprites group with a random number of sprites must be the last one of its layer')
-    # covered slots of every layer must form the tail the template leaves to the sampler
-    shape_off = []
-    for rec_ in shape_recs:
-        shape_off.append(len(prog.dpool))
-        prog.dpool.extend(rec_)
-    prog.shape_tab = prog.add_ints(shape_off)
     emitted = []
     for sp_ in specs:
-        tab = []
-        for kind, values in sp_['table']:
-            tab += [kind, len(prog.dpool), len(values)]
-            prog.dpool.extend(float(v) for v in values)
-
-        def put_leaves(leaves_):
-            out_ = [len(leaves_)]
-            for attr, kind, values in leaves_:
-                out_ += [attr, kind, len(prog.dpool), len(values)]
-                prog.dpool.extend(float(v) for v in values)
-            return out_
-        # extension program: [n_ext, then per component: 1, n_alt, probs dpool index, alternatives... |
-        #                     2, keep_if_inside, base leaves, n_box, (attr, dpool index of lo hi)...]
-        tab.append(len(sp_['ext']))
-        for comp in sp_['ext']:
-            if comp['kind'] == 3:      # 3, n, (attr, expression start, float32?) ...
-                tab += [3, len(comp['deps'])]
-                for attr, start_, is32 in comp['deps']:
-                    tab += [attr, start_, is32]
-                continue
-            if comp['kind'] == 1:
-                cum = list(np.cumsum(comp['probs']))
-                tab += [1, len(comp['alts']), len(prog.dpool)]
-                prog.dpool.extend(float(v) for v in cum)
-                for alt in comp['alts']:
-                    tab += put_leaves(alt)
-            else:
-                tab += [2, 1 if comp['keep'] else 0] + put_leaves(comp['base']) + [len(comp['box'])]
-                for attr, lo_, hi_ in comp['box']:
-                    tab += [attr, len(prog.dpool)]
-                    prog.dpool.extend([float(lo_), float(hi_)])
         a_start = prog.add_ints(sp_['avoid'])
-        t_start = prog.add_ints(tab)
+        t_start = _emit_sampler_table(prog, sp_['table'], sp_['ext'])
         emitted.append((sp_, a_start, t_start))
     start = len(prog.ops)
     for sp_, a_start, t_start in emitted:
