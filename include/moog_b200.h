@@ -150,8 +150,10 @@ int moog_step_draws_frames(const moog_program *p, int n_envs);
  * MOOG_FUSED_RENDER, MOOG_TAIL_RENDER, MOOG_TAIL_CTAS_PER_SM, MOOG_TAIL_BUSY_THR, MOOG_RENDER_EPB,
  * MOOG_TRACE_TIMES) are read once, when the program is created; this call changes one option of a
  * live program: name in {"helper", "ctas_per_sm", "smem_pad", "fused_render", "tail_render",
- * "tail_ctas_per_sm", "tail_busy_thr", "render_epb", "trace_times"}; value -1 (helper,
- * fused_render) or 0 (the counts) hands the decision back to the library.  Never changes results. */
+ * "tail_ctas_per_sm", "tail_busy_thr", "render_epb", "trace_times", "seed"}; value -1 (helper,
+ * fused_render) or 0 (the counts) hands the decision back to the library.  None of the launch options
+ * changes results; "seed" is the io.seed that moog_env_post_reset (which takes no moog_step_io) keys
+ * the draws of its rules pass with (CreateSprites, random conditions). */
 int moog_program_set_option(moog_program *p, const char *name, int value);
 
 #ifdef __cplusplus

@@ -94,7 +94,9 @@ enum { MOOG_M_SHAPE = 0, MOOG_M_FLAGS, MOOG_M_NV };
 #define MOOG_ENVI_WORDS 8
 enum {
   MOOG_EI_STEP_COUNT = 0, MOOG_EI_RESET_NEXT, MOOG_EI_ERR, MOOG_EI_EPISODES,
-  MOOG_EI_RNG0, MOOG_EI_RNG1, MOOG_EI_LAST_RESET, MOOG_EI_VALIAS_NEXT /* last alias id handed out */
+  MOOG_EI_CREATED,      /* CreateSprites calls this env has made (keys their Philox draws) */
+  MOOG_EI_RULE_PASSES,  /* passes over the game rules this env has made (keys the rule-noise draws) */
+  MOOG_EI_LAST_RESET, MOOG_EI_VALIAS_NEXT /* last alias id handed out */
 };
 
 /* error bits (data-dependent reference exceptions, raised lazily by the host) */

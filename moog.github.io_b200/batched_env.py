@@ -137,6 +137,7 @@ class Engine(object):
         self.seed = int(seed)
         with torch.cuda.device(self.device):
             self.dev_program = capi.DeviceProgram(program.blob)
+        self.dev_program.set_option('seed', self.seed & 0x7fffffff)
         self.state = DeviceState(program, self.n, self.device)
         self.pool = None
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -154,6 +155,10 @@ class Engine(object):
         self._pinned_ok = set()
 
     # -- helpers -----------------------------------------------------------
+    def call_seed(self):
+        """io.seed of the next env_step call (a different Philox key every call)."""
+        return (self.seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
+
     def _on_device(self):
         """Context that makes this engine's GPU current (free when it already is)."""
         index = self.device.index
@@ -225,7 +230,7 @@ class Engine(object):
             io.pool_size = self.pool.n
         io.reset_index = _ptr(ri)
         io.sample_resets = 1 if sample_resets else 0
-        io.seed = (self.seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
+        io.seed = self.call_seed()
         io.reward, io.step_type, io.discount = _ptr(self.reward), _ptr(self.step_type), _ptr(self.discount)
         io.counters = _ptr(self.counters) if want_counters else None
         io.stats = _ptr(self.stats)

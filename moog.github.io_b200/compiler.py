@@ -60,11 +60,11 @@ F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
 C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED, C_MAZE_PHYSICS = 32, 33, 34, 35
 R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
     R_MODIFY_SPRITES, R_COND_BEGIN, R_TIMED_BEGIN, R_KEEP_NEAR_CENTER = 64, 65, 66, 67, 68, 69, 70
-R_PORTAL, R_CHANGE_LAYER = 71, 72
+R_PORTAL, R_CHANGE_LAYER, R_CREATE_SPRITES = 71, 72, 73
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
-    SC_BINARY, SC_NOT, SC_FIRST = 160, 161, 162, 163, 164, 165, 166, 167, 168
+    SC_BINARY, SC_NOT, SC_FIRST, SC_BERNOULLI = 160, 161, 162, 163, 164, 165, 166, 167, 168, 169
 Z_GENERATE = 192
 Z_N_ATTRS, Z_SHAPE_ATTR = 14, 13
 ZK_CONST, ZK_UNIFORM32, ZK_DISCRETE = 0, 1, 2
@@ -481,6 +481,7 @@ def _compile_actions(prog, action_space):
 # ---------------------------------------------------------------------------
 
 MAX_COND_DEPTH = 4   # MOOG_MAX_COND_DEPTH (csrc/moog_step.cu rules_step: explicit block stack)
+CREATE_HEADROOM = 16  # default room for the sprites CreateSprites makes (compile_config)
 
 
 def _rule_specs(prog, rule, out, depth=0):
@@ -551,6 +552,20 @@ def _rule_specs(prog, rule, out, depth=0):
         code = lambdas.compile_sprite_predicate(rule._filter_fn)
         out.append(dict(kind=R_CHANGE_LAYER, i=(prog.layer_index(rule._old_layer), prog.layer_index(rule._new_layer),
                                                 prog.add_expr(code))))
+    elif k == 'CreateSprites':
+        # create_sprites.py:27-34; the generator's recipe is sampled on the device (Philox), like a reset group
+        gen = rule._generator
+        if not hasattr(gen, 'factor_dist'):
+            raise CompileError('CreateSprites needs a generator made by sprite_generators.generate_sprites')
+        if callable(gen.num_sprites):
+            raise CompileError('CreateSprites with a random number of sprites per call is not on the accelerated path')
+        lay = prog.layer_index(rule._layer)
+        table, meta_flags, ext = _sampler_group(prog, gen.factor_dist, lay)
+        t_start = _emit_sampler_table(prog, table, ext)
+        ls, ln = prog.add_list(_as_list(rule._without_overlapping))
+        out.append(dict(kind=R_CREATE_SPRITES, flags=FL_FAIL_GRACEFULLY if gen.fail_gracefully else 0,
+                        i=(lay, int(gen.num_sprites), ls, ln, t_start, meta_flags),
+                        p=(float(gen.max_recursion_depth),)))
     elif k == 'KeepNearCenter':
         layers = list(rule._layers_to_center)
         ls, ln = prog.add_list(layers)
@@ -572,6 +587,27 @@ def _layer_moves(rules):
         elif hasattr(r, '_rules'):
             out += _layer_moves(r._rules)
     return out
+
+
+def _created(rules):
+    """(layer, generator) of every CreateSprites rule, nested ones included."""
+    out = []
+    for r in (rules or ()):
+        if _kind(r) == 'CreateSprites':
+            out.append((r._layer, r._generator))
+        elif hasattr(r, '_rules'):
+            out += _created(r._rules)
+    return out
+
+
+def _generator_outline(gen):
+    """Most vertices a sprite drawn from the generator's factor distribution can have."""
+    from moog import sprite as sprite_lib
+    flat, _ = _lower_distribution(gen.factor_dist)
+    leaf = flat.get('shape', ('discrete', [_sprite_defaults()['shape']]))
+    if leaf[0] != 'discrete':
+        raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
+    return max(len(sprite_lib.Sprite(x=0., y=0., shape=shape).vertices) for shape in leaf[1])
 
 
 def _compile_rules(prog, rules):
@@ -676,6 +712,13 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     moves = _layer_moves(config.get('game_rules', ()))
     for old, new in moves:
         caps[prog.layer_names.index(new)] += caps[prog.layer_names.index(old)]
+    # CreateSprites appends to a layer for as long as the episode lasts (create_sprites.py:27-34); the
+    # record gives the layer room for CREATE_HEADROOM more sprites unless `layer_capacity` says how many
+    # (an env whose layer is full flags MOOG_ERR_LAYER_OVERFLOW and creates nothing)
+    created = [(name, gen) for name, gen in _created(config.get('game_rules', ())) if hasattr(gen, 'factor_dist')]
+    for name in {name for name, _ in created}:
+        if name not in (layer_capacity or {}):
+            caps[prog.layer_names.index(name)] += CREATE_HEADROOM
     for name, cap in (layer_capacity or {}).items():
         caps[prog.layer_index(name)] = max(cap, caps[prog.layer_index(name)])
     prog.layer_cap = [int(c) for c in caps]
@@ -693,6 +736,9 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     for old, new in moves:
         io, in_ = prog.layer_names.index(old), prog.layer_names.index(new)
         vcap[in_] = max(vcap[in_], vcap[io])
+    for name, gen in created:
+        il = prog.layer_names.index(name)
+        vcap[il] = max(vcap[il], _generator_outline(gen))
     prog.layer_vcap = vcap
     voff = [0]
     for cap, vc in zip(caps, vcap):
@@ -1058,6 +1104,8 @@ def _check_outline_caps(prog):
             geom.update(i[0:2])
         elif k in (R_MODIFY_ON_CONTACT, T_CONTACT_REWARD, SC_CONTACT_ANY_COUNT):
             geom.update(layers_of_list(i[0], i[1]) + layers_of_list(i[2], i[3]))
+        elif k == R_CREATE_SPRITES and i[3] > 0:
+            geom.update([i[0]] + layers_of_list(i[2], i[3]))
         elif k == Z_GENERATE:
             slots = [i[0]] + [prog.ipool[i[2] + q] for q in range(i[3])]
             for s in slots:

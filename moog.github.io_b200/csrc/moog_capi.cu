@@ -71,6 +71,7 @@ bool set_launch_option(LaunchOptions &o, const char *name, int value) {
   else if (n == "tail_busy_thr") o.tail_busy_thr = value;
   else if (n == "render_epb") o.render_epb = value;
   else if (n == "trace_times") o.trace_times = value;
+  else if (n == "seed") o.seed = value;
   else return false;
   return true;
 }
@@ -306,6 +307,7 @@ int moog_env_post_reset(moog_program *p, const moog_state *st, int n_envs, const
   moog_step_io io;
   memset(&io, 0, sizeof(io));
   io.rule_noise = rule_noise;
+  if (p) io.seed = (uint64_t)(uint32_t)p->opt.seed;
   return run_step(p, st, n_envs, moog::MODE_POST_RESET, &io, 0, 0, nullptr, stream);
 }
 

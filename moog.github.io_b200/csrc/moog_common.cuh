@@ -80,6 +80,7 @@ struct LaunchOptions {
   int tail_busy_thr = 1;      // "tail_busy_thr": envs stepped on an SM from which its render CTAs stand back
   int render_epb = 0;         // "render_epb": envs per CTA of the stand-alone render kernel
   int trace_times = 0;        // "trace_times": per-env globaltimer stamps in io.counters (diagnostic)
+  int seed = 0;               // "seed": the draws of moog_env_post_reset (which has no io.seed of its own)
 };
 LaunchOptions launch_options_from_env();
 bool set_launch_option(LaunchOptions &o, const char *name, int value);

@@ -2513,11 +2513,20 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
   return sp ? st[sp - 1] : 1.0;
 }
 
+// The step's uniform of one rule-noise column: supplied by the caller (io.rule_noise), else drawn from the
+// Philox stream keyed by (seed, env, number of rules_step passes so far, episode, column)
+__device__ double rule_noise_at(const Env &e, int col) {
+  if (e.rule_noise) return e.rule_noise[col];
+  return philox_uniform(e.seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_RULE_PASSES],
+                        (uint32_t)e.envi[MOOG_EI_EPISODES], (uint32_t)col);
+}
+
 __device__ __noinline__ double eval_condition_leaf(const Env &, int op_index) {
   const Env e = env_view();
   const moog_op *op = e.ops + op_index;
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
+    case MOOG_SC_BERNOULLI: return rule_noise_at(e, op->i[0]) < op->p[0];  // np.random.binomial(1, p)
     case MOOG_SC_ALL:
     case MOOG_SC_ANY:
     case MOOG_SC_COUNT: {
@@ -2648,10 +2657,239 @@ __device__ inline void vanish(const Env &e, int l, const unsigned *gone) {
   wsync();
 }
 
-__device__ double rule_noise_at(const Env &e, int col) {
-  if (e.rule_noise) return e.rule_noise[col];
-  return philox_uniform(e.seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_STEP_COUNT],
-                        (uint32_t)e.envi[MOOG_EI_EPISODES], (uint32_t)col);
+// ---------------------------------------------------------------------------
+// Device-side reset sampler (SURVEY section 8 f1): one generate_sprites group
+// (state_initialization/sprite_generators.py:26-105) for this env.  Factors are drawn from
+// the Philox stream keyed by (seed, env, episode, slot, try, factor); the sprite is built
+// like Sprite.__init__ does on the host (sprite.py:261-424: centroid-centred outline scaled
+// by (scale, scale * aspect_ratio), rotated, translated; position += raw centroid;
+// circumscribed radius; inertia * scale^2) and redrawn while it overlaps a sprite it must avoid.
+// ---------------------------------------------------------------------------
+// one factor from a leaf sampler (MOOG_ZK_*): a constant, np.float32(rng.uniform(lo, hi)), or one of n values
+__device__ __forceinline__ double sample_leaf(const double *dpool, int kind, int idx, int n, double u) {
+  if (kind == MOOG_ZK_CONST) return dpool[idx];
+  if (kind == MOOG_ZK_UNIFORM32) return (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);
+  const int pick = (int)(u * n);
+  return dpool[idx + (pick < n ? pick : n - 1)];
+}
+
+// A DependentDistribution's expression (distributions.py:420-470) over the factors drawn so far:
+// the arithmetic subset of the expression VM, X_ATTR0 reading factor `arg` of the sample
+__device__ inline double eval_factor_expr(const moog_ex *x, const double *v) {
+  double st[16];
+  int sp = 0;
+  for (; x->op != MOOG_X_END && sp < 15; ++x) {
+    double a, b;
+    switch (x->op) {
+      case MOOG_X_CONST: st[sp++] = x->c; break;
+      case MOOG_X_ATTR0: st[sp++] = v[x->arg]; break;
+      case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
+      case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      default:
+        if (sp < 2) return NAN;
+        b = st[--sp];
+        a = st[--sp];
+        switch (x->op) {
+          case MOOG_X_LT: a = a < b; break;
+          case MOOG_X_LE: a = a <= b; break;
+          case MOOG_X_GT: a = a > b; break;
+          case MOOG_X_GE: a = a >= b; break;
+          case MOOG_X_EQ: a = a == b; break;
+          case MOOG_X_NE: a = a != b; break;
+          case MOOG_X_AND: a = (a != 0) && (b != 0); break;
+          case MOOG_X_OR: a = (a != 0) || (b != 0); break;
+          case MOOG_X_ADD: a = a + b; break;
+          case MOOG_X_SUB: a = a - b; break;
+          case MOOG_X_MUL: a = a * b; break;
+          case MOOG_X_DIV: a = a / b; break;
+          default: a = NAN; break;
+        }
+        st[sp++] = a;
+    }
+  }
+  return sp ? st[sp - 1] : NAN;
+}
+
+// One generate_sprites call.  op: a MOOG_Z_GENERATE (reset) or MOOG_R_CREATE_SPRITES (rule) op -- both carry
+// the sampler table in i[4], the dtype flags in i[5] and max_recursion_depth in p[0].  The `count`
+// sprites go to slots first.. of `layer`; they must not overlap the slots avoid[0..n_avoid)
+// (avoid_layers = 0) or the sprites that the LAYERS avoid[..] held when the call began
+// (avoid_layers = 1: create_sprites.py:31-33).  Draws: Philox(key; env, c1, slot << 20 | try, tag | factor).
+__device__ __noinline__ void generate_sprites_dev(const Env &, const moog_op *op, uint64_t key, uint32_t c1, int layer,
+                                                  int first, int count, const int32_t *avoid, int n_avoid,
+                                                  int avoid_layers) {
+  const Env e = env_view();
+  const double *dpool = e.dpool;
+  const int32_t *shape_off = e.ipool + e.hdr[MOOG_H_SHAPE_TAB];
+  const int32_t *tab = e.ipool + op->i[4];
+  const int max_depth = (int)fmin(op->p[0], 1048575.0);
+  const uint32_t episode = c1;
+  int placed = 0;
+  for (int k = 0; k < count; ++k) {
+    const int s = first + k;
+    bool stop = false;
+    for (int tries = 0;; ++tries) {
+      double v[MOOG_Z_N_ATTRS];
+#pragma unroll 1
+      for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
+        const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
+        const double u = kind == MOOG_ZK_CONST ? 0.0
+                                               : philox_uniform(key, (uint32_t)e.env_id, episode,
+                                                                ((uint32_t)s << 20) | (uint32_t)tries, (0x5Au << 24) | (uint32_t)a);
+        v[a] = sample_leaf(dpool, kind, idx, n, u);
+      }
+      {
+        // extension components of the factor distribution (distributions.py: Mixture picks one
+        // alternative; SetMinus / Selection redraw their base until it is outside / inside a box)
+        const int32_t *x = tab + 3 * MOOG_Z_N_ATTRS;
+        const int n_ext = *x++;
+        uint32_t draw = 0;
+        for (int c = 0; c < n_ext; ++c) {
+          const int kind = *x++;
+          if (kind == 3) {  // DependentDistribution: attr, expression, float32?
+            const int n_dep = *x++;
+            for (int q = 0; q < n_dep; ++q, x += 3) {
+              const double val = eval_factor_expr(e.expr + x[1], v);
+              v[x[0]] = x[2] ? (double)(float)val : val;
+            }
+          } else if (kind == 1) {
+            const int n_alt = *x++;
+            const double *cum = dpool + *x++;
+            const double u = philox_uniform(key, (uint32_t)e.env_id, episode,
+                                            ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
+            int pick = 0;
+            while (pick < n_alt - 1 && !(u < cum[pick])) ++pick;   // rng.choice(n, p=probs)
+            for (int a = 0; a < n_alt; ++a) {
+              const int n_leaves = *x++;
+              for (int q = 0; q < n_leaves; ++q, x += 4) {
+                if (a != pick) continue;
+                const double uu = philox_uniform(key, (uint32_t)e.env_id, episode,
+                                                 ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
+                v[x[0]] = sample_leaf(dpool, x[1], x[2], x[3], uu);
+              }
+            }
+          } else {
+            const int keep_inside = *x++;
+            const int n_leaves = *x++;
+            const int32_t *leaves = x;
+            x += 4 * n_leaves;
+            const int n_box = *x++;
+            const int32_t *box = x;
+            x += 2 * n_box;
+            // distributions.py:341-349, 394-404: redraw the base until it is outside / inside the box,
+            // at most _MAX_TRIES = 1e5 times, then raise
+            bool accepted = false;
+            for (int inner = 0; inner < 100000 && !accepted; ++inner) {
+              for (int q = 0; q < n_leaves; ++q) {
+                const double uu = philox_uniform(key, (uint32_t)e.env_id, episode,
+                                                 ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
+                v[leaves[4 * q]] = sample_leaf(dpool, leaves[4 * q + 1], leaves[4 * q + 2], leaves[4 * q + 3], uu);
+              }
+              bool inside = true;
+              for (int q = 0; q < n_box; ++q) {
+                const double val = v[box[2 * q]], lo = dpool[box[2 * q + 1]], hi = dpool[box[2 * q + 1] + 1];
+                inside = inside && val >= lo && val < hi;   // Continuous.contains
+              }
+              accepted = inside == (keep_inside != 0);
+            }
+            if (!accepted) {  // the reference raises ValueError here; the env carries the error bit
+              const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_RESET_REJECTED;
+              wsync();
+              puti(e, &e.envi[MOOG_EI_ERR], err);
+              wsync();
+            }
+          }
+        }
+      }
+      const double *R = dpool + shape_off[(int)v[MOOG_Z_SHAPE_ATTR]];
+      const int nv = (int)R[0];
+      const double px = v[MOOG_AT_X] + R[4], py = v[MOOG_AT_Y] + R[5];
+      const double sx = v[MOOG_AT_SCALE], sy = v[MOOG_AT_SCALE] * v[MOOG_AT_ASPECT_RATIO];
+      double c = 1.0, sn = v[MOOG_AT_ANGLE];
+      if (v[MOOG_AT_ANGLE] != 0.0) {
+        const double2 cs = cos_sin_ol(v[MOOG_AT_ANGLE]);
+        c = cs.x;
+        sn = cs.y;
+      }
+      const double m00 = c * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = c * sy;
+      wsync();
+      double r = 0.0;
+      for (int i = e.lane; i < nv; i += 32) {
+        const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
+        const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
+        e.vtx[e.voff[s] + i] = make_double2(wx, wy);
+        const double rx = wx - px, ry = wy - py;
+        r = fmax(r, sqrt(rx * rx + ry * ry));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r = fmax(r, shflx_d(r, o));
+      if (e.lane == 0) {
+        DYN(e, MOOG_D_X, s) = px; DYN(e, MOOG_D_Y, s) = py;
+        DYN(e, MOOG_D_VX, s) = v[MOOG_AT_X_VEL]; DYN(e, MOOG_D_VY, s) = v[MOOG_AT_Y_VEL];
+        DYN(e, MOOG_D_ANG, s) = v[MOOG_AT_ANGLE]; DYN(e, MOOG_D_ANGVEL, s) = v[MOOG_AT_ANGLE_VEL];
+        STAT(e, MOOG_S_MASS, s) = v[MOOG_AT_MASS]; STAT(e, MOOG_S_SCALE, s) = v[MOOG_AT_SCALE];
+        STAT(e, MOOG_S_ASPECT, s) = v[MOOG_AT_ASPECT_RATIO];
+        STAT(e, MOOG_S_IX, s) = R[2] * (sx * sx); STAT(e, MOOG_S_IY, s) = R[3] * (sy * sy);
+        STAT(e, MOOG_S_MAXR, s) = r;
+        STAT(e, MOOG_S_C0, s) = v[MOOG_AT_C0]; STAT(e, MOOG_S_C1, s) = v[MOOG_AT_C1];
+        STAT(e, MOOG_S_C2, s) = v[MOOG_AT_C2]; STAT(e, MOOG_S_OPACITY, s) = v[MOOG_AT_OPACITY];
+        META(e, MOOG_M_SHAPE, s) = (int)v[MOOG_Z_SHAPE_ATTR];
+        META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
+        META(e, MOOG_M_NV, s) = nv;
+        e.cnt[layer] = s - LOFF(e, layer) + 1;
+      }
+      wsync();
+      refresh_all_boxes(e);
+      bool hit = false;
+      if (avoid_layers) {
+        for (int q = 0; q < n_avoid; ++q) {
+          const int la = avoid[q], n_la = la == layer ? first - LOFF(e, la) : e.cnt[la];
+          for (int j = 0; j < n_la; ++j) hit |= overlaps(e, s, LOFF(e, la) + j);
+        }
+      } else {
+        for (int q = 0; q < n_avoid; ++q) hit |= overlaps(e, s, avoid[q]);  // every pair is evaluated
+      }
+      if (op->flags & MOOG_FL_DISJOINT)
+        for (int j = first; j < s; ++j) hit |= overlaps(e, s, j);
+      if (!hit) break;
+      if (tries > max_depth) {  // sprite_generators.py:92-98
+        if (op->flags & MOOG_FL_FAIL_GRACEFULLY) {
+          stop = true;
+        } else {
+          const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_RESET_REJECTED;
+          wsync();
+          puti(e, &e.envi[MOOG_EI_ERR], err);
+          wsync();
+        }
+        break;
+      }
+    }
+    if (stop) break;
+    placed = k + 1;
+  }
+  wsync();
+  puti(e, &e.cnt[layer], first - LOFF(e, layer) + placed);
+  wsync();
+}
+
+// sprite_generators.py:26-105 at a reset: the group's slots are fixed by the traced initializer
+__device__ inline void reset_generate(const Env &e, const moog_op *op, uint64_t seed) {
+  const int first = op->i[0];
+  int count = op->i[1];
+  if (op->p[2] > op->p[1]) {  // num_sprites = np.random.randint(p1, p2): drawn per env and episode
+    const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_EPISODES],
+                                    ((uint32_t)first << 20) | 0xfffffu, (0x5Cu << 24));
+    const int lo = (int)op->p[1], hi = (int)op->p[2];
+    int c = lo + (int)(u * (double)(hi - lo));
+    if (c >= hi) c = hi - 1;
+    if (c < count) count = c < 0 ? 0 : c;
+  }
+  int layer = 0;
+  for (int l = 0; l < e.L; ++l)
+    if (first >= LOFF(e, l) && first < LOFF(e, l + 1)) layer = l;
+  generate_sprites_dev(e, op, seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.envi[MOOG_EI_EPISODES], layer, first, count,
+                       e.ipool + op->i[2], op->i[3], 0);
 }
 
 // one non-conditional rule
@@ -2712,6 +2950,24 @@ __device__ __noinline__ void rule_leaf(const Env &, int r) {
         puti(e, &META(e, MOOG_M_FLAGS, s), fl | MOOG_SF_TELEPORTING);
         wsync();
       }
+      return;
+    }
+    case MOOG_R_CREATE_SPRITES: {  // create_sprites.py:27-34
+      const int layer = op->i[0], have = e.cnt[layer], cap = LOFF(e, layer + 1) - LOFF(e, layer);
+      int count = op->i[1];
+      const int serial = e.envi[MOOG_EI_CREATED];
+      wsync();
+      puti(e, &e.envi[MOOG_EI_CREATED], serial + 1);
+      wsync();
+      if (have + count > cap) {  // the reference's lists grow without bound; a layer of the record does not
+        const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_LAYER_OVERFLOW;
+        wsync();
+        puti(e, &e.envi[MOOG_EI_ERR], err);
+        wsync();
+        count = cap - have;
+      }
+      generate_sprites_dev(e, op, e.seed ^ 0x3C6EF372FE94F82Bull, (uint32_t)serial, layer, LOFF(e, layer) + have, count,
+                           e.ipool + op->i[2], op->i[3], 1);
       return;
     }
     case MOOG_R_CHANGE_LAYER: {  // change_layer.py:34-45
@@ -2819,6 +3075,12 @@ __device__ __noinline__ void rules_step(const Env &) {
   const int end = h[MOOG_H_RULES] + h[MOOG_H_N_RULES];
   int blk_start[MOOG_MAX_COND_DEPTH], blk_end[MOOG_MAX_COND_DEPTH], blk_left[MOOG_MAX_COND_DEPTH];
   int depth = 0;
+  {
+    const int passes = e.envi[MOOG_EI_RULE_PASSES] + 1;
+    wsync();
+    puti(e, &e.envi[MOOG_EI_RULE_PASSES], passes);
+    wsync();
+  }
   for (;;) {
     if (depth > 0 && r >= blk_end[depth - 1]) {
       if (--blk_left[depth - 1] > 0) {
@@ -3094,222 +3356,6 @@ __device__ inline void store_env(const Env &e, const moog_state &st, size_t n) {
   wsync();
 }
 
-// ---------------------------------------------------------------------------
-// Device-side reset sampler (SURVEY section 8 f1): one generate_sprites group
-// (state_initialization/sprite_generators.py:26-105) for this env.  Factors are drawn from
-// the Philox stream keyed by (seed, env, episode, slot, try, factor); the sprite is built
-// like Sprite.__init__ does on the host (sprite.py:261-424: centroid-centred outline scaled
-// by (scale, scale * aspect_ratio), rotated, translated; position += raw centroid;
-// circumscribed radius; inertia * scale^2) and redrawn while it overlaps a sprite it must avoid.
-// ---------------------------------------------------------------------------
-// one factor from a leaf sampler (MOOG_ZK_*): a constant, np.float32(rng.uniform(lo, hi)), or one of n values
-__device__ __forceinline__ double sample_leaf(const double *dpool, int kind, int idx, int n, double u) {
-  if (kind == MOOG_ZK_CONST) return dpool[idx];
-  if (kind == MOOG_ZK_UNIFORM32) return (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);
-  const int pick = (int)(u * n);
-  return dpool[idx + (pick < n ? pick : n - 1)];
-}
-
-// A DependentDistribution's expression (distributions.py:420-470) over the factors drawn so far:
-// the arithmetic subset of the expression VM, X_ATTR0 reading factor `arg` of the sample
-__device__ inline double eval_factor_expr(const moog_ex *x, const double *v) {
-  double st[16];
-  int sp = 0;
-  for (; x->op != MOOG_X_END && sp < 15; ++x) {
-    double a, b;
-    switch (x->op) {
-      case MOOG_X_CONST: st[sp++] = x->c; break;
-      case MOOG_X_ATTR0: st[sp++] = v[x->arg]; break;
-      case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
-      case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
-      case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
-      default:
-        if (sp < 2) return NAN;
-        b = st[--sp];
-        a = st[--sp];
-        switch (x->op) {
-          case MOOG_X_LT: a = a < b; break;
-          case MOOG_X_LE: a = a <= b; break;
-          case MOOG_X_GT: a = a > b; break;
-          case MOOG_X_GE: a = a >= b; break;
-          case MOOG_X_EQ: a = a == b; break;
-          case MOOG_X_NE: a = a != b; break;
-          case MOOG_X_AND: a = (a != 0) && (b != 0); break;
-          case MOOG_X_OR: a = (a != 0) || (b != 0); break;
-          case MOOG_X_ADD: a = a + b; break;
-          case MOOG_X_SUB: a = a - b; break;
-          case MOOG_X_MUL: a = a * b; break;
-          case MOOG_X_DIV: a = a / b; break;
-          default: a = NAN; break;
-        }
-        st[sp++] = a;
-    }
-  }
-  return sp ? st[sp - 1] : NAN;
-}
-
-__device__ __noinline__ void reset_generate(const Env &, const moog_op *op, const double *dpool,
-                                            const int32_t *shape_off, uint64_t seed) {
-  const Env e = env_view();
-  const int first = op->i[0];
-  int count = op->i[1];
-  if (op->p[2] > op->p[1]) {  // num_sprites = np.random.randint(p1, p2): drawn per env and episode
-    const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, (uint32_t)e.envi[MOOG_EI_EPISODES],
-                                    ((uint32_t)first << 20) | 0xfffffu, (0x5Cu << 24));
-    const int lo = (int)op->p[1], hi = (int)op->p[2];
-    int c = lo + (int)(u * (double)(hi - lo));
-    if (c >= hi) c = hi - 1;
-    if (c < count) count = c < 0 ? 0 : c;
-  }
-  const int32_t *avoid = e.ipool + op->i[2];
-  const int n_avoid = op->i[3];
-  const int32_t *tab = e.ipool + op->i[4];
-  int layer = 0;
-  for (int l = 0; l < e.L; ++l)
-    if (first >= LOFF(e, l) && first < LOFF(e, l + 1)) layer = l;
-  const int max_depth = (int)fmin(op->p[0], 1048575.0);
-  const uint32_t episode = (uint32_t)e.envi[MOOG_EI_EPISODES];
-  int placed = 0;
-  for (int k = 0; k < count; ++k) {
-    const int s = first + k;
-    bool stop = false;
-    for (int tries = 0;; ++tries) {
-      double v[MOOG_Z_N_ATTRS];
-#pragma unroll 1
-      for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
-        const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
-        const double u = kind == MOOG_ZK_CONST ? 0.0
-                                               : philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                                                ((uint32_t)s << 20) | (uint32_t)tries, (0x5Au << 24) | (uint32_t)a);
-        v[a] = sample_leaf(dpool, kind, idx, n, u);
-      }
-      {
-        // extension components of the factor distribution (distributions.py: Mixture picks one
-        // alternative; SetMinus / Selection redraw their base until it is outside / inside a box)
-        const int32_t *x = tab + 3 * MOOG_Z_N_ATTRS;
-        const int n_ext = *x++;
-        uint32_t draw = 0;
-        for (int c = 0; c < n_ext; ++c) {
-          const int kind = *x++;
-          if (kind == 3) {  // DependentDistribution: attr, expression, float32?
-            const int n_dep = *x++;
-            for (int q = 0; q < n_dep; ++q, x += 3) {
-              const double val = eval_factor_expr(e.expr + x[1], v);
-              v[x[0]] = x[2] ? (double)(float)val : val;
-            }
-          } else if (kind == 1) {
-            const int n_alt = *x++;
-            const double *cum = dpool + *x++;
-            const double u = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                            ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
-            int pick = 0;
-            while (pick < n_alt - 1 && !(u < cum[pick])) ++pick;   // rng.choice(n, p=probs)
-            for (int a = 0; a < n_alt; ++a) {
-              const int n_leaves = *x++;
-              for (int q = 0; q < n_leaves; ++q, x += 4) {
-                if (a != pick) continue;
-                const double uu = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                                 ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
-                v[x[0]] = sample_leaf(dpool, x[1], x[2], x[3], uu);
-              }
-            }
-          } else {
-            const int keep_inside = *x++;
-            const int n_leaves = *x++;
-            const int32_t *leaves = x;
-            x += 4 * n_leaves;
-            const int n_box = *x++;
-            const int32_t *box = x;
-            x += 2 * n_box;
-            // distributions.py:341-349, 394-404: redraw the base until it is outside / inside the box,
-            // at most _MAX_TRIES = 1e5 times, then raise
-            bool accepted = false;
-            for (int inner = 0; inner < 100000 && !accepted; ++inner) {
-              for (int q = 0; q < n_leaves; ++q) {
-                const double uu = philox_uniform(seed ^ 0x6A09E667F3BCC908ull, (uint32_t)e.env_id, episode,
-                                                 ((uint32_t)s << 20) | (uint32_t)tries, (0x5Bu << 24) | (draw++ & 0xffffffu));
-                v[leaves[4 * q]] = sample_leaf(dpool, leaves[4 * q + 1], leaves[4 * q + 2], leaves[4 * q + 3], uu);
-              }
-              bool inside = true;
-              for (int q = 0; q < n_box; ++q) {
-                const double val = v[box[2 * q]], lo = dpool[box[2 * q + 1]], hi = dpool[box[2 * q + 1] + 1];
-                inside = inside && val >= lo && val < hi;   // Continuous.contains
-              }
-              accepted = inside == (keep_inside != 0);
-            }
-            if (!accepted) {  // the reference raises ValueError here; the env carries the error bit
-              const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_RESET_REJECTED;
-              wsync();
-              puti(e, &e.envi[MOOG_EI_ERR], err);
-              wsync();
-            }
-          }
-        }
-      }
-      const double *R = dpool + shape_off[(int)v[MOOG_Z_SHAPE_ATTR]];
-      const int nv = (int)R[0];
-      const double px = v[MOOG_AT_X] + R[4], py = v[MOOG_AT_Y] + R[5];
-      const double sx = v[MOOG_AT_SCALE], sy = v[MOOG_AT_SCALE] * v[MOOG_AT_ASPECT_RATIO];
-      double c = 1.0, sn = v[MOOG_AT_ANGLE];
-      if (v[MOOG_AT_ANGLE] != 0.0) {
-        const double2 cs = cos_sin_ol(v[MOOG_AT_ANGLE]);
-        c = cs.x;
-        sn = cs.y;
-      }
-      const double m00 = c * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = c * sy;
-      wsync();
-      double r = 0.0;
-      for (int i = e.lane; i < nv; i += 32) {
-        const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
-        const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
-        e.vtx[e.voff[s] + i] = make_double2(wx, wy);
-        const double rx = wx - px, ry = wy - py;
-        r = fmax(r, sqrt(rx * rx + ry * ry));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) r = fmax(r, shflx_d(r, o));
-      if (e.lane == 0) {
-        DYN(e, MOOG_D_X, s) = px; DYN(e, MOOG_D_Y, s) = py;
-        DYN(e, MOOG_D_VX, s) = v[MOOG_AT_X_VEL]; DYN(e, MOOG_D_VY, s) = v[MOOG_AT_Y_VEL];
-        DYN(e, MOOG_D_ANG, s) = v[MOOG_AT_ANGLE]; DYN(e, MOOG_D_ANGVEL, s) = v[MOOG_AT_ANGLE_VEL];
-        STAT(e, MOOG_S_MASS, s) = v[MOOG_AT_MASS]; STAT(e, MOOG_S_SCALE, s) = v[MOOG_AT_SCALE];
-        STAT(e, MOOG_S_ASPECT, s) = v[MOOG_AT_ASPECT_RATIO];
-        STAT(e, MOOG_S_IX, s) = R[2] * (sx * sx); STAT(e, MOOG_S_IY, s) = R[3] * (sy * sy);
-        STAT(e, MOOG_S_MAXR, s) = r;
-        STAT(e, MOOG_S_C0, s) = v[MOOG_AT_C0]; STAT(e, MOOG_S_C1, s) = v[MOOG_AT_C1];
-        STAT(e, MOOG_S_C2, s) = v[MOOG_AT_C2]; STAT(e, MOOG_S_OPACITY, s) = v[MOOG_AT_OPACITY];
-        META(e, MOOG_M_SHAPE, s) = (int)v[MOOG_Z_SHAPE_ATTR];
-        META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
-        META(e, MOOG_M_NV, s) = nv;
-        e.cnt[layer] = s - LOFF(e, layer) + 1;
-      }
-      wsync();
-      refresh_all_boxes(e);
-      bool hit = false;
-      for (int q = 0; q < n_avoid; ++q) hit |= overlaps(e, s, avoid[q]);  // every pair is evaluated
-      if (op->flags & MOOG_FL_DISJOINT)
-        for (int j = first; j < s; ++j) hit |= overlaps(e, s, j);
-      if (!hit) break;
-      if (tries > max_depth) {  // sprite_generators.py:92-98
-        if (op->flags & MOOG_FL_FAIL_GRACEFULLY) {
-          stop = true;
-        } else {
-          const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_RESET_REJECTED;
-          wsync();
-          puti(e, &e.envi[MOOG_EI_ERR], err);
-          wsync();
-        }
-        break;
-      }
-    }
-    if (stop) break;
-    placed = k + 1;
-  }
-  wsync();
-  puti(e, &e.cnt[layer], first - LOFF(e, layer) + placed);
-  wsync();
-}
-
 // environment.py:88-96: task / action reset, every rule reset and stepped once
 __device__ inline void post_reset(const Env &e) {
   wsync();
@@ -3424,7 +3470,7 @@ __device__ __forceinline__ void owner_warp(const StepArgs &a, unsigned char *sme
   if (do_reset && a.io.sample_resets && pv.hdr[MOOG_H_N_RESET] > 0) {
     // the generated sprites of the template are drawn afresh for this env and episode
     for (int z = 0; z < pv.hdr[MOOG_H_N_RESET]; ++z)
-      reset_generate(e, pv.ops + pv.hdr[MOOG_H_RESET] + z, pv.dpool, pv.ipool + pv.hdr[MOOG_H_SHAPE_TAB], a.io.seed);
+      reset_generate(e, pv.ops + pv.hdr[MOOG_H_RESET] + z, a.io.seed);
   }
 
   double reward = 0.0;

@@ -701,10 +701,42 @@ class _StateLowering(object):
         if isinstance(node, ast.Name) and node.id in self.ns and isinstance(
                 self.ns[node.id], (bool, int, float)):
             return ('const', float(self.ns[node.id]))
+        bern = self._bernoulli(node)
+        if bern is not None:
+            return bern
         first = self._trace_first(node)
         if first is not None:
             return first
         self.fail(node)
+
+    def _bernoulli(self, node):
+        """`np.random.binomial(1, p)` with a constant p (first_person_predators_prey.py:181,190) ->
+        MOOG_SC_BERNOULLI: true when the step's uniform of a rule-noise column of its own is < p."""
+        if not isinstance(node, ast.Call):
+            return None
+        try:
+            func = eval(compile(ast.Expression(node.func), '<cond>', 'eval'), self.ns)  # pylint: disable=eval-used
+        except Exception:  # pylint: disable=broad-except
+            return None
+        if func is not np.random.binomial:
+            return None
+        try:
+            args = [eval(compile(ast.Expression(a), '<cond>', 'eval'), self.ns) for a in node.args]  # pylint: disable=eval-used
+            kwargs = {k.arg: eval(compile(ast.Expression(k.value), '<cond>', 'eval'), self.ns)  # pylint: disable=eval-used
+                      for k in node.keywords}
+        except Exception:  # pylint: disable=broad-except
+            self.fail(node)
+        names = ('n', 'p', 'size')
+        for k, v in zip(names, args):
+            kwargs[k] = v
+        if set(kwargs) - set(names) or kwargs.get('size') is not None or kwargs.get('n') != 1 or 'p' not in kwargs:
+            self.fail(node)
+        p = float(kwargs['p'])
+        if not 0.0 <= p <= 1.0:
+            self.fail(node)
+        col = self.prog.rule_noise_dim
+        self.prog.rule_noise_dim += 1
+        return ('op', self.prog.emit(169, 0, (col,), (p,)))  # MOOG_SC_BERNOULLI
 
     def _trace_first(self, node):
         """An expression over `state[layer][0]` (one layer), e.g. pacman.py's

@@ -167,6 +167,17 @@ class ChangeLayer(AbstractRule):
         self._filter_fn = filter_fn if filter_fn is not None else (lambda s: True)
 
 
+class CreateSprites(AbstractRule):
+    """Appends the sprites `generator(without_overlapping=<the sprites of those layers>)` returns to
+    `layer` (create_sprites.py:8-34).  `generator` must come from
+    sprite_generators.generate_sprites: its factor distribution is what the device draws from."""
+
+    def __init__(self, layer, generator, without_overlapping=()):
+        self._layer = layer
+        self._generator = generator
+        self._without_overlapping = without_overlapping
+
+
 def _out_of_scope(name, where):
     def _ctor(*args, **kwargs):
         raise NotImplementedError(
@@ -177,7 +188,6 @@ def _out_of_scope(name, where):
     return _ctor
 
 
-CreateSprites = _out_of_scope('CreateSprites', 'create_sprites.py')
 Fixation = _out_of_scope('Fixation', 'fixation.py')
 ModifyMetaState = _out_of_scope('ModifyMetaState', 'modify_meta_state.py')
 UpdateMetaStateValue = _out_of_scope(

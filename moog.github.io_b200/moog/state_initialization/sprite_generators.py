@@ -86,6 +86,11 @@ def generate_sprites(factor_dist, num_sprites=1, max_recursion_depth=int(1e4),
                 max_recursion_depth=max_recursion_depth, fail_gracefully=bool(fail_gracefully)))
         return out
 
+    # what moog_b200.compiler lowers a game_rules.CreateSprites(generator=_generate) from
+    _generate.factor_dist = factor_dist
+    _generate.num_sprites = num_sprites
+    _generate.max_recursion_depth = max_recursion_depth
+    _generate.fail_gracefully = bool(fail_gracefully)
     return _generate
 
 

@@ -140,6 +140,8 @@ typedef struct {
   const int32_t *voff;  /* [S+1] first vertex of each slot          */
   const double *dpool;  /* shape records / sampler parameters       */
   const double *noise; /* [K][noise_dim] uniforms in [0,1) for this step, or NULL */
+  const double *rule_noise; /* [rule_noise_dim] uniforms of the rules pass being made, or NULL */
+  int env_id;               /* row of the batch: a key of the counter-based draws */
   int substep;
   /* instrumentation for parity tests */
   int64_t n_overlap_calls, n_overlap_true, n_collisions;
@@ -1522,11 +1524,222 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
 }
 
 /* state conditions */
+/* ------------------------------------------------------------------------ */
+/* counter-based draws (Philox4x32-10)                                        */
+/*                                                                            */
+/* The reference draws from np.random's global Mersenne Twister, in Python   */
+/* call order; a batch of envs stepped concurrently cannot share that stream, */
+/* so the CUDA path keys every draw by (seed, env, counters).  This is the    */
+/* same generator restated, so that trajectories with CreateSprites / random  */
+/* conditions can be compared draw for draw; that the DISTRIBUTIONS are the   */
+/* reference's is what tests/test_create_sprites.py checks against it.        */
+/* ------------------------------------------------------------------------ */
+static uint64_t g_seed = 0;
+void orc_set_seed(uint64_t seed) { g_seed = seed; }
+
+static double philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t m0 = (uint64_t)0xD2511F53u * c0, m1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(m1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)m1, n2 = (uint32_t)(m0 >> 32) ^ c3 ^ k1,
+                   n3 = (uint32_t)m0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint64_t bits = ((uint64_t)c0 << 21) ^ (uint64_t)(c1 >> 11);
+  return (double)(bits & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
+
+/* the uniform of one rule-noise column for the rules pass being made */
+static double rule_noise_at(env_t *e, int col) {
+  if (e->rule_noise) return e->rule_noise[col];
+  return philox_uniform(g_seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)e->env_id, (uint32_t)e->envi[MOOG_EI_RULE_PASSES],
+                        (uint32_t)e->envi[MOOG_EI_EPISODES], (uint32_t)col);
+}
+
+/* one factor from a leaf sampler: a constant, np.float32(rng.uniform(lo, hi)) (distributions.py:91-93),
+ * or one of n candidates (:127-129) */
+static double sample_leaf(const double *dpool, int kind, int idx, int n, double u) {
+  if (kind == MOOG_ZK_CONST) return dpool[idx];
+  if (kind == MOOG_ZK_UNIFORM32) return (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);
+  const int pick = (int)(u * n);
+  return dpool[idx + (pick < n ? pick : n - 1)];
+}
+
+/* a DependentDistribution's function (distributions.py:420-470) over the factors drawn so far */
+static double eval_factor_expr(const moog_ex *x, const double *v) {
+  double st[16];
+  int sp = 0;
+  for (; x->op != MOOG_X_END && sp < 15; ++x) {
+    double a, b;
+    switch (x->op) {
+      case MOOG_X_CONST: st[sp++] = x->c; break;
+      case MOOG_X_ATTR0: st[sp++] = v[x->arg]; break;
+      case MOOG_X_NOT: st[sp - 1] = !(st[sp - 1] != 0); break;
+      case MOOG_X_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case MOOG_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      default:
+        if (sp < 2) return NAN;
+        b = st[--sp];
+        a = st[--sp];
+        switch (x->op) {
+          case MOOG_X_LT: a = a < b; break;
+          case MOOG_X_LE: a = a <= b; break;
+          case MOOG_X_GT: a = a > b; break;
+          case MOOG_X_GE: a = a >= b; break;
+          case MOOG_X_EQ: a = a == b; break;
+          case MOOG_X_NE: a = a != b; break;
+          case MOOG_X_AND: a = (a != 0) && (b != 0); break;
+          case MOOG_X_OR: a = (a != 0) || (b != 0); break;
+          case MOOG_X_ADD: a = a + b; break;
+          case MOOG_X_SUB: a = a - b; break;
+          case MOOG_X_MUL: a = a * b; break;
+          case MOOG_X_DIV: a = a / b; break;
+          default: a = NAN; break;
+        }
+        st[sp++] = a;
+    }
+  }
+  return sp ? st[sp - 1] : NAN;
+}
+
+/* One call of the closure generate_sprites returns (sprite_generators.py:75-103): `count` sprites
+ * drawn from the op's factor table (i4; extension components: Mixture :278-306, SetMinus :325-349,
+ * Selection / Intersection :376-404, DependentDistribution :420-470) go to slots first.. of `layer`;
+ * each is built like Sprite.__init__ (sprite.py:261-424) and redrawn while it overlaps a sprite it
+ * must avoid -- slots avoid[..], or (avoid_layers, create_sprites.py:31-33) the sprites that the
+ * layers avoid[..] held when the call began.  Draw k of sprite s, try t: Philox(key; env, c1, s << 20 | t, tag | k). */
+static void generate_sprites(env_t *e, const moog_op *op, uint64_t key, uint32_t c1, int layer, int first,
+                             int count, const int32_t *avoid, int n_avoid, int avoid_layers) {
+  const double *dpool = e->dpool;
+  const int32_t *shape_off = e->ipool + e->hdr[MOOG_H_SHAPE_TAB];
+  const int32_t *tab = e->ipool + op->i[4];
+  const int max_depth = (int)fmin(op->p[0], 1048575.0);
+  int placed = 0;
+  for (int k = 0; k < count; ++k) {
+    const int s = first + k;
+    int stop = 0;
+    for (int tries = 0;; ++tries) {
+      double v[MOOG_Z_N_ATTRS];
+      const uint32_t c2 = ((uint32_t)s << 20) | (uint32_t)tries;
+      for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
+        const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
+        const double u = kind == MOOG_ZK_CONST ? 0.0 : philox_uniform(key, (uint32_t)e->env_id, c1, c2, (0x5Au << 24) | (uint32_t)a);
+        v[a] = sample_leaf(dpool, kind, idx, n, u);
+      }
+      const int32_t *x = tab + 3 * MOOG_Z_N_ATTRS;
+      const int n_ext = *x++;
+      uint32_t draw = 0;
+      for (int c = 0; c < n_ext; ++c) {
+        const int kind = *x++;
+        if (kind == 3) {
+          const int n_dep = *x++;
+          for (int q = 0; q < n_dep; ++q, x += 3) {
+            const double val = eval_factor_expr(e->expr + x[1], v);
+            v[x[0]] = x[2] ? (double)(float)val : val;
+          }
+        } else if (kind == 1) {
+          const int n_alt = *x++;
+          const double *cum = dpool + *x++;
+          const double u = philox_uniform(key, (uint32_t)e->env_id, c1, c2, (0x5Bu << 24) | (draw++ & 0xffffffu));
+          int pick = 0;
+          while (pick < n_alt - 1 && !(u < cum[pick])) ++pick; /* rng.choice(n, p=probs) */
+          for (int a = 0; a < n_alt; ++a) {
+            const int n_leaves = *x++;
+            for (int q = 0; q < n_leaves; ++q, x += 4) {
+              if (a != pick) continue;
+              const double uu = philox_uniform(key, (uint32_t)e->env_id, c1, c2, (0x5Bu << 24) | (draw++ & 0xffffffu));
+              v[x[0]] = sample_leaf(dpool, x[1], x[2], x[3], uu);
+            }
+          }
+        } else {
+          const int keep_inside = *x++;
+          const int n_leaves = *x++;
+          const int32_t *leaves = x;
+          x += 4 * n_leaves;
+          const int n_box = *x++;
+          const int32_t *box = x;
+          x += 2 * n_box;
+          int accepted = 0; /* at most _MAX_TRIES = 1e5 redraws, then the reference raises */
+          for (int inner = 0; inner < 100000 && !accepted; ++inner) {
+            for (int q = 0; q < n_leaves; ++q) {
+              const double uu = philox_uniform(key, (uint32_t)e->env_id, c1, c2, (0x5Bu << 24) | (draw++ & 0xffffffu));
+              v[leaves[4 * q]] = sample_leaf(dpool, leaves[4 * q + 1], leaves[4 * q + 2], leaves[4 * q + 3], uu);
+            }
+            int inside = 1;
+            for (int q = 0; q < n_box; ++q) {
+              const double val = v[box[2 * q]], lo = dpool[box[2 * q + 1]], hi = dpool[box[2 * q + 1] + 1];
+              inside = inside && val >= lo && val < hi; /* Continuous.contains */
+            }
+            accepted = inside == (keep_inside != 0);
+          }
+          if (!accepted) e->envi[MOOG_EI_ERR] |= MOOG_ERR_RESET_REJECTED;
+        }
+      }
+      const double *R = dpool + shape_off[(int)v[MOOG_Z_SHAPE_ATTR]];
+      const int nv = (int)R[0];
+      const double px = v[MOOG_AT_X] + R[4], py = v[MOOG_AT_Y] + R[5];
+      const double sx = v[MOOG_AT_SCALE], sy = v[MOOG_AT_SCALE] * v[MOOG_AT_ASPECT_RATIO];
+      double cs = 1.0, sn = v[MOOG_AT_ANGLE];
+      if (v[MOOG_AT_ANGLE] != 0.0) {
+        cs = cos(v[MOOG_AT_ANGLE]);
+        sn = sin(v[MOOG_AT_ANGLE]);
+      }
+      const double m00 = cs * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = cs * sy;
+      double *w = e->vtx + 2 * (size_t)e->voff[s];
+      double r = 0.0;
+      for (int i = 0; i < nv; ++i) {
+        const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
+        const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
+        w[2 * i] = wx;
+        w[2 * i + 1] = wy;
+        r = fmax(r, norm_ax(wx - px, wy - py));
+      }
+      DYN(e, MOOG_D_X, s) = px; DYN(e, MOOG_D_Y, s) = py;
+      DYN(e, MOOG_D_VX, s) = v[MOOG_AT_X_VEL]; DYN(e, MOOG_D_VY, s) = v[MOOG_AT_Y_VEL];
+      DYN(e, MOOG_D_ANG, s) = v[MOOG_AT_ANGLE]; DYN(e, MOOG_D_ANGVEL, s) = v[MOOG_AT_ANGLE_VEL];
+      STAT(e, MOOG_S_MASS, s) = v[MOOG_AT_MASS]; STAT(e, MOOG_S_SCALE, s) = v[MOOG_AT_SCALE];
+      STAT(e, MOOG_S_ASPECT, s) = v[MOOG_AT_ASPECT_RATIO];
+      STAT(e, MOOG_S_IX, s) = R[2] * (sx * sx); STAT(e, MOOG_S_IY, s) = R[3] * (sy * sy);
+      STAT(e, MOOG_S_MAXR, s) = r;
+      STAT(e, MOOG_S_C0, s) = v[MOOG_AT_C0]; STAT(e, MOOG_S_C1, s) = v[MOOG_AT_C1];
+      STAT(e, MOOG_S_C2, s) = v[MOOG_AT_C2]; STAT(e, MOOG_S_OPACITY, s) = v[MOOG_AT_OPACITY];
+      META(e, MOOG_M_SHAPE, s) = (int)v[MOOG_Z_SHAPE_ATTR];
+      META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
+      META(e, MOOG_M_NV, s) = nv;
+      e->cnt[layer] = s - LOFF(e, layer) + 1;
+      int hit = 0; /* every pair is evaluated (no short-circuit), sprite_generators.py:69-74 */
+      if (avoid_layers) {
+        for (int q = 0; q < n_avoid; ++q) {
+          const int la = avoid[q], n_la = la == layer ? first - LOFF(e, la) : e->cnt[la];
+          for (int j = 0; j < n_la; ++j) hit |= overlaps(e, s, LOFF(e, la) + j);
+        }
+      } else {
+        for (int q = 0; q < n_avoid; ++q) hit |= overlaps(e, s, avoid[q]);
+      }
+      if (op->flags & MOOG_FL_DISJOINT)
+        for (int j = first; j < s; ++j) hit |= overlaps(e, s, j);
+      if (!hit) break;
+      if (tries > max_depth) { /* sprite_generators.py:92-98 */
+        if (op->flags & MOOG_FL_FAIL_GRACEFULLY)
+          stop = 1;
+        else
+          e->envi[MOOG_EI_ERR] |= MOOG_ERR_RESET_REJECTED;
+        break;
+      }
+    }
+    if (stop) break;
+    placed = k + 1;
+  }
+  e->cnt[layer] = first - LOFF(e, layer) + placed;
+}
+
 static double eval_condition(env_t *e, int op_index) {
   const moog_op *op = e->ops + op_index;
   int sp[MOOG_MAX_SLOTS], sq[MOOG_MAX_SLOTS];
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
+    case MOOG_SC_BERNOULLI: return rule_noise_at(e, op->i[0]) < op->p[0]; /* np.random.binomial(1, p) */
     case MOOG_SC_ALL:
     case MOOG_SC_ANY:
     case MOOG_SC_COUNT: {
@@ -1745,6 +1958,18 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
       vanish(e, lo, gone);
       return 1;
     }
+    case MOOG_R_CREATE_SPRITES: { /* create_sprites.py:27-34 */
+      const int layer = op->i[0], have = e->cnt[layer], cap = LOFF(e, layer + 1) - LOFF(e, layer);
+      int count = op->i[1];
+      const int serial = e->envi[MOOG_EI_CREATED]++;
+      if (have + count > cap) { /* the reference's lists grow without bound; a layer of the record does not */
+        e->envi[MOOG_EI_ERR] |= MOOG_ERR_LAYER_OVERFLOW;
+        count = cap - have;
+      }
+      generate_sprites(e, op, g_seed ^ 0x3C6EF372FE94F82Bull, (uint32_t)serial, layer, LOFF(e, layer) + have, count,
+                       e->ipool + op->i[2], op->i[3], 1);
+      return 1;
+    }
     case MOOG_R_COND_BEGIN: { /* conditional.py:55-58 */
       int times = (int)eval_condition(e, op->i[0]);
       int nsub = op->i[1];
@@ -1775,6 +2000,8 @@ static void rules_reset(env_t *e) {
 static void rules_step(env_t *e, const double *rule_noise) {
   const int32_t *h = e->hdr;
   int r = h[MOOG_H_RULES], end = h[MOOG_H_RULES] + h[MOOG_H_N_RULES];
+  e->envi[MOOG_EI_RULE_PASSES] += 1;
+  e->rule_noise = rule_noise;
   while (r < end) r += rule_step(e, r, rule_noise);
 }
 
@@ -1910,6 +2137,7 @@ typedef struct {
 static void bind_env(env_t *e, const void *blob, const orc_state *st, int n) {
   memset(e, 0, sizeof(*e));
   bind_program(e, blob);
+  e->env_id = n;
   int S = e->S;
   e->dyn = st->dyn + (size_t)n * MOOG_DYN_FIELDS * S;
   e->stat = st->stat + (size_t)n * MOOG_STAT_FIELDS * S;

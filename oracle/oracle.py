@@ -114,6 +114,12 @@ class Oracle(object):
             _ptr(reward), _ptr(step_type), _ptr(self.counters))
         return reward, step_type
 
+    @staticmethod
+    def set_seed(seed):
+        """Key of the counter-based draws (CreateSprites, random conditions without a rule-noise
+        tensor) of the calls that follow: what the CUDA path receives as io.seed."""
+        lib().orc_set_seed(ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF))
+
     def step_auto(self, actions, pool, reset_index, noise=None, rule_noise=None):
         """Environment.step with its auto-reset (environment.py:98-126 incl. :100-101,
         reset() :82-96): envs whose previous transition terminated take row

@@ -1,0 +1,169 @@
+"""`game_rules.CreateSprites` behind `np.random.binomial(1, p)` conditions
+(/root/reference/moog/game_rules/create_sprites.py:8-34, conditional.py:55-58; the pattern of
+moog_demos/example_configs/first_person_predators_prey.py:176-193).
+
+The reference draws from np.random's global stream in Python call order; a batch of envs stepped
+concurrently keys every draw by (seed, env, counters) instead (Philox).  So:
+  * the LOGIC (which sprites a new one must avoid, where it is appended, fail_gracefully, what a
+    rejected try costs, Mixture / SetMinus factor trees, the rules that follow in the same pass) is
+    pinned against the unmodified reference on a trajectory whose draws are replayed into the
+    oracle (tests/golden/spawn_zoo.npz, first_person.npz: test_oracle_replays_reference_*);
+  * the CUDA path is compared with the oracle draw for draw on the Philox stream (gpu tests);
+  * that the Philox draws follow the reference's DISTRIBUTIONS is checked on the factors of the
+    sprites made (test_cuda_created_factors_follow_the_distributions).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from tests import util
+
+
+def _compile(name='spawn_zoo', n_states=6, seed=3):
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    mod = importlib.import_module('moog_b200.configs.' + name)
+    cfg = mod.get_config()
+    np.random.seed(seed)
+    states = [cfg['state_initializer']() for _ in range(n_states)]
+    prog = compiler.compile_config(cfg, states, layer_capacity=mod.LAYER_CAPACITY)
+    pool = compiler.pack_states(prog, states)
+    return cfg, prog, {k: pool[k] for k in util.STATE_KEYS}
+
+
+def test_create_sprites_lowering():
+    """The program holds one MOOG_R_CREATE_SPRITES op per rule, guarded by a MOOG_SC_BERNOULLI condition
+    with a rule-noise column of its own; the growing layers get the room and outline width asked for."""
+    from moog_b200 import compiler as C
+    _, prog, _ = _compile()
+    kinds = [o['kind'] for o in prog.ops]
+    assert kinds.count(C.R_CREATE_SPRITES) == 2 and kinds.count(C.SC_BERNOULLI) == 2
+    bern = [o for o in prog.ops if o['kind'] == C.SC_BERNOULLI]
+    assert sorted(o['i'][0] for o in bern) == [0, 1] and sorted(o['p'][0] for o in bern) == [0.35, 0.6]
+    assert prog.rule_noise_dim == 2
+    assert prog.layer_cap == [2, 32, 32, 1] and prog.layer_vcap[1] == 30 and prog.layer_vcap[2] == 4
+    drops = [o for o in prog.ops if o['kind'] == C.R_CREATE_SPRITES and o['i'][0] == 1][0]
+    assert drops['flags'] & C.FL_FAIL_GRACEFULLY and drops['i'][1] == 1 and drops['p'][0] == 6.0
+    assert [prog.ipool[drops['i'][2] + q] for q in range(drops['i'][3])] == [0, 3, 1]      # walls, agent, drops
+
+
+def test_create_sprites_is_refused_where_it_cannot_be_lowered():
+    import moog_b200  # noqa: F401
+    from moog import game_rules
+    from moog_b200 import compiler
+    from moog_b200.configs import spawn_zoo
+    cfg = spawn_zoo.get_config()
+    states = [cfg['state_initializer']()]
+    bad = dict(cfg, game_rules=(game_rules.CreateSprites('drops', lambda without_overlapping: []),))
+    with pytest.raises(compiler.CompileError, match='generate_sprites'):
+        compiler.compile_config(bad, states)
+    bad = dict(cfg, game_rules=(game_rules.ConditionalRule(
+        condition=lambda state: np.random.binomial(2, 0.5), rules=cfg['game_rules'][2]),))
+    with pytest.raises(Exception):
+        compiler.compile_config(bad, states)
+
+
+def test_oracle_create_sprites_invariants():
+    """On the oracle alone (Philox draws): new sprites never overlap what they must avoid at the moment
+    they appear, are appended in order, the Bernoulli conditions fire at their rates, a full layer
+    flags MOOG_ERR_LAYER_OVERFLOW and creates nothing."""
+    from oracle.oracle import Oracle
+    _, prog, pool = _compile()
+    N = 48
+    rng = np.random.RandomState(2)
+    arrays = {k: np.ascontiguousarray(pool[k][rng.randint(0, 6, size=N)]) for k in util.STATE_KEYS}
+    orc = Oracle(prog, arrays)
+    Oracle.set_seed(11)
+    orc.post_reset()
+    lo = prog.layer_off
+    fired = np.zeros(2)
+    passes = 0
+    for t in range(50):
+        before = orc.cnt.copy()
+        created = orc.envi[:, 4].copy()
+        Oracle.set_seed(1000 + t)
+        orc.step(rng.uniform(-1, 1, size=(N, 2)))
+        passes += N
+        # drops: at most one more, minus those the agent ate in this pass (VanishOnContact runs after)
+        assert (orc.cnt[:, 1] <= before[:, 1] + 1).all()
+        fired[0] += (orc.envi[:, 4] - created >= 1).sum()
+        ov = orc.overlap_pairs('drops', 'walls')
+        assert not ov.any(), 'a drop appeared on a wall'
+        dd = orc.overlap_pairs('drops', 'drops')
+        for e in range(N):
+            n = orc.cnt[e, 1]
+            assert not (dd[e][:n, :n] & ~np.eye(n, dtype=bool)).any(), 'two drops overlap'
+        # sparks are axis-aligned squares on the border with speeds in the ring
+        for e in range(N):
+            n = orc.cnt[e, 2]
+            v = orc.dyn[e][2:4, lo[2]:lo[2] + n]
+            assert (np.abs(v).max(axis=0) >= 0.02).all() and (np.abs(v) < 0.05).all()
+    assert (orc.envi[:, 2] == 0).all()
+    # tiny layer: the flag is raised, nothing is written past the layer
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from moog_b200.configs import spawn_zoo
+    cfg = spawn_zoo.get_config()
+    np.random.seed(3)
+    states = [cfg['state_initializer']() for _ in range(2)]
+    small = compiler.compile_config(cfg, states, layer_capacity={'drops': 3, 'sparks': 2})
+    orc = Oracle(small, compiler.pack_states(small, states))
+    Oracle.set_seed(1)
+    orc.post_reset()
+    for t in range(30):
+        Oracle.set_seed(50 + t)
+        orc.step(np.zeros((2, 2)))
+    assert (orc.cnt[:, 1] <= 3).all() and (orc.cnt[:, 2] <= 2).all()
+    assert ((orc.envi[:, 2] & 8) != 0).all()
+
+
+def _same(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+
+
+@pytest.mark.gpu
+def test_cuda_create_sprites_matches_oracle():
+    """spawn_zoo, 192 envs, 140 steps through two time-outs with auto-resets from a pool: the CUDA path
+    and the oracle draw from the same Philox stream (io.seed), so the states -- every created sprite's
+    factors, outline, slot -- the rewards, step types, overlap pair sets, error words and the frames
+    must be IDENTICAL every step (no sin / cos on this path: bit-exact)."""
+    from moog_b200.batched_env import Engine
+    from oracle.oracle import Oracle
+    _, prog, pool_arrays = _compile()
+    N = 192
+    rng = np.random.RandomState(4)
+    arrays = {k: np.ascontiguousarray(pool_arrays[k][rng.randint(0, 6, size=N)]) for k in util.STATE_KEYS}
+    orc = Oracle(prog, arrays)
+    eng = Engine(prog, N, 'cuda:0', seed=21)
+    eng.state.upload(arrays)
+    eng.set_pool(pool_arrays)
+    pool = Oracle(prog, pool_arrays)
+    Oracle.set_seed(21 & 0x7fffffff)            # moog_env_post_reset: the program's "seed" option
+    orc.post_reset()
+    eng.post_reset()
+    orc.envi[:, 0] = rng.randint(0, 40, size=N)        # staggered time-outs
+    eng.state.upload(orc.arrays())
+    made = 0
+    for t in range(140):
+        ri = rng.randint(0, 6, size=N)
+        act = rng.uniform(-1, 1, size=(N, 2))
+        serial = orc.envi[:, 4].copy()
+        Oracle.set_seed(eng.call_seed())
+        r_ref, st_ref, d_ref = orc.step_auto(act, pool, ri)
+        eng.env_step(act, auto_reset=True, reset_index=ri, want_counters=True, frames=t % 20 == 0 or None)
+        made += int((orc.envi[:, 4] - serial).sum())
+        assert np.array_equal(eng.step_type.cpu().numpy(), st_ref), t
+        assert _same(eng.reward.cpu().numpy(), r_ref.astype(np.float32)), (t, 'reward')
+        assert np.array_equal(eng.counters.cpu().numpy()[:, :4], orc.counters), (t, 'overlap pair sets')
+        dev = eng.state.download()
+        assert np.array_equal(dev['cnt'], orc.cnt), t
+        assert np.array_equal(dev['envi'][:, :6], orc.envi[:, :6]), (t, 'counters / error words')
+        for e in range(N):
+            util.assert_live_equal(prog, {k: dev[k][e] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')},
+                                   {k: getattr(orc, k)[e] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')},
+                                   'step {} env {}'.format(t, e))
+        if t % 20 == 0:
+            assert np.array_equal(eng.frames.cpu().numpy(), orc.render()), (t, 'frames')
+    assert made > 100 * N // 2, 'CreateSprites calls made: {}'.format(made)
+    assert (orc.cnt[:, 1] > 3).any() and (orc.envi[:, 3] >= 2).all()
