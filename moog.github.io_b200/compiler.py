@@ -554,9 +554,7 @@ def _rule_specs(prog, rule, out, depth=0):
                                                 prog.add_expr(code))))
     elif k == 'CreateSprites':
         # create_sprites.py:27-34; the generator's recipe is sampled on the device (Philox), like a reset group
-        gen = rule._generator
-        if not hasattr(gen, 'factor_dist'):
-            raise CompileError('CreateSprites needs a generator made by sprite_generators.generate_sprites')
+        gen = _Recipe(rule._generator)
         if callable(gen.num_sprites):
             raise CompileError('CreateSprites with a random number of sprites per call is not on the accelerated path')
         lay = prog.layer_index(rule._layer)
@@ -598,6 +596,23 @@ def _created(rules):
         elif hasattr(r, '_rules'):
             out += _created(r._rules)
     return out
+
+
+class _Recipe(object):
+    """What a generate_sprites closure was made with (sprite_generators.py:26-29)."""
+
+    def __init__(self, gen):
+        names = ('factor_dist', 'num_sprites', 'max_recursion_depth', 'fail_gracefully')
+        if all(hasattr(gen, n) for n in names):          # this repo's generate_sprites says so itself
+            values = {n: getattr(gen, n) for n in names}
+        else:                                            # the reference's: the closure's free variables
+            values = lambdas.closure_vars(gen) if callable(gen) else {}
+        if any(n not in values for n in names):
+            raise CompileError('CreateSprites needs a generator made by sprite_generators.generate_sprites')
+        self.factor_dist = values['factor_dist']
+        self.num_sprites = values['num_sprites']
+        self.max_recursion_depth = values['max_recursion_depth']
+        self.fail_gracefully = bool(values['fail_gracefully'])
 
 
 def _generator_outline(gen):
@@ -715,7 +730,7 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
     # CreateSprites appends to a layer for as long as the episode lasts (create_sprites.py:27-34); the
     # record gives the layer room for CREATE_HEADROOM more sprites unless `layer_capacity` says how many
     # (an env whose layer is full flags MOOG_ERR_LAYER_OVERFLOW and creates nothing)
-    created = [(name, gen) for name, gen in _created(config.get('game_rules', ())) if hasattr(gen, 'factor_dist')]
+    created = [(name, _Recipe(gen)) for name, gen in _created(config.get('game_rules', ()))]
     for name in {name for name, _ in created}:
         if name not in (layer_capacity or {}):
             caps[prog.layer_names.index(name)] += CREATE_HEADROOM
@@ -812,7 +827,7 @@ def _lower_distribution(dist):
         return {}, [('mixture', alts, probs)]
     if k in ('SetMinus', 'Selection'):
         base = _flatten_distribution(dist.base)
-        box = _flatten_distribution(dist._other)  # pylint: disable=protected-access
+        box = _flatten_distribution(dist.filtering if k == 'Selection' else dist.hold_out)
         if any(v[0] != 'uniform' for v in box.values()):
             raise CompileError('{} against anything but a box of Continuous factors is not on the device sampler'.format(k))
         return {}, [('filtered', base, [(key, v[1], v[2]) for key, v in box.items()], k == 'Selection')]

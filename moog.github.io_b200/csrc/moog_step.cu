@@ -2802,43 +2802,28 @@ __device__ __noinline__ void generate_sprites_dev(const Env &, const moog_op *op
           }
         }
       }
+      // Sprite.__init__ (sprite.py:261-327) then the shape setter (:329-409): the outline is laid out at
+      // (x, y) by _set_path (:411-424: circumscribed radius, inertia * scale^2), THEN the position setter
+      // (:616-633) moves sprite and cached outline by the shape's raw centroid
       const double *R = dpool + shape_off[(int)v[MOOG_Z_SHAPE_ATTR]];
-      const int nv = (int)R[0];
-      const double px = v[MOOG_AT_X] + R[4], py = v[MOOG_AT_Y] + R[5];
-      const double sx = v[MOOG_AT_SCALE], sy = v[MOOG_AT_SCALE] * v[MOOG_AT_ASPECT_RATIO];
-      double c = 1.0, sn = v[MOOG_AT_ANGLE];
-      if (v[MOOG_AT_ANGLE] != 0.0) {
-        const double2 cs = cos_sin_ol(v[MOOG_AT_ANGLE]);
-        c = cs.x;
-        sn = cs.y;
-      }
-      const double m00 = c * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = c * sy;
       wsync();
-      double r = 0.0;
-      for (int i = e.lane; i < nv; i += 32) {
-        const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
-        const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
-        e.vtx[e.voff[s] + i] = make_double2(wx, wy);
-        const double rx = wx - px, ry = wy - py;
-        r = fmax(r, sqrt(rx * rx + ry * ry));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) r = fmax(r, shflx_d(r, o));
       if (e.lane == 0) {
-        DYN(e, MOOG_D_X, s) = px; DYN(e, MOOG_D_Y, s) = py;
+        DYN(e, MOOG_D_X, s) = v[MOOG_AT_X]; DYN(e, MOOG_D_Y, s) = v[MOOG_AT_Y];
         DYN(e, MOOG_D_VX, s) = v[MOOG_AT_X_VEL]; DYN(e, MOOG_D_VY, s) = v[MOOG_AT_Y_VEL];
         DYN(e, MOOG_D_ANG, s) = v[MOOG_AT_ANGLE]; DYN(e, MOOG_D_ANGVEL, s) = v[MOOG_AT_ANGLE_VEL];
         STAT(e, MOOG_S_MASS, s) = v[MOOG_AT_MASS]; STAT(e, MOOG_S_SCALE, s) = v[MOOG_AT_SCALE];
         STAT(e, MOOG_S_ASPECT, s) = v[MOOG_AT_ASPECT_RATIO];
-        STAT(e, MOOG_S_IX, s) = R[2] * (sx * sx); STAT(e, MOOG_S_IY, s) = R[3] * (sy * sy);
-        STAT(e, MOOG_S_MAXR, s) = r;
+        STAT(e, MOOG_S_IX, s) = R[2]; STAT(e, MOOG_S_IY, s) = R[3];
         STAT(e, MOOG_S_C0, s) = v[MOOG_AT_C0]; STAT(e, MOOG_S_C1, s) = v[MOOG_AT_C1];
         STAT(e, MOOG_S_C2, s) = v[MOOG_AT_C2]; STAT(e, MOOG_S_OPACITY, s) = v[MOOG_AT_OPACITY];
         META(e, MOOG_M_SHAPE, s) = (int)v[MOOG_Z_SHAPE_ATTR];
         META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
-        META(e, MOOG_M_NV, s) = nv;
+        META(e, MOOG_M_NV, s) = (int)R[0];
         e.cnt[layer] = s - LOFF(e, layer) + 1;
       }
+      wsync();
+      set_path(e, s);
+      set_position(e, s, v[MOOG_AT_X] + R[4], v[MOOG_AT_Y] + R[5]);
       wsync();
       refresh_all_boxes(e);
       bool hit = false;

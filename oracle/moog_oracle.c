@@ -1534,8 +1534,22 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
 /* conditions can be compared draw for draw; that the DISTRIBUTIONS are the   */
 /* reference's is what tests/test_create_sprites.py checks against it.        */
 /* ------------------------------------------------------------------------ */
+static void set_path(env_t *e, int s);
 static uint64_t g_seed = 0;
 void orc_set_seed(uint64_t seed) { g_seed = seed; }
+
+/* Replay hook of the parity tests: rows of MOOG_Z_N_ATTRS factors that the next generate_sprites tries
+ * take, in order, INSTEAD of drawing them -- the factor dicts the reference's own factor_dist.sample()
+ * returned on a recorded trajectory (oracle/gen_golden_spawn.py).  With it the oracle follows the
+ * reference through CreateSprites draw for draw, which pins everything around the draw itself. */
+static const double *g_forced = NULL;
+static int g_forced_n = 0, g_forced_pos = 0;
+void orc_force_factors(const double *rows, int n_rows) {
+  g_forced = rows;
+  g_forced_n = n_rows;
+  g_forced_pos = 0;
+}
+int orc_forced_left(void) { return g_forced_n - g_forced_pos; }
 
 static double philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -1622,13 +1636,15 @@ static void generate_sprites(env_t *e, const moog_op *op, uint64_t key, uint32_t
     for (int tries = 0;; ++tries) {
       double v[MOOG_Z_N_ATTRS];
       const uint32_t c2 = ((uint32_t)s << 20) | (uint32_t)tries;
-      for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
+      const int forced = g_forced != NULL && g_forced_pos < g_forced_n;
+      if (forced) memcpy(v, g_forced + (size_t)MOOG_Z_N_ATTRS * g_forced_pos++, sizeof(v));
+      for (int a = 0; a < MOOG_Z_N_ATTRS && !forced; ++a) {
         const int kind = tab[3 * a], idx = tab[3 * a + 1], n = tab[3 * a + 2];
         const double u = kind == MOOG_ZK_CONST ? 0.0 : philox_uniform(key, (uint32_t)e->env_id, c1, c2, (0x5Au << 24) | (uint32_t)a);
         v[a] = sample_leaf(dpool, kind, idx, n, u);
       }
       const int32_t *x = tab + 3 * MOOG_Z_N_ATTRS;
-      const int n_ext = *x++;
+      const int n_ext = forced ? 0 : *x++;
       uint32_t draw = 0;
       for (int c = 0; c < n_ext; ++c) {
         const int kind = *x++;
@@ -1676,38 +1692,24 @@ static void generate_sprites(env_t *e, const moog_op *op, uint64_t key, uint32_t
           if (!accepted) e->envi[MOOG_EI_ERR] |= MOOG_ERR_RESET_REJECTED;
         }
       }
+      /* Sprite.__init__ (sprite.py:261-327) then the shape setter (:329-409): the outline is laid out at
+       * (x, y) by _set_path (:411-424: circumscribed radius, inertia * scale^2), THEN the position setter
+       * (:616-633) moves sprite and cached outline by the shape's raw centroid */
       const double *R = dpool + shape_off[(int)v[MOOG_Z_SHAPE_ATTR]];
-      const int nv = (int)R[0];
-      const double px = v[MOOG_AT_X] + R[4], py = v[MOOG_AT_Y] + R[5];
-      const double sx = v[MOOG_AT_SCALE], sy = v[MOOG_AT_SCALE] * v[MOOG_AT_ASPECT_RATIO];
-      double cs = 1.0, sn = v[MOOG_AT_ANGLE];
-      if (v[MOOG_AT_ANGLE] != 0.0) {
-        cs = cos(v[MOOG_AT_ANGLE]);
-        sn = sin(v[MOOG_AT_ANGLE]);
-      }
-      const double m00 = cs * sx, m01 = -(sn * sy), m10 = sn * sx, m11 = cs * sy;
-      double *w = e->vtx + 2 * (size_t)e->voff[s];
-      double r = 0.0;
-      for (int i = 0; i < nv; ++i) {
-        const double bx = R[6 + 2 * i], by = R[7 + 2 * i];
-        const double wx = m00 * bx + m01 * by + px, wy = m10 * bx + m11 * by + py;
-        w[2 * i] = wx;
-        w[2 * i + 1] = wy;
-        r = fmax(r, norm_ax(wx - px, wy - py));
-      }
-      DYN(e, MOOG_D_X, s) = px; DYN(e, MOOG_D_Y, s) = py;
+      DYN(e, MOOG_D_X, s) = v[MOOG_AT_X]; DYN(e, MOOG_D_Y, s) = v[MOOG_AT_Y];
       DYN(e, MOOG_D_VX, s) = v[MOOG_AT_X_VEL]; DYN(e, MOOG_D_VY, s) = v[MOOG_AT_Y_VEL];
       DYN(e, MOOG_D_ANG, s) = v[MOOG_AT_ANGLE]; DYN(e, MOOG_D_ANGVEL, s) = v[MOOG_AT_ANGLE_VEL];
       STAT(e, MOOG_S_MASS, s) = v[MOOG_AT_MASS]; STAT(e, MOOG_S_SCALE, s) = v[MOOG_AT_SCALE];
       STAT(e, MOOG_S_ASPECT, s) = v[MOOG_AT_ASPECT_RATIO];
-      STAT(e, MOOG_S_IX, s) = R[2] * (sx * sx); STAT(e, MOOG_S_IY, s) = R[3] * (sy * sy);
-      STAT(e, MOOG_S_MAXR, s) = r;
+      STAT(e, MOOG_S_IX, s) = R[2]; STAT(e, MOOG_S_IY, s) = R[3];
       STAT(e, MOOG_S_C0, s) = v[MOOG_AT_C0]; STAT(e, MOOG_S_C1, s) = v[MOOG_AT_C1];
       STAT(e, MOOG_S_C2, s) = v[MOOG_AT_C2]; STAT(e, MOOG_S_OPACITY, s) = v[MOOG_AT_OPACITY];
       META(e, MOOG_M_SHAPE, s) = (int)v[MOOG_Z_SHAPE_ATTR];
       META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
-      META(e, MOOG_M_NV, s) = nv;
+      META(e, MOOG_M_NV, s) = (int)R[0];
       e->cnt[layer] = s - LOFF(e, layer) + 1;
+      set_path(e, s);
+      set_position(e, s, v[MOOG_AT_X] + R[4], v[MOOG_AT_Y] + R[5]);
       int hit = 0; /* every pair is evaluated (no short-circuit), sprite_generators.py:69-74 */
       if (avoid_layers) {
         for (int q = 0; q < n_avoid; ++q) {

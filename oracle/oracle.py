@@ -120,6 +120,20 @@ class Oracle(object):
         tensor) of the calls that follow: what the CUDA path receives as io.seed."""
         lib().orc_set_seed(ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF))
 
+    _forced = None
+
+    @classmethod
+    def force_factors(cls, rows):
+        """The next generate_sprites tries take these factor rows ([n, 14]) instead of drawing
+        (replay of a recorded reference trajectory); None / empty turns the hook off."""
+        rows = None if rows is None or len(rows) == 0 else np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 14)
+        cls._forced = rows          # keeps the buffer alive
+        lib().orc_force_factors(_ptr(rows), ctypes.c_int(0 if rows is None else len(rows)))
+
+    @staticmethod
+    def forced_left():
+        return int(lib().orc_forced_left())
+
     def step_auto(self, actions, pool, reset_index, noise=None, rule_noise=None):
         """Environment.step with its auto-reset (environment.py:98-126 incl. :100-101,
         reset() :82-96): envs whose previous transition terminated take row

@@ -167,3 +167,72 @@ def test_cuda_create_sprites_matches_oracle():
             assert np.array_equal(eng.frames.cpu().numpy(), orc.render()), (t, 'frames')
     assert made > 100 * N // 2, 'CreateSprites calls made: {}'.format(made)
     assert (orc.cnt[:, 1] > 3).any() and (orc.envi[:, 3] >= 2).all()
+
+
+SPAWN_SCENES = ['zoo', 'first_person']
+
+
+def _load_spawn(name):
+    g = dict(np.load(util.GOLDEN + '/spawn_' + name + '.npz'))
+    g['program'] = util.ProgramStub(g['blob'], g['layer_names'])
+    return g
+
+
+def _meta_rows(meta, live):
+    """dtype flags and outline sizes of the live sprites.  Row 0 (the shape's number) is left out: a
+    created sprite carries its index in the sampler's shape records, a packed reference state the
+    index in pack_states' own table -- read only by the scale / aspect_ratio setters, which the
+    compiler refuses to combine with the device sampler."""
+    return util.canonical_meta(meta, live)[1:]
+
+
+@pytest.mark.parametrize('name', SPAWN_SCENES)
+def test_oracle_replays_reference_create_sprites(name):
+    """The unmodified reference's trajectory (oracle/gen_golden_spawn.py) replayed on the oracle: the
+    Bernoulli conditions receive the reference's outcomes through the rule-noise columns and every
+    generate_sprites try the factor dict the reference's factor_dist.sample() returned.  State (every
+    created sprite's attributes, dtype flags, outline, slot), rewards, terminations, the overlap calls
+    of every pass (count, Trues, order-sensitive hash -- candidates that were rejected included) and the
+    frames are identical, and every recorded draw is consumed by exactly the pass that made it."""
+    from oracle.oracle import Oracle
+    g = _load_spawn(name)
+    prog = g['program']
+    try:
+        orc = Oracle(prog, util.state_at(g, 0, prefix='init'))
+        p = 0
+        Oracle.force_factors(g['factors'][g['factor_start'][p]:g['factor_start'][p + 1]])
+        orc.post_reset(rule_noise=g['rule_noise'][p][None])
+        assert Oracle.forced_left() == 0
+        want = util.state_at(g, 0, prefix='reset')
+        live = util.live_mask(prog, want['cnt'][0])
+        assert np.array_equal(orc.cnt[0], want['cnt'][0])
+        assert np.array_equal(orc.dyn[0][:, live], want['dyn'][0][:, live])
+        assert np.array_equal(_meta_rows(orc.meta[0], live), _meta_rows(want['meta'][0], live))
+        fi = {int(t): k for k, t in enumerate(g['frame_steps'])}
+        fu = {int(t): k for k, t in enumerate(g['full_steps'])}
+        assert np.array_equal(orc.render()[0], g['frames'][fi[-1]])
+        created = 0
+        for t in range(len(g['reward'])):
+            p = t + 1
+            rows = g['factors'][g['factor_start'][p]:g['factor_start'][p + 1]]
+            Oracle.force_factors(rows)
+            created += len(rows)
+            reward, step_type = orc.step(g['actions'][t][None], rule_noise=g['rule_noise'][p][None])
+            assert Oracle.forced_left() == 0, (t, 'draws left over')
+            assert reward[0] == g['reward'][t] and bool(step_type[0] == 2) == bool(g['last'][t]), t
+            assert np.array_equal(orc.cnt[0], g['cnt'][t]), (t, orc.cnt[0], g['cnt'][t])
+            live = util.live_mask(prog, g['cnt'][t])
+            assert np.array_equal(orc.dyn[0][:, live], g['dyn'][t][:, live]), t
+            assert tuple(int(v) for v in orc.counters[0][[0, 1]]) == (int(g['n_calls'][p]), int(g['n_true'][p])), (t, 'overlap calls')
+            assert np.uint64(orc.counters[0][3]) == g['true_hash'][p], (t, 'order of the True overlap events')
+            if t in fu:
+                k = fu[t]
+                assert np.array_equal(orc.stat[0][:, live], g['stat'][k][:, live]), t
+                assert np.array_equal(_meta_rows(orc.meta[0], live), _meta_rows(g['meta'][k], live)), t
+                vlive = util.live_vertex_mask(prog, g['cnt'][t], g['meta'][k])
+                assert np.array_equal(orc.vtx[0][vlive], g['vtx'][k][vlive]), t
+            if t in fi:
+                assert np.array_equal(orc.render()[0], g['frames'][fi[t]]), (t, 'frame')
+        assert created > 50 and (orc.envi[0, 2] == 0)
+    finally:
+        Oracle.force_factors(None)
