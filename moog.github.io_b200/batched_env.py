@@ -320,6 +320,14 @@ class BatchedEnvironment(object):
         self._auto_times = {'mapped': [], 'chunked': []}
 
     # -- dm_env-like protocol -------------------------------------------------
+    def _clear_envi(self):
+        """Counters and error words back to 0 -- but not the two draw serials (MOOG_EI_CREATED,
+        MOOG_EI_RULE_PASSES): they key the Philox draws of CreateSprites / random conditions, and an
+        env reset by hand must not see the draws of its first episode again."""
+        envi = self.engine.state.envi
+        envi[:, :4].zero_()
+        envi[:, 6:].zero_()
+
     def reset(self):
         """environment.py:82-96 for every env."""
         e = self.engine
@@ -328,7 +336,7 @@ class BatchedEnvironment(object):
             # and draws its generated sprites on the device
             for k in DeviceState.KEYS:
                 getattr(e.state, k).copy_(getattr(e.pool, k)[0:1].expand_as(getattr(e.state, k)))
-            e.state.envi.zero_()
+            self._clear_envi()
             e.state.envi[:, 1] = 1
             e.env_step(None, sample_resets=True)
             self._started = True
@@ -336,7 +344,7 @@ class BatchedEnvironment(object):
         idx = torch.from_numpy(self._rng.randint(0, e.pool.n, size=self.num_envs)).to(e.device)
         for k in DeviceState.KEYS:
             if k == 'envi':
-                e.state.envi.zero_()
+                self._clear_envi()
             else:
                 getattr(e.state, k).copy_(getattr(e.pool, k).index_select(0, idx))
         e.post_reset()

@@ -236,3 +236,120 @@ def test_oracle_replays_reference_create_sprites(name):
         assert created > 50 and (orc.envi[0, 2] == 0)
     finally:
         Oracle.force_factors(None)
+
+
+@pytest.mark.gpu
+def test_cuda_first_person_predators_prey_matches_oracle():
+    """The SHIPPED first_person_predators_prey config (its program compiled from the reference's own
+    config objects travels in the golden): 96 envs x 150 steps, CUDA vs oracle on the same Philox
+    stream -- predators and prey appearing on the border (Mixture + SetMinus factors), vanishing far
+    away, KeepNearCenter, the `reward_fn` rewards, and the FirstPersonAgent frames -- identical."""
+    from moog_b200.batched_env import Engine
+    from oracle.oracle import Oracle
+    g = _load_spawn('first_person')
+    prog = g['program']
+    N = 96
+    arrays = util.tile_state(util.state_at(g, 0, prefix='init'), N)
+    orc = Oracle(prog, arrays)
+    eng = Engine(prog, N, 'cuda:0', seed=8)
+    eng.state.upload(arrays)
+    eng.set_pool({k: arrays[k][:2] for k in util.STATE_KEYS})
+    pool = Oracle(prog, {k: arrays[k][:2] for k in util.STATE_KEYS})
+    Oracle.set_seed(8)
+    orc.post_reset()
+    eng.post_reset()
+    rng = np.random.RandomState(6)
+    ri = np.zeros(N, dtype=np.int32)
+    rewards = 0
+    for t in range(150):
+        act = rng.uniform(-1, 1, size=(N, 2))
+        Oracle.set_seed(eng.call_seed())
+        r_ref, st_ref, _ = orc.step_auto(act, pool, ri)
+        want_frame = t % 25 == 24
+        eng.env_step(act, auto_reset=True, reset_index=ri, want_counters=True, frames=want_frame or None)
+        assert np.array_equal(eng.step_type.cpu().numpy(), st_ref), t
+        assert _same(eng.reward.cpu().numpy(), r_ref.astype(np.float32)), (t, 'reward')
+        rewards += int((np.nan_to_num(r_ref) != 0).sum())
+        assert np.array_equal(eng.counters.cpu().numpy()[:, :4], orc.counters), (t, 'overlap pair sets')
+        dev = eng.state.download()
+        assert np.array_equal(dev['cnt'], orc.cnt), t
+        assert np.array_equal(dev['envi'][:, :6], orc.envi[:, :6]), t
+        for e in range(0, N, 5):
+            util.assert_live_equal(prog, {k: dev[k][e] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')},
+                                   {k: getattr(orc, k)[e] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')},
+                                   'step {} env {}'.format(t, e))
+        if want_frame:
+            assert np.array_equal(eng.frames.cpu().numpy(), orc.render()), (t, 'frames')
+    # (the fixture's 44 predator slots fill up in some envs late in the run: MOOG_ERR_LAYER_OVERFLOW, on both sides)
+    assert ((orc.envi[:, 2] & ~8) == 0).all() and rewards > 20
+    assert orc.cnt[:, 3].max() > 30 and orc.cnt[:, 1].max() > 10
+
+
+@pytest.mark.gpu
+def test_cuda_created_factors_follow_the_distributions():
+    """The Philox draws against the reference's distributions (spawn_zoo, 2048 envs x 40 steps, the
+    BatchedEnvironment API): Bernoulli rates of the two conditions (conditional.py:55-58 with
+    np.random.binomial(1, p)), the Mixture's side probabilities and the SetMinus ring of the sparks
+    (distributions.py:159-209, 319-365), uniform Discrete shapes and float32 Continuous scales of the
+    first drop of an episode (:78-157) -- each within 5 sigma of its expectation."""
+    import torch
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment
+    from moog_b200.configs import spawn_zoo
+    cfg = spawn_zoo.get_config()
+    N, T = 2048, 40
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=3, pool_size=8,
+                             layer_capacity=spawn_zoo.LAYER_CAPACITY)
+    env.reset()
+    prog, eng = env.program, env.engine
+    lo = prog.layer_off
+    sides = np.zeros(4)
+    speeds_ok = True
+    n_sparks = 0
+    shapes = np.zeros(4)
+    scales = []
+    drop_calls = spark_calls = 0
+    prev = eng.state.download()
+    for t in range(T):
+        env.step(torch.zeros((N, 2), dtype=torch.float64))
+        st = eng.state.download()
+        fresh = st['envi'][:, 0] > 0                 # envs that did not auto-reset in this step
+        # sparks are appended two at a time and only leave from the far outside: new ones sit at the end
+        d_sp = st['cnt'][:, 2] - prev['cnt'][:, 2]
+        for e in np.nonzero(fresh & (d_sp == 2))[0][:400]:
+            k = lo[2] + st['cnt'][e, 2] - 2
+            for s in (k, k + 1):
+                # position after one step of flight: undo it
+                x = st['dyn'][e, 0, s] - st['dyn'][e, 2, s]
+                y = st['dyn'][e, 1, s] - st['dyn'][e, 3, s]
+                side = [abs(x + 0.1) < 1e-6, abs(x - 1.1) < 1e-6, abs(y + 0.1) < 1e-6, abs(y - 1.1) < 1e-6]
+                assert sum(side) >= 1, (x, y)
+                sides[int(np.argmax(side))] += 1
+                v = np.abs(st['dyn'][e, 2:4, s])
+                speeds_ok &= bool(v.max() >= 0.02 and v.max() < 0.05)
+                n_sparks += 1
+        spark_calls += int((fresh & (d_sp == 2)).sum())
+        d_dr = st['cnt'][:, 1] - prev['cnt'][:, 1]
+        # (only the FIRST drop of an episode: later ones are what the rejection against the other drops
+        # left over, which favours small shapes)
+        for e in np.nonzero(fresh & (d_dr == 1) & (prev['cnt'][:, 1] == 0))[0]:
+            s = lo[1] + st['cnt'][e, 1] - 1
+            shapes[st['meta'][e, 0, s]] += 1
+            scales.append(st['stat'][e, 1, s])
+        prev = st
+    assert (st['envi'][:, 2] == 0).all()
+    assert speeds_ok and n_sparks > 2000
+    p = np.array([0.1, 0.2, 0.3, 0.4])
+    sigma = np.sqrt(n_sparks * p * (1 - p))
+    assert (np.abs(sides - n_sparks * p) < 5 * sigma).all(), (sides, n_sparks)
+    n_drops = shapes.sum()
+    assert n_drops > 500 and (np.abs(shapes - n_drops / 4) < 5 * np.sqrt(n_drops * 0.1875)).all(), shapes
+    scales = np.array(scales)
+    assert np.array_equal(scales, scales.astype(np.float32).astype(np.float64))
+    assert scales.min() >= 0.1 and scales.max() < 0.17
+    assert abs(scales.mean() - 0.135) < 5 * (0.07 / np.sqrt(12)) / np.sqrt(len(scales))
+    # Bernoulli rates over all rule passes: serial of CreateSprites calls per env / passes
+    calls = st['envi'][:, 4].sum()
+    passes = st['envi'][:, 5].sum()
+    rate = calls / passes
+    assert abs(rate - 0.95) < 5 * np.sqrt((0.6 * 0.4 + 0.35 * 0.65) / passes), (rate, passes)
