@@ -981,8 +981,7 @@ def _sampler_group(prog, factor_dist, lay):
         meta_flags |= SF_VEL32
     if 'angle_vel' in sampled32:
         meta_flags |= 1 << SF_ANGVEL_SHIFT
-    if 'angle' in sampled32:
-        meta_flags |= 1 << SF_ANG_SHIFT
+    # (the angle is never float32 at birth: Sprite.__init__ stores float(angle), sprite.py:310)
     return table, meta_flags, ext_specs
 
 

@@ -210,10 +210,78 @@ def generate(name, out_dir):
         float(np.mean(rec['n_true'])), path, os.path.getsize(path) // 1024))
 
 
+RESET_SCENES = {
+    # name: (module, seed, number of initial states)
+    'colliding_predators84': ('moog_b200.configs.colliding_predators84', 33, 12),
+}
+
+
+def shape_key(shape):
+    """Text key of a shape factor: 's:<name>' or 'a:<hex of the float64 vertex array>'."""
+    return 's:' + shape if isinstance(shape, str) else 'a:' + np.asarray(shape, dtype=np.float64).tobytes().hex()
+
+
+def generate_resets(name, out_dir):
+    """The reference's state initializer (sprite_generators.py:75-103 with disjoint / without_overlapping)
+    called P times; every OUTERMOST factor_dist.sample() call is recorded, so that the oracle's reset
+    sampler can replay the draws:  factors[M, 13], shape_keys[M], row_start[P + 1], and the packed states
+    pool_*[P, ...] the initializer returned (layout words layer_off / voff stored for the test to check
+    that its own program -- compiled with the reset sampler, outside this script -- agrees)."""
+    from moog.state_initialization import distributions as distribs
+    module, seed, P = RESET_SCENES[name]
+    np.random.seed(seed)
+    config = importlib.import_module(module).get_config(None)
+    attr_keys = compiler._ATTR_KEYS  # pylint: disable=protected-access
+    defaults = compiler._sprite_defaults()  # pylint: disable=protected-access
+    rows, keys, depth = [], [], [0]
+    patched = []
+    for cls_name in ('Continuous', 'Discrete', 'Mixture', 'Intersection', 'Product', 'SetMinus', 'Selection',
+                     'DependentDistribution'):
+        cls = getattr(distribs, cls_name)
+
+        def _sample(self, rng=None, _orig=cls.sample):
+            depth[0] += 1
+            try:
+                out = _orig(self, rng)
+            finally:
+                depth[0] -= 1
+            if depth[0] == 0:
+                row = [float(out.get(k, defaults[k])) for k in attr_keys]
+                for k, v in zip(attr_keys, row):
+                    assert v == out.get(k, defaults[k]), (k, out.get(k))
+                rows.append(row)
+                keys.append(shape_key(out.get('shape', defaults['shape'])))
+            return out
+        patched.append((cls, cls.sample))
+        cls.sample = _sample
+    row_start, states = [0], []
+    try:
+        for _ in range(P):
+            states.append(config['state_initializer']())
+            row_start.append(len(rows))
+    finally:
+        for cls, orig in patched:
+            cls.sample = orig
+    prog = compiler.compile_config(config, states)
+    pool = compiler.pack_states(prog, states)
+    out = dict(factors=np.array(rows, dtype=np.float64), shape_keys=np.array(keys), row_start=np.array(row_start, dtype=np.int32),
+               layer_off=np.array(prog.layer_off, dtype=np.int32), voff=np.array(prog.voff, dtype=np.int32),
+               layer_names=np.array(prog.layer_names))
+    for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt'):
+        out['pool_' + k] = pool[k]
+    path = os.path.join(out_dir, 'resets_' + name + '.npz')
+    np.savez_compressed(path, **out)
+    print('{:22s} {} initial states, {} sample() calls -> {} ({} KB)'.format(name, P, len(rows), path,
+                                                                             os.path.getsize(path) // 1024))
+
+
 def main():
     out_dir = os.path.join(_ROOT, 'tests', 'golden')
-    for n in (sys.argv[1:] or list(SCENES)):
-        generate(n, out_dir)
+    for n in (sys.argv[1:] or list(SCENES) + list(RESET_SCENES)):
+        if n in RESET_SCENES:
+            generate_resets(n, out_dir)
+        else:
+            generate(n, out_dir)
 
 
 if __name__ == '__main__':

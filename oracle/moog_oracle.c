@@ -2233,6 +2233,32 @@ void orc_env_step(const void *blob, const orc_state *st, int n_envs, const doubl
   }
 }
 
+/* The state initializer drawn per env instead of taken from the pool (moog_step_io.sample_resets): every
+ * generate_sprites group the initializer was traced into (MOOG_Z_GENERATE) is drawn afresh into the
+ * template, on the Philox stream keyed by (seed, env, episode).  sprite_generators.py:75-103; a count given
+ * as `lambda: np.random.randint(lo, hi)` is drawn first. */
+static int g_sample_resets = 0;
+void orc_set_sample_resets(int on) { g_sample_resets = on; }
+
+static void reset_generate(env_t *e, const moog_op *op) {
+  const int first = op->i[0];
+  int count = op->i[1];
+  const uint64_t key = g_seed ^ 0x6A09E667F3BCC908ull;
+  if (op->p[2] > op->p[1]) {
+    const double u = philox_uniform(key, (uint32_t)e->env_id, (uint32_t)e->envi[MOOG_EI_EPISODES],
+                                    ((uint32_t)first << 20) | 0xfffffu, (0x5Cu << 24));
+    const int lo = (int)op->p[1], hi = (int)op->p[2];
+    int c = lo + (int)(u * (double)(hi - lo));
+    if (c >= hi) c = hi - 1;
+    if (c < count) count = c < 0 ? 0 : c;
+  }
+  int layer = 0;
+  for (int l = 0; l < e->L; ++l)
+    if (first >= LOFF(e, l) && first < LOFF(e, l + 1)) layer = l;
+  generate_sprites(e, op, key, (uint32_t)e->envi[MOOG_EI_EPISODES], layer, first, count, e->ipool + op->i[2],
+                   op->i[3], 0);
+}
+
 /* Environment.step INCLUDING its first two lines (environment.py:100-101): an env whose previous
  * transition was a termination ignores the action and runs reset() instead (environment.py:82-96).
  * The state initializer's result is row reset_index[n] of a pool of initial states (the batched
@@ -2253,8 +2279,10 @@ void orc_env_step_auto(const void *blob, const orc_state *st, int n_envs, const 
     const double *rn = rule_noise ? rule_noise + (size_t)n * n_rule_noise : NULL;
     e.noise = noise ? noise + (size_t)n * e.K * nd : NULL;
     if (e.envi[MOOG_EI_RESET_NEXT] != 0) {
-      int idx = reset_index[n];
+      int idx = reset_index ? reset_index[n] : 0;
       idx = idx < 0 ? 0 : (idx >= pool_size ? pool_size - 1 : idx);
+      const int sample = g_sample_resets && e.hdr[MOOG_H_N_RESET] > 0;
+      if (sample) idx = 0; /* pool row 0 is the template the generated sprites are drawn into */
       env_t p;
       bind_env(&p, blob, pool, idx);
       const int S = e.S, NF = e.hdr[MOOG_H_N_ENVF], VT = e.hdr[MOOG_H_N_VTX];
@@ -2264,6 +2292,8 @@ void orc_env_step_auto(const void *blob, const orc_state *st, int n_envs, const 
       memcpy(e.cnt, p.cnt, sizeof(int32_t) * MOOG_MAX_LAYERS);
       memcpy(e.envf, p.envf, sizeof(double) * NF);
       memcpy(e.vtx, p.vtx, sizeof(double) * 2 * VT);
+      if (sample)
+        for (int z = 0; z < e.hdr[MOOG_H_N_RESET]; ++z) reset_generate(&e, e.ops + e.hdr[MOOG_H_RESET] + z);
       e.envi[MOOG_EI_EPISODES] += 1;
       e.envi[MOOG_EI_STEP_COUNT] = 0;
       e.envi[MOOG_EI_RESET_NEXT] = 0;

@@ -120,6 +120,12 @@ class Oracle(object):
         tensor) of the calls that follow: what the CUDA path receives as io.seed."""
         lib().orc_set_seed(ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF))
 
+    @staticmethod
+    def set_sample_resets(on):
+        """step_auto draws the generate_sprites groups of the program's reset section per env
+        (moog_step_io.sample_resets) instead of copying a pool row."""
+        lib().orc_set_sample_resets(ctypes.c_int(1 if on else 0))
+
     _forced = None
 
     @classmethod

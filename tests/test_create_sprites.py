@@ -353,3 +353,52 @@ def test_cuda_created_factors_follow_the_distributions():
     passes = st['envi'][:, 5].sum()
     rate = calls / passes
     assert abs(rate - 0.95) < 5 * np.sqrt((0.6 * 0.4 + 0.35 * 0.65) / passes), (rate, passes)
+
+
+def test_oracle_replays_reference_state_initializer():
+    """The reset sampler's logic against the unmodified reference: colliding_predators' initializer
+    (5 predators `disjoint=True, without_overlapping=walls`, then the agent avoiding walls + predators;
+    sprite_generators.py:75-103) called 12 times by the reference with every factor_dist.sample()
+    recorded (64 of the 136 draws were rejected ones); the oracle's MOOG_Z_GENERATE groups replay those
+    draws and must end with the very states the reference returned -- positions, rotated outlines,
+    circumscribed radii, inertias, dtype flags -- and consume exactly the draws of each call."""
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from moog_b200.configs import colliding_predators84
+    from oracle.oracle import Oracle
+    g = dict(np.load(util.GOLDEN + '/resets_colliding_predators84.npz'))
+    cfg = colliding_predators84.get_config()
+    np.random.seed(1)
+    states = [cfg['state_initializer']() for _ in range(16)]
+    prog = compiler.compile_config(cfg, states, reset_sampler=True)
+    assert np.array_equal(g['layer_off'], prog.layer_off) and np.array_equal(g['voff'], prog.voff), 'layouts differ'
+    template = compiler.pack_states(prog, [prog.reset_template])
+    template = {k: template[k] for k in util.STATE_KEYS}
+
+    def _shape_id(key):
+        key = str(key)
+        return prog.z_shape_ids[key[2:] if key.startswith('s:') else bytes.fromhex(key[2:])]
+
+    ids = np.array([_shape_id(k) for k in g['shape_keys']], dtype=np.float64)
+    rows = np.concatenate([g['factors'], ids[:, None]], axis=1)
+    pool = Oracle(prog, template)
+    Oracle.set_sample_resets(True)
+    try:
+        for p in range(len(g['row_start']) - 1):
+            arrays = {k: v.copy() for k, v in template.items()}
+            arrays['envi'][:, 1] = 1
+            orc = Oracle(prog, arrays)
+            Oracle.force_factors(rows[g['row_start'][p]:g['row_start'][p + 1]])
+            _, step_type, _ = orc.step_auto(None, pool, np.zeros(1, dtype=np.int32))
+            assert Oracle.forced_left() == 0 and step_type[0] == 0 and orc.envi[0, 2] == 0, p
+            want = {k: g['pool_' + k][p] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')}
+            assert np.array_equal(orc.cnt[0], want['cnt']), p
+            live = util.live_mask(prog, want['cnt'])
+            assert np.array_equal(orc.dyn[0][:, live], want['dyn'][:, live]), p
+            assert np.array_equal(orc.stat[0][:, live], want['stat'][:, live]), p
+            assert np.array_equal(_meta_rows(orc.meta[0], live), _meta_rows(want['meta'], live)), p
+            vlive = util.live_vertex_mask(prog, want['cnt'], want['meta'])
+            assert np.array_equal(orc.vtx[0][vlive], want['vtx'][vlive]), p
+    finally:
+        Oracle.force_factors(None)
+        Oracle.set_sample_resets(False)

@@ -318,7 +318,7 @@ def test_device_side_reset_sampler():
     states = [cfg['state_initializer']() for _ in range(8)]
     N = 512
     env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=5, initial_states=states, reset_mode='device')
-    ts = env.reset()
+    ts = util.device_reset_vs_oracle(env, exact=False)      # (random angles)
     assert bool((ts.step_type == 0).all())
     eng, prog = env.engine, env.program
     st = eng.state.download()
@@ -337,7 +337,7 @@ def test_device_side_reset_sampler():
         assert np.array_equal(a, a.astype(np.float32).astype(np.float64)), 'Continuous factors are float32'
     assert len(np.unique(scale)) > 0.9 * scale.size, 'the envs draw different sprites'
     assert (st['stat'][:, 6:10, pred] == np.array([0., 1., 0.8, 255.])[None, :, None]).all()
-    assert (st['meta'][:, 1, pred] & 0x3f == 22).all()          # float32 velocity / angle_vel / angle
+    assert (st['meta'][:, 1, pred] & 0x3f == 6).all()           # float32 velocity / angle_vel; the angle is float(angle)
     shapes = st['meta'][:, 0, pred]
     assert set(np.unique(shapes)) == {0, 1, 2, 3, 4}, 'all five shape candidates occur'
     # construction: world vertices, circumscribed radius, inertia as the host Sprite computes them
@@ -548,7 +548,7 @@ def test_device_reset_sampler_mixture_and_setminus():
     states = [state_initializer() for _ in range(2)]
     N = 1024
     env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=3, initial_states=states, reset_mode='device')
-    env.reset()
+    util.device_reset_vs_oracle(env, exact=True)      # (no rotated sprite: bit for bit)
     st = env.engine.state.download()
     assert (st['envi'][:, 2] == 0).all() and (st['cnt'][:, :2] == [1, 6]).all()
     s0 = env.program.layer_off[1]
@@ -772,7 +772,7 @@ def test_device_reset_sampler_intersection_and_dependent():
     states = [state_initializer() for _ in range(2)]
     N = 2048
     env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=6, initial_states=states, reset_mode='device')
-    env.reset()
+    util.device_reset_vs_oracle(env, exact=True)      # (no rotated sprite: bit for bit)
     st = env.engine.state.download()
     assert (st['envi'][:, 2] == 0).all() and (st['cnt'][:, :2] == [1, 5]).all()
     s0 = env.program.layer_off[1]
@@ -817,7 +817,7 @@ def test_device_reset_sampler_random_sprite_count():
     N = 3000
     env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=6, initial_states=states, reset_mode='device',
                              layer_capacity={'prey': 4})
-    env.reset()
+    util.device_reset_vs_oracle(env, exact=True)      # (no rotated sprite: bit for bit)
     st = env.engine.state.download()
     counts = st['cnt'][:, 1]
     share = np.array([(counts == c).mean() for c in (2, 3, 4)])

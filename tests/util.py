@@ -198,3 +198,40 @@ def with_image_size(g, width, height):
 
 def load_golden_big(name):
     return dict(np.load(os.path.join(GOLDEN, name + '_big.npz')))
+
+
+def device_reset_vs_oracle(env, exact):
+    """`env.reset()` of a BatchedEnvironment(reset_mode='device') checked against the oracle, which draws
+    the same generate_sprites groups from the same Philox stream (oracle/moog_oracle.c reset_generate):
+    counts, dtype flags and outline sizes identical; attributes and outlines identical (`exact`: no
+    sin / cos on the path) or within RTOL (a rotated sprite: device cos / sin vs libm).  Returns what
+    env.reset() returned."""
+    from oracle.oracle import Oracle
+    eng, prog = env.engine, env.program
+    seed = eng.call_seed()
+    out = env.reset()
+    dev = eng.state.download()
+    pool_arrays = eng.pool.download()
+    n = eng.n
+    arrays = {k: np.repeat(pool_arrays[k][0:1], n, axis=0) for k in STATE_KEYS}
+    arrays['envi'][:] = 0
+    arrays['envi'][:, 1] = 1
+    orc, pool = Oracle(prog, arrays), Oracle(prog, pool_arrays)
+    Oracle.set_seed(seed)
+    Oracle.set_sample_resets(True)
+    try:
+        orc.step_auto(None, pool, np.zeros(n, dtype=np.int32))
+    finally:
+        Oracle.set_sample_resets(False)
+    assert np.array_equal(dev['cnt'], orc.cnt), 'device reset: counts'
+    assert np.array_equal(dev['envi'][:, :6], orc.envi[:, :6]), 'device reset: counters / error words'
+    worst = 0.0
+    for e in range(n):
+        live = live_mask(prog, orc.cnt[e])
+        assert np.array_equal(canonical_meta(dev['meta'][e], live), canonical_meta(orc.meta[e], live)), (e, 'meta')
+        vlive = live_vertex_mask(prog, orc.cnt[e], orc.meta[e])
+        worst = max(worst, rel_err(dev['dyn'][e][:, live], orc.dyn[e][:, live]),
+                    rel_err(dev['stat'][e][:, live], orc.stat[e][:, live]),
+                    rel_err(dev['vtx'][e][vlive], orc.vtx[e][vlive]))
+    assert worst <= (0.0 if exact else RTOL), ('device reset vs oracle', worst)
+    return out
