@@ -319,7 +319,8 @@ def test_reset_sampler_lowering():
     pred, agent = ops
     assert pred['i'][0] == prog.layer_off[1] and pred['i'][1] == 5 and pred['i'][3] == 4 and pred['flags'] & C.FL_DISJOINT
     assert agent['i'][0] == prog.layer_off[2] and agent['i'][1] == 1 and agent['i'][3] == 9 and not agent['flags'] & C.FL_DISJOINT
-    assert pred['i'][5] == C.SF_VEL32 | (1 << C.SF_ANGVEL_SHIFT) | (1 << C.SF_ANG_SHIFT) and agent['i'][5] == 0
+    # float32 velocity and angle_vel; the angle is float(angle) (sprite.py:310), never float32 at birth
+    assert pred['i'][5] == C.SF_VEL32 | (1 << C.SF_ANGVEL_SHIFT) and agent['i'][5] == 0
     assert len(prog.reset_shapes) == 6          # 5 predator candidates + the agent's circle
     tab = prog.ipool[pred['i'][4]:pred['i'][4] + 3 * C.Z_N_ATTRS]
     kinds = tab[0::3]
