@@ -84,6 +84,11 @@ typedef struct {
                           cudaHostRegister under unified addressing) for frames the host reads          */
 } moog_step_io;
 
+/* Checks a program blob without touching the GPU: every section start / count, pool index, layer id,
+ * expression start and sampler table an op refers to lies inside the blob (moog_program_create runs it
+ * first).  0, or MOOG_E_INVAL.  (No reference counterpart: the reference passes Python objects.) */
+int moog_program_validate(const void *blob, size_t nbytes);
+
 /* Upload a compiled program (host pointer to the blob).  Replaces nothing in the
  * reference: it is the device-side image of the component objects passed to
  * Environment.__init__ (moog/environment.py:28-68). */

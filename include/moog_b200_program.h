@@ -281,7 +281,9 @@ enum {
   MOOG_X_AND, MOOG_X_OR, MOOG_X_NOT,
   MOOG_X_ADD, MOOG_X_SUB, MOOG_X_MUL, MOOG_X_DIV, MOOG_X_NEG, MOOG_X_ABS,
   MOOG_X_MOD,        /* python float modulo                                  */
-  MOOG_X_STORE,      /* pop -> attribute `arg` of sprite 0 (modifier programs) */
+  MOOG_X_STORE,      /* pop -> attribute `arg` of sprite 0 (modifier programs).  c: for `angle` the NumPy kind of
+                        the value (sprite.py:531-540); for `x_vel` / `y_vel` 3 = the components of a FRESH float64
+                        array (`s.velocity = np.zeros(2)`, sprite.py:639-643): MOOG_SF_VEL32 and the alias id go */
   MOOG_X_STORE_POS   /* pop y, pop x -> sprite 0 `.position = (x, y)`: one translation of the cached
                         outline (sprite.py:616-633) */
 };

@@ -40,7 +40,8 @@ SYMBOLS = ('moog_program_create', 'moog_program_destroy',
            'moog_render', 'moog_strerror', 'moog_last_cuda_error',
            'moog_launch_count', 'moog_host_paths_overlap',
            'moog_host_points_in_path', 'moog_step_launch_info',
-           'moog_step_draws_frames', 'moog_program_set_option')
+           'moog_step_draws_frames', 'moog_program_set_option',
+           'moog_program_validate')
 
 
 class MoogError(RuntimeError):
@@ -98,6 +99,8 @@ def lib():
     L.moog_step_draws_frames.restype = ci
     L.moog_program_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     L.moog_program_set_option.restype = ci
+    L.moog_program_validate.argtypes = [vp, ctypes.c_size_t]
+    L.moog_program_validate.restype = ci
     L.moog_launch_count.argtypes = []
     L.moog_launch_count.restype = ctypes.c_int64
     _lib = L

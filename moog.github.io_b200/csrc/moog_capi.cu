@@ -79,18 +79,146 @@ bool set_launch_option(LaunchOptions &o, const char *name, int value) {
 
 extern "C" {
 
-int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
-  if (!blob || !out || nbytes < sizeof(int32_t) * MOOG_HDR_WORDS) return MOOG_E_INVAL;
+// Every offset, count and pool index a kernel (or this file) will follow is checked here, before the blob
+// is accepted: a malformed program is MOOG_E_INVAL, not an out-of-bounds read on the host or the device.
+int moog_program_validate(const void *blob, size_t nbytes) {
+  if (!blob || nbytes < sizeof(int32_t) * MOOG_HDR_WORDS) return MOOG_E_INVAL;
   const int32_t *hdr = (const int32_t *)blob;
   if ((uint32_t)hdr[MOOG_H_MAGIC] != MOOG_MAGIC || hdr[MOOG_H_VERSION] != MOOG_VERSION) return MOOG_E_INVAL;
   if ((size_t)hdr[MOOG_H_BYTES] != nbytes) return MOOG_E_INVAL;
-  if (hdr[MOOG_H_N_SLOTS] < 0 || hdr[MOOG_H_N_SLOTS] > MOOG_MAX_SLOTS || hdr[MOOG_H_N_LAYERS] > MOOG_MAX_LAYERS ||
-      hdr[MOOG_H_K] < 1)
-    return MOOG_E_INVAL;
-  size_t need = sizeof(int32_t) * MOOG_HDR_WORDS + sizeof(moog_op) * (size_t)hdr[MOOG_H_N_OPS] +
-                sizeof(int32_t) * (size_t)((hdr[MOOG_H_N_IPOOL] + 1) & ~1) + sizeof(moog_ex) * (size_t)hdr[MOOG_H_N_EXPR] +
-                sizeof(double) * (size_t)hdr[MOOG_H_N_DPOOL];
+  const int S = hdr[MOOG_H_N_SLOTS], L = hdr[MOOG_H_N_LAYERS], NO = hdr[MOOG_H_N_OPS], NI = hdr[MOOG_H_N_IPOOL],
+            NX = hdr[MOOG_H_N_EXPR], ND = hdr[MOOG_H_N_DPOOL], VT = hdr[MOOG_H_N_VTX], NF = hdr[MOOG_H_N_ENVF];
+  if (S < 0 || S > MOOG_MAX_SLOTS || L < 0 || L > MOOG_MAX_LAYERS || hdr[MOOG_H_K] < 1) return MOOG_E_INVAL;
+  if (NO < 0 || NI < 0 || NX < 0 || ND < 0 || VT < 0 || NF < 0) return MOOG_E_INVAL;
+  if (hdr[MOOG_H_ACTION_DIM] < 0 || hdr[MOOG_H_NOISE_DIM] < 0 || hdr[MOOG_H_RULE_NOISE_DIM] < 0) return MOOG_E_INVAL;
+  const size_t need = sizeof(int32_t) * MOOG_HDR_WORDS + sizeof(moog_op) * (size_t)NO +
+                      sizeof(int32_t) * (((size_t)NI + 1) & ~(size_t)1) + sizeof(moog_ex) * (size_t)NX +
+                      sizeof(double) * (size_t)ND;
   if (need != nbytes) return MOOG_E_INVAL;
+  const moog::ProgramView pv = moog::view_of(blob);
+  // layers partition the slots
+  if (hdr[MOOG_H_LAYER_OFF] != 0 || hdr[MOOG_H_LAYER_OFF + L] != S) return MOOG_E_INVAL;
+  for (int l = 0; l < L; ++l)
+    if (hdr[MOOG_H_LAYER_OFF + l + 1] < hdr[MOOG_H_LAYER_OFF + l]) return MOOG_E_INVAL;
+  // cached vertices: voff[S + 1] in ipool, non-decreasing, inside [0, VT]
+  const int vo = hdr[MOOG_H_VOFF];
+  if (vo < 0 || (long long)vo + S + 1 > NI) return MOOG_E_INVAL;
+  if (pv.ipool[vo] != 0 || pv.ipool[vo + S] > VT) return MOOG_E_INVAL;
+  for (int s2 = 0; s2 < S; ++s2) {
+    const int nv = pv.ipool[vo + s2 + 1] - pv.ipool[vo + s2];
+    if (nv < 0 || nv > MOOG_MAX_OUTLINE) return MOOG_E_INVAL;
+  }
+  // op sections
+  const int sect[6][2] = {{MOOG_H_FORCES, MOOG_H_N_FORCES}, {MOOG_H_CORR, MOOG_H_N_CORR},   {MOOG_H_RULES, MOOG_H_N_RULES},
+                          {MOOG_H_TASKS, MOOG_H_N_TASKS},   {MOOG_H_ACTIONS, MOOG_H_N_ACTIONS}, {MOOG_H_RESET, MOOG_H_N_RESET}};
+  for (int k = 0; k < 6; ++k) {
+    const int a = hdr[sect[k][0]], n = hdr[sect[k][1]];
+    if (n < 0 || (n > 0 && (a < 0 || (long long)a + n > NO))) return MOOG_E_INVAL;
+  }
+  // expression programs end inside the pool
+  if (NX > 0 && pv.expr[NX - 1].op != MOOG_X_END) return MOOG_E_INVAL;
+  for (int x = 0; x < NX; ++x) {
+    const moog_ex &e = pv.expr[x];
+    if (e.op < 0 || e.op > MOOG_X_STORE_POS) return MOOG_E_INVAL;
+    if ((e.op == MOOG_X_ATTR0 || e.op == MOOG_X_ATTR1 || e.op == MOOG_X_STORE) && (e.arg < 0 || e.arg >= MOOG_Z_N_ATTRS))
+      return MOOG_E_INVAL;
+  }
+  const int n_shapes_max = NI;  // shape table: offsets into dpool
+  const int st = hdr[MOOG_H_SHAPE_TAB];
+  if (st < 0 || st > NI) return MOOG_E_INVAL;
+  (void)n_shapes_max;
+  auto layer_ok = [&](int l) { return l >= 0 && l < L; };
+  auto list_ok = [&](int start, int count, int limit) {  // ipool[start, start + count): values in [0, limit)
+    if (count < 0 || (count > 0 && (start < 0 || (long long)start + count > NI))) return false;
+    for (int q = 0; q < count; ++q)
+      if (pv.ipool[start + q] < 0 || pv.ipool[start + q] >= limit) return false;
+    return true;
+  };
+  auto expr_ok = [&](int x) { return x == -1 || (x >= 0 && x < NX); };
+  auto cond_ok = [&](int o) { return o >= 0 && o < NO && pv.ops[o].kind >= MOOG_SC_ALL && pv.ops[o].kind <= MOOG_SC_BERNOULLI; };
+  auto envf_ok = [&](int f, int n) { return f >= 0 && (long long)f + n <= NF; };
+  auto table_ok = [&](int t) {  // sampler table: MOOG_Z_N_ATTRS leaves (kind, dpool index, n) + the extension count
+    if (t < 0 || (long long)t + 3 * MOOG_Z_N_ATTRS + 1 > NI) return false;
+    for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
+      const int kind = pv.ipool[t + 3 * a], idx = pv.ipool[t + 3 * a + 1], n = pv.ipool[t + 3 * a + 2];
+      if (kind < MOOG_ZK_CONST || kind > MOOG_ZK_DISCRETE || idx < 0 || n < 1 || (long long)idx + (kind == MOOG_ZK_UNIFORM32 ? 2 : n) > ND)
+        return false;
+    }
+    return pv.ipool[t + 3 * MOOG_Z_N_ATTRS] >= 0;
+  };
+  for (int o = 0; o < NO; ++o) {
+    const moog_op &op = pv.ops[o];
+    bool ok = true;
+    switch (op.kind) {
+      case MOOG_F_DRAG: case MOOG_F_KINETIC_FRICTION: case MOOG_F_DOWN_GRAVITY: case MOOG_F_GRAVITY: case MOOG_F_RANDOM:
+      case MOOG_F_DIST_LINEAR: case MOOG_F_DIST_SPRING: case MOOG_F_COLLISION: case MOOG_F_MAZE_WALK:
+        ok = layer_ok(op.i[0]) && (op.i[1] == -1 || layer_ok(op.i[1]));
+        if (op.kind == MOOG_F_MAZE_WALK) ok = ok && envf_ok(op.i[3], 1);
+        break;
+      case MOOG_C_TETHER: case MOOG_C_TETHER_ZIPPED: case MOOG_C_CONSTANT_SPEED: case MOOG_C_MAZE_PHYSICS:
+        ok = list_ok(op.i[0], op.i[1], L);
+        if (op.kind == MOOG_C_MAZE_PHYSICS) ok = ok && envf_ok(op.i[2], 1);
+        break;
+      case MOOG_R_VANISH_ON_CONTACT: case MOOG_R_PORTAL: ok = layer_ok(op.i[0]) && layer_ok(op.i[1]); break;
+      case MOOG_R_VANISH_BY_FILTER: ok = layer_ok(op.i[0]) && expr_ok(op.i[2]); break;
+      case MOOG_R_CHANGE_LAYER: ok = layer_ok(op.i[0]) && layer_ok(op.i[1]) && expr_ok(op.i[2]); break;
+      case MOOG_R_MODIFY_ON_CONTACT:
+        ok = list_ok(op.i[0], op.i[1], L) && list_ok(op.i[2], op.i[3], L) && op.i[4] >= 0 && (long long)op.i[4] + 4 <= NI;
+        for (int q = 0; ok && q < 4; ++q) ok = expr_ok(pv.ipool[op.i[4] + q]);
+        break;
+      case MOOG_R_MODIFY_SPRITES:
+        ok = list_ok(op.i[0], op.i[1], L) && expr_ok(op.i[2]) && expr_ok(op.i[3]) && op.i[4] >= 0 &&
+             op.i[4] <= hdr[MOOG_H_RULE_NOISE_DIM];
+        break;
+      case MOOG_R_COND_BEGIN: ok = cond_ok(op.i[0]) && op.i[1] >= 0 && (long long)o + 1 + op.i[1] <= NO; break;
+      case MOOG_R_TIMED_BEGIN: ok = op.i[1] >= 0 && (long long)o + 1 + op.i[1] <= NO && envf_ok(op.i[2], 2); break;
+      case MOOG_R_KEEP_NEAR_CENTER: ok = layer_ok(op.i[0]) && list_ok(op.i[1], op.i[2], L); break;
+      case MOOG_R_CREATE_SPRITES:
+        ok = layer_ok(op.i[0]) && op.i[1] >= 0 && list_ok(op.i[2], op.i[3], L) && table_ok(op.i[4]);
+        break;
+      case MOOG_T_CONTACT_REWARD:
+        ok = list_ok(op.i[0], op.i[1], L) && list_ok(op.i[2], op.i[3], L) && expr_ok(op.i[4]) && envf_ok(op.i[5], 1) &&
+             (!(op.p[2] > 0) || expr_ok((int)op.p[2] - 1));
+        break;
+      case MOOG_T_RESET: ok = cond_ok(op.i[0]) && envf_ok(op.i[5], 1); break;
+      case MOOG_T_STAY_ALIVE: ok = op.p[0] >= 1; break;
+      case MOOG_T_TIMEOUT: break;
+      case MOOG_A_JOYSTICK: case MOOG_A_GRID: case MOOG_A_SET_POSITION:
+        ok = list_ok(op.i[0], op.i[1], L) && op.i[2] >= 0 &&
+             op.i[2] + (op.kind == MOOG_A_GRID ? 1 : 2) <= (hdr[MOOG_H_ACTION_DIM] > 0 ? hdr[MOOG_H_ACTION_DIM] : 1) + 1 &&
+             (op.kind == MOOG_A_SET_POSITION || envf_ok(op.i[5], 2));
+        break;
+      case MOOG_Z_GENERATE:
+        ok = op.i[0] >= 0 && op.i[1] >= 0 && (long long)op.i[0] + op.i[1] <= S && list_ok(op.i[2], op.i[3], S > 0 ? S : 1) &&
+             table_ok(op.i[4]);
+        break;
+      case MOOG_SC_ALL: case MOOG_SC_ANY: case MOOG_SC_COUNT: case MOOG_SC_FIRST:
+        ok = list_ok(op.i[0], op.i[1], L) && expr_ok(op.i[2]);
+        break;
+      case MOOG_SC_CONTACT_COUNT: ok = layer_ok(op.i[0]) && layer_ok(op.i[1]); break;
+      case MOOG_SC_CONTACT_ANY_COUNT: ok = list_ok(op.i[0], op.i[1], L) && list_ok(op.i[2], op.i[3], L) && expr_ok(op.i[4]); break;
+      case MOOG_SC_CONST: break;
+      case MOOG_SC_BINARY: ok = cond_ok(op.i[0]) && cond_ok(op.i[1]); break;
+      case MOOG_SC_NOT: ok = cond_ok(op.i[0]); break;
+      case MOOG_SC_BERNOULLI: ok = op.i[0] >= 0 && op.i[0] < hdr[MOOG_H_RULE_NOISE_DIM]; break;
+      default: ok = false; break;  // an op kind no kernel knows
+    }
+    if (!ok) return MOOG_E_INVAL;
+  }
+  if (hdr[MOOG_H_R_ENABLED]) {
+    if (hdr[MOOG_H_R_HEIGHT] < 1 || hdr[MOOG_H_R_WIDTH] < 1 || hdr[MOOG_H_R_AA] < 1 || hdr[MOOG_H_R_HEIGHT] > 8192 ||
+        hdr[MOOG_H_R_WIDTH] > 8192 || hdr[MOOG_H_R_AA] > 16)
+      return MOOG_E_INVAL;
+    if (hdr[MOOG_H_R_MODIFIER] == MOOG_PMOD_FIRST_PERSON && !layer_ok(hdr[MOOG_H_R_MOD_LAYER])) return MOOG_E_INVAL;
+  }
+  return 0;
+}
+
+int moog_program_create(const void *blob, size_t nbytes, moog_program **out) {
+  if (!out) return MOOG_E_INVAL;
+  const int bad = moog_program_validate(blob, nbytes);
+  if (bad) return bad;
+  const int32_t *hdr = (const int32_t *)blob;
   if (hdr[MOOG_H_N_FORCES] > moog::kMaxForceOps) return MOOG_E_TOO_BIG;
   moog_program *p = (moog_program *)calloc(1, sizeof(moog_program));
   if (!p) return MOOG_E_INVAL;
@@ -354,7 +482,11 @@ static int render_impl(moog_program *p, const moog_state *st, int n_envs, uint8_
       cudaError_t err = cudaMalloc((void **)&p->resample, sizeof(int) * (size_t)n);
       if (err == cudaSuccess)
         err = cudaMemcpy(p->resample, table.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice);
-      if (err != cudaSuccess) return cuda_fail(err);
+      if (err != cudaSuccess) {  // never keep a table that was not filled
+        if (p->resample) cudaFree(p->resample);
+        p->resample = nullptr;
+        return cuda_fail(err);
+      }
     }
     a.resample = p->resample;
     a.ksize_h = p->ksize_h;

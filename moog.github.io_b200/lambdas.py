@@ -129,8 +129,7 @@ class SymSprite(object):
             self._stores.append(('position', (Sym.lift(value[0]), Sym.lift(value[1]))))
             return
         if name == 'velocity':
-            self._stores.append(('x_vel', Sym.lift(value[0])))
-            self._stores.append(('y_vel', Sym.lift(value[1])))
+            self._stores.append(('velocity', (Sym.lift(value[0]), Sym.lift(value[1]))))
             return
         if name not in _WRITABLE:
             raise LoweringError(
@@ -467,6 +466,18 @@ def compile_modifier(fn):
     for name, value in stores:
         if name == 'position':
             code += value[0].code + value[1].code + [(X_STORE_POS, 0, 0.0)]
+            continue
+        if name == 'velocity':
+            # Python evaluates the whole right-hand side first (`s.velocity = np.array([-s.y_vel, s.x_vel])`):
+            # both components are pushed, then stored from the top of the stack down.  The setter installs
+            # a FRESH array (sprite.py:639-643): one that is built from constants / positions only is
+            # float64 and shared with nobody (c = 3: the device drops MOOG_SF_VEL32 and the alias id);
+            # one computed from the sprite's own velocity keeps that velocity's dtype (c = 0).
+            dtype_free = not any(op in (X_ATTR0, X_ATTR1) and ATTRS[arg] in ('x_vel', 'y_vel', 'angle_vel', 'angle')
+                                 for v in value for op, arg, _ in v.code)
+            kind = 3.0 if dtype_free else 0.0
+            code += value[0].code + value[1].code + [(X_STORE, ATTRS.index('y_vel'), kind),
+                                                     (X_STORE, ATTRS.index('x_vel'), kind)]
             continue
         # c: NumPy kind of the stored value as far as the device tracks it (angle: a pure constant is a
         # python float, anything computed from sprite factors counts as np.float64)

@@ -1491,6 +1491,9 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
         } else {
           *attr_ptr(e, s0, x->arg) = v;
           if (x->arg == MOOG_AT_SCALE || x->arg == MOOG_AT_ASPECT_RATIO) set_path(e, s0);
+          /* sprite.py:639-643: the velocity setter installs a fresh array; x->c = 3: a float64 one */
+          if ((x->arg == MOOG_AT_X_VEL || x->arg == MOOG_AT_Y_VEL) && x->c == 3.0)
+            META(e, MOOG_M_FLAGS, s0) &= ~(MOOG_SF_VEL32 | (MOOG_SF_VALIAS_MASK << MOOG_SF_VALIAS_SHIFT));
         }
         break;
       }

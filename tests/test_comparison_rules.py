@@ -27,3 +27,41 @@ def test_rel_err_is_relative_with_a_floor():
     assert rel_err([1e-12], [0.0]) < RTOL          # absolute floor for exact zeros
     assert rel_err([1e-3], [0.0]) > RTOL
     assert rel_err(np.zeros((3, 4)), np.zeros((3, 4))) == 0.0
+
+
+def test_velocity_assignment_evaluates_the_right_hand_side_first():
+    """`s.velocity = np.array([-s.y_vel, s.x_vel])` (a quarter turn): Python builds the new array from
+    the OLD components before the setter runs (sprite.py:639-643); the lowered modifier pushes both
+    values and only then stores them.  A velocity built from constants is a fresh float64 array: the
+    float32 flag and the alias id of the sprite go, one computed from the old velocity keeps the dtype."""
+    import collections
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, game_rules, physics as physics_lib, sprite, tasks
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+
+    def turn(s):
+        s.velocity = np.array([-s.y_vel, s.x_vel])
+
+    def stop(s):
+        s.velocity = np.zeros(2)
+
+    def state_initializer():
+        a = sprite.Sprite(x=0.3, y=0.5, shape='square', scale=0.1,
+                          x_vel=np.float32(0.25), y_vel=np.float32(0.5))
+        b = sprite.Sprite(x=0.7, y=0.5, shape='square', scale=0.1,
+                          x_vel=np.float32(0.125), y_vel=np.float32(-0.375))
+        return collections.OrderedDict([('turning', [a]), ('stopping', [b])])
+
+    cfg = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(timeout_steps=50), action_space=action_spaces.Grid(action_layers=()),
+               observers={}, game_rules=(game_rules.ModifySprites('turning', turn),
+                                         game_rules.ModifySprites('stopping', stop)))
+    states = [state_initializer()]
+    prog = compiler.compile_config(cfg, states)
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    assert (orc.meta[0, 1] & 2).all(), 'both sprites start with a float32 velocity array'
+    orc.post_reset()            # every rule is stepped once (environment.py:94-95)
+    assert orc.dyn[0, 2:4, 0].tolist() == [-0.5, 0.25]
+    assert orc.dyn[0, 2:4, 1].tolist() == [0.0, 0.0]
+    assert orc.meta[0, 1, 0] & 2 and not orc.meta[0, 1, 1] & 2

@@ -509,3 +509,69 @@ def test_impure_config_callables_are_refused():
     cfg['game_rules'] = (inner,)
     with pytest.raises(compiler.CompileError, match='nested deeper'):
         compiler.compile_config(cfg, states)
+
+
+def test_program_blobs_are_validated():
+    """moog_program_validate (what moog_program_create runs first; no GPU needed): every golden program
+    and every config of this package passes; blobs with a section, pool index, layer id, expression
+    start, op kind or outline offset out of range are MOOG_E_INVAL, not an out-of-bounds read."""
+    import ctypes
+    import glob
+    import importlib
+    import moog_b200  # noqa: F401
+    from moog_b200 import capi, compiler as C
+    L = capi.lib()
+
+    def check(blob):
+        buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(bytes(blob))
+        return L.moog_program_validate(ctypes.cast(buf, ctypes.c_void_p), len(blob))
+
+    blobs = []
+    for path in sorted(glob.glob(os.path.join(util.GOLDEN, '*.npz'))):
+        g = np.load(path)
+        if 'blob' in g:
+            blobs.append((os.path.basename(path), bytes(bytearray(g['blob']))))
+    for name in ('colliding_predators84', 'cleanup64', 'synthetic32', 'pacman64', 'spawn_zoo', 'portal_zoo'):
+        mod = importlib.import_module('moog_b200.configs.' + name)
+        cfg = mod.get_config()
+        np.random.seed(4)
+        states = [cfg['state_initializer']() for _ in range(3)]
+        blobs.append((name, C.compile_config(cfg, states, layer_capacity=getattr(mod, 'LAYER_CAPACITY', None),
+                                             reset_sampler=name == 'colliding_predators84').blob))
+    assert len(blobs) > 25
+    for name, blob in blobs:
+        assert check(blob) == 0, name
+    # corruptions of one well-formed program
+    good = np.frombuffer(dict(blobs)['spawn_zoo'], dtype=np.uint8)
+    hdr0 = good[:C.HDR_WORDS * 4].view('<i4')
+    n_ops = int(hdr0[C.H_N_OPS])
+
+    def corrupt(edit):
+        b = good.copy()
+        edit(b[:C.HDR_WORDS * 4].view('<i4'), b[C.HDR_WORDS * 4:C.HDR_WORDS * 4 + 80 * n_ops].view('<i4').reshape(n_ops, 20))
+        return check(b.tobytes())
+
+    def setw(i, v):
+        return lambda h, ops: h.__setitem__(i, v)
+
+    assert check(good.tobytes()[:-8]) != 0                                  # truncated
+    assert corrupt(setw(C.H_N_RULES, n_ops + 1)) != 0                        # section beyond the ops
+    assert corrupt(setw(C.H_RULES, -3)) != 0
+    assert corrupt(setw(C.H_VOFF, int(hdr0[C.H_N_IPOOL]))) != 0              # voff outside ipool
+    assert corrupt(setw(C.H_LAYER_OFF + 1, 10 ** 6)) != 0                    # layers not a partition of the slots
+    assert corrupt(setw(C.H_N_LAYERS, 99)) != 0
+    assert corrupt(setw(C.H_SHAPE_TAB, -1)) != 0
+    assert corrupt(setw(C.H_N_VTX, 1)) != 0                                  # outlines beyond the vertex array
+    rules = int(hdr0[C.H_RULES])
+    assert corrupt(lambda h, ops: ops[rules].__setitem__(0, 9999)) != 0       # unknown op kind
+    assert corrupt(lambda h, ops: ops[rules].__setitem__(2, n_ops + 5)) != 0  # ConditionalRule -> no condition op
+    create = [k for k in range(n_ops) if ops_kind(good, n_ops, k) == C.R_CREATE_SPRITES][0]
+    assert corrupt(lambda h, ops: ops[create].__setitem__(2, 77)) != 0        # layer id
+    assert corrupt(lambda h, ops: ops[create].__setitem__(6, 10 ** 7)) != 0   # sampler table outside ipool
+    vanish = [k for k in range(n_ops) if ops_kind(good, n_ops, k) == C.R_VANISH_BY_FILTER][0]
+    assert corrupt(lambda h, ops: ops[vanish].__setitem__(4, 10 ** 6)) != 0   # expression start
+
+
+def ops_kind(blob, n_ops, k):
+    from moog_b200 import compiler as C
+    return int(blob[C.HDR_WORDS * 4:C.HDR_WORDS * 4 + 80 * n_ops].view('<i4').reshape(n_ops, 20)[k, 0])
