@@ -124,6 +124,9 @@ enum {
   MOOG_H_N_RESET = 52,    /* number of them (0: resets draw from the caller's pool only) */
   MOOG_H_N_DPOOL = 53,    /* doubles in dpool */
   MOOG_H_SHAPE_TAB = 54,  /* index in ipool of shape_off[n_shapes]: offset in dpool of each shape record */
+  MOOG_H_N_META = 55,     /* numeric `sprite.metadata[key]` columns the program's callables read (<= MOOG_MAX_META) */
+  MOOG_H_META_OFF = 56,   /* envf offset of column 0; column k of slot s is envf[off + k * S + s], NaN = no such key.
+                             Read as attribute MOOG_AT_META0 + k; travels with the sprite when slots are compacted */
   MOOG_H_CMASK_WORDS = 50 /* 32-bit words of the per-env broad-phase candidate matrices of all
                              MOOG_F_COLLISION ops (rows = capacity of layer a, ceil(capacity of
                              layer b / 32) words per row).  Derived: moog_program_create fills
@@ -284,16 +287,20 @@ enum {
   MOOG_X_STORE,      /* pop -> attribute `arg` of sprite 0 (modifier programs).  c: for `angle` the NumPy kind of
                         the value (sprite.py:531-540); for `x_vel` / `y_vel` 3 = the components of a FRESH float64
                         array (`s.velocity = np.zeros(2)`, sprite.py:639-643): MOOG_SF_VEL32 and the alias id go */
-  MOOG_X_STORE_POS   /* pop y, pop x -> sprite 0 `.position = (x, y)`: one translation of the cached
+  MOOG_X_STORE_POS,  /* pop y, pop x -> sprite 0 `.position = (x, y)`: one translation of the cached
                         outline (sprite.py:616-633) */
+  MOOG_X_SELECT      /* pop b, pop a, pop c -> (c != 0 ? a : b): an `if` / `else` of a config callable on a
+                        per-sprite value, both sides traced (lambdas._explore) */
 };
 
 /* attribute ids for the expression VM (Sprite.FACTOR_NAMES, sprite.py:237-253) */
 enum {
   MOOG_AT_X = 0, MOOG_AT_Y, MOOG_AT_X_VEL, MOOG_AT_Y_VEL, MOOG_AT_ANGLE,
   MOOG_AT_ANGLE_VEL, MOOG_AT_MASS, MOOG_AT_SCALE, MOOG_AT_ASPECT_RATIO,
-  MOOG_AT_C0, MOOG_AT_C1, MOOG_AT_C2, MOOG_AT_OPACITY
+  MOOG_AT_C0, MOOG_AT_C1, MOOG_AT_C2, MOOG_AT_OPACITY,
+  MOOG_AT_META0 = 16 /* + k: column k of the sprite's numeric metadata (MOOG_H_META_OFF) */
 };
+#define MOOG_MAX_META 8
 
 /* step_type values written by the kernels (dm_env.StepType) */
 enum { MOOG_STEP_FIRST = 0, MOOG_STEP_MID = 1, MOOG_STEP_LAST = 2 };

@@ -54,6 +54,7 @@ H_VOFF = 31
 H_LAYER_OFF = 32
 H_N_VTX = 49
 H_RESET, H_N_RESET, H_N_DPOOL, H_SHAPE_TAB = 51, 52, 53, 54
+H_N_META, H_META_OFF = 55, 56
 
 F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
     F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION, F_MAZE_WALK = range(1, 10)
@@ -115,6 +116,8 @@ class Program(object):
         self.ipool = []
         self.expr = []           # list of (op, arg, c)
         self.dpool = []          # doubles: shape table / sampler parameters of the reset sampler
+        self.meta_keys = []      # `sprite.metadata[key]` columns the callables read (lambdas.metadata_columns)
+        self.meta_off = 0        # envf offset of column 0 (column k of slot s: meta_off + k * n_slots + s)
         self.z_shape_ids = {}    # device sampler: shape candidate -> index of its shape record
         self.z_shape_recs = []
         self.reset_shapes = []   # shape candidates of the reset sampler, by shape id
@@ -243,6 +246,8 @@ class Program(object):
         hdr[H_RESET], hdr[H_N_RESET] = start, count
         hdr[H_N_DPOOL] = len(self.dpool)
         hdr[H_SHAPE_TAB] = getattr(self, 'shape_tab', 0)
+        hdr[H_N_META] = len(self.meta_keys)
+        hdr[H_META_OFF] = self.meta_off
         dpool = np.array(self.dpool, dtype='<f8')
         blob = hdr.tobytes() + ops.tobytes() + ipool.tobytes() + expr.tobytes() + dpool.tobytes()
         hdr[H_BYTES] = len(blob)
@@ -761,11 +766,15 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
             voff.append(voff[-1] + vc)
     prog.voff = voff
 
-    _compile_physics(prog, config['physics'])
-    _compile_tasks(prog, config['task'])
-    _compile_actions(prog, config['action_space'])
-    _compile_rules(prog, config.get('game_rules', ()))
+    with lambdas.metadata_columns(prog.meta_keys):
+        _compile_physics(prog, config['physics'])
+        _compile_tasks(prog, config['task'])
+        _compile_actions(prog, config['action_space'])
+        _compile_rules(prog, config.get('game_rules', ()))
     _compile_render(prog, config.get('observers', {}))
+    if prog.meta_keys:
+        # numeric sprite.metadata[key] values travel with the sprite: one envf column of n_slots doubles per key
+        prog.meta_off = prog.alloc_envf(len(prog.meta_keys) * prog.n_slots)
     if reset_sampler:
         _compile_reset_sampler(prog, config['state_initializer'])
     _finish_z_shapes(prog)
@@ -1269,6 +1278,25 @@ def pack_states(prog, states, shape_table=None):
         for e, st in enumerate(states):
             for layer, off in prog.maze_offsets.items():
                 envf[e, off:off + host_maze.MAZE_WORDS] = host_maze.maze_record(st[layer])
+    meta_keys = getattr(prog, 'meta_keys', None)
+    if meta_keys:
+        # sprite.metadata[key] for the keys the program's callables read; NaN where a sprite has no such
+        # key (the reference would raise KeyError there) -- bools and numbers only
+        S = prog.n_slots
+        envf[:, prog.meta_off:prog.meta_off + len(meta_keys) * S] = np.nan
+        for e, st in enumerate(states):
+            for l, name in enumerate(prog.layer_names):
+                for k, sp in enumerate(st[name]):
+                    md = getattr(sp, 'metadata', None)
+                    if not isinstance(md, dict):
+                        continue
+                    for c, key in enumerate(meta_keys):
+                        if key in md:
+                            v = md[key]
+                            if v is None or not (isinstance(v, (bool, int, float)) or hasattr(v, '__float__')):
+                                raise CompileError('sprite.metadata[{!r}] = {!r}: only numbers and bools are carried on '
+                                                   'the device'.format(key, v))
+                            envf[e, prog.meta_off + c * S + prog.layer_off[l] + k] = float(v)
     shape_verts, shape_nv = table.arrays()
     return dict(dyn=dyn, stat=stat, meta=meta, vtx=vtx, cnt=cnt, envi=envi,
                 envf=envf, shape_verts=shape_verts, shape_nv=shape_nv,

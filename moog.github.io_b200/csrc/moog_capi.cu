@@ -96,6 +96,10 @@ int moog_program_validate(const void *blob, size_t nbytes) {
                       sizeof(double) * (size_t)ND;
   if (need != nbytes) return MOOG_E_INVAL;
   const moog::ProgramView pv = moog::view_of(blob);
+  // metadata columns: N_META blocks of S doubles inside envf
+  if (hdr[MOOG_H_N_META] < 0 || hdr[MOOG_H_N_META] > MOOG_MAX_META ||
+      (hdr[MOOG_H_N_META] > 0 && (hdr[MOOG_H_META_OFF] < 0 || (long long)hdr[MOOG_H_META_OFF] + (long long)hdr[MOOG_H_N_META] * S > NF)))
+    return MOOG_E_INVAL;
   // layers partition the slots
   if (hdr[MOOG_H_LAYER_OFF] != 0 || hdr[MOOG_H_LAYER_OFF + L] != S) return MOOG_E_INVAL;
   for (int l = 0; l < L; ++l)
@@ -119,8 +123,9 @@ int moog_program_validate(const void *blob, size_t nbytes) {
   if (NX > 0 && pv.expr[NX - 1].op != MOOG_X_END) return MOOG_E_INVAL;
   for (int x = 0; x < NX; ++x) {
     const moog_ex &e = pv.expr[x];
-    if (e.op < 0 || e.op > MOOG_X_STORE_POS) return MOOG_E_INVAL;
-    if ((e.op == MOOG_X_ATTR0 || e.op == MOOG_X_ATTR1 || e.op == MOOG_X_STORE) && (e.arg < 0 || e.arg >= MOOG_Z_N_ATTRS))
+    if (e.op < 0 || e.op > MOOG_X_SELECT) return MOOG_E_INVAL;
+    if ((e.op == MOOG_X_ATTR0 || e.op == MOOG_X_ATTR1 || e.op == MOOG_X_STORE) &&
+        !((e.arg >= 0 && e.arg <= MOOG_AT_OPACITY) || (e.arg >= MOOG_AT_META0 && e.arg < MOOG_AT_META0 + hdr[MOOG_H_N_META])))
       return MOOG_E_INVAL;
   }
   const int n_shapes_max = NI;  // shape table: offsets into dpool

@@ -2430,6 +2430,7 @@ __device__ __noinline__ void set_path(const Env &, int s) {
 // expression VM (config lambdas compiled by the host)
 // ---------------------------------------------------------------------------
 __device__ inline double *attr_ptr(const Env &e, int s, int at) {
+  if (at >= MOOG_AT_META0) return &e.envf[e.hdr[MOOG_H_META_OFF] + (at - MOOG_AT_META0) * e.S + s];
   switch (at) {
     case MOOG_AT_X: return &DYN(e, MOOG_D_X, s);
     case MOOG_AT_Y: return &DYN(e, MOOG_D_Y, s);
@@ -2494,6 +2495,11 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
           puti(e, &META(e, MOOG_M_FLAGS, s0), fl);
           wsync();
         }
+        break;
+      }
+      case MOOG_X_SELECT: {  // c ? a : b
+        const double vb = st[--sp], va = st[--sp], vc = st[--sp];
+        st[sp++] = vc != 0 ? va : vb;
         break;
       }
       default:
@@ -2646,6 +2652,10 @@ __device__ inline void copy_slot(const Env &e, int dst, int src) {
   if (e.lane < MOOG_META_FIELDS) META(e, e.lane, dst) = META(e, e.lane, src);
   if (e.lane < 4) BOX(e, e.lane, dst) = BOX(e, e.lane, src);
   if (e.lane == 0) e.sflag[dst] = e.sflag[src];
+  if (e.lane < e.hdr[MOOG_H_N_META]) {  // the sprite's metadata columns travel with it
+    double *m = e.envf + e.hdr[MOOG_H_META_OFF] + e.lane * e.S;
+    m[dst] = m[src];
+  }
   for (int i = e.lane; i < nv; i += 32) e.vtx[e.voff[dst] + i] = e.vtx[e.voff[src] + i];
   wsync();
 }
@@ -2827,6 +2837,8 @@ __device__ __noinline__ void generate_sprites_dev(const Env &, const moog_op *op
         META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
         META(e, MOOG_M_NV, s) = (int)R[0];
         e.cnt[layer] = s - LOFF(e, layer) + 1;
+        for (int m = 0; m < e.hdr[MOOG_H_N_META]; ++m)  // a new sprite's metadata is {}
+          e.envf[e.hdr[MOOG_H_META_OFF] + m * e.S + s] = NAN;
       }
       wsync();
       set_path(e, s);

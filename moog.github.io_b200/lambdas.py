@@ -28,7 +28,11 @@ import numpy as np
 
 (X_END, X_CONST, X_ATTR0, X_ATTR1, X_LT, X_LE, X_GT, X_GE, X_EQ, X_NE, X_AND,
  X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE,
- X_STORE_POS) = range(22)
+ X_STORE_POS, X_SELECT) = range(23)
+
+# attribute ids from here on read the sprite's numeric `metadata[key]` columns (MOOG_AT_META0)
+AT_META0 = 16
+MAX_META_KEYS = 8
 
 ATTRS = ('x', 'y', 'x_vel', 'y_vel', 'angle', 'angle_vel', 'mass', 'scale',
          'aspect_ratio', 'c0', 'c1', 'c2', 'opacity')
@@ -97,10 +101,102 @@ class Sym(object):
     def __invert__(self): return Sym(self.code + [(X_NOT, 0, 0.0)])
 
     def __bool__(self):
-        raise LoweringError(
-            'the callable branches on a per-sprite value (if / and / or / not '
-            'on a sprite attribute); write the test as a single comparison or '
-            'combine comparisons with & and |')
+        path = _PATH[0]
+        if path is None:
+            raise LoweringError(
+                'the callable branches on a per-sprite value (if / and / or / not '
+                'on a sprite attribute); write the test as a single comparison or '
+                'combine comparisons with & and |')
+        return path.decide(self)
+
+
+class _Path(object):
+    """One execution path of a callable that branches on traced values (`if sprite.c0 < 128: ...`):
+    the first len(forced) decisions are replayed, later ones are taken True and remembered."""
+
+    def __init__(self, forced):
+        self.forced = list(forced)
+        self.pos = 0
+        self.new = []
+
+    def decide(self, cond):
+        k = self.pos
+        self.pos += 1
+        if k < len(self.forced):
+            return self.forced[k]
+        self.new.append(cond)
+        self.forced.append(True)
+        return True
+
+
+_PATH = [None]
+_MAX_PATHS = 64
+
+
+def _select(cond, a, b):
+    """`a if cond else b` as one expression (MOOG_X_SELECT; both sides are evaluated, neither has effects)."""
+    if not isinstance(a, Sym) and not isinstance(b, Sym) and type(a) is type(b) and a == b:
+        return a
+    a, b = Sym.lift(a), Sym.lift(b)
+    if a.code == b.code:
+        return a
+    return Sym(cond.code + a.code + b.code + [(X_SELECT, 0, 0.0)])
+
+
+def _explore(fn, args, prefix=(), budget=None):
+    """Value of fn(*args) over every path its data-dependent `if`s can take, folded into selects."""
+    budget = [_MAX_PATHS] if budget is None else budget
+    budget[0] -= 1
+    if budget[0] < 0:
+        raise LoweringError('the callable branches on per-sprite values along more than {} paths'.format(_MAX_PATHS))
+    previous, _PATH[0] = _PATH[0], _Path(prefix)
+    path = _PATH[0]
+    try:
+        value = fn(*args)
+    finally:
+        _PATH[0] = previous
+    base = len(prefix)
+    for j in range(len(path.new) - 1, -1, -1):
+        other = _explore(fn, args, tuple(path.forced[:base + j]) + (False,), budget)
+        value = _select(path.new[j], value, other)
+    return value
+
+
+# `sprite.metadata[key]` of numeric (or bool) values: the keys a program's callables read, in the order
+# they were first seen; column k lives in the state record (envf block MOOG_H_META_OFF) and is read
+# as attribute AT_META0 + k.  compiler.compile_config installs the list for the program it builds.
+_META_KEYS = [None]
+
+
+@contextlib.contextmanager
+def metadata_columns(keys):
+    previous, _META_KEYS[0] = _META_KEYS[0], keys
+    try:
+        yield keys
+    finally:
+        _META_KEYS[0] = previous
+
+
+class SymMetadata(object):
+    """`sprite.metadata` while tracing: item reads become reads of a metadata column."""
+
+    def __init__(self, which):
+        self._which = which
+
+    def __getitem__(self, key):
+        keys = _META_KEYS[0]
+        if keys is None:
+            raise LoweringError('sprite.metadata is not available to this callable on the device')
+        if not isinstance(key, str):
+            raise LoweringError('sprite.metadata keys must be strings on the device path')
+        if key not in keys:
+            if len(keys) >= MAX_META_KEYS:
+                raise LoweringError('at most {} metadata keys are carried on the device'.format(MAX_META_KEYS))
+            keys.append(key)
+        return Sym([(X_ATTR0 if self._which == 0 else X_ATTR1, AT_META0 + keys.index(key), 0.0)])
+
+    def get(self, key, default=None):
+        raise LoweringError('sprite.metadata.get() is not lowered: read the key directly')
 
 
 class SymSprite(object):
@@ -119,6 +215,8 @@ class SymSprite(object):
             return SymVec([self.x, self.y])
         if name == 'velocity':
             return SymVec([self.x_vel, self.y_vel])
+        if name == 'metadata':
+            return SymMetadata(self._which)
         raise LoweringError(
             'sprite attribute {!r} is not available on the device'.format(name))
 
@@ -415,11 +513,14 @@ def no_randomness(what='callable'):
             setattr(mod, n, fn)
 
 
-def _symbolic_call(fn, *args):
+def _symbolic_call(fn, *args, **options):
     """fn(*args) on symbolic sprites; when the callable uses Python's `and` / `or` / `not` /
     `any` / `all` on per-sprite values (which plain tracing cannot see), it is recompiled with
-    those constructs turned into expression builders and traced again.  Random draws are refused
-    (`no_randomness`)."""
+    those constructs turned into expression builders and traced again; when it still branches
+    (`if` / `elif` / conditional expressions on a traced value) and has no effects
+    (`branches=True`: predicates, conditions, rewards), every path is traced and the results are
+    folded into selects.  Random draws are refused (`no_randomness`)."""
+    branches = options.get('branches', True)
     with no_randomness(repr(getattr(fn, '__name__', fn))):
         try:
             return fn(*args)
@@ -427,7 +528,19 @@ def _symbolic_call(fn, *args):
             raise
         except (LoweringError, TypeError):
             try:
-                return _rewritten(fn)(*args)
+                rewritten = _rewritten(fn)
+            except LoweringError:
+                raise
+            except Exception as exc:  # pylint: disable=broad-except
+                raise LoweringError('cannot lower {!r} to a device expression ({}: {})'.format(
+                    getattr(fn, '__name__', fn), type(exc).__name__, exc))
+            try:
+                try:
+                    return rewritten(*args)
+                except LoweringError:
+                    if not branches:
+                        raise
+                    return _explore(rewritten, args)
             except LoweringError:
                 raise
             except Exception as exc:  # pylint: disable=broad-except
@@ -461,7 +574,7 @@ def compile_pair_condition(fn):
 def compile_modifier(fn):
     """`fn(sprite)` mutating the sprite -> postfix code of its stores."""
     stores = []
-    _symbolic_call(fn, SymSprite(0, stores))
+    _symbolic_call(fn, SymSprite(0, stores), branches=False)
     code = []
     for name, value in stores:
         if name == 'position':
@@ -473,7 +586,7 @@ def compile_modifier(fn):
             # a FRESH array (sprite.py:639-643): one that is built from constants / positions only is
             # float64 and shared with nobody (c = 3: the device drops MOOG_SF_VEL32 and the alias id);
             # one computed from the sprite's own velocity keeps that velocity's dtype (c = 0).
-            dtype_free = not any(op in (X_ATTR0, X_ATTR1) and ATTRS[arg] in ('x_vel', 'y_vel', 'angle_vel', 'angle')
+            dtype_free = not any(op in (X_ATTR0, X_ATTR1) and arg < len(ATTRS) and ATTRS[arg] in ('x_vel', 'y_vel', 'angle_vel', 'angle')
                                  for v in value for op, arg, _ in v.code)
             kind = 3.0 if dtype_free else 0.0
             code += value[0].code + value[1].code + [(X_STORE, ATTRS.index('y_vel'), kind),

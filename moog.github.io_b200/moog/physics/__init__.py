@@ -5,7 +5,8 @@ gravity.py, friction.py, random_force.py, distance_fn_force.py,
 tether_physics.py, constant_speed.py).  These classes only record their
 parameters under the reference's attribute names; the config compiler
 (moog_b200.compiler) lowers them to device ops and the sm_100a physics kernel
-executes them.  Calling `.step()` on the host is deliberately unsupported.
+executes them.  `Physics.step(state)` on the host (used by a few state initializers) runs that same
+kernel on a batch of one env (moog_b200/host_physics.py); single forces cannot be stepped on the host.
 """
 
 import abc
@@ -52,7 +53,11 @@ class AbstractPhysics(_DeviceOnly, abc.ABC):
         pass
 
     def step(self, state):
-        self._host_call()
+        """abstract_physics.py:39-42 called by a config on the host (a state initializer that rolls
+        the physics forward): a batch of one env through the CUDA physics kernel, results written
+        back into the host sprites (moog_b200/host_physics.py).  Needs the GPU."""
+        from moog_b200 import host_physics
+        host_physics.step(self, state)
 
     @property
     def updates_per_env_step(self):

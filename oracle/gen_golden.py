@@ -90,6 +90,12 @@ SCENES = {
     'reshape_zoo': ('moog_b200.configs.reshape_zoo', None, 16, 40, 5),
     # Portal (square and circular portal pairs) and ChangeLayer into a layer that starts empty
     'portal_zoo': ('moog_b200.configs.portal_zoo', None, 17, 45, 5),
+    # a shipped config whose ContactReward reward_fn branches on `sprite.metadata[...]` (red_green.py:171-176)
+    # and whose state initializer rolls the physics forward on the host; the agent waits, then walks into
+    # the red response box
+    'red_green': ('moog_demos.example_configs.red_green', 1, 18, 200, 10),
+    # this repo's small version of the same pattern: an if / elif / else reward over two metadata keys
+    'predict_zoo': ('moog_b200.configs.predict_zoo', None, 19, 69, 6),
 }
 
 
@@ -300,6 +306,10 @@ def generate(name, out_dir):
             action = _chase_action(env, t)
         elif name == 'pacman':
             action = _pacman_action(env, t)
+        elif name == 'predict_zoo':
+            action = 4 if t < 30 else (0 if t < 50 else 1)      # wait, walk into the left box, then back to the right one
+        elif name == 'red_green':
+            action = (4 if t % 9 else 3 - (t // 9) % 2) if t < 100 else 1      # wait (a little up / down), then go right
         elif name == 'timed_center':
             action = np.array([1.0, 0.6]) if t < 25 else np.array([-1.0, -1.0])   # leaves the centre cell repeatedly
         else:

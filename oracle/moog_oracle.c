@@ -1404,6 +1404,8 @@ static void apply_physics(env_t *e) {
 /* ------------------------------------------------------------------------ */
 
 static double *attr_ptr(env_t *e, int s, int at) {
+  if (at >= MOOG_AT_META0) /* sprite.metadata[key], column at - MOOG_AT_META0 */
+    return &e->envf[e->hdr[MOOG_H_META_OFF] + (at - MOOG_AT_META0) * e->S + s];
   switch (at) {
     case MOOG_AT_X: return &DYN(e, MOOG_D_X, s);
     case MOOG_AT_Y: return &DYN(e, MOOG_D_Y, s);
@@ -1500,6 +1502,11 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
       case MOOG_X_STORE_POS: {
         double ny = st[--sp], nx = st[--sp];
         set_position(e, s0, nx, ny);
+        break;
+      }
+      case MOOG_X_SELECT: { /* an `if` / `else` of the config callable on a per-sprite value */
+        const double vb = st[--sp], va = st[--sp], vc = st[--sp];
+        st[sp++] = vc != 0 ? va : vb;
         break;
       }
       default:
@@ -1711,6 +1718,8 @@ static void generate_sprites(env_t *e, const moog_op *op, uint64_t key, uint32_t
       META(e, MOOG_M_FLAGS, s) = op->i[5] | (R[1] != 0.0 ? MOOG_SF_CIRCLE : 0);
       META(e, MOOG_M_NV, s) = (int)R[0];
       e->cnt[layer] = s - LOFF(e, layer) + 1;
+      for (int m = 0; m < e->hdr[MOOG_H_N_META]; ++m) /* a new sprite's metadata is {} */
+        e->envf[e->hdr[MOOG_H_META_OFF] + m * e->S + s] = NAN;
       set_path(e, s);
       set_position(e, s, v[MOOG_AT_X] + R[4], v[MOOG_AT_Y] + R[5]);
       int hit = 0; /* every pair is evaluated (no short-circuit), sprite_generators.py:69-74 */
@@ -1808,6 +1817,10 @@ static void copy_slot(env_t *e, int dst, int src) {
   for (int f = 0; f < MOOG_DYN_FIELDS; ++f) DYN(e, f, dst) = DYN(e, f, src);
   for (int f = 0; f < MOOG_STAT_FIELDS; ++f) STAT(e, f, dst) = STAT(e, f, src);
   for (int f = 0; f < MOOG_META_FIELDS; ++f) META(e, f, dst) = META(e, f, src);
+  for (int m = 0; m < e->hdr[MOOG_H_N_META]; ++m) { /* the sprite's metadata columns travel with it */
+    double *col = e->envf + e->hdr[MOOG_H_META_OFF] + m * e->S;
+    col[dst] = col[src];
+  }
   memcpy(e->vtx + 2 * (size_t)e->voff[dst], e->vtx + 2 * (size_t)e->voff[src],
          sizeof(double) * 2 * META(e, MOOG_M_NV, src));
 }

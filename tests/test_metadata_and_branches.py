@@ -1,0 +1,207 @@
+"""Numeric `sprite.metadata[...]` on the device path and config callables that branch on traced
+values (`if` / `elif` / `else`): /root/reference/moog_demos/example_configs/red_green.py:144-176
+(`agent.metadata = {'true_contact_color': ...}` read by the ContactReward's reward_fn) and
+bounce_box_contact_prediction.py:94-110.  The reference trajectories are the `red_green` and
+`predict_zoo` goldens (tests/util.SCENES); here: every branch, the lowering itself, metadata that
+moves with its sprite, and the host-side `Physics.step` of the state initializers."""
+import collections
+
+import numpy as np
+import pytest
+
+from tests import util
+
+
+def _answer(agent, box):
+    said_right = box.x > 0.5
+    if agent.metadata['goal'] == said_right:
+        return 1.
+    elif agent.metadata['when'] > 30:
+        return -0.5
+    else:
+        return -1.
+
+
+def _config(reward_fn, metadata, rules=()):
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, physics as physics_lib, sprite, tasks
+
+    def state_initializer(md=None):
+        boxes = [sprite.Sprite(x=0.4, y=0.5, shape='square', scale=0.1, c0=1.),
+                 sprite.Sprite(x=0.6, y=0.5, shape='square', scale=0.1, c0=2.)]
+        agent = sprite.Sprite(x=0.5, y=0.5, shape='square', scale=0.15)      # touches both boxes
+        agent.metadata = dict(md if md is not None else metadata[0])
+        extra = [sprite.Sprite(x=0.1 + 0.2 * k, y=0.1, shape='triangle', scale=0.05, metadata={'goal': 10 + k, 'when': k})
+                 for k in range(4)]
+        return collections.OrderedDict([('boxes', boxes), ('extra', extra), ('agent', [agent])])
+
+    cfg = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(tasks.ContactReward(reward_fn=reward_fn, layers_0='agent', layers_1='boxes'),
+                                        timeout_steps=100),
+               action_space=action_spaces.Grid(scaling_factor=0.01, action_layers='agent'), observers={}, game_rules=rules)
+    return cfg, [state_initializer(md) for md in metadata]
+
+
+def test_reward_branches_on_metadata_match_python():
+    """The lowered reward (selects over both sides of every `if`) against the Python function itself
+    called on the host sprites, for every combination of the metadata the branches read."""
+    from moog_b200 import compiler, lambdas
+    from oracle.oracle import Oracle
+    metadata = [{'goal': g, 'when': w} for g in (0, 1) for w in (5, 31, 60)]
+    cfg, states = _config(_answer, metadata)
+    prog = compiler.compile_config(cfg, states)
+    assert prog.meta_keys == ['goal', 'when'] and prog.header[compiler.H_N_META] == 2
+    assert any(op == lambdas.X_SELECT for op, _, _ in prog.expr)
+    arrays = compiler.pack_states(prog, states)
+    orc = Oracle(prog, arrays)
+    orc.post_reset()
+    reward, _ = orc.step(np.full((len(states), 1), 4.0))
+    want = [_answer(st['agent'][0], st['boxes'][-1]) for st in states]      # contact_reward.py:88-95: the last touching pair's reward
+    assert reward.tolist() == want and len(set(want)) >= 3
+    # a sprite without the key: NaN in the column (the reference raises KeyError there)
+    S = prog.n_slots
+    col = arrays['envf'][0, prog.meta_off:prog.meta_off + 2 * S].reshape(2, S)
+    assert np.isnan(col[:, prog.layer_off[0]:prog.layer_off[0] + 2]).all()
+    assert col[0, prog.layer_off[1]:prog.layer_off[1] + 4].tolist() == [10, 11, 12, 13]
+
+
+def test_metadata_moves_with_its_sprite():
+    """VanishByFilter pops the second `extra` sprite (vanish.py:31-39): the sprites behind it move down
+    one slot and their metadata columns with them (read back through a reward that uses them)."""
+    import moog_b200  # noqa: F401
+    from moog import game_rules, tasks
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+    cfg, states = _config(_answer, [{'goal': 1, 'when': 2}],
+                          rules=(game_rules.VanishByFilter('extra', lambda s: s.metadata['goal'] == 11),))
+    cfg['task'] = tasks.CompositeTask(
+        tasks.ContactReward(reward_fn=lambda a, e: e.metadata['goal'] + 100 * e.metadata['when'], layers_0='extra',
+                            layers_1='extra', condition=lambda a, e: a.x < e.x), timeout_steps=100)
+    prog = compiler.compile_config(cfg, states)
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    orc.post_reset()                       # the rules pass of reset() pops the sprite with goal == 11
+    S, lo = prog.n_slots, prog.layer_off[1]
+    assert orc.cnt[0, 1] == 3
+    col = orc.envf[0, prog.meta_off:prog.meta_off + 2 * S].reshape(2, S)
+    assert col[0, lo:lo + 3].tolist() == [10, 12, 13] and col[1, lo:lo + 3].tolist() == [0, 2, 3]
+
+
+def test_branch_lowering_forms():
+    """if / elif / else with returns, a conditional expression, nested ifs and a branch on an `and`;
+    callables with effects (modifiers) may not branch on traced values."""
+    from moog_b200 import lambdas
+
+    def nested(a, b):
+        if a.x > 0.5:
+            if b.y > 0.5:
+                return 1.
+            return 2.
+        return 3. if b.c0 > a.c0 else b.mass
+
+    def both(a, b):
+        if a.x > 0.5 and b.x > 0.5:
+            return a.scale
+        return -1.
+
+    for fn in (nested, both):
+        const, code = lambdas.pair_reward(fn)
+        assert const == 0.0 and any(op == lambdas.X_SELECT for op, _, _ in code)
+
+    def modifier(s):
+        if s.x > 0.5:
+            s.c0 = 1.
+    with pytest.raises(lambdas.LoweringError):
+        lambdas.compile_modifier(modifier)
+
+
+@pytest.mark.gpu
+def test_host_physics_step_predicts_what_the_device_then_does():
+    """predict_zoo through the public API: the initializer rolls the puck forward with
+    `physics.step(state)` on the host (a batch of one env through the CUDA physics kernel) and stores the
+    goal it will reach and when in `agent.metadata`; the batched environment then steps the same initial
+    states: the puck must reach THAT goal at THAT step, and the metadata-branching reward must pay what
+    the Python function says."""
+    import torch
+    import moog_b200  # noqa: F401
+    from moog_b200.batched_env import BatchedEnvironment
+    from moog_b200.configs import predict_zoo
+    cfg = predict_zoo.get_config()
+    np.random.seed(7)
+    states = [cfg['state_initializer']() for _ in range(6)]
+    predicted = [(st['agent'][0].metadata['goal'], st['agent'][0].metadata['when']) for st in states]
+    assert all(predict_zoo.STEP_RANGE[0] <= w < predict_zoo.STEP_RANGE[1] for _, w in predicted)
+    N = len(states)
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=1, initial_states=states)
+    prog, eng = env.program, env.engine
+    eng.state.upload({k: v for k, v in moog_b200.compiler.pack_states(prog, states).items() if k in util.STATE_KEYS})
+    eng.post_reset()
+    env._started = True
+    puck, goals = prog.layer_off[2], prog.layer_off[1]
+    stopped_at = [None] * N
+    for t in range(predict_zoo.STEP_RANGE[1] + 2):
+        env.step(torch.full((N, 1), 4.0, dtype=torch.float64))
+        touch = eng.overlap_pairs('puck', 'goals').cpu().numpy()[:, 0, :]
+        for e in range(N):
+            if stopped_at[e] is None and touch[e].any():
+                stopped_at[e] = (int(np.argmax(touch[e])), t + 1)
+    assert stopped_at == predicted, (stopped_at, predicted)
+    st = eng.state.download()
+    assert (st['dyn'][:, 2:4, puck] == 0).all(), 'the rule stopped every puck on its goal'
+    # the agents answer: env e walks left when e is even, right when odd; rewards per the Python function
+    paid = np.zeros(N)
+    for t in range(12):
+        act = torch.tensor([[0.0] if e % 2 == 0 else [1.0] for e in range(N)], dtype=torch.float64)
+        ts = env.step(act)
+        r = ts.reward.cpu().numpy()
+        paid += np.where(np.isnan(r), 0.0, r)
+    for e, (goal, when) in enumerate(predicted):
+        said_right = e % 2 == 1
+        want = 1. if goal == said_right else (-0.5 if when > 30 else -1.)
+        assert paid[e] != 0 and np.sign(paid[e]) == np.sign(want) and abs(paid[e] / want - round(paid[e] / want)) < 1e-9, (e, paid[e], want)
+
+
+@pytest.mark.reference
+def test_shipped_red_green_compiles_unchanged(monkeypatch):
+    """Build container only: moog_demos/example_configs/red_green.py as shipped, on this repo's `moog`
+    package -- its custom RadialVelocity distribution, the recursive initializer that rolls
+    `physics.step(state)` forward (served here by the CPU oracle as a TEST stand-in for the CUDA call of
+    moog_b200/host_physics.py, which has its own GPU test), `agent.metadata` and the branching reward --
+    compiles and runs; the metadata column holds what the initializer predicted."""
+    import importlib
+    import sys
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler, host_physics
+    from oracle.oracle import Oracle
+
+    def _oracle_step(physics, state):
+        from moog import action_spaces, tasks
+        cfg = dict(physics=physics, task=tasks.CompositeTask(), action_space=action_spaces.Grid(action_layers=()),
+                   observers={}, game_rules=())
+        prog = compiler.compile_config(cfg, [state])
+        orc = Oracle(prog, compiler.pack_states(prog, [state]))
+        orc.physics_step()
+        for l, name in enumerate(prog.layer_names):
+            for k, sp in enumerate(state[name]):
+                s = prog.layer_off[l] + k
+                sp.position = np.array(orc.dyn[0, 0:2, s])
+                sp.velocity = np.array(orc.dyn[0, 2:4, s])
+
+    monkeypatch.setattr(host_physics, 'step', _oracle_step)
+    monkeypatch.syspath_prepend('/root/reference')
+    for name in [m for m in sys.modules if m.startswith('moog_demos')]:
+        monkeypatch.delitem(sys.modules, name)
+    red_green = importlib.import_module('moog_demos.example_configs.red_green')
+    np.random.seed(3)
+    cfg = red_green.get_config(1)
+    states = [cfg['state_initializer']() for _ in range(2)]
+    prog = compiler.compile_config(cfg, states)
+    assert prog.meta_keys == ['true_contact_color']
+    arrays = compiler.pack_states(prog, states)
+    agent = prog.layer_off[prog.layer_index('agent')]
+    col = arrays['envf'][:, prog.meta_off + agent]
+    assert col.tolist() == [float(st['agent'][0].metadata['true_contact_color']) for st in states]
+    orc = Oracle(prog, arrays)
+    orc.post_reset()
+    for _ in range(20):
+        orc.step(np.full((2, 1), 4.0))
+    assert (orc.envi[:, 2] == 0).all()
