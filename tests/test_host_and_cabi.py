@@ -341,17 +341,24 @@ def test_reset_sampler_lowering():
 
 def test_reward_function_lowering():
     """constant rewards stay constants; functions of the two sprites become expressions;
-    anything else (metadata, Python branches on sprite values) is refused."""
+    Python branches on sprite values become selects, numeric metadata becomes columns."""
     import moog_b200  # noqa: F401
     from moog_b200 import lambdas
     assert lambdas.pair_reward(-5) == (-5.0, None)
     assert lambdas.pair_reward(lambda a, b: 1.5) == (1.5, None)
     const, code = lambdas.pair_reward(lambda a, b: -2. * b.scale)
     assert const == 0.0 and [c[0] for c in code] == [lambdas.X_CONST, lambdas.X_ATTR1, lambdas.X_MUL]
-    with pytest.raises(lambdas.LoweringError):
-        lambdas.pair_reward(lambda a, b: 1. if b.c0 < 128 else -1.)
+    # a Python branch on a sprite value: both sides are traced and folded into a select
+    const, code = lambdas.pair_reward(lambda a, b: 1. if b.c0 < 128 else -1.)
+    assert const == 0.0 and [c[0] for c in code] == [lambdas.X_ATTR1, lambdas.X_CONST, lambdas.X_LT, lambdas.X_CONST,
+                                                      lambdas.X_CONST, lambdas.X_SELECT]
+    # metadata is only readable while a program is being compiled (its keys become columns of the record)
     with pytest.raises(lambdas.LoweringError):
         lambdas.pair_reward(lambda a, b: a.metadata['true_contact_color'])
+    keys = []
+    with lambdas.metadata_columns(keys):
+        const, code = lambdas.pair_reward(lambda a, b: a.metadata['true_contact_color'])
+    assert keys == ['true_contact_color'] and code == [(lambdas.X_ATTR0, lambdas.AT_META0, 0.0)]
 
 
 _VANISH_RANGE = [-1.2, 2.2]
@@ -409,8 +416,15 @@ def test_vector_valued_and_boolean_lambdas_lower_to_expressions():
     assert attrs == dict(x=0.25, y=0.75)
     code = L.compile_sprite_predicate(lambda s: s.c2 > 0.6 and not s.mass == 1)
     assert run(code, dict(c2=0.7, mass=2.)) == 1.0 and run(code, dict(c2=0.7, mass=1.)) == 0.0
+    # a Python branch on a sprite value: every path is traced, the results folded into a select
+    code = L.compile_sprite_predicate(lambda s: 1. if s.c0 < 128 else -1.)
+    assert L.X_SELECT in [op for op, _, _ in code]
+    # ... but not in a callable with effects
+    def _branching_modifier(s):
+        if s.c0 < 128:
+            s.c0 = 255
     with pytest.raises(L.LoweringError):
-        L.compile_sprite_predicate(lambda s: 1. if s.c0 < 128 else -1.)   # a Python branch on a sprite value
+        L.compile_modifier(_branching_modifier)
 
 
 def test_bench_reference_arm_prints_the_contract_line():
