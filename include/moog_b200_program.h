@@ -190,7 +190,8 @@ enum {
   /* tasks: i[5] = envf slot of the countdown */
   MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps; p2 > 0: the
                                  reward is the expression p2 - 1 of (sprite_0, sprite_1) instead of p0  contact_reward.py:70-102 */
-  MOOG_T_RESET,               /* i0 condition op index; p0 steps_after p1 reward   reset.py:48-61  */
+  MOOG_T_RESET,               /* i0 condition op index; p0 steps_after p1 reward; i1 > 0: the reward is the value of
+                                 condition op i1 - 1 (a reward_fn that reads the state)   reset.py:48-61  */
   MOOG_T_STAY_ALIVE,          /* p0 period p1 value                          stay_alive.py:22-32   */
   MOOG_T_TIMEOUT,             /* p0 timeout_steps                            composite_task.py:35  */
 
@@ -223,8 +224,17 @@ enum {
   MOOG_SC_NOT,             /* i0 operand condition op: python `not`             */
   MOOG_SC_FIRST,           /* i0,i1 layer list; i2 sprite expr evaluated on the FIRST sprite of the list
                               (`state[layer][0]`); 0 when the list is empty      */
-  MOOG_SC_BERNOULLI        /* `np.random.binomial(1, p)` as a condition (first_person_predators_prey.py:181,189):
+  MOOG_SC_BERNOULLI,       /* `np.random.binomial(1, p)` as a condition (first_person_predators_prey.py:181,189):
                               1 when the uniform in rule-noise column i0 is below p0 */
+  MOOG_SC_TREE             /* a state-level callable that picks single sprites (`state['agent'][0]`), reads their
+                              attributes / metadata, tests overlaps between them and branches
+                              (bounce_box_contact_prediction.py:94-110), as a decision tree walked lazily from node
+                              0 -- the overlap tests made are the ones Python would make, in its order.
+                              i0 ipool start, i1 number of nodes of 8 ints:
+                                kind (0 leaf: value = expr; 1 test expr != 0; 2 test overlaps(sprite 0, sprite 1)),
+                                expr, layer and index of sprite 0, layer and index of sprite 1 (layer -1: unused),
+                                next node if true, next node if false.
+                              An index beyond the layer's count is the reference's IndexError: MOOG_ERR_BAD_INDEX */
 };
 
 /* op flags */
@@ -260,6 +270,7 @@ enum {
 #define MOOG_Z_SHAPE_ATTR 13
 enum { MOOG_ZK_CONST = 0, MOOG_ZK_UNIFORM32 = 1, MOOG_ZK_DISCRETE = 2 };
 #define MOOG_ERR_PORTAL_ODD      64u /* portal.py:49-52 ValueError: odd number of portals */
+#define MOOG_ERR_BAD_INDEX      128u /* `state[layer][i]` with i >= len(state[layer]): the reference's IndexError */
 #define MOOG_ERR_RESET_REJECTED  32u /* sprite_generators.py:92-98 RecursionError (no room for a sprite) */
 
 /* Maze record in envf (maze_lib/maze.py:20-35, Maze.from_state :38-84, evaluated by the host when

@@ -43,6 +43,7 @@ _ERR_TEXT = {
     32: 'RecursionError: max_recursion_depth exceeded trying to initialize a non-overlapping sprite '
         '(sprite_generators.py:92-98) / ValueError: maximum number of tries exceeded (distributions.py:341-349)',
     64: 'ValueError: There must be an even number of portals (portal.py:49-52)',
+    128: 'IndexError: a condition / reward function indexed state[layer][i] beyond the sprites the layer holds',
 }
 
 _STATE_DTYPES = dict(dyn=torch.float64, stat=torch.float64, meta=torch.int32,

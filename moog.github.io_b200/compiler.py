@@ -65,7 +65,7 @@ R_PORTAL, R_CHANGE_LAYER, R_CREATE_SPRITES = 71, 72, 73
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
-    SC_BINARY, SC_NOT, SC_FIRST, SC_BERNOULLI = 160, 161, 162, 163, 164, 165, 166, 167, 168, 169
+    SC_BINARY, SC_NOT, SC_FIRST, SC_BERNOULLI, SC_TREE = 160, 161, 162, 163, 164, 165, 166, 167, 168, 169, 170
 Z_GENERATE = 192
 Z_N_ATTRS, Z_SHAPE_ATTR = 14, 13
 ZK_CONST, ZK_UNIFORM32, ZK_DISCRETE = 0, 1, 2
@@ -412,10 +412,10 @@ def _compile_task(prog, task, out):
             p=(float(reward), float(task._reset_steps_after_contact),
                float(prog.add_expr(reward_code) + 1) if reward_code is not None else 0.0)))
     elif k == 'Reset':
-        reward = lambdas.constant_state_reward(task._reward_fn)
+        reward, reward_op = lambdas.state_reward(task._reward_fn, prog)
         out.append(dict(
             kind=T_RESET, cond=task._condition,
-            i=[0, 0, 0, 0, 0, prog.alloc_envf(1)],
+            i=[0, 0 if reward_op is None else reward_op + 1, 0, 0, 0, prog.alloc_envf(1)],
             p=(float(task._steps_after_condition), float(reward))))
     else:
         raise CompileError('unsupported task {}'.format(k))

@@ -140,7 +140,7 @@ int moog_program_validate(const void *blob, size_t nbytes) {
     return true;
   };
   auto expr_ok = [&](int x) { return x == -1 || (x >= 0 && x < NX); };
-  auto cond_ok = [&](int o) { return o >= 0 && o < NO && pv.ops[o].kind >= MOOG_SC_ALL && pv.ops[o].kind <= MOOG_SC_BERNOULLI; };
+  auto cond_ok = [&](int o) { return o >= 0 && o < NO && pv.ops[o].kind >= MOOG_SC_ALL && pv.ops[o].kind <= MOOG_SC_TREE; };
   auto envf_ok = [&](int f, int n) { return f >= 0 && (long long)f + n <= NF; };
   auto table_ok = [&](int t) {  // sampler table: MOOG_Z_N_ATTRS leaves (kind, dpool index, n) + the extension count
     if (t < 0 || (long long)t + 3 * MOOG_Z_N_ATTRS + 1 > NI) return false;
@@ -185,7 +185,7 @@ int moog_program_validate(const void *blob, size_t nbytes) {
         ok = list_ok(op.i[0], op.i[1], L) && list_ok(op.i[2], op.i[3], L) && expr_ok(op.i[4]) && envf_ok(op.i[5], 1) &&
              (!(op.p[2] > 0) || expr_ok((int)op.p[2] - 1));
         break;
-      case MOOG_T_RESET: ok = cond_ok(op.i[0]) && envf_ok(op.i[5], 1); break;
+      case MOOG_T_RESET: ok = cond_ok(op.i[0]) && envf_ok(op.i[5], 1) && (op.i[1] == 0 || cond_ok(op.i[1] - 1)); break;
       case MOOG_T_STAY_ALIVE: ok = op.p[0] >= 1; break;
       case MOOG_T_TIMEOUT: break;
       case MOOG_A_JOYSTICK: case MOOG_A_GRID: case MOOG_A_SET_POSITION:
@@ -206,6 +206,16 @@ int moog_program_validate(const void *blob, size_t nbytes) {
       case MOOG_SC_BINARY: ok = cond_ok(op.i[0]) && cond_ok(op.i[1]); break;
       case MOOG_SC_NOT: ok = cond_ok(op.i[0]); break;
       case MOOG_SC_BERNOULLI: ok = op.i[0] >= 0 && op.i[0] < hdr[MOOG_H_RULE_NOISE_DIM]; break;
+      case MOOG_SC_TREE:
+        ok = op.i[1] >= 1 && op.i[0] >= 0 && (long long)op.i[0] + 8LL * op.i[1] <= NI;
+        for (int j = 0; ok && j < op.i[1]; ++j) {
+          const int32_t *nd = pv.ipool + op.i[0] + 8 * j;
+          ok = nd[0] >= 0 && nd[0] <= 2 && (nd[0] == 2 || (nd[1] >= 0 && nd[1] < NX)) && (nd[2] == -1 || layer_ok(nd[2])) &&
+               (nd[4] == -1 || layer_ok(nd[4])) && nd[3] >= 0 && nd[5] >= 0 &&
+               (nd[0] == 0 || (nd[6] >= 0 && nd[6] < op.i[1] && nd[7] >= 0 && nd[7] < op.i[1])) &&
+               (nd[0] != 2 || (layer_ok(nd[2]) && layer_ok(nd[4])));
+        }
+        break;
       default: ok = false; break;  // an op kind no kernel knows
     }
     if (!ok) return MOOG_E_INVAL;

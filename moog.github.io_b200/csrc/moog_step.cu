@@ -2540,6 +2540,30 @@ __device__ __noinline__ double eval_condition_leaf(const Env &, int op_index) {
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
     case MOOG_SC_BERNOULLI: return rule_noise_at(e, op->i[0]) < op->p[0];  // np.random.binomial(1, p)
+    case MOOG_SC_TREE: {  // lambdas.state_tree: walked lazily, so the overlap calls are Python's, in its order
+      const int32_t *nodes = e.ipool + op->i[0];
+      int j = 0;
+      for (int guard = 0; guard <= op->i[1]; ++guard) {
+        const int32_t *nd = nodes + 8 * j;
+        int sl[2] = {0, 0};
+        for (int q = 0; q < 2; ++q) {
+          const int l = nd[2 + 2 * q], k = nd[3 + 2 * q];
+          if (l < 0) continue;
+          if (k >= e.cnt[l]) {  // IndexError in the reference
+            const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_BAD_INDEX;
+            wsync();
+            puti(e, &e.envi[MOOG_EI_ERR], err);
+            wsync();
+            return 0;
+          }
+          sl[q] = LOFF(e, l) + k;
+        }
+        if (nd[0] == 0) return eval_expr(e, nd[1], sl[0], sl[1]);
+        const bool yes = nd[0] == 2 ? overlaps(e, sl[0], sl[1]) : eval_expr(e, nd[1], sl[0], sl[1]) != 0;
+        j = yes ? nd[6] : nd[7];
+      }
+      return 0;
+    }
     case MOOG_SC_ALL:
     case MOOG_SC_ANY:
     case MOOG_SC_COUNT: {
@@ -3247,7 +3271,7 @@ __device__ __noinline__ void tasks_reward(const Env &, int step_count, double *r
         double r = 0.;
         double cd = e.envf[op->i[5]];
         if (cd == INFINITY && eval_condition(e, op->i[0]) != 0) {
-          r = op->p[1];
+          r = op->i[1] > 0 ? eval_condition(e, op->i[1] - 1) : op->p[1];  // reward_fn(state), only now
           cd = op->p[0];
         }
         cd -= 1;

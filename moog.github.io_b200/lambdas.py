@@ -143,6 +143,28 @@ def _select(cond, a, b):
     return Sym(cond.code + a.code + b.code + [(X_SELECT, 0, 0.0)])
 
 
+def _explore_tree(fn, args, prefix=(), budget=None):
+    """Like _explore, but the result is the decision TREE itself -- ('test', condition, subtree if true,
+    subtree if false) / ('leaf', value) -- for callables whose tests have to run lazily and in order
+    (overlap tests: which ones the reference makes depends on the outcome of the earlier ones)."""
+    budget = [_MAX_PATHS] if budget is None else budget
+    budget[0] -= 1
+    if budget[0] < 0:
+        raise LoweringError('the callable branches along more than {} paths'.format(_MAX_PATHS))
+    previous, _PATH[0] = _PATH[0], _Path(prefix)
+    path = _PATH[0]
+    try:
+        value = fn(*args)
+    finally:
+        _PATH[0] = previous
+    node = ('leaf', value)
+    base = len(prefix)
+    for j in range(len(path.new) - 1, -1, -1):
+        other = _explore_tree(fn, args, tuple(path.forced[:base + j]) + (False,), budget)
+        node = ('test', path.new[j], node, other)
+    return node
+
+
 def _explore(fn, args, prefix=(), budget=None):
     """Value of fn(*args) over every path its data-dependent `if`s can take, folded into selects."""
     budget = [_MAX_PATHS] if budget is None else budget
@@ -177,6 +199,31 @@ def metadata_columns(keys):
         _META_KEYS[0] = previous
 
 
+def _attr_read(which, attr):
+    """Code entry reading attribute `attr` of sprite 0 / sprite 1 of a pair callable, or -- `which` =
+    ('bound', k) -- of the k-th sprite a state-level callable picked out of the state (`state[layer][i]`):
+    the binding travels in the high bits of the argument until _bind_pair assigns it to sprite 0 or 1."""
+    if isinstance(which, tuple):
+        return (X_ATTR0, attr | ((which[1] + 1) << 8), 0.0)
+    return (X_ATTR0 if which == 0 else X_ATTR1, attr, 0.0)
+
+
+class SymOverlap(object):
+    """`a.overlaps_sprite(b)` between two sprites picked out of the state: only usable as a test."""
+
+    def __init__(self, a, b):
+        if not (isinstance(a, SymSprite) and isinstance(b, SymSprite) and isinstance(a._which, tuple)
+                and isinstance(b._which, tuple)):
+            raise LoweringError('overlaps_sprite is lowered between two sprites taken from the state only')
+        self.pair = (a._which[1], b._which[1])
+
+    def __bool__(self):
+        path = _PATH[0]
+        if path is None:
+            raise LoweringError('overlaps_sprite can only be branched on')
+        return path.decide(self)
+
+
 class SymMetadata(object):
     """`sprite.metadata` while tracing: item reads become reads of a metadata column."""
 
@@ -193,7 +240,7 @@ class SymMetadata(object):
             if len(keys) >= MAX_META_KEYS:
                 raise LoweringError('at most {} metadata keys are carried on the device'.format(MAX_META_KEYS))
             keys.append(key)
-        return Sym([(X_ATTR0 if self._which == 0 else X_ATTR1, AT_META0 + keys.index(key), 0.0)])
+        return Sym([_attr_read(self._which, AT_META0 + keys.index(key))])
 
     def get(self, key, default=None):
         raise LoweringError('sprite.metadata.get() is not lowered: read the key directly')
@@ -209,8 +256,9 @@ class SymSprite(object):
 
     def __getattr__(self, name):
         if name in ATTRS:
-            op = X_ATTR0 if self._which == 0 else X_ATTR1
-            return Sym([(op, ATTRS.index(name), 0.0)])
+            return Sym([_attr_read(self._which, ATTRS.index(name))])
+        if name == 'overlaps_sprite' and isinstance(self._which, tuple):
+            return lambda other: SymOverlap(self, other)
         if name == 'position':
             return SymVec([self.x, self.y])
         if name == 'velocity':
@@ -351,6 +399,110 @@ class SymState(object):
 
     def __getitem__(self, name):
         return _SymLayer(self, name)
+
+
+class _BoundLayer(object):
+    def __init__(self, owner, name):
+        self._owner, self._name = owner, name
+
+    def __getitem__(self, index):
+        if not isinstance(index, int) or index < 0:
+            raise LoweringError('state[{!r}][...] must be a fixed non-negative index in a state-level callable'.format(self._name))
+        key = (self._name, index)
+        if key not in self._owner.bound:
+            self._owner.bound.append(key)
+        return SymSprite(('bound', self._owner.bound.index(key)))
+
+    def __iter__(self):
+        raise LoweringError('iterating over state[{!r}] is not lowered here'.format(self._name))
+
+    def __len__(self):
+        raise LoweringError('len(state[{!r}]) is not lowered here'.format(self._name))
+
+
+class BoundState(object):
+    """The environment state for a state-level callable that picks single sprites (`state['agent'][0]`),
+    reads their attributes / metadata and tests overlaps between them (bounce_box_contact_prediction.py:94-103)."""
+
+    def __init__(self):
+        self.bound = []       # (layer name, index) of every sprite picked, in first-use order
+
+    def __getitem__(self, name):
+        return _BoundLayer(self, name)
+
+
+def _bind_pair(code, what):
+    """Expression over bound sprites -> (code over sprite 0 / sprite 1, [bound ids of sprite 0, sprite 1])."""
+    ids = []
+    for op, arg, _ in code:
+        if op in (X_ATTR0, X_ATTR1, X_STORE) and arg >> 8:
+            k = (arg >> 8) - 1
+            if k not in ids:
+                ids.append(k)
+    if len(ids) > 2:
+        raise LoweringError('{} reads more than two sprites of the state in one expression'.format(what))
+    out = []
+    for op, arg, c in code:
+        if op in (X_ATTR0, X_ATTR1) and arg >> 8:
+            out.append((X_ATTR0 if ids.index((arg >> 8) - 1) == 0 else X_ATTR1, arg & 0xff, c))
+        else:
+            out.append((op, arg, c))
+    return out, ids
+
+
+def state_tree(fn, prog, what):
+    """A state-level callable `fn(state)` made of single-sprite picks, attribute / metadata reads, overlap
+    tests and `if`s -> index of a MOOG_SC_TREE op: a decision tree evaluated lazily, test by test, in the
+    order Python would make them (so the overlap calls are the reference's, call for call)."""
+    state = BoundState()
+    call = fn
+    try:
+        call = _rewritten(fn)
+    except Exception:  # pylint: disable=broad-except
+        call = fn
+    with no_randomness(what):
+        try:
+            tree = _explore_tree(call, (state,))
+        except LoweringError:
+            raise
+        except Exception as exc:  # pylint: disable=broad-except
+            raise LoweringError('{} cannot be lowered to a decision tree over the state ({}: {})'.format(
+                what, type(exc).__name__, exc))
+    nodes = []
+
+    def sprite_ref(k):
+        if k is None:
+            return (-1, 0)
+        layer, index = state.bound[k]
+        return (prog.layer_index(layer), index)
+
+    def emit(node):
+        me = len(nodes)
+        nodes.append(None)
+        if node[0] == 'leaf':
+            value = node[1]
+            if isinstance(value, SymOverlap):
+                raise LoweringError('{} returns an overlap test; branch on it instead'.format(what))
+            code, ids = _bind_pair(Sym.lift(value).code, what)
+            ids = ids + [None] * (2 - len(ids))
+            nodes[me] = (0, prog.add_expr(code)) + sprite_ref(ids[0]) + sprite_ref(ids[1]) + (0, 0)
+            return me
+        cond = node[1]
+        if isinstance(cond, SymOverlap):
+            head = (2, -1) + sprite_ref(cond.pair[0]) + sprite_ref(cond.pair[1])
+        else:
+            code, ids = _bind_pair(cond.code, what)
+            ids = ids + [None] * (2 - len(ids))
+            head = (1, prog.add_expr(code)) + sprite_ref(ids[0]) + sprite_ref(ids[1])
+        yes = emit(node[2])
+        no = emit(node[3])
+        nodes[me] = head + (yes, no)
+        return me
+
+    emit(tree)
+    flat = [v for nd in nodes for v in nd]
+    start = prog.add_ints(flat)
+    return prog.emit(170, 0, (start, len(nodes)))   # MOOG_SC_TREE
 
 
 def _n_params(fn):
@@ -964,7 +1116,27 @@ def compile_state_condition(cond, prog):
                     cond.__name__))
         body = stmts[0].value
     low = _StateLowering(cond, prog, node)
-    kind, value = low.lower(body)
+    n_ops, n_expr, n_ipool = len(prog.ops), len(prog.expr), len(prog.ipool)
+    try:
+        kind, value = low.lower(body)
+    except LoweringError as first:
+        # not one of the aggregate forms: a callable that picks single sprites and branches on them
+        del prog.ops[n_ops:], prog.expr[n_expr:], prog.ipool[n_ipool:]
+        try:
+            return state_tree(cond, prog, 'state condition {}'.format(getattr(cond, '__name__', cond)))
+        except LoweringError as second:
+            raise LoweringError('{}; as a decision tree: {}'.format(first, second))
     if kind == 'const':
         return prog.emit(C.SC_CONST, 0, (), (value,))
     return value
+
+
+def state_reward(reward_fn, prog):
+    """Reset reward_fn (reset.py:41-43, called only when the condition holds) -> (constant, None), or
+    (0.0, index of the MOOG_SC_TREE op that evaluates it)."""
+    try:
+        return constant_state_reward(reward_fn), None
+    except ImpureCallable:
+        raise
+    except LoweringError:
+        return 0.0, state_tree(reward_fn, prog, 'Reset reward_fn')

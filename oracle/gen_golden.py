@@ -96,6 +96,10 @@ SCENES = {
     'red_green': ('moog_demos.example_configs.red_green', 1, 18, 200, 10),
     # this repo's small version of the same pattern: an if / elif / else reward over two metadata keys
     'predict_zoo': ('moog_b200.configs.predict_zoo', None, 19, 69, 6),
+    # a shipped config whose Reset task's condition and reward_fn pick single sprites out of the state, test
+    # overlaps between them and branch on metadata (bounce_box_contact_prediction.py:94-110): a decision tree;
+    # translucent occluder (opacity 128), a TimedRule that removes the screen
+    'bounce_box': ('moog_demos.example_configs.bounce_box_contact_prediction', True, 20, 120, 8),
 }
 
 
@@ -306,6 +310,8 @@ def generate(name, out_dir):
             action = _chase_action(env, t)
         elif name == 'pacman':
             action = _pacman_action(env, t)
+        elif name == 'bounce_box':
+            action = 4 if t < 25 else 0             # wait, then walk into the left response box
         elif name == 'predict_zoo':
             action = 4 if t < 30 else (0 if t < 50 else 1)      # wait, walk into the left box, then back to the right one
         elif name == 'red_green':

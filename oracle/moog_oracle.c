@@ -1754,6 +1754,27 @@ static double eval_condition(env_t *e, int op_index) {
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
     case MOOG_SC_BERNOULLI: return rule_noise_at(e, op->i[0]) < op->p[0]; /* np.random.binomial(1, p) */
+    case MOOG_SC_TREE: { /* lambdas.state_tree: walked lazily, so the overlap calls are Python's, in its order */
+      const int32_t *nodes = e->ipool + op->i[0];
+      int j = 0;
+      for (int guard = 0; guard <= op->i[1]; ++guard) {
+        const int32_t *nd = nodes + 8 * j;
+        int sl[2] = {0, 0};
+        for (int q = 0; q < 2; ++q) {
+          const int l = nd[2 + 2 * q], k = nd[3 + 2 * q];
+          if (l < 0) continue;
+          if (k >= e->cnt[l]) { /* IndexError in the reference */
+            e->envi[MOOG_EI_ERR] |= MOOG_ERR_BAD_INDEX;
+            return 0;
+          }
+          sl[q] = LOFF(e, l) + k;
+        }
+        if (nd[0] == 0) return eval_expr(e, nd[1], sl[0], sl[1]);
+        const int yes = nd[0] == 2 ? overlaps(e, sl[0], sl[1]) : eval_expr(e, nd[1], sl[0], sl[1]) != 0;
+        j = yes ? nd[6] : nd[7];
+      }
+      return 0;
+    }
     case MOOG_SC_ALL:
     case MOOG_SC_ANY:
     case MOOG_SC_COUNT: {
@@ -2127,7 +2148,7 @@ static void tasks_reward(env_t *e, int step_count, double *reward, int *should_r
         double r = 0.;
         double *cd = e->envf + op->i[5];
         if (*cd == INFINITY && eval_condition(e, op->i[0]) != 0) {
-          r = op->p[1];
+          r = op->i[1] > 0 ? eval_condition(e, op->i[1] - 1) : op->p[1]; /* reward_fn(state), only now */
           *cd = op->p[0];
         }
         *cd -= 1;

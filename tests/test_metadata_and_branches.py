@@ -161,12 +161,15 @@ def test_host_physics_step_predicts_what_the_device_then_does():
 
 
 @pytest.mark.reference
-def test_shipped_red_green_compiles_unchanged(monkeypatch):
-    """Build container only: moog_demos/example_configs/red_green.py as shipped, on this repo's `moog`
-    package -- its custom RadialVelocity distribution, the recursive initializer that rolls
-    `physics.step(state)` forward (served here by the CPU oracle as a TEST stand-in for the CUDA call of
-    moog_b200/host_physics.py, which has its own GPU test), `agent.metadata` and the branching reward --
-    compiles and runs; the metadata column holds what the initializer predicted."""
+@pytest.mark.parametrize('module,level,key', [('red_green', 1, 'true_contact_color'),
+                                              ('bounce_box_contact_prediction', False, 'will_contact')])
+def test_shipped_prediction_configs_compile_unchanged(monkeypatch, module, level, key):
+    """Build container only: moog_demos/example_configs/red_green.py and bounce_box_contact_prediction.py
+    as shipped, on this repo's `moog` package -- the custom RadialVelocity distribution, initializers
+    that roll `physics.step(state)` forward (served here by the CPU oracle as a TEST stand-in for the
+    CUDA call of moog_b200/host_physics.py, which has its own GPU test), `agent.metadata`, the
+    branching reward / the decision-tree Reset task -- compile and run; the metadata column holds what
+    the initializer predicted."""
     import importlib
     import sys
     import moog_b200  # noqa: F401
@@ -190,18 +193,73 @@ def test_shipped_red_green_compiles_unchanged(monkeypatch):
     monkeypatch.syspath_prepend('/root/reference')
     for name in [m for m in sys.modules if m.startswith('moog_demos')]:
         monkeypatch.delitem(sys.modules, name)
-    red_green = importlib.import_module('moog_demos.example_configs.red_green')
+    shipped = importlib.import_module('moog_demos.example_configs.' + module)
     np.random.seed(3)
-    cfg = red_green.get_config(1)
+    cfg = shipped.get_config(level)
     states = [cfg['state_initializer']() for _ in range(2)]
     prog = compiler.compile_config(cfg, states)
-    assert prog.meta_keys == ['true_contact_color']
+    assert prog.meta_keys == [key]
     arrays = compiler.pack_states(prog, states)
     agent = prog.layer_off[prog.layer_index('agent')]
     col = arrays['envf'][:, prog.meta_off + agent]
-    assert col.tolist() == [float(st['agent'][0].metadata['true_contact_color']) for st in states]
+    assert col.tolist() == [float(st['agent'][0].metadata[key]) for st in states]
     orc = Oracle(prog, arrays)
     orc.post_reset()
     for _ in range(20):
         orc.step(np.full((2, 1), 4.0))
     assert (orc.envi[:, 2] == 0).all()
+
+
+def _verdict(state):
+    """bounce_box_contact_prediction.py:94-103 in structure: single sprites picked out of the state,
+    overlap tests made lazily, metadata read only on the branch that needs it."""
+    agent = state['agent'][0]
+    if agent.overlaps_sprite(state['boxes'][0]):
+        return -1 if agent.metadata['goal'] else 1
+    elif agent.overlaps_sprite(state['boxes'][1]):
+        return 2 if agent.metadata['goal'] else -2
+    else:
+        return 0
+
+
+def test_state_decision_tree_matches_python_call_for_call():
+    """Reset(condition=lambda state: f(state) != 0, reward_fn=f) with f a branching function over picked
+    sprites: the MOOG_SC_TREE ops pay what Python pays, reset when Python resets, and make exactly the
+    overlap calls Python makes (the second test only when the first one failed; the reward function
+    only when the condition held)."""
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, physics as physics_lib, sprite, tasks
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+
+    def state_initializer(x, goal):
+        boxes = [sprite.Sprite(x=0.3, y=0.5, shape='square', scale=0.1), sprite.Sprite(x=0.7, y=0.5, shape='square', scale=0.1)]
+        agent = sprite.Sprite(x=x, y=0.5, shape='circle', scale=0.08, metadata={'goal': goal})
+        return collections.OrderedDict([('boxes', boxes), ('agent', [agent])])
+
+    cases = [(x, goal) for x in (0.3, 0.5, 0.7) for goal in (False, True)]
+    states = [state_initializer(x, goal) for x, goal in cases]
+    cfg = dict(state_initializer=lambda: state_initializer(0.5, True), physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(tasks.Reset(condition=lambda state: _verdict(state) != 0, reward_fn=_verdict,
+                                                    steps_after_condition=2), timeout_steps=100),
+               action_space=action_spaces.Grid(scaling_factor=0.01, action_layers='agent'), observers={}, game_rules=())
+    prog = compiler.compile_config(cfg, states)
+    assert [o['kind'] for o in prog.ops].count(compiler.SC_TREE) == 2
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    orc.post_reset()
+    reward, step_type = orc.step(np.full((len(states), 1), 4.0))
+    want = [float(_verdict(st)) for st in states]
+    assert reward.tolist() == want == [-0.0 + 1, -1, 0, 0, -2, 2]
+    # overlap calls: left box only (1) when it is hit -- condition + reward function: 2 calls;
+    # right box: 2 tests each time -> 4; nothing hit: the condition alone -> 2
+    assert orc.counters[:, 0].tolist() == [2, 2, 2, 2, 4, 4]
+    for _ in range(2):
+        reward, step_type = orc.step(np.full((len(states), 1), 4.0))
+    assert step_type.tolist() == [2, 2, 1, 1, 2, 2]          # steps_after_condition = 2
+    # an index beyond the layer: the reference's IndexError becomes MOOG_ERR_BAD_INDEX
+    bad = dict(cfg, task=tasks.CompositeTask(tasks.Reset(condition=lambda state: state['boxes'][5].x > 0, steps_after_condition=2)))
+    prog2 = compiler.compile_config(bad, states)
+    orc2 = Oracle(prog2, compiler.pack_states(prog2, states))
+    orc2.post_reset()
+    orc2.step(np.full((len(states), 1), 4.0))
+    assert ((orc2.envi[:, 2] & 128) != 0).all()
