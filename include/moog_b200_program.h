@@ -186,6 +186,11 @@ enum {
                                     (as MOOG_Z_GENERATE), i5 dtype flags; MOOG_FL_DISJOINT / FAIL_GRACEFULLY,
                                     p0 max_recursion_depth.  Drawn on the device (Philox keyed by seed, env,
                                     episode, step) */
+  MOOG_R_TREE,                   /* a user-defined rule class (functional_maze.py:18-67 `Booster`), its `step` traced along
+                                    every path into a decision tree (node layout: MOOG_SC_TREE; kinds 3 = test
+                                    `index < len(layer)`, 4 = run the stores of `expr` then go on; the leaf ends the
+                                    rule): i0 ipool start, i1 nodes; the rule's own numeric attributes live in envf
+                                    [i2, i2 + i3) and are set to dpool[i4 ...] when the rule is reset */
 
   /* tasks: i[5] = envf slot of the countdown */
   MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps; p2 > 0: the
@@ -300,8 +305,10 @@ enum {
                         array (`s.velocity = np.zeros(2)`, sprite.py:639-643): MOOG_SF_VEL32 and the alias id go */
   MOOG_X_STORE_POS,  /* pop y, pop x -> sprite 0 `.position = (x, y)`: one translation of the cached
                         outline (sprite.py:616-633) */
-  MOOG_X_SELECT      /* pop b, pop a, pop c -> (c != 0 ? a : b): an `if` / `else` of a config callable on a
+  MOOG_X_SELECT,     /* pop b, pop a, pop c -> (c != 0 ? a : b): an `if` / `else` of a config callable on a
                         per-sprite value, both sides traced (lambdas._explore) */
+  MOOG_X_ENVF,       /* push envf[arg]: a state variable of a user-defined rule (MOOG_R_TREE) */
+  MOOG_X_STORE_ENVF  /* pop -> envf[arg] */
 };
 
 /* attribute ids for the expression VM (Sprite.FACTOR_NAMES, sprite.py:237-253) */

@@ -61,7 +61,9 @@ F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
 C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED, C_MAZE_PHYSICS = 32, 33, 34, 35
 R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
     R_MODIFY_SPRITES, R_COND_BEGIN, R_TIMED_BEGIN, R_KEEP_NEAR_CENTER = 64, 65, 66, 67, 68, 69, 70
-R_PORTAL, R_CHANGE_LAYER, R_CREATE_SPRITES = 71, 72, 73
+R_PORTAL, R_CHANGE_LAYER, R_CREATE_SPRITES, R_TREE = 71, 72, 73, 74
+# rule classes of the reference that keep Python-side state the tracer must not guess at
+_RULES_OF_THE_REFERENCE_NOT_LOWERED = ('Fixation', 'ModifyMetaState', 'UpdateMetaStateValue', 'Phase', 'PhaseSequence')
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
@@ -575,6 +577,15 @@ def _rule_specs(prog, rule, out, depth=0):
         grid = rule._grid_cell
         out.append(dict(kind=R_KEEP_NEAR_CENTER, i=(prog.layer_index(rule._agent_layer), ls, ln),
                         p=(float(grid[0]), float(grid[1]))))
+    elif callable(getattr(type(rule), 'step', None)) and k not in _RULES_OF_THE_REFERENCE_NOT_LOWERED:
+        # a rule class of the config's own (functional_maze.py:18-67): its step() is traced path by path
+        try:
+            start, count, base, initial = lambdas.trace_rule(rule, prog)
+        except lambdas.LoweringError as exc:
+            raise CompileError('game rule {} is not on the accelerated path and cannot be traced: {}'.format(k, exc))
+        first = len(prog.dpool)
+        prog.dpool.extend(float(v) for v in initial)
+        out.append(dict(kind=R_TREE, i=(start, count, base, len(initial), first)))
     else:
         raise CompileError(
             'game rule {} is not on the accelerated path'.format(k))

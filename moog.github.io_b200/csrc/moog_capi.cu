@@ -123,7 +123,8 @@ int moog_program_validate(const void *blob, size_t nbytes) {
   if (NX > 0 && pv.expr[NX - 1].op != MOOG_X_END) return MOOG_E_INVAL;
   for (int x = 0; x < NX; ++x) {
     const moog_ex &e = pv.expr[x];
-    if (e.op < 0 || e.op > MOOG_X_SELECT) return MOOG_E_INVAL;
+    if (e.op < 0 || e.op > MOOG_X_STORE_ENVF) return MOOG_E_INVAL;
+    if ((e.op == MOOG_X_ENVF || e.op == MOOG_X_STORE_ENVF) && (e.arg < 0 || e.arg >= NF)) return MOOG_E_INVAL;
     if ((e.op == MOOG_X_ATTR0 || e.op == MOOG_X_ATTR1 || e.op == MOOG_X_STORE) &&
         !((e.arg >= 0 && e.arg <= MOOG_AT_OPACITY) || (e.arg >= MOOG_AT_META0 && e.arg < MOOG_AT_META0 + hdr[MOOG_H_N_META])))
       return MOOG_E_INVAL;
@@ -150,6 +151,19 @@ int moog_program_validate(const void *blob, size_t nbytes) {
         return false;
     }
     return pv.ipool[t + 3 * MOOG_Z_N_ATTRS] >= 0;
+  };
+  auto tree_ok = [&](int start, int n, bool rule) {  // decision tree nodes of 8 ints (MOOG_SC_TREE / MOOG_R_TREE)
+    if (n < 1 || start < 0 || (long long)start + 8LL * n > NI) return false;
+    for (int j = 0; j < n; ++j) {
+      const int32_t *nd = pv.ipool + start + 8 * j;
+      const int kind = nd[0];
+      if (kind < 0 || kind > 4 || (!rule && kind == 4)) return false;
+      if ((kind == 1 || kind == 4 || (kind == 0 && !rule)) && !(nd[1] >= 0 && nd[1] < NX)) return false;
+      if (!(nd[2] == -1 || layer_ok(nd[2])) || !(nd[4] == -1 || layer_ok(nd[4])) || nd[3] < 0 || nd[5] < 0) return false;
+      if ((kind == 2 && !(layer_ok(nd[2]) && layer_ok(nd[4]))) || (kind == 3 && !layer_ok(nd[2]))) return false;
+      if (kind != 0 && !(nd[6] > j && nd[6] < n && nd[7] > j && nd[7] < n)) return false;  // forward only: the walk ends
+    }
+    return true;
   };
   for (int o = 0; o < NO; ++o) {
     const moog_op &op = pv.ops[o];
@@ -206,15 +220,10 @@ int moog_program_validate(const void *blob, size_t nbytes) {
       case MOOG_SC_BINARY: ok = cond_ok(op.i[0]) && cond_ok(op.i[1]); break;
       case MOOG_SC_NOT: ok = cond_ok(op.i[0]); break;
       case MOOG_SC_BERNOULLI: ok = op.i[0] >= 0 && op.i[0] < hdr[MOOG_H_RULE_NOISE_DIM]; break;
-      case MOOG_SC_TREE:
-        ok = op.i[1] >= 1 && op.i[0] >= 0 && (long long)op.i[0] + 8LL * op.i[1] <= NI;
-        for (int j = 0; ok && j < op.i[1]; ++j) {
-          const int32_t *nd = pv.ipool + op.i[0] + 8 * j;
-          ok = nd[0] >= 0 && nd[0] <= 2 && (nd[0] == 2 || (nd[1] >= 0 && nd[1] < NX)) && (nd[2] == -1 || layer_ok(nd[2])) &&
-               (nd[4] == -1 || layer_ok(nd[4])) && nd[3] >= 0 && nd[5] >= 0 &&
-               (nd[0] == 0 || (nd[6] >= 0 && nd[6] < op.i[1] && nd[7] >= 0 && nd[7] < op.i[1])) &&
-               (nd[0] != 2 || (layer_ok(nd[2]) && layer_ok(nd[4])));
-        }
+      case MOOG_SC_TREE: ok = tree_ok(op.i[0], op.i[1], false); break;
+      case MOOG_R_TREE:
+        ok = tree_ok(op.i[0], op.i[1], true) && op.i[3] >= 0 && (op.i[3] == 0 || envf_ok(op.i[2], op.i[3])) && op.i[4] >= 0 &&
+             (long long)op.i[4] + op.i[3] <= ND;
         break;
       default: ok = false; break;  // an op kind no kernel knows
     }

@@ -2497,6 +2497,14 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
         }
         break;
       }
+      case MOOG_X_ENVF: st[sp++] = e.envf[x->arg]; break;  // a user-defined rule's own attribute
+      case MOOG_X_STORE_ENVF: {
+        const double v = st[--sp];
+        wsync();
+        put(e, &e.envf[x->arg], v);
+        wsync();
+        break;
+      }
       case MOOG_X_SELECT: {  // c ? a : b
         const double vb = st[--sp], va = st[--sp], vc = st[--sp];
         st[sp++] = vc != 0 ? va : vb;
@@ -2526,6 +2534,44 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
   return sp ? st[sp - 1] : 1.0;
 }
 
+// A decision tree of lambdas.state_tree / lambdas.trace_rule (MOOG_SC_TREE, MOOG_R_TREE), walked lazily from
+// node 0: the tests made -- overlap calls included -- are the ones Python would make, in its order.  Node: kind,
+// expr, layer / index of sprite 0, layer / index of sprite 1, next if true, next if false.  A sprite index
+// beyond its layer's count is the reference's IndexError (MOOG_ERR_BAD_INDEX).
+__device__ __noinline__ double walk_tree(const Env &, const int32_t *nodes, int n) {
+  const Env e = env_view();
+  int j = 0;
+  for (int guard = 0; guard <= n; ++guard) {
+    const int32_t *nd = nodes + 8 * j;
+    if (nd[0] == 3) {  // index < len(state[layer])
+      j = nd[3] < e.cnt[nd[2]] ? nd[6] : nd[7];
+      continue;
+    }
+    int sl[2] = {0, 0};
+    for (int q = 0; q < 2; ++q) {
+      const int l = nd[2 + 2 * q], k = nd[3 + 2 * q];
+      if (l < 0) continue;
+      if (k >= e.cnt[l]) {
+        const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_BAD_INDEX;
+        wsync();
+        puti(e, &e.envi[MOOG_EI_ERR], err);
+        wsync();
+        return 0;
+      }
+      sl[q] = LOFF(e, l) + k;
+    }
+    if (nd[0] == 0) return nd[1] >= 0 ? eval_expr(e, nd[1], sl[0], sl[1]) : 0.0;  // leaf: the value / end of the rule
+    if (nd[0] == 4) {  // the assignments this path made
+      eval_expr(e, nd[1], sl[0], sl[1]);
+      j = nd[6];
+      continue;
+    }
+    const bool yes = nd[0] == 2 ? overlaps(e, sl[0], sl[1]) : eval_expr(e, nd[1], sl[0], sl[1]) != 0;
+    j = yes ? nd[6] : nd[7];
+  }
+  return 0;
+}
+
 // The step's uniform of one rule-noise column: supplied by the caller (io.rule_noise), else drawn from the
 // Philox stream keyed by (seed, env, number of rules_step passes so far, episode, column)
 __device__ double rule_noise_at(const Env &e, int col) {
@@ -2540,30 +2586,7 @@ __device__ __noinline__ double eval_condition_leaf(const Env &, int op_index) {
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
     case MOOG_SC_BERNOULLI: return rule_noise_at(e, op->i[0]) < op->p[0];  // np.random.binomial(1, p)
-    case MOOG_SC_TREE: {  // lambdas.state_tree: walked lazily, so the overlap calls are Python's, in its order
-      const int32_t *nodes = e.ipool + op->i[0];
-      int j = 0;
-      for (int guard = 0; guard <= op->i[1]; ++guard) {
-        const int32_t *nd = nodes + 8 * j;
-        int sl[2] = {0, 0};
-        for (int q = 0; q < 2; ++q) {
-          const int l = nd[2 + 2 * q], k = nd[3 + 2 * q];
-          if (l < 0) continue;
-          if (k >= e.cnt[l]) {  // IndexError in the reference
-            const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_BAD_INDEX;
-            wsync();
-            puti(e, &e.envi[MOOG_EI_ERR], err);
-            wsync();
-            return 0;
-          }
-          sl[q] = LOFF(e, l) + k;
-        }
-        if (nd[0] == 0) return eval_expr(e, nd[1], sl[0], sl[1]);
-        const bool yes = nd[0] == 2 ? overlaps(e, sl[0], sl[1]) : eval_expr(e, nd[1], sl[0], sl[1]) != 0;
-        j = yes ? nd[6] : nd[7];
-      }
-      return 0;
-    }
+    case MOOG_SC_TREE: return walk_tree(e, e.ipool + op->i[0], op->i[1]);
     case MOOG_SC_ALL:
     case MOOG_SC_ANY:
     case MOOG_SC_COUNT: {
@@ -2980,6 +3003,9 @@ __device__ __noinline__ void rule_leaf(const Env &, int r) {
       }
       return;
     }
+    case MOOG_R_TREE:  // a user-defined rule's step(), path by path
+      walk_tree(e, e.ipool + op->i[0], op->i[1]);
+      return;
     case MOOG_R_CREATE_SPRITES: {  // create_sprites.py:27-34
       const int layer = op->i[0], have = e.cnt[layer], cap = LOFF(e, layer + 1) - LOFF(e, layer);
       int count = op->i[1];
@@ -3403,6 +3429,8 @@ __device__ inline void post_reset(const Env &e) {
       }
       if (op->kind == MOOG_R_PORTAL)  // portal.py:36-39: _currently_teleporting = set()
         for (int s2 = e.lane; s2 < e.S; s2 += 32) META(e, MOOG_M_FLAGS, s2) &= ~MOOG_SF_TELEPORTING;
+      if (op->kind == MOOG_R_TREE)  // the rule's own reset(): its attributes back to their first values
+        for (int q = e.lane; q < op->i[3]; q += 32) e.envf[op->i[2] + q] = e.dpool[op->i[4] + q];
     }
     wsync();
   }

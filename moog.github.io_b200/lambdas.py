@@ -20,6 +20,7 @@ there is no per-step Python fallback.
 """
 
 import ast
+import collections
 import contextlib
 import inspect
 import textwrap
@@ -28,7 +29,7 @@ import numpy as np
 
 (X_END, X_CONST, X_ATTR0, X_ATTR1, X_LT, X_LE, X_GT, X_GE, X_EQ, X_NE, X_AND,
  X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE,
- X_STORE_POS, X_SELECT) = range(23)
+ X_STORE_POS, X_SELECT, X_ENVF, X_STORE_ENVF) = range(25)
 
 # attribute ids from here on read the sprite's numeric `metadata[key]` columns (MOOG_AT_META0)
 AT_META0 = 16
@@ -143,10 +144,11 @@ def _select(cond, a, b):
     return Sym(cond.code + a.code + b.code + [(X_SELECT, 0, 0.0)])
 
 
-def _explore_tree(fn, args, prefix=(), budget=None):
+def _explore_tree(fn, args, prefix=(), budget=None, hooks=None):
     """Like _explore, but the result is the decision TREE itself -- ('test', condition, subtree if true,
-    subtree if false) / ('leaf', value) -- for callables whose tests have to run lazily and in order
-    (overlap tests: which ones the reference makes depends on the outcome of the earlier ones)."""
+    subtree if false) / ('leaf', value, effects) -- for callables whose tests have to run lazily and in
+    order (overlap tests: which ones the reference makes depends on the outcome of the earlier ones).
+    hooks = (begin, end): begin() before every path is run, end() -> the effects that path recorded."""
     budget = [_MAX_PATHS] if budget is None else budget
     budget[0] -= 1
     if budget[0] < 0:
@@ -154,13 +156,16 @@ def _explore_tree(fn, args, prefix=(), budget=None):
     previous, _PATH[0] = _PATH[0], _Path(prefix)
     path = _PATH[0]
     try:
+        if hooks:
+            hooks[0]()
         value = fn(*args)
+        effects = hooks[1]() if hooks else []
     finally:
         _PATH[0] = previous
-    node = ('leaf', value)
+    node = ('leaf', value, effects)
     base = len(prefix)
     for j in range(len(path.new) - 1, -1, -1):
-        other = _explore_tree(fn, args, tuple(path.forced[:base + j]) + (False,), budget)
+        other = _explore_tree(fn, args, tuple(path.forced[:base + j]) + (False,), budget, hooks)
         node = ('test', path.new[j], node, other)
     return node
 
@@ -216,12 +221,25 @@ class SymOverlap(object):
                 and isinstance(b._which, tuple)):
             raise LoweringError('overlaps_sprite is lowered between two sprites taken from the state only')
         self.pair = (a._which[1], b._which[1])
+        self.owner = getattr(a, '_owner', None)
 
-    def __bool__(self):
+    def decide(self):
+        """The test is made where the CALL is made (`[a.overlaps_sprite(s) for s in layer]` calls for every
+        sprite before any() looks at the results): the outcome is a plain bool on this path."""
         path = _PATH[0]
         if path is None:
-            raise LoweringError('overlaps_sprite can only be branched on')
+            raise LoweringError('overlaps_sprite between sprites of the state is lowered in state-level callables only')
+        owner = self.owner
+        if owner is not None and owner.geometry_touched():
+            raise LoweringError('an overlap test after the callable moved / reshaped a sprite is not lowered')
         return path.decide(self)
+
+
+class SymHas(object):
+    """`index < len(state[layer])` while a state-level callable iterates over a layer."""
+
+    def __init__(self, layer, index):
+        self.layer, self.index = layer, index
 
 
 class SymMetadata(object):
@@ -258,7 +276,7 @@ class SymSprite(object):
         if name in ATTRS:
             return Sym([_attr_read(self._which, ATTRS.index(name))])
         if name == 'overlaps_sprite' and isinstance(self._which, tuple):
-            return lambda other: SymOverlap(self, other)
+            return lambda other: SymOverlap(self, other).decide()
         if name == 'position':
             return SymVec([self.x, self.y])
         if name == 'velocity':
@@ -401,20 +419,68 @@ class SymState(object):
         return _SymLayer(self, name)
 
 
+class BoundSprite(SymSprite):
+    """A sprite picked out of the state by a state-level callable.  Reads see what the callable itself
+    assigned earlier on this path; assignments are recorded as effects of the path (a rule's `step`)."""
+
+    def __init__(self, owner, k):
+        SymSprite.__init__(self, ('bound', k), None)
+        object.__setattr__(self, '_owner', owner)
+        object.__setattr__(self, '_k', k)
+
+    def __getattr__(self, name):
+        shadow = self._owner.shadow
+        if (self._k, name) in shadow:
+            return shadow[(self._k, name)]
+        if name == 'velocity' and ((self._k, 'x_vel') in shadow or (self._k, 'y_vel') in shadow):
+            return SymVec([self.x_vel, self.y_vel])
+        if name == 'position' and ((self._k, 'x') in shadow or (self._k, 'y') in shadow):
+            return SymVec([self.x, self.y])
+        return SymSprite.__getattr__(self, name)
+
+    def __setattr__(self, name, value):
+        owner = self._owner
+        if owner.effects is None:
+            raise LoweringError('this callable may not modify sprites')
+        if name in ('position', 'velocity'):
+            pair = (Sym.lift(value[0]), Sym.lift(value[1]))
+            a, b = ('x', 'y') if name == 'position' else ('x_vel', 'y_vel')
+            owner.shadow[(self._k, a)], owner.shadow[(self._k, b)] = pair
+            owner.effects.append(('sprite', self._k, name, pair))
+            return
+        if name not in _WRITABLE:
+            raise LoweringError('assigning sprite.{} is not supported on the device path (writable: {})'.format(
+                name, ', '.join(_WRITABLE)))
+        value = Sym.lift(value)
+        owner.shadow[(self._k, name)] = value
+        owner.effects.append(('sprite', self._k, name, value))
+
+
 class _BoundLayer(object):
     def __init__(self, owner, name):
         self._owner, self._name = owner, name
 
-    def __getitem__(self, index):
-        if not isinstance(index, int) or index < 0:
-            raise LoweringError('state[{!r}][...] must be a fixed non-negative index in a state-level callable'.format(self._name))
+    def _sprite(self, index):
         key = (self._name, index)
         if key not in self._owner.bound:
             self._owner.bound.append(key)
-        return SymSprite(('bound', self._owner.bound.index(key)))
+        return BoundSprite(self._owner, self._owner.bound.index(key))
+
+    def __getitem__(self, index):
+        if not isinstance(index, int) or index < 0:
+            raise LoweringError('state[{!r}][...] must be a fixed non-negative index in a state-level callable'.format(self._name))
+        return self._sprite(index)
 
     def __iter__(self):
-        raise LoweringError('iterating over state[{!r}] is not lowered here'.format(self._name))
+        """`for s in state[layer]`: one path per number of sprites the layer can hold (a test of
+        `index < len(layer)` before each one)."""
+        path, cap = _PATH[0], self._owner.capacity(self._name)
+        if path is None or cap is None:
+            raise LoweringError('iterating over state[{!r}] is not lowered here'.format(self._name))
+        for index in range(cap):
+            if not path.decide(SymHas(self._name, index)):
+                return
+            yield self._sprite(index)
 
     def __len__(self):
         raise LoweringError('len(state[{!r}]) is not lowered here'.format(self._name))
@@ -424,18 +490,37 @@ class BoundState(object):
     """The environment state for a state-level callable that picks single sprites (`state['agent'][0]`),
     reads their attributes / metadata and tests overlaps between them (bounce_box_contact_prediction.py:94-103)."""
 
-    def __init__(self):
-        self.bound = []       # (layer name, index) of every sprite picked, in first-use order
+    _GEOMETRY = ('x', 'y', 'position', 'angle', 'scale', 'aspect_ratio')
+
+    def __init__(self, prog=None, effects=False):
+        self.bound = []       # (layer name, index) of every sprite picked, in first-use order (all paths)
+        self.prog = prog
+        self.shadow = {}      # this path: (bound id, attribute) -> value the callable assigned
+        self.effects = [] if effects else None
+
+    def begin_path(self):
+        self.shadow = {}
+        if self.effects is not None:
+            self.effects = []
+
+    def capacity(self, layer):
+        if self.prog is None:
+            return None
+        return self.prog.layer_cap[self.prog.layer_index(layer)]
+
+    def geometry_touched(self):
+        return any(e[0] == 'sprite' and e[2] in self._GEOMETRY for e in (self.effects or ()))
 
     def __getitem__(self, name):
         return _BoundLayer(self, name)
 
 
-def _bind_pair(code, what):
-    """Expression over bound sprites -> (code over sprite 0 / sprite 1, [bound ids of sprite 0, sprite 1])."""
-    ids = []
+def _bind_pair(code, what, first=None):
+    """Expression over bound sprites -> (code over sprite 0 / sprite 1, [bound ids of sprite 0, sprite 1]);
+    `first`: the bound sprite that must be sprite 0 (the target of the stores in `code`)."""
+    ids = [] if first is None else [first]
     for op, arg, _ in code:
-        if op in (X_ATTR0, X_ATTR1, X_STORE) and arg >> 8:
+        if op in (X_ATTR0, X_ATTR1) and arg >> 8:
             k = (arg >> 8) - 1
             if k not in ids:
                 ids.append(k)
@@ -450,24 +535,13 @@ def _bind_pair(code, what):
     return out, ids
 
 
-def state_tree(fn, prog, what):
-    """A state-level callable `fn(state)` made of single-sprite picks, attribute / metadata reads, overlap
-    tests and `if`s -> index of a MOOG_SC_TREE op: a decision tree evaluated lazily, test by test, in the
-    order Python would make them (so the overlap calls are the reference's, call for call)."""
-    state = BoundState()
-    call = fn
-    try:
-        call = _rewritten(fn)
-    except Exception:  # pylint: disable=broad-except
-        call = fn
-    with no_randomness(what):
-        try:
-            tree = _explore_tree(call, (state,))
-        except LoweringError:
-            raise
-        except Exception as exc:  # pylint: disable=broad-except
-            raise LoweringError('{} cannot be lowered to a decision tree over the state ({}: {})'.format(
-                what, type(exc).__name__, exc))
+# node kinds of a decision tree (MOOG_SC_TREE / MOOG_R_TREE)
+TN_LEAF, TN_TEST_EXPR, TN_TEST_OVERLAP, TN_TEST_HAS, TN_ACTION = range(5)
+
+
+def _emit_tree(tree, state, prog, what, with_value):
+    """Decision tree -> ipool nodes of 8 ints (kind, expr, layer / index of sprite 0, layer / index of
+    sprite 1, next if true, next if false); returns (ipool start, number of nodes)."""
     nodes = []
 
     def sprite_ref(k):
@@ -476,24 +550,61 @@ def state_tree(fn, prog, what):
         layer, index = state.bound[k]
         return (prog.layer_index(layer), index)
 
+    def refs(ids):
+        ids = list(ids) + [None] * (2 - len(ids))
+        return sprite_ref(ids[0]) + sprite_ref(ids[1])
+
+    def effect_code(effect):
+        """One recorded assignment -> (code ending in its store, bound id of the sprite stored to or None)."""
+        if effect[0] == 'var':
+            return Sym.lift(effect[2]).code + [(X_STORE_ENVF, effect[1], 0.0)], None
+        _, k, name, value = effect
+        return _stores_to_code([(name, value)])[:-1], k
+
     def emit(node):
         me = len(nodes)
         nodes.append(None)
         if node[0] == 'leaf':
-            value = node[1]
-            if isinstance(value, SymOverlap):
-                raise LoweringError('{} returns an overlap test; branch on it instead'.format(what))
-            code, ids = _bind_pair(Sym.lift(value).code, what)
-            ids = ids + [None] * (2 - len(ids))
-            nodes[me] = (0, prog.add_expr(code)) + sprite_ref(ids[0]) + sprite_ref(ids[1]) + (0, 0)
+            effects = list(node[2])
+            written = set()
+            chain = []
+            for effect in effects:
+                code, target = effect_code(effect)
+                reads = {('sprite', (arg >> 8) - 1, arg & 0xff) for op, arg, _ in code if op in (X_ATTR0, X_ATTR1) and arg >> 8}
+                reads |= {('var', arg) for op, arg, _ in code if op == X_ENVF}
+                if reads & written:
+                    raise LoweringError('{}: an assignment reads a value an earlier assignment of the same call changed '
+                                        '(effects are applied one after the other on the device)'.format(what))
+                if effect[0] == 'var':
+                    written.add(('var', effect[1]))
+                else:
+                    for attr in ({'position': ('x', 'y'), 'velocity': ('x_vel', 'y_vel')}.get(effect[2], (effect[2],))):
+                        written.add(('sprite', effect[1], ATTRS.index(attr)))
+                bound_code, ids = _bind_pair(code, what, first=target)
+                chain.append((TN_ACTION, prog.add_expr(bound_code + [(X_CONST, 0, 1.0)])) + refs(ids))
+            if with_value:
+                value = node[1]
+                code, ids = _bind_pair(Sym.lift(value).code, what)
+                last = (TN_LEAF, prog.add_expr(code)) + refs(ids) + (0, 0)
+            else:
+                last = (TN_LEAF, -1, -1, 0, -1, 0, 0, 0)
+            # the actions of the path, then the leaf
+            slots = [me] + [None] * len(chain)
+            for q in range(len(chain)):
+                slots[q + 1] = len(nodes)
+                nodes.append(None)
+            for q, head in enumerate(chain):
+                nodes[slots[q]] = head + (slots[q + 1], slots[q + 1])
+            nodes[slots[-1]] = last
             return me
         cond = node[1]
         if isinstance(cond, SymOverlap):
-            head = (2, -1) + sprite_ref(cond.pair[0]) + sprite_ref(cond.pair[1])
+            head = (TN_TEST_OVERLAP, -1) + refs(cond.pair)
+        elif isinstance(cond, SymHas):
+            head = (TN_TEST_HAS, -1, prog.layer_index(cond.layer), cond.index, -1, 0)
         else:
             code, ids = _bind_pair(cond.code, what)
-            ids = ids + [None] * (2 - len(ids))
-            head = (1, prog.add_expr(code)) + sprite_ref(ids[0]) + sprite_ref(ids[1])
+            head = (TN_TEST_EXPR, prog.add_expr(code)) + refs(ids)
         yes = emit(node[2])
         no = emit(node[3])
         nodes[me] = head + (yes, no)
@@ -501,8 +612,149 @@ def state_tree(fn, prog, what):
 
     emit(tree)
     flat = [v for nd in nodes for v in nd]
-    start = prog.add_ints(flat)
-    return prog.emit(170, 0, (start, len(nodes)))   # MOOG_SC_TREE
+    return prog.add_ints(flat), len(nodes)
+
+
+def state_tree(fn, prog, what):
+    """A state-level callable `fn(state)` made of single-sprite picks, attribute / metadata reads, overlap
+    tests and `if`s -> index of a MOOG_SC_TREE op: a decision tree evaluated lazily, test by test, in the
+    order Python would make them (so the overlap calls are the reference's, call for call)."""
+    state = BoundState(prog)
+    call = fn
+    try:
+        call = _rewritten(fn)
+    except Exception:  # pylint: disable=broad-except
+        call = fn
+    with no_randomness(what):
+        try:
+            tree = _explore_tree(call, (state,), hooks=(state.begin_path, lambda: []))
+        except LoweringError:
+            raise
+        except Exception as exc:  # pylint: disable=broad-except
+            raise LoweringError('{} cannot be lowered to a decision tree over the state ({}: {})'.format(
+                what, type(exc).__name__, exc))
+    start, count = _emit_tree(tree, state, prog, what, with_value=True)
+    return prog.emit(170, 0, (start, count))   # MOOG_SC_TREE
+
+
+class _RuleProxy(object):
+    """`self` of a user-defined rule while its reset / step is traced: numeric attributes the rule assigns
+    are its state variables (one envf slot each); everything else reads through to the real object;
+    methods are re-bound to the proxy."""
+
+    def __init__(self, rule, variables):
+        object.__setattr__(self, '_rule', rule)
+        object.__setattr__(self, '_values', dict(variables))
+        object.__setattr__(self, '_assigned', [])
+
+    def __getattr__(self, name):
+        values = object.__getattribute__(self, '_values')
+        if name in values:
+            return values[name]
+        value = getattr(object.__getattribute__(self, '_rule'), name)
+        if inspect.ismethod(value):
+            return value.__func__.__get__(self)
+        return value
+
+    def __setattr__(self, name, value):
+        object.__getattribute__(self, '_values')[name] = value
+        object.__getattribute__(self, '_assigned').append(name)
+
+
+def trace_rule(rule, prog):
+    """A user-defined rule class (functional_maze.py:18-67 `Booster`: a countdown of its own, an overlap
+    test over a layer, attribute changes on a sprite) -> (nodes start, node count, envf slot of its first
+    state variable, initial values): `reset` is traced for the variables and their initial values, `step`
+    along every path into a decision tree whose leaves carry the assignments of that path
+    (MOOG_R_TREE).  What it may do: pick sprites (`state[layer][i]`, `for s in state[layer]`), read their
+    attributes / metadata, test overlaps, branch, assign writable sprite attributes and its own numeric
+    attributes.  Anything else is refused."""
+    what = 'rule {}'.format(type(rule).__name__)
+    cls = type(rule)
+
+    def numeric(v):
+        return isinstance(v, (bool, int, float)) or (hasattr(v, '__float__') and not isinstance(v, (Sym, SymVec)))
+
+    # reset(): which attributes are state, and what they start from
+    proxy = _RuleProxy(rule, {})
+    with no_randomness(what):
+        try:
+            cls.reset(proxy, BoundState(prog), None)
+        except LoweringError:
+            raise
+        except Exception as exc:  # pylint: disable=broad-except
+            raise LoweringError('{}.reset cannot be traced ({}: {})'.format(what, type(exc).__name__, exc))
+    initial = collections.OrderedDict()
+    for name in proxy._assigned:
+        v = proxy._values[name]
+        if not numeric(v):
+            raise LoweringError('{}.reset assigns self.{} = {!r}: only numbers are carried on the device'.format(what, name, v))
+        initial[name] = float(v)
+
+    def explore(variables, slots):
+        state = BoundState(prog, effects=True)
+        holder = {}
+
+        def begin():
+            state.begin_path()
+            holder['proxy'] = _RuleProxy(rule, {n: Sym([(X_ENVF, slots[n], 0.0)]) for n in variables})
+
+        def end():
+            px = holder['proxy']
+            effects = list(state.effects)
+            for name in dict.fromkeys(px._assigned):
+                v = px._values[name]
+                if isinstance(v, SymVec) or not (isinstance(v, Sym) or numeric(v)):
+                    raise LoweringError('{}.step assigns self.{} = {!r}: only numbers are carried on the device'.format(
+                        what, name, v))
+                effects.append(('var', slots.get(name, -1), v, name))
+            return effects
+
+        def call(st):
+            out = cls.step(holder['proxy'], st, None)
+            if out is not None:
+                raise LoweringError('{}.step returns a value'.format(what))
+
+        with no_randomness(what):
+            try:
+                tree = _explore_tree(call, (state,), hooks=(begin, end))
+            except LoweringError:
+                raise
+            except Exception as exc:  # pylint: disable=broad-except
+                raise LoweringError('{}.step cannot be lowered to a decision tree over the state ({}: {})'.format(
+                    what, type(exc).__name__, exc))
+        return tree, state
+
+    def assigned_names(tree, out):
+        if tree[0] == 'leaf':
+            for e in tree[2]:
+                if e[0] == 'var' and e[3] not in out:
+                    out.append(e[3])
+        else:
+            assigned_names(tree[2], out)
+            assigned_names(tree[3], out)
+        return out
+
+    # first pass: discover the variables step() assigns that reset() did not (they start from the object's own value)
+    probe_slots = {n: k for k, n in enumerate(initial)}
+    tree, _ = explore(list(initial), probe_slots)
+    for name in assigned_names(tree, []):
+        if name not in initial:
+            v = getattr(rule, name, None)
+            if not numeric(v):
+                raise LoweringError('{}.step assigns self.{}, which has no numeric value before the first step'.format(what, name))
+            initial[name] = float(v)
+    base = prog.alloc_envf(max(len(initial), 1))
+    slots = {n: base + k for k, n in enumerate(initial)}
+    tree, state = explore(list(initial), slots)
+
+    def strip(node):        # ('var', slot, value, name) -> ('var', slot, value)
+        if node[0] == 'leaf':
+            return ('leaf', node[1], [e[:3] if e[0] == 'var' else e for e in node[2]])
+        return ('test', node[1], strip(node[2]), strip(node[3]))
+
+    start, count = _emit_tree(strip(tree), state, prog, what, with_value=False)
+    return start, count, base, list(initial.values())
 
 
 def _n_params(fn):
@@ -727,6 +979,11 @@ def compile_modifier(fn):
     """`fn(sprite)` mutating the sprite -> postfix code of its stores."""
     stores = []
     _symbolic_call(fn, SymSprite(0, stores), branches=False)
+    return _stores_to_code(stores)
+
+
+def _stores_to_code(stores):
+    """[(attribute name, value)] recorded while tracing -> postfix code of the stores (+ a final constant)."""
     code = []
     for name, value in stores:
         if name == 'position':
@@ -738,7 +995,7 @@ def compile_modifier(fn):
             # a FRESH array (sprite.py:639-643): one that is built from constants / positions only is
             # float64 and shared with nobody (c = 3: the device drops MOOG_SF_VEL32 and the alias id);
             # one computed from the sprite's own velocity keeps that velocity's dtype (c = 0).
-            dtype_free = not any(op in (X_ATTR0, X_ATTR1) and arg < len(ATTRS) and ATTRS[arg] in ('x_vel', 'y_vel', 'angle_vel', 'angle')
+            dtype_free = not any(op in (X_ATTR0, X_ATTR1) and (arg & 0xff) < len(ATTRS) and ATTRS[arg & 0xff] in ('x_vel', 'y_vel', 'angle_vel', 'angle')
                                  for v in value for op, arg, _ in v.code)
             kind = 3.0 if dtype_free else 0.0
             code += value[0].code + value[1].code + [(X_STORE, ATTRS.index('y_vel'), kind),

@@ -100,6 +100,10 @@ SCENES = {
     # overlaps between them and branch on metadata (bounce_box_contact_prediction.py:94-110): a decision tree;
     # translucent occluder (opacity 128), a TimedRule that removes the screen
     'bounce_box': ('moog_demos.example_configs.bounce_box_contact_prediction', True, 20, 120, 8),
+    # a shipped config with a rule class of its own (functional_maze.py:18-67 `Booster`: a countdown attribute,
+    # an overlap test over a layer, mass / colour changes applied and reverted 60 steps later), Portal,
+    # RandomForce, DistanceForce; the agent is steered into a booster, then after the prey
+    'functional_maze': ('moog_demos.example_configs.functional_maze', None, 127, 130, 10),
 }
 
 
@@ -139,6 +143,16 @@ def _chase_action(env, t):
     n = float(np.linalg.norm(d))
     d = d / n if n > 0 else np.zeros(2)
     return -d if t % 4 == 3 else d
+
+
+def _booster_action(env, t):
+    """functional_maze: full stick towards the nearest booster for 45 steps, then towards the nearest prey."""
+    a = env.state['agent'][0]
+    targets = env.state['boosters'] if t < 45 else (env.state['prey'] or env.state['boosters'])
+    d = [np.array(s.position) - np.array(a.position) for s in targets]
+    d = min(d, key=lambda v: float(np.dot(v, v)))
+    n = float(np.linalg.norm(d))
+    return d / n if n > 0 else np.zeros(2)
 
 
 def _pacman_action(env, t):
@@ -310,6 +324,8 @@ def generate(name, out_dir):
             action = _chase_action(env, t)
         elif name == 'pacman':
             action = _pacman_action(env, t)
+        elif name == 'functional_maze':
+            action = _booster_action(env, t)
         elif name == 'bounce_box':
             action = 4 if t < 25 else 0             # wait, then walk into the left response box
         elif name == 'predict_zoo':

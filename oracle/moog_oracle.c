@@ -1504,6 +1504,8 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
         set_position(e, s0, nx, ny);
         break;
       }
+      case MOOG_X_ENVF: st[sp++] = e->envf[x->arg]; break; /* a user-defined rule's own attribute */
+      case MOOG_X_STORE_ENVF: e->envf[x->arg] = st[--sp]; break;
       case MOOG_X_SELECT: { /* an `if` / `else` of the config callable on a per-sprite value */
         const double vb = st[--sp], va = st[--sp], vc = st[--sp];
         st[sp++] = vc != 0 ? va : vb;
@@ -1534,6 +1536,41 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
 }
 
 /* state conditions */
+/* A decision tree of lambdas.state_tree / lambdas.trace_rule (MOOG_SC_TREE, MOOG_R_TREE), walked lazily from
+ * node 0: the tests made -- overlap calls included -- are the ones Python would make, in its order.  Node: kind,
+ * expr, layer / index of sprite 0, layer / index of sprite 1, next if true, next if false.  A sprite index
+ * beyond its layer's count is the reference's IndexError (MOOG_ERR_BAD_INDEX). */
+static double eval_expr(env_t *e, int start, int s0, int s1);
+static double walk_tree(env_t *e, const int32_t *nodes, int n) {
+  int j = 0;
+  for (int guard = 0; guard <= n; ++guard) {
+    const int32_t *nd = nodes + 8 * j;
+    if (nd[0] == 3) { /* index < len(state[layer]) */
+      j = nd[3] < e->cnt[nd[2]] ? nd[6] : nd[7];
+      continue;
+    }
+    int sl[2] = {0, 0};
+    for (int q = 0; q < 2; ++q) {
+      const int l = nd[2 + 2 * q], k = nd[3 + 2 * q];
+      if (l < 0) continue;
+      if (k >= e->cnt[l]) {
+        e->envi[MOOG_EI_ERR] |= MOOG_ERR_BAD_INDEX;
+        return 0;
+      }
+      sl[q] = LOFF(e, l) + k;
+    }
+    if (nd[0] == 0) return nd[1] >= 0 ? eval_expr(e, nd[1], sl[0], sl[1]) : 0.0; /* leaf: the value / end of the rule */
+    if (nd[0] == 4) { /* the assignments this path made */
+      eval_expr(e, nd[1], sl[0], sl[1]);
+      j = nd[6];
+      continue;
+    }
+    const int yes = nd[0] == 2 ? overlaps(e, sl[0], sl[1]) : eval_expr(e, nd[1], sl[0], sl[1]) != 0;
+    j = yes ? nd[6] : nd[7];
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------ */
 /* counter-based draws (Philox4x32-10)                                        */
 /*                                                                            */
@@ -1754,27 +1791,7 @@ static double eval_condition(env_t *e, int op_index) {
   switch (op->kind) {
     case MOOG_SC_CONST: return op->p[0];
     case MOOG_SC_BERNOULLI: return rule_noise_at(e, op->i[0]) < op->p[0]; /* np.random.binomial(1, p) */
-    case MOOG_SC_TREE: { /* lambdas.state_tree: walked lazily, so the overlap calls are Python's, in its order */
-      const int32_t *nodes = e->ipool + op->i[0];
-      int j = 0;
-      for (int guard = 0; guard <= op->i[1]; ++guard) {
-        const int32_t *nd = nodes + 8 * j;
-        int sl[2] = {0, 0};
-        for (int q = 0; q < 2; ++q) {
-          const int l = nd[2 + 2 * q], k = nd[3 + 2 * q];
-          if (l < 0) continue;
-          if (k >= e->cnt[l]) { /* IndexError in the reference */
-            e->envi[MOOG_EI_ERR] |= MOOG_ERR_BAD_INDEX;
-            return 0;
-          }
-          sl[q] = LOFF(e, l) + k;
-        }
-        if (nd[0] == 0) return eval_expr(e, nd[1], sl[0], sl[1]);
-        const int yes = nd[0] == 2 ? overlaps(e, sl[0], sl[1]) : eval_expr(e, nd[1], sl[0], sl[1]) != 0;
-        j = yes ? nd[6] : nd[7];
-      }
-      return 0;
-    }
+    case MOOG_SC_TREE: return walk_tree(e, e->ipool + op->i[0], op->i[1]);
     case MOOG_SC_ALL:
     case MOOG_SC_ANY:
     case MOOG_SC_COUNT: {
@@ -1997,6 +2014,9 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
       vanish(e, lo, gone);
       return 1;
     }
+    case MOOG_R_TREE: /* a user-defined rule's step(), path by path */
+      walk_tree(e, e->ipool + op->i[0], op->i[1]);
+      return 1;
     case MOOG_R_CREATE_SPRITES: { /* create_sprites.py:27-34 */
       const int layer = op->i[0], have = e->cnt[layer], cap = LOFF(e, layer + 1) - LOFF(e, layer);
       int count = op->i[1];
@@ -2033,6 +2053,8 @@ static void rules_reset(env_t *e) {
     }
     if (op->kind == MOOG_R_PORTAL) /* portal.py:36-39: _currently_teleporting = set() */
       for (int s2 = 0; s2 < e->S; ++s2) META(e, MOOG_M_FLAGS, s2) &= ~MOOG_SF_TELEPORTING;
+    if (op->kind == MOOG_R_TREE) /* the rule's own reset(): its attributes back to their first values */
+      for (int q = 0; q < op->i[3]; ++q) e->envf[op->i[2] + q] = e->dpool[op->i[4] + q];
   }
 }
 

@@ -263,3 +263,119 @@ def test_state_decision_tree_matches_python_call_for_call():
     orc2.post_reset()
     orc2.step(np.full((len(states), 1), 4.0))
     assert ((orc2.envi[:, 2] & 128) != 0).all()
+
+
+class _Tagger(object):
+    """A rule class of a config's own, in the style of functional_maze.py:18-67: numeric attributes of its
+    own (one of them never touched by reset), a loop over a layer whose length varies, overlap tests,
+    assignments to sprites under branches."""
+
+    def __init__(self, threshold):
+        self._threshold = threshold
+        self.total = 0
+
+    def reset(self, state, meta_state):
+        del state, meta_state
+        self.hits = 0
+
+    def step(self, state, meta_state):
+        del meta_state
+        agent = state['agent'][0]
+        for s in state['items']:
+            if agent.overlaps_sprite(s):
+                self.hits += 1
+                self.total = self.total + 1
+                s.c0 = s.c0 + 1.
+        if self.hits > self._threshold:
+            agent.mass = agent.mass * 2
+            self.hits = 0
+
+
+def test_user_defined_rule_is_traced_path_by_path():
+    """lambdas.trace_rule: the rule's step() as a decision tree (MOOG_R_TREE) against the rule itself run
+    in Python on host sprites, step by step, for states with 0..3 items of which some touch the agent."""
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, physics as physics_lib, sprite, tasks
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+
+    def state_initializer(n_items):
+        agent = sprite.Sprite(x=0.5, y=0.5, shape='square', scale=0.2, mass=1.)
+        xs = [0.45, 0.9, 0.55]           # the first and the third touch the agent
+        items = [sprite.Sprite(x=xs[k], y=0.5, shape='circle', scale=0.05, c0=float(k)) for k in range(n_items)]
+        return collections.OrderedDict([('items', items), ('agent', [agent])])
+
+    states = [state_initializer(n) for n in (3, 0, 1, 2, 3)]
+    rule = _Tagger(threshold=3)
+    cfg = dict(state_initializer=lambda: state_initializer(3), physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(timeout_steps=100), action_space=action_spaces.Grid(action_layers=()),
+               observers={}, game_rules=(rule,))
+    prog = compiler.compile_config(cfg, states)
+    tree = [o for o in prog.ops if o['kind'] == compiler.R_TREE]
+    assert len(tree) == 1 and tree[0]['i'][3] == 2          # two state variables: hits (reset) and total (constructor)
+    assert prog.dpool[tree[0]['i'][4]:tree[0]['i'][4] + 2] == [0.0, 0.0]
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    orc.post_reset()                                   # reset(), then every rule is stepped once
+    twins = [(_Tagger(threshold=3), st) for st in states]
+    for r, st in twins:
+        r.reset(st, None)
+        r.step(st, None)
+    lo, ag = prog.layer_off[0], prog.layer_off[1]
+    base = tree[0]['i'][2]
+    for t in range(7):
+        for e, (r, st) in enumerate(twins):
+            n = len(st['items'])
+            assert orc.stat[e, 6, lo:lo + n].tolist() == [s.c0 for s in st['items']], (t, e, 'c0')
+            assert orc.stat[e, 0, ag] == st['agent'][0].mass, (t, e, 'mass')
+            assert orc.envf[e, base:base + 2].tolist() == [float(r.hits), float(r.total)], (t, e, 'rule attributes')
+        orc.step(np.full((len(states), 1), 4.0))
+        for r, st in twins:
+            r.step(st, None)
+    assert orc.stat[0, 0, ag] == 16.0 and orc.stat[1, 0, ag] == 1.0         # 2 hits per pass, 8 passes: doubled 4 times; no items: never
+    assert (orc.envi[:, 2] == 0).all()
+
+
+def test_rules_that_cannot_be_traced_are_refused():
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, physics as physics_lib, sprite, tasks
+    from moog_b200 import compiler
+
+    def state_initializer():
+        return collections.OrderedDict([('agent', [sprite.Sprite(x=0.5, y=0.5)]), ('items', [sprite.Sprite(x=0.2, y=0.2)])])
+
+    class Random(object):
+        def reset(self, state, meta_state):
+            pass
+
+        def step(self, state, meta_state):
+            state['agent'][0].c0 = np.random.uniform()
+
+    class MovesThenTests(object):
+        def reset(self, state, meta_state):
+            pass
+
+        def step(self, state, meta_state):
+            agent = state['agent'][0]
+            agent.position = np.array([0.1, 0.1])
+            if agent.overlaps_sprite(state['items'][0]):
+                agent.c0 = 1.
+
+    class ReadsItsOwnWrite(object):
+        def reset(self, state, meta_state):
+            pass
+
+        def step(self, state, meta_state):
+            agent = state['agent'][0]
+            if agent.x > 0.2:
+                agent.mass = 2.
+                state['items'][0].mass = agent.mass * state['items'][0].mass     # fine: the traced value of agent.mass is 2
+                agent.c0 = agent.c1
+                agent.c1 = 5.
+                agent.c2 = agent.c1 + state['items'][0].mass                      # reads items[0].mass, assigned above
+
+    base = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+                task=tasks.CompositeTask(timeout_steps=10), action_space=action_spaces.Grid(action_layers=()), observers={})
+    states = [state_initializer()]
+    for cls, text in ((Random, 'random'), (MovesThenTests, 'moved'), (ReadsItsOwnWrite, 'earlier assignment')):
+        with pytest.raises(compiler.CompileError, match=text):
+            compiler.compile_config(dict(base, game_rules=(cls(),)), states)
