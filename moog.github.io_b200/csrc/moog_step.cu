@@ -772,7 +772,12 @@ __device__ __forceinline__ bool unit_ratio(double n, double d, bool &exact) {
 
 enum { HELPER_EXIT = 0, HELPER_DCV = 1 };
 // named barrier over the owner and helper warps of the CTA (also orders their shared-memory traffic)
-__device__ __forceinline__ void cta_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// (the warp reconverges first: `bar.sync` is the .aligned form, which every lane of a warp must execute together --
+// compute-sanitizer synccheck flagged lanes still apart after an `if (lane == 0)` store in front of it)
+__device__ __forceinline__ void cta_bar(int id) {
+  __syncwarp();
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
 
 struct CVec {
   int has_point, future, has_since;
@@ -1390,6 +1395,7 @@ __device__ __forceinline__ bool pair_candidate(const Env &e, int a, int b, bool 
 __device__ __noinline__ void rebuild_near(const Env &) {
   const Env e = env_view();
   const int32_t *h = e.hdr;
+  wsync();  // the caller's lanes have read the old snapshot (refresh_candidates)
   for (int i = e.lane; i < 4 * e.S; i += 32) e.aabb0[i] = (float)e.aabb[i];
   {
     const double rem = (double)(e.K - (int)e.ctr[CT_SUBSTEP]) / (double)e.K;
