@@ -125,6 +125,9 @@ enum {
   MOOG_H_N_DPOOL = 53,    /* doubles in dpool */
   MOOG_H_SHAPE_TAB = 54,  /* index in ipool of shape_off[n_shapes]: offset in dpool of each shape record */
   MOOG_H_N_META = 55,     /* numeric `sprite.metadata[key]` columns the program's callables read (<= MOOG_MAX_META) */
+  MOOG_H_N_METAVAR = 57,  /* entries of the env's `meta_state` dict carried in envf (numbers; strings as codes) */
+  MOOG_H_METAVAR_OFF = 58,  /* envf offset of the first one */
+  MOOG_H_METAVAR_INIT = 59, /* dpool index of their values after meta_state_initializer() (environment.py:86) */
   MOOG_H_META_OFF = 56,   /* envf offset of column 0; column k of slot s is envf[off + k * S + s], NaN = no such key.
                              Read as attribute MOOG_AT_META0 + k; travels with the sprite when slots are compacted */
   MOOG_H_CMASK_WORDS = 50 /* 32-bit words of the per-env broad-phase candidate matrices of all
@@ -191,6 +194,21 @@ enum {
                                     `index < len(layer)`, 4 = run the stores of `expr` then go on; the leaf ends the
                                     rule): i0 ipool start, i1 nodes; the rule's own numeric attributes live in envf
                                     [i2, i2 + i3) and are set to dpool[i4 ...] when the rule is reset */
+  MOOG_R_FIXATION,               /* fixation.py:45-54: i0 agent layer, i1 fixation layer (first sprite of each), i2 envf
+                                    slot of meta_state[key], p0 threshold: += 1 while the two are closer, else 0 */
+  MOOG_R_PHASESEQ_BEGIN,         /* task_phases.py:98-141 PhaseSequence: i0 envf slots (current phase index, its value
+                                    when this pass began), i1 phases, i2 envf slot of meta_state[phase name key] or -1,
+                                    i4 dpool index of the phases' name codes */
+  MOOG_R_PHASE_BEGIN,            /* task_phases.py:18-95 Phase: guards the i1 ops that follow (a MOOG_R_COND_BEGIN on
+                                    "first step" around the one-time rules, the continual rules, MOOG_R_PHASE_END);
+                                    they run while the phase has not ended and -- i0 >= 0: envf slot pair of its
+                                    PhaseSequence -- it is phase i2 of the sequence.  i3 envf slots (should_end,
+                                    step_count, duration); the duration is p0, or (p2 > p1) drawn at reset from
+                                    {p1 .. p2 - 1} with the uniform of rule-noise column i4 */
+  MOOG_R_PHASE_END,              /* step_count += 1; ended when step_count >= duration or condition op i0 (-1: never)
+                                    holds; then the sequence (i2 >= 0) moves on and names the next phase in envf[i3]
+                                    (dpool[i4 + index], i5 phases; past the last one: the reference's IndexError).
+                                    i1 envf slots of the phase */
 
   /* tasks: i[5] = envf slot of the countdown */
   MOOG_T_CONTACT_REWARD = 96, /* i0,i1 list0; i2,i3 list1; i4 cond expr; p0 reward p1 reset_steps; p2 > 0: the
@@ -301,7 +319,7 @@ enum {
   MOOG_X_ADD, MOOG_X_SUB, MOOG_X_MUL, MOOG_X_DIV, MOOG_X_NEG, MOOG_X_ABS,
   MOOG_X_MOD,        /* python float modulo                                  */
   MOOG_X_STORE,      /* pop -> attribute `arg` of sprite 0 (modifier programs).  c: for `angle` the NumPy kind of
-                        the value (sprite.py:531-540); for `x_vel` / `y_vel` 3 = the components of a FRESH float64
+                        the value (sprite.py:531-540; 4 = whatever kind the angle has now); for `x_vel` / `y_vel` 3 = the components of a FRESH float64
                         array (`s.velocity = np.zeros(2)`, sprite.py:639-643): MOOG_SF_VEL32 and the alias id go */
   MOOG_X_STORE_POS,  /* pop y, pop x -> sprite 0 `.position = (x, y)`: one translation of the cached
                         outline (sprite.py:616-633) */

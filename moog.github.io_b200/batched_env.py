@@ -291,7 +291,8 @@ class BatchedEnvironment(object):
         self.state_initializer = state_initializer
         self.num_envs = int(num_envs)
         config = dict(state_initializer=state_initializer, physics=physics, task=task,
-                      action_space=action_space, observers=observers, game_rules=game_rules)
+                      action_space=action_space, observers=observers, game_rules=game_rules,
+                      meta_state_initializer=meta_state_initializer)
         if initial_states is None:
             pool_size = int(pool_size or min(self.num_envs, 256))
             initial_states = [state_initializer() for _ in range(pool_size)]

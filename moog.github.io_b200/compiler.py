@@ -55,6 +55,8 @@ H_LAYER_OFF = 32
 H_N_VTX = 49
 H_RESET, H_N_RESET, H_N_DPOOL, H_SHAPE_TAB = 51, 52, 53, 54
 H_N_META, H_META_OFF = 55, 56
+H_N_METAVAR, H_METAVAR_OFF, H_METAVAR_INIT = 57, 58, 59
+MAX_META_VARS = 16
 
 F_DRAG, F_KINETIC_FRICTION, F_DOWN_GRAVITY, F_GRAVITY, F_RANDOM, \
     F_DIST_LINEAR, F_DIST_SPRING, F_COLLISION, F_MAZE_WALK = range(1, 10)
@@ -62,8 +64,9 @@ C_TETHER, C_TETHER_ZIPPED, C_CONSTANT_SPEED, C_MAZE_PHYSICS = 32, 33, 34, 35
 R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
     R_MODIFY_SPRITES, R_COND_BEGIN, R_TIMED_BEGIN, R_KEEP_NEAR_CENTER = 64, 65, 66, 67, 68, 69, 70
 R_PORTAL, R_CHANGE_LAYER, R_CREATE_SPRITES, R_TREE = 71, 72, 73, 74
+R_FIXATION, R_PHASESEQ_BEGIN, R_PHASE_BEGIN, R_PHASE_END = 75, 76, 77, 78
 # rule classes of the reference that keep Python-side state the tracer must not guess at
-_RULES_OF_THE_REFERENCE_NOT_LOWERED = ('Fixation', 'ModifyMetaState', 'UpdateMetaStateValue', 'Phase', 'PhaseSequence')
+_RULES_OF_THE_REFERENCE_NOT_LOWERED = ('ModifyMetaState', 'UpdateMetaStateValue')
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
@@ -118,6 +121,11 @@ class Program(object):
         self.ipool = []
         self.expr = []           # list of (op, arg, c)
         self.dpool = []          # doubles: shape table / sampler parameters of the reset sampler
+        self.meta_vars = collections.OrderedDict()   # env `meta_state[key]` -> envf slot (numbers; strings as codes)
+        self.meta_var_init = {}  # key -> value after meta_state_initializer()
+        self.meta_var_off = -1   # envf offset of the block reserved for them
+        self.strings = []        # interned strings (phase names ...): code = index + 1
+        self.duration_draws = [] # (rule-noise column, lo, hi) of every Phase whose duration is np.random.randint(lo, hi)
         self.meta_keys = []      # `sprite.metadata[key]` columns the callables read (lambdas.metadata_columns)
         self.meta_off = 0        # envf offset of column 0 (column k of slot s: meta_off + k * n_slots + s)
         self.z_shape_ids = {}    # device sampler: shape candidate -> index of its shape record
@@ -172,6 +180,22 @@ class Program(object):
             self.maze_offsets[layer] = self.alloc_envf(host_maze.MAZE_WORDS)
         return self.maze_offsets[layer]
 
+    def intern(self, text):
+        """Code of a string the env's meta_state holds or is compared with."""
+        if text not in self.strings:
+            self.strings.append(text)
+        return float(self.strings.index(text) + 1)
+
+    def meta_slot(self, key):
+        """envf slot of meta_state[key] (a block of MAX_META_VARS slots is reserved on first use)."""
+        if key not in self.meta_vars:
+            if self.meta_var_off < 0:
+                self.meta_var_off = self.alloc_envf(MAX_META_VARS)
+            if len(self.meta_vars) >= MAX_META_VARS:
+                raise CompileError('at most {} meta_state entries are carried on the device'.format(MAX_META_VARS))
+            self.meta_vars[key] = self.meta_var_off + len(self.meta_vars)
+        return self.meta_vars[key]
+
     def alloc_envf(self, n):
         start = self.n_envf
         self.n_envf += n
@@ -194,6 +218,14 @@ class Program(object):
     @property
     def n_vtx(self):
         return self.voff[-1]
+
+    def meta_values(self):
+        """The meta_state variables right after meta_state_initializer() (0 for keys only rules create)."""
+        out = []
+        for key in self.meta_vars:
+            v = self.meta_var_init.get(key, 0.0)
+            out.append(self.intern(v) if isinstance(v, str) else float(v))
+        return out
 
     def finalize(self):
         hdr = np.zeros(HDR_WORDS, dtype='<i4')
@@ -250,6 +282,12 @@ class Program(object):
         hdr[H_SHAPE_TAB] = getattr(self, 'shape_tab', 0)
         hdr[H_N_META] = len(self.meta_keys)
         hdr[H_META_OFF] = self.meta_off
+        if self.meta_vars:
+            hdr[H_N_METAVAR] = len(self.meta_vars)
+            hdr[H_METAVAR_OFF] = self.meta_var_off
+            hdr[H_METAVAR_INIT] = len(self.dpool)
+            self.dpool.extend(self.meta_values())
+            hdr[H_N_DPOOL] = len(self.dpool)
         dpool = np.array(self.dpool, dtype='<f8')
         blob = hdr.tobytes() + ops.tobytes() + ipool.tobytes() + expr.tobytes() + dpool.tobytes()
         hdr[H_BYTES] = len(blob)
@@ -559,6 +597,23 @@ def _rule_specs(prog, rule, out, depth=0):
         code = lambdas.compile_sprite_predicate(rule._filter_fn)
         out.append(dict(kind=R_CHANGE_LAYER, i=(prog.layer_index(rule._old_layer), prog.layer_index(rule._new_layer),
                                                 prog.add_expr(code))))
+    elif k == 'Fixation':
+        out.append(dict(kind=R_FIXATION, i=(prog.layer_index(rule._agent_layer), prog.layer_index(rule._fixation_layer),
+                                            prog.meta_slot(rule._meta_state_fixation_key)),
+                        p=(float(rule._fixation_threshold),)))
+    elif k == 'Phase':
+        _phase_specs(prog, rule, out, depth, seq=-1, index=0)
+    elif k == 'PhaseSequence':
+        phases = list(rule._phases)
+        if not phases or any(_kind(ph) != 'Phase' for ph in phases):
+            raise CompileError('PhaseSequence takes Phase instances')
+        seq = prog.alloc_envf(2)          # current phase index, its value when the pass began
+        name_slot = prog.meta_slot(rule._meta_state_key) if rule._meta_state_key is not None else -1
+        names = len(prog.dpool)
+        prog.dpool.extend(prog.intern(ph.name) for ph in phases)
+        out.append(dict(kind=R_PHASESEQ_BEGIN, i=(seq, len(phases), name_slot, 0, names)))
+        for index, ph in enumerate(phases):
+            _phase_specs(prog, ph, out, depth, seq=seq, index=index, name_slot=name_slot, names=names, n_phases=len(phases))
     elif k == 'CreateSprites':
         # create_sprites.py:27-34; the generator's recipe is sampled on the device (Philox), like a reset group
         gen = _Recipe(rule._generator)
@@ -589,6 +644,50 @@ def _rule_specs(prog, rule, out, depth=0):
     else:
         raise CompileError(
             'game rule {} is not on the accelerated path'.format(k))
+
+
+def _phase_specs(prog, phase, out, depth, seq, index, name_slot=-1, names=0, n_phases=0):
+    """task_phases.py:18-95: MOOG_R_PHASE_BEGIN, [a MOOG_R_COND_BEGIN on `step_count == 0` around the
+    one-time rules], the continual rules, MOOG_R_PHASE_END."""
+    if depth + 2 > MAX_COND_DEPTH:
+        raise CompileError('phases nested deeper than {} blocks are not on the accelerated path'.format(MAX_COND_DEPTH))
+    base = prog.alloc_envf(3)             # should_end, step_count, duration
+    duration = phase._duration
+    drawn = lambdas.randint_range(duration) if callable(duration) else None
+    col, fixed, lo, hi = 0, 0.0, 0.0, 0.0
+    if drawn is not None:
+        lo, hi = float(drawn[0]), float(drawn[1])
+        col = prog.rule_noise_dim
+        prog.rule_noise_dim += 1
+        prog.duration_draws.append((col, drawn[0], drawn[1]))
+    else:
+        try:
+            with lambdas.no_randomness('Phase duration'):
+                fixed = float(duration() if callable(duration) else duration)
+        except lambdas.ImpureCallable:
+            raise CompileError('a random Phase duration is only lowered when it is `np.random.randint(lo, hi)`')
+    once, always = [], []
+    for r in phase._one_time_rules:
+        _rule_specs(prog, r, once, depth + 2)
+    for r in phase._continual_rules:
+        _rule_specs(prog, r, always, depth + 1)
+    block = []
+    if once:
+        first = prog.add_expr([(lambdas.X_ENVF, base + 1, 0.0), (lambdas.X_CONST, 0, 0.0), (lambdas.X_EQ, 0, 0.0)])
+        first_op = prog.emit(SC_TREE, 0, (prog.add_ints([0, first, -1, 0, -1, 0, 0, 0]), 1))
+        block.append(dict(kind=R_COND_BEGIN, i=[first_op, len(once)]))
+        block += once
+    block += always
+    end = lambdas._unwrap(phase._end_condition, 'end_condition')  # pylint: disable=protected-access
+    never = False
+    try:
+        never = end(None, None) is False
+    except Exception:  # pylint: disable=broad-except
+        never = False
+    block.append(dict(kind=R_PHASE_END, i=[-1, base, seq, name_slot, names, n_phases], p=(float(index),),
+                      **({} if never else {'cond': end})))
+    out.append(dict(kind=R_PHASE_BEGIN, i=(seq, len(block), index, base, col), p=(fixed, lo, hi)))
+    out.extend(block)
 
 
 def _layer_moves(rules):
@@ -777,6 +876,18 @@ def compile_config(config, sample_states, layer_capacity=None, reset_sampler=Fal
             voff.append(voff[-1] + vc)
     prog.voff = voff
 
+    meta_init = config.get('meta_state_initializer')
+    meta_init = meta_init() if callable(meta_init) else meta_init
+    if meta_init is not None:
+        # environment.py:86: a fresh meta_state per episode.  A dict of numbers / strings becomes variables
+        # of the env's record; anything else has no device form
+        if not isinstance(meta_init, dict):
+            raise CompileError('meta_state must be None or a dict of numbers / strings on the device path')
+        for key, value in meta_init.items():
+            if not (isinstance(value, (bool, int, float, str)) or hasattr(value, '__float__')):
+                raise CompileError('meta_state[{!r}] = {!r}: only numbers and strings are carried on the device'.format(key, value))
+            prog.meta_var_init[key] = value if isinstance(value, str) else float(value)
+            prog.meta_slot(key)
     with lambdas.metadata_columns(prog.meta_keys):
         _compile_physics(prog, config['physics'])
         _compile_tasks(prog, config['task'])
@@ -1289,6 +1400,9 @@ def pack_states(prog, states, shape_table=None):
         for e, st in enumerate(states):
             for layer, off in prog.maze_offsets.items():
                 envf[e, off:off + host_maze.MAZE_WORDS] = host_maze.maze_record(st[layer])
+    if getattr(prog, 'meta_vars', None):     # the env's meta_state variables as meta_state_initializer() leaves them
+        values = prog.meta_values()
+        envf[:, prog.meta_var_off:prog.meta_var_off + len(values)] = values
     meta_keys = getattr(prog, 'meta_keys', None)
     if meta_keys:
         # sprite.metadata[key] for the keys the program's callables read; NaN where a sprite has no such

@@ -100,6 +100,10 @@ int moog_program_validate(const void *blob, size_t nbytes) {
   if (hdr[MOOG_H_N_META] < 0 || hdr[MOOG_H_N_META] > MOOG_MAX_META ||
       (hdr[MOOG_H_N_META] > 0 && (hdr[MOOG_H_META_OFF] < 0 || (long long)hdr[MOOG_H_META_OFF] + (long long)hdr[MOOG_H_N_META] * S > NF)))
     return MOOG_E_INVAL;
+  if (hdr[MOOG_H_N_METAVAR] < 0 ||
+      (hdr[MOOG_H_N_METAVAR] > 0 && (hdr[MOOG_H_METAVAR_OFF] < 0 || (long long)hdr[MOOG_H_METAVAR_OFF] + hdr[MOOG_H_N_METAVAR] > NF ||
+                                     hdr[MOOG_H_METAVAR_INIT] < 0 || (long long)hdr[MOOG_H_METAVAR_INIT] + hdr[MOOG_H_N_METAVAR] > ND)))
+    return MOOG_E_INVAL;
   // layers partition the slots
   if (hdr[MOOG_H_LAYER_OFF] != 0 || hdr[MOOG_H_LAYER_OFF + L] != S) return MOOG_E_INVAL;
   for (int l = 0; l < L; ++l)
@@ -220,6 +224,19 @@ int moog_program_validate(const void *blob, size_t nbytes) {
       case MOOG_SC_BINARY: ok = cond_ok(op.i[0]) && cond_ok(op.i[1]); break;
       case MOOG_SC_NOT: ok = cond_ok(op.i[0]); break;
       case MOOG_SC_BERNOULLI: ok = op.i[0] >= 0 && op.i[0] < hdr[MOOG_H_RULE_NOISE_DIM]; break;
+      case MOOG_R_FIXATION: ok = layer_ok(op.i[0]) && layer_ok(op.i[1]) && envf_ok(op.i[2], 1); break;
+      case MOOG_R_PHASESEQ_BEGIN:
+        ok = envf_ok(op.i[0], 2) && op.i[1] >= 1 && (op.i[2] == -1 || envf_ok(op.i[2], 1)) && op.i[4] >= 0 &&
+             (long long)op.i[4] + op.i[1] <= ND;
+        break;
+      case MOOG_R_PHASE_BEGIN:
+        ok = (op.i[0] == -1 || envf_ok(op.i[0], 2)) && op.i[1] >= 1 && (long long)o + 1 + op.i[1] <= NO && envf_ok(op.i[3], 3) &&
+             op.i[4] >= 0 && (!(op.p[2] > op.p[1]) || op.i[4] < hdr[MOOG_H_RULE_NOISE_DIM]);
+        break;
+      case MOOG_R_PHASE_END:
+        ok = (op.i[0] == -1 || cond_ok(op.i[0])) && envf_ok(op.i[1], 3) && (op.i[2] == -1 || envf_ok(op.i[2], 2)) &&
+             (op.i[3] == -1 || envf_ok(op.i[3], 1)) && op.i[4] >= 0 && op.i[5] >= 0 && (long long)op.i[4] + op.i[5] <= ND;
+        break;
       case MOOG_SC_TREE: ok = tree_ok(op.i[0], op.i[1], false); break;
       case MOOG_R_TREE:
         ok = tree_ok(op.i[0], op.i[1], true) && op.i[3] >= 0 && (op.i[3] == 0 || envf_ok(op.i[2], op.i[3])) && op.i[4] >= 0 &&

@@ -2487,7 +2487,8 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
       case MOOG_X_STORE: {
         double v = st[--sp];
         if (x->arg == MOOG_AT_ANGLE) {  // sprite.py:531-540; x->c: NumPy kind of the assigned value
-          set_angle_f64(e, s0, v, (int)x->c);
+          // (c = 4: computed from the sprite's own angle and python floats only -- the NumPy kind it has stays)
+          set_angle_f64(e, s0, v, x->c == 4.0 ? ((META(e, MOOG_M_FLAGS, s0) >> MOOG_SF_ANG_SHIFT) & 3) : (int)x->c);
           break;
         }
         wsync();
@@ -3009,6 +3010,50 @@ __device__ __noinline__ void rule_leaf(const Env &, int r) {
       }
       return;
     }
+    case MOOG_R_FIXATION: {  // fixation.py:45-54
+      if (e.cnt[op->i[0]] < 1 || e.cnt[op->i[1]] < 1) {  // state[layer][0]: IndexError
+        const int err = e.envi[MOOG_EI_ERR] | MOOG_ERR_BAD_INDEX;
+        wsync();
+        puti(e, &e.envi[MOOG_EI_ERR], err);
+        wsync();
+        return;
+      }
+      const int sa = LOFF(e, op->i[0]), st2 = LOFF(e, op->i[1]);
+      const double dist = norm1(DYN(e, MOOG_D_X, sa) - DYN(e, MOOG_D_X, st2), DYN(e, MOOG_D_Y, sa) - DYN(e, MOOG_D_Y, st2));
+      const double count = dist < op->p[0] ? e.envf[op->i[2]] + 1 : 0.0;
+      wsync();
+      put(e, &e.envf[op->i[2]], count);
+      wsync();
+      return;
+    }
+    case MOOG_R_PHASESEQ_BEGIN: {  // task_phases.py:126-141: the phase that is current when the pass begins is stepped
+      const double now = e.envf[op->i[0]];
+      wsync();
+      put(e, &e.envf[op->i[0] + 1], now);
+      wsync();
+      return;
+    }
+    case MOOG_R_PHASE_END: {  // task_phases.py:90-95, 133-141
+      const double count = e.envf[op->i[1] + 1] + 1;
+      wsync();
+      put(e, &e.envf[op->i[1] + 1], count);
+      wsync();
+      if (count >= e.envf[op->i[1] + 2] || (op->i[0] >= 0 && eval_condition(e, op->i[0]) != 0)) {
+        wsync();
+        put(e, &e.envf[op->i[1]], 1.0);
+        if (op->i[2] >= 0) {
+          const double next = e.envf[op->i[2]] + 1;
+          const int ind = (int)next;
+          put(e, &e.envf[op->i[2]], next);
+          if (ind >= op->i[5])
+            puti(e, &e.envi[MOOG_EI_ERR], e.envi[MOOG_EI_ERR] | MOOG_ERR_BAD_INDEX);  // self._phases[ind]: IndexError
+          else if (op->i[3] >= 0)
+            put(e, &e.envf[op->i[3]], e.dpool[op->i[4] + ind]);
+        }
+        wsync();
+      }
+      return;
+    }
     case MOOG_R_TREE:  // a user-defined rule's step(), path by path
       walk_tree(e, e.ipool + op->i[0], op->i[1]);
       return;
@@ -3153,9 +3198,11 @@ __device__ __noinline__ void rules_step(const Env &) {
     }
     if (depth == 0 && r >= end) break;
     const moog_op *op = e.ops + r;
-    if (op->kind == MOOG_R_COND_BEGIN || op->kind == MOOG_R_TIMED_BEGIN) {
+    if (op->kind == MOOG_R_COND_BEGIN || op->kind == MOOG_R_TIMED_BEGIN || op->kind == MOOG_R_PHASE_BEGIN) {
       int times;
-      if (op->kind == MOOG_R_TIMED_BEGIN) {  // timing.py:50-56; the guarded rules never read the countdowns
+      if (op->kind == MOOG_R_PHASE_BEGIN) {  // task_phases.py:79-95: not ended, and the sequence's current phase
+        times = (e.envf[op->i[3]] == 0 && (op->i[0] < 0 || e.envf[op->i[0] + 1] == (double)op->i[2])) ? 1 : 0;
+      } else if (op->kind == MOOG_R_TIMED_BEGIN) {  // timing.py:50-56; the guarded rules never read the countdowns
         const double c0 = e.envf[op->i[2]], c1 = e.envf[op->i[2] + 1];
         times = (c0 <= 0 && c1 > 0) ? 1 : 0;
         wsync();
@@ -3422,6 +3469,11 @@ __device__ inline void post_reset(const Env &e) {
   puti(e, &e.envi[MOOG_EI_STEP_COUNT], 0);
   puti(e, &e.envi[MOOG_EI_RESET_NEXT], 0);
   wsync();
+  {  // environment.py:86: meta_state = meta_state_initializer() -- its entries are variables of the record
+    const int32_t *h = e.hdr;
+    for (int q = e.lane; q < h[MOOG_H_N_METAVAR]; q += 32) e.envf[h[MOOG_H_METAVAR_OFF] + q] = e.dpool[h[MOOG_H_METAVAR_INIT] + q];
+    wsync();
+  }
   tasks_reset(e);
   actions_reset(e);
   {  // AbstractRule.reset of the rules that keep state: TimedRule re-arms its interval (timing.py:45-48)
@@ -3435,6 +3487,23 @@ __device__ inline void post_reset(const Env &e) {
       }
       if (op->kind == MOOG_R_PORTAL)  // portal.py:36-39: _currently_teleporting = set()
         for (int s2 = e.lane; s2 < e.S; s2 += 32) META(e, MOOG_M_FLAGS, s2) &= ~MOOG_SF_TELEPORTING;
+      if (op->kind == MOOG_R_FIXATION) put(e, &e.envf[op->i[2]], 0.0);  // fixation.py:41-43
+      if (op->kind == MOOG_R_PHASESEQ_BEGIN) {  // task_phases.py:118-124
+        put(e, &e.envf[op->i[0]], 0.0);
+        put(e, &e.envf[op->i[0] + 1], 0.0);
+        if (op->i[2] >= 0) put(e, &e.envf[op->i[2]], e.dpool[op->i[4]]);
+      }
+      if (op->kind == MOOG_R_PHASE_BEGIN) {  // task_phases.py:71-77: the duration is drawn anew
+        double dur = op->p[0];
+        if (op->p[2] > op->p[1]) {  // np.random.randint(p1, p2)
+          const int lo = (int)op->p[1], hi = (int)op->p[2];
+          const int d = lo + (int)(rule_noise_at(e, op->i[4]) * (double)(hi - lo));
+          dur = d >= hi ? hi - 1 : d;
+        }
+        put(e, &e.envf[op->i[3]], 0.0);
+        put(e, &e.envf[op->i[3] + 1], 0.0);
+        put(e, &e.envf[op->i[3] + 2], dur);
+      }
       if (op->kind == MOOG_R_TREE)  // the rule's own reset(): its attributes back to their first values
         for (int q = e.lane; q < op->i[3]; q += 32) e.envf[op->i[2] + q] = e.dpool[op->i[4] + q];
     }

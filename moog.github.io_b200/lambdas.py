@@ -419,6 +419,75 @@ class SymState(object):
         return _SymLayer(self, name)
 
 
+class SymMetaValue(Sym):
+    """`meta_state[key]` while tracing: a variable of the env (envf slot); strings compare by their codes."""
+
+    __slots__ = ('prog',)
+    __hash__ = None
+
+    def __init__(self, code, prog):
+        Sym.__init__(self, code)
+        self.prog = prog
+
+    def _bin(self, other, op, swap=False):
+        if isinstance(other, str):
+            other = self.prog.intern(other)
+        return Sym._bin(self, other, op, swap)
+
+
+class SymMetaState(object):
+    """The env's `meta_state` dict while a state-level callable is traced: reads are reads of the env's
+    variables; writes (only where effects are allowed) are recorded as effects of the path."""
+
+    def __init__(self, prog, owner=None):
+        self._prog, self._owner = prog, owner
+
+    def __getitem__(self, key):
+        if self._owner is not None and ('meta', key) in self._owner.shadow:
+            return self._owner.shadow[('meta', key)]
+        return SymMetaValue([(X_ENVF, self._prog.meta_slot(key), 0.0)], self._prog)
+
+    def __setitem__(self, key, value):
+        owner = self._owner
+        if owner is None or owner.effects is None:
+            raise LoweringError('this callable may not modify meta_state')
+        if isinstance(value, str):
+            value = self._prog.intern(value)
+        value = Sym.lift(value)
+        owner.shadow[('meta', key)] = value
+        owner.effects.append(('var', self._prog.meta_slot(key), value))
+
+    def __contains__(self, key):
+        return key in self._prog.meta_vars
+
+    def get(self, key, default=None):
+        return self[key] if key in self._prog.meta_vars else default
+
+
+def randint_range(fn):
+    """`fn` of the form `lambda: np.random.randint(lo, hi)` -> (lo, hi); any other callable -> None.
+    (Phase durations, task_phases.py:60-63; sprite counts, sprite_generators.py.)"""
+    calls = []
+    real = np.random.randint
+
+    def _randint(low, high=None, size=None, **kwargs):
+        if size is not None or kwargs:
+            return real(low, high, size, **kwargs)
+        lo, hi = (0, low) if high is None else (low, high)
+        calls.append((int(lo), int(hi)))
+        return int(hi) - 1
+    np.random.randint = _randint
+    try:
+        value = fn()
+    except Exception:  # pylint: disable=broad-except
+        return None
+    finally:
+        np.random.randint = real
+    if len(calls) == 1 and value == calls[0][1] - 1 and calls[0][1] > calls[0][0]:
+        return calls[0]
+    return None
+
+
 class BoundSprite(SymSprite):
     """A sprite picked out of the state by a state-level callable.  Reads see what the callable itself
     assigned earlier on this path; assignments are recorded as effects of the path (a rule's `step`)."""
@@ -616,18 +685,24 @@ def _emit_tree(tree, state, prog, what, with_value):
 
 
 def state_tree(fn, prog, what):
-    """A state-level callable `fn(state)` made of single-sprite picks, attribute / metadata reads, overlap
-    tests and `if`s -> index of a MOOG_SC_TREE op: a decision tree evaluated lazily, test by test, in the
-    order Python would make them (so the overlap calls are the reference's, call for call)."""
+    """A state-level callable `fn(state[, meta_state])` made of single-sprite picks, attribute / metadata /
+    meta_state reads, overlap tests and `if`s -> index of a MOOG_SC_TREE op: a decision tree evaluated
+    lazily, test by test, in the order Python would make them (so the overlap calls are the reference's,
+    call for call)."""
     state = BoundState(prog)
     call = fn
     try:
         call = _rewritten(fn)
     except Exception:  # pylint: disable=broad-except
         call = fn
+    try:
+        arity = _n_params(fn)
+    except (TypeError, ValueError):
+        arity = 1
+    args = (state,) if arity < 2 else (state, SymMetaState(prog))
     with no_randomness(what):
         try:
-            tree = _explore_tree(call, (state,), hooks=(state.begin_path, lambda: []))
+            tree = _explore_tree(call, args, hooks=(state.begin_path, lambda: []))
         except LoweringError:
             raise
         except Exception as exc:  # pylint: disable=broad-except
@@ -711,7 +786,7 @@ def trace_rule(rule, prog):
             return effects
 
         def call(st):
-            out = cls.step(holder['proxy'], st, None)
+            out = cls.step(holder['proxy'], st, SymMetaState(prog, st))
             if out is not None:
                 raise LoweringError('{}.step returns a value'.format(what))
 
@@ -728,7 +803,7 @@ def trace_rule(rule, prog):
     def assigned_names(tree, out):
         if tree[0] == 'leaf':
             for e in tree[2]:
-                if e[0] == 'var' and e[3] not in out:
+                if e[0] == 'var' and len(e) > 3 and e[3] not in out:
                     out.append(e[3])
         else:
             assigned_names(tree[2], out)
@@ -1003,8 +1078,14 @@ def _stores_to_code(stores):
             continue
         # c: NumPy kind of the stored value as far as the device tracks it (angle: a pure constant is a
         # python float, anything computed from sprite factors counts as np.float64)
-        has_attr = any(op in (X_ATTR0, X_ATTR1) for op, _, _ in value.code)
-        code += value.code + [(X_STORE, ATTRS.index(name), 2.0 if has_attr else 0.0)]
+        reads = {ATTRS[arg & 0xff] if (arg & 0xff) < len(ATTRS) else 'metadata'
+                 for op, arg, _ in value.code if op in (X_ATTR0, X_ATTR1)}
+        weak = {'scale', 'aspect_ratio', 'mass', 'c0', 'c1', 'c2', 'opacity'}     # python numbers in the reference's Sprite
+        if name == 'angle' and reads and reads <= weak | {'angle'} and 'angle' in reads:
+            kind = 4.0      # `s.angle = s.angle + 0.5 * np.pi`: stays what the angle is (a python float at birth)
+        else:
+            kind = 2.0 if reads else 0.0
+        code += value.code + [(X_STORE, ATTRS.index(name), kind)]
     # Leave a value on the stack so the VM has a defined result.
     return code + [(X_CONST, 0, 1.0)]
 
@@ -1362,6 +1443,12 @@ def compile_state_condition(cond, prog):
     declared = getattr(cond, 'moog_b200_condition', None)
     if declared is not None:
         return declared(prog)
+    try:
+        takes_meta = _n_params(cond) >= 2
+    except (TypeError, ValueError):
+        takes_meta = False
+    if takes_meta:      # (state, meta_state): the env's meta_state entries are variables of the record
+        return state_tree(cond, prog, 'state condition {}'.format(getattr(cond, '__name__', cond)))
     node = _lambda_ast(cond)
     body = node.body
     if isinstance(body, list):  # def: single `return <expr>`

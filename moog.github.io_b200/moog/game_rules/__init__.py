@@ -178,6 +178,44 @@ class CreateSprites(AbstractRule):
         self._without_overlapping = without_overlapping
 
 
+class Fixation(AbstractRule):
+    """Counts in `meta_state[meta_state_fixation_key]` for how many consecutive steps the first sprite of
+    `agent_layer` has been within `fixation_threshold` of the first sprite of `fixation_layer`
+    (fixation.py:19-54)."""
+
+    def __init__(self, agent_layer, fixation_layer, fixation_threshold=0.1,
+                 meta_state_fixation_key='fixation_duration'):
+        self._agent_layer = agent_layer
+        self._fixation_layer = fixation_layer
+        self._fixation_threshold = fixation_threshold
+        self._meta_state_fixation_key = meta_state_fixation_key
+
+
+class Phase(AbstractRule):
+    """`one_time_rules` on its first step, `continual_rules` on every step, until `duration` steps have
+    passed or `end_condition(state[, meta_state])` holds (task_phases.py:18-95)."""
+
+    def __init__(self, one_time_rules=(), continual_rules=(), end_condition=None, duration=np.inf, name=''):
+        self._one_time_rules = one_time_rules if isinstance(one_time_rules, (list, tuple)) else (one_time_rules,)
+        self._continual_rules = continual_rules if isinstance(continual_rules, (list, tuple)) else (continual_rules,)
+        self._end_condition = end_condition if end_condition is not None else (lambda state, meta_state: False)
+        self._duration = duration if callable(duration) else (lambda: duration)
+        self._name = name
+
+    @property
+    def name(self):
+        return self._name
+
+
+class PhaseSequence(AbstractRule):
+    """Phases stepped one after the other; `meta_state[meta_state_phase_name_key]` names the current one
+    (task_phases.py:98-141)."""
+
+    def __init__(self, *single_phases, meta_state_phase_name_key=None):
+        self._phases = single_phases
+        self._meta_state_key = meta_state_phase_name_key
+
+
 def _out_of_scope(name, where):
     def _ctor(*args, **kwargs):
         raise NotImplementedError(
@@ -188,9 +226,6 @@ def _out_of_scope(name, where):
     return _ctor
 
 
-Fixation = _out_of_scope('Fixation', 'fixation.py')
 ModifyMetaState = _out_of_scope('ModifyMetaState', 'modify_meta_state.py')
 UpdateMetaStateValue = _out_of_scope(
     'UpdateMetaStateValue', 'modify_meta_state.py')
-Phase = _out_of_scope('Phase', 'task_phases.py')
-PhaseSequence = _out_of_scope('PhaseSequence', 'task_phases.py')

@@ -104,6 +104,10 @@ SCENES = {
     # an overlap test over a layer, mass / colour changes applied and reverted 60 steps later), Portal,
     # RandomForce, DistanceForce; the agent is steered into a booster, then after the prey
     'functional_maze': ('moog_demos.example_configs.functional_maze', None, 127, 130, 10),
+    # a shipped config built on PhaseSequence / Phase (end conditions on meta_state, a duration drawn with
+    # np.random.randint at reset), two Fixation rules, a dict meta_state whose 'phase' entry the Reset task
+    # reads, a rule class of its own, SetPosition, TetherZippedLayers; the agent fixates the cross, then target 0
+    'multi_tracking': ('moog_demos.example_configs.multi_tracking_with_feature', 3, 22, 220, 10),
 }
 
 
@@ -153,6 +157,13 @@ def _booster_action(env, t):
     d = min(d, key=lambda v: float(np.dot(v, v)))
     n = float(np.linalg.norm(d))
     return d / n if n > 0 else np.zeros(2)
+
+
+def _fixate_action(env, t):
+    """multi_tracking_with_feature: SetPosition on the fixation cross while it exists, then on target 0."""
+    del t
+    target = env.state['fixation'][0] if env.state['fixation'] else env.state['targets'][0]
+    return np.array(target.position, dtype=np.float64)
 
 
 def _pacman_action(env, t):
@@ -227,7 +238,26 @@ def generate(name, out_dir):
     prog = compiler.compile_config(config, samples)
     init = compiler.pack_states(prog, [init_state])
     env.state_initializer = lambda: init_state
-    ts = env.reset()
+    # Phase durations drawn as np.random.randint(lo, hi) in Phase.reset (task_phases.py:71-77): the outcome d
+    # is replayed through the phase's rule-noise column as a uniform u with lo + int(u * (hi - lo)) == d
+    reset_draws = []
+    real_randint = np.random.randint
+
+    def _reset_randint(low, high=None, size=None, **kwargs):
+        out = real_randint(low, high, size, **kwargs)
+        if size is None and not kwargs:
+            reset_draws.append(int(out))
+        return out
+    np.random.randint = _reset_randint
+    try:
+        ts = env.reset()
+    finally:
+        np.random.randint = real_randint
+    reset_rule_noise = np.zeros(max(prog.rule_noise_dim, 1))
+    assert len(reset_draws) == len(prog.duration_draws), (reset_draws, prog.duration_draws)
+    for d, (col, lo, hi) in zip(reset_draws, prog.duration_draws):
+        assert lo <= d < hi
+        reset_rule_noise[col] = (d - lo + 0.5) / (hi - lo)
     table = init['shape_table']
     after_reset = compiler.pack_states(prog, [env.state], table)
     renderer = config.get('observers', {}).get('image')
@@ -326,6 +356,8 @@ def generate(name, out_dir):
             action = _pacman_action(env, t)
         elif name == 'functional_maze':
             action = _booster_action(env, t)
+        elif name == 'multi_tracking':
+            action = _fixate_action(env, t)
         elif name == 'bounce_box':
             action = 4 if t < 25 else 0             # wait, then walk into the left response box
         elif name == 'predict_zoo':
@@ -406,6 +438,8 @@ def generate(name, out_dir):
         out['reset_' + k] = after_reset[k][0]
     for k, v in rec.items():
         out[k] = np.array(v)
+    if prog.duration_draws:
+        out['reset_rule_noise'] = reset_rule_noise
     path = os.path.join(out_dir, name + '.npz')
     if os.environ.get('MOOG_GOLDEN_BIG_ONLY'):
         # big-canvas frames only, for states the main fixture already holds

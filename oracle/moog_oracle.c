@@ -1488,8 +1488,10 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
       case MOOG_X_STORE: {
         const double v = st[--sp];
         if (x->arg == MOOG_AT_ANGLE) { /* sprite.py:531-540; x->c: kind of the assigned value */
+          const int kept = (META(e, MOOG_M_FLAGS, s0) >> MOOG_SF_ANG_SHIFT) & 3;
           set_angle(e, s0, v, 0);
-          set_ang_kind(e, s0, (int)x->c);
+          /* c = 4: computed from the sprite's own angle and python floats only -- the NumPy kind it has stays */
+          set_ang_kind(e, s0, x->c == 4.0 ? kept : (int)x->c);
         } else {
           *attr_ptr(e, s0, x->arg) = v;
           if (x->arg == MOOG_AT_SCALE || x->arg == MOOG_AT_ASPECT_RATIO) set_path(e, s0);
@@ -2014,6 +2016,47 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
       vanish(e, lo, gone);
       return 1;
     }
+    case MOOG_R_FIXATION: { /* fixation.py:45-54 */
+      double *count = e->envf + op->i[2];
+      if (e->cnt[op->i[0]] < 1 || e->cnt[op->i[1]] < 1) { /* state[layer][0]: IndexError */
+        e->envi[MOOG_EI_ERR] |= MOOG_ERR_BAD_INDEX;
+        return 1;
+      }
+      const int a = LOFF(e, op->i[0]), t = LOFF(e, op->i[1]);
+      const double dist = norm1(DYN(e, MOOG_D_X, a) - DYN(e, MOOG_D_X, t), DYN(e, MOOG_D_Y, a) - DYN(e, MOOG_D_Y, t));
+      *count = dist < op->p[0] ? *count + 1 : 0;
+      return 1;
+    }
+    case MOOG_R_PHASESEQ_BEGIN: /* task_phases.py:126-141: the phase that is current when the pass begins is stepped */
+      e->envf[op->i[0] + 1] = e->envf[op->i[0]];
+      return 1;
+    case MOOG_R_PHASE_BEGIN: { /* task_phases.py:79-95 */
+      const int nsub = op->i[1];
+      const double *ph = e->envf + op->i[3];
+      const int active = ph[0] == 0 && (op->i[0] < 0 || e->envf[op->i[0] + 1] == (double)op->i[2]);
+      if (active) {
+        int q = r + 1;
+        while (q < r + 1 + nsub) q += rule_step(e, q, rule_noise);
+      }
+      return 1 + nsub;
+    }
+    case MOOG_R_PHASE_END: { /* task_phases.py:90-95, 133-141 */
+      double *ph = e->envf + op->i[1];
+      ph[1] += 1;
+      if (ph[1] >= ph[2] || (op->i[0] >= 0 && eval_condition(e, op->i[0]) != 0)) {
+        ph[0] = 1;
+        if (op->i[2] >= 0) {
+          double *seq = e->envf + op->i[2];
+          seq[0] += 1;
+          const int ind = (int)seq[0];
+          if (ind >= op->i[5])
+            e->envi[MOOG_EI_ERR] |= MOOG_ERR_BAD_INDEX; /* self._phases[ind]: IndexError */
+          else if (op->i[3] >= 0)
+            e->envf[op->i[3]] = e->dpool[op->i[4] + ind];
+        }
+      }
+      return 1;
+    }
     case MOOG_R_TREE: /* a user-defined rule's step(), path by path */
       walk_tree(e, e->ipool + op->i[0], op->i[1]);
       return 1;
@@ -2042,6 +2085,12 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
   return 1;
 }
 
+/* environment.py:86: meta_state = meta_state_initializer() -- its entries are variables of the record */
+static void meta_reset(env_t *e) {
+  const int32_t *h = e->hdr;
+  for (int q = 0; q < h[MOOG_H_N_METAVAR]; ++q) e->envf[h[MOOG_H_METAVAR_OFF] + q] = e->dpool[h[MOOG_H_METAVAR_INIT] + q];
+}
+
 /* AbstractRule.reset of the rules that keep state: TimedRule re-arms its interval (timing.py:45-48) */
 static void rules_reset(env_t *e) {
   const int32_t *h = e->hdr;
@@ -2053,6 +2102,23 @@ static void rules_reset(env_t *e) {
     }
     if (op->kind == MOOG_R_PORTAL) /* portal.py:36-39: _currently_teleporting = set() */
       for (int s2 = 0; s2 < e->S; ++s2) META(e, MOOG_M_FLAGS, s2) &= ~MOOG_SF_TELEPORTING;
+    if (op->kind == MOOG_R_FIXATION) e->envf[op->i[2]] = 0; /* fixation.py:41-43 */
+    if (op->kind == MOOG_R_PHASESEQ_BEGIN) { /* task_phases.py:118-124 */
+      e->envf[op->i[0]] = 0;
+      e->envf[op->i[0] + 1] = 0;
+      if (op->i[2] >= 0) e->envf[op->i[2]] = e->dpool[op->i[4]];
+    }
+    if (op->kind == MOOG_R_PHASE_BEGIN) { /* task_phases.py:71-77: the duration is drawn anew */
+      double *ph = e->envf + op->i[3];
+      ph[0] = 0;
+      ph[1] = 0;
+      ph[2] = op->p[0];
+      if (op->p[2] > op->p[1]) { /* np.random.randint(p1, p2) */
+        const int lo = (int)op->p[1], hi = (int)op->p[2];
+        int d = lo + (int)(rule_noise_at(e, op->i[4]) * (double)(hi - lo));
+        ph[2] = d >= hi ? hi - 1 : d;
+      }
+    }
     if (op->kind == MOOG_R_TREE) /* the rule's own reset(): its attributes back to their first values */
       for (int q = 0; q < op->i[3]; ++q) e->envf[op->i[2] + q] = e->dpool[op->i[4] + q];
   }
@@ -2217,8 +2283,10 @@ void orc_env_post_reset(const void *blob, const orc_state *st, int n_envs, const
     bind_env(&e, blob, st, n);
     e.envi[MOOG_EI_STEP_COUNT] = 0;
     e.envi[MOOG_EI_RESET_NEXT] = 0;
+    meta_reset(&e);
     tasks_reset(&e);
     actions_reset(&e);
+    e.rule_noise = rule_noise;
     rules_reset(&e);
     int nrn = 0; /* rule noise columns */
     (void)nrn;
@@ -2356,8 +2424,10 @@ void orc_env_step_auto(const void *blob, const orc_state *st, int n_envs, const 
       e.envi[MOOG_EI_EPISODES] += 1;
       e.envi[MOOG_EI_STEP_COUNT] = 0;
       e.envi[MOOG_EI_RESET_NEXT] = 0;
+      meta_reset(&e);
       tasks_reset(&e);
       actions_reset(&e);
+      e.rule_noise = rn;
       rules_reset(&e);
       rules_step(&e, rn);
       reward[n] = NAN;

@@ -51,7 +51,7 @@ def test_cuda_follows_reference_trajectory(scene):
     g = util.load_golden(scene)
     prog = g['program']
     eng = _engine(prog, util.state_at(g, None, prefix='init'))
-    eng.post_reset()
+    eng.post_reset(rule_noise=util.reset_rule_noise(g))
     dev = eng.state.download()
     util.assert_live_equal(prog, {k: dev[k][0] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')},
                            {k: g['reset_' + k] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')}, 'reset')

@@ -19,7 +19,7 @@ def test_oracle_follows_reference_trajectory(scene):
     g = util.load_golden(scene)
     prog = g['program']
     orc = Oracle(prog, util.state_at(g, None, prefix='init'))
-    orc.post_reset()
+    orc.post_reset(rule_noise=util.reset_rule_noise(g))
     util.assert_live_equal(prog, {k: getattr(orc, k)[0] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')},
                            {k: g['reset_' + k] for k in ('dyn', 'stat', 'vtx', 'cnt', 'meta')}, 'reset')
     T = len(g['reward'])

@@ -9,7 +9,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 SCENES = ['pong', 'falling_balls', 'falling_balls20', 'colliding_predators',
           'predators_arena', 'synthetic32', 'falling_balls20_nan', 'cleanup',
           'chase_avoid_torus', 'pacman', 'timed_center', 'parallelogram_catch', 'forces_zoo',
-          'reshape_zoo', 'portal_zoo', 'red_green', 'predict_zoo', 'bounce_box', 'functional_maze']
+          'reshape_zoo', 'portal_zoo', 'red_green', 'predict_zoo', 'bounce_box', 'functional_maze', 'multi_tracking']
 # scenes whose step() uses no sin/cos of a non-zero angle: every operation on
 # the path is IEEE-exact (+ - * / sqrt fma), so the CUDA path must be bit-exact
 EXACT_SCENES = ['pong', 'falling_balls', 'falling_balls20', 'falling_balls20_nan']
@@ -62,6 +62,14 @@ def rule_noise_at(g, t):
     if not prog.rule_noise_dim or 'rule_noise' not in g:
         return None
     return np.asarray(g['rule_noise'][t], dtype=np.float64)[None, :prog.rule_noise_dim]
+
+
+def reset_rule_noise(g):
+    """[1, rule_noise_dim] uniforms behind the draws Environment.reset() made in the rules' reset
+    (a Phase duration drawn with np.random.randint), or None."""
+    if 'reset_rule_noise' not in g:
+        return None
+    return np.asarray(g['reset_rule_noise'], dtype=np.float64)[None, :g['program'].rule_noise_dim]
 
 
 def state_at(g, t, prefix=None):
