@@ -379,3 +379,115 @@ def test_rules_that_cannot_be_traced_are_refused():
     for cls, text in ((Random, 'random'), (MovesThenTests, 'moved'), (ReadsItsOwnWrite, 'earlier assignment')):
         with pytest.raises(compiler.CompileError, match=text):
             compiler.compile_config(dict(base, game_rules=(cls(),)), states)
+
+
+def _phase_config(rules, meta=None, task=None):
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, physics as physics_lib, sprite, tasks
+
+    def state_initializer():
+        agent = sprite.Sprite(x=0.5, y=0.5, shape='square', scale=0.1, c0=0.)
+        cross = sprite.Sprite(x=0.52, y=0.5, shape='square', scale=0.05)
+        return collections.OrderedDict([('cross', [cross]), ('agent', [agent])])
+
+    cfg = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+               task=task or tasks.CompositeTask(timeout_steps=100),
+               action_space=action_spaces.SetPosition(action_layers='agent'), observers={}, game_rules=rules,
+               meta_state_initializer=meta)
+    return cfg, [state_initializer()]
+
+
+def test_phase_sequence_fixation_and_meta_state():
+    """task_phases.py:18-141, fixation.py:19-54 and a dict meta_state, against what the reference's
+    classes do (restated inline): one-time rules on a phase's first step only, continual rules every
+    step, a phase ends by duration or by an end condition that reads meta_state, the sequence steps only
+    the phase that was current when the pass began and names it in meta_state; a Reset task reads the
+    name; stepping past the last phase is the reference's IndexError."""
+    import moog_b200  # noqa: F401
+    from moog import game_rules as gr, tasks
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+
+    def bump(s):
+        s.c0 = s.c0 + 1.
+
+    def mark(s):
+        s.c1 = s.c1 + 10.
+
+    phases = gr.PhaseSequence(
+        gr.Phase(continual_rules=gr.Fixation('agent', 'cross', 0.1, 'held'),
+                 end_condition=lambda state, meta_state: meta_state['held'] >= 3, name='fixate'),
+        gr.Phase(one_time_rules=gr.ModifySprites('agent', mark), continual_rules=gr.ModifySprites('agent', bump),
+                 duration=4, name='count'),
+        gr.Phase(one_time_rules=gr.ModifySprites('agent', mark), duration=lambda: np.random.randint(2, 5), name='wait'),
+        gr.Phase(name='done'),
+        meta_state_phase_name_key='phase')
+    task = tasks.CompositeTask(tasks.Reset(condition=lambda state, meta_state: meta_state['phase'] == 'done',
+                                           reward_fn=lambda _: 7., steps_after_condition=1), timeout_steps=100)
+    cfg, states = _phase_config((phases,), meta=lambda: {'phase': '', 'held': 0}, task=task)
+    prog = compiler.compile_config(cfg, states)
+    assert list(prog.meta_vars) == ['phase', 'held'] and prog.duration_draws == [(0, 2, 5)]
+    kinds = [o['kind'] for o in prog.ops]
+    assert kinds.count(compiler.R_PHASE_BEGIN) == 4 and kinds.count(compiler.R_PHASESEQ_BEGIN) == 1
+    for wait in (2, 3, 4):
+        orc = Oracle(prog, compiler.pack_states(prog, states))
+        orc.post_reset(rule_noise=np.array([[(wait - 2 + 0.5) / 3]]))     # the reset pass is the first step of 'fixate'
+        slot = prog.meta_vars
+        ag = prog.layer_off[1]
+        names = {float(prog.strings.index(n) + 1): n for n in prog.strings}
+        trace, paid = [], 0.0
+        for t in range(14):
+            trace.append((names[orc.envf[0, slot['phase']]], orc.envf[0, slot['held']], orc.stat[0, 6, ag], orc.stat[0, 7, ag]))
+            act = np.array([[0.5, 0.5]]) if t != 0 else np.array([[0.9, 0.9]])     # looks away once (seen by the next pass): the count restarts
+            reward, step_type = orc.step(act)
+            paid += reward[0]
+            if step_type[0] == 2:
+                break
+        phases_seen = [p for p, _, _, _ in trace]
+        # held: 1 after the reset pass, 2, 0 (looked away), 1, 2, 3 -> 'fixate' ends on the 6th pass
+        assert [h for _, h, _, _ in trace[:6]] == [1, 2, 0, 1, 2, 3]
+        assert phases_seen[:5] == ['fixate'] * 5 and phases_seen[5:9] == ['count'] * 4
+        assert phases_seen[9:9 + wait] == ['wait'] * wait, (wait, phases_seen)
+        assert trace[9][2:] == (4.0, 10.0)                 # bump every step of 'count', mark once
+        assert trace[-1][2:] == (4.0, 20.0) and trace[-1][0] == 'done'
+        assert paid == 7.0 and step_type[0] == 2 and orc.envi[0, 2] == 0       # paid once, when 'done' is first seen
+    # past the last phase: IndexError in the reference
+    short = gr.PhaseSequence(gr.Phase(duration=1, name='a'), gr.Phase(duration=1, name='b'))
+    cfg, states = _phase_config((short,))
+    prog = compiler.compile_config(cfg, states)
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    orc.post_reset()
+    orc.step(np.array([[0.5, 0.5]]))
+    assert orc.envi[0, 2] & 128
+    # meta_state must be a dict of numbers / strings
+    cfg, states = _phase_config((), meta=lambda: [1, 2])
+    with pytest.raises(compiler.CompileError, match='dict'):
+        compiler.compile_config(cfg, states)
+
+
+@pytest.mark.reference
+def test_shipped_multi_tracking_compiles_unchanged(monkeypatch):
+    """Build container only: moog_demos/example_configs/multi_tracking_with_feature.py as shipped, on this
+    repo's `moog` package (PhaseSequence of five phases, two Fixation rules, its own ChangeTargetFeature
+    rule, dict meta_state, RawState observer ignored)."""
+    import importlib
+    import sys
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+    monkeypatch.syspath_prepend('/root/reference')
+    for name in [m for m in sys.modules if m.startswith('moog_demos')]:
+        monkeypatch.delitem(sys.modules, name)
+    shipped = importlib.import_module('moog_demos.example_configs.multi_tracking_with_feature')
+    np.random.seed(5)
+    cfg = shipped.get_config(3)
+    states = [cfg['state_initializer']() for _ in range(2)]
+    prog = compiler.compile_config(cfg, states)
+    assert list(prog.meta_vars) == ['phase', 'fixation_duration', 'response_duration'] and len(prog.duration_draws) == 1
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    Oracle.set_seed(3)
+    orc.post_reset()
+    for _ in range(30):
+        orc.step(np.full((2, 2), 0.5))
+    assert (orc.envi[:, 2] == 0).all()
+    assert (orc.envf[:, prog.meta_vars['phase']] > 1).all()        # past the fixation phase
