@@ -326,7 +326,10 @@ enum {
   MOOG_X_SELECT,     /* pop b, pop a, pop c -> (c != 0 ? a : b): an `if` / `else` of a config callable on a
                         per-sprite value, both sides traced (lambdas._explore) */
   MOOG_X_ENVF,       /* push envf[arg]: a state variable of a user-defined rule (MOOG_R_TREE) */
-  MOOG_X_STORE_ENVF  /* pop -> envf[arg] */
+  MOOG_X_STORE_ENVF, /* pop -> envf[arg] */
+  MOOG_X_RULE_NOISE, /* push this pass's uniform of rule-noise column arg: np.random.uniform / randint inside a traced
+                        rule (match_to_sample.py:62-65) */
+  MOOG_X_NORM2       /* pop y, pop x -> np.linalg.norm([x, y]) */
 };
 
 /* attribute ids for the expression VM (Sprite.FACTOR_NAMES, sprite.py:237-253) */

@@ -126,6 +126,7 @@ class Program(object):
         self.meta_var_off = -1   # envf offset of the block reserved for them
         self.strings = []        # interned strings (phase names ...): code = index + 1
         self.duration_draws = [] # (rule-noise column, lo, hi) of every Phase whose duration is np.random.randint(lo, hi)
+        self.rule_draws = []     # (rule object, [(kind, rule-noise column, parameter)]) of traced rules that draw
         self.meta_keys = []      # `sprite.metadata[key]` columns the callables read (lambdas.metadata_columns)
         self.meta_off = 0        # envf offset of column 0 (column k of slot s: meta_off + k * n_slots + s)
         self.z_shape_ids = {}    # device sampler: shape candidate -> index of its shape record

@@ -127,7 +127,8 @@ int moog_program_validate(const void *blob, size_t nbytes) {
   if (NX > 0 && pv.expr[NX - 1].op != MOOG_X_END) return MOOG_E_INVAL;
   for (int x = 0; x < NX; ++x) {
     const moog_ex &e = pv.expr[x];
-    if (e.op < 0 || e.op > MOOG_X_STORE_ENVF) return MOOG_E_INVAL;
+    if (e.op < 0 || e.op > MOOG_X_NORM2) return MOOG_E_INVAL;
+    if (e.op == MOOG_X_RULE_NOISE && (e.arg < 0 || e.arg >= hdr[MOOG_H_RULE_NOISE_DIM])) return MOOG_E_INVAL;
     if ((e.op == MOOG_X_ENVF || e.op == MOOG_X_STORE_ENVF) && (e.arg < 0 || e.arg >= NF)) return MOOG_E_INVAL;
     if ((e.op == MOOG_X_ATTR0 || e.op == MOOG_X_ATTR1 || e.op == MOOG_X_STORE) &&
         !((e.arg >= 0 && e.arg <= MOOG_AT_OPACITY) || (e.arg >= MOOG_AT_META0 && e.arg < MOOG_AT_META0 + hdr[MOOG_H_N_META])))

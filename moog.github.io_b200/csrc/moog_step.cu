@@ -2465,6 +2465,7 @@ __device__ inline double py_fmod(double a, double b) {
   return r;
 }
 
+__device__ double rule_noise_at(const Env &e, int col);
 __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1) {
   const Env e = env_view();
   if (start < 0) return 1.0;
@@ -2502,6 +2503,12 @@ __device__ __noinline__ double eval_expr(const Env &, int start, int s0, int s1)
           puti(e, &META(e, MOOG_M_FLAGS, s0), fl);
           wsync();
         }
+        break;
+      }
+      case MOOG_X_RULE_NOISE: st[sp++] = rule_noise_at(e, x->arg); break;  // a draw of a traced rule
+      case MOOG_X_NORM2: {  // np.linalg.norm of a 2-vector
+        const double vy = st[--sp], vx = st[--sp];
+        st[sp++] = norm1(vx, vy);
         break;
       }
       case MOOG_X_ENVF: st[sp++] = e.envf[x->arg]; break;  // a user-defined rule's own attribute

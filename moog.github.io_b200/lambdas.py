@@ -29,7 +29,7 @@ import numpy as np
 
 (X_END, X_CONST, X_ATTR0, X_ATTR1, X_LT, X_LE, X_GT, X_GE, X_EQ, X_NE, X_AND,
  X_OR, X_NOT, X_ADD, X_SUB, X_MUL, X_DIV, X_NEG, X_ABS, X_MOD, X_STORE,
- X_STORE_POS, X_SELECT, X_ENVF, X_STORE_ENVF) = range(25)
+ X_STORE_POS, X_SELECT, X_ENVF, X_STORE_ENVF, X_RULE_NOISE, X_NORM2) = range(27)
 
 # attribute ids from here on read the sprite's numeric `metadata[key]` columns (MOOG_AT_META0)
 AT_META0 = 16
@@ -371,7 +371,27 @@ class SymVec(object):
                 return getattr(self, self._REVERSED[op])(inputs[0])
             return getattr(SymVec(list(inputs[0]) if hasattr(inputs[0], '__len__') else [inputs[0]] * len(self.elems)),
                            op)(self)
+        if name == 'matmul' and len(inputs) == 2 and inputs[1] is self and len(self.elems) == 2:
+            # a 2 x 2 matrix of 0 / +-1 entries times the vector (a quarter turn, a reflection): every product is
+            # exact, so the order BLAS adds them in cannot matter
+            m = np.asarray(inputs[0])
+            if m.shape == (2, 2) and m.dtype != object and np.isin(m, (-1, 0, 1)).all():
+                x, y = (Sym.lift(v) for v in self.elems)
+                return SymVec([float(m[0, 0]) * x + float(m[0, 1]) * y, float(m[1, 0]) * x + float(m[1, 1]) * y])
         raise LoweringError('numpy.{} of a sprite vector is not available on the device'.format(name))
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func is np.linalg.norm and len(args) == 1 and args[0] is self and not kwargs and len(self.elems) == 2:
+            x, y = (Sym.lift(v) for v in self.elems)       # np.linalg.norm of a 2-vector: sqrt(dot(v, v))
+            return Sym(x.code + y.code + [(X_NORM2, 0, 0.0)])
+        if func is np.all:
+            return self.all()
+        if func is np.any:
+            return self.any()
+        impl = getattr(func, '_implementation', None)     # anything else: NumPy's own code, as without this protocol
+        if impl is None:
+            raise LoweringError('numpy.{} of a sprite vector is not available on the device'.format(getattr(func, '__name__', func)))
+        return impl(*args, **kwargs)
 
     def __len__(self):
         return len(self.elems)
@@ -766,12 +786,56 @@ def trace_rule(rule, prog):
             raise LoweringError('{}.reset assigns self.{} = {!r}: only numbers are carried on the device'.format(what, name, v))
         initial[name] = float(v)
 
+    draws = []          # (kind, rule-noise column, parameter) of the k-th random draw step() makes, on every path
+
+    def draw(kind, k, param):
+        if k == len(draws):
+            draws.append((kind, prog.rule_noise_dim, param))
+            prog.rule_noise_dim += 1
+        if draws[k][0] != kind or draws[k][2] != param:
+            raise LoweringError('{}.step draws random numbers in an order that depends on the state'.format(what))
+        return Sym([(X_RULE_NOISE, draws[k][1], 0.0)])
+
+    @contextlib.contextmanager
+    def traced_draws(counter):
+        """np.random.uniform(lo, hi) and np.random.randint(n) (scalars) become reads of rule-noise columns:
+        lo + (hi - lo) * u, and the number of thresholds k / n that u has passed."""
+        saved = (np.random.uniform, np.random.randint)
+
+        def uniform(low=0.0, high=1.0, size=None):
+            if size is not None:
+                raise LoweringError('{}.step draws an array of random numbers'.format(what))
+            u = draw('uniform', counter[0], None)
+            counter[0] += 1
+            return low + (high - low) * u
+
+        def randint(low, high=None, size=None, **kwargs):
+            if size is not None or kwargs:
+                raise LoweringError('{}.step draws an array of random integers'.format(what))
+            lo, hi = (0, low) if high is None else (low, high)
+            n = int(hi) - int(lo)
+            if n < 1 or n > 16:
+                raise LoweringError('{}.step: np.random.randint over {} values is not lowered'.format(what, n))
+            u = draw('randint', counter[0], n)
+            counter[0] += 1
+            out = Sym.lift(float(lo))
+            for k in range(1, n):
+                out = out + (u >= (k / n))
+            return out
+        np.random.uniform, np.random.randint = uniform, randint
+        try:
+            yield
+        finally:
+            np.random.uniform, np.random.randint = saved
+
     def explore(variables, slots):
         state = BoundState(prog, effects=True)
         holder = {}
+        counter = [0]
 
         def begin():
             state.begin_path()
+            counter[0] = 0
             holder['proxy'] = _RuleProxy(rule, {n: Sym([(X_ENVF, slots[n], 0.0)]) for n in variables})
 
         def end():
@@ -790,7 +854,7 @@ def trace_rule(rule, prog):
             if out is not None:
                 raise LoweringError('{}.step returns a value'.format(what))
 
-        with no_randomness(what):
+        with no_randomness(what), traced_draws(counter):
             try:
                 tree = _explore_tree(call, (state,), hooks=(begin, end))
             except LoweringError:
@@ -829,6 +893,8 @@ def trace_rule(rule, prog):
         return ('test', node[1], strip(node[2]), strip(node[3]))
 
     start, count = _emit_tree(strip(tree), state, prog, what, with_value=False)
+    if draws:
+        prog.rule_draws.append((rule, list(draws)))
     return start, count, base, list(initial.values())
 
 

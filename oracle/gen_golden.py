@@ -108,6 +108,11 @@ SCENES = {
     # np.random.randint at reset), two Fixation rules, a dict meta_state whose 'phase' entry the Reset task
     # reads, a rule class of its own, SetPosition, TetherZippedLayers; the agent fixates the cross, then target 0
     'multi_tracking': ('moog_demos.example_configs.multi_tracking_with_feature', 3, 22, 220, 10),
+    # a shipped config whose own rule draws random numbers and does vector algebra on the sprites it loops over
+    # (match_to_sample.py:45-71 BeginMotion: np.random.uniform / randint, np.matmul, np.linalg.norm, zip over two
+    # layers), PhaseSequence with one-time and continual rules, a Reset condition on a sprite AND meta_state,
+    # metadata rewards, TetherZippedLayers with an anchor, infinite and zero masses, transparent sprites
+    'match_to_sample': ('moog_demos.example_configs.match_to_sample', 4, 23, 220, 10),
 }
 
 
@@ -164,6 +169,15 @@ def _fixate_action(env, t):
     del t
     target = env.state['fixation'][0] if env.state['fixation'] else env.state['targets'][0]
     return np.array(target.position, dtype=np.float64)
+
+
+def _match_action(env, t):
+    """match_to_sample: full stick towards the cover that hides the prey (the agent is glued until the
+    response phase)."""
+    del t
+    d = np.array(env.state['covers'][0].position) - np.array(env.state['agent'][0].position)
+    n = float(np.linalg.norm(d))
+    return d / n if n > 0 else np.zeros(2)
 
 
 def _pacman_action(env, t):
@@ -266,12 +280,44 @@ def generate(name, out_dir):
     draws = []
     orig_uniform = np.random.uniform
 
+    # draws made inside a rule class of the config's own (lambdas.trace_rule: np.random.uniform / randint become
+    # rule-noise columns, in call order): the uniform behind each one goes to its column
+    plan_now = [None, 0]
+    orig_randint = np.random.randint
+
+    def _next_planned(kind):
+        plan, k = plan_now
+        assert k < len(plan) and plan[k][0] == kind, (kind, plan, k)
+        plan_now[1] = k + 1
+        return plan[k]
+
     def _uniform(low=0.0, high=1.0, size=None):
         if size is not None:
             return orig_uniform(low, high, size)
         u = np.random.random_sample()
-        draws.append(u)
+        if plan_now[0] is not None:
+            _, col, _ = _next_planned('uniform')
+            rule_draws[col] = u
+        else:
+            draws.append(u)
         return low + (high - low) * u
+
+    def _randint(low, high=None, size=None, **kwargs):
+        out = orig_randint(low, high, size, **kwargs)
+        if plan_now[0] is not None and size is None and not kwargs:
+            _, col, n = _next_planned('randint')
+            lo = 0 if high is None else low
+            rule_draws[col] = (int(out) - lo + 0.5) / n
+        return out
+
+    for rule_obj, plan in prog.rule_draws:
+        def _planned_step(state, meta_state, _orig=rule_obj.step, _plan=plan):
+            plan_now[0], plan_now[1] = _plan, 0
+            try:
+                return _orig(state, meta_state)
+            finally:
+                plan_now[0] = None
+        rule_obj.step = _planned_step
 
     # the uniform behind ModifySprites(sample_one)'s np.random.choice
     # (modify_sprites.py:48-49): element int(u * len) of the filtered list
@@ -358,6 +404,8 @@ def generate(name, out_dir):
             action = _booster_action(env, t)
         elif name == 'multi_tracking':
             action = _fixate_action(env, t)
+        elif name == 'match_to_sample':
+            action = _match_action(env, t)
         elif name == 'bounce_box':
             action = 4 if t < 25 else 0             # wait, then walk into the left response box
         elif name == 'predict_zoo':
@@ -376,6 +424,7 @@ def generate(name, out_dir):
         np.random.uniform = _uniform
         np.random.choice = _choice
         np.random.rand = _rand
+        np.random.randint = _randint
         try:
             with refenv.OverlapLog() as log:
                 ts = env.step(action)
@@ -383,6 +432,7 @@ def generate(name, out_dir):
             np.random.uniform = orig_uniform
             np.random.choice = orig_choice
             np.random.rand = orig_rand
+            np.random.randint = orig_randint
         h, n_true = 0, 0
         for a, b, r in log.calls:
             if r:

@@ -1471,6 +1471,7 @@ static void set_path(env_t *e, int s) {
   STAT(e, MOOG_S_IY, s) *= sy * sy;
 }
 
+static double rule_noise_at(env_t *e, int col);
 /* Runs the postfix program at `start`; returns top of stack (or 1.0 when start < 0). */
 static double eval_expr(env_t *e, int start, int s0, int s1) {
   if (start < 0) return 1.0;
@@ -1504,6 +1505,12 @@ static double eval_expr(env_t *e, int start, int s0, int s1) {
       case MOOG_X_STORE_POS: {
         double ny = st[--sp], nx = st[--sp];
         set_position(e, s0, nx, ny);
+        break;
+      }
+      case MOOG_X_RULE_NOISE: st[sp++] = rule_noise_at(e, x->arg); break; /* a draw of a traced rule */
+      case MOOG_X_NORM2: { /* np.linalg.norm of a 2-vector */
+        const double vy = st[--sp], vx = st[--sp];
+        st[sp++] = norm1(vx, vy);
         break;
       }
       case MOOG_X_ENVF: st[sp++] = e->envf[x->arg]; break; /* a user-defined rule's own attribute */

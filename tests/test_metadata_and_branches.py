@@ -348,7 +348,7 @@ def test_rules_that_cannot_be_traced_are_refused():
             pass
 
         def step(self, state, meta_state):
-            state['agent'][0].c0 = np.random.uniform()
+            state['agent'][0].c0 = np.random.normal()        # (uniform / randint scalars ARE lowered: rule-noise columns)
 
     class MovesThenTests(object):
         def reset(self, state, meta_state):
@@ -491,3 +491,93 @@ def test_shipped_multi_tracking_compiles_unchanged(monkeypatch):
         orc.step(np.full((2, 2), 0.5))
     assert (orc.envi[:, 2] == 0).all()
     assert (orc.envf[:, prog.meta_vars['phase']] > 1).all()        # past the fixation phase
+
+
+class _Kick(object):
+    """match_to_sample.py:45-71 in structure: one random speed and sign per call, then a quarter turn of
+    every mover's offset from the centre scaled by its distance, given to the mover and to its twin."""
+
+    def __init__(self, speeds):
+        self._speeds = speeds
+
+    def reset(self, state, meta_state):
+        pass
+
+    def step(self, state, meta_state):
+        del meta_state
+        w = np.random.uniform(*self._speeds)
+        w *= (2 * np.random.randint(2) - 1)
+        for a, b in zip(state['movers'], state['twins']):
+            rel = a.position - 0.5
+            turned = np.matmul(np.array([[0, -1], [1, 0]]), rel)
+            v = turned * np.linalg.norm(rel) * w
+            a.velocity = v
+            b.velocity = v
+
+
+def test_traced_rule_with_random_draws_and_vector_algebra():
+    """np.random.uniform / randint inside a traced rule become rule-noise columns; np.matmul with a
+    quarter-turn matrix and np.linalg.norm on a sprite's position are lowered.  With the uniforms behind the
+    draws replayed, the oracle's velocities equal what the Python rule computes on the host sprites."""
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, physics as physics_lib, sprite, tasks
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+
+    def state_initializer():
+        movers = [sprite.Sprite(x=0.2 + 0.25 * k, y=0.3 + 0.1 * k, shape='circle', scale=0.05) for k in range(3)]
+        twins = [sprite.Sprite(x=m.x, y=m.y, shape='square', scale=0.03) for m in movers]
+        return collections.OrderedDict([('movers', movers), ('twins', twins)])
+
+    rule = _Kick((0.1, 0.3))
+    cfg = dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(timeout_steps=10), action_space=action_spaces.Grid(action_layers=()),
+               observers={}, game_rules=(rule,))
+    states = [state_initializer()]
+    prog = compiler.compile_config(cfg, states)
+    assert prog.rule_noise_dim == 2 and prog.rule_draws[0][1] == [('uniform', 0, None), ('randint', 1, 2)]
+    for u0, sign in ((0.25, 0), (0.8, 1)):
+        orc = Oracle(prog, compiler.pack_states(prog, states))
+        orc.post_reset(rule_noise=np.array([[u0, (sign + 0.5) / 2]]))
+        # the same call in Python, its two draws forced to the same outcomes
+        twin_state = state_initializer()
+        real = (np.random.uniform, np.random.randint)
+        np.random.uniform = lambda lo, hi: lo + (hi - lo) * u0
+        np.random.randint = lambda n: sign
+        try:
+            _Kick((0.1, 0.3)).step(twin_state, None)
+        finally:
+            np.random.uniform, np.random.randint = real
+        for layer, lo in (('movers', prog.layer_off[0]), ('twins', prog.layer_off[1])):
+            want = np.array([sp.velocity for sp in twin_state[layer]]).T
+            assert np.array_equal(orc.dyn[0, 2:4, lo:lo + 3], want), (layer, u0, sign)
+        assert (orc.dyn[0, 2:4, :] != 0).any()
+
+
+@pytest.mark.reference
+def test_shipped_match_to_sample_compiles_unchanged(monkeypatch):
+    """Build container only: moog_demos/example_configs/match_to_sample.py as shipped, on this repo's `moog`
+    package: PhaseSequence of four phases, its own BeginMotion rule (random draws, matmul, norm, zip over two
+    layers), metadata reward, a Reset condition on a sprite and meta_state, TetherZippedLayers."""
+    import importlib
+    import sys
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+    monkeypatch.syspath_prepend('/root/reference')
+    for name in [m for m in sys.modules if m.startswith('moog_demos')]:
+        monkeypatch.delitem(sys.modules, name)
+    shipped = importlib.import_module('moog_demos.example_configs.match_to_sample')
+    np.random.seed(6)
+    cfg = shipped.get_config(4)
+    states = [cfg['state_initializer']() for _ in range(2)]
+    prog = compiler.compile_config(cfg, states)
+    assert list(prog.meta_vars) == ['phase'] and prog.meta_keys == ['prey'] and len(prog.rule_draws) == 1
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    Oracle.set_seed(9)
+    orc.post_reset()
+    for _ in range(12):
+        orc.step(np.zeros((2, 2)))
+    assert (orc.envi[:, 2] == 0).all()
+    targets = prog.layer_off[prog.layer_index('targets')]
+    assert (np.abs(orc.dyn[:, 2:4, targets:targets + 4]).max(axis=(1, 2)) > 0.01).all(), 'BeginMotion set the targets moving'

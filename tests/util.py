@@ -9,7 +9,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 SCENES = ['pong', 'falling_balls', 'falling_balls20', 'colliding_predators',
           'predators_arena', 'synthetic32', 'falling_balls20_nan', 'cleanup',
           'chase_avoid_torus', 'pacman', 'timed_center', 'parallelogram_catch', 'forces_zoo',
-          'reshape_zoo', 'portal_zoo', 'red_green', 'predict_zoo', 'bounce_box', 'functional_maze', 'multi_tracking']
+          'reshape_zoo', 'portal_zoo', 'red_green', 'predict_zoo', 'bounce_box', 'functional_maze', 'multi_tracking', 'match_to_sample']
 # scenes whose step() uses no sin/cos of a non-zero angle: every operation on
 # the path is IEEE-exact (+ - * / sqrt fma), so the CUDA path must be bit-exact
 EXACT_SCENES = ['pong', 'falling_balls', 'falling_balls20', 'falling_balls20_nan']
