@@ -66,7 +66,7 @@ R_VANISH_ON_CONTACT, R_VANISH_BY_FILTER, R_MODIFY_ON_CONTACT, \
 R_PORTAL, R_CHANGE_LAYER, R_CREATE_SPRITES, R_TREE = 71, 72, 73, 74
 R_FIXATION, R_PHASESEQ_BEGIN, R_PHASE_BEGIN, R_PHASE_END = 75, 76, 77, 78
 # rule classes of the reference that keep Python-side state the tracer must not guess at
-_RULES_OF_THE_REFERENCE_NOT_LOWERED = ('ModifyMetaState', 'UpdateMetaStateValue')
+_RULES_OF_THE_REFERENCE_NOT_LOWERED = ()
 T_CONTACT_REWARD, T_RESET, T_STAY_ALIVE, T_TIMEOUT = 96, 97, 98, 99
 A_JOYSTICK, A_GRID, A_SET_POSITION = 128, 129, 130
 SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \

@@ -4,10 +4,9 @@ On the hot path (lowered to device ops by moog_b200.compiler):
 `VanishOnContact`, `VanishByFilter`, `ModifyOnContact`, `ModifySprites`,
 `ConditionalRule`, plus the `get_contact_indices` / `get_contact_counter`
 condition builders, `TimedRule` / `DelayedRule` / `TemporaryRule` with fixed
-intervals, `KeepNearCenter`, `Portal` and `ChangeLayer`.  The remaining psychophysics trial-structure
-rules of the reference (Phase*, Fixation, CreateSprites, ...) are
-outside the accelerated path; constructing one raises so that a config never
-silently loses a rule.
+intervals, `KeepNearCenter`, `Portal`, `ChangeLayer`, `CreateSprites`, `Fixation`, `Phase` / `PhaseSequence`,
+`ModifyMetaState` / `UpdateMetaStateValue`.  A rule class of a config's own is traced by the compiler
+(lambdas.trace_rule); what cannot be lowered raises at compile time, so a config never silently loses a rule.
 """
 
 import abc
@@ -216,16 +215,25 @@ class PhaseSequence(AbstractRule):
         self._meta_state_key = meta_state_phase_name_key
 
 
-def _out_of_scope(name, where):
-    def _ctor(*args, **kwargs):
-        raise NotImplementedError(
-            'game_rules.{} ({}) is outside the accelerated Environment.step '
-            'path of this build (see DESIGN.md, "out of scope").'.format(
-                name, where))
-    _ctor.__name__ = name
-    return _ctor
+class ModifyMetaState(AbstractRule):
+    """`modifier(meta_state)` every step (modify_meta_state.py:8-26).  On the device the modifier is traced:
+    it may read and assign numeric / string entries of the dict."""
+
+    def __init__(self, modifier):
+        self._modifier = modifier
+
+    def step(self, state, meta_state):
+        del state
+        self._modifier(meta_state)
 
 
-ModifyMetaState = _out_of_scope('ModifyMetaState', 'modify_meta_state.py')
-UpdateMetaStateValue = _out_of_scope(
-    'UpdateMetaStateValue', 'modify_meta_state.py')
+class UpdateMetaStateValue(AbstractRule):
+    """`meta_state[key] = value` (modify_meta_state.py:29-48)."""
+
+    def __init__(self, key, value):
+        self._key = key
+        self._value = value
+
+    def step(self, state, meta_state):
+        del state
+        meta_state[self._key] = self._value

@@ -581,3 +581,37 @@ def test_shipped_match_to_sample_compiles_unchanged(monkeypatch):
     assert (orc.envi[:, 2] == 0).all()
     targets = prog.layer_off[prog.layer_index('targets')]
     assert (np.abs(orc.dyn[:, 2:4, targets:targets + 4]).max(axis=(1, 2)) > 0.01).all(), 'BeginMotion set the targets moving'
+
+
+def test_modify_meta_state_rules():
+    """modify_meta_state.py:8-48: `ModifyMetaState(modifier)` (the modifier traced: it reads and assigns
+    entries of the dict) and `UpdateMetaStateValue(key, value)` with a string value."""
+    import moog_b200  # noqa: F401
+    from moog import game_rules as gr
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+
+    def count_up(meta_state):
+        meta_state['count'] += 2
+        if meta_state['count'] > 5:
+            meta_state['level'] = meta_state['level'] + 1
+            meta_state['count'] = 0
+
+    rules = (gr.ModifyMetaState(count_up),
+             gr.ConditionalRule(condition=lambda state, meta_state: meta_state['level'] >= 2,
+                                rules=gr.UpdateMetaStateValue('phase', 'late')))
+    cfg, states = _phase_config(rules, meta=lambda: {'count': 0, 'level': 0, 'phase': 'early'})
+    prog = compiler.compile_config(cfg, states)
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    orc.post_reset()
+    host = {'count': 0, 'level': 0, 'phase': 'early'}
+    count_up(host)
+    for t in range(9):
+        got = {k: orc.envf[0, s] for k, s in prog.meta_vars.items()}
+        assert (got['count'], got['level']) == (host['count'], host['level']), t
+        assert prog.strings[int(got['phase']) - 1] == host['phase'], t
+        orc.step(np.array([[0.5, 0.5]]))
+        count_up(host)
+        if host['level'] >= 2:
+            host['phase'] = 'late'
+    assert host['phase'] == 'late' and orc.envi[0, 2] == 0
