@@ -284,10 +284,8 @@ class BatchedEnvironment(object):
                  game_rules=(), meta_state_initializer=None, *, num_envs,
                  device='cuda', pool_size=None, seed=0, layer_capacity=None,
                  initial_states=None, reset_mode='pool'):
-        if meta_state_initializer is not None and meta_state_initializer() is not None:
-            raise compiler.CompileError(
-                'meta_state is an arbitrary Python object in MOOG; the device '
-                'path supports configs whose meta_state is None')
+        # (meta_state: None, or a dict of numbers / strings whose entries become variables of the env's
+        # record -- compile_config refuses anything else)
         self.state_initializer = state_initializer
         self.num_envs = int(num_envs)
         config = dict(state_initializer=state_initializer, physics=physics, task=task,
@@ -500,6 +498,22 @@ class BatchedEnvironment(object):
         return action
 
     # -- extras -----------------------------------------------------------------
+    def meta_state(self, env=0):
+        """The env's meta_state as the dict the reference would hold (environment.py:129-131): the entries the
+        program carries, strings decoded; None when the config has no meta_state."""
+        prog = self.program
+        if not getattr(prog, 'meta_vars', None):
+            return None
+        row = self.engine.state.envf[env].cpu().numpy()
+        out = {}
+        for key, slot in prog.meta_vars.items():
+            v = float(row[slot])
+            if isinstance(prog.meta_var_init.get(key), str) or key in getattr(prog, 'string_vars', ()):
+                out[key] = prog.strings[int(v) - 1] if 1 <= int(v) <= len(prog.strings) else ''
+            else:
+                out[key] = int(v) if v == int(v) and abs(v) < 2 ** 53 else v
+        return out
+
     def raise_errors(self):
         """Raises the data-dependent exceptions the reference would have raised."""
         err = self.engine.state.envi[:, 2]  # MOOG_EI_ERR

@@ -125,6 +125,7 @@ class Program(object):
         self.meta_var_init = {}  # key -> value after meta_state_initializer()
         self.meta_var_off = -1   # envf offset of the block reserved for them
         self.strings = []        # interned strings (phase names ...): code = index + 1
+        self.string_vars = set() # meta_state keys that hold strings
         self.duration_draws = [] # (rule-noise column, lo, hi) of every Phase whose duration is np.random.randint(lo, hi)
         self.rule_draws = []     # (rule object, [(kind, rule-noise column, parameter)]) of traced rules that draw
         self.meta_keys = []      # `sprite.metadata[key]` columns the callables read (lambdas.metadata_columns)
@@ -610,6 +611,8 @@ def _rule_specs(prog, rule, out, depth=0):
             raise CompileError('PhaseSequence takes Phase instances')
         seq = prog.alloc_envf(2)          # current phase index, its value when the pass began
         name_slot = prog.meta_slot(rule._meta_state_key) if rule._meta_state_key is not None else -1
+        if rule._meta_state_key is not None:
+            prog.string_vars.add(rule._meta_state_key)
         names = len(prog.dpool)
         prog.dpool.extend(prog.intern(ph.name) for ph in phases)
         out.append(dict(kind=R_PHASESEQ_BEGIN, i=(seq, len(phases), name_slot, 0, names)))

@@ -294,7 +294,8 @@ class BatchedLoggingEnvironment(object):
             r = None if (first or np.isnan(reward[k])) else float(reward[k])
             # dm_env.StepType: FIRST 0, MID 1, LAST 2
             step = [['time', now], ['reward', r], ['step_type', int(step_type[k])],
-                    ['action', None if act is None else self._unflatten_action(act[k])], ['meta_state', None], state]
+                    ['action', None if act is None else self._unflatten_action(act[k])],
+                    ['meta_state', self._env.meta_state(int(n))], state]
             self._episode_log[n].append(step)
             if int(step_type[k]) == STEP_LAST:
                 fn = os.path.join(self._dirs[n], str(self._episode_count[n]).zfill(_FILENAME_ZFILL))

@@ -615,3 +615,51 @@ def test_modify_meta_state_rules():
         if host['level'] >= 2:
             host['phase'] = 'late'
     assert host['phase'] == 'late' and orc.envi[0, 2] == 0
+
+
+@pytest.mark.gpu
+def test_cuda_phase_sequence_through_the_public_api():
+    """The PhaseSequence / Fixation / meta_state config of the CPU test above through BatchedEnvironment
+    (`meta_state_initializer` accepted, auto-resets from the pool, Phase durations drawn on the device):
+    `env.meta_state(i)` returns the dict the reference would hold; every env walks the phases in order
+    and is paid once per episode."""
+    import torch
+    import moog_b200  # noqa: F401
+    from moog import game_rules as gr, tasks
+    from moog_b200.batched_env import BatchedEnvironment
+
+    def bump(s):
+        s.c0 = s.c0 + 1.
+
+    phases = gr.PhaseSequence(
+        gr.Phase(continual_rules=gr.Fixation('agent', 'cross', 0.1, 'held'),
+                 end_condition=lambda state, meta_state: meta_state['held'] >= 3, name='fixate'),
+        gr.Phase(continual_rules=gr.ModifySprites('agent', bump), duration=lambda: np.random.randint(2, 6), name='count'),
+        gr.Phase(name='done'),
+        meta_state_phase_name_key='phase')
+    task = tasks.CompositeTask(tasks.Reset(condition=lambda state, meta_state: meta_state['phase'] == 'done',
+                                           reward_fn=lambda _: 7., steps_after_condition=1), timeout_steps=100)
+    cfg, states = _phase_config((phases,), meta=lambda: {'phase': '', 'held': 0}, task=task)
+    N = 256
+    env = BatchedEnvironment(**cfg, num_envs=N, device='cuda:0', seed=2, initial_states=states)
+    env.reset()
+    assert env.meta_state(0) == {'phase': 'fixate', 'held': 1}
+    act = torch.full((N, 2), 0.5, dtype=torch.float64)
+    paid = np.zeros(N)
+    lengths = []
+    seen = [[] for _ in range(4)]
+    for t in range(40):
+        ts = env.step(act)
+        r = ts.reward.cpu().numpy()
+        paid += np.where(np.isnan(r), 0.0, r)
+        for e in range(4):
+            seen[e].append(env.meta_state(e)['phase'])
+    st = env.engine.state.download()
+    assert (st['envi'][:, 2] == 0).all()
+    episodes = st['envi'][:, 3]
+    # (an env whose condition has just held was paid for an episode that ends on the next step)
+    assert (episodes >= 3).all() and np.isin(paid - 7.0 * episodes, (0.0, 7.0)).all(), 'paid once per episode'
+    assert len(set(episodes.tolist())) > 1, 'the drawn durations differ between envs'
+    for e in range(4):
+        order = [p for k, p in enumerate(seen[e]) if k == 0 or seen[e][k - 1] != p]
+        assert order[:3] == ['fixate', 'count', 'done'], order
