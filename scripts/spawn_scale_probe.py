@@ -1,5 +1,6 @@
-import sys, time
-sys.path.insert(0, '/root/repo')
+"""The shipped first_person_predators_prey program (from its golden) at 4096 envs: env-steps/s with frames."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import moog_b200
 from moog_b200.batched_env import Engine
