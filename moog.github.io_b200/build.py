@@ -62,7 +62,8 @@ def build(force=False, verbose=False):
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-lcudart']
+    # (the arch again at the link step: without it nvcc adds an empty default-arch device stub to the library)
+    cmd = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return LIB
 
