@@ -190,7 +190,8 @@ def test_shipped_prediction_configs_compile_unchanged(monkeypatch, module, level
                 sp.velocity = np.array(orc.dyn[0, 2:4, s])
 
     monkeypatch.setattr(host_physics, 'step', _oracle_step)
-    monkeypatch.syspath_prepend('/root/reference')
+    import moog  # noqa: F401  (this repo's package, before the reference's directory joins sys.path)
+    monkeypatch.setattr(sys, 'path', sys.path + ['/root/reference'])
     for name in [m for m in sys.modules if m.startswith('moog_demos')]:
         monkeypatch.delitem(sys.modules, name)
     shipped = importlib.import_module('moog_demos.example_configs.' + module)
@@ -475,7 +476,8 @@ def test_shipped_multi_tracking_compiles_unchanged(monkeypatch):
     import moog_b200  # noqa: F401
     from moog_b200 import compiler
     from oracle.oracle import Oracle
-    monkeypatch.syspath_prepend('/root/reference')
+    import moog  # noqa: F401  (this repo's package, before the reference's directory joins sys.path)
+    monkeypatch.setattr(sys, 'path', sys.path + ['/root/reference'])
     for name in [m for m in sys.modules if m.startswith('moog_demos')]:
         monkeypatch.delitem(sys.modules, name)
     shipped = importlib.import_module('moog_demos.example_configs.multi_tracking_with_feature')
@@ -564,7 +566,8 @@ def test_shipped_match_to_sample_compiles_unchanged(monkeypatch):
     import moog_b200  # noqa: F401
     from moog_b200 import compiler
     from oracle.oracle import Oracle
-    monkeypatch.syspath_prepend('/root/reference')
+    import moog  # noqa: F401  (this repo's package, before the reference's directory joins sys.path)
+    monkeypatch.setattr(sys, 'path', sys.path + ['/root/reference'])
     for name in [m for m in sys.modules if m.startswith('moog_demos')]:
         monkeypatch.delitem(sys.modules, name)
     shipped = importlib.import_module('moog_demos.example_configs.match_to_sample')
@@ -663,3 +666,63 @@ def test_cuda_phase_sequence_through_the_public_api():
     for e in range(4):
         order = [p for k, p in enumerate(seen[e]) if k == 0 or seen[e][k - 1] != p]
         assert order[:3] == ['fixate', 'count', 'done'], order
+
+
+_SHIPPED = [('pong', None), ('falling_balls', None), ('colliding_predators', None), ('predators_arena', 3),
+            ('cleanup', None), ('chase_avoid_torus', 0), ('pacman', 0), ('parallelogram_catch', 0),
+            ('first_person_predators_prey', None), ('red_green', 1), ('bounce_box_contact_prediction', True),
+            ('functional_maze', None), ('multi_tracking_with_feature', 3), ('match_to_sample', 4)]
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize('module,level', _SHIPPED)
+def test_every_shipped_example_config_compiles_unchanged(monkeypatch, module, level):
+    """Build container only: each of the 14 modules of /root/reference/moog_demos/example_configs, imported as
+    shipped on this repo's `moog` package, compiles to a valid program and steps on the oracle without an
+    error flag.  (`Physics.step` inside two initializers is served by the oracle here -- a TEST stand-in for
+    the CUDA call of moog_b200/host_physics.py, which has its own GPU test.)"""
+    import ctypes
+    import importlib
+    import sys
+    import moog_b200  # noqa: F401
+    from moog_b200 import capi, compiler, host_physics
+    from oracle.oracle import Oracle
+
+    def _oracle_step(physics, state):
+        from moog import action_spaces, tasks
+        cfg = dict(physics=physics, task=tasks.CompositeTask(), action_space=action_spaces.Grid(action_layers=()),
+                   observers={}, game_rules=())
+        prog = compiler.compile_config(cfg, [state])
+        orc = Oracle(prog, compiler.pack_states(prog, [state]))
+        orc.physics_step()
+        for l, name in enumerate(prog.layer_names):
+            for k, sp in enumerate(state[name]):
+                s = prog.layer_off[l] + k
+                sp.position = np.array(orc.dyn[0, 0:2, s])
+                sp.velocity = np.array(orc.dyn[0, 2:4, s])
+
+    monkeypatch.setattr(host_physics, 'step', _oracle_step)
+    import moog  # noqa: F401  (this repo's package, before the reference's directory joins sys.path)
+    monkeypatch.setattr(sys, 'path', sys.path + ['/root/reference'])
+    for name in [m for m in sys.modules if m.startswith('moog_demos')]:
+        monkeypatch.delitem(sys.modules, name)
+    shipped = importlib.import_module('moog_demos.example_configs.' + module)
+    np.random.seed(11)
+    cfg = shipped.get_config(level)
+    states = [cfg['state_initializer']() for _ in range(2)]
+    capacity = {'predators': 24, 'prey': 24} if module == 'first_person_predators_prey' else None
+    prog = compiler.compile_config(cfg, states, layer_capacity=capacity)
+    buf = (ctypes.c_uint8 * len(prog.blob)).from_buffer_copy(prog.blob)
+    assert capi.lib().moog_program_validate(ctypes.cast(buf, ctypes.c_void_p), len(prog.blob)) == 0
+    orc = Oracle(prog, compiler.pack_states(prog, states))
+    Oracle.set_seed(4)
+    orc.post_reset()
+    rng = np.random.RandomState(0)
+    ad = max(prog.action_dim, 1)
+    grid = any(kind == 'Grid' for _, kind, _, _ in prog.action_layout)
+    for t in range(12):
+        act = rng.randint(0, 5, size=(2, ad)).astype(np.float64) if grid else rng.uniform(0.2, 0.8, size=(2, ad))
+        noise = rng.uniform(size=(2, prog.K, prog.noise_dim)) if prog.noise_dim else None
+        Oracle.set_seed(100 + t)
+        orc.step(act, noise=noise)
+    assert (orc.envi[:, 2] == 0).all(), orc.envi[:, 2]
