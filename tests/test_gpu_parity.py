@@ -833,3 +833,66 @@ def test_device_reset_sampler_random_sprite_count():
         env.step(torch.zeros((N, 2), dtype=torch.float64))
     again = env.engine.state.download()['cnt'][:, 1]
     assert (again != first).mean() > 0.5, 'a new count is drawn every episode'
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('scene,n_envs', [('colliding_predators84', 16384), ('cleanup64', 8192), ('pacman64', 8192),
+                                          ('synthetic32', 131072)])
+def test_full_size_other_baseline_configs_match_oracle_on_a_sample(scene, n_envs):
+    """BASELINE configs[2..4] and the synthetic stress scene AT THEIR FULL SIZES (16 384 / 8 192 / 8 192 /
+    131 072 envs on one GPU -- the launch modes, residencies and record sizes `bench.py --scene` exercises): the
+    batch is stepped by the CUDA path with seeded per-env actions / noise; 40 of its envs are stepped by the
+    oracle from the same initial states.  Envs are independent (the size-independent property), so the sample
+    must agree: counts, dtype flags and overlap call statistics exactly, attributes and outlines within 1e-5
+    (bit for bit where no sprite rotates), frames identical at the end."""
+    import importlib
+    import moog_b200  # noqa: F401
+    from moog_b200 import compiler
+    from moog_b200.batched_env import Engine
+    from oracle.oracle import Oracle
+    cfg = importlib.import_module('moog_b200.configs.' + scene).get_config()
+    np.random.seed(31)
+    states = [cfg['state_initializer']() for _ in range(24)]
+    prog = compiler.compile_config(cfg, states)
+    pool = compiler.pack_states(prog, states)
+    N = n_envs
+    rng = np.random.RandomState(5)
+    idx = rng.randint(0, 24, size=N)
+    arrays = {k: np.ascontiguousarray(pool[k][idx]) for k in util.STATE_KEYS}
+    eng = Engine(prog, N, 'cuda:0')
+    eng.state.upload(arrays)
+    eng.post_reset()
+    sample = np.sort(rng.choice(N, size=40, replace=False))
+    orc = Oracle(prog, {k: arrays[k][sample] for k in util.STATE_KEYS})
+    orc.post_reset()
+    ad = max(prog.action_dim, 1)
+    grid = any(kind == 'Grid' for _, kind, _, _ in prog.action_layout)
+    worst = 0.0
+    for step in range(6):
+        act = rng.randint(0, 5, size=(N, ad)).astype(np.float64) if grid else rng.uniform(-1, 1, size=(N, ad))
+        noise = rng.uniform(size=(N, prog.K * prog.noise_dim)) if prog.noise_dim else None
+        rn = rng.uniform(size=(N, prog.rule_noise_dim)) if prog.rule_noise_dim else None
+        eng.env_step(act, noise=noise, rule_noise=rn, auto_reset=False, want_counters=True)
+        r_ref, st_ref = orc.step(act[sample],
+                                 noise=None if noise is None else noise[sample].reshape(len(sample), prog.K, prog.noise_dim),
+                                 rule_noise=None if rn is None else rn[sample])
+        assert np.array_equal(eng.step_type[torch_index(sample)].cpu().numpy(), st_ref), (scene, step)
+        c = eng.counters[torch_index(sample)].cpu().numpy()
+        assert np.array_equal(c[:, :2], orc.counters[:, :2]), (scene, step, 'overlap calls / true')
+        got = {k: getattr(eng.state, k)[torch_index(sample)].cpu().numpy() for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')}
+        assert np.array_equal(got['cnt'], orc.cnt), (scene, step)
+        for e in range(len(sample)):
+            live = util.live_mask(prog, orc.cnt[e])
+            assert np.array_equal(util.canonical_meta(got['meta'][e], live), util.canonical_meta(orc.meta[e], live)), (scene, step, e)
+            vlive = util.live_vertex_mask(prog, orc.cnt[e], orc.meta[e])
+            worst = max(worst, util.rel_err(got['dyn'][e][:, live], orc.dyn[e][:, live]),
+                        util.rel_err(got['stat'][e][:, live], orc.stat[e][:, live]),
+                        util.rel_err(got['vtx'][e][vlive], orc.vtx[e][vlive]))
+        assert worst <= util.RTOL, (scene, step, worst)
+    st = eng.state.download() if N <= 16384 else None
+    if st is not None:
+        assert (st['envi'][:, 2] == 0).all()
+    if prog.render is not None and worst == 0.0:
+        frames = eng.render()[torch_index(sample)].cpu().numpy()
+        assert np.array_equal(frames, orc.render())
+
