@@ -187,8 +187,9 @@ enum {
   MOOG_R_CREATE_SPRITES,         /* create_sprites.py:27-34: i0 layer the new sprites are appended to, i1 how many,
                                     i2,i3 ipool list of the LAYERS they must not overlap, i4 sampler table
                                     (as MOOG_Z_GENERATE), i5 dtype flags; MOOG_FL_DISJOINT / FAIL_GRACEFULLY,
-                                    p0 max_recursion_depth.  Drawn on the device (Philox keyed by seed, env,
-                                    episode, step) */
+                                    p0 max_recursion_depth; p2 > p1: the count is drawn per call from {p1 .. p2 - 1}
+                                    with the uniform of rule-noise column p3.  Drawn on the device (Philox keyed by
+                                    seed, env and a per-env serial) */
   MOOG_R_TREE,                   /* a user-defined rule class (functional_maze.py:18-67 `Booster`), its `step` traced along
                                     every path into a decision tree (node layout: MOOG_SC_TREE; kinds 3 = test
                                     `index < len(layer)`, 4 = run the stores of `expr` then go on; the leaf ends the
@@ -291,7 +292,8 @@ enum {
  * [6 ...] the nv centroid-centred vertices (x, y). */
 #define MOOG_Z_N_ATTRS 14
 #define MOOG_Z_SHAPE_ATTR 13
-enum { MOOG_ZK_CONST = 0, MOOG_ZK_UNIFORM32 = 1, MOOG_ZK_DISCRETE = 2 };
+enum { MOOG_ZK_CONST = 0, MOOG_ZK_UNIFORM32 = 1, MOOG_ZK_DISCRETE = 2,
+       MOOG_ZK_DISCRETE_P = 3 /* n candidates followed by their n cumulative probabilities (Discrete(probs=...)) */ };
 #define MOOG_ERR_PORTAL_ODD      64u /* portal.py:49-52 ValueError: odd number of portals */
 #define MOOG_ERR_BAD_INDEX      128u /* `state[layer][i]` with i >= len(state[layer]): the reference's IndexError */
 #define MOOG_ERR_RESET_REJECTED  32u /* sprite_generators.py:92-98 RecursionError (no room for a sprite) */

@@ -73,7 +73,7 @@ SC_ALL, SC_ANY, SC_COUNT, SC_CONTACT_COUNT, SC_CONTACT_ANY_COUNT, SC_CONST, \
     SC_BINARY, SC_NOT, SC_FIRST, SC_BERNOULLI, SC_TREE = 160, 161, 162, 163, 164, 165, 166, 167, 168, 169, 170
 Z_GENERATE = 192
 Z_N_ATTRS, Z_SHAPE_ATTR = 14, 13
-ZK_CONST, ZK_UNIFORM32, ZK_DISCRETE = 0, 1, 2
+ZK_CONST, ZK_UNIFORM32, ZK_DISCRETE, ZK_DISCRETE_P = 0, 1, 2, 3
 
 FL_SYMMETRIC = 1
 FL_UPDATE_ANGLE_VEL = 2
@@ -621,15 +621,22 @@ def _rule_specs(prog, rule, out, depth=0):
     elif k == 'CreateSprites':
         # create_sprites.py:27-34; the generator's recipe is sampled on the device (Philox), like a reset group
         gen = _Recipe(rule._generator)
+        count, lo, hi, col = gen.num_sprites, 0.0, 0.0, 0.0
         if callable(gen.num_sprites):
-            raise CompileError('CreateSprites with a random number of sprites per call is not on the accelerated path')
+            # num_sprites=lambda: np.random.randint(lo, hi): drawn per call from a rule-noise column of its own
+            drawn = lambdas.randint_range(gen.num_sprites)
+            if drawn is None:
+                raise CompileError('CreateSprites with a random number of sprites per call is only lowered when it is '
+                                   '`np.random.randint(lo, hi)`')
+            count, lo, hi, col = drawn[1] - 1, float(drawn[0]), float(drawn[1]), float(prog.rule_noise_dim)
+            prog.rule_noise_dim += 1
         lay = prog.layer_index(rule._layer)
         table, meta_flags, ext = _sampler_group(prog, gen.factor_dist, lay)
         t_start = _emit_sampler_table(prog, table, ext)
         ls, ln = prog.add_list(_as_list(rule._without_overlapping))
         out.append(dict(kind=R_CREATE_SPRITES, flags=FL_FAIL_GRACEFULLY if gen.fail_gracefully else 0,
-                        i=(lay, int(gen.num_sprites), ls, ln, t_start, meta_flags),
-                        p=(float(gen.max_recursion_depth),)))
+                        i=(lay, int(count), ls, ln, t_start, meta_flags),
+                        p=(float(gen.max_recursion_depth), lo, hi, col)))
     elif k == 'KeepNearCenter':
         layers = list(rule._layers_to_center)
         ls, ln = prog.add_list(layers)
@@ -739,7 +746,7 @@ def _generator_outline(gen):
     from moog import sprite as sprite_lib
     flat, _ = _lower_distribution(gen.factor_dist)
     leaf = flat.get('shape', ('discrete', [_sprite_defaults()['shape']]))
-    if leaf[0] != 'discrete':
+    if leaf[0] not in ('discrete', 'discrete_p'):
         raise CompileError('the shape must be a plain Discrete / constant factor on the device sampler')
     return max(len(sprite_lib.Sprite(x=0., y=0., shape=shape).vertices) for shape in leaf[1])
 
@@ -932,7 +939,13 @@ def _flatten_distribution(dist):
         return {dist.key: ('uniform', float(dist.minval), float(dist.maxval))}
     if k == 'Discrete':
         if getattr(dist, 'probs', None) is not None:
-            raise CompileError('Discrete with explicit probabilities is not on the device sampler yet')
+            # distributions.py:127-129: rng.choice(n, p=probs) -- the first candidate whose cumulative
+            # probability exceeds the uniform
+            probs = np.asarray(dist.probs, dtype=np.float64)
+            if len(probs) != len(dist.candidates) or (probs < 0).any() or not probs.sum() > 0:
+                raise CompileError('Discrete: one non-negative probability per candidate expected')
+            cum = np.cumsum(probs)
+            return {dist.key: ('discrete_p', list(dist.candidates), [float(v) for v in cum / cum[-1]])}
         return {dist.key: ('discrete', list(dist.candidates))}
     raise CompileError(
         'factor distribution {} cannot be sampled on the device (supported: Product of '
@@ -1060,8 +1073,10 @@ def _sampler_group(prog, factor_dist, lay):
     sampled32 = set()
     for key in _ATTR_KEYS + ('shape',):
         kind, payload = 'discrete', [defaults[key]]
+        cum = None
         if key in flat:
             kind, payload = flat[key][0], list(flat[key][1:]) if flat[key][0] == 'uniform' else flat[key][1]
+            cum = flat[key][2] if kind == 'discrete_p' else None
         if kind == 'uniform':
             table.append((ZK_UNIFORM32, payload))
             sampled32.add(key)
@@ -1074,7 +1089,10 @@ def _sampler_group(prog, factor_dist, lay):
                             'a shape candidate has {} vertices, more than the sample states showed for layer '
                             '{!r} ({}); pass more sample states'.format(
                                 int(prog.z_shape_recs[sid][0]), prog.layer_names[lay], prog.layer_vcap[lay]))
-            table.append((ZK_CONST if len(values) == 1 else ZK_DISCRETE, values))
+            if cum is not None and len(values) > 1:
+                table.append((ZK_DISCRETE_P, values + cum))
+            else:
+                table.append((ZK_CONST if len(values) == 1 else ZK_DISCRETE, values))
     # factors drawn by the extensions: float32 iff every alternative draws them from a Continuous
     ext_specs = []
     for comp in extensions:
@@ -1105,6 +1123,8 @@ def _sampler_group(prog, factor_dist, lay):
             for key_, leaf in leaves_.items():
                 values = list(leaf[1:]) if leaf[0] == 'uniform' else [float(v) for v in leaf[1]]
                 kind_ = ZK_UNIFORM32 if leaf[0] == 'uniform' else (ZK_CONST if len(values) == 1 else ZK_DISCRETE)
+                if leaf[0] == 'discrete_p' and len(values) > 1:
+                    kind_, values = ZK_DISCRETE_P, values + list(leaf[2])
                 out_.append((_ATTR_KEYS.index(key_), kind_, values))
             return out_
         if comp[0] == 'mixture':
@@ -1123,14 +1143,17 @@ def _sampler_group(prog, factor_dist, lay):
 def _emit_sampler_table(prog, table, ext):
     """Writes a group's factor table and extension program into the pools; returns the ipool start."""
     tab = []
+    def count(kind, values):        # candidates of a leaf (a weighted one carries its cumulative probabilities too)
+        return len(values) // 2 if kind == ZK_DISCRETE_P else len(values)
+
     for kind, values in table:
-        tab += [kind, len(prog.dpool), len(values)]
+        tab += [kind, len(prog.dpool), count(kind, values)]
         prog.dpool.extend(float(v) for v in values)
 
     def put_leaves(leaves_):
         out_ = [len(leaves_)]
         for attr, kind, values in leaves_:
-            out_ += [attr, kind, len(prog.dpool), len(values)]
+            out_ += [attr, kind, len(prog.dpool), count(kind, values)]
             prog.dpool.extend(float(v) for v in values)
         return out_
     # extension program: [n_ext, then per component: 1, n_alt, probs dpool index, alternatives... |

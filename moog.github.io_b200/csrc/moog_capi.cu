@@ -152,7 +152,8 @@ int moog_program_validate(const void *blob, size_t nbytes) {
     if (t < 0 || (long long)t + 3 * MOOG_Z_N_ATTRS + 1 > NI) return false;
     for (int a = 0; a < MOOG_Z_N_ATTRS; ++a) {
       const int kind = pv.ipool[t + 3 * a], idx = pv.ipool[t + 3 * a + 1], n = pv.ipool[t + 3 * a + 2];
-      if (kind < MOOG_ZK_CONST || kind > MOOG_ZK_DISCRETE || idx < 0 || n < 1 || (long long)idx + (kind == MOOG_ZK_UNIFORM32 ? 2 : n) > ND)
+      if (kind < MOOG_ZK_CONST || kind > MOOG_ZK_DISCRETE_P || idx < 0 || n < 1 ||
+          (long long)idx + (kind == MOOG_ZK_UNIFORM32 ? 2 : (kind == MOOG_ZK_DISCRETE_P ? 2 * n : n)) > ND)
         return false;
     }
     return pv.ipool[t + 3 * MOOG_Z_N_ATTRS] >= 0;
@@ -198,7 +199,8 @@ int moog_program_validate(const void *blob, size_t nbytes) {
       case MOOG_R_TIMED_BEGIN: ok = op.i[1] >= 0 && (long long)o + 1 + op.i[1] <= NO && envf_ok(op.i[2], 2); break;
       case MOOG_R_KEEP_NEAR_CENTER: ok = layer_ok(op.i[0]) && list_ok(op.i[1], op.i[2], L); break;
       case MOOG_R_CREATE_SPRITES:
-        ok = layer_ok(op.i[0]) && op.i[1] >= 0 && list_ok(op.i[2], op.i[3], L) && table_ok(op.i[4]);
+        ok = layer_ok(op.i[0]) && op.i[1] >= 0 && list_ok(op.i[2], op.i[3], L) && table_ok(op.i[4]) &&
+             (!(op.p[2] > op.p[1]) || (op.p[3] >= 0 && op.p[3] < hdr[MOOG_H_RULE_NOISE_DIM]));
         break;
       case MOOG_T_CONTACT_REWARD:
         ok = list_ok(op.i[0], op.i[1], L) && list_ok(op.i[2], op.i[3], L) && expr_ok(op.i[4]) && envf_ok(op.i[5], 1) &&

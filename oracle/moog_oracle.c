@@ -1632,6 +1632,11 @@ static double rule_noise_at(env_t *e, int col) {
 static double sample_leaf(const double *dpool, int kind, int idx, int n, double u) {
   if (kind == MOOG_ZK_CONST) return dpool[idx];
   if (kind == MOOG_ZK_UNIFORM32) return (double)(float)(dpool[idx] + (dpool[idx + 1] - dpool[idx]) * u);
+  if (kind == MOOG_ZK_DISCRETE_P) {  /* rng.choice(n, p=probs): the first candidate whose cumulative probability exceeds u */
+    int k = 0;
+    while (k < n - 1 && !(u < dpool[idx + n + k])) ++k;
+    return dpool[idx + k];
+  }
   const int pick = (int)(u * n);
   return dpool[idx + (pick < n ? pick : n - 1)];
 }
@@ -2070,6 +2075,11 @@ static int rule_step(env_t *e, int r, const double *rule_noise) {
     case MOOG_R_CREATE_SPRITES: { /* create_sprites.py:27-34 */
       const int layer = op->i[0], have = e->cnt[layer], cap = LOFF(e, layer + 1) - LOFF(e, layer);
       int count = op->i[1];
+      if (op->p[2] > op->p[1]) { /* num_sprites = lambda: np.random.randint(p1, p2): drawn per call */
+        const int lo = (int)op->p[1], hi = (int)op->p[2];
+        const int c = lo + (int)(rule_noise_at(e, (int)op->p[3]) * (double)(hi - lo));
+        count = c >= hi ? hi - 1 : (c < 0 ? 0 : c);
+      }
       const int serial = e->envi[MOOG_EI_CREATED]++;
       if (have + count > cap) { /* the reference's lists grow without bound; a layer of the record does not */
         e->envi[MOOG_EI_ERR] |= MOOG_ERR_LAYER_OVERFLOW;

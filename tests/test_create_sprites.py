@@ -402,3 +402,83 @@ def test_oracle_replays_reference_state_initializer():
     finally:
         Oracle.force_factors(None)
         Oracle.set_sample_resets(False)
+
+
+def _weighted_config():
+    """CreateSprites with a random number of sprites per call and a Discrete factor with explicit
+    probabilities (distributions.py:121-157, sprite_generators.py:75-77)."""
+    import collections
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, game_rules, physics as physics_lib, sprite, tasks
+    from moog.state_initialization import distributions as distribs
+    from moog.state_initialization import sprite_generators
+
+    def state_initializer():
+        return collections.OrderedDict([('agent', [sprite.Sprite(x=0.5, y=0.5, shape='square', scale=0.05)]), ('motes', [])])
+
+    factors = distribs.Product(
+        [distribs.Continuous('x', 0., 1.), distribs.Continuous('y', 0., 1.),
+         distribs.Discrete('c0', [0.1, 0.5, 0.9], probs=[0.6, 0.3, 0.1]),
+         distribs.Discrete('shape', ['triangle', 'square'], probs=[0.25, 0.75])],
+        scale=0.02, c1=1., c2=1.)
+    gen = sprite_generators.generate_sprites(factors, num_sprites=lambda: np.random.randint(1, 4))
+    rules = (game_rules.CreateSprites('motes', gen),
+             game_rules.VanishByFilter('motes', lambda s: s.x >= 0.))        # every mote lives for one pass
+    return dict(state_initializer=state_initializer, physics=physics_lib.Physics(updates_per_env_step=1),
+                task=tasks.CompositeTask(timeout_steps=1000), action_space=action_spaces.Grid(action_layers='agent'),
+                observers={}, game_rules=rules)
+
+
+def test_oracle_weighted_discrete_and_random_count():
+    from moog_b200 import compiler
+    from oracle.oracle import Oracle
+    cfg = _weighted_config()
+    states = [cfg['state_initializer']()]
+    prog = compiler.compile_config(dict(cfg, game_rules=cfg['game_rules'][:1]), states, layer_capacity={'motes': 60})
+    assert prog.rule_noise_dim == 1
+    N = 64
+    arrays = util.tile_state({k: compiler.pack_states(prog, states)[k] for k in util.STATE_KEYS}, N)
+    orc = Oracle(prog, arrays)
+    Oracle.set_seed(3)
+    orc.post_reset()
+    for t in range(14):
+        Oracle.set_seed(20 + t)
+        orc.step(np.full((N, 1), 4.0))
+    lo = prog.layer_off[1]
+    made = orc.cnt[:, 1]
+    calls = 15 * N
+    assert abs(made.sum() / calls - 2.0) < 5 * np.sqrt(2. / 3 / calls), made.sum() / calls        # uniform on {1, 2, 3}
+    c0 = np.concatenate([orc.stat[e, 6, lo:lo + made[e]] for e in range(N)])
+    shape = np.concatenate([orc.meta[e, 0, lo:lo + made[e]] for e in range(N)])
+    n = len(c0)
+    for value, p in ((0.1, 0.6), (0.5, 0.3), (0.9, 0.1)):
+        assert abs((c0 == value).mean() - p) < 5 * np.sqrt(p * (1 - p) / n), (value, (c0 == value).mean())
+    assert abs((shape == 0).mean() - 0.25) < 5 * np.sqrt(0.1875 / n)
+    assert (orc.envi[:, 2] == 0).all()
+
+
+@pytest.mark.gpu
+def test_cuda_weighted_discrete_and_random_count_match_oracle():
+    from moog_b200 import compiler
+    from moog_b200.batched_env import Engine
+    from oracle.oracle import Oracle
+    cfg = _weighted_config()
+    states = [cfg['state_initializer']()]
+    prog = compiler.compile_config(cfg, states, layer_capacity={'motes': 8})
+    N = 512
+    arrays = util.tile_state({k: compiler.pack_states(prog, states)[k] for k in util.STATE_KEYS}, N)
+    orc, eng = Oracle(prog, arrays), Engine(prog, N, 'cuda:0', seed=13)
+    eng.state.upload(arrays)
+    Oracle.set_seed(13)
+    orc.post_reset()
+    eng.post_reset()
+    for t in range(12):
+        Oracle.set_seed(eng.call_seed())
+        orc.step(np.full((N, 1), 4.0))
+        eng.env_step(np.full((N, 1), 4.0), auto_reset=False)
+        dev = eng.state.download()
+        assert np.array_equal(dev['cnt'], orc.cnt) and np.array_equal(dev['envi'][:, :6], orc.envi[:, :6]), t
+        # the motes were written and popped in the same pass: the slots still hold what was drawn
+        lo = prog.layer_off[1]
+        assert np.array_equal(dev['stat'][:, :, lo:lo + 3], orc.stat[:, :, lo:lo + 3]), t
+        assert np.array_equal(dev['dyn'][:, :, lo:lo + 3], orc.dyn[:, :, lo:lo + 3]), t
