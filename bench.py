@@ -137,7 +137,9 @@ def _json_default(o):
 def _ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
     committed `ncu --set full` summary of this round (profiles/), or None."""
-    path = os.path.join(ROOT, 'profiles', 'r01_{}_ncu.json'.format(kernel))
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_{}_ncu.json'.format(kernel))))
+    path = found[-1] if found else ''          # the latest round's capture
     try:
         with open(path) as f:
             d = json.load(f)
