@@ -726,3 +726,116 @@ def test_every_shipped_example_config_compiles_unchanged(monkeypatch, module, le
         Oracle.set_seed(100 + t)
         orc.step(act, noise=noise)
     assert (orc.envi[:, 2] == 0).all(), orc.envi[:, 2]
+
+
+def _small_configs():
+    """The hand-made configs of the CPU tests above, as (name, config, states, action width)."""
+    import moog_b200  # noqa: F401
+    from moog import action_spaces, game_rules as gr, physics as physics_lib, sprite, tasks
+    out = []
+    # metadata reward with branches
+    metadata = [{'goal': g, 'when': w} for g in (0, 1) for w in (5, 31, 60)]
+    cfg, states = _config(_answer, metadata)
+    out.append(('answer', cfg, states))
+    # decision-tree Reset task
+    def verdict_state(x, goal):
+        boxes = [sprite.Sprite(x=0.3, y=0.5, shape='square', scale=0.1), sprite.Sprite(x=0.7, y=0.5, shape='square', scale=0.1)]
+        agent = sprite.Sprite(x=x, y=0.5, shape='circle', scale=0.08, metadata={'goal': goal})
+        return collections.OrderedDict([('boxes', boxes), ('agent', [agent])])
+    states = [verdict_state(x, goal) for x in (0.3, 0.5, 0.7) for goal in (False, True)]
+    cfg = dict(state_initializer=lambda: verdict_state(0.5, True), physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(tasks.Reset(condition=lambda state: _verdict(state) != 0, reward_fn=_verdict,
+                                                    steps_after_condition=2), timeout_steps=100),
+               action_space=action_spaces.Grid(scaling_factor=0.01, action_layers='agent'), observers={}, game_rules=())
+    out.append(('verdict', cfg, states))
+    # traced rule class with a loop over a layer
+    def tagger_state(n_items):
+        agent = sprite.Sprite(x=0.5, y=0.5, shape='square', scale=0.2, mass=1.)
+        xs = [0.45, 0.9, 0.55]
+        items = [sprite.Sprite(x=xs[k], y=0.5, shape='circle', scale=0.05, c0=float(k)) for k in range(n_items)]
+        return collections.OrderedDict([('items', items), ('agent', [agent])])
+    states = [tagger_state(n) for n in (3, 0, 1, 2, 3)]
+    cfg = dict(state_initializer=lambda: tagger_state(3), physics=physics_lib.Physics(updates_per_env_step=1),
+               task=tasks.CompositeTask(timeout_steps=100), action_space=action_spaces.Grid(action_layers=()),
+               observers={}, game_rules=(_Tagger(threshold=3),))
+    out.append(('tagger', cfg, states))
+    # traced rule with random draws and vector algebra
+    def kick_state():
+        movers = [sprite.Sprite(x=0.2 + 0.25 * k, y=0.3 + 0.1 * k, shape='circle', scale=0.05) for k in range(3)]
+        twins = [sprite.Sprite(x=m.x, y=m.y, shape='square', scale=0.03) for m in movers]
+        return collections.OrderedDict([('movers', movers), ('twins', twins)])
+    cfg = dict(state_initializer=kick_state, physics=physics_lib.Physics(updates_per_env_step=2),
+               task=tasks.CompositeTask(timeout_steps=10), action_space=action_spaces.Grid(action_layers=()),
+               observers={}, game_rules=(_Kick((0.1, 0.3)),))
+    out.append(('kick', cfg, [kick_state() for _ in range(3)]))
+    # phases, fixation, meta_state, modify-meta-state rules
+    def bump(s):
+        s.c0 = s.c0 + 1.
+
+    def count_up(meta_state):
+        meta_state['count'] += 2
+        if meta_state['count'] > 5:
+            meta_state['level'] = meta_state['level'] + 1
+            meta_state['count'] = 0
+    phases = gr.PhaseSequence(
+        gr.Phase(continual_rules=gr.Fixation('agent', 'cross', 0.1, 'held'),
+                 end_condition=lambda state, meta_state: meta_state['held'] >= 3, name='fixate'),
+        gr.Phase(one_time_rules=gr.UpdateMetaStateValue('level', 10), continual_rules=gr.ModifySprites('agent', bump),
+                 duration=lambda: np.random.randint(2, 6), name='count'),
+        gr.Phase(name='done'),
+        meta_state_phase_name_key='phase')
+    task = tasks.CompositeTask(tasks.Reset(condition=lambda state, meta_state: meta_state['phase'] == 'done',
+                                           reward_fn=lambda _: 7., steps_after_condition=1), timeout_steps=100)
+    cfg, states = _phase_config((phases, gr.ModifyMetaState(count_up)),
+                                meta=lambda: {'phase': '', 'held': 0, 'count': 0, 'level': 0}, task=task)
+    out.append(('phases', cfg, states * 3))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('which', ['answer', 'verdict', 'tagger', 'kick', 'phases'])
+def test_cuda_matches_oracle_on_the_small_configs(which):
+    """The hand-made configs of this file (metadata rewards, decision trees, traced rule classes with loops /
+    random draws / vector algebra, PhaseSequence + Fixation + meta_state + ModifyMetaState) on the CUDA path
+    against the oracle: same Philox stream, auto-resets from the pool, every array of the record -- envf with
+    the rules' own variables, meta_state entries and metadata columns included -- identical after every step."""
+    from moog_b200 import compiler
+    from moog_b200.batched_env import Engine
+    from oracle.oracle import Oracle
+    name, cfg, states = [c for c in _small_configs() if c[0] == which][0]
+    prog = compiler.compile_config(cfg, states)
+    pool_arrays = {k: v for k, v in compiler.pack_states(prog, states).items() if k in util.STATE_KEYS}
+    P = len(states)
+    N = 8 * P
+    rng = np.random.RandomState(3)
+    arrays = {k: np.ascontiguousarray(pool_arrays[k][np.arange(N) % P]) for k in util.STATE_KEYS}
+    orc, eng = Oracle(prog, arrays), Engine(prog, N, 'cuda:0', seed=17)
+    eng.state.upload(arrays)
+    eng.set_pool(pool_arrays)
+    pool = Oracle(prog, pool_arrays)
+    Oracle.set_seed(17)
+    orc.post_reset()
+    eng.post_reset()
+    ad = max(prog.action_dim, 1)
+    grid = any(kind == 'Grid' for _, kind, _, _ in prog.action_layout)
+    for t in range(25):
+        act = rng.randint(0, 5, size=(N, ad)).astype(np.float64) if grid else rng.uniform(0.3, 0.7, size=(N, ad))
+        ri = rng.randint(0, P, size=N)
+        Oracle.set_seed(eng.call_seed())
+        r_ref, st_ref, _ = orc.step_auto(act, pool, ri)
+        eng.env_step(act, auto_reset=True, reset_index=ri, want_counters=True)
+        dev = eng.state.download()
+        assert np.array_equal(eng.step_type.cpu().numpy(), st_ref), (name, t)
+        assert _same_f(eng.reward.cpu().numpy(), r_ref.astype(np.float32)), (name, t, 'reward')
+        assert np.array_equal(eng.counters.cpu().numpy()[:, :2], orc.counters[:, :2]), (name, t, 'overlap calls')
+        assert np.array_equal(dev['cnt'], orc.cnt) and np.array_equal(dev['envi'][:, :6], orc.envi[:, :6]), (name, t)
+        assert np.array_equal(dev['envf'], orc.envf, equal_nan=True), (name, t, 'envf')
+        for e in range(N):
+            util.assert_live_equal(prog, {k: dev[k][e] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')},
+                                   {k: getattr(orc, k)[e] for k in ('dyn', 'stat', 'meta', 'vtx', 'cnt')},
+                                   '{} step {} env {}'.format(name, t, e))
+    assert (orc.envi[:, 2] == 0).all()
+
+
+def _same_f(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
